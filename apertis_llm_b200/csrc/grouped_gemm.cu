@@ -1,0 +1,431 @@
+// Grouped expert GEMM on 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
+// staged by TMA into 128B-swizzled shared memory, warp-specialised and persistent.
+// Replaces the per-(slot, expert) nn.Linear calls of core.py:596 (experts[e] = LN, Linear, act, Dropout,
+// Linear; core.py:434-442) and their autograd (dgrad / wgrad).
+//
+//   MODE_NT  C[r,n] = epi(sum_k A[r,k] * W[e,n,k])      A [rows,K] K-major,   W [E*N, K] K-major   (forward)
+//   MODE_NN  C[r,n] = epi(sum_k A[r,k] * W[e,k,n])      A [rows,K] K-major,   W [E*K, N] N-major   (dgrad)
+//   MODE_TN  Cw[e,m,n] = sum_{r in seg e} A[r,m]*B[r,n] A [rows,M] M-major,   B [rows,N] N-major   (wgrad)
+//
+// Tile 128 x BN x 64 (BN <= 256 chosen per shape on the host and carried in the TMA maps / the
+// instruction descriptor), 4-stage TMA->MMA ring, 2 accumulator stages in TMEM (2 x 256 columns) so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM
+// alloc), 2..9 = epilogue (two warps per TMEM lane quarter, splitting the column chunks).
+// Row tiles (128 permuted rows) belong to one expert; the number of valid row tiles is read from device
+// memory (n_rows[0]) so no host synchronisation is needed after the routing plan.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, NSTAGE = 4, NACC = 2;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES_MAX = 256 * BK * 2;     // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int ATOM_BYTES = 64 * BK * 2;       // one 64(MN) x 64(K) swizzle-128B MN-major atom = 8 KB
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARP0 = 2, EPI_WARPS = 8;
+constexpr int MODE_NT = 0, MODE_NN = 1, MODE_TN = 2;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + 256;
+
+struct GemmParams {
+    int N, K, E, M;          // M only for MODE_TN (rows of each expert's output)
+    int bn;                  // N tile
+    int num_n_tiles, num_m_tiles;
+    int epi, act, c_f32;
+    const int32_t* tile_expert;
+    const int32_t* n_rows;
+    const int32_t* seg_off;
+    const float* bias;
+    const void* aux;
+    void* c;
+    void* c2;
+    float* cw;
+};
+
+// ---- math for the epilogues -------------------------------------------------------------------
+// erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26); enough for the fp32 tolerance and much cheaper than erff
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = ab_rcp(fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float y = 1.0f - p * t * ab_ex2(-ax * ax * AB_LOG2E);
+    return copysignf(y, x);
+}
+__device__ __forceinline__ float act_fwd(float x, int act) {
+    if (act == AB_ACT_GELU) return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f));
+    if (act == AB_ACT_RELU) return fmaxf(x, 0.f);
+    return x * ab_sigmoid(x);
+}
+__device__ __forceinline__ float act_bwd(float x, int act) {
+    if (act == AB_ACT_GELU) {
+        const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
+        const float pdf = 0.3989422804014327f * ab_ex2(-0.5f * x * x * AB_LOG2E);
+        return fmaf(x, pdf, cdf);
+    }
+    if (act == AB_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+    const float s = ab_sigmoid(x);
+    return s * fmaf(x, 1.f - s, 1.f);
+}
+
+// ---- descriptors ------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // version
+    d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: bf16 x bf16 -> f32, M = 128
+__host__ __device__ inline uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // D format f32
+    d |= 1u << 7;                    // A format bf16
+    d |= 1u << 10;                   // B format bf16
+    d |= (uint32_t)a_mn_major << 15;
+    d |= (uint32_t)b_mn_major << 16;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(BM >> 4) << 24;
+    return d;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                      const __grid_constant__ CUtensorMap tm_b,
+                                                                      const GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = ab_smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);      // swizzle-128B atoms need 1024 B alignment
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGE * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
+    uint64_t* tfull = bars + 2 * NSTAGE;
+    uint64_t* tempty = bars + 2 * NSTAGE + NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ab_prefetch_tmap(&tm_a);
+        ab_prefetch_tmap(&tm_b);
+        for (int i = 0; i < NSTAGE; ++i) { ab_mbar_init(&full[i], 1); ab_mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NACC; ++i) { ab_mbar_init(&tfull[i], 1); ab_mbar_init(&tempty[i], EPI_WARPS * 32); }
+        ab_fence_mbar_init();
+    }
+    if (warp == 1) {
+        ab_tmem_alloc(tmem_slot, 512);
+        ab_tmem_relinquish();
+    }
+    ab_tc_fence_before();
+    __syncthreads();
+    ab_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- tile schedule (identical in every role)
+    int total_tiles;
+    if (MODE == MODE_TN) total_tiles = p.E * p.num_m_tiles * p.num_n_tiles;
+    else total_tiles = (p.n_rows[0] / BM) * p.num_n_tiles;
+    const int bn = p.bn;
+    const uint32_t b_bytes = MODE == MODE_NT ? (uint32_t)bn * BK * 2 : (uint32_t)(bn / 64) * ATOM_BYTES;
+    const uint32_t stage_tx = A_BYTES + b_bytes;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m_tile, n_tile, e, k_begin, nk;
+                if (MODE == MODE_TN) {
+                    e = tile / (p.num_m_tiles * p.num_n_tiles);
+                    const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
+                    m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
+                    k_begin = p.seg_off[e];
+                    nk = (p.seg_off[e + 1] - k_begin) / BK;
+                } else {
+                    m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
+                    e = p.tile_expert[m_tile];
+                    k_begin = 0;
+                    nk = (p.K + BK - 1) / BK;
+                }
+                for (int kb = 0; kb < nk; ++kb) {
+                    ab_mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + (size_t)stage * STAGE_BYTES;
+                    unsigned char* sb = sa + A_BYTES;
+                    ab_mbar_expect_tx(&full[stage], stage_tx);
+                    if (MODE == MODE_TN) {
+                        const int r0 = k_begin + kb * BK;
+                        ab_tma_load_2d(sa, &tm_a, &full[stage], m_tile * BM, r0);
+                        ab_tma_load_2d(sa + ATOM_BYTES, &tm_a, &full[stage], m_tile * BM + 64, r0);
+                        for (int j = 0; j < bn / 64; ++j)
+                            ab_tma_load_2d(sb + j * ATOM_BYTES, &tm_b, &full[stage], n_tile * bn + j * 64, r0);
+                    } else {
+                        ab_tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_tile * BM);
+                        if (MODE == MODE_NT) {
+                            ab_tma_load_2d(sb, &tm_b, &full[stage], kb * BK, e * p.N + n_tile * bn);
+                        } else {
+                            for (int j = 0; j < bn / 64; ++j)
+                                ab_tma_load_2d(sb + j * ATOM_BYTES, &tm_b, &full[stage], n_tile * bn + j * 64, e * p.K + kb * BK);
+                        }
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(bn, MODE == MODE_TN ? 1 : 0, MODE == MODE_NT ? 0 : 1);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int nk;
+                if (MODE == MODE_TN) {
+                    const int e = tile / (p.num_m_tiles * p.num_n_tiles);
+                    nk = (p.seg_off[e + 1] - p.seg_off[e]) / BK;
+                    if (nk == 0) continue;          // empty expert: the epilogue writes zeros without an accumulator
+                } else {
+                    nk = (p.K + BK - 1) / BK;
+                }
+                ab_mbar_wait(&tempty[acc], acc_phase ^ 1);
+                ab_tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                for (int kb = 0; kb < nk; ++kb) {
+                    ab_mbar_wait(&full[stage], phase);
+                    ab_tc_fence_after();
+                    const uint32_t sa = ab_smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+                    // K-major operand: 8-row groups 1024 B apart; MN-major: 64-wide atoms 8 KB apart, 8-k groups 1024 B apart
+                    const uint64_t da = MODE == MODE_TN ? make_smem_desc(sa, ATOM_BYTES, 1024) : make_smem_desc(sa, 0, 1024);
+                    const uint64_t db = MODE == MODE_NT ? make_smem_desc(sb, 0, 1024) : make_smem_desc(sb, ATOM_BYTES, 1024);
+                    const uint32_t a_step = MODE == MODE_TN ? (16 * 128) >> 4 : 32 >> 4;     // advance 16 k per MMA
+                    const uint32_t b_step = MODE == MODE_NT ? 32 >> 4 : (16 * 128) >> 4;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        ab_umma_f16(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    ab_umma_commit(&empty[stage]);              // smem slot free once these MMAs retire
+                    if (kb == nk - 1) ab_umma_commit(&tfull[acc]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int ew = warp - EPI_WARP0;
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = ew >> 2;                // which half of the column chunks
+        const int row_in_tile = quarter * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int m_tile, n_tile, e, nk;
+            if (MODE == MODE_TN) {
+                e = tile / (p.num_m_tiles * p.num_n_tiles);
+                const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
+                m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
+                nk = (p.seg_off[e + 1] - p.seg_off[e]) / BK;
+            } else {
+                m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
+                e = p.tile_expert[m_tile];
+                nk = 1;
+            }
+            const bool have_acc = nk > 0;
+            if (have_acc) {
+                ab_mbar_wait(&tfull[acc], acc_phase);
+                ab_tc_fence_after();
+            }
+            const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+            const int n0 = n_tile * bn;
+            const int nchunks = bn / 16;          // 16-column chunks, split between the two halves
+            for (int ch = half; ch < nchunks; ch += 2) {
+                uint32_t v[16];
+                if (have_acc) {
+                    ab_tmem_ld16(t_row + (uint32_t)(ch * 16), v);
+                    ab_tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0u;
+                }
+                const int ncol = n0 + ch * 16;
+                if (ncol >= p.N) continue;
+                if (MODE == MODE_TN) {
+                    const int m = m_tile * BM + row_in_tile;
+                    if (m < p.M) {
+                        float* dst = p.cw + ((size_t)e * p.M + m) * p.N + ncol;
+                        if (ncol + 16 <= p.N) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<uint4*>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
+                            for (int i = 0; i < 16 && ncol + i < p.N; ++i) dst[i] = __uint_as_float(v[i]);
+                        }
+                    }
+                } else {
+                    const size_t row = (size_t)m_tile * BM + row_in_tile;
+                    float f[16], f2[16];
+                    const int nvalid = min(16, p.N - ncol);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.epi == AB_EPI_BIAS || p.epi == AB_EPI_BIAS_ACT) {
+                        const float* bp = p.bias + (size_t)e * p.N + ncol;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
+                    }
+                    if (p.epi == AB_EPI_BIAS_ACT) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (!p.c_f32) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));   // Linear output is rounded first
+                            f2[i] = f[i];
+                            f[i] = act_fwd(f[i], p.act);
+                        }
+                    } else if (p.epi == AB_EPI_DACT) {
+                        float pre[16];
+                        if (p.c_f32) {
+                            const float* ap = reinterpret_cast<const float*>(p.aux) + row * p.N + ncol;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pre[i] = (i < nvalid) ? __ldg(ap + i) : 0.f;
+                        } else {
+                            const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * p.N + ncol;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pre[i] = (i < nvalid) ? __bfloat162float(ap[i]) : 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] *= act_bwd(pre[i], p.act);
+                    }
+                    if (p.c_f32) {
+                        float* dst = reinterpret_cast<float*>(p.c) + row * p.N + ncol;
+                        float* dst2 = reinterpret_cast<float*>(p.c2) + row * p.N + ncol;
+                        if (nvalid == 16) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                            if (p.epi == AB_EPI_BIAS_ACT) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst2 + i) = make_float4(f2[i], f2[i + 1], f2[i + 2], f2[i + 3]);
+                            }
+                        } else {
+                            for (int i = 0; i < nvalid; ++i) { dst[i] = f[i]; if (p.epi == AB_EPI_BIAS_ACT) dst2[i] = f2[i]; }
+                        }
+                    } else {
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.N + ncol;
+                        __nv_bfloat16* dst2 = reinterpret_cast<__nv_bfloat16*>(p.c2) + row * p.N + ncol;
+                        if (nvalid == 16) {
+                            *reinterpret_cast<uint4*>(dst) = ab_vec16<__nv_bfloat16>::pack(f);
+                            *reinterpret_cast<uint4*>(dst + 8) = ab_vec16<__nv_bfloat16>::pack(f + 8);
+                            if (p.epi == AB_EPI_BIAS_ACT) {
+                                *reinterpret_cast<uint4*>(dst2) = ab_vec16<__nv_bfloat16>::pack(f2);
+                                *reinterpret_cast<uint4*>(dst2 + 8) = ab_vec16<__nv_bfloat16>::pack(f2 + 8);
+                            }
+                        } else {
+                            for (int i = 0; i < nvalid; ++i) {
+                                dst[i] = __float2bfloat16_rn(f[i]);
+                                if (p.epi == AB_EPI_BIAS_ACT) dst2[i] = __float2bfloat16_rn(f2[i]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (have_acc) {
+                ab_tc_fence_before();
+                ab_mbar_arrive(&tempty[acc]);
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+    ab_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ab_tmem_dealloc(tmem_base, 512);
+}
+
+int pick_bn(int N, bool mn_major_b) {
+    const int step = mn_major_b ? 64 : 16;
+    int best = step, best_cost = 1 << 30;
+    for (int bn = step; bn <= 256; bn += step) {
+        const int cost = (int)ab_ceil_div(N, bn) * (bn + 48);
+        if (cost <= best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+int make_map2(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+    AB_REQUIRE(((uintptr_t)base % 16) == 0 && (inner * 2) % 16 == 0,
+               "grouped_gemm: operand base must be 16-byte aligned and the contiguous dimension (%llu) a multiple of 8",
+               (unsigned long long)inner);
+    uint64_t dims[2] = {inner, outer};
+    uint64_t strides[1] = {inner * 2};
+    uint32_t box[2] = {box_inner, box_outer};
+    return ab_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int64_t max_tiles, cudaStream_t stream) {
+    auto k = grouped_gemm_kernel<MODE>;
+    AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int64_t grid = ab_num_sms();
+    if (max_tiles < grid) grid = max_tiles;
+    if (grid < 1) grid = 1;
+    k<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+int gemm_rows(int mode, const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
+              const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E, int epi, int act,
+              int c_dtype, cudaStream_t stream) {
+    AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm: max_rows must be a positive multiple of %d", BM);
+    AB_REQUIRE(N > 0 && K > 0 && E > 0 && N % 8 == 0 && K % 8 == 0, "grouped_gemm: N (%d) and K (%d) must be multiples of 8", N, K);
+    AB_REQUIRE(c_dtype == AB_F32 || c_dtype == AB_BF16, "grouped_gemm: bad output dtype");
+    AB_REQUIRE(epi >= AB_EPI_NONE && epi <= AB_EPI_DACT, "grouped_gemm: bad epilogue %d", epi);
+    AB_REQUIRE((epi != AB_EPI_BIAS && epi != AB_EPI_BIAS_ACT) || bias, "grouped_gemm: bias epilogue without bias");
+    AB_REQUIRE(epi != AB_EPI_BIAS_ACT || c2, "grouped_gemm: bias+act epilogue needs the pre-activation output c2");
+    AB_REQUIRE(epi != AB_EPI_DACT || aux, "grouped_gemm: dact epilogue needs aux");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.K = K; p.E = E;
+    p.bn = pick_bn(N, mode == MODE_NN);
+    p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
+    p.epi = epi; p.act = act; p.c_f32 = c_dtype == AB_F32;
+    p.tile_expert = tile_expert; p.n_rows = n_rows; p.bias = bias; p.aux = aux; p.c = c; p.c2 = c2;
+    CUtensorMap ta, tb;
+    if (int e = make_map2(&ta, A, (uint64_t)K, (uint64_t)max_rows, BK, BM)) return e;
+    const int64_t max_tiles = (max_rows / BM) * p.num_n_tiles;
+    if (mode == MODE_NT) {
+        if (int e = make_map2(&tb, W, (uint64_t)K, (uint64_t)E * N, BK, (uint32_t)p.bn)) return e;
+        return launch<MODE_NT>(ta, tb, p, max_tiles, stream);
+    }
+    if (int e = make_map2(&tb, W, (uint64_t)N, (uint64_t)E * K, 64, BK)) return e;
+    return launch<MODE_NN>(ta, tb, p, max_tiles, stream);
+}
+
+}  // namespace
+
+extern "C" int ab_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
+                                  const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
+                                  int epi, int act, int c_dtype, cudaStream_t stream) {
+    return gemm_rows(MODE_NT, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, stream);
+}
+
+extern "C" int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
+                                  const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
+                                  int epi, int act, int c_dtype, cudaStream_t stream) {
+    return gemm_rows(MODE_NN, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, stream);
+}
+
+extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
+                                  int N, int E, cudaStream_t stream) {
+    AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm_tn: max_rows must be a positive multiple of %d", BM);
+    AB_REQUIRE(M > 0 && N > 0 && E > 0 && M % 8 == 0 && N % 8 == 0, "grouped_gemm_tn: M (%d) and N (%d) must be multiples of 8", M, N);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.M = M; p.E = E; p.K = 0;
+    p.bn = pick_bn(N, true);
+    p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
+    p.num_m_tiles = (int)ab_ceil_div(M, BM);
+    p.seg_off = seg_off; p.cw = Cw;
+    CUtensorMap ta, tb;
+    if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)max_rows, 64, BK)) return e;
+    if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)max_rows, 64, BK)) return e;
+    return launch<MODE_TN>(ta, tb, p, (int64_t)E * p.num_m_tiles * p.num_n_tiles, stream);
+}

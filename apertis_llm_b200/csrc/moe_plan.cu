@@ -1,0 +1,491 @@
+// MoE dispatch on the device: capacity plan (bit-exact restatement of the reference's slot-major /
+// expert-inner loop with keep-the-largest-gate overflow, core.py:508-511, 547-590), token permutation
+// with the per-expert LayerNorm fused in (core.py:593 + :436), weighted un-permutation (core.py:605),
+// their backward passes and per-expert column sums for the bias gradients.  No host synchronisation:
+// everything downstream reads counts / offsets from device memory.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PLAN_THREADS = 1024;
+
+// exclusive prefix of a 0/1 flag over the CTA (in thread order) + CTA total; two __syncthreads
+__device__ __forceinline__ int block_excl_scan(bool flag, int* warp_tot /*[32]*/, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned ball = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_tot[warp] = __popc(ball);
+    __syncthreads();
+    int before = 0, tot = 0;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) {
+        const int c = warp_tot[i];
+        if (i < warp) before += c;
+        tot += c;
+    }
+    __syncthreads();
+    total = tot;
+    return before + __popc(ball & ((1u << lane) - 1u));
+}
+
+// One CTA per expert.  row_local[s,k] = position of the kept (token, slot) inside the expert's segment, -1 if dropped.
+__global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w,
+                                                                  const int32_t* __restrict__ active, int cap,
+                                                                  int32_t* __restrict__ counts, int32_t* __restrict__ row_local,
+                                                                  int S, int K) {
+    __shared__ int hist[256];
+    __shared__ int warp_tot[32];
+    __shared__ int s_sel_bin, s_need;
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x;
+    const bool is_active = active == nullptr || active[e] != 0;
+    int kept_total = 0;
+    for (int k = 0; k < K; ++k) {
+        // ---- candidates of this (slot, expert) group
+        int n_cand = 0;
+        for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+            const int s = s0 + tid;
+            const bool c = s < S && idx[(size_t)s * K + k] == e;
+            int tot;
+            block_excl_scan(c, warp_tot, tot);
+            n_cand += tot;
+        }
+        const int rem = cap - kept_total;
+        int mode = 0;                       // 0 none, 1 all, 2 select the `rem` largest
+        if (is_active && n_cand > 0 && rem > 0) mode = n_cand <= rem ? 1 : 2;
+        uint32_t tau = 0;
+        int n_eq_take = 0;
+        if (mode == 2) {
+            // radix select of the rem-th largest weight (positive floats order like their bit patterns)
+            uint32_t prefix = 0, mask = 0;
+            int need = rem;
+            for (int pass = 3; pass >= 0; --pass) {
+                for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+                __syncthreads();
+                for (int s = tid; s < S; s += blockDim.x) {
+                    if (idx[(size_t)s * K + k] == e) {
+                        const uint32_t b = __float_as_uint(w[(size_t)s * K + k]);
+                        if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int nd = need, bin = 255;
+                    for (; bin > 0; --bin) {
+                        if (hist[bin] >= nd) break;
+                        nd -= hist[bin];
+                    }
+                    s_sel_bin = bin;
+                    s_need = nd;
+                }
+                __syncthreads();
+                prefix |= (uint32_t)s_sel_bin << (8 * pass);
+                mask |= 0xffu << (8 * pass);
+                need = s_need;
+                __syncthreads();
+            }
+            tau = prefix;
+            n_eq_take = need;
+        }
+        // ---- positions in token order
+        int run_eq = 0, run_kept = 0;
+        for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+            const int s = s0 + tid;
+            const bool c = s < S && idx[(size_t)s * K + k] == e;
+            const uint32_t b = c ? __float_as_uint(w[(size_t)s * K + k]) : 0u;
+            const bool gt = c && (mode == 1 || (mode == 2 && b > tau));
+            const bool eq = c && mode == 2 && b == tau;
+            int tot_eq, tot_kept;
+            const int eq_rank = run_eq + block_excl_scan(eq, warp_tot, tot_eq);
+            const bool kept = gt || (eq && eq_rank < n_eq_take);
+            const int pos = kept_total + run_kept + block_excl_scan(kept, warp_tot, tot_kept);
+            if (c) row_local[(size_t)s * K + k] = kept ? pos : -1;
+            run_eq += tot_eq;
+            run_kept += tot_kept;
+        }
+        kept_total += run_kept;
+    }
+    if (tid == 0) counts[e] = kept_total;
+}
+
+__global__ void plan_finalize_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ counts,
+                                     const int32_t* __restrict__ row_local, int32_t* __restrict__ seg_off,
+                                     int32_t* __restrict__ row_of, int32_t* __restrict__ tok_of_row,
+                                     int32_t* __restrict__ slot_of_row, int32_t* __restrict__ tile_expert,
+                                     int32_t* __restrict__ n_rows, int S, int K, int E, int align, int64_t max_rows) {
+    __shared__ int soff[34];
+    if (threadIdx.x == 0) {
+        int o = 0, kept = 0;
+        for (int e = 0; e < E; ++e) {
+            soff[e] = o;
+            o += (counts[e] + align - 1) / align * align;
+            kept += counts[e];
+        }
+        soff[E] = o;
+        soff[E + 1] = kept;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i <= E; i += blockDim.x) seg_off[i] = soff[i];
+        if (threadIdx.x == 0) { n_rows[0] = soff[E]; n_rows[1] = soff[E + 1]; }
+        const int ntiles = (int)(max_rows / align);
+        for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+            const int r = t * align;
+            int ex = -1;
+            for (int e = 0; e < E; ++e)
+                if (r >= soff[e] && r < soff[e + 1]) ex = e;
+            tile_expert[t] = ex;
+        }
+    }
+    const int64_t n = (int64_t)S * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int rl = row_local[i];
+        if (rl >= 0) {
+            const int r = soff[idx[i]] + rl;
+            row_of[i] = r;
+            tok_of_row[r] = (int)(i / K);
+            slot_of_row[r] = (int)(i % K);
+        } else {
+            row_of[i] = -1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// permute + LayerNorm (warp per row)
+// ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ x, const float* __restrict__ stats,
+                                                         const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                         const int32_t* __restrict__ tok_of_row,
+                                                         const int32_t* __restrict__ tile_expert,
+                                                         const int32_t* __restrict__ n_rows, TO* __restrict__ xn, int Dm,
+                                                         int align) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int total = n_rows[0];
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
+        const int tok = tok_of_row[r];
+        TO* orow = xn + (size_t)r * Dm;
+        if (tok < 0) {
+            for (int d = lane * 4; d < Dm; d += 128) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) orow[d + v] = ab_from_float<TO>(0.f);
+            }
+            continue;
+        }
+        const int e = tile_expert[r / align];
+        const float mean = stats[2 * (size_t)tok], rstd = stats[2 * (size_t)tok + 1];
+        const TI* irow = x + (size_t)tok * Dm;
+        const float* g = ln_w + (size_t)e * Dm;
+        const float* bb = ln_b + (size_t)e * Dm;
+        for (int d = lane * 4; d < Dm; d += 128) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(g + d));
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bb + d));
+            float xv[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) xv[v] = ab_to_float(irow[d + v]);
+            orow[d + 0] = ab_from_float<TO>(fmaf((xv[0] - mean) * rstd, gv.x, bv.x));
+            orow[d + 1] = ab_from_float<TO>(fmaf((xv[1] - mean) * rstd, gv.y, bv.y));
+            orow[d + 2] = ab_from_float<TO>(fmaf((xv[2] - mean) * rstd, gv.z, bv.z));
+            orow[d + 3] = ab_from_float<TO>(fmaf((xv[3] - mean) * rstd, gv.w, bv.w));
+        }
+    }
+}
+
+// out[s,:] = sum_k w[s,k] * y[row_of[s,k],:]   (warp per token, fixed slot order)
+template <typename TY, typename TO>
+__global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y, const int32_t* __restrict__ row_of,
+                                                        const float* __restrict__ w, TO* __restrict__ out, int S, int K, int Dm) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
+        TO* orow = out + (size_t)s * Dm;
+        for (int d = lane * 4; d < Dm; d += 128) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < K; ++k) {
+                const int r = row_of[(size_t)s * K + k];
+                if (r < 0) continue;
+                const float wk = w[(size_t)s * K + k];
+                const TY* yr = y + (size_t)r * Dm + d;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] += ab_to_float(yr[v]) * wk;   // separate mul and add, as index_add_(y*w)
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) orow[d + v] = ab_from_float<TO>(acc[v]);
+        }
+    }
+}
+
+// dy[r,:] = w[r] * dout[tok,:] ; dw_row[r] = <dout[tok,:], y[r,:]>
+template <typename TD, typename TY, typename TO>
+__global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict__ dout, const TY* __restrict__ y,
+                                                            const float* __restrict__ w, const int32_t* __restrict__ tok_of_row,
+                                                            const int32_t* __restrict__ slot_of_row,
+                                                            const int32_t* __restrict__ n_rows, TO* __restrict__ dy,
+                                                            float* __restrict__ dw_row, int K, int Dm) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int total = n_rows[0];
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
+        const int tok = tok_of_row[r];
+        TO* orow = dy + (size_t)r * Dm;
+        if (tok < 0) {
+            for (int d = lane; d < Dm; d += 32) orow[d] = ab_from_float<TO>(0.f);
+            if (lane == 0) dw_row[r] = 0.f;
+            continue;
+        }
+        const float wk = w[(size_t)tok * K + slot_of_row[r]];
+        const TD* drow = dout + (size_t)tok * Dm;
+        const TY* yrow = y + (size_t)r * Dm;
+        float dot = 0.f;
+        for (int d = lane * 4; d < Dm; d += 128) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float g = ab_to_float(drow[d + v]);
+                dot = fmaf(g, ab_to_float(yrow[d + v]), dot);
+                orow[d + v] = ab_from_float<TO>(g * wk);
+            }
+        }
+        dot = ab_warp_sum(dot);
+        if (lane == 0) dw_row[r] = dot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward per permuted row + per-tile partial sums of the affine grads (CTA per row tile)
+// ---------------------------------------------------------------------------------------------
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(256) permute_ln_bwd_kernel(const TG* __restrict__ dxn, const TX* __restrict__ x,
+                                                             const float* __restrict__ stats, const float* __restrict__ ln_w,
+                                                             const int32_t* __restrict__ tok_of_row,
+                                                             const int32_t* __restrict__ tile_expert,
+                                                             const int32_t* __restrict__ n_rows, float* __restrict__ dxrow,
+                                                             float* __restrict__ part, int Dm, int align) {
+    extern __shared__ float sm[];       // [align] tok (as int), [align] mean, [align] rstd
+    int* s_tok = reinterpret_cast<int*>(sm);
+    float* s_mean = sm + align;
+    float* s_rstd = sm + 2 * align;
+    const int t = blockIdx.x;
+    if ((int64_t)t * align >= n_rows[0]) return;
+    const int e = tile_expert[t];
+    if (e < 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const float* g = ln_w + (size_t)e * Dm;
+    for (int i = warp; i < align; i += wpb) {
+        const int r = t * align + i;
+        const int tok = tok_of_row[r];
+        if (lane == 0) s_tok[i] = tok;
+        if (tok < 0) continue;
+        const float mean = stats[2 * (size_t)tok], rstd = stats[2 * (size_t)tok + 1];
+        if (lane == 0) { s_mean[i] = mean; s_rstd[i] = rstd; }
+        const TX* xr = x + (size_t)tok * Dm;
+        const TG* gr = dxn + (size_t)r * Dm;
+        float a1 = 0.f, a2 = 0.f;
+        for (int d = lane; d < Dm; d += 32) {
+            const float dh = ab_to_float(gr[d]) * __ldg(g + d);
+            const float xh = (ab_to_float(xr[d]) - mean) * rstd;
+            a1 += dh;
+            a2 = fmaf(dh, xh, a2);
+        }
+        const float m1 = ab_warp_sum(a1) / (float)Dm, m2 = ab_warp_sum(a2) / (float)Dm;
+        float* orow = dxrow + (size_t)r * Dm;
+        for (int d = lane; d < Dm; d += 32) {
+            const float dh = ab_to_float(gr[d]) * __ldg(g + d);
+            const float xh = (ab_to_float(xr[d]) - mean) * rstd;
+            orow[d] = rstd * (dh - m1 - xh * m2);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < Dm; d += blockDim.x) {
+        float gw = 0.f, gb = 0.f;
+        for (int i = 0; i < align; ++i) {
+            const int tok = s_tok[i];
+            if (tok < 0) continue;
+            const float dv = ab_to_float(dxn[((size_t)t * align + i) * Dm + d]);
+            const float xh = (ab_to_float(x[(size_t)tok * Dm + d]) - s_mean[i]) * s_rstd[i];
+            gw = fmaf(dv, xh, gw);
+            gb += dv;
+        }
+        part[((size_t)t * 2 + 0) * Dm + d] = gw;
+        part[((size_t)t * 2 + 1) * Dm + d] = gb;
+    }
+}
+
+// per-tile column sums (CTA per row tile)
+template <typename T>
+__global__ void __launch_bounds__(256) tile_colsum_kernel(const T* __restrict__ a, const int32_t* __restrict__ tile_expert,
+                                                          const int32_t* __restrict__ n_rows, float* __restrict__ part, int C,
+                                                          int align) {
+    const int t = blockIdx.x;
+    if ((int64_t)t * align >= n_rows[0] || tile_expert[t] < 0) return;
+    for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+        float s0 = 0.f, s1 = 0.f;
+        const T* col = a + (size_t)t * align * C + c;
+        if (c + 1 < C) {
+            for (int i = 0; i < align; ++i) {
+                s0 += ab_to_float(col[(size_t)i * C]);
+                s1 += ab_to_float(col[(size_t)i * C + 1]);
+            }
+            part[(size_t)t * C + c] = s0;
+            part[(size_t)t * C + c + 1] = s1;
+        } else {
+            for (int i = 0; i < align; ++i) s0 += ab_to_float(col[(size_t)i * C]);
+            part[(size_t)t * C + c] = s0;
+        }
+    }
+}
+
+// out[e][j] = sum over tiles of expert e of part[t][j], fixed order.  Columns [0, split) go to out_a [E][split],
+// columns [split, ncols) to out_b [E][ncols-split].
+__global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t* __restrict__ tile_expert,
+                                   const int32_t* __restrict__ n_rows, float* __restrict__ out_a, float* __restrict__ out_b,
+                                   int split, int ncols, int align) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.y;
+    if (j >= ncols) return;
+    const int ntiles = n_rows[0] / align;
+    float s = 0.f;
+    for (int t = 0; t < ntiles; ++t)
+        if (tile_expert[t] == e) s += part[(size_t)t * ncols + j];
+    if (j < split) out_a[(size_t)e * split + j] = s;
+    else out_b[(size_t)e * (ncols - split) + (j - split)] = s;
+}
+
+int rows_grid(int64_t max_rows) {
+    const int64_t want = ab_ceil_div(max_rows, 8);
+    const int64_t cap = (int64_t)ab_num_sms() * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+extern "C" int64_t ab_moe_max_rows(int S, int K, int E, int cap, int row_align) {
+    int64_t kept = (int64_t)S * K;
+    if ((int64_t)E * cap < kept) kept = (int64_t)E * cap;
+    return ab_round_up(kept + (int64_t)E * (row_align - 1), row_align);
+}
+
+extern "C" size_t ab_moe_plan_workspace_bytes(int S, int K, int E) {
+    (void)E;
+    return (size_t)ab_round_up((int64_t)S * K * sizeof(int32_t), 256);
+}
+
+extern "C" int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* active, int cap, int32_t* counts,
+                           int32_t* seg_off, int32_t* row_of, int32_t* tok_of_row, int32_t* slot_of_row,
+                           int32_t* tile_expert, int32_t* n_rows, void* ws, size_t ws_bytes, int S, int K, int E,
+                           int row_align, int64_t max_rows, cudaStream_t stream) {
+    AB_REQUIRE(S > 0 && K >= 1 && E >= 1 && E <= 32, "moe_plan: bad shape S=%d K=%d E=%d", S, K, E);
+    AB_REQUIRE(row_align > 0 && max_rows % row_align == 0 && max_rows >= ab_moe_max_rows(S, K, E, cap < S ? cap : S, row_align),
+               "moe_plan: max_rows %lld too small or not a multiple of %d", (long long)max_rows, row_align);
+    AB_REQUIRE(ws && ws_bytes >= ab_moe_plan_workspace_bytes(S, K, E), "moe_plan: workspace too small");
+    int32_t* row_local = (int32_t*)ws;
+    AB_CHECK_CUDA(cudaMemsetAsync(tok_of_row, 0xFF, (size_t)max_rows * sizeof(int32_t), stream));
+    AB_CHECK_CUDA(cudaMemsetAsync(slot_of_row, 0xFF, (size_t)max_rows * sizeof(int32_t), stream));
+    plan_count_kernel<<<E, PLAN_THREADS, 0, stream>>>(idx, w, active, cap, counts, row_local, S, K);
+    AB_LAUNCH_CHECK();
+    const int64_t want = ab_ceil_div((int64_t)S * K, 256);
+    const int grid = (int)(want < ab_num_sms() * 4 ? want : ab_num_sms() * 4);
+    plan_finalize_kernel<<<grid, 256, 0, stream>>>(idx, counts, row_local, seg_off, row_of, tok_of_row, slot_of_row, tile_expert,
+                                                   n_rows, S, K, E, row_align, max_rows);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" int ab_moe_permute_ln(const void* x, const float* stats, const float* ln_w, const float* ln_b,
+                                 const int32_t* tok_of_row, const int32_t* tile_expert, const int32_t* n_rows, void* xn, int Dm,
+                                 int row_align, int64_t max_rows, int dtype, int out_dtype, cudaStream_t stream) {
+    AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_permute_ln: hidden size must be a multiple of 4");
+    const int grid = rows_grid(max_rows);
+#define AB_PLN(TI, TO) permute_ln_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, stats, ln_w, ln_b, tok_of_row, tile_expert, n_rows, (TO*)xn, Dm, row_align)
+    if (dtype == AB_F32 && out_dtype == AB_F32) AB_PLN(float, float);
+    else if (dtype == AB_F32 && out_dtype == AB_BF16) AB_PLN(float, __nv_bfloat16);
+    else if (dtype == AB_BF16 && out_dtype == AB_BF16) AB_PLN(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype == AB_BF16 && out_dtype == AB_F32) AB_PLN(__nv_bfloat16, float);
+    else AB_REQUIRE(false, "moe_permute_ln: bad dtypes");
+#undef AB_PLN
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, void* out, int S, int K, int Dm,
+                                int y_dtype, int out_dtype, cudaStream_t stream) {
+    AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute: hidden size must be a multiple of 4");
+    const int grid = rows_grid(S);
+#define AB_UNP(TY, TO) unpermute_kernel<TY, TO><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, (TO*)out, S, K, Dm)
+    if (y_dtype == AB_F32 && out_dtype == AB_F32) AB_UNP(float, float);
+    else if (y_dtype == AB_BF16 && out_dtype == AB_F32) AB_UNP(__nv_bfloat16, float);
+    else if (y_dtype == AB_BF16 && out_dtype == AB_BF16) AB_UNP(__nv_bfloat16, __nv_bfloat16);
+    else if (y_dtype == AB_F32 && out_dtype == AB_BF16) AB_UNP(float, __nv_bfloat16);
+    else AB_REQUIRE(false, "moe_unpermute: bad dtypes");
+#undef AB_UNP
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" int ab_moe_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row,
+                                    const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, int K, int Dm,
+                                    int64_t max_rows, int dout_dtype, int y_dtype, int dy_dtype, cudaStream_t stream) {
+    AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute_bwd: hidden size must be a multiple of 4");
+    const int grid = rows_grid(max_rows);
+#define AB_UB(TD, TY, TO) unpermute_bwd_kernel<TD, TY, TO><<<grid, 256, 0, stream>>>((const TD*)dout, (const TY*)y, w, tok_of_row, slot_of_row, n_rows, (TO*)dy, dw_row, K, Dm)
+    const int key = dout_dtype * 4 + y_dtype * 2 + dy_dtype;
+    switch (key) {
+        case 0: AB_UB(float, float, float); break;
+        case 1: AB_UB(float, float, __nv_bfloat16); break;
+        case 2: AB_UB(float, __nv_bfloat16, float); break;
+        case 3: AB_UB(float, __nv_bfloat16, __nv_bfloat16); break;
+        case 4: AB_UB(__nv_bfloat16, float, float); break;
+        case 5: AB_UB(__nv_bfloat16, float, __nv_bfloat16); break;
+        case 6: AB_UB(__nv_bfloat16, __nv_bfloat16, float); break;
+        case 7: AB_UB(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+        default: AB_REQUIRE(false, "moe_unpermute_bwd: bad dtypes");
+    }
+#undef AB_UB
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" size_t ab_moe_permute_ln_bwd_workspace_bytes(int Dm, int row_align, int64_t max_rows) {
+    return (size_t)ab_round_up((max_rows / row_align) * 2 * (int64_t)Dm * sizeof(float), 256);
+}
+
+extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float* stats, const float* ln_w,
+                                     const int32_t* tok_of_row, const int32_t* tile_expert, const int32_t* n_rows, float* dxrow,
+                                     float* dln_w, float* dln_b, void* ws, size_t ws_bytes, int Dm, int E, int row_align,
+                                     int64_t max_rows, int dtype, int dxn_dtype, cudaStream_t stream) {
+    AB_REQUIRE(ws && ws_bytes >= ab_moe_permute_ln_bwd_workspace_bytes(Dm, row_align, max_rows), "moe_permute_ln_bwd: workspace too small");
+    const int ntiles = (int)(max_rows / row_align);
+    const size_t smem = (size_t)3 * row_align * sizeof(float);
+    float* part = (float*)ws;
+#define AB_LNB(TX, TG) permute_ln_bwd_kernel<TX, TG><<<ntiles, 256, smem, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row, tile_expert, n_rows, dxrow, part, Dm, row_align)
+    if (dtype == AB_F32 && dxn_dtype == AB_F32) AB_LNB(float, float);
+    else if (dtype == AB_F32 && dxn_dtype == AB_BF16) AB_LNB(float, __nv_bfloat16);
+    else if (dtype == AB_BF16 && dxn_dtype == AB_BF16) AB_LNB(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype == AB_BF16 && dxn_dtype == AB_F32) AB_LNB(__nv_bfloat16, float);
+    else AB_REQUIRE(false, "moe_permute_ln_bwd: bad dtypes");
+#undef AB_LNB
+    AB_LAUNCH_CHECK();
+    dim3 grid((unsigned)ab_ceil_div(2 * Dm, 128), E);       // part is [tile][2][Dm]: reduce as 2*Dm columns, split in two
+    tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, dln_w, dln_b, Dm, 2 * Dm, row_align);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" size_t ab_moe_segment_colsum_workspace_bytes(int C, int row_align, int64_t max_rows) {
+    return (size_t)ab_round_up((max_rows / row_align) * (int64_t)C * sizeof(float), 256);
+}
+
+extern "C" int ab_moe_segment_colsum(const void* a, const int32_t* tile_expert, const int32_t* n_rows, float* out, void* ws,
+                                     size_t ws_bytes, int C, int E, int row_align, int64_t max_rows, int dtype,
+                                     cudaStream_t stream) {
+    AB_REQUIRE(ws && ws_bytes >= ab_moe_segment_colsum_workspace_bytes(C, row_align, max_rows), "moe_segment_colsum: workspace too small");
+    const int ntiles = (int)(max_rows / row_align);
+    float* part = (float*)ws;
+    if (dtype == AB_F32) tile_colsum_kernel<float><<<ntiles, 256, 0, stream>>>((const float*)a, tile_expert, n_rows, part, C, row_align);
+    else tile_colsum_kernel<__nv_bfloat16><<<ntiles, 256, 0, stream>>>((const __nv_bfloat16*)a, tile_expert, n_rows, part, C, row_align);
+    AB_LAUNCH_CHECK();
+    dim3 grid((unsigned)ab_ceil_div(C, 128), E);
+    tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, out, nullptr, C, C, row_align);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}

@@ -1,0 +1,471 @@
+// MoE router: LayerNorm + Linear(E) + noise + softmax + top-K + normalised weights + aux-loss sums,
+// and its backward.  Replaces core.py:480-492, 499-505, 524-529 and their autograd.
+//
+// Forward: one warp per token.  The row is read twice (mean, then centred second moment + the E dot
+// products in the same pass; the second read hits L1), LayerNorm affine is folded into the router
+// weight once per CTA (G[e,d] = ln_w[d]*Wr[e,d] in shared memory; c[e] = sum_d ln_b[d]*Wr[e,d] + br[e]).
+// Lanes 0..E-1 then own one expert each for softmax / top-K.  Ties in top-K go to the lower expert id.
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int MAX_K = 8;
+
+template <typename T>
+__device__ __forceinline__ void row_load(const T* row, int i, float* f) {   // vector i of the row
+    ab_vec16<T>::unpack(__ldg(reinterpret_cast<const uint4*>(row) + i), f);
+}
+
+// softmax / top-K / weights on lanes (lane e < E holds logit e).  Returns gate in g.
+__device__ __forceinline__ void select_topk(float logit, int lane, int E, int K, float& g, float& lse, int* sel_idx,
+                                            float* sel_p) {
+    const float lv = lane < E ? logit : -INFINITY;
+    const float m = ab_warp_max(lv);
+    const float ex = lane < E ? expf(lv - m) : 0.f;
+    const float sum = ab_warp_sum(ex);
+    g = ex / sum;
+    lse = m + logf(sum);
+    float cand = lane < E ? g : -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        const float best = ab_warp_max(cand);
+        const unsigned ball = __ballot_sync(0xffffffffu, cand == best);
+        const int win = __ffs(ball) - 1;               // lowest expert id among equals
+        sel_idx[k] = win;
+        sel_p[k] = best;
+        if (lane == win) cand = -INFINITY;
+    }
+}
+
+__device__ __forceinline__ void write_selection(int s, int lane, int E, int K, float g, float lse, const int* sel_idx,
+                                                const float* sel_p, float* gates, int32_t* idx, float* probs, float* w,
+                                                float* lse_out) {
+    if (lane < E) gates[(size_t)s * E + lane] = g;
+    float den = 0.f;
+    for (int k = 0; k < K; ++k) den += sel_p[k];       // (sum probs) + 1e-6, summed in slot order like torch.sum over K
+    den += 1e-6f;
+    if (lane < K) {
+        int myi = 0; float myp = 0.f;
+        for (int k = 0; k < K; ++k) if (k == lane) { myi = sel_idx[k]; myp = sel_p[k]; }
+        idx[(size_t)s * K + lane] = myi;
+        probs[(size_t)s * K + lane] = myp;
+        w[(size_t)s * K + lane] = myp / den;
+    }
+    if (lane == 0) lse_out[s] = lse;
+}
+
+// aux partial layout per CTA: [2E+1] = sum gates[e], count[e], sum lse^2
+template <typename T, int EM>
+__global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
+                                                                const float* __restrict__ ln_b, float eps,
+                                                                const float* __restrict__ Wr, const float* __restrict__ br,
+                                                                const float* __restrict__ noise,
+                                                                const float* __restrict__ noise_scale, float* __restrict__ lclean,
+                                                                float* __restrict__ logits, float* __restrict__ gates,
+                                                                int32_t* __restrict__ idx, float* __restrict__ probs,
+                                                                float* __restrict__ w, float* __restrict__ lse_out,
+                                                                float* __restrict__ stats, float* __restrict__ part, int S,
+                                                                int Dm, int E, int K) {
+    constexpr int V = ab_vec16<T>::N;
+    extern __shared__ float sm[];
+    float* G = sm;                 // [E][Dm]
+    float* cvec = G + (size_t)E * Dm;   // [E]
+    float* red = cvec + 32;        // [WARPS][2E+1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < E * Dm; i += blockDim.x) G[i] = ln_w[i % Dm] * Wr[i];
+    for (int e = warp; e < E; e += WARPS) {
+        float acc = 0.f;
+        for (int d = lane; d < Dm; d += 32) acc = fmaf(ln_b[d], Wr[(size_t)e * Dm + d], acc);
+        acc = ab_warp_sum(acc);
+        if (lane == 0) cvec[e] = acc + br[e];
+    }
+    __syncthreads();
+    const int nvec = Dm / V;
+    float a_g = 0.f, a_cnt = 0.f, a_l2 = 0.f;
+    for (int s = blockIdx.x * WARPS + warp; s < S; s += gridDim.x * WARPS) {
+        const T* row = x + (size_t)s * Dm;
+        float sum = 0.f;
+        for (int i = lane; i < nvec; i += 32) {
+            float f[V];
+            row_load<T>(row, i, f);
+#pragma unroll
+            for (int v = 0; v < V; ++v) sum += f[v];
+        }
+        const float mean = ab_warp_sum(sum) / (float)Dm;
+        float var = 0.f;
+        float dot[EM];
+#pragma unroll
+        for (int e = 0; e < EM; ++e) dot[e] = 0.f;
+        for (int i = lane; i < nvec; i += 32) {
+            float f[V];
+            row_load<T>(row, i, f);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float c = f[v] - mean;
+                var = fmaf(c, c, var);
+                const int d = i * V + v;
+#pragma unroll
+                for (int e = 0; e < EM; ++e)
+                    if (e < E) dot[e] = fmaf(c, G[(size_t)e * Dm + d], dot[e]);
+            }
+        }
+        var = ab_warp_sum(var) / (float)Dm;
+        const float rstd = rsqrtf(var + eps);
+        float mylogit = 0.f;
+#pragma unroll
+        for (int e = 0; e < EM; ++e) {
+            if (e < E) {
+                const float t = ab_warp_sum(dot[e]);
+                if (lane == e) mylogit = t;
+            }
+        }
+        float lc = 0.f;
+        if (lane < E) {
+            lc = fmaf(rstd, mylogit, cvec[lane]);
+            mylogit = lc;
+            if (noise) mylogit = fmaf(noise[(size_t)s * E + lane], noise_scale[lane], lc);
+            if (lclean) lclean[(size_t)s * E + lane] = lc;
+            if (logits) logits[(size_t)s * E + lane] = mylogit;
+        }
+        if (lane == 0) { stats[2 * (size_t)s] = mean; stats[2 * (size_t)s + 1] = rstd; }
+        float g, lse;
+        int sel_idx[MAX_K];
+        float sel_p[MAX_K];
+        select_topk(mylogit, lane, E, K, g, lse, sel_idx, sel_p);
+        write_selection(s, lane, E, K, g, lse, sel_idx, sel_p, gates, idx, probs, w, lse_out);
+        if (lane < E) {
+            a_g += g;
+            for (int k = 0; k < K; ++k) a_cnt += (sel_idx[k] == lane) ? 1.f : 0.f;
+        }
+        if (lane == 0) a_l2 = fmaf(lse, lse, a_l2);
+    }
+    const int NA = 2 * E + 1;
+    if (lane < E) { red[warp * NA + lane] = a_g; red[warp * NA + E + lane] = a_cnt; }
+    if (lane == 0) red[warp * NA + 2 * E] = a_l2;
+    __syncthreads();
+    if (tid < NA) {
+        float s2 = 0.f;
+        for (int wv = 0; wv < WARPS; ++wv) s2 += red[wv * NA + tid];
+        part[(size_t)blockIdx.x * NA + tid] = s2;
+    }
+}
+
+__global__ void reduce_rows_kernel(const float* __restrict__ part, int nrows, int ncols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    float s = 0.f;
+    for (int r = 0; r < nrows; ++r) s += part[(size_t)r * ncols + c];
+    out[c] = s;
+}
+
+__global__ void __launch_bounds__(WARPS * 32) topk_from_logits_kernel(const float* __restrict__ logits, float* __restrict__ gates,
+                                                                      int32_t* __restrict__ idx, float* __restrict__ probs,
+                                                                      float* __restrict__ w, float* __restrict__ lse_out, int S,
+                                                                      int E, int K) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = blockIdx.x * WARPS + warp; s < S; s += gridDim.x * WARPS) {
+        const float l = lane < E ? logits[(size_t)s * E + lane] : 0.f;
+        float g, lse;
+        int sel_idx[MAX_K];
+        float sel_p[MAX_K];
+        select_topk(l, lane, E, K, g, lse, sel_idx, sel_p);
+        write_selection(s, lane, E, K, g, lse, sel_idx, sel_p, gates, idx, probs, w, lse_out);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, kernel B: per token d logits and dx
+// part layout per CTA: [2E] = sum dlogit[e] (-> dbr), sum dlogit[e]*noise[s,e] (-> dnoise_scale)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int EM>
+__global__ void __launch_bounds__(WARPS * 32) router_bwd_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                                                const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                                const float* __restrict__ Wr, const float* __restrict__ br,
+                                                                const float* __restrict__ gates, const int32_t* __restrict__ idx,
+                                                                const float* __restrict__ probs, const float* __restrict__ lse,
+                                                                const float* __restrict__ lclean, const float* __restrict__ noise,
+                                                                const float* __restrict__ f, const float* __restrict__ scal,
+                                                                const float* __restrict__ dw_row, const float* __restrict__ dxrow,
+                                                                const int32_t* __restrict__ row_of, T* __restrict__ dx,
+                                                                float* __restrict__ dlogits, float* __restrict__ part, int S,
+                                                                int Dm, int E, int K) {
+    constexpr int V = ab_vec16<T>::N;
+    extern __shared__ float sm[];
+    float* Wsm = sm;                         // [E][Dm] raw router weight
+    float* gam = Wsm + (size_t)E * Dm;       // [Dm]
+    float* GS = gam + Dm;                    // [32]  sum_d ln_w[d]*Wr[e,d]
+    float* cvec = GS + 32;                   // [32]
+    float* red = cvec + 32;                  // [WARPS][2E]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < E * Dm; i += blockDim.x) Wsm[i] = Wr[i];
+    for (int i = tid; i < Dm; i += blockDim.x) gam[i] = ln_w[i];
+    for (int e = warp; e < E; e += WARPS) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int d = lane; d < Dm; d += 32) {
+            a1 = fmaf(ln_w[d], Wr[(size_t)e * Dm + d], a1);
+            a2 = fmaf(ln_b[d], Wr[(size_t)e * Dm + d], a2);
+        }
+        a1 = ab_warp_sum(a1); a2 = ab_warp_sum(a2);
+        if (lane == 0) { GS[e] = a1; cvec[e] = a2 + br[e]; }
+    }
+    __syncthreads();
+    const float g_lb = scal[0], g_rz = scal[1];
+    const int nvec = Dm / V;
+    float a_db = 0.f, a_dn = 0.f;
+    for (int s = blockIdx.x * WARPS + warp; s < S; s += gridDim.x * WARPS) {
+        // ---- d weights -> d probs
+        float dwk[MAX_K], pk[MAX_K];
+        int ik[MAX_K], rk[MAX_K];
+        float den = 0.f, dot = 0.f;
+        for (int k = 0; k < K; ++k) {
+            rk[k] = row_of[(size_t)s * K + k];
+            ik[k] = idx[(size_t)s * K + k];
+            pk[k] = probs[(size_t)s * K + k];
+            dwk[k] = rk[k] >= 0 ? dw_row[rk[k]] : 0.f;
+            den += pk[k];
+            dot = fmaf(dwk[k], pk[k], dot);
+        }
+        den += 1e-6f;
+        const float inv = 1.f / den;
+        float dgate = 0.f, g = 0.f;
+        if (lane < E) {
+            g = gates[(size_t)s * E + lane];
+            for (int k = 0; k < K; ++k)
+                if (ik[k] == lane) dgate += dwk[k] * inv - dot * inv * inv;
+            dgate = fmaf(g_lb, f[lane], dgate);
+        }
+        const float gd = ab_warp_sum(g * dgate);
+        float dl = 0.f;
+        if (lane < E) {
+            dl = g * (dgate - gd) + g_rz * 2.f * lse[s] * g;
+            dlogits[(size_t)s * E + lane] = dl;
+            a_db += dl;
+            if (noise) a_dn = fmaf(dl, noise[(size_t)s * E + lane], a_dn);
+        }
+        // ---- LayerNorm backward constants:  m1 = mean_d(dxhat), m2 = mean_d(dxhat * xhat)
+        const float mean = stats[2 * (size_t)s], rstd = stats[2 * (size_t)s + 1];
+        float t1 = 0.f, t2 = 0.f;
+        if (lane < E) {
+            t1 = dl * GS[lane];
+            t2 = dl * (lclean[(size_t)s * E + lane] - cvec[lane]);    // sum_d G[e,d]*xhat[d]
+        }
+        const float m1 = ab_warp_sum(t1) / (float)Dm;
+        const float m2 = ab_warp_sum(t2) / (float)Dm;
+        float dle[EM];
+#pragma unroll
+        for (int e = 0; e < EM; ++e) dle[e] = __shfl_sync(0xffffffffu, dl, e);
+        const T* row = x + (size_t)s * Dm;
+        T* orow = dx + (size_t)s * Dm;
+        for (int i = lane; i < nvec; i += 32) {
+            float fx[V], o[V];
+            row_load<T>(row, i, fx);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int d = i * V + v;
+                float dxn = 0.f;
+#pragma unroll
+                for (int e = 0; e < EM; ++e)
+                    if (e < E) dxn = fmaf(dle[e], Wsm[(size_t)e * Dm + d], dxn);
+                const float xh = (fx[v] - mean) * rstd;
+                o[v] = rstd * (dxn * gam[d] - m1 - xh * m2);
+            }
+            for (int k = 0; k < K; ++k) {
+                if (rk[k] >= 0) {
+                    const float* er = dxrow + (size_t)rk[k] * Dm + i * V;
+#pragma unroll
+                    for (int v4 = 0; v4 < V; v4 += 4) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(er + v4));
+                        o[v4] += q.x; o[v4 + 1] += q.y; o[v4 + 2] += q.z; o[v4 + 3] += q.w;
+                    }
+                }
+            }
+            *(reinterpret_cast<uint4*>(orow) + i) = ab_vec16<T>::pack(o);
+        }
+    }
+    const int NA = 2 * E;
+    if (lane < E) { red[warp * NA + lane] = a_db; red[warp * NA + E + lane] = a_dn; }
+    __syncthreads();
+    if (tid < NA) {
+        float s2 = 0.f;
+        for (int wv = 0; wv < WARPS; ++wv) s2 += red[wv * NA + tid];
+        part[(size_t)blockIdx.x * NA + tid] = s2;
+    }
+}
+
+// kernel C: Q[e,d] = sum_s dlogits[s,e] * xhat[s,d]; thread per column d, token blocks of QB tokens
+constexpr int QB = 128;
+template <typename T, int EM>
+__global__ void __launch_bounds__(256) router_q_kernel(const T* __restrict__ x, const float* __restrict__ stats,
+                                                       const float* __restrict__ dlogits, float* __restrict__ qpart, int S,
+                                                       int Dm, int E) {
+    __shared__ float sdl[QB * 32];
+    __shared__ float sst[QB * 2];
+    const int s0 = blockIdx.y * QB;
+    const int ns = min(QB, S - s0);
+    for (int i = threadIdx.x; i < ns * E; i += blockDim.x) sdl[i] = dlogits[(size_t)s0 * E + i];
+    for (int i = threadIdx.x; i < ns * 2; i += blockDim.x) sst[i] = stats[(size_t)s0 * 2 + i];
+    __syncthreads();
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= Dm) return;
+    float acc[EM];
+#pragma unroll
+    for (int e = 0; e < EM; ++e) acc[e] = 0.f;
+    for (int j = 0; j < ns; ++j) {
+        const float xh = (ab_to_float(x[(size_t)(s0 + j) * Dm + d]) - sst[2 * j]) * sst[2 * j + 1];
+#pragma unroll
+        for (int e = 0; e < EM; ++e)
+            if (e < E) acc[e] = fmaf(sdl[j * E + e], xh, acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < EM; ++e)
+        if (e < E) qpart[((size_t)blockIdx.y * E + e) * Dm + d] = acc[e];
+}
+
+// kernel D: reduce Q partials and derive all router parameter grads
+//   dbr[e] = sum dlogits;  dWr[e,d] = ln_w[d]*Q[e,d] + ln_b[d]*dbr[e]
+//   dln_w[d] = sum_e Wr[e,d]*Q[e,d];  dln_b[d] = sum_e Wr[e,d]*dbr[e]
+__global__ void router_param_kernel(const float* __restrict__ qpart, int nqb, const float* __restrict__ part, int nparts,
+                                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, const float* __restrict__ Wr,
+                                    float* __restrict__ dWr, float* __restrict__ dbr, float* __restrict__ dln_w,
+                                    float* __restrict__ dln_b, float* __restrict__ dnoise_scale, int Dm, int E) {
+    __shared__ float sdb[32];
+    if (threadIdx.x < 2 * E) {
+        float s = 0.f;
+        for (int r = 0; r < nparts; ++r) s += part[(size_t)r * 2 * E + threadIdx.x];
+        if (threadIdx.x < E) { sdb[threadIdx.x] = s; if (blockIdx.x == 0) dbr[threadIdx.x] = s; }
+        else if (blockIdx.x == 0 && dnoise_scale) dnoise_scale[threadIdx.x - E] = s;
+    }
+    __syncthreads();
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= Dm) return;
+    float gw = 0.f, gb = 0.f;
+    for (int e = 0; e < E; ++e) {
+        float q = 0.f;
+        for (int r = 0; r < nqb; ++r) q += qpart[((size_t)r * E + e) * Dm + d];
+        const float wv = Wr[(size_t)e * Dm + d];
+        dWr[(size_t)e * Dm + d] = fmaf(ln_w[d], q, ln_b[d] * sdb[e]);
+        gw = fmaf(wv, q, gw);
+        gb = fmaf(wv, sdb[e], gb);
+    }
+    dln_w[d] = gw;
+    dln_b[d] = gb;
+}
+
+int router_grid(int S) {
+    const int want = (int)ab_ceil_div(S, WARPS);
+    const int cap = ab_num_sms() * 4;
+    return want < cap ? want : cap;
+}
+
+struct FwdWs { size_t part_off, total; int grid; };
+FwdWs fwd_ws(int S, int E) {
+    FwdWs w;
+    w.grid = router_grid(S);
+    w.part_off = 0;
+    w.total = ab_round_up((int64_t)w.grid * (2 * E + 1) * sizeof(float), 256);
+    return w;
+}
+struct BwdWs { size_t part_off, dl_off, q_off, total; int grid, nqb; };
+BwdWs bwd_ws(int S, int Dm, int E) {
+    BwdWs w;
+    w.grid = router_grid(S);
+    w.nqb = (int)ab_ceil_div(S, QB);
+    size_t o = 0;
+    w.part_off = o; o += ab_round_up((int64_t)w.grid * 2 * E * sizeof(float), 256);
+    w.dl_off = o; o += ab_round_up((int64_t)S * E * sizeof(float), 256);
+    w.q_off = o; o += ab_round_up((int64_t)w.nqb * E * Dm * sizeof(float), 256);
+    w.total = o;
+    return w;
+}
+
+int check_router(int S, int Dm, int E, int K, int dtype) {
+    AB_REQUIRE(S > 0 && Dm > 0, "moe_router: empty shape S=%d Dm=%d", S, Dm);
+    AB_REQUIRE(E >= 1 && E <= 32, "moe_router: num_experts must be in [1,32] (got %d)", E);
+    AB_REQUIRE(K >= 1 && K <= MAX_K && K <= E, "moe_router: experts_per_token must be in [1,%d] and <= E (got %d)", MAX_K, K);
+    AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "moe_router: bad dtype %d", dtype);
+    const int V = dtype == AB_F32 ? 4 : 8;
+    AB_REQUIRE(Dm % V == 0, "moe_router: hidden size %d must be a multiple of %d", Dm, V);
+    return AB_OK;
+}
+
+}  // namespace
+
+extern "C" size_t ab_moe_router_workspace_bytes(int S, int Dm, int E) { (void)Dm; return fwd_ws(S, E).total; }
+
+extern "C" int ab_moe_router_fwd(const void* x, const float* ln_w, const float* ln_b, float eps, const float* Wr,
+                                 const float* br, const float* noise, const float* noise_scale, float* lclean, float* logits,
+                                 float* gates, int32_t* idx, float* probs, float* w, float* lse, float* stats_out, float* aux,
+                                 void* ws, size_t ws_bytes, int S, int Dm, int E, int K, int dtype, cudaStream_t stream) {
+    if (int e = check_router(S, Dm, E, K, dtype)) return e;
+    const FwdWs wl = fwd_ws(S, E);
+    AB_REQUIRE(ws && ws_bytes >= wl.total, "moe_router_fwd: workspace too small");
+    AB_REQUIRE(noise == nullptr || noise_scale != nullptr, "moe_router_fwd: noise without noise_scale");
+    const size_t smem = ((size_t)E * Dm + 32 + WARPS * (2 * E + 1)) * sizeof(float);
+    float* part = (float*)ws;
+#define AB_ROUTER_FWD(TT, EMV)                                                                                          \
+    {                                                                                                                    \
+        auto k = router_fwd_kernel<TT, EMV>;                                                                             \
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        k<<<wl.grid, WARPS * 32, smem, stream>>>((const TT*)x, ln_w, ln_b, eps, Wr, br, noise, noise_scale, lclean,     \
+                                                 logits, gates, idx, probs, w, lse, stats_out, part, S, Dm, E, K);      \
+    }
+    if (dtype == AB_F32) {
+        if (E <= 8) AB_ROUTER_FWD(float, 8) else if (E <= 16) AB_ROUTER_FWD(float, 16) else AB_ROUTER_FWD(float, 32)
+    } else {
+        if (E <= 8) AB_ROUTER_FWD(__nv_bfloat16, 8) else if (E <= 16) AB_ROUTER_FWD(__nv_bfloat16, 16) else AB_ROUTER_FWD(__nv_bfloat16, 32)
+    }
+#undef AB_ROUTER_FWD
+    AB_LAUNCH_CHECK();
+    reduce_rows_kernel<<<1, 128, 0, stream>>>(part, wl.grid, 2 * E + 1, aux);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" int ab_moe_topk_from_logits(const float* logits, float* gates, int32_t* idx, float* probs, float* w, float* lse,
+                                       int S, int E, int K, cudaStream_t stream) {
+    if (int e = check_router(S, 8, E, K, AB_F32)) return e;
+    topk_from_logits_kernel<<<router_grid(S), WARPS * 32, 0, stream>>>(logits, gates, idx, probs, w, lse, S, E, K);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+extern "C" size_t ab_moe_router_bwd_workspace_bytes(int S, int Dm, int E) { return bwd_ws(S, Dm, E).total; }
+
+extern "C" int ab_moe_router_bwd(const void* x, const float* stats, const float* ln_w, const float* ln_b, const float* Wr,
+                                 const float* br, const float* gates, const int32_t* idx, const float* probs, const float* lse,
+                                 const float* lclean, const float* noise, const float* f, const float* scal,
+                                 const float* dw_row, const float* dxrow, const int32_t* row_of, void* dx, float* dWr,
+                                 float* dbr, float* dln_w, float* dln_b, float* dnoise_scale, void* ws, size_t ws_bytes, int S,
+                                 int Dm, int E, int K, int dtype, cudaStream_t stream) {
+    if (int e = check_router(S, Dm, E, K, dtype)) return e;
+    AB_REQUIRE(Dm % 4 == 0, "moe_router_bwd: hidden size must be a multiple of 4");
+    const BwdWs wl = bwd_ws(S, Dm, E);
+    AB_REQUIRE(ws && ws_bytes >= wl.total, "moe_router_bwd: workspace too small");
+    unsigned char* w8 = (unsigned char*)ws;
+    float* part = (float*)(w8 + wl.part_off);
+    float* dl = (float*)(w8 + wl.dl_off);
+    float* qpart = (float*)(w8 + wl.q_off);
+    const size_t smem = ((size_t)E * Dm + Dm + 64 + WARPS * 2 * E) * sizeof(float);
+    dim3 qgrid((unsigned)ab_ceil_div(Dm, 256), wl.nqb);
+#define AB_ROUTER_BWD(TT, EMV)                                                                                          \
+    {                                                                                                                    \
+        auto k = router_bwd_kernel<TT, EMV>;                                                                             \
+        AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        k<<<wl.grid, WARPS * 32, smem, stream>>>((const TT*)x, stats, ln_w, ln_b, Wr, br, gates, idx, probs, lse,       \
+                                                 lclean, noise, f, scal, dw_row, dxrow, row_of, (TT*)dx, dl, part, S,   \
+                                                 Dm, E, K);                                                              \
+        AB_LAUNCH_CHECK();                                                                                               \
+        router_q_kernel<TT, EMV><<<qgrid, 256, 0, stream>>>((const TT*)x, stats, dl, qpart, S, Dm, E);                  \
+    }
+    if (dtype == AB_F32) {
+        if (E <= 8) AB_ROUTER_BWD(float, 8) else if (E <= 16) AB_ROUTER_BWD(float, 16) else AB_ROUTER_BWD(float, 32)
+    } else {
+        if (E <= 8) AB_ROUTER_BWD(__nv_bfloat16, 8) else if (E <= 16) AB_ROUTER_BWD(__nv_bfloat16, 16) else AB_ROUTER_BWD(__nv_bfloat16, 32)
+    }
+#undef AB_ROUTER_BWD
+    AB_LAUNCH_CHECK();
+    router_param_kernel<<<(unsigned)ab_ceil_div(Dm, 128), 128, 0, stream>>>(qpart, wl.nqb, part, wl.grid, ln_w, ln_b, Wr, dWr, dbr,
+                                                                           dln_w, dln_b, dnoise_scale, Dm, E);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}

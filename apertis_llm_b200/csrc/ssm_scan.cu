@@ -1,0 +1,822 @@
+// Chunked selective scan, forward and recompute-based backward (sm_100a).
+//
+// Replaces core.py:324-353 (both scan formulations), :383 (softplus), :394-396 (transpose copy, D skip,
+// SiLU(z) gate) and their autograd.  Math per channel c = head*16 + n (fp32 throughout):
+//     delta = softplus(dlog[b,t,head]);  abar = exp2(A2[c] * delta),  A2 = -exp(A_log[c]) * log2(e)
+//     s_t = abar_t * s_{t-1} + Bm_t ;  y_ssm = Cm_t * s_t ;  y = (y_ssm + D * xa_t) * silu(z_t)
+//
+// Decomposition.  Tensors are [B, L, Di] channels-last.  A tile is `T` consecutive tokens x `Cs`
+// channels of one sequence; its operands are staged in shared memory by TMA (3-D tiled maps, OOB rows
+// zero-filled, completion on an mbarrier).  Inside the tile a thread owns one channel vector and a run
+// of TS=4 tokens; run aggregates (P = prod abar, S = state contribution) are combined across runs in
+// shared memory.  Across tiles of a sequence the incoming state is resolved
+//   * single pass: each tile publishes (P, S) per channel as two self-validating 64-bit words
+//     {epoch|status, fp32}, then walks back over its predecessors with a window of LB_W speculative
+//     loads (decoupled look-back); it overwrites S with the inclusive state when known.  Tiles take
+//     their id from an atomic ticket so every predecessor is already resident or finished.
+//   * two pass: aggregate kernel -> sequential combine kernel -> apply kernel.
+// The backward recomputes the in-tile states from the saved per-tile incoming state (hstart) and runs
+// the same machinery in reverse time for G_t = g_t + abar_{t+1} G_{t+1}.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TS = 4;            // tokens per thread run
+constexpr int LB_W = 8;          // look-back window (speculative loads in flight)
+constexpr int MODE_FUSED = 0, MODE_AGG = 1, MODE_APPLY = 2;
+constexpr uint32_t ST_AGG = 1, ST_INCL = 2;
+constexpr int SPIN_LIMIT = 1 << 24;
+
+struct ScanTiling {
+    int V_f, V_b;     // channel-vector width of the forward / backward kernels
+    int Cs, T, n_s;   // slab channels, tile rows, runs per tile
+    int nslab, nchunks;
+    int esize;
+};
+
+int make_tiling(int L, int Di, int dtype, ScanTiling& t) {
+    t.esize = dtype == AB_F32 ? 4 : 2;
+    t.V_f = 16 / t.esize;
+    t.V_b = 4;
+    const int unit = t.V_f > t.V_b ? t.V_f : t.V_b;
+    int Cs = 0;
+    for (int k = Di / unit; k >= 1; --k) {           // smallest slab first
+        if (Di % k) continue;
+        const int c = Di / k;
+        if (c % unit) continue;
+        if (c * t.esize >= 128 && c <= 256) { Cs = c; break; }
+    }
+    if (!Cs) {
+        if (Di % unit == 0 && Di <= 256) Cs = Di;    // narrow model: one slab
+        else return 0;
+    }
+    t.Cs = Cs;
+    t.nslab = Di / Cs;
+    int T = (56 * 1024) / (5 * Cs * t.esize);
+    const int Tthr = (256 * TS * t.V_b) / Cs;
+    if (T > Tthr) T = Tthr;
+    if (T > 256) T = 256;
+    const int Lr = (int)ab_round_up(L, TS);
+    if (T > Lr) T = Lr;
+    T = (T / TS) * TS;
+    if (T < TS) T = TS;
+    t.T = T;
+    t.n_s = T / TS;
+    t.nchunks = (int)ab_ceil_div(L, T);
+    return 1;
+}
+
+struct ScanParams {
+    int B, L, Di, H;
+    int Cs, T, n_s, nslab, nchunks, nchains;
+    const void* dlog;        // [B, L, H] activation dtype
+    const float* A_log;      // [Di]
+    const float* Dp;         // [Di]
+    const float* h0;         // [B, Di] or null
+    void* y; void* y_ssm;    // [B, L, Di]
+    float* h_last;           // [B, Di] or null
+    float* hstart;           // [B, nchunks, Di] or null
+    unsigned long long* words;   // [nchains*nchunks][Cs][2]
+    unsigned int* ticket;
+    unsigned int* err_flag;
+    float* aggP; float* aggS;    // two-pass: [nchains*nchunks][Cs]
+    uint32_t epoch;
+    // backward only
+    const void* dyssm;       // optional grad of y_ssm, [B, L, Di]
+    void* dxa; void* dBm; void* dCm; void* dz; int64_t dbc_stride;
+    float* ddlog_parts;      // [B, L, Di / V_b]
+    float* part;             // [ntiles][2][Cs] partial dA_log / dD sums
+};
+
+__device__ __forceinline__ unsigned long long pack_word(uint32_t epoch, uint32_t st, float v) {
+    return ((unsigned long long)((epoch << 2) | st) << 32) | (unsigned long long)__float_as_uint(v);
+}
+
+// Walks the chain of already-published tiles.  `dir` = -1 walks towards chunk 0 (forward scan),
+// +1 towards the last chunk (reverse scan).  Returns the state entering this tile.
+__device__ __forceinline__ float lookback(const ScanParams& p, int chain, int j, int c, int dir, float boundary,
+                                          unsigned int* err_flag) {
+    float accP = 1.f, accS = 0.f;
+    int q = j + dir;
+    const int last = dir < 0 ? -1 : p.nchunks;
+    int spins = 0;
+    while (true) {
+        unsigned long long wP[LB_W], wS[LB_W];
+#pragma unroll
+        for (int k = 0; k < LB_W; ++k) {
+            const int qq = q + dir * k;
+            if (qq != last && (dir < 0 ? qq > last : qq < last)) {
+                const unsigned long long* w = p.words + (((size_t)chain * p.nchunks + qq) * p.Cs + c) * 2;
+                wP[k] = ab_ld_relaxed_u64(w);
+                wS[k] = ab_ld_relaxed_u64(w + 1);
+            } else { wP[k] = 0; wS[k] = 0; }
+        }
+#pragma unroll
+        for (int k = 0; k < LB_W; ++k) {
+            const int qq = q + dir * k;
+            if (dir < 0 ? qq <= last : qq >= last) return fmaf(accP, boundary, accS);
+            const unsigned long long* w = p.words + (((size_t)chain * p.nchunks + qq) * p.Cs + c) * 2;
+            unsigned long long s = wS[k];
+            while ((uint32_t)(s >> 34) != p.epoch) {
+                if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1u); return 0.f; }
+                s = ab_ld_relaxed_u64(w + 1);
+            }
+            const float sv = __uint_as_float((uint32_t)s);
+            if (((uint32_t)(s >> 32) & 3u) == ST_INCL) return fmaf(accP, sv, accS);
+            unsigned long long pw = wP[k];
+            while ((uint32_t)(pw >> 34) != p.epoch) {
+                if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1u); return 0.f; }
+                pw = ab_ld_relaxed_u64(w);
+            }
+            accS = fmaf(accP, sv, accS);
+            accP *= __uint_as_float((uint32_t)pw);
+        }
+        q += dir * LB_W;
+    }
+}
+
+// softplus'd delta rows of this tile (plus one extra row for the reverse scan) into shared memory
+template <typename T>
+__device__ __forceinline__ void stage_delta(const ScanParams& p, float* sdel, int b, int row0, int nrows, int h_lo, int nh) {
+    const T* dl = reinterpret_cast<const T*>(p.dlog);
+    for (int i = threadIdx.x; i < nrows * nh; i += blockDim.x) {
+        const int r = i / nh, hh = i % nh;
+        const int row = row0 + r;
+        float d = 0.f;
+        if (row < p.L && h_lo + hh < p.H) d = ab_softplus(ab_to_float(dl[((size_t)b * p.L + row) * p.H + h_lo + hh]));
+        sdel[i] = d;
+    }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void lds_vec(const T* p, float* f) {
+    if constexpr (sizeof(T) * V == 16) {
+        ab_vec16<T>::unpack(*reinterpret_cast<const uint4*>(p), f);
+    } else {   // 4 x bf16 = 8 bytes
+        const uint2 r = *reinterpret_cast<const uint2*>(p);
+        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+}
+template <typename T, int V>
+__device__ __forceinline__ void st_vec(T* p, const float* f) {
+    if constexpr (sizeof(T) * V == 16) {
+        *reinterpret_cast<uint4*>(p) = ab_vec16<T>::pack(f);
+    } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b2 = __floats2bfloat162_rn(f[2], f[3]);
+        uint2 r; r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b2);
+        *reinterpret_cast<uint2*>(p) = r;
+    }
+}
+template <typename T, int V>
+__device__ __forceinline__ void ldg_vec(const T* p, float* f) {
+    if constexpr (sizeof(T) * V == 16) {
+        ab_vec16<T>::unpack(__ldg(reinterpret_cast<const uint4*>(p)), f);
+    } else {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// smem: [tiles: nT x T x Cs of T] [sdel: (T+1) x nh] [sP: n_s x Cs] [sS: n_s x Cs] [hT: Cs] [bar] [tile id]
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
+                                                       const __grid_constant__ CUtensorMap tm_b,
+                                                       const __grid_constant__ CUtensorMap tm_c,
+                                                       const __grid_constant__ CUtensorMap tm_z, const ScanParams p) {
+    constexpr int V = 16 / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Cs = p.Cs, Tt = p.T, n_s = p.n_s;
+    const size_t tile_bytes = (size_t)Tt * Cs * sizeof(T);
+    const size_t pitch = (tile_bytes + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
+    constexpr int n_tiles_staged = MODE == MODE_AGG ? 1 : 4; // the aggregate pass only needs Bm
+    T* s_b = reinterpret_cast<T*>(smem);
+    T* s_xa = reinterpret_cast<T*>(smem + pitch);
+    T* s_c = reinterpret_cast<T*>(smem + 2 * pitch);
+    T* s_z = reinterpret_cast<T*>(smem + 3 * pitch);
+    float* sdel = reinterpret_cast<float*>(smem + (size_t)n_tiles_staged * pitch);
+    const int nh_max = Cs / 16 + 2;
+    float* sP = sdel + (size_t)(Tt + 1) * nh_max;
+    float* sS = sP + (size_t)n_s * Cs;
+    float* hT = sS + (size_t)n_s * Cs;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + Cs + (((uintptr_t)(hT + Cs)) % 8 ? 1 : 0));
+    __shared__ unsigned int s_ticket;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        if (MODE == MODE_FUSED) s_ticket = atomicAdd(p.ticket, 1u); else s_ticket = blockIdx.x;
+        ab_mbar_init(bar, 1);
+        ab_fence_mbar_init();
+    }
+    __syncthreads();
+    const int ticket = (int)s_ticket;
+    const int chain = ticket % p.nchains, j = ticket / p.nchains;
+    const int slab = chain % p.nslab, b = chain / p.nslab;
+    const int c0 = slab * Cs, row0 = j * Tt;
+    const int h_lo = c0 / 16;
+    const int nh = (c0 + Cs - 1) / 16 - h_lo + 1;
+
+    if (tid == 0) {
+        ab_mbar_expect_tx(bar, (uint32_t)(n_tiles_staged * tile_bytes));
+        ab_tma_load_3d(s_b, &tm_b, bar, c0, row0, b);
+        if (MODE != MODE_AGG) {
+            ab_tma_load_3d(s_xa, &tm_xa, bar, c0, row0, b);
+            ab_tma_load_3d(s_c, &tm_c, bar, c0, row0, b);
+            ab_tma_load_3d(s_z, &tm_z, bar, c0, row0, b);
+        }
+    }
+    stage_delta<T>(p, sdel, b, row0, Tt, h_lo, nh);
+
+    const int ncv = Cs / V;
+    const int i_run = tid / ncv, cv = tid % ncv;       // blockDim.x == n_s * ncv
+    const int cl = cv * V;                             // channel offset inside the slab
+    const int hh = (c0 + cl) / 16 - h_lo;              // head slot of this thread's channels (V divides 16)
+    float A2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) A2[v] = -__expf(__ldg(p.A_log + c0 + cl + v)) * AB_LOG2E;
+
+    __syncthreads();            // sdel visible
+    ab_mbar_wait(bar, 0);       // TMA tiles landed
+
+    // ---- sweep 1: per-run decay factors and aggregates
+    float a[TS][V];
+    {
+        float P[V], S[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { P[v] = 1.f; S[v] = 0.f; }
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+            const int r = i_run * TS + t;
+            const float d = sdel[r * nh + hh];
+            float bv[V];
+            lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                a[t][v] = ab_ex2(A2[v] * d);
+                P[v] *= a[t][v];
+                S[v] = fmaf(a[t][v], S[v], bv[v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { sP[i_run * Cs + cl + v] = P[v]; sS[i_run * Cs + cl + v] = S[v]; }
+    }
+    __syncthreads();
+
+    // ---- tile aggregate, publish, resolve incoming state (one thread per channel)
+    const size_t tile_lin = (size_t)chain * p.nchunks + j;
+    for (int c = tid; c < Cs; c += blockDim.x) {
+        float Pt = 1.f, St = 0.f;
+        for (int i = 0; i < n_s; ++i) { St = fmaf(St, sP[i * Cs + c], sS[i * Cs + c]); Pt *= sP[i * Cs + c]; }
+        float hin;
+        if (MODE == MODE_AGG) {
+            p.aggP[tile_lin * Cs + c] = Pt;
+            p.aggS[tile_lin * Cs + c] = St;
+            continue;
+        } else if (MODE == MODE_APPLY) {
+            hin = p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
+        } else {
+            unsigned long long* w = p.words + (tile_lin * Cs + c) * 2;
+            const float bnd = p.h0 ? __ldg(p.h0 + (size_t)b * p.Di + c0 + c) : 0.f;
+            if (j == 0) {
+                hin = bnd;
+            } else {
+                ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
+                ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
+                hin = lookback(p, chain, j, c, -1, bnd, p.err_flag);
+            }
+            ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_INCL, fmaf(Pt, hin, St)));
+            if (p.hstart) p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c] = hin;
+        }
+        hT[c] = hin;
+        if (p.h_last && j == p.nchunks - 1) p.h_last[(size_t)b * p.Di + c0 + c] = fmaf(Pt, hin, St);
+    }
+    if (MODE == MODE_AGG) return;
+    __syncthreads();
+
+    // ---- state entering this thread's run, then sweep 2
+    float h[V], Dv[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { h[v] = hT[cl + v]; Dv[v] = __ldg(p.Dp + c0 + cl + v); }
+    for (int i = 0; i < i_run; ++i) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) h[v] = fmaf(h[v], sP[i * Cs + cl + v], sS[i * Cs + cl + v]);
+    }
+    T* yo = reinterpret_cast<T*>(p.y);
+    T* yso = reinterpret_cast<T*>(p.y_ssm);
+#pragma unroll
+    for (int t = 0; t < TS; ++t) {
+        const int r = i_run * TS + t;
+        const int row = row0 + r;
+        float bv[V], cvv[V], xv[V], zv[V], o[V], os[V];
+        lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
+        lds_vec<T, V>(s_c + (size_t)r * Cs + cl, cvv);
+        lds_vec<T, V>(s_xa + (size_t)r * Cs + cl, xv);
+        lds_vec<T, V>(s_z + (size_t)r * Cs + cl, zv);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            h[v] = fmaf(a[t][v], h[v], bv[v]);
+            os[v] = cvv[v] * h[v];
+            o[v] = fmaf(Dv[v], xv[v], os[v]) * (zv[v] * ab_sigmoid(zv[v]));
+        }
+        if (row < p.L) {
+            const size_t off = ((size_t)b * p.L + row) * p.Di + c0 + cl;
+            st_vec<T, V>(yo + off, o);
+            if (yso) st_vec<T, V>(yso + off, os);
+        }
+    }
+}
+
+// two-pass: hstart[b][j][c] for all j, sequential over chunks (forward direction) or reversed
+__global__ void scan_combine_kernel(const float* __restrict__ aggP, const float* __restrict__ aggS,
+                                    const float* __restrict__ h0, float* __restrict__ hstart, float* __restrict__ h_last,
+                                    int B, int Di, int Cs, int nslab, int nchunks, int reverse) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B * Di) return;
+    const int b = g / Di, cg = g % Di;
+    const int slab = cg / Cs, c = cg % Cs;
+    const int chain = b * nslab + slab;
+    float h = (!reverse && h0) ? h0[(size_t)b * Di + cg] : 0.f;
+    for (int jj = 0; jj < nchunks; ++jj) {
+        const int j = reverse ? nchunks - 1 - jj : jj;
+        hstart[((size_t)b * nchunks + j) * Di + cg] = h;
+        const size_t o = ((size_t)chain * nchunks + j) * Cs + c;
+        h = fmaf(aggP[o], h, aggS[o]);
+    }
+    if (h_last) h_last[(size_t)b * Di + cg] = h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (V = 4 channels per thread for both dtypes)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
+                                                       const __grid_constant__ CUtensorMap tm_b,
+                                                       const __grid_constant__ CUtensorMap tm_c,
+                                                       const __grid_constant__ CUtensorMap tm_z,
+                                                       const __grid_constant__ CUtensorMap tm_do, const ScanParams p,
+                                                       float* __restrict__ gin_ws) {
+    constexpr int V = 4;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Cs = p.Cs, Tt = p.T, n_s = p.n_s;
+    const size_t tile_bytes = (size_t)Tt * Cs * sizeof(T);
+    const size_t pitch = (tile_bytes + 127) / 128 * 128;
+    T* s_b = reinterpret_cast<T*>(smem);
+    T* s_c = reinterpret_cast<T*>(smem + pitch);
+    T* s_z = reinterpret_cast<T*>(smem + 2 * pitch);
+    T* s_do = reinterpret_cast<T*>(smem + 3 * pitch);
+    T* s_xa = reinterpret_cast<T*>(smem + 4 * pitch);
+    const int n_staged = MODE == MODE_AGG ? 4 : 5;
+    const int nh_max = Cs / 16 + 2;
+    float* sdel = reinterpret_cast<float*>(smem + 5 * pitch);
+    float* sP = sdel + (size_t)(Tt + 1) * nh_max;
+    float* sS = sP + (size_t)n_s * Cs;
+    float* hT = sS + (size_t)n_s * Cs;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + Cs + (((uintptr_t)(hT + Cs)) % 8 ? 1 : 0));
+    __shared__ unsigned int s_ticket;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        if (MODE == MODE_FUSED) s_ticket = atomicAdd(p.ticket, 1u); else s_ticket = blockIdx.x;
+        ab_mbar_init(bar, 1);
+        ab_fence_mbar_init();
+    }
+    __syncthreads();
+    const int ticket = (int)s_ticket;
+    const int chain = ticket % p.nchains;
+    const int j = p.nchunks - 1 - ticket / p.nchains;       // reverse time order
+    const int slab = chain % p.nslab, b = chain / p.nslab;
+    const int c0 = slab * Cs, row0 = j * Tt;
+    const int h_lo = c0 / 16;
+    const int nh = (c0 + Cs - 1) / 16 - h_lo + 1;
+
+    if (tid == 0) {
+        ab_mbar_expect_tx(bar, (uint32_t)(n_staged * tile_bytes));
+        ab_tma_load_3d(s_b, &tm_b, bar, c0, row0, b);
+        ab_tma_load_3d(s_c, &tm_c, bar, c0, row0, b);
+        ab_tma_load_3d(s_z, &tm_z, bar, c0, row0, b);
+        ab_tma_load_3d(s_do, &tm_do, bar, c0, row0, b);
+        if (MODE != MODE_AGG) ab_tma_load_3d(s_xa, &tm_xa, bar, c0, row0, b);
+    }
+    stage_delta<T>(p, sdel, b, row0, Tt + 1, h_lo, nh);
+
+    const int ncv = Cs / V;
+    const int i_run = tid / ncv, cv = tid % ncv;
+    const int cl = cv * V;
+    const int hh = (c0 + cl) / 16 - h_lo;
+    float A2[V], Dv[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        A2[v] = -__expf(__ldg(p.A_log + c0 + cl + v)) * AB_LOG2E;
+        Dv[v] = __ldg(p.Dp + c0 + cl + v);
+    }
+    if (MODE != MODE_AGG)
+        for (int c = tid; c < Cs; c += blockDim.x) hT[c] = p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
+
+    __syncthreads();
+    ab_mbar_wait(bar, 0);
+
+    // ---- F1: decay factors + forward run aggregates
+    float a[TS][V];
+    float dl[TS];
+    {
+        float P[V], S[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { P[v] = 1.f; S[v] = 0.f; }
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+            const int r = i_run * TS + t;
+            dl[t] = sdel[r * nh + hh];
+            float bv[V];
+            lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                a[t][v] = ab_ex2(A2[v] * dl[t]);
+                P[v] *= a[t][v];
+                S[v] = fmaf(a[t][v], S[v], bv[v]);
+            }
+        }
+        if (MODE != MODE_AGG) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) { sP[i_run * Cs + cl + v] = P[v]; sS[i_run * Cs + cl + v] = S[v]; }
+        }
+    }
+    float anext[V];
+    {
+        const float dn = sdel[(i_run * TS + TS) * nh + hh];
+#pragma unroll
+        for (int v = 0; v < V; ++v) anext[v] = ab_ex2(A2[v] * dn);
+    }
+    __syncthreads();
+
+    // ---- F2: recompute states, emit dxa / dCm / dz, keep hprev and g
+    float hprev[TS][V], g[TS][V];
+    float accD[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) accD[v] = 0.f;
+    {
+        float h[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) h[v] = MODE != MODE_AGG ? hT[cl + v] : 0.f;
+        if (MODE != MODE_AGG) {
+            for (int i = 0; i < i_run; ++i) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) h[v] = fmaf(h[v], sP[i * Cs + cl + v], sS[i * Cs + cl + v]);
+            }
+        }
+        T* dxa_o = reinterpret_cast<T*>(p.dxa);
+        T* dc_o = reinterpret_cast<T*>(p.dCm);
+        T* dz_o = reinterpret_cast<T*>(p.dz);
+        const T* dys_i = reinterpret_cast<const T*>(p.dyssm);
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+            const int r = i_run * TS + t;
+            const int row = row0 + r;
+            float bv[V], cvv[V], zv[V], dov[V], xv[V], dys[V];
+            lds_vec<T, V>(s_c + (size_t)r * Cs + cl, cvv);
+            lds_vec<T, V>(s_z + (size_t)r * Cs + cl, zv);
+            lds_vec<T, V>(s_do + (size_t)r * Cs + cl, dov);
+#pragma unroll
+            for (int v = 0; v < V; ++v) dys[v] = 0.f;
+            if (dys_i && row < p.L) ldg_vec<T, V>(dys_i + ((size_t)b * p.L + row) * p.Di + c0 + cl, dys);
+            if (MODE != MODE_AGG) {
+                lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
+                lds_vec<T, V>(s_xa + (size_t)r * Cs + cl, xv);
+            }
+            float o_dxa[V], o_dc[V], o_dz[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float sg = ab_sigmoid(zv[v]);
+                const float gate = zv[v] * sg;
+                const float dyv = dov[v] * gate;           // grad of (y_ssm + D*xa)
+                const float dtot = dyv + dys[v];           // grad of y_ssm
+                g[t][v] = dtot * cvv[v];
+                if (MODE != MODE_AGG) {
+                    hprev[t][v] = h[v];
+                    h[v] = fmaf(a[t][v], h[v], bv[v]);
+                    const float yv = fmaf(Dv[v], xv[v], cvv[v] * h[v]);
+                    o_dxa[v] = dyv * Dv[v];
+                    o_dc[v] = dtot * h[v];
+                    o_dz[v] = dov[v] * yv * (sg * fmaf(zv[v], 1.f - sg, 1.f));
+                    accD[v] = fmaf(dyv, xv[v], accD[v]);
+                }
+            }
+            if (MODE != MODE_AGG && row < p.L) {
+                const size_t off = ((size_t)b * p.L + row) * p.Di + c0 + cl;
+                st_vec<T, V>(dxa_o + off, o_dxa);
+                st_vec<T, V>(dz_o + off, o_dz);
+                st_vec<T, V>(dc_o + ((size_t)b * p.L + row) * p.dbc_stride + c0 + cl, o_dc);
+            }
+        }
+    }
+    __syncthreads();     // all forward-prefix reads of sP/sS done before they are reused
+
+    // ---- reverse run aggregates:  G(run start) = Sr + Pr * G(next run start)
+    {
+        float Gs[V], Pr[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            Gs[v] = g[TS - 1][v];
+            Pr[v] = anext[v];
+        }
+#pragma unroll
+        for (int t = TS - 2; t >= 0; --t) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                Gs[v] = fmaf(a[t + 1][v], Gs[v], g[t][v]);
+                Pr[v] *= a[t + 1][v];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { sP[i_run * Cs + cl + v] = Pr[v]; sS[i_run * Cs + cl + v] = Gs[v]; }
+    }
+    __syncthreads();
+
+    const size_t tile_lin = (size_t)chain * p.nchunks + j;
+    for (int c = tid; c < Cs; c += blockDim.x) {
+        float Pt = 1.f, St = 0.f;
+        for (int i = n_s - 1; i >= 0; --i) { St = fmaf(St, sP[i * Cs + c], sS[i * Cs + c]); Pt *= sP[i * Cs + c]; }
+        float gin;
+        if (MODE == MODE_AGG) {
+            p.aggP[tile_lin * Cs + c] = Pt;
+            p.aggS[tile_lin * Cs + c] = St;
+            continue;
+        } else if (MODE == MODE_APPLY) {
+            gin = gin_ws[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
+        } else {
+            unsigned long long* w = p.words + (tile_lin * Cs + c) * 2;
+            if (j == p.nchunks - 1) {
+                gin = 0.f;
+            } else {
+                ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
+                ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
+                gin = lookback(p, chain, j, c, +1, 0.f, p.err_flag);
+            }
+            ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_INCL, fmaf(Pt, gin, St)));
+        }
+        hT[c] = gin;
+    }
+    if (MODE == MODE_AGG) return;
+    __syncthreads();
+
+    // ---- G entering this run from later runs, then the reverse sweep
+    float accA[V];
+    {
+        float G[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { G[v] = hT[cl + v]; accA[v] = 0.f; }
+        for (int i = n_s - 1; i > i_run; --i) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) G[v] = fmaf(G[v], sP[i * Cs + cl + v], sS[i * Cs + cl + v]);
+        }
+        float q[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) q[v] = anext[v] * G[v];
+        T* db_o = reinterpret_cast<T*>(p.dBm);
+        const int nparts = p.Di / V;
+#pragma unroll
+        for (int t = TS - 1; t >= 0; --t) {
+            const int row = row0 + i_run * TS + t;
+            float o_db[V];
+            float dd = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float Gt = g[t][v] + q[v];
+                o_db[v] = Gt;
+                const float e = Gt * hprev[t][v] * a[t][v];      // d abar * abar
+                dd = fmaf(e, A2[v], dd);
+                accA[v] = fmaf(e, dl[t], accA[v]);
+                q[v] = a[t][v] * Gt;
+            }
+            if (row < p.L) {
+                st_vec<T, V>(db_o + ((size_t)b * p.L + row) * p.dbc_stride + c0 + cl, o_db);
+                // d delta = sum_n e * A  (A = A2 / log2e);  d dlog = d delta * sigmoid(dlog) = d delta * (1 - exp(-delta))
+                const float sp = 1.f - __expf(-dl[t]);
+                p.ddlog_parts[((size_t)b * p.L + row) * nparts + (c0 + cl) / V] = dd * (1.f / AB_LOG2E) * sp;
+            }
+        }
+    }
+    __syncthreads();     // reverse-prefix reads of sP/sS done
+    // ---- per-tile partial sums of dA_log (= A * sum e*delta) and dD
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        sP[i_run * Cs + cl + v] = accA[v] * A2[v] * (1.f / AB_LOG2E);
+        sS[i_run * Cs + cl + v] = accD[v];
+    }
+    __syncthreads();
+    for (int c = tid; c < Cs; c += blockDim.x) {
+        float sa = 0.f, sd = 0.f;
+        for (int i = 0; i < n_s; ++i) { sa += sP[i * Cs + c]; sd += sS[i * Cs + c]; }
+        p.part[(tile_lin * 2 + 0) * Cs + c] = sa;
+        p.part[(tile_lin * 2 + 1) * Cs + c] = sd;
+    }
+}
+
+// dA_log[c], dD[c] = sum over (b, j) of the tile partials, fixed order
+__global__ void scan_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dA, float* __restrict__ dD,
+                                         int B, int Di, int Cs, int nslab, int nchunks) {
+    const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cg >= Di) return;
+    const int slab = cg / Cs, c = cg % Cs;
+    float sa = 0.f, sd = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const int chain = b * nslab + slab;
+        for (int j = 0; j < nchunks; ++j) {
+            const size_t tl = (size_t)chain * nchunks + j;
+            sa += part[(tl * 2 + 0) * Cs + c];
+            sd += part[(tl * 2 + 1) * Cs + c];
+        }
+    }
+    dA[cg] = sa;
+    dD[cg] = sd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct WsLayout {
+    size_t off_ticket, off_err, off_words, off_aggP, off_aggS, off_gin, off_part, total;
+};
+WsLayout ws_layout(const ScanTiling& t, int B, int Di) {
+    WsLayout w;
+    const size_t ntiles = (size_t)B * t.nslab * t.nchunks;
+    size_t o = 0;
+    w.off_ticket = o; o += 64;
+    w.off_err = o; o += 64;
+    w.off_words = o; o += ntiles * t.Cs * 2 * sizeof(unsigned long long);
+    w.off_aggP = o; o += ntiles * t.Cs * sizeof(float);
+    w.off_aggS = o; o += ntiles * t.Cs * sizeof(float);
+    w.off_gin = o; o += (size_t)B * t.nchunks * Di * sizeof(float);
+    w.off_part = o; o += ntiles * 2 * t.Cs * sizeof(float);
+    w.total = ab_round_up((int64_t)o, 256);
+    return w;
+}
+
+int make_map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di, int64_t row_stride, int Cs, int T) {
+    const int es = dtype == AB_F32 ? 4 : 2;
+    AB_REQUIRE(((uintptr_t)base % 16) == 0 && (row_stride * es) % 16 == 0,
+               "selective_scan: tensor base and row stride must be 16-byte aligned for TMA (stride %lld elems)", (long long)row_stride);
+    uint64_t dims[3] = {(uint64_t)Di, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)row_stride * es, (uint64_t)row_stride * es * L};
+    uint32_t box[3] = {(uint32_t)Cs, (uint32_t)T, 1};
+    return ab_encode_tmap(m, dtype == AB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base,
+                          dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+size_t smem_bytes(const ScanTiling& t, int ntiles_staged_max) {
+    const size_t tile_bytes = (size_t)t.T * t.Cs * t.esize;
+    const size_t pitch = (tile_bytes + 127) / 128 * 128;
+    const int nh_max = t.Cs / 16 + 2;
+    size_t o = ntiles_staged_max * pitch;
+    o += (size_t)(t.T + 1) * nh_max * 4;
+    o += (size_t)2 * t.n_s * t.Cs * 4;
+    o += (size_t)t.Cs * 4 + 8 + 16;
+    return o;
+}
+
+template <typename T, int MODE>
+int launch_fwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
+    const size_t smem = smem_bytes(t, n_staged);
+    auto kfn = scan_fwd_kernel<T, MODE>;
+    AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = t.n_s * (t.Cs / (16 / (int)sizeof(T)));
+    const unsigned grid = (unsigned)(p.nchains * p.nchunks);
+    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+template <typename T, int MODE>
+int launch_bwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, float* gin, cudaStream_t st) {
+    const size_t smem = smem_bytes(t, 5);
+    auto kfn = scan_bwd_kernel<T, MODE>;
+    AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = t.n_s * (t.Cs / 4);
+    const unsigned grid = (unsigned)(p.nchains * p.nchunks);
+    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p, gin);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+int check_common(int B, int L, int Di, int H, int dtype, ScanTiling& t) {
+    AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "selective_scan: bad dtype %d", dtype);
+    AB_REQUIRE(B > 0 && L > 0 && Di > 0 && H > 0 && Di == H * 16, "selective_scan: need Di == 16*H (ssm_d_state 16); got Di=%d H=%d", Di, H);
+    AB_REQUIRE(make_tiling(L, Di, dtype, t), "selective_scan: no tiling for Di=%d", Di);
+    return AB_OK;
+}
+
+}  // namespace
+
+extern "C" int ab_selective_scan_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_chunks,
+                                      size_t* ws_bytes) {
+    ScanTiling t;
+    AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "selective_scan_plan: bad dtype");
+    AB_REQUIRE(B > 0 && L > 0 && Di > 0 && make_tiling(L, Di, dtype, t), "selective_scan_plan: no tiling for Di=%d", Di);
+    if (tile_rows) *tile_rows = t.T;
+    if (slab) *slab = t.Cs;
+    if (n_chunks) *n_chunks = t.nchunks;
+    if (ws_bytes) *ws_bytes = ws_layout(t, B, Di).total;
+    return AB_OK;
+}
+
+extern "C" int ab_selective_scan_fwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride,
+                                     const void* z, int64_t z_stride, const float* A_log, const float* D, const float* h0,
+                                     void* y, void* y_ssm, float* h_last, float* hstart, void* ws, size_t ws_bytes,
+                                     uint32_t epoch, int mode, int B, int L, int Di, int H, int dtype, cudaStream_t stream) {
+    ScanTiling t;
+    if (int e = check_common(B, L, Di, H, dtype, t)) return e;
+    const WsLayout wl = ws_layout(t, B, Di);
+    AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_fwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
+    AB_REQUIRE(mode == AB_SCAN_SINGLE_PASS || mode == AB_SCAN_TWO_PASS, "selective_scan_fwd: bad mode %d", mode);
+    AB_REQUIRE(mode == AB_SCAN_SINGLE_PASS ? (epoch > 0 && epoch < (1u << 30)) : hstart != nullptr,
+               "selective_scan_fwd: single-pass needs 0 < epoch < 2^30; two-pass needs hstart");
+    CUtensorMap maps[4];
+    if (int e = make_map3(&maps[0], xa, dtype, B, L, Di, Di, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[1], Bm, dtype, B, L, Di, bc_stride, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[2], Cm, dtype, B, L, Di, bc_stride, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[3], z, dtype, B, L, Di, z_stride, t.Cs, t.T)) return e;
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.L = L; p.Di = Di; p.H = H;
+    p.Cs = t.Cs; p.T = t.T; p.n_s = t.n_s; p.nslab = t.nslab; p.nchunks = t.nchunks; p.nchains = B * t.nslab;
+    p.dlog = dlog; p.A_log = A_log; p.Dp = D; p.h0 = h0; p.y = y; p.y_ssm = y_ssm; p.h_last = h_last; p.hstart = hstart;
+    unsigned char* w8 = (unsigned char*)ws;
+    p.ticket = (unsigned int*)(w8 + wl.off_ticket);
+    p.err_flag = (unsigned int*)(w8 + wl.off_err);
+    p.words = (unsigned long long*)(w8 + wl.off_words);
+    p.aggP = (float*)(w8 + wl.off_aggP);
+    p.aggS = (float*)(w8 + wl.off_aggS);
+    p.epoch = epoch;
+    const bool f32 = dtype == AB_F32;
+    if (mode == AB_SCAN_SINGLE_PASS) {
+        AB_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), stream));
+        return f32 ? launch_fwd_mode<float, MODE_FUSED>(maps, p, t, 4, stream)
+                   : launch_fwd_mode<__nv_bfloat16, MODE_FUSED>(maps, p, t, 4, stream);
+    }
+    if (int e = f32 ? launch_fwd_mode<float, MODE_AGG>(maps, p, t, 1, stream)
+                    : launch_fwd_mode<__nv_bfloat16, MODE_AGG>(maps, p, t, 1, stream)) return e;
+    scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, 128), 128, 0, stream>>>(p.aggP, p.aggS, h0, hstart, h_last, B, Di,
+                                                                                   t.Cs, t.nslab, t.nchunks, 0);
+    AB_LAUNCH_CHECK();
+    p.h_last = nullptr;
+    return f32 ? launch_fwd_mode<float, MODE_APPLY>(maps, p, t, 4, stream)
+               : launch_fwd_mode<__nv_bfloat16, MODE_APPLY>(maps, p, t, 4, stream);
+}
+
+extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride,
+                                     const void* z, int64_t z_stride, const void* dout, const void* dyssm,
+                                     const float* A_log, const float* D, const float* hstart, void* dxa, void* dBm,
+                                     void* dCm, int64_t dbc_stride, void* dz, float* ddlog_parts, float* dA_log, float* dD,
+                                     void* ws, size_t ws_bytes, uint32_t epoch, int mode, int B, int L, int Di, int H,
+                                     int dtype, cudaStream_t stream) {
+    ScanTiling t;
+    if (int e = check_common(B, L, Di, H, dtype, t)) return e;
+    const WsLayout wl = ws_layout(t, B, Di);
+    AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
+    AB_REQUIRE(hstart != nullptr, "selective_scan_bwd: hstart (saved by the forward) is required");
+    AB_REQUIRE(mode == AB_SCAN_SINGLE_PASS || mode == AB_SCAN_TWO_PASS, "selective_scan_bwd: bad mode %d", mode);
+    AB_REQUIRE(mode != AB_SCAN_SINGLE_PASS || (epoch > 0 && epoch < (1u << 30)), "selective_scan_bwd: need 0 < epoch < 2^30");
+    const int es = dtype == AB_F32 ? 4 : 2;
+    AB_REQUIRE((dbc_stride * es) % 8 == 0, "selective_scan_bwd: dB/dC row stride must be 8-byte aligned");
+    CUtensorMap maps[5];
+    if (int e = make_map3(&maps[0], xa, dtype, B, L, Di, Di, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[1], Bm, dtype, B, L, Di, bc_stride, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[2], Cm, dtype, B, L, Di, bc_stride, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[3], z, dtype, B, L, Di, z_stride, t.Cs, t.T)) return e;
+    if (int e = make_map3(&maps[4], dout, dtype, B, L, Di, Di, t.Cs, t.T)) return e;
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.L = L; p.Di = Di; p.H = H;
+    p.Cs = t.Cs; p.T = t.T; p.n_s = t.n_s; p.nslab = t.nslab; p.nchunks = t.nchunks; p.nchains = B * t.nslab;
+    p.dlog = dlog; p.A_log = A_log; p.Dp = D; p.hstart = const_cast<float*>(hstart);
+    p.dyssm = dyssm; p.dxa = dxa; p.dBm = dBm; p.dCm = dCm; p.dz = dz; p.dbc_stride = dbc_stride; p.ddlog_parts = ddlog_parts;
+    unsigned char* w8 = (unsigned char*)ws;
+    p.ticket = (unsigned int*)(w8 + wl.off_ticket);
+    p.err_flag = (unsigned int*)(w8 + wl.off_err);
+    p.words = (unsigned long long*)(w8 + wl.off_words);
+    p.aggP = (float*)(w8 + wl.off_aggP);
+    p.aggS = (float*)(w8 + wl.off_aggS);
+    p.part = (float*)(w8 + wl.off_part);
+    float* gin = (float*)(w8 + wl.off_gin);
+    p.epoch = epoch;
+    const bool f32 = dtype == AB_F32;
+    if (mode == AB_SCAN_SINGLE_PASS) {
+        AB_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), stream));
+        if (int e = f32 ? launch_bwd_mode<float, MODE_FUSED>(maps, p, t, gin, stream)
+                        : launch_bwd_mode<__nv_bfloat16, MODE_FUSED>(maps, p, t, gin, stream)) return e;
+    } else {
+        if (int e = f32 ? launch_bwd_mode<float, MODE_AGG>(maps, p, t, gin, stream)
+                        : launch_bwd_mode<__nv_bfloat16, MODE_AGG>(maps, p, t, gin, stream)) return e;
+        scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, 128), 128, 0, stream>>>(p.aggP, p.aggS, nullptr, gin, nullptr, B,
+                                                                                       Di, t.Cs, t.nslab, t.nchunks, 1);
+        AB_LAUNCH_CHECK();
+        if (int e = f32 ? launch_bwd_mode<float, MODE_APPLY>(maps, p, t, gin, stream)
+                        : launch_bwd_mode<__nv_bfloat16, MODE_APPLY>(maps, p, t, gin, stream)) return e;
+    }
+    scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, 128), 128, 0, stream>>>(p.part, dA_log, dD, B, Di, t.Cs, t.nslab, t.nchunks);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}

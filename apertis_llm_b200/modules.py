@@ -1,0 +1,365 @@
+"""Drop-in nn.Modules for the Apertis block hot path.
+
+``SelectiveLinearAttention`` and ``AdaptiveExpertSystem`` keep the reference's class names, constructor
+arguments, ``forward()`` signatures, return tuples and ``state_dict`` keys (core.py:295-401, 403-607), so
+``ApertisAttention`` / ``ApertisFeedForward`` (core.py:650, 861-865, 699-704, 894) can hold them unchanged.
+``patch_apertis_model`` swaps them into an existing reference ``ApertisModel`` in place.
+
+All arithmetic of the two layers runs in the sm_100a kernels behind the C ABI; the five SSM projection
+GEMMs stay plain library GEMMs (F.linear -> cuBLAS), everything else is hand-written CUDA.  There is no
+CPU / other-GPU fallback: calling these modules on a non-sm_100 device raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+
+
+@dataclass
+class BlockConfig:
+    """The subset of ApertisConfig (core.py:67-204) the hot path reads, with the reference's defaults."""
+    hidden_size: int = 768
+    num_attention_heads: int = 12
+    intermediate_size: int = 3072
+    hidden_act: str = "gelu"
+    hidden_dropout_prob: float = 0.1
+    layer_norm_eps: float = 1e-12
+    ssm_d_state: int = 16
+    ssm_dt_rank: Any = "auto"
+    ssm_conv_kernel: int = 4
+    num_experts: int = 8
+    experts_per_token: int = 2
+    load_balancing_loss_coef: float = 0.01
+    expert_capacity_factor: float = 1.25
+    noisy_routing_alpha: float = 0.1
+    expert_dropout_prob: float = 0.1
+    router_z_loss_coef: float = 0.001
+    use_noisy_top_k_routing: bool = True
+    use_expert_capacity_limit: bool = True
+    use_expert_dropout: bool = True
+    use_router_z_loss: bool = True
+    use_load_balancing_loss: bool = True
+    attention_type: str = "selective_ssm"
+    use_expert_system: bool = True
+    use_rmsnorm: bool = False
+
+    def __post_init__(self):
+        if self.ssm_dt_rank == "auto":
+            self.ssm_dt_rank = math.ceil(self.hidden_size / 16)      # core.py:163-164
+        self.ssm_d_inner = self.num_attention_heads * self.ssm_d_state  # core.py:154
+        self.experts_per_token = min(self.num_experts, self.experts_per_token)
+
+
+def _autocast_dtype(device_type: str = "cuda") -> Optional[torch.dtype]:
+    if not torch.is_autocast_enabled(device_type):
+        return None
+    d = torch.get_autocast_dtype(device_type)
+    if d == torch.float16:
+        raise NotImplementedError("apertis_llm_b200: fp16 autocast is not supported by the sm_100a kernels; "
+                                  "use torch.autocast('cuda', dtype=torch.bfloat16) or fp32")
+    return d
+
+
+# ================================================================================================
+# SSM layer
+# ================================================================================================
+class SelectiveLinearAttention(nn.Module):
+    """B200-native SelectiveLinearAttention (core.py:295-401): same parameters, same forward contract."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.d_state = config.ssm_d_state
+        self.d_inner = self.num_heads * self.d_state
+        self.dt_rank = config.ssm_dt_rank
+        self.conv_kernel_size = config.ssm_conv_kernel
+        if self.d_state != 16:
+            raise NotImplementedError("the selective-scan kernel is specialised for ssm_d_state == 16 (the reference default)")
+        self.in_proj_x = nn.Linear(self.hidden_size, self.d_inner, bias=False)
+        self.in_proj_z = nn.Linear(self.hidden_size, self.d_inner, bias=False)
+        self.conv1d = nn.Conv1d(self.d_inner, self.d_inner, kernel_size=self.conv_kernel_size, groups=self.d_inner,
+                                padding=self.conv_kernel_size - 1)
+        self.x_param_proj = nn.Linear(self.d_inner, self.dt_rank + 2 * self.d_inner, bias=False)
+        self.dt_proj_head = nn.Linear(self.dt_rank, self.num_heads, bias=True)
+        nn.init.uniform_(self.dt_proj_head.bias, a=math.log(1e-3), b=math.log(1e-2))          # core.py:315
+        self.A_log = nn.Parameter(torch.empty(self.num_heads, self.d_state))
+        nn.init.uniform_(self.A_log, a=math.log(0.5), b=math.log(0.99))                       # core.py:316-317
+        self.D = nn.Parameter(torch.ones(self.d_inner))
+        self.out_proj = nn.Linear(self.d_inner, self.hidden_size, bias=False)
+        self.use_cache = False
+        self.scan_mode: Optional[int] = None      # None = library default (single-pass look-back)
+
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None,
+                past_key_value: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                output_attentions: bool = False, use_cache: bool = False):
+        # attention_mask / position_ids are accepted and ignored, exactly like the reference (core.py:355-401)
+        _lib.ensure_device(hidden_states.device)
+        _autocast_dtype()
+        self.use_cache = use_cache
+        B, L, _ = hidden_states.shape
+        Di, R, Kc = self.d_inner, self.dt_rank, self.conv_kernel_size
+        conv_prev, h_prev = (past_key_value if past_key_value is not None else (None, None))
+        xp = self.in_proj_x(hidden_states)                                    # :366
+        z = self.in_proj_z(hidden_states)                                     # :367
+        x_seq = xp
+        if conv_prev is not None and use_cache and conv_prev.shape[1] == Di and conv_prev.shape[2] == Kc - 1:
+            x_seq = torch.cat([conv_prev.transpose(1, 2).to(xp.dtype), xp], dim=1)      # :369-371 (state goes in FRONT)
+        conv_state = x_seq[:, -(Kc - 1):, :].transpose(1, 2).detach() if use_cache else None   # :372
+        # the reference convolves the (possibly state-prefixed) sequence and keeps the FIRST L outputs (:373)
+        xa = ops.causal_conv1d_silu(x_seq, self.conv1d.weight, self.conv1d.bias)
+        if x_seq.shape[1] != L:
+            xa = xa[:, :L].contiguous()
+        wp = self.x_param_proj.weight
+        dtf = F.linear(xa, wp[:R])                                            # :376-381, as two GEMMs so that the
+        bc = F.linear(xa, wp[R:])                                             # B|C block is 16-byte aligned for TMA
+        dlog = self.dt_proj_head(dtf)                                         # :382
+        recurrent = not (self.training and not use_cache)                     # :388-393
+        h0 = h_prev if (recurrent and use_cache and h_prev is not None) else None
+        if not (xa.dtype == z.dtype == bc.dtype == dlog.dtype):
+            common = xa.dtype
+            z, bc, dlog = z.to(common), bc.to(common), dlog.to(common)
+        y, y_ssm, h_last = ops.selective_scan(xa, dlog, bc, z, self.A_log, self.D, h0=h0, want_yssm=output_attentions,
+                                              want_hlast=use_cache, mode=self.scan_mode)     # :389/391, :394-396
+        out = self.out_proj(y)                                                # :397
+        cache = None
+        if use_cache:
+            cache = (conv_state, h_last.view(B, self.num_heads, self.d_state).to(xa.dtype))      # :398-400
+        return out, (y_ssm if output_attentions else None), cache
+
+
+# ================================================================================================
+# MoE layer
+# ================================================================================================
+class AdaptiveExpertSystem(nn.Module):
+    """B200-native AdaptiveExpertSystem (core.py:403-607).
+
+    Expert parameters are stored stacked ([E, ...]) so that the grouped GEMM reads them in place; the
+    ``state_dict`` is translated to / from the reference's per-expert keys (``experts.{e}.0.weight`` ...
+    ``experts.{e}.4.bias``) so reference checkpoints load with ``strict=True`` and vice versa.
+    With ``ep_group`` (a torch.distributed process group) experts are sharded across ranks; see ep.py."""
+
+    _STACKED = {"expert_ln_weight": "0.weight", "expert_ln_bias": "0.bias", "expert_w1": "1.weight",
+                "expert_b1": "1.bias", "expert_w2": "4.weight", "expert_b2": "4.bias"}
+
+    def __init__(self, config, activation_function_override: Optional[str] = None, ep_group=None):
+        super().__init__()
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.intermediate_size = config.intermediate_size
+        self.num_experts = config.num_experts
+        self.experts_per_token = config.experts_per_token
+        self.ep_group = ep_group
+        self.router = None
+        self.w_noise = None
+        g = lambda k, d: getattr(config, k, d)
+        if self.num_experts <= 0:                                             # core.py:412-427 passthrough
+            self.use_noisy_top_k_routing = self.use_expert_capacity_limit = self.use_expert_dropout = False
+            self.use_router_z_loss = self.use_load_balancing_loss = False
+            self.load_balancing_loss_coef = self.router_z_loss_coef = self.expert_dropout_prob = self.noisy_routing_alpha = 0.0
+            return
+        E, Dm, I = self.num_experts, self.hidden_size, self.intermediate_size
+        self.eps = config.layer_norm_eps
+        self.router_norm = nn.LayerNorm(Dm, eps=self.eps)
+        self.router = nn.Linear(Dm, E)
+        act = activation_function_override if activation_function_override is not None else g("hidden_act", "gelu")
+        self.act_name = act if act in _lib.ACT else "gelu"                    # core.py:463-468 (unknown -> GELU)
+        self.hidden_dropout_prob = float(g("hidden_dropout_prob", 0.0))
+        self.ep_world = ep_group.size() if ep_group is not None else 1
+        self.ep_rank = ep_group.rank() if ep_group is not None else 0
+        if E % self.ep_world:
+            raise ValueError(f"num_experts ({E}) must be divisible by the expert-parallel world size ({self.ep_world})")
+        El = E // self.ep_world
+        self.local_experts = El
+        self.expert_ln_weight = nn.Parameter(torch.ones(El, Dm))
+        self.expert_ln_bias = nn.Parameter(torch.zeros(El, Dm))
+        self.expert_w1 = nn.Parameter(torch.empty(El, I, Dm))
+        self.expert_b1 = nn.Parameter(torch.empty(El, I))
+        self.expert_w2 = nn.Parameter(torch.empty(El, Dm, I))
+        self.expert_b2 = nn.Parameter(torch.empty(El, Dm))
+        for e in range(El):                                                   # nn.Linear default init per expert
+            nn.init.kaiming_uniform_(self.expert_w1[e], a=math.sqrt(5))
+            nn.init.uniform_(self.expert_b1[e], -1 / math.sqrt(Dm), 1 / math.sqrt(Dm))
+            nn.init.kaiming_uniform_(self.expert_w2[e], a=math.sqrt(5))
+            nn.init.uniform_(self.expert_b2[e], -1 / math.sqrt(I), 1 / math.sqrt(I))
+        if g("use_noisy_top_k_routing", True):
+            self.w_noise = nn.Parameter(torch.zeros(E))
+        self.load_balancing_loss_coef = g("load_balancing_loss_coef", 0.01)
+        self.expert_capacity_factor = g("expert_capacity_factor", 1.25)
+        self.router_z_loss_coef = g("router_z_loss_coef", 0.001)
+        self.noisy_routing_alpha = g("noisy_routing_alpha", 0.1)
+        self.expert_dropout_prob = g("expert_dropout_prob", 0.1)
+        self.use_noisy_top_k_routing = g("use_noisy_top_k_routing", True)
+        self.use_expert_capacity_limit = g("use_expert_capacity_limit", True)
+        self.use_expert_dropout = g("use_expert_dropout", True)
+        self.use_router_z_loss = g("use_router_z_loss", True)
+        self.use_load_balancing_loss = g("use_load_balancing_loss", True)
+        self.last_counts: Optional[torch.Tensor] = None       # expert_token_counts_post_capacity of the last call (int32 [E])
+        self._register_state_dict_hook(self._to_reference_keys)
+        self._register_load_state_dict_pre_hook(self._from_reference_keys)
+
+    # ---- state_dict translation (reference keys: experts.{e}.{0,1,4}.{weight,bias}) ----
+    @staticmethod
+    def _to_reference_keys(module, state_dict, prefix, local_metadata):
+        if module.num_experts <= 0:
+            return state_dict
+        base = module.ep_rank * module.local_experts
+        for name, suffix in module._STACKED.items():
+            t = state_dict.pop(prefix + name)
+            for e in range(module.local_experts):
+                state_dict[f"{prefix}experts.{base + e}.{suffix}"] = t[e]
+        return state_dict
+
+    def _from_reference_keys(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        if self.num_experts <= 0:
+            return
+        base = self.ep_rank * self.local_experts
+        for name, suffix in self._STACKED.items():
+            if prefix + name in state_dict:
+                continue
+            keys = [f"{prefix}experts.{base + e}.{suffix}" for e in range(self.local_experts)]
+            if all(k in state_dict for k in keys):
+                state_dict[prefix + name] = torch.stack([state_dict[k] for k in keys])
+        for k in [k for k in state_dict if k.startswith(prefix + "experts.")]:      # other ranks' experts under EP
+            del state_dict[k]
+
+    # ---- hooks the parity tests use to feed both sides the same random numbers ----
+    def _draw_noise(self, S: int, E: int, device) -> torch.Tensor:
+        """The standard-normal draw of core.py:487 (torch.randn_like on the fp32 logits)."""
+        return torch.randn(S, E, device=device, dtype=torch.float32)
+
+    def _draw_active_mask(self, device) -> Optional[torch.Tensor]:
+        """Whole-expert dropout mask of core.py:514-521 (None = all experts active)."""
+        E = self.num_experts
+        if not (self.use_expert_dropout and self.training and self.expert_dropout_prob > 0):
+            return None
+        ndrop = math.floor(E * self.expert_dropout_prob)
+        if ndrop >= E:
+            ndrop = E - 1
+        if ndrop <= 0:
+            return None
+        perm = torch.randperm(E, device=device)
+        active = torch.ones(E, dtype=torch.int32, device=device)
+        active[perm[:ndrop]] = 0
+        return active
+
+    def forward(self, hidden_states: torch.Tensor):
+        zero = lambda: torch.tensor(0.0, device=hidden_states.device, dtype=hidden_states.dtype)
+        if self.num_experts <= 0 or self.router is None:
+            return hidden_states, zero(), zero()                              # core.py:474-475
+        _lib.ensure_device(hidden_states.device)
+        ac = _autocast_dtype()
+        if self.training and self.hidden_dropout_prob > 0:
+            raise NotImplementedError("expert-internal Dropout (core.py:439) with p > 0 is not implemented in the B200 path yet; "
+                                      "set hidden_dropout_prob = 0")
+        B, L, Dm = hidden_states.shape
+        S, E, K = B * L, self.num_experts, self.experts_per_token
+        x2 = hidden_states.reshape(S, Dm)
+        training = self.training
+        noise = noise_scale = None
+        if self.use_noisy_top_k_routing and training and self.w_noise is not None:          # core.py:485-488
+            noise_scale = F.softplus(self.w_noise.float()) * self.noisy_routing_alpha
+            noise = self._draw_noise(S, E, x2.device)
+        cap = ops.moe_capacity(S, E, self.expert_capacity_factor, training, self.use_expert_capacity_limit)
+        cfg = dict(K=K, eps=self.eps, act=_lib.ACT[self.act_name], training=training, cap=cap,
+                   lb_coef=self.load_balancing_loss_coef if self.use_load_balancing_loss else 0.0,
+                   rz_coef=self.router_z_loss_coef if self.use_router_z_loss else 0.0,
+                   active=self._draw_active_mask(x2.device),
+                   precise=(x2.dtype == torch.float32 and ac is None))
+        if self.ep_world > 1:
+            from . import ep
+            out, lb, rz, counts = ep.moe_experts_ep(self, x2, noise, noise_scale, cfg)
+        else:
+            out, lb, rz, counts = ops.moe_experts(x2, self.router_norm.weight, self.router_norm.bias, self.router.weight,
+                                                  self.router.bias, noise, noise_scale, self.expert_ln_weight,
+                                                  self.expert_ln_bias, self.expert_w1, self.expert_b1, self.expert_w2,
+                                                  self.expert_b2, cfg)
+        self.last_counts = counts
+        return out.reshape(B, L, Dm), lb, rz
+
+
+# ================================================================================================
+# the callers (boundary; kept as plain PyTorch like the reference's ApertisAttention / ApertisFeedForward)
+# ================================================================================================
+class _AttentionWrapper(nn.Module):
+    """ApertisAttention for attention_type == 'selective_ssm' (core.py:639-704, 836-838)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.attention_mechanism_impl = SelectiveLinearAttention(config)
+        self.pre_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.output_dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, hidden_s, att_mask=None, pos_ids=None, past_kv=None, output_att=False, use_c=False):
+        out, proxy, cache = self.attention_mechanism_impl(self.pre_norm(hidden_s), attention_mask=att_mask, position_ids=pos_ids,
+                                                          past_key_value=past_kv, output_attentions=output_att, use_cache=use_c)
+        return self.output_dropout(out) + hidden_s, proxy, cache
+
+
+class _FeedForwardWrapper(nn.Module):
+    """ApertisFeedForward with the expert system (core.py:840-923)."""
+
+    def __init__(self, config, ep_group=None):
+        super().__init__()
+        self.config = config
+        self.pre_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.ffn = AdaptiveExpertSystem(config, activation_function_override=config.hidden_act, ep_group=ep_group)
+        self.is_expert_system = True
+        self.output_dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, hidden_s):
+        out, lb, rz = self.ffn(self.pre_norm(hidden_s))
+        return self.output_dropout(out) + hidden_s, lb, rz
+
+
+class ApertisLayerB200(nn.Module):
+    """ApertisLayer (core.py:995-1018) built from the B200 modules; state_dict keys equal the reference layer's."""
+
+    def __init__(self, config, ep_group=None):
+        super().__init__()
+        self.config = config
+        self.attention = _AttentionWrapper(config)
+        self.feed_forward = _FeedForwardWrapper(config, ep_group=ep_group)
+
+    def forward(self, hidden_s, att_mask=None, pos_ids=None, past_kv=None, output_att=False, use_c=False):
+        att_out, att_w, cache = self.attention(hidden_s, att_mask, pos_ids, past_kv, output_att, use_c)
+        out, lb, rz = self.feed_forward(att_out)
+        return out, att_w, cache, lb, rz
+
+
+def patch_apertis_model(model: nn.Module, ep_group=None) -> nn.Module:
+    """Swaps the B200 modules into a reference ApertisModel / ApertisForCausalLM in place.
+
+    For every layer: ``attention.attention_mechanism_impl`` (core.py:650) is replaced by a
+    SelectiveLinearAttention that adopts the SAME Parameter objects, and ``feed_forward.ffn`` (core.py:861)
+    by an AdaptiveExpertSystem whose stacked parameters are filled from the per-expert modules."""
+    layers = model.model.layers if hasattr(model, "model") and hasattr(model.model, "layers") else model.layers
+    for layer in layers:
+        att = layer.attention
+        old = getattr(att, "attention_mechanism_impl", None)
+        if old is not None and type(old).__name__ == "SelectiveLinearAttention" and not isinstance(old, SelectiveLinearAttention):
+            new = SelectiveLinearAttention(att.config)
+            for name, prm in old.named_parameters():
+                mod, _, leaf = name.rpartition(".")
+                setattr(new.get_submodule(mod) if mod else new, leaf, prm)
+            new.train(old.training)
+            att.attention_mechanism_impl = new
+        ff = layer.feed_forward
+        oldf = getattr(ff, "ffn", None)
+        if getattr(ff, "is_expert_system", False) and type(oldf).__name__ == "AdaptiveExpertSystem" \
+                and not isinstance(oldf, AdaptiveExpertSystem):
+            newf = AdaptiveExpertSystem(ff.config, activation_function_override=ff.config.hidden_act, ep_group=ep_group)
+            newf.to(next(oldf.parameters()).device)
+            newf.load_state_dict(oldf.state_dict(), strict=True)
+            newf.train(oldf.training)
+            ff.ffn = newf
+    return model

@@ -1,0 +1,397 @@
+"""torch.autograd bindings of the C-ABI kernels (device memory, streams and autograd plumbing only;
+all arithmetic on the hot path runs in libapertis_b200.so).
+
+  causal_conv1d_silu   core.py:368-375
+  selective_scan       core.py:324-353, 383, 394-396
+  moe_experts          core.py:480-607 (router, plan, permute, expert MLPs, combine, aux losses)
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AB_BF16, AB_F32, ROW_ALIGN, call, dt, ptr, query, stream_ptr
+
+# --------------------------------------------------------------------------------------------
+# workspaces
+# --------------------------------------------------------------------------------------------
+_scan_ws = {}       # (device index, stream) -> [tensor, epoch]
+SCAN_MODE = _lib.SCAN_TWO_PASS if os.environ.get("APERTIS_B200_SCAN", "single") == "two_pass" else _lib.SCAN_SINGLE_PASS
+
+
+def _scan_workspace(device, nbytes: int):
+    """Persistent, zero-initialised look-back workspace per (device, stream) with its launch epoch."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ent = _scan_ws.get(key)
+    if ent is None or ent[0].numel() < nbytes:
+        epoch = ent[1] if ent is not None else 0
+        ent = [torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device), epoch]
+        _scan_ws[key] = ent
+    ent[1] += 1
+    if ent[1] >= (1 << 30) - 1:          # epoch wrap: start over on a clean buffer
+        ent[0].zero_()
+        ent[1] = 1
+    return ent[0], ent[1]
+
+
+def scan_plan(B: int, L: int, Di: int, dtype: torch.dtype):
+    t, s, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    ws = ctypes.c_size_t()
+    call("ab_selective_scan_plan", B, L, Di, dt(dtype), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    return t.value, s.value, n.value, ws.value
+
+
+def _row_stride(t: torch.Tensor) -> int:
+    """Row stride (elements) of a [B, L, C] tensor whose rows may be slices of a wider contiguous buffer."""
+    B, L, C = t.shape
+    assert t.stride(2) == 1 and (B == 1 or t.stride(0) == L * t.stride(1)), "unsupported layout"
+    return t.stride(1)
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """Ensures a [B,L,C] tensor is usable as strided rows (last dim contiguous, batches back to back)."""
+    B, L, C = t.shape
+    if t.stride(2) == 1 and (B == 1 or t.stride(0) == L * t.stride(1)) and (L == 1 or t.stride(1) >= C):
+        return t
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# causal conv1d + SiLU
+# --------------------------------------------------------------------------------------------
+class _CausalConv1dSiLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xp, weight, bias):
+        _lib.ensure_device(xp.device)
+        xp = _rows(xp)
+        B, L, Di = xp.shape
+        Kc = weight.shape[-1]
+        w = weight.reshape(Di, Kc).float().contiguous()
+        b = bias.float().contiguous()
+        xa = torch.empty(B, L, Di, dtype=xp.dtype, device=xp.device)
+        call("ab_causal_conv1d_silu_fwd", ptr(xp), _row_stride(xp), ptr(w), ptr(b), ptr(xa), B, L, Di, Kc, dt(xp), stream_ptr())
+        ctx.save_for_backward(xp, w, b)
+        ctx.wshape = weight.shape
+        ctx.wdtype, ctx.bdtype = weight.dtype, bias.dtype
+        return xa
+
+    @staticmethod
+    def backward(ctx, dxa):
+        xp, w, b = ctx.saved_tensors
+        B, L, Di = xp.shape
+        Kc = w.shape[-1]
+        dxa = dxa.contiguous()
+        dxp = torch.empty(B, L, Di, dtype=xp.dtype, device=xp.device)
+        dw = torch.empty(Di, Kc, dtype=torch.float32, device=xp.device)
+        db = torch.empty(Di, dtype=torch.float32, device=xp.device)
+        nws = query("ab_causal_conv1d_silu_bwd_workspace_bytes", B, L, Di)
+        ws = torch.empty(nws, dtype=torch.uint8, device=xp.device)
+        call("ab_causal_conv1d_silu_bwd", ptr(xp), _row_stride(xp), ptr(dxa), ptr(w), ptr(b), ptr(dxp), ptr(dw), ptr(db),
+             ptr(ws), nws, B, L, Di, Kc, dt(xp), stream_ptr())
+        return dxp, dw.reshape(ctx.wshape).to(ctx.wdtype), db.to(ctx.bdtype)
+
+
+def causal_conv1d_silu(xp: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """xp [B,L,Di] (channels last), weight [Di,1,4], bias [Di] -> silu(causal depthwise conv) [B,L,Di]."""
+    return _CausalConv1dSiLU.apply(xp, weight, bias)
+
+
+# --------------------------------------------------------------------------------------------
+# selective scan
+# --------------------------------------------------------------------------------------------
+class _SelectiveScan(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, mode):
+        _lib.ensure_device(xa.device)
+        xa = xa.contiguous()
+        dlog = dlog.contiguous()
+        BC, z = BC.contiguous(), _rows(z)
+        B, L, Di = xa.shape
+        H = dlog.shape[-1]
+        assert BC.shape == (B, L, 2 * Di)
+        Bm, Cm = BC[..., :Di], BC[..., Di:]
+        dev = xa.device
+        A = A_log.reshape(-1).float().contiguous()
+        Dv = D.float().contiguous()
+        T, Cs, nchunks, nws = scan_plan(B, L, Di, xa.dtype)
+        ws, epoch = _scan_workspace(dev, nws)
+        y = torch.empty_like(xa)
+        y_ssm = torch.empty_like(xa) if want_yssm else None
+        h_last = torch.empty(B, Di, dtype=torch.float32, device=dev) if want_hlast else None
+        hstart = torch.empty(B, nchunks, Di, dtype=torch.float32, device=dev)
+        h0c = h0.reshape(B, Di).float().contiguous() if h0 is not None else None
+        call("ab_selective_scan_fwd", ptr(xa), ptr(dlog), ptr(Bm), ptr(Cm), 2 * Di, ptr(z), _row_stride(z), ptr(A),
+             ptr(Dv), ptr(h0c), ptr(y), ptr(y_ssm), ptr(h_last), ptr(hstart), ptr(ws), ws.numel(), epoch, mode,
+             B, L, Di, H, dt(xa), stream_ptr())
+        ctx.save_for_backward(xa, dlog, BC, z, A, Dv, hstart)
+        ctx.mode = mode
+        ctx.a_shape, ctx.want_yssm = A_log.shape, want_yssm
+        if h_last is not None:
+            ctx.mark_non_differentiable(h_last)
+        return y, y_ssm, h_last
+
+    @staticmethod
+    def backward(ctx, dy, dyssm, _dh):
+        xa, dlog, BC, z, A, Dv, hstart = ctx.saved_tensors
+        B, L, Di = xa.shape
+        H = dlog.shape[-1]
+        dev = xa.device
+        Bm, Cm = BC[..., :Di], BC[..., Di:]
+        dy = dy.contiguous()
+        dys = dyssm.contiguous() if (dyssm is not None and ctx.want_yssm) else None
+        T, Cs, nchunks, nws = scan_plan(B, L, Di, xa.dtype)
+        ws, epoch = _scan_workspace(dev, nws)
+        dxa = torch.empty_like(xa)
+        dz = torch.empty_like(xa)
+        dbc = torch.empty(B, L, 2 * Di, dtype=xa.dtype, device=dev)       # [dB | dC] rows, ready for the x_param_proj GEMM
+        parts = Di // 4
+        ddl = torch.empty(B, L, parts, dtype=torch.float32, device=dev)
+        dA = torch.empty(Di, dtype=torch.float32, device=dev)
+        dD = torch.empty(Di, dtype=torch.float32, device=dev)
+        dB, dC = dbc[..., :Di], dbc[..., Di:]
+        call("ab_selective_scan_bwd", ptr(xa), ptr(dlog), ptr(Bm), ptr(Cm), 2 * Di, ptr(z), _row_stride(z), ptr(dy),
+             ptr(dys), ptr(A), ptr(Dv), ptr(hstart), ptr(dxa), ptr(dB), ptr(dC), 2 * Di, ptr(dz), ptr(ddl), ptr(dA), ptr(dD),
+             ptr(ws), ws.numel(), epoch, ctx.mode, B, L, Di, H, dt(xa), stream_ptr())
+        ddlog = ddl.view(B, L, H, parts // H).sum(-1).to(dlog.dtype)
+        return dxa, ddlog, dbc, dz, dA.reshape(ctx.a_shape), dD, None, None, None, None
+
+
+def selective_scan(xa, dlog, BC, z, A_log, D, h0=None, want_yssm=False, want_hlast=False, mode: Optional[int] = None):
+    """Fused softplus(dt) / discretise / scan / D skip / SiLU(z) gate.
+
+    xa, z [B,L,Di]; BC [B,L,2*Di] = [B-term | C-term]; dlog [B,L,H]; A_log [H,16]; D [Di]; h0 [B,H,16] or None.
+    Returns (y [B,L,Di], y_ssm | None, h_last [B,Di] fp32 | None)."""
+    return _SelectiveScan.apply(xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, SCAN_MODE if mode is None else mode)
+
+
+# --------------------------------------------------------------------------------------------
+# MoE
+# --------------------------------------------------------------------------------------------
+def _u8(n, dev):
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev)
+
+
+def moe_route(x2, ln_w, ln_b, eps, Wr, br, noise, noise_scale, K):
+    """Router forward (no autograd).  Returns dict of routing tensors."""
+    S, Dm = x2.shape
+    E = Wr.shape[0]
+    dev = x2.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    r = dict(lclean=torch.empty(S, E, **f32), logits=torch.empty(S, E, **f32), gates=torch.empty(S, E, **f32),
+             idx=torch.empty(S, K, dtype=torch.int32, device=dev), probs=torch.empty(S, K, **f32),
+             w=torch.empty(S, K, **f32), lse=torch.empty(S, **f32), stats=torch.empty(S, 2, **f32),
+             aux=torch.empty(2 * E + 1, **f32))
+    nws = query("ab_moe_router_workspace_bytes", S, Dm, E)
+    ws = _u8(nws, dev)
+    call("ab_moe_router_fwd", ptr(x2), ptr(ln_w), ptr(ln_b), float(eps), ptr(Wr), ptr(br), ptr(noise), ptr(noise_scale),
+         ptr(r["lclean"]), ptr(r["logits"]), ptr(r["gates"]), ptr(r["idx"]), ptr(r["probs"]), ptr(r["w"]), ptr(r["lse"]),
+         ptr(r["stats"]), ptr(r["aux"]), ptr(ws), ws.numel(), S, Dm, E, K, dt(x2), stream_ptr())
+    return r
+
+
+def moe_topk_from_logits(logits, K):
+    S, E = logits.shape
+    dev = logits.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    gates, probs, w, lse = torch.empty(S, E, **f32), torch.empty(S, K, **f32), torch.empty(S, K, **f32), torch.empty(S, **f32)
+    idx = torch.empty(S, K, dtype=torch.int32, device=dev)
+    call("ab_moe_topk_from_logits", ptr(logits.contiguous()), ptr(gates), ptr(idx), ptr(probs), ptr(w), ptr(lse), S, E, K, stream_ptr())
+    return gates, idx, probs, w, lse
+
+
+def moe_plan(idx, w, E, cap, active=None):
+    """Capacity plan on the device (no host sync).  idx [S,K] int32, w [S,K] fp32."""
+    S, K = idx.shape
+    dev = idx.device
+    cap = int(min(cap, S))
+    max_rows = int(query("ab_moe_max_rows", S, K, E, cap, ROW_ALIGN))
+    i32 = dict(dtype=torch.int32, device=dev)
+    p = dict(counts=torch.empty(E, **i32), seg_off=torch.empty(E + 1, **i32), row_of=torch.empty(S, K, **i32),
+             tok_of_row=torch.empty(max_rows, **i32), slot_of_row=torch.empty(max_rows, **i32),
+             tile_expert=torch.empty(max_rows // ROW_ALIGN, **i32), n_rows=torch.empty(2, **i32), max_rows=max_rows, cap=cap)
+    nws = query("ab_moe_plan_workspace_bytes", S, K, E)
+    ws = _u8(nws, dev)
+    call("ab_moe_plan", ptr(idx), ptr(w), ptr(active), cap, ptr(p["counts"]), ptr(p["seg_off"]), ptr(p["row_of"]),
+         ptr(p["tok_of_row"]), ptr(p["slot_of_row"]), ptr(p["tile_expert"]), ptr(p["n_rows"]), ptr(ws), ws.numel(),
+         S, K, E, ROW_ALIGN, max_rows, stream_ptr())
+    return p
+
+
+def _cast_bf16(t):
+    out = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    call("ab_cast_f32_to_bf16", ptr(t), ptr(out), t.numel(), stream_ptr())
+    return out
+
+
+def _split_cols(t2d, which):
+    rows, cols = t2d.shape
+    out = torch.empty(rows, 3 * cols, dtype=torch.bfloat16, device=t2d.device)
+    call("ab_split_f32_to_bf16x3", ptr(t2d), ptr(out), rows, cols, which, stream_ptr())
+    return out
+
+
+def _split_rows(t2d, which, seg_off=None, G=1, rows_per_group=0):
+    rows, cols = t2d.shape
+    out = torch.empty(3 * rows, cols, dtype=torch.bfloat16, device=t2d.device)
+    call("ab_split_f32_to_bf16x3_rows", ptr(t2d), ptr(out), ptr(seg_off), G, rows_per_group, cols, which, stream_ptr())
+    return out
+
+
+def grouped_gemm(mode, A, W, plan, N, K, E, *, bias=None, aux=None, epi=_lib.EPI_NONE, act=0, out_dtype=torch.bfloat16,
+                 want_c2=False):
+    """C = epi(A @ W[e]^T) ('nt', W [E,N,K]) or epi(A @ W[e]) ('nn', W [E,K,N]) over the permuted rows."""
+    max_rows = A.shape[0]
+    c = torch.empty(max_rows, N, dtype=out_dtype, device=A.device)
+    c2 = torch.empty(max_rows, N, dtype=out_dtype, device=A.device) if want_c2 else None
+    call("ab_grouped_gemm_" + mode, ptr(A), ptr(W), ptr(bias), ptr(aux), ptr(c), ptr(c2), ptr(plan["tile_expert"]),
+         ptr(plan["n_rows"]), max_rows, N, K, E, epi, act, dt(out_dtype), stream_ptr())
+    return (c, c2) if want_c2 else c
+
+
+def grouped_gemm_tn(A, Bm, seg_off, M, N, E):
+    """Cw[e] = A[seg e]^T @ Bm[seg e]  -> fp32 [E, M, N]."""
+    out = torch.empty(E, M, N, dtype=torch.float32, device=A.device)
+    call("ab_grouped_gemm_tn", ptr(A), ptr(Bm), ptr(out), ptr(seg_off), A.shape[0], M, N, E, stream_ptr())
+    return out
+
+
+class _MoEExperts(torch.autograd.Function):
+    """Whole AdaptiveExpertSystem.forward as one autograd node.
+
+    inputs: x2 [S,Dm]; router_norm weight/bias; router weight/bias; noise [S,E] | None; noise_scale [E] | None;
+            stacked expert params ln_w/ln_b [E,Dm], W1 [E,I,Dm], b1 [E,I], W2 [E,Dm,I], b2 [E,Dm]
+    cfg:    dict(K, eps, act, training, cap, lb_coef, rz_coef, active (int32 [E] | None), precise (fp32-accurate GEMMs))
+    returns out [S,Dm], lb, rz, counts (non-differentiable int32 [E])"""
+
+    @staticmethod
+    def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg):
+        _lib.ensure_device(x2.device)
+        dev = x2.device
+        S, Dm = x2.shape
+        E, I, _ = W1.shape
+        K, act, training, precise = cfg["K"], cfg["act"], cfg["training"], cfg["precise"]
+        x2 = x2.contiguous()
+        f = lambda t: t.float().contiguous()
+        rn_w, rn_b, Wr, br, ln_w, ln_b, b1, b2 = map(f, (rn_w, rn_b, Wr, br, ln_w, ln_b, b1, b2))
+        W1, W2 = f(W1), f(W2)
+        use_noise = noise is not None and noise_scale is not None
+        r = moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
+                      f(noise_scale) if use_noise else None, K)
+        plan = moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"])
+        max_rows = plan["max_rows"]
+        cdt = torch.float32 if precise else torch.bfloat16         # dtype of the GEMM outputs that feed later GEMMs
+        # ---- permute + per-expert LayerNorm
+        xn = torch.empty(max_rows, Dm, dtype=cdt, device=dev)
+        call("ab_moe_permute_ln", ptr(x2), ptr(r["stats"]), ptr(ln_w), ptr(ln_b), ptr(plan["tok_of_row"]), ptr(plan["tile_expert"]),
+             ptr(plan["n_rows"]), ptr(xn), Dm, ROW_ALIGN, max_rows, dt(x2), dt(cdt), stream_ptr())
+        if precise:
+            a1 = _split_cols(xn, 0)
+            w1 = _split_cols(W1.view(E * I, Dm), 1)
+            k1 = 3 * Dm
+        else:
+            a1, w1, k1 = xn, _cast_bf16(W1), Dm
+        h, hpre = grouped_gemm("nt", a1, w1, plan, I, k1, E, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True)
+        if precise:
+            a2 = _split_cols(h, 0)
+            w2 = _split_cols(W2.view(E * Dm, I), 1)
+            k2 = 3 * I
+        else:
+            a2, w2, k2 = h, _cast_bf16(W2), I
+        y = grouped_gemm("nt", a2, w2, plan, Dm, k2, E, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
+        out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
+        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(out), S, K, Dm, dt(y), dt(out), stream_ptr())
+        # ---- aux losses (core.py:499-505, 524-526) from the kernel's deterministic sums
+        aux = r["aux"]
+        zero = torch.zeros((), dtype=x2.dtype, device=dev)
+        lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
+        rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
+        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt)
+        ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
+        ctx.save_for_backward(x2, rn_w, rn_b, Wr, br, ln_w, W1, W2, noise if use_noise else None,
+                              r["stats"], r["gates"], r["idx"], r["probs"], r["lse"], r["lclean"], r["w"], aux,
+                              xn, h, hpre, y)
+        ctx.routing = r
+        counts = plan["counts"]
+        ctx.mark_non_differentiable(counts)
+        return out, lb.to(x2.dtype) if torch.is_tensor(lb) else lb, rz.to(x2.dtype) if torch.is_tensor(rz) else rz, counts
+
+    @staticmethod
+    def backward(ctx, dout, dlb, drz, _dcounts):
+        (x2, rn_w, rn_b, Wr, br, ln_w, W1, W2, noise, stats, gates, idx, probs, lse, lclean, w, aux, xn, h, hpre, y) = ctx.saved_tensors
+        cfg, plan = ctx.cfg, ctx.plan
+        S, Dm, E, I, K = cfg["S"], cfg["Dm"], cfg["E"], cfg["I"], cfg["K"]
+        act, precise, max_rows, cdt = cfg["act"], cfg["precise"], cfg["max_rows"], cfg["cdt"]
+        dev = x2.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dout = dout.contiguous()
+        # ---- combine backward: dY rows and d(gate weight)
+        dy = torch.empty(max_rows, Dm, dtype=cdt, device=dev)
+        dw_row = torch.empty(max_rows, **f32)
+        call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
+             ptr(dy), ptr(dw_row), K, Dm, max_rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+        seg = plan["seg_off"]
+        if precise:
+            seg3 = (seg * 3).contiguous()
+            w2r = _split_rows(W2.view(E * Dm, I), 1, None, E, Dm)                 # [E, 3*Dm, I]
+            dhpre = grouped_gemm("nn", _split_cols(dy, 0), w2r, plan, I, 3 * Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dW2 = grouped_gemm_tn(_split_rows(dy, 0, seg, E), _split_rows(h, 1, seg, E), seg3, Dm, I, E)
+            dW1 = grouped_gemm_tn(_split_rows(dhpre, 0, seg, E), _split_rows(xn, 1, seg, E), seg3, I, Dm, E)
+            w1r = _split_rows(W1.view(E * I, Dm), 1, None, E, I)                  # [E, 3*I, Dm]
+            dxn = grouped_gemm("nn", _split_cols(dhpre, 0), w1r, plan, Dm, 3 * I, E, out_dtype=torch.float32)
+        else:
+            w1b, w2b = _cast_bf16(W1), _cast_bf16(W2)
+            dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dW2 = grouped_gemm_tn(dy, h, seg, Dm, I, E)
+            dW1 = grouped_gemm_tn(dhpre, xn, seg, I, Dm, E)
+            dxn = grouped_gemm("nn", dhpre, w1b, plan, Dm, I, E, out_dtype=torch.float32)
+        # ---- bias grads
+        db2 = torch.empty(E, Dm, **f32)
+        db1 = torch.empty(E, I, **f32)
+        nws = max(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, max_rows),
+                  query("ab_moe_segment_colsum_workspace_bytes", Dm, ROW_ALIGN, max_rows),
+                  query("ab_moe_permute_ln_bwd_workspace_bytes", Dm, ROW_ALIGN, max_rows))
+        ws = _u8(nws, dev)
+        call("ab_moe_segment_colsum", ptr(dy), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(db2), ptr(ws), ws.numel(), Dm, E,
+             ROW_ALIGN, max_rows, dt(dy), stream_ptr())
+        call("ab_moe_segment_colsum", ptr(dhpre), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(db1), ptr(ws), ws.numel(), I, E,
+             ROW_ALIGN, max_rows, dt(dhpre), stream_ptr())
+        # ---- per-expert LayerNorm backward on the permuted rows
+        dxrow = torch.empty(max_rows, Dm, **f32)
+        dln_w = torch.empty(E, Dm, **f32)
+        dln_b = torch.empty(E, Dm, **f32)
+        call("ab_moe_permute_ln_bwd", ptr(dxn), ptr(x2), ptr(stats), ptr(ln_w), ptr(plan["tok_of_row"]), ptr(plan["tile_expert"]),
+             ptr(plan["n_rows"]), ptr(dxrow), ptr(dln_w), ptr(dln_b), ptr(ws), ws.numel(), Dm, E, ROW_ALIGN, max_rows, dt(x2),
+             dt(dxn), stream_ptr())
+        # ---- router backward (+ gather of the expert path into dx)
+        training = cfg["training"]
+        g_lb = (dlb.float() * (cfg["lb_coef"] * E / S)) if (training and cfg["lb_coef"] > 0) else torch.zeros((), **f32)
+        g_rz = (drz.float() * (cfg["rz_coef"] / S)) if (training and cfg["rz_coef"] > 0) else torch.zeros((), **f32)
+        scal = torch.stack([g_lb.reshape(()), g_rz.reshape(())]).contiguous()
+        fvec = (aux[E:2 * E] / S).contiguous()
+        dx = torch.empty_like(x2)
+        dWr, dbr = torch.empty(E, Dm, **f32), torch.empty(E, **f32)
+        drn_w, drn_b = torch.empty(Dm, **f32), torch.empty(Dm, **f32)
+        dns = torch.empty(E, **f32) if cfg["use_noise"] else None
+        nws = query("ab_moe_router_bwd_workspace_bytes", S, Dm, E)
+        ws2 = _u8(nws, dev)
+        call("ab_moe_router_bwd", ptr(x2), ptr(stats), ptr(rn_w), ptr(rn_b), ptr(Wr), ptr(br), ptr(gates), ptr(idx), ptr(probs),
+             ptr(lse), ptr(lclean), ptr(noise.float().contiguous()) if cfg["use_noise"] else None, ptr(fvec), ptr(scal), ptr(dw_row),
+             ptr(dxrow), ptr(plan["row_of"]), ptr(dx), ptr(dWr), ptr(dbr), ptr(drn_w), ptr(drn_b), ptr(dns), ptr(ws2), ws2.numel(),
+             S, Dm, E, K, dt(x2), stream_ptr())
+        return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w, dln_b, dW1, db1, dW2, db2, None)
+
+
+def moe_experts(x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg):
+    return _MoEExperts.apply(x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg)
+
+
+def moe_capacity(S: int, E: int, factor: float, training: bool, use_limit: bool) -> int:
+    """core.py:508-511."""
+    if use_limit and training and E > 0:
+        return max(1, math.floor((S / E) * factor)) if S > 0 else 0
+    return S

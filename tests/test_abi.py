@@ -1,0 +1,49 @@
+"""CPU-side checks of the drop-in boundary: the shared library builds for sm_100a, loads, exports every
+symbol include/apertis_b200.h declares, and the ctypes table mirrors the header's arities.  No compute calls."""
+import os
+import re
+
+from apertis_llm_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "apertis_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    fns = {}
+    for m in re.finditer(r"\b(int|size_t|int64_t)\s+(ab_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(3).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        fns[m.group(2)] = n
+    return fns
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    _lib.build()
+    lib = _lib.load()
+    fns = _header_functions()
+    assert len(fns) >= 25
+    for name in fns:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert lib.ab_version() >= 100
+
+
+def test_ctypes_table_mirrors_header():
+    fns = _header_functions()
+    assert set(fns) == set(_lib.SIGNATURES), set(fns) ^ set(_lib.SIGNATURES)
+    for name, n in fns.items():
+        assert len(_lib.SIGNATURES[name][1]) == n, (name, n, len(_lib.SIGNATURES[name][1]))
+
+
+def test_pure_queries_work_without_gpu():
+    r = _lib.query("ab_moe_max_rows", 4096, 2, 8, 640, 128)
+    assert r % 128 == 0 and r >= 8 * 640
+    import ctypes
+    t, s, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    ws = ctypes.c_size_t()
+    rc = _lib.query("ab_selective_scan_plan", 1, 65536, 512, _lib.AB_BF16, ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    assert rc == 0 and t.value % 4 == 0 and 512 % s.value == 0 and n.value == -(-65536 // t.value)
+    rc = _lib.query("ab_selective_scan_plan", 1, 16, 20, _lib.AB_BF16, ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    assert rc != 0 and "tiling" in _lib.last_error()

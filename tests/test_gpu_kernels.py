@@ -1,0 +1,263 @@
+"""Kernel-level parity on the B200, through the C ABI (ctypes), against the CPU oracle / plain torch fp32."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import apertis_oracle as O
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}     # north_star tolerances (max|a-b| / max|b|)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# causal conv1d + SiLU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,L,Di", [(2, 37, 32), (1, 300, 176), (3, 16, 64), (2, 1, 32), (1, 129, 512)])
+def test_conv_silu(dtype, B, L, Di):
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    xp = torch.randn(B, L, Di, generator=g)
+    w = torch.rand(Di, 1, 4, generator=g) - 0.5
+    b = torch.rand(Di, generator=g) - 0.5
+    dy = torch.randn(B, L, Di, generator=g)
+    xr = xp.to(dtype).float().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.silu(F.conv1d(xr.transpose(1, 2), wr, br, padding=3, groups=Di)[:, :, :L].transpose(1, 2))
+    ref.backward(dy.to(dtype).float())
+    xg = xp.to(dev(), dtype).requires_grad_(True)
+    wg, bg = w.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
+    out = ops.causal_conv1d_silu(xg, wg, bg)
+    out.backward(dy.to(dev(), dtype))
+    tol = TOL[dtype]
+    assert rel_err(out.float(), ref.detach()) < tol
+    assert rel_err(xg.grad.float(), xr.grad) < tol
+    assert rel_err(wg.grad, wr.grad) < tol and rel_err(bg.grad, br.grad) < tol
+
+
+# ------------------------------------------------------------------------------------------------
+# selective scan
+# ------------------------------------------------------------------------------------------------
+def _scan_ref(xa, dlog, BC, z, A_log, D, h0):
+    B, L, Di = xa.shape
+    H = dlog.shape[-1]
+    delta = F.softplus(dlog).transpose(1, 2).unsqueeze(-1)
+    Bt = BC[..., :Di].view(B, L, H, 16).transpose(1, 2)
+    Ct = BC[..., Di:].view(B, L, H, 16).transpose(1, 2)
+    y, hl = O.scan_recurrent(delta, A_log, Bt, Ct, h0)
+    y_ssm = y.transpose(1, 2).reshape(B, L, Di)
+    return (y_ssm + D * xa) * F.silu(z), y_ssm, hl.reshape(B, Di)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,L,H", [(2, 48, 2), (1, 1000, 11), (2, 333, 4), (1, 5, 3), (1, 2500, 32)])
+def test_selective_scan(mode, dtype, B, L, H):
+    from apertis_llm_b200 import ops
+    Di = 16 * H
+    g = torch.Generator().manual_seed(L + H)
+    q = lambda t: t.to(dtype).float()
+    xa, z = q(torch.randn(B, L, Di, generator=g)), q(torch.randn(B, L, Di, generator=g))
+    BC = q(torch.randn(B, L, 2 * Di, generator=g) * 0.5)
+    dlog = q(torch.randn(B, L, H, generator=g) - 3.0)          # softplus -> delta ~ 0.05, decays matter over ~100 steps
+    A_log = torch.rand(H, 16, generator=g) * (math.log(0.99) - math.log(0.5)) + math.log(0.5)
+    D = 1.0 + 0.1 * torch.randn(Di, generator=g)
+    h0 = torch.randn(B, H, 16, generator=g)
+    dy, dys = q(torch.randn(B, L, Di, generator=g)), q(torch.randn(B, L, Di, generator=g) * 0.3)
+    leaves = [t.clone().double().requires_grad_(True) for t in (xa, dlog, BC, z, A_log, D)]
+    y, ys, hl = _scan_ref(*leaves, h0.double())
+    (y * dy.double()).sum().add((ys * dys.double()).sum()).backward()
+    gl = [t.to(dev(), dtype if i < 4 else torch.float32).requires_grad_(True) for i, t in enumerate((xa, dlog, BC, z, A_log, D))]
+    yg, ysg, hlg = ops.selective_scan(*gl, h0=h0.to(dev()), want_yssm=True, want_hlast=True, mode=mode)
+    torch.autograd.backward([yg, ysg], [dy.to(dev(), dtype), dys.to(dev(), dtype)])
+    torch.cuda.synchronize()
+    tol = TOL[dtype]
+    assert rel_err(yg.float(), y.detach()) < tol, "y"
+    assert rel_err(ysg.float(), ys.detach()) < tol, "y_ssm"
+    assert rel_err(hlg, hl.detach()) < tol, "h_last"
+    names = ["dxa", "ddlog", "dBC", "dz", "dA_log", "dD"]
+    for n, a, b in zip(names, gl, leaves):
+        assert rel_err(a.grad.float(), b.grad) < (tol if n not in ("dA_log", "dD", "ddlog") else max(tol, 2e-3 if dtype == torch.bfloat16 else tol)), n
+
+
+def test_selective_scan_modes_agree_and_deterministic():
+    from apertis_llm_b200 import ops
+    B, L, H = 2, 3000, 8
+    Di = 16 * H
+    g = torch.Generator().manual_seed(5)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev(), torch.bfloat16)
+    xa, z, BC, dlog = mk(B, L, Di), mk(B, L, Di), mk(B, L, 2 * Di), (torch.randn(B, L, H, generator=g) - 3).to(dev(), torch.bfloat16)
+    A_log = (torch.rand(H, 16, generator=g) * 0.6 - 0.7).to(dev())
+    D = torch.ones(Di, device=dev())
+    outs = [ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=m)[0] for m in (0, 1, 0)]
+    assert torch.equal(outs[0], outs[2]), "single-pass scan is not deterministic"
+    assert torch.equal(outs[0], outs[1]), "single-pass and two-pass scans differ"
+
+
+# ------------------------------------------------------------------------------------------------
+# router, top-k, plan
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,Dm,E,K", [(96, 64, 8, 2), (513, 704, 8, 2), (200, 96, 4, 2), (64, 256, 10, 3)])
+def test_router_fwd(S, Dm, E, K):
+    from apertis_llm_b200 import ops
+    sd = O.make_layer_params(Dm, max(1, Dm // 64), 128, E, seed=S)
+    _, moe, _ = O.split_layer_params(sd)
+    x, noise = O.make_inputs(1, S, Dm, E, seed=S)
+    x2 = x.reshape(S, Dm)
+    logits, gates, probs, idx, w = O.moe_router(moe, x2, eps=1e-12, noise=noise, alpha=0.1, K=K)
+    ns = F.softplus(moe["w_noise"]) * 0.1
+    d = dev()
+    r = ops.moe_route(x2.to(d), moe["router_norm.weight"].to(d), moe["router_norm.bias"].to(d), 1e-12, moe["router.weight"].to(d),
+                      moe["router.bias"].to(d), noise.to(d), ns.to(d), K)
+    assert rel_err(r["logits"], logits) < 1e-5
+    assert rel_err(r["gates"], gates) < 1e-5
+    assert np.array_equal(r["idx"].cpu().numpy(), idx.numpy().astype(np.int32)), "router indices differ from the oracle"
+    assert rel_err(r["w"], w) < 1e-5
+    assert rel_err(r["lse"], torch.logsumexp(logits, -1)) < 1e-5
+    xn_mean = x2.mean(-1)
+    assert rel_err(r["stats"][:, 0], xn_mean) < 1e-4
+    aux = r["aux"].cpu()
+    assert rel_err(aux[:E], gates.sum(0)) < 1e-5
+    cnt = torch.zeros(E).scatter_add_(0, idx.reshape(-1), torch.ones(S * K))
+    assert torch.equal(aux[E:2 * E], cnt)
+
+
+def test_topk_from_logits_bit_exact_with_ties():
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    S, E, K = 4096, 8, 2
+    logits = torch.randn(S, E, generator=g)
+    logits[::7] = torch.round(logits[::7])              # many exact ties
+    logits[5] = 0.25                                    # an all-equal row
+    gates_ref = torch.softmax(logits, -1).numpy()
+    gates, idx, probs, w, lse = ops.moe_topk_from_logits(logits.to(dev()), K)
+    # selection is defined on the kernel's own gates: ties -> lower expert id
+    _, idx_ref = O.topk_lowest_index(gates.cpu().numpy(), K)
+    assert np.array_equal(idx.cpu().numpy(), idx_ref.astype(np.int32))
+    assert rel_err(gates, gates_ref) < 1e-6
+    assert idx[5].tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("S,E,K,cap,ties,inactive", [(96, 8, 2, 15, False, None), (4096, 8, 2, 640, False, None),
+                                                      (1000, 4, 2, 300, True, None), (777, 10, 3, 200, False, [3]),
+                                                      (512, 8, 2, 512, False, None), (300, 8, 2, 1, True, [0, 5])])
+def test_plan_bit_exact(S, E, K, cap, ties, inactive):
+    from apertis_llm_b200 import ops
+    rng = np.random.default_rng(S + cap)
+    idx = np.stack([rng.permutation(E)[:K] for _ in range(S)]).astype(np.int32)
+    idx[: S // 3, 0] = 1 % E                            # skew: force overflow on one expert
+    w = rng.random((S, K)).astype(np.float32) * 0.9 + 0.05
+    if ties:
+        w = np.round(w * 8) / 8 + 0.0625
+    active = None
+    if inactive:
+        active = np.ones(E, dtype=bool)
+        active[inactive] = False
+    kept, counts, groups = O.moe_plan(idx, w, E, cap, active)
+    d = dev()
+    act_t = torch.from_numpy(active.astype(np.int32)).to(d) if active is not None else None
+    p = ops.moe_plan(torch.from_numpy(idx).to(d), torch.from_numpy(w).to(d), E, cap, act_t)
+    torch.cuda.synchronize()
+    assert np.array_equal(p["counts"].cpu().numpy(), counts.astype(np.int32)), "per-expert counts"
+    row_of = p["row_of"].cpu().numpy()
+    assert np.array_equal(row_of >= 0, kept), "kept (token, slot) sets"
+    seg = p["seg_off"].cpu().numpy()
+    assert seg[0] == 0 and np.all(np.diff(seg) == (counts + 127) // 128 * 128)
+    n_rows = p["n_rows"].cpu().numpy()
+    assert n_rows[0] == seg[-1] and n_rows[1] == counts.sum()
+    tok, slot = p["tok_of_row"].cpu().numpy(), p["slot_of_row"].cpu().numpy()
+    te = p["tile_expert"].cpu().numpy()
+    # permutation is a bijection between kept pairs and non-padding rows, rows live in their expert's segment
+    rows = row_of[kept]
+    assert len(np.unique(rows)) == rows.size
+    s_idx, k_idx = np.nonzero(kept)
+    assert np.array_equal(tok[rows], s_idx) and np.array_equal(slot[rows], k_idx)
+    e_of = idx[s_idx, k_idx]
+    assert np.all(rows >= seg[e_of]) and np.all(rows < seg[e_of] + counts[e_of])
+    assert (tok[: n_rows[0]] >= 0).sum() == counts.sum()
+    for t in range(n_rows[0] // 128):
+        assert seg[te[t]] <= t * 128 < seg[te[t] + 1]
+    assert np.all(te[n_rows[0] // 128:] == -1)
+
+
+# ------------------------------------------------------------------------------------------------
+# grouped GEMM (tcgen05)
+# ------------------------------------------------------------------------------------------------
+def _fake_plan(counts, d):
+    E = len(counts)
+    pad = [(c + 127) // 128 * 128 for c in counts]
+    seg = np.concatenate([[0], np.cumsum(pad)]).astype(np.int32)
+    max_rows = int(seg[-1]) + 256                        # spare tiles past the end must be skipped
+    te = -np.ones(max_rows // 128, dtype=np.int32)
+    for e in range(E):
+        te[seg[e] // 128: seg[e + 1] // 128] = e
+    valid = np.zeros(max_rows, dtype=bool)
+    for e in range(E):
+        valid[seg[e]: seg[e] + counts[e]] = True
+    plan = dict(tile_expert=torch.from_numpy(te).to(d), n_rows=torch.tensor([int(seg[-1]), int(sum(counts))], dtype=torch.int32, device=d),
+                seg_off=torch.from_numpy(seg).to(d), max_rows=max_rows)
+    return plan, seg, te, valid
+
+
+@pytest.mark.parametrize("N,K,counts", [(128, 64, [128, 0, 200]), (2816, 704, [640, 1, 300, 0, 129, 640, 77, 5]),
+                                        (704, 2816, [300, 640]), (160, 96, [50, 70, 0, 128]), (256, 1600, [130, 10])])
+@pytest.mark.parametrize("mode", ["nt", "nn"])
+def test_grouped_gemm_rows(mode, N, K, counts):
+    from apertis_llm_b200 import _lib, ops
+    d = dev()
+    E = len(counts)
+    plan, seg, te, valid = _fake_plan(counts, d)
+    g = torch.Generator().manual_seed(N + K)
+    A = (torch.randn(plan["max_rows"], K, generator=g) * 0.5).to(torch.bfloat16)
+    A[~torch.from_numpy(valid)] = 0
+    W = (torch.randn(E, N, K, generator=g) * 0.05).to(torch.bfloat16) if mode == "nt" else (torch.randn(E, K, N, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(E, N, generator=g) * 0.1
+    Ad, Wd, bd = A.to(d), W.to(d), bias.to(d)
+    total = int(seg[-1])
+    ref = torch.zeros(total, N, dtype=torch.float32)
+    for e in range(E):
+        a = A[seg[e]:seg[e + 1]].float()
+        ref[seg[e]:seg[e + 1]] = a @ (W[e].float().t() if mode == "nt" else W[e].float())
+    # plain
+    c = ops.grouped_gemm(mode, Ad, Wd, plan, N, K, E, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_err(c[:total], ref) < 2e-5, "fp32 accumulate of bf16 operands"
+    # bias + gelu with bf16 outputs
+    erow = torch.from_numpy(np.repeat(te[: total // 128], 128)).long()
+    pre = (ref + bias[erow]).to(torch.bfloat16).float()
+    h, hpre = ops.grouped_gemm(mode, Ad, Wd, plan, N, K, E, bias=bd, epi=_lib.EPI_BIAS_ACT, act=0, out_dtype=torch.bfloat16, want_c2=True)
+    assert rel_err(hpre[:total].float(), pre) < 1e-2
+    assert rel_err(h[:total].float(), F.gelu(pre)) < 1e-2
+    # d-activation epilogue against a saved pre-activation
+    aux = (torch.randn(plan["max_rows"], N, generator=g)).to(torch.bfloat16)
+    dact = ops.grouped_gemm(mode, Ad, Wd, plan, N, K, E, aux=aux.to(d), epi=_lib.EPI_DACT, act=0, out_dtype=torch.float32)
+    xg = aux[:total].float().requires_grad_(True)
+    F.gelu(xg).sum().backward()
+    assert rel_err(dact[:total], ref * xg.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,counts", [(128, 64, [128, 0, 200]), (2816, 704, [640, 1, 300]), (704, 2816, [300, 640]),
+                                        (160, 96, [50, 70, 0, 128])])
+def test_grouped_gemm_tn(M, N, counts):
+    from apertis_llm_b200 import ops
+    d = dev()
+    E = len(counts)
+    plan, seg, te, valid = _fake_plan(counts, d)
+    g = torch.Generator().manual_seed(M + N)
+    A = (torch.randn(plan["max_rows"], M, generator=g) * 0.5).to(torch.bfloat16)
+    Bm = (torch.randn(plan["max_rows"], N, generator=g) * 0.5).to(torch.bfloat16)
+    A[~torch.from_numpy(valid)] = 0                       # padding rows of one operand are zero by construction
+    out = ops.grouped_gemm_tn(A.to(d), Bm.to(d), plan["seg_off"], M, N, E)
+    torch.cuda.synchronize()
+    for e in range(E):
+        ref = A[seg[e]:seg[e + 1]].float().t() @ Bm[seg[e]:seg[e + 1]].float()
+        assert rel_err(out[e], ref) < 2e-5 if counts[e] else float(out[e].abs().max()) == 0.0, e

@@ -1,0 +1,233 @@
+"""Module-level parity on the B200: the drop-in modules against the golden fixtures recorded from the
+unmodified reference (tests/golden) and against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import apertis_oracle as O
+from tests.util import load_golden, rel_err, sample
+
+pytestmark = pytest.mark.gpu
+
+BLOCK_CASES = ["block_small_train", "block_small_eval", "block_relu_e4", "block_drop_expert", "block_h3_ragged", "block_c1dims"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def build_layer(spec, sd=None, dropout=0.0):
+    from apertis_llm_b200 import ApertisLayerB200, BlockConfig
+    cfg = BlockConfig(hidden_size=spec["Dm"], num_attention_heads=spec["H"], intermediate_size=spec["I"],
+                      num_experts=spec["E"], experts_per_token=spec["K"], hidden_dropout_prob=dropout,
+                      hidden_act=spec.get("act", "gelu"))
+    layer = ApertisLayerB200(cfg)
+    if sd is None:
+        sd = O.make_layer_params(spec["Dm"], spec["H"], spec["I"], spec["E"], seed=spec["seed"])
+    layer.load_state_dict(sd, strict=True)          # reference key names -> stacked expert parameters
+    return layer.to(dev()), sd
+
+
+def set_rng_hooks(layer, spec, noise):
+    ffn = layer.feed_forward.ffn
+    ffn._draw_noise = lambda S, E, device: noise.to(device)
+    if spec.get("perm") is not None:
+        E = spec["E"]
+        ndrop = int(np.floor(E * 0.1))
+        act = torch.ones(E, dtype=torch.int32)
+        act[torch.tensor(spec["perm"][:ndrop])] = 0
+        ffn._draw_active_mask = lambda device: act.to(device)
+
+
+def named_grads(layer):
+    """Gradients keyed like the reference's named_parameters()."""
+    sd = {}
+    for k, p in layer.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        sd[k] = g
+    out = {}
+    ffn = layer.feed_forward.ffn
+    for k, g in sd.items():
+        leaf = k.split(".")[-1]
+        if leaf in ffn._STACKED:
+            for e in range(g.shape[0]):
+                out[f"feed_forward.ffn.experts.{e}.{ffn._STACKED[leaf]}"] = g[e]
+        else:
+            out[k] = g
+    return out
+
+
+def run_block(spec, g, autocast):
+    layer, sd = build_layer(spec)
+    x, noise = O.make_inputs(spec["B"], spec["L"], spec["Dm"], spec["E"], seed=spec["seed"])
+    training = spec.get("training", True)
+    layer.train(training)
+    set_rng_hooks(layer, spec, noise)
+    xg = x.to(dev()).requires_grad_(training)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out, _, _, lb, rz = layer(xg)
+    grads = None
+    if training:
+        O.block_loss(out, lb, rz).backward()
+        grads = named_grads(layer)
+    torch.cuda.synchronize()
+    return layer, out, lb, rz, xg, grads
+
+
+@pytest.mark.parametrize("name", BLOCK_CASES)
+def test_block_fp32_matches_reference(name):
+    spec, g = load_golden(name)
+    layer, out, lb, rz, xg, grads = run_block(spec, g, autocast=False)
+    ffn = layer.feed_forward.ffn
+    # integer artefacts first: they must be bit-exact
+    S = spec["B"] * spec["L"]
+    training = spec.get("training", True)
+    cap = O.moe_capacity(S, spec["E"], 1.25, training)
+    active = None
+    if spec.get("perm") is not None:
+        active = np.ones(spec["E"], dtype=bool)
+        active[np.array(spec["perm"][: int(np.floor(spec["E"] * 0.1))])] = False
+    kept, counts, _ = O.moe_plan(g["idx"], g["w"], spec["E"], cap, active)
+    assert np.array_equal(ffn.last_counts.cpu().numpy(), counts.astype(np.int32)), "expert_token_counts_post_capacity"
+    assert rel_err(out.float(), g["out"]) < 1e-4, "block output"
+    assert abs(float(lb) - float(g["lb"])) < 1e-4 * max(abs(float(g["lb"])), 1e-3)
+    assert abs(float(rz) - float(g["rz"])) < 1e-4 * max(abs(float(g["rz"])), 1e-3)
+    if not training:
+        return
+    assert rel_err(xg.grad, g["dx"]) < 1e-4, "dx"
+    for k, gr in grads.items():
+        if "grad/" + k in g:
+            assert rel_err(gr, g["grad/" + k]) < 1e-4, k
+        else:
+            assert rel_err(sample(gr), g["gsample/" + k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("name", ["block_small_train", "block_h3_ragged", "block_c1dims", "block_small_eval"])
+def test_block_bf16_autocast_within_tolerance(name):
+    spec, g = load_golden(name)
+    layer, out, lb, rz, xg, grads = run_block(spec, g, autocast=True)
+    assert rel_err(out.float(), g["out"]) < 2e-2
+    if not spec.get("training", True):
+        return
+    assert rel_err(xg.grad, g["dx"]) < 2e-2
+    bad = []
+    for k, gr in grads.items():
+        ref = g["grad/" + k] if "grad/" + k in g else None
+        err = rel_err(gr, ref) if ref is not None else rel_err(sample(gr), g["gsample/" + k])
+        if err >= 2e-2:
+            bad.append((k, err))
+    assert not bad, bad
+
+
+def test_router_indices_bit_exact_vs_reference():
+    """Indices recorded from the reference's own torch.topk equal the CUDA router's on the same block input."""
+    from apertis_llm_b200 import ops
+    for name in BLOCK_CASES:
+        spec, g = load_golden(name)
+        sd = O.make_layer_params(spec["Dm"], spec["H"], spec["I"], spec["E"], seed=spec["seed"])
+        _, moe, _ = O.split_layer_params(sd)
+        _, noise = O.make_inputs(spec["B"], spec["L"], spec["Dm"], spec["E"], seed=spec["seed"])
+        training = spec.get("training", True)
+        d = dev()
+        ns = (torch.nn.functional.softplus(moe["w_noise"]) * 0.1).to(d)
+        r = ops.moe_route(torch.from_numpy(g["moe_in"]).to(d), moe["router_norm.weight"].to(d), moe["router_norm.bias"].to(d), 1e-12,
+                          moe["router.weight"].to(d), moe["router.bias"].to(d), noise.to(d) if training else None,
+                          ns if training else None, spec["K"])
+        assert np.array_equal(r["idx"].cpu().numpy(), g["idx"].astype(np.int32)), name
+        assert rel_err(r["w"], g["w"]) < 1e-5, name
+        assert rel_err(r["logits"], g["logits"]) < 1e-5, name
+
+
+def test_ssm_train_and_eval_vs_reference():
+    from apertis_llm_b200 import BlockConfig, SelectiveLinearAttention
+    spec, g = load_golden("ssm_scans_l512")
+    sd = O.make_layer_params(spec["Dm"], spec["H"], spec["I"], spec["E"], seed=spec["seed"])
+    ssm_sd, _, _ = O.split_layer_params(sd)
+    cfg = BlockConfig(hidden_size=spec["Dm"], num_attention_heads=spec["H"], intermediate_size=spec["I"])
+    for mode in (0, 1):
+        m = SelectiveLinearAttention(cfg)
+        m.load_state_dict(ssm_sd, strict=True)
+        m = m.to(dev()).train()
+        m.scan_mode = mode
+        x, _ = O.make_inputs(spec["B"], spec["L"], spec["Dm"], spec["E"], seed=spec["seed"])
+        xg = x.to(dev()).requires_grad_(True)
+        out, y, _ = m(xg, output_attentions=True)
+        (out.pow(2).mean() + y.pow(2).mean()).backward()
+        assert rel_err(out, g["train_out"]) < 1e-4 and rel_err(y, g["train_y"]) < 1e-4
+        assert rel_err(xg.grad, g["dx"]) < 1e-4
+        for k, p in m.named_parameters():
+            assert rel_err(p.grad, g["grad/" + k]) < 1e-4, (mode, k)
+        m.eval()
+        with torch.no_grad():
+            out2, y2, _ = m(xg.detach(), output_attentions=True)
+        assert rel_err(out2, g["eval_out"]) < 1e-4 and rel_err(y2, g["eval_y"]) < 1e-4
+
+
+def test_ssm_cached_decode_vs_reference():
+    from apertis_llm_b200 import BlockConfig, SelectiveLinearAttention
+    spec, g = load_golden("ssm_cache_decode")
+    sd = O.make_layer_params(spec["Dm"], spec["H"], spec["I"], spec["E"], seed=spec["seed"])
+    ssm_sd, _, _ = O.split_layer_params(sd)
+    m = SelectiveLinearAttention(BlockConfig(hidden_size=spec["Dm"], num_attention_heads=spec["H"]))
+    m.load_state_dict(ssm_sd, strict=True)
+    m = m.to(dev()).eval()
+    x, _ = O.make_inputs(spec["B"], spec["L"] + spec["steps"], spec["Dm"], spec["E"], seed=spec["seed"])
+    x = x.to(dev())
+    with torch.no_grad():
+        full, yfull, _ = m(x, output_attentions=True)
+        assert rel_err(full, g["full_out"]) < 1e-4 and rel_err(yfull, g["full_y"]) < 1e-4
+        out, y, cache = m(x[:, :spec["L"]], output_attentions=True, use_cache=True)
+        assert rel_err(out, g["prefill_out"]) < 1e-4
+        assert rel_err(cache[0], g["prefill_conv"]) < 1e-5 and rel_err(cache[1], g["prefill_h"]) < 1e-4
+        for s in range(spec["steps"]):
+            out, y, cache = m(x[:, spec["L"] + s: spec["L"] + s + 1], past_key_value=cache, output_attentions=True, use_cache=True)
+            assert rel_err(out, g[f"step{s}_out"]) < 1e-4, s
+            assert rel_err(cache[0], g[f"step{s}_conv"]) < 1e-5 and rel_err(cache[1], g[f"step{s}_h"]) < 1e-4, s
+
+
+def test_state_dict_round_trip_uses_reference_keys():
+    spec, _ = load_golden("block_small_train")
+    layer, sd = build_layer(spec)
+    out_sd = layer.state_dict()
+    assert set(out_sd) == set(sd)
+    for k in sd:
+        assert torch.equal(out_sd[k].cpu(), sd[k]), k
+
+
+def test_block_is_deterministic():
+    spec, g = load_golden("block_small_train")
+    outs = []
+    for _ in range(2):
+        layer, out, lb, rz, xg, grads = run_block(spec, g, autocast=True)
+        outs.append((out.detach().clone(), xg.grad.clone(), {k: v.clone() for k, v in grads.items()}))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for k in outs[0][2]:
+        assert torch.equal(outs[0][2][k], outs[1][2][k]), k
+
+
+def test_block_medium_vs_oracle_fp32():
+    """C2-like widths at a reduced token count against the CPU oracle (seconds on CPU)."""
+    spec = dict(Dm=704, H=11, I=2816, E=8, K=2, B=2, L=384, seed=11)
+    layer, sd = build_layer(spec)
+    x, noise = O.make_inputs(spec["B"], spec["L"], spec["Dm"], spec["E"], seed=spec["seed"])
+    layer.train()
+    set_rng_hooks(layer, spec, noise)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    out_r, lb_r, rz_r = O.block_forward(sdr, xr, num_heads=spec["H"], E=spec["E"], K=spec["K"], training=True, noise=noise)
+    O.block_loss(out_r, lb_r, rz_r).backward()
+    xg = x.to(dev()).requires_grad_(True)
+    out, _, _, lb, rz = layer(xg)
+    O.block_loss(out, lb, rz).backward()
+    assert rel_err(out, out_r.detach()) < 1e-4
+    assert rel_err(xg.grad, xr.grad) < 1e-4
+    grads = named_grads(layer)
+    for k, gr in grads.items():
+        assert rel_err(gr, sdr[k].grad) < 1e-4, k
+
+
+def test_no_cpu_fallback():
+    from apertis_llm_b200 import BlockConfig, SelectiveLinearAttention
+    m = SelectiveLinearAttention(BlockConfig(hidden_size=64, num_attention_heads=2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 4, 64))
