@@ -134,11 +134,53 @@ def ensure_device(device) -> None:
     _checked_devices.add(idx)
 
 
+# kernels launched by one call of each entry point (memsets not counted)
+KERNELS_PER_CALL = {
+    "ab_causal_conv1d_silu_fwd": 1, "ab_causal_conv1d_silu_bwd": 2,
+    "ab_selective_scan_fwd": 1, "ab_selective_scan_bwd": 2,          # single pass; two pass adds 2
+    "ab_moe_router_fwd": 2, "ab_moe_topk_from_logits": 1, "ab_moe_plan": 2, "ab_moe_permute_ln": 1, "ab_moe_unpermute": 1,
+    "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,
+    "ab_grouped_gemm_nt": 1, "ab_grouped_gemm_nn": 1, "ab_grouped_gemm_tn": 1, "ab_cast_f32_to_bf16": 1,
+    "ab_split_f32_to_bf16x3": 1, "ab_split_f32_to_bf16x3_rows": 1,
+}
+launch_count = 0          # kernels launched through this binding since import (bench.py reads deltas)
+_timed = None             # None, or {"names": set, "events": [(name, start, end), ...]} while bench.py profiles
+
+
+def start_timing(names):
+    """Record CUDA events (on the launching stream) around every call of the given entry points."""
+    global _timed
+    _timed = {"names": set(names), "events": []}
+
+
+def stop_timing():
+    """-> {name: [ms per call, ...]} for the calls recorded since start_timing(); synchronises."""
+    global _timed
+    t, _timed = _timed, None
+    out = {}
+    if t is None:
+        return out
+    torch.cuda.synchronize()
+    for name, a, b in t["events"]:
+        out.setdefault(name, []).append(a.elapsed_time(b))
+    return out
+
+
 def call(name: str, *args):
     """Calls an int-returning entry point; non-zero -> RuntimeError carrying ab_last_error()."""
-    rc = getattr(load(), name)(*args)
+    global launch_count
+    fn = getattr(load(), name)
+    if _timed is not None and name in _timed["names"]:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _timed["events"].append((name, a, b))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
+    launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
 def query(name: str, *args):

@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: Apertis SSM+MoE block forward+backward tokens/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path (ApertisLayer = pre-norm + SelectiveLinearAttention + residual,
+pre-norm + AdaptiveExpertSystem + residual; forward, synthetic loss of SURVEY.md 8(d), backward) over one
+batch of synthetic tokens.  Workload = BASELINE.json configs[1]: the 1.5B text-only Apertis block
+(hidden 704, 11 heads, d_inner 176, intermediate 2816, 8 experts top-2), seq 4096, bf16 autocast over fp32
+master weights (the only low-precision mode the reference supports).
+
+N > 1 (torchrun, one rank per GPU): experts sharded E/N per rank with NCCL all-to-all dispatch/combine, every
+rank keeps its own batch (weak scaling), replicated-parameter gradients all-reduced as DDP would.
+
+--impl reference times the reference's algorithm on the host CPU: the oracle port (oracle/apertis_oracle.py,
+same ATen op sequence as core.py) with all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (Dm, H, I, E, K, seq)      shapes from SURVEY.md section 8 / BASELINE.md section 3
+    "c1_125m": (256, 4, 1024, 8, 2, 1024),
+    "c2_1p5b": (704, 11, 2816, 8, 2, 4096),
+    "c4_7b": (1600, 25, 6400, 8, 2, 4096),
+}
+METRIC = "SSM+MoE block fwd+bwd tokens/sec"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def __enter__(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        try:
+            self.f.flush()
+            for line in open(self.f.name):
+                c = [t.strip() for t in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(args, wl, steps, warmup, sample_tokens):
+    """Oracle port of the reference block on the host cores (fp32, dropout 0): tokens/s on a bounded sample."""
+    from oracle import apertis_oracle as O
+    Dm, H, I, E, K, seq = wl
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    L = min(seq, sample_tokens)
+    Bsz = max(1, sample_tokens // L)
+    sd = {k: v.requires_grad_(True) for k, v in O.make_layer_params(Dm, H, I, E, seed=0).items()}
+    x, noise = O.make_inputs(Bsz, L, Dm, E, seed=0)
+    x.requires_grad_(True)
+
+    def step():
+        for p in sd.values():
+            p.grad = None
+        x.grad = None
+        out, lb, rz = O.block_forward(sd, x, num_heads=H, E=E, K=K, training=True, noise=noise)
+        O.block_loss(out, lb, rz).backward()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return Bsz * L / dt, dt * 1e3, cores, f"{Bsz}x{L} tokens per step, fp32, {steps} steps after {warmup} warm-up, torch {torch.__version__} CPU ops"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_1p5b", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=8, help="sequences per GPU per step")
+    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-sample-tokens", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    Dm, H, I, E, K, seq = wl
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_common = {"workload": f"{args.workload}: Apertis block hidden {Dm}, heads {H}, d_inner {16 * H}, intermediate {I}, "
+                              f"{E} experts top-{K}, seq {seq}", "tokens_per_step_per_gpu": args.batch * seq}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        v, ms, cores, sample = cpu_reference_arm(args, wl, steps, warmup, args.cpu_sample_tokens)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": dict(cfg_common, tokens_per_step_per_gpu=None, sample=sample),
+                          "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch.distributed as dist
+    from apertis_llm_b200 import ApertisLayerB200, BlockConfig, _lib
+    from oracle import apertis_oracle as O   # only for the deterministic parameter factory and the cpu_baseline leg
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ep_group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ep_group = dist.group.WORLD
+    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun"
+
+    cfg = BlockConfig(hidden_size=Dm, num_attention_heads=H, intermediate_size=I, num_experts=E, experts_per_token=K,
+                      hidden_dropout_prob=args.dropout)
+    layer = ApertisLayerB200(cfg, ep_group=ep_group)
+    sd = O.make_layer_params(Dm, H, I, E, seed=0, perturb=False)       # the reference initialiser's distributions
+    layer.load_state_dict(sd, strict=True)
+    layer = layer.to(dev).train()
+    replicated = [p for n, p in layer.named_parameters() if ".expert_" not in n]
+
+    B = args.batch
+    tokens_per_step = B * seq
+    nbuf = 4
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_x = [torch.randn(B, seq, Dm, generator=gen).pin_memory() for _ in range(nbuf)]
+    dev_x = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host_x]
+    amp = args.dtype == "bf16"
+
+    def step(x):
+        for p in layer.parameters():
+            p.grad = None
+        x.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            out, _, _, lb, rz = layer(x)
+        loss = out.float().pow(2).mean() + lb + rz
+        loss.backward()
+        if world > 1:                                   # DDP-equivalent all-reduce of the replicated parameters' grads
+            flat = torch.cat([p.grad.reshape(-1) for p in replicated])
+            dist.all_reduce(flat)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(dev_x[i % nbuf])
+    barrier()
+
+    # ---- timed region: device-resident inputs, CUDA events, per-kernel events for the roofline
+    timed_names = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_selective_scan_fwd", "ab_selective_scan_bwd"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        _lib.start_timing(timed_names)
+        e0.record()
+        for i in range(args.steps):
+            step(dev_x[i % nbuf])
+        e1.record()
+        barrier()
+        per_kernel = _lib.stop_timing()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.launch_count - launches0
+    clocks = clk.summary()
+    kept = int(layer.feed_forward.ffn.last_counts.sum().item())        # A_kept of the last step (rows through the experts)
+
+    # ---- end to end: pinned host input -> device every step (prefetched on a copy stream), loss read back
+    copy_stream = torch.cuda.Stream()
+    stage = [torch.empty(B, seq, Dm, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            stage[i % 2].copy_(host_x[i % nbuf], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    for c in consumed:
+        c.record()
+    barrier()
+    t0 = time.perf_counter()
+    prefetch(0)
+    last = 0.0
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        x = stage[i % 2].detach().requires_grad_(True)
+        loss = step(x)
+        consumed[i % 2].record()
+        last = loss.item()                              # device -> host read of the step's result
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+        k = torch.tensor([kept], device=dev, dtype=torch.int64)
+        dist.all_reduce(k)
+        kept_total = int(k.item())
+    else:
+        kept_total = kept
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    gemm_ms = sum(sum(per_kernel.get(n, [])) for n in timed_names[:3]) / args.steps
+    scan_ms = sum(sum(per_kernel.get(n, [])) for n in timed_names[3:]) / args.steps
+    n_gemm = sum(len(per_kernel.get(n, [])) for n in timed_names[:3]) / args.steps
+    gemm_flops = 12.0 * Dm * I * (kept_total / world)                    # per GPU per step
+    es = 2 if amp else 4
+    scan_bytes = tokens_per_step * (14 * 16 * H + 3 * H) * es           # fwd+bwd algorithmic bytes
+    gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    roofline = {"kernel": "grouped_gemm_kernel<NT|NN|TN> (tcgen05 expert GEMM: 2 fwd + 2 dgrad + 2 wgrad launches per step)",
+                "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_src + ", sustained bf16",
+                "ms_per_step_in_kernel": gemm_ms, "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms,
+                "algorithmic_flops_per_step": gemm_flops, "kept_rows_per_step": kept_total / world}
+    kernels = {"selective_scan_fwd+bwd": {"bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                           "frac": scan_gbs / pk["hbm_gbs"], "ms_per_step_in_kernel": scan_ms,
+                                           "algorithmic_bytes_per_step": scan_bytes, "share_of_step": scan_ms / ms}}
+    out = {"metric": METRIC, "value": tokens_per_step * world / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+           "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+           "config": dict(cfg_common, global_batch_tokens=tokens_per_step * world, hidden_dropout_prob=args.dropout,
+                          parallelism=("single GPU" if world == 1 else f"ep{world} (experts sharded, all-to-all) + dp{world}"),
+                          precision="bf16 autocast over fp32 master weights" if amp else "fp32 (3x bf16-split tensor-core GEMMs)",
+                          l2="inputs rotate over 4 buffers (%.0f MB > 126 MB L2); per-step activations ~GBs" % (nbuf * B * seq * Dm * 4 / 1e6)),
+           "clocks": clocks,
+           "e2e": {"value": tokens_per_step * world / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": B * seq * Dm * 4, "d2h_bytes_per_step": 4,
+                   "how": "pinned host x -> device each step (prefetched on a copy stream), block fwd+bwd through the module API, loss.item()"},
+           "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "last_loss": last}
+    if not args.no_cpu_baseline:
+        v, cms, cores, sample = cpu_reference_arm(args, wl, 3, 1, args.cpu_sample_tokens)
+        out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
