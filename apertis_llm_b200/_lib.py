@@ -56,6 +56,9 @@ SIGNATURES = {
     "ab_grouped_gemm_nt": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, P]),
     "ab_grouped_gemm_nn": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, P]),
     "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, P]),
+    "ab_layernorm_fwd": (I, [P, P, P, F, P, P, I, I, I, I, P]),
+    "ab_layernorm_bwd_workspace_bytes": (SZ, [I, I]),
+    "ab_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, P]),
     "ab_cast_f32_to_bf16": (I, [P, P, I64, P]),
     "ab_split_f32_to_bf16x3": (I, [P, P, I64, I64, I, P]),
     "ab_split_f32_to_bf16x3_rows": (I, [P, P, P, I, I64, I64, I, P]),
@@ -140,6 +143,7 @@ KERNELS_PER_CALL = {
     "ab_selective_scan_fwd": 1, "ab_selective_scan_bwd": 2,          # single pass; two pass adds 2
     "ab_moe_router_fwd": 2, "ab_moe_topk_from_logits": 1, "ab_moe_plan": 2, "ab_moe_permute_ln": 1, "ab_moe_unpermute": 1,
     "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,
+    "ab_layernorm_fwd": 1, "ab_layernorm_bwd": 3,
     "ab_grouped_gemm_nt": 1, "ab_grouped_gemm_nn": 1, "ab_grouped_gemm_tn": 1, "ab_cast_f32_to_bf16": 1,
     "ab_split_f32_to_bf16x3": 1, "ab_split_f32_to_bf16x3_rows": 1,
 }

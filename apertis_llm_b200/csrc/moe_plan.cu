@@ -9,11 +9,18 @@ namespace {
 
 constexpr int PLAN_THREADS = 1024;
 
-// exclusive prefix of a 0/1 flag over the CTA (in thread order) + CTA total; two __syncthreads
-__device__ __forceinline__ int block_excl_scan(bool flag, int* warp_tot /*[32]*/, int& total) {
+constexpr int TPT = 4;   // tokens per thread per sweep iteration
+
+// exclusive prefix of a small per-thread count over the CTA (thread order) + CTA total; two __syncthreads
+__device__ __forceinline__ int block_excl_scan(int cnt, int* warp_tot /*[32]*/, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned ball = __ballot_sync(0xffffffffu, flag);
-    if (lane == 0) warp_tot[warp] = __popc(ball);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
     int before = 0, tot = 0;
     const int nw = blockDim.x >> 5;
@@ -24,31 +31,39 @@ __device__ __forceinline__ int block_excl_scan(bool flag, int* warp_tot /*[32]*/
     }
     __syncthreads();
     total = tot;
-    return before + __popc(ball & ((1u << lane) - 1u));
+    return before + inc - cnt;
 }
 
 // One CTA per expert.  row_local[s,k] = position of the kept (token, slot) inside the expert's segment, -1 if dropped.
+// A thread owns TPT consecutive tokens per sweep iteration, so positions stay in token order.
 __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w,
                                                                   const int32_t* __restrict__ active, int cap,
                                                                   int32_t* __restrict__ counts, int32_t* __restrict__ row_local,
                                                                   int S, int K) {
     __shared__ int hist[256];
     __shared__ int warp_tot[32];
-    __shared__ int s_sel_bin, s_need;
+    __shared__ int s_sel_bin, s_need, s_ncand;
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
     const bool is_active = active == nullptr || active[e] != 0;
+    const int span = blockDim.x * TPT;
     int kept_total = 0;
     for (int k = 0; k < K; ++k) {
-        // ---- candidates of this (slot, expert) group
-        int n_cand = 0;
-        for (int s0 = 0; s0 < S; s0 += blockDim.x) {
-            const int s = s0 + tid;
-            const bool c = s < S && idx[(size_t)s * K + k] == e;
-            int tot;
-            block_excl_scan(c, warp_tot, tot);
-            n_cand += tot;
+        // ---- candidates of this (slot, expert) group + histogram of the top byte in the same sweep
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int s = tid; s < S; s += blockDim.x) {
+            if (idx[(size_t)s * K + k] == e) {
+                ++mine;
+                atomicAdd(&hist[__float_as_uint(w[(size_t)s * K + k]) >> 24], 1);
+            }
         }
+        mine = (int)ab_warp_sum((float)mine);      // exact: counts < 2^24
+        if ((tid & 31) == 0 && mine) atomicAdd(&s_ncand, mine);
+        __syncthreads();
+        const int n_cand = s_ncand;
         const int rem = cap - kept_total;
         int mode = 0;                       // 0 none, 1 all, 2 select the `rem` largest
         if (is_active && n_cand > 0 && rem > 0) mode = n_cand <= rem ? 1 : 2;
@@ -59,15 +74,17 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t*
             uint32_t prefix = 0, mask = 0;
             int need = rem;
             for (int pass = 3; pass >= 0; --pass) {
-                for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-                __syncthreads();
-                for (int s = tid; s < S; s += blockDim.x) {
-                    if (idx[(size_t)s * K + k] == e) {
-                        const uint32_t b = __float_as_uint(w[(size_t)s * K + k]);
-                        if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
+                if (pass != 3) {
+                    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+                    __syncthreads();
+                    for (int s = tid; s < S; s += blockDim.x) {
+                        if (idx[(size_t)s * K + k] == e) {
+                            const uint32_t b = __float_as_uint(w[(size_t)s * K + k]);
+                            if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
                 if (tid == 0) {
                     int nd = need, bin = 255;
                     for (; bin > 0; --bin) {
@@ -88,21 +105,41 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t*
         }
         // ---- positions in token order
         int run_eq = 0, run_kept = 0;
-        for (int s0 = 0; s0 < S; s0 += blockDim.x) {
-            const int s = s0 + tid;
-            const bool c = s < S && idx[(size_t)s * K + k] == e;
-            const uint32_t b = c ? __float_as_uint(w[(size_t)s * K + k]) : 0u;
-            const bool gt = c && (mode == 1 || (mode == 2 && b > tau));
-            const bool eq = c && mode == 2 && b == tau;
-            int tot_eq, tot_kept;
-            const int eq_rank = run_eq + block_excl_scan(eq, warp_tot, tot_eq);
-            const bool kept = gt || (eq && eq_rank < n_eq_take);
-            const int pos = kept_total + run_kept + block_excl_scan(kept, warp_tot, tot_kept);
-            if (c) row_local[(size_t)s * K + k] = kept ? pos : -1;
+        for (int s0 = 0; s0 < S; s0 += span) {
+            const int sb = s0 + tid * TPT;
+            bool c[TPT], gt[TPT], eq[TPT];
+            int n_eq = 0;
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                const int s = sb + t;
+                c[t] = s < S && idx[(size_t)s * K + k] == e;
+                const uint32_t b = c[t] ? __float_as_uint(w[(size_t)s * K + k]) : 0u;
+                gt[t] = c[t] && (mode == 1 || (mode == 2 && b > tau));
+                eq[t] = c[t] && mode == 2 && b == tau;
+                n_eq += eq[t];
+            }
+            int tot_eq = 0, tot_kept = 0;
+            int eq_rank = run_eq;
+            if (mode == 2) eq_rank += block_excl_scan(n_eq, warp_tot, tot_eq);
+            bool kept[TPT];
+            int n_kept = 0;
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                kept[t] = gt[t] || (eq[t] && eq_rank < n_eq_take);
+                eq_rank += eq[t];
+                n_kept += kept[t];
+            }
+            int pos = kept_total + run_kept + block_excl_scan(n_kept, warp_tot, tot_kept);
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                if (c[t]) row_local[(size_t)(sb + t) * K + k] = kept[t] ? pos : -1;
+                pos += kept[t];
+            }
             run_eq += tot_eq;
             run_kept += tot_kept;
         }
         kept_total += run_kept;
+        __syncthreads();
     }
     if (tid == 0) counts[e] = kept_total;
 }
@@ -252,101 +289,143 @@ __global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm backward per permuted row + per-tile partial sums of the affine grads (CTA per row tile)
+// LayerNorm backward per permuted row (warp per row) and per-tile partial sums of the affine grads
 // ---------------------------------------------------------------------------------------------
 template <typename TX, typename TG>
-__global__ void __launch_bounds__(256) permute_ln_bwd_kernel(const TG* __restrict__ dxn, const TX* __restrict__ x,
-                                                             const float* __restrict__ stats, const float* __restrict__ ln_w,
-                                                             const int32_t* __restrict__ tok_of_row,
-                                                             const int32_t* __restrict__ tile_expert,
-                                                             const int32_t* __restrict__ n_rows, float* __restrict__ dxrow,
-                                                             float* __restrict__ part, int Dm, int align) {
-    extern __shared__ float sm[];       // [align] tok (as int), [align] mean, [align] rstd
-    int* s_tok = reinterpret_cast<int*>(sm);
-    float* s_mean = sm + align;
-    float* s_rstd = sm + 2 * align;
-    const int t = blockIdx.x;
-    if ((int64_t)t * align >= n_rows[0]) return;
-    const int e = tile_expert[t];
-    if (e < 0) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const float* g = ln_w + (size_t)e * Dm;
-    for (int i = warp; i < align; i += wpb) {
-        const int r = t * align + i;
+__global__ void __launch_bounds__(256) permute_ln_bwd_rows_kernel(const TG* __restrict__ dxn, const TX* __restrict__ x,
+                                                                  const float* __restrict__ stats, const float* __restrict__ ln_w,
+                                                                  const int32_t* __restrict__ tok_of_row,
+                                                                  const int32_t* __restrict__ tile_expert,
+                                                                  const int32_t* __restrict__ n_rows, float* __restrict__ dxrow,
+                                                                  int Dm, int align) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int total = n_rows[0];
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
         const int tok = tok_of_row[r];
-        if (lane == 0) s_tok[i] = tok;
         if (tok < 0) continue;
+        const int e = tile_expert[r / align];
+        const float* g = ln_w + (size_t)e * Dm;
         const float mean = stats[2 * (size_t)tok], rstd = stats[2 * (size_t)tok + 1];
-        if (lane == 0) { s_mean[i] = mean; s_rstd[i] = rstd; }
         const TX* xr = x + (size_t)tok * Dm;
         const TG* gr = dxn + (size_t)r * Dm;
         float a1 = 0.f, a2 = 0.f;
-        for (int d = lane; d < Dm; d += 32) {
-            const float dh = ab_to_float(gr[d]) * __ldg(g + d);
-            const float xh = (ab_to_float(xr[d]) - mean) * rstd;
-            a1 += dh;
-            a2 = fmaf(dh, xh, a2);
+        for (int d = lane * 4; d < Dm; d += 128) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(g + d));
+            const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float dh = ab_to_float(gr[d + v]) * gg[v];
+                const float xh = (ab_to_float(xr[d + v]) - mean) * rstd;
+                a1 += dh;
+                a2 = fmaf(dh, xh, a2);
+            }
         }
         const float m1 = ab_warp_sum(a1) / (float)Dm, m2 = ab_warp_sum(a2) / (float)Dm;
         float* orow = dxrow + (size_t)r * Dm;
-        for (int d = lane; d < Dm; d += 32) {
-            const float dh = ab_to_float(gr[d]) * __ldg(g + d);
-            const float xh = (ab_to_float(xr[d]) - mean) * rstd;
-            orow[d] = rstd * (dh - m1 - xh * m2);
+        for (int d = lane * 4; d < Dm; d += 128) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(g + d));
+            const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+            float o[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float dh = ab_to_float(gr[d + v]) * gg[v];
+                const float xh = (ab_to_float(xr[d + v]) - mean) * rstd;
+                o[v] = rstd * (dh - m1 - xh * m2);
+            }
+            *reinterpret_cast<float4*>(orow + d) = make_float4(o[0], o[1], o[2], o[3]);
         }
-    }
-    __syncthreads();
-    for (int d = threadIdx.x; d < Dm; d += blockDim.x) {
-        float gw = 0.f, gb = 0.f;
-        for (int i = 0; i < align; ++i) {
-            const int tok = s_tok[i];
-            if (tok < 0) continue;
-            const float dv = ab_to_float(dxn[((size_t)t * align + i) * Dm + d]);
-            const float xh = (ab_to_float(x[(size_t)tok * Dm + d]) - s_mean[i]) * s_rstd[i];
-            gw = fmaf(dv, xh, gw);
-            gb += dv;
-        }
-        part[((size_t)t * 2 + 0) * Dm + d] = gw;
-        part[((size_t)t * 2 + 1) * Dm + d] = gb;
     }
 }
 
-// per-tile column sums (CTA per row tile)
+// grid (tiles, ceil(Dm/128)); block (32 lanes x 4 columns, 8 warps over the tile's rows)
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(256) permute_ln_bwd_cols_kernel(const TG* __restrict__ dxn, const TX* __restrict__ x,
+                                                                  const float* __restrict__ stats,
+                                                                  const int32_t* __restrict__ tok_of_row,
+                                                                  const int32_t* __restrict__ tile_expert,
+                                                                  const int32_t* __restrict__ n_rows, float* __restrict__ part,
+                                                                  int Dm, int align) {
+    __shared__ float red[8][2][128];
+    const int t = blockIdx.x;
+    if ((int64_t)t * align >= n_rows[0] || tile_expert[t] < 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.y * 128 + lane * 4;
+    float gw[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d < Dm) {
+        for (int i = warp; i < align; i += 8) {
+            const int r = t * align + i;
+            const int tok = tok_of_row[r];
+            if (tok < 0) continue;
+            const float mean = stats[2 * (size_t)tok], rstd = stats[2 * (size_t)tok + 1];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float dv = ab_to_float(dxn[(size_t)r * Dm + d + v]);
+                const float xh = (ab_to_float(x[(size_t)tok * Dm + d + v]) - mean) * rstd;
+                gw[v] = fmaf(dv, xh, gw[v]);
+                gb[v] += dv;
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { red[warp][0][lane * 4 + v] = gw[v]; red[warp][1][lane * 4 + v] = gb[v]; }
+    __syncthreads();
+    const int q = threadIdx.x >> 7, c = threadIdx.x & 127;      // 256 threads: (w|b) x 128 columns
+    float s2 = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s2 += red[wv][q][c];
+    const int dd = blockIdx.y * 128 + c;
+    if (dd < Dm) part[((size_t)t * 2 + q) * Dm + dd] = s2;
+}
+
+// per-tile column sums: grid (tiles, ceil(C/256)); block (32 lanes x 8 columns, 8 warps over the rows)
 template <typename T>
 __global__ void __launch_bounds__(256) tile_colsum_kernel(const T* __restrict__ a, const int32_t* __restrict__ tile_expert,
                                                           const int32_t* __restrict__ n_rows, float* __restrict__ part, int C,
                                                           int align) {
+    __shared__ float red[8][256];
     const int t = blockIdx.x;
     if ((int64_t)t * align >= n_rows[0] || tile_expert[t] < 0) return;
-    for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-        float s0 = 0.f, s1 = 0.f;
-        const T* col = a + (size_t)t * align * C + c;
-        if (c + 1 < C) {
-            for (int i = 0; i < align; ++i) {
-                s0 += ab_to_float(col[(size_t)i * C]);
-                s1 += ab_to_float(col[(size_t)i * C + 1]);
-            }
-            part[(size_t)t * C + c] = s0;
-            part[(size_t)t * C + c + 1] = s1;
-        } else {
-            for (int i = 0; i < align; ++i) s0 += ab_to_float(col[(size_t)i * C]);
-            part[(size_t)t * C + c] = s0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * 256 + lane * 8;
+    float acc[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+    if (c0 < C) {
+        for (int i = warp; i < align; i += 8) {
+            const T* row = a + ((size_t)t * align + i) * C + c0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc[v] += ab_to_float(row[v]);
         }
     }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) red[warp][lane * 8 + v] = acc[v];
+    __syncthreads();
+    const int c = threadIdx.x;
+    float s2 = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s2 += red[wv][c];
+    if (blockIdx.y * 256 + c < C) part[(size_t)t * C + blockIdx.y * 256 + c] = s2;
 }
 
-// out[e][j] = sum over tiles of expert e of part[t][j], fixed order.  Columns [0, split) go to out_a [E][split],
-// columns [split, ncols) to out_b [E][ncols-split].
+// out[e][j] = sum over the (contiguous) tiles of expert e of part[t][j], fixed order.  Columns [0, split) go to
+// out_a [E][split], columns [split, ncols) to out_b [E][ncols-split].
 __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t* __restrict__ tile_expert,
                                    const int32_t* __restrict__ n_rows, float* __restrict__ out_a, float* __restrict__ out_b,
                                    int split, int ncols, int align) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_t0, s_t1;
     const int e = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const int ntiles = n_rows[0] / align;
+        int t0 = ntiles, t1 = 0;
+        for (int t = 0; t < ntiles; ++t)
+            if (tile_expert[t] == e) { if (t < t0) t0 = t; t1 = t + 1; }
+        s_t0 = t0; s_t1 = t1;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
-    const int ntiles = n_rows[0] / align;
     float s = 0.f;
-    for (int t = 0; t < ntiles; ++t)
-        if (tile_expert[t] == e) s += part[(size_t)t * ncols + j];
+    for (int t = s_t0; t < s_t1; ++t) s += part[(size_t)t * ncols + j];
     if (j < split) out_a[(size_t)e * split + j] = s;
     else out_b[(size_t)e * (ncols - split) + (j - split)] = s;
 }
@@ -454,14 +533,22 @@ extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float
                                      float* dln_w, float* dln_b, void* ws, size_t ws_bytes, int Dm, int E, int row_align,
                                      int64_t max_rows, int dtype, int dxn_dtype, cudaStream_t stream) {
     AB_REQUIRE(ws && ws_bytes >= ab_moe_permute_ln_bwd_workspace_bytes(Dm, row_align, max_rows), "moe_permute_ln_bwd: workspace too small");
+    AB_REQUIRE(Dm % 4 == 0, "moe_permute_ln_bwd: hidden size must be a multiple of 4");
     const int ntiles = (int)(max_rows / row_align);
-    const size_t smem = (size_t)3 * row_align * sizeof(float);
     float* part = (float*)ws;
-#define AB_LNB(TX, TG) permute_ln_bwd_kernel<TX, TG><<<ntiles, 256, smem, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row, tile_expert, n_rows, dxrow, part, Dm, row_align)
-    if (dtype == AB_F32 && dxn_dtype == AB_F32) AB_LNB(float, float);
-    else if (dtype == AB_F32 && dxn_dtype == AB_BF16) AB_LNB(float, __nv_bfloat16);
-    else if (dtype == AB_BF16 && dxn_dtype == AB_BF16) AB_LNB(__nv_bfloat16, __nv_bfloat16);
-    else if (dtype == AB_BF16 && dxn_dtype == AB_F32) AB_LNB(__nv_bfloat16, float);
+    const int rgrid = rows_grid(max_rows);
+    dim3 cgrid(ntiles, (unsigned)ab_ceil_div(Dm, 128));
+#define AB_LNB(TX, TG)                                                                                                           \
+    {                                                                                                                            \
+        permute_ln_bwd_rows_kernel<TX, TG><<<rgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row,   \
+                                                                      tile_expert, n_rows, dxrow, Dm, row_align);              \
+        permute_ln_bwd_cols_kernel<TX, TG><<<cgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, tok_of_row,         \
+                                                                      tile_expert, n_rows, part, Dm, row_align);               \
+    }
+    if (dtype == AB_F32 && dxn_dtype == AB_F32) AB_LNB(float, float)
+    else if (dtype == AB_F32 && dxn_dtype == AB_BF16) AB_LNB(float, __nv_bfloat16)
+    else if (dtype == AB_BF16 && dxn_dtype == AB_BF16) AB_LNB(__nv_bfloat16, __nv_bfloat16)
+    else if (dtype == AB_BF16 && dxn_dtype == AB_F32) AB_LNB(__nv_bfloat16, float)
     else AB_REQUIRE(false, "moe_permute_ln_bwd: bad dtypes");
 #undef AB_LNB
     AB_LAUNCH_CHECK();
@@ -481,8 +568,10 @@ extern "C" int ab_moe_segment_colsum(const void* a, const int32_t* tile_expert, 
     AB_REQUIRE(ws && ws_bytes >= ab_moe_segment_colsum_workspace_bytes(C, row_align, max_rows), "moe_segment_colsum: workspace too small");
     const int ntiles = (int)(max_rows / row_align);
     float* part = (float*)ws;
-    if (dtype == AB_F32) tile_colsum_kernel<float><<<ntiles, 256, 0, stream>>>((const float*)a, tile_expert, n_rows, part, C, row_align);
-    else tile_colsum_kernel<__nv_bfloat16><<<ntiles, 256, 0, stream>>>((const __nv_bfloat16*)a, tile_expert, n_rows, part, C, row_align);
+    AB_REQUIRE(C % 8 == 0, "moe_segment_colsum: column count must be a multiple of 8");
+    dim3 cgrid(ntiles, (unsigned)ab_ceil_div(C, 256));
+    if (dtype == AB_F32) tile_colsum_kernel<float><<<cgrid, 256, 0, stream>>>((const float*)a, tile_expert, n_rows, part, C, row_align);
+    else tile_colsum_kernel<__nv_bfloat16><<<cgrid, 256, 0, stream>>>((const __nv_bfloat16*)a, tile_expert, n_rows, part, C, row_align);
     AB_LAUNCH_CHECK();
     dim3 grid((unsigned)ab_ceil_div(C, 128), E);
     tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, out, nullptr, C, C, row_align);

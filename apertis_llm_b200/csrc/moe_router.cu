@@ -150,12 +150,15 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
     }
 }
 
+// out[c] = sum_r part[r][c]; one warp per column, fixed order -> deterministic
 __global__ void reduce_rows_kernel(const float* __restrict__ part, int nrows, int ncols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (c >= ncols) return;
     float s = 0.f;
-    for (int r = 0; r < nrows; ++r) s += part[(size_t)r * ncols + c];
-    out[c] = s;
+    for (int r = lane; r < nrows; r += 32) s += part[(size_t)r * ncols + c];
+    s = ab_warp_sum(s);
+    if (lane == 0) out[c] = s;
 }
 
 __global__ void __launch_bounds__(WARPS * 32) topk_from_logits_kernel(const float* __restrict__ logits, float* __restrict__ gates,
@@ -293,12 +296,14 @@ __global__ void __launch_bounds__(WARPS * 32) router_bwd_kernel(const T* __restr
 }
 
 // kernel C: Q[e,d] = sum_s dlogits[s,e] * xhat[s,d]; thread per column d, token blocks of QB tokens
-constexpr int QB = 128;
+constexpr int qb_for(int em) { return 4096 / em; }     // tokens per partial block (smem [QB][EM] floats)
+int em_for(int E) { return E <= 8 ? 8 : (E <= 16 ? 16 : 32); }
 template <typename T, int EM>
 __global__ void __launch_bounds__(256) router_q_kernel(const T* __restrict__ x, const float* __restrict__ stats,
                                                        const float* __restrict__ dlogits, float* __restrict__ qpart, int S,
                                                        int Dm, int E) {
-    __shared__ float sdl[QB * 32];
+    constexpr int QB = qb_for(EM);
+    __shared__ float sdl[QB * EM];
     __shared__ float sst[QB * 2];
     const int s0 = blockIdx.y * QB;
     const int ns = min(QB, S - s0);
@@ -321,34 +326,46 @@ __global__ void __launch_bounds__(256) router_q_kernel(const T* __restrict__ x, 
         if (e < E) qpart[((size_t)blockIdx.y * E + e) * Dm + d] = acc[e];
 }
 
-// kernel D: reduce Q partials and derive all router parameter grads
+// kernel D: reduce Q partials and derive all router parameter grads.  block = (32 columns, E experts)
 //   dbr[e] = sum dlogits;  dWr[e,d] = ln_w[d]*Q[e,d] + ln_b[d]*dbr[e]
 //   dln_w[d] = sum_e Wr[e,d]*Q[e,d];  dln_b[d] = sum_e Wr[e,d]*dbr[e]
 __global__ void router_param_kernel(const float* __restrict__ qpart, int nqb, const float* __restrict__ part, int nparts,
                                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, const float* __restrict__ Wr,
                                     float* __restrict__ dWr, float* __restrict__ dbr, float* __restrict__ dln_w,
                                     float* __restrict__ dln_b, float* __restrict__ dnoise_scale, int Dm, int E) {
-    __shared__ float sdb[32];
-    if (threadIdx.x < 2 * E) {
+    __shared__ float sdb[64];
+    __shared__ float sgw[32][33], sgb[32][33];
+    const int tx = threadIdx.x, e = threadIdx.y;
+    const int tid = e * 32 + tx;
+    if (tid < 2 * E) {
         float s = 0.f;
-        for (int r = 0; r < nparts; ++r) s += part[(size_t)r * 2 * E + threadIdx.x];
-        if (threadIdx.x < E) { sdb[threadIdx.x] = s; if (blockIdx.x == 0) dbr[threadIdx.x] = s; }
-        else if (blockIdx.x == 0 && dnoise_scale) dnoise_scale[threadIdx.x - E] = s;
+        for (int r = 0; r < nparts; ++r) s += part[(size_t)r * 2 * E + tid];
+        sdb[tid] = s;
+        if (blockIdx.x == 0) {
+            if (tid < E) dbr[tid] = s;
+            else if (dnoise_scale) dnoise_scale[tid - E] = s;
+        }
     }
     __syncthreads();
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= Dm) return;
+    const int d = blockIdx.x * 32 + tx;
     float gw = 0.f, gb = 0.f;
-    for (int e = 0; e < E; ++e) {
+    if (d < Dm) {
         float q = 0.f;
         for (int r = 0; r < nqb; ++r) q += qpart[((size_t)r * E + e) * Dm + d];
         const float wv = Wr[(size_t)e * Dm + d];
         dWr[(size_t)e * Dm + d] = fmaf(ln_w[d], q, ln_b[d] * sdb[e]);
-        gw = fmaf(wv, q, gw);
-        gb = fmaf(wv, sdb[e], gb);
+        gw = wv * q;
+        gb = wv * sdb[e];
     }
-    dln_w[d] = gw;
-    dln_b[d] = gb;
+    sgw[e][tx] = gw;
+    sgb[e][tx] = gb;
+    __syncthreads();
+    if (e == 0 && d < Dm) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < E; ++i) { a += sgw[i][tx]; b += sgb[i][tx]; }
+        dln_w[d] = a;
+        dln_b[d] = b;
+    }
 }
 
 int router_grid(int S) {
@@ -369,7 +386,7 @@ struct BwdWs { size_t part_off, dl_off, q_off, total; int grid, nqb; };
 BwdWs bwd_ws(int S, int Dm, int E) {
     BwdWs w;
     w.grid = router_grid(S);
-    w.nqb = (int)ab_ceil_div(S, QB);
+    w.nqb = (int)ab_ceil_div(S, qb_for(em_for(E)));
     size_t o = 0;
     w.part_off = o; o += ab_round_up((int64_t)w.grid * 2 * E * sizeof(float), 256);
     w.dl_off = o; o += ab_round_up((int64_t)S * E * sizeof(float), 256);
@@ -416,7 +433,7 @@ extern "C" int ab_moe_router_fwd(const void* x, const float* ln_w, const float* 
     }
 #undef AB_ROUTER_FWD
     AB_LAUNCH_CHECK();
-    reduce_rows_kernel<<<1, 128, 0, stream>>>(part, wl.grid, 2 * E + 1, aux);
+    reduce_rows_kernel<<<(unsigned)ab_ceil_div(2 * E + 1, 4), 128, 0, stream>>>(part, wl.grid, 2 * E + 1, aux);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
@@ -464,8 +481,8 @@ extern "C" int ab_moe_router_bwd(const void* x, const float* stats, const float*
     }
 #undef AB_ROUTER_BWD
     AB_LAUNCH_CHECK();
-    router_param_kernel<<<(unsigned)ab_ceil_div(Dm, 128), 128, 0, stream>>>(qpart, wl.nqb, part, wl.grid, ln_w, ln_b, Wr, dWr, dbr,
-                                                                           dln_w, dln_b, dnoise_scale, Dm, E);
+    router_param_kernel<<<(unsigned)ab_ceil_div(Dm, 32), dim3(32, E), 0, stream>>>(qpart, wl.nqb, part, wl.grid, ln_w, ln_b, Wr, dWr,
+                                                                                  dbr, dln_w, dln_b, dnoise_scale, Dm, E);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

@@ -615,23 +615,25 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
     }
 }
 
-// dA_log[c], dD[c] = sum over (b, j) of the tile partials, fixed order
-__global__ void scan_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dA, float* __restrict__ dD,
-                                         int B, int Di, int Cs, int nslab, int nchunks) {
-    const int cg = blockIdx.x * blockDim.x + threadIdx.x;
+// dA_log[c], dD[c] = sum over (b, j) of the tile partials; one warp per channel, fixed order -> deterministic
+__global__ void __launch_bounds__(256) scan_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dA,
+                                                                float* __restrict__ dD, int B, int Di, int Cs, int nslab,
+                                                                int nchunks) {
+    const int cg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (cg >= Di) return;
     const int slab = cg / Cs, c = cg % Cs;
     float sa = 0.f, sd = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const int chain = b * nslab + slab;
-        for (int j = 0; j < nchunks; ++j) {
-            const size_t tl = (size_t)chain * nchunks + j;
-            sa += part[(tl * 2 + 0) * Cs + c];
-            sd += part[(tl * 2 + 1) * Cs + c];
-        }
+    const int n = B * nchunks;
+    for (int i = lane; i < n; i += 32) {
+        const int b = i / nchunks, j = i % nchunks;
+        const size_t tl = (size_t)(b * nslab + slab) * nchunks + j;
+        sa += part[(tl * 2 + 0) * Cs + c];
+        sd += part[(tl * 2 + 1) * Cs + c];
     }
-    dA[cg] = sa;
-    dD[cg] = sd;
+    sa = ab_warp_sum(sa);
+    sd = ab_warp_sum(sd);
+    if (lane == 0) { dA[cg] = sa; dD[cg] = sd; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -816,7 +818,7 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
         if (int e = f32 ? launch_bwd_mode<float, MODE_APPLY>(maps, p, t, gin, stream)
                         : launch_bwd_mode<__nv_bfloat16, MODE_APPLY>(maps, p, t, gin, stream)) return e;
     }
-    scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, 128), 128, 0, stream>>>(p.part, dA_log, dD, B, Di, t.Cs, t.nslab, t.nchunks);
+    scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, 8), 256, 0, stream>>>(p.part, dA_log, dD, B, Di, t.Cs, t.nslab, t.nchunks);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

@@ -300,7 +300,12 @@ class _AttentionWrapper(nn.Module):
         self.output_dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_s, att_mask=None, pos_ids=None, past_kv=None, output_att=False, use_c=False):
-        out, proxy, cache = self.attention_mechanism_impl(self.pre_norm(hidden_s), attention_mask=att_mask, position_ids=pos_ids,
+        # under autocast the projections consume bf16: emit the normalised rows in that type directly (same rounding
+        # point as the reference's fp32 LayerNorm followed by the autocast cast inside nn.Linear)
+        ac = _autocast_dtype()
+        normed = ops.layer_norm(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps,
+                                out_dtype=ac if (ac is not None and hidden_s.dtype == torch.float32) else None)
+        out, proxy, cache = self.attention_mechanism_impl(normed, attention_mask=att_mask, position_ids=pos_ids,
                                                           past_key_value=past_kv, output_attentions=output_att, use_cache=use_c)
         return self.output_dropout(out) + hidden_s, proxy, cache
 
@@ -317,7 +322,8 @@ class _FeedForwardWrapper(nn.Module):
         self.output_dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_s):
-        out, lb, rz = self.ffn(self.pre_norm(hidden_s))
+        normed = ops.layer_norm(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
+        out, lb, rz = self.ffn(normed)
         return self.output_dropout(out) + hidden_s, lb, rz
 
 

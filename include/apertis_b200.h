@@ -203,6 +203,17 @@ int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const vo
 int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
                        int N, int E, cudaStream_t stream);
 
+/* ---- block wrappers: pre-norm LayerNorm  (core.py:694-695, 887-888) ------------
+ * y = (x - mean) * rstd * w + b per row, eps inside the sqrt; stats [S,2] = (mean, rstd) saved for the backward.
+ * backward: dx = LayerNorm-backward(dy) (+ dres when given: the residual branch's gradient, fused add),
+ * dw/db [Dm] fp32 (overwritten, deterministic two-stage reduction through ws). */
+int ab_layernorm_fwd(const void* x, const float* w, const float* b, float eps, void* y, float* stats, int S, int Dm,
+                     int x_dtype, int y_dtype, cudaStream_t stream);
+size_t ab_layernorm_bwd_workspace_bytes(int S, int Dm);
+int ab_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* w, const void* dres, void* dx,
+                     float* dw, float* db, void* ws, size_t ws_bytes, int S, int Dm, int x_dtype, int dy_dtype,
+                     cudaStream_t stream);
+
 /* ---- helpers ----------------------------------------------------------------------------------- */
 /* fp32 -> bf16 cast of n elements (weight shadows for the tensor-core path) */
 int ab_cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);

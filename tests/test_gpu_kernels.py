@@ -265,3 +265,25 @@ def test_grouped_gemm_tn(M, N, counts):
     for e in range(E):
         ref = A[seg[e]:seg[e + 1]].float().t() @ Bm[seg[e]:seg[e + 1]].float()
         assert rel_err(out[e], ref) < 2e-5 if counts[e] else float(out[e].abs().max()) == 0.0, e
+
+
+# ------------------------------------------------------------------------------------------------
+# block-wrapper LayerNorm
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,Dm", [(96, 64), (1000, 704), (257, 96)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_layer_norm(S, Dm, out_dtype):
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(S)
+    x = torch.randn(S, Dm, generator=g) * 2 + 0.5
+    w, b = 1 + 0.1 * torch.randn(Dm, generator=g), 0.1 * torch.randn(Dm, generator=g)
+    dy = torch.randn(S, Dm, generator=g).to(out_dtype).float()
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    ref = F.layer_norm(xr, (Dm,), wr, br, 1e-12)
+    ref.backward(dy)
+    xg, wg, bg = (t.to(dev()).requires_grad_(True) for t in (x, w, b))
+    out = ops.layer_norm(xg, wg, bg, 1e-12, out_dtype=out_dtype)
+    out.backward(dy.to(dev(), out_dtype))
+    tol = TOL[out_dtype]
+    assert rel_err(out.float(), ref.detach()) < tol
+    assert rel_err(xg.grad, xr.grad) < 1e-4 and rel_err(wg.grad, wr.grad) < 1e-4 and rel_err(bg.grad, br.grad) < 1e-4
