@@ -43,7 +43,7 @@ SIGNATURES = {
     "ab_moe_topk_from_logits": (I, [P, P, P, P, P, P, I, I, I, P]),
     "ab_moe_max_rows": (I64, [I, I, I, I, I]),
     "ab_moe_plan_workspace_bytes": (SZ, [I, I, I]),
-    "ab_moe_plan": (I, [P, P, P, I, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I64, P]),
+    "ab_moe_plan": (I, [P, P, P, I, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I64, I, P]),
     "ab_moe_permute_ln": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, P]),
     "ab_moe_unpermute": (I, [P, P, P, P, I, I, I, I, I, P]),
     "ab_moe_unpermute_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, I, P]),
@@ -55,7 +55,7 @@ SIGNATURES = {
     "ab_moe_router_bwd": (I, [P] * 24 + [SZ, I, I, I, I, I, P]),
     "ab_grouped_gemm_nt": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, P]),
     "ab_grouped_gemm_nn": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, P]),
-    "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, P]),
+    "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, I, I64, P]),
     "ab_layernorm_fwd": (I, [P, P, P, F, P, P, I, I, I, I, P]),
     "ab_layernorm_bwd_workspace_bytes": (SZ, [I, I]),
     "ab_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, P]),

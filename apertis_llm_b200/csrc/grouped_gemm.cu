@@ -32,6 +32,8 @@ struct GemmParams {
     int bn;                  // N tile
     int num_n_tiles, num_m_tiles;
     int epi, act, c_f32;
+    int tn_nsrc;             // MODE_TN: an expert's rows are nsrc blocks [src*stride + seg_off[e], src*stride + seg_off[e+1])
+    int64_t tn_src_stride;
     const int32_t* tile_expert;
     const int32_t* n_rows;
     const int32_t* seg_off;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                     const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
                     m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
                     k_begin = p.seg_off[e];
-                    nk = (p.seg_off[e + 1] - k_begin) / BK;
+                    nk = p.tn_nsrc * ((p.seg_off[e + 1] - k_begin) / BK);
                 } else {
                     m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
                     e = p.tile_expert[m_tile];
@@ -157,7 +159,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                     unsigned char* sb = sa + A_BYTES;
                     ab_mbar_expect_tx(&full[stage], stage_tx);
                     if (MODE == MODE_TN) {
-                        const int r0 = k_begin + kb * BK;
+                        const int per_src = nk / p.tn_nsrc;
+                        const int r0 = (int)((kb / per_src) * p.tn_src_stride) + k_begin + (kb % per_src) * BK;
                         ab_tma_load_2d(sa, &tm_a, &full[stage], m_tile * BM, r0);
                         ab_tma_load_2d(sa + ATOM_BYTES, &tm_a, &full[stage], m_tile * BM + 64, r0);
                         for (int j = 0; j < bn / 64; ++j)
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 int nk;
                 if (MODE == MODE_TN) {
                     const int e = tile / (p.num_m_tiles * p.num_n_tiles);
-                    nk = (p.seg_off[e + 1] - p.seg_off[e]) / BK;
+                    nk = p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK);
                     if (nk == 0) continue;          // empty expert: the epilogue writes zeros without an accumulator
                 } else {
                     nk = (p.K + BK - 1) / BK;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 e = tile / (p.num_m_tiles * p.num_n_tiles);
                 const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
                 m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                nk = (p.seg_off[e + 1] - p.seg_off[e]) / BK;
+                nk = p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK);
             } else {
                 m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
                 e = p.tile_expert[m_tile];
@@ -414,7 +417,9 @@ extern "C" int ab_grouped_gemm_nn(const void* A, const void* W, const float* bia
 }
 
 extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
-                                  int N, int E, cudaStream_t stream) {
+                                  int N, int E, int nsrc, int64_t src_stride, cudaStream_t stream) {
+    AB_REQUIRE(nsrc >= 1 && (nsrc == 1 || (src_stride > 0 && src_stride % BK == 0 && nsrc * src_stride <= max_rows)),
+               "grouped_gemm_tn: bad source blocking nsrc=%d stride=%lld", nsrc, (long long)src_stride);
     AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm_tn: max_rows must be a positive multiple of %d", BM);
     AB_REQUIRE(M > 0 && N > 0 && E > 0 && M % 8 == 0 && N % 8 == 0, "grouped_gemm_tn: M (%d) and N (%d) must be multiples of 8", M, N);
     GemmParams p;
@@ -424,6 +429,7 @@ extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, cons
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
     p.num_m_tiles = (int)ab_ceil_div(M, BM);
     p.seg_off = seg_off; p.cw = Cw;
+    p.tn_nsrc = nsrc; p.tn_src_stride = src_stride;
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)max_rows, 64, BK)) return e;
     if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)max_rows, 64, BK)) return e;

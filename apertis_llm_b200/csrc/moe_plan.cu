@@ -148,13 +148,14 @@ __global__ void plan_finalize_kernel(const int32_t* __restrict__ idx, const int3
                                      const int32_t* __restrict__ row_local, int32_t* __restrict__ seg_off,
                                      int32_t* __restrict__ row_of, int32_t* __restrict__ tok_of_row,
                                      int32_t* __restrict__ slot_of_row, int32_t* __restrict__ tile_expert,
-                                     int32_t* __restrict__ n_rows, int S, int K, int E, int align, int64_t max_rows) {
+                                     int32_t* __restrict__ n_rows, int S, int K, int E, int align, int64_t max_rows,
+                                     int fixed_seg) {
     __shared__ int soff[34];
     if (threadIdx.x == 0) {
         int o = 0, kept = 0;
         for (int e = 0; e < E; ++e) {
             soff[e] = o;
-            o += (counts[e] + align - 1) / align * align;
+            o += fixed_seg > 0 ? fixed_seg : (counts[e] + align - 1) / align * align;
             kept += counts[e];
         }
         soff[E] = o;
@@ -425,7 +426,8 @@ __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
     float s = 0.f;
-    for (int t = s_t0; t < s_t1; ++t) s += part[(size_t)t * ncols + j];
+    for (int t = s_t0; t < s_t1; ++t)
+        if (tile_expert[t] == e) s += part[(size_t)t * ncols + j];      // tiles of an expert may be interleaved (EP layout)
     if (j < split) out_a[(size_t)e * split + j] = s;
     else out_b[(size_t)e * (ncols - split) + (j - split)] = s;
 }
@@ -452,10 +454,15 @@ extern "C" size_t ab_moe_plan_workspace_bytes(int S, int K, int E) {
 extern "C" int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* active, int cap, int32_t* counts,
                            int32_t* seg_off, int32_t* row_of, int32_t* tok_of_row, int32_t* slot_of_row,
                            int32_t* tile_expert, int32_t* n_rows, void* ws, size_t ws_bytes, int S, int K, int E,
-                           int row_align, int64_t max_rows, cudaStream_t stream) {
+                           int row_align, int64_t max_rows, int fixed_seg, cudaStream_t stream) {
     AB_REQUIRE(S > 0 && K >= 1 && E >= 1 && E <= 32, "moe_plan: bad shape S=%d K=%d E=%d", S, K, E);
-    AB_REQUIRE(row_align > 0 && max_rows % row_align == 0 && max_rows >= ab_moe_max_rows(S, K, E, cap < S ? cap : S, row_align),
-               "moe_plan: max_rows %lld too small or not a multiple of %d", (long long)max_rows, row_align);
+    if (fixed_seg > 0) {
+        AB_REQUIRE(fixed_seg % row_align == 0 && fixed_seg >= (cap < S ? cap : S) && max_rows == (int64_t)E * fixed_seg,
+                   "moe_plan: fixed_seg (%d) must be a multiple of %d, >= cap, and max_rows == E*fixed_seg", fixed_seg, row_align);
+    } else {
+        AB_REQUIRE(row_align > 0 && max_rows % row_align == 0 && max_rows >= ab_moe_max_rows(S, K, E, cap < S ? cap : S, row_align),
+                   "moe_plan: max_rows %lld too small or not a multiple of %d", (long long)max_rows, row_align);
+    }
     AB_REQUIRE(ws && ws_bytes >= ab_moe_plan_workspace_bytes(S, K, E), "moe_plan: workspace too small");
     int32_t* row_local = (int32_t*)ws;
     AB_CHECK_CUDA(cudaMemsetAsync(tok_of_row, 0xFF, (size_t)max_rows * sizeof(int32_t), stream));
@@ -465,7 +472,7 @@ extern "C" int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* ac
     const int64_t want = ab_ceil_div((int64_t)S * K, 256);
     const int grid = (int)(want < ab_num_sms() * 4 ? want : ab_num_sms() * 4);
     plan_finalize_kernel<<<grid, 256, 0, stream>>>(idx, counts, row_local, seg_off, row_of, tok_of_row, slot_of_row, tile_expert,
-                                                   n_rows, S, K, E, row_align, max_rows);
+                                                   n_rows, S, K, E, row_align, max_rows, fixed_seg);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

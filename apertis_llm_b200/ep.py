@@ -1,0 +1,225 @@
+"""Expert parallelism for AdaptiveExpertSystem: experts sharded across the ranks of one node, token rows
+exchanged with an all-to-all over NCCL (NVLink 5 / NVSwitch), batch data-parallel everywhere else.
+
+The reference has no expert parallelism (only DDP, pipeline.py:435-466); this is the B200-native addition
+SURVEY.md section 8(e) specifies.  Semantics are those of replicated experts under DDP:
+
+* every rank routes ITS OWN tokens and applies the capacity limit to its local S (core.py:508-511 uses the
+  local S), so the forward is identical to running all experts locally;
+* rank r owns experts [r*E/W, (r+1)*E/W).  The local permuted layout uses FIXED expert segments of
+  `seg = round_up(cap, 128)` rows (no counts need to reach the host: the exchange has equal splits), so
+  `xn[W, El*seg, Dm]` goes out with one all_to_all_single, the owner runs the grouped GEMMs over the
+  received `[W, El*seg, Dm]` rows (row tile -> local expert is a static map), and the result comes back the
+  same way.  The per-expert LayerNorm affine is all-gathered (E*Dm floats) and applied at the source, so the
+  numerics equal the single-GPU path bit for bit;
+* backward mirrors it (dY out, dXn back); expert gradients are sums over all ranks' tokens and are scaled by
+  1/W so that they equal what DDP's gradient averaging would give for replicated experts.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import ROW_ALIGN, call, dt, ptr, query, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers (pure, device agnostic: covered by the CPU gloo tests)
+# ------------------------------------------------------------------------------------------------
+def segment_rows(cap: int) -> int:
+    """Rows reserved per expert in the exchange layout."""
+    return (int(cap) + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN
+
+
+def recv_tile_expert(W: int, El: int, seg: int, device=None) -> torch.Tensor:
+    """Local expert of every 128-row tile of the received buffer [W, El*seg, C] (source-major)."""
+    tiles_per_seg = seg // ROW_ALIGN
+    return torch.arange(El, dtype=torch.int32, device=device).repeat_interleave(tiles_per_seg).repeat(W)
+
+
+def local_seg_off(El: int, seg: int, device=None) -> torch.Tensor:
+    return torch.arange(El + 1, dtype=torch.int32, device=device) * seg
+
+
+def all_to_all_equal(send: torch.Tensor, group) -> torch.Tensor:
+    """send [W, n, C] (block d goes to rank d) -> recv [W, n, C] (block s came from rank s)."""
+    W = dist.get_world_size(group)
+    assert send.shape[0] == W and send.is_contiguous()
+    recv = torch.empty_like(send)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+        return recv
+    # gloo has no all_to_all: pairwise exchange (used by the CPU tests of the host logic)
+    rank = dist.get_rank(group)
+    recv[rank].copy_(send[rank])
+    ops_ = []
+    for peer in range(W):
+        if peer == rank:
+            continue
+        ops_.append(dist.P2POp(dist.isend, send[peer], dist.get_global_rank(group, peer), group))
+        ops_.append(dist.P2POp(dist.irecv, recv[peer], dist.get_global_rank(group, peer), group))
+    for w in dist.batch_isend_irecv(ops_):
+        w.wait()
+    return recv
+
+
+def all_gather_cat(t: torch.Tensor, group) -> torch.Tensor:
+    W = dist.get_world_size(group)
+    out = torch.empty((W,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=group) if dist.get_backend(group) == "nccl" else \
+        dist.all_gather(list(out.unbind(0)), t.contiguous(), group=group)
+    return out.view((-1,) + tuple(t.shape[1:]))
+
+
+# ------------------------------------------------------------------------------------------------
+# the autograd node
+# ------------------------------------------------------------------------------------------------
+class _MoEExpertsEP(torch.autograd.Function):
+    """ops._MoEExperts with the expert MLPs executed on the owning ranks."""
+
+    @staticmethod
+    def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg, group):
+        _lib.ensure_device(x2.device)
+        dev = x2.device
+        W = dist.get_world_size(group)
+        S, Dm = x2.shape
+        El, I, _ = W1.shape
+        E = El * W
+        K, act, training, precise = cfg["K"], cfg["act"], cfg["training"], cfg["precise"]
+        x2 = x2.contiguous()
+        f = lambda t: t.float().contiguous()
+        rn_w, rn_b, Wr, br, b1, b2, W1, W2 = map(f, (rn_w, rn_b, Wr, br, b1, b2, W1, W2))
+        ln_w_full = all_gather_cat(f(ln_w), group)          # [E, Dm]
+        ln_b_full = all_gather_cat(f(ln_b), group)
+        use_noise = noise is not None and noise_scale is not None
+        r = ops.moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
+                          f(noise_scale) if use_noise else None, K)
+        seg = segment_rows(min(cfg["cap"], S))
+        plan = ops.moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"], fixed_seg=seg)
+        rows_local = E * seg                                  # == W * El * seg
+        cdt = torch.float32 if precise else torch.bfloat16
+        xn = torch.empty(rows_local, Dm, dtype=cdt, device=dev)
+        call("ab_moe_permute_ln", ptr(x2), ptr(r["stats"]), ptr(ln_w_full), ptr(ln_b_full), ptr(plan["tok_of_row"]),
+             ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(xn), Dm, ROW_ALIGN, rows_local, dt(x2), dt(cdt), stream_ptr())
+        # ---- dispatch
+        xr = all_to_all_equal(xn.view(W, El * seg, Dm), group).view(rows_local, Dm)
+        rplan = dict(tile_expert=recv_tile_expert(W, El, seg, dev),
+                     n_rows=torch.full((2,), rows_local, dtype=torch.int32, device=dev),
+                     seg_off=local_seg_off(El, seg, dev))
+        if precise:
+            a1, w1, k1 = ops._split_cols(xr, 0), ops._split_cols(W1.view(El * I, Dm), 1), 3 * Dm
+        else:
+            a1, w1, k1 = xr, ops._cast_bf16(W1), Dm
+        h, hpre = ops.grouped_gemm("nt", a1, w1, rplan, I, k1, El, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True)
+        if precise:
+            a2, w2, k2 = ops._split_cols(h, 0), ops._split_cols(W2.view(El * Dm, I), 1), 3 * I
+        else:
+            a2, w2, k2 = h, ops._cast_bf16(W2), I
+        yr = ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
+        # ---- combine
+        y = all_to_all_equal(yr.view(W, El * seg, Dm), group).view(rows_local, Dm)
+        out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
+        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(out), S, K, Dm, dt(y), dt(out), stream_ptr())
+        aux = r["aux"]
+        zero = torch.zeros((), dtype=x2.dtype, device=dev)
+        lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
+        rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
+        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt)
+        ctx.group = group
+        ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
+        ctx.rplan = rplan
+        ctx.save_for_backward(x2, rn_w, rn_b, Wr, br, ln_w_full, W1, W2, noise if use_noise else None, r["stats"], r["gates"],
+                              r["idx"], r["probs"], r["lse"], r["lclean"], r["w"], aux, xr, h, hpre, y)
+        counts = plan["counts"]
+        ctx.mark_non_differentiable(counts)
+        return out, lb.to(x2.dtype), rz.to(x2.dtype), counts
+
+    @staticmethod
+    def backward(ctx, dout, dlb, drz, _dcounts):
+        (x2, rn_w, rn_b, Wr, br, ln_w_full, W1, W2, noise, stats, gates, idx, probs, lse, lclean, w, aux, xr, h, hpre, y) = ctx.saved_tensors
+        cfg, plan, rplan, group = ctx.cfg, ctx.plan, ctx.rplan, ctx.group
+        S, Dm, E, El, I, K, W, seg = (cfg[k] for k in ("S", "Dm", "E", "El", "I", "K", "W", "seg"))
+        act, precise, rows, cdt = cfg["act"], cfg["precise"], cfg["rows"], cfg["cdt"]
+        dev = x2.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dout = dout.contiguous()
+        dy = torch.empty(rows, Dm, dtype=cdt, device=dev)
+        dw_row = torch.empty(rows, **f32)
+        call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
+             ptr(dy), ptr(dw_row), K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+        dyr = all_to_all_equal(dy.view(W, El * seg, Dm), group).view(rows, Dm)
+        lseg = rplan["seg_off"]
+        stride = El * seg
+        if precise:
+            # row-stacked splits: every (source, local expert) block of `seg` rows is one group
+            G = W * El
+            lseg3 = (lseg * 3).contiguous()
+            w2r = ops._split_rows(W2.view(El * Dm, I), 1, None, El, Dm)
+            dhpre = ops.grouped_gemm("nn", ops._split_cols(dyr, 0), w2r, rplan, I, 3 * Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            sr = lambda t, which: ops._split_rows(t, which, None, G, seg)
+            dW2 = ops.grouped_gemm_tn(sr(dyr, 0), sr(h, 1), lseg3, Dm, I, El, nsrc=W, src_stride=3 * stride)
+            dW1 = ops.grouped_gemm_tn(sr(dhpre, 0), sr(xr, 1), lseg3, I, Dm, El, nsrc=W, src_stride=3 * stride)
+            w1r = ops._split_rows(W1.view(El * I, Dm), 1, None, El, I)
+            dxnr = ops.grouped_gemm("nn", ops._split_cols(dhpre, 0), w1r, rplan, Dm, 3 * I, El, out_dtype=torch.float32)
+        else:
+            w1b, w2b = ops._cast_bf16(W1), ops._cast_bf16(W2)
+            dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dW2 = ops.grouped_gemm_tn(dyr, h, lseg, Dm, I, El, nsrc=W, src_stride=stride)
+            dW1 = ops.grouped_gemm_tn(dhpre, xr, lseg, I, Dm, El, nsrc=W, src_stride=stride)
+            dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)
+        db2 = torch.empty(El, Dm, **f32)
+        db1 = torch.empty(El, I, **f32)
+        nws = max(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, rows),
+                  query("ab_moe_segment_colsum_workspace_bytes", Dm, ROW_ALIGN, rows),
+                  query("ab_moe_permute_ln_bwd_workspace_bytes", Dm, ROW_ALIGN, rows))
+        ws = ops._u8(nws, dev)
+        call("ab_moe_segment_colsum", ptr(dyr), ptr(rplan["tile_expert"]), ptr(rplan["n_rows"]), ptr(db2), ptr(ws), ws.numel(), Dm, El,
+             ROW_ALIGN, rows, dt(dyr), stream_ptr())
+        call("ab_moe_segment_colsum", ptr(dhpre), ptr(rplan["tile_expert"]), ptr(rplan["n_rows"]), ptr(db1), ptr(ws), ws.numel(), I, El,
+             ROW_ALIGN, rows, dt(dhpre), stream_ptr())
+        # ---- gradient rows back to their source ranks
+        dxn = all_to_all_equal(dxnr.view(W, El * seg, Dm), group).view(rows, Dm)
+        dxrow = torch.empty(rows, Dm, **f32)
+        dln_w = torch.empty(E, Dm, **f32)
+        dln_b = torch.empty(E, Dm, **f32)
+        call("ab_moe_permute_ln_bwd", ptr(dxn), ptr(x2), ptr(stats), ptr(ln_w_full), ptr(plan["tok_of_row"]), ptr(plan["tile_expert"]),
+             ptr(plan["n_rows"]), ptr(dxrow), ptr(dln_w), ptr(dln_b), ptr(ws), ws.numel(), Dm, E, ROW_ALIGN, rows, dt(x2), dt(dxn),
+             stream_ptr())
+        dln = torch.stack([dln_w, dln_b])                      # [2, E, Dm]: sum over source ranks, keep the local experts
+        dist.all_reduce(dln, group=group)
+        rank = dist.get_rank(group)
+        inv = 1.0 / W
+        dln_w_l = dln[0, rank * El:(rank + 1) * El] * inv
+        dln_b_l = dln[1, rank * El:(rank + 1) * El] * inv
+        training = cfg["training"]
+        g_lb = (dlb.float() * (cfg["lb_coef"] * E / S)) if (training and cfg["lb_coef"] > 0) else torch.zeros((), **f32)
+        g_rz = (drz.float() * (cfg["rz_coef"] / S)) if (training and cfg["rz_coef"] > 0) else torch.zeros((), **f32)
+        scal = torch.stack([g_lb.reshape(()), g_rz.reshape(())]).contiguous()
+        fvec = (aux[E:2 * E] / S).contiguous()
+        dx = torch.empty_like(x2)
+        dWr, dbr = torch.empty(E, Dm, **f32), torch.empty(E, **f32)
+        drn_w, drn_b = torch.empty(Dm, **f32), torch.empty(Dm, **f32)
+        dns = torch.empty(E, **f32) if cfg["use_noise"] else None
+        nws = query("ab_moe_router_bwd_workspace_bytes", S, Dm, E)
+        ws2 = ops._u8(nws, dev)
+        call("ab_moe_router_bwd", ptr(x2), ptr(stats), ptr(rn_w), ptr(rn_b), ptr(Wr), ptr(br), ptr(gates), ptr(idx), ptr(probs),
+             ptr(lse), ptr(lclean), ptr(noise.float().contiguous()) if cfg["use_noise"] else None, ptr(fvec), ptr(scal), ptr(dw_row),
+             ptr(dxrow), ptr(plan["row_of"]), ptr(dx), ptr(dWr), ptr(dbr), ptr(drn_w), ptr(drn_b), ptr(dns), ptr(ws2), ws2.numel(),
+             S, Dm, E, K, dt(x2), stream_ptr())
+        return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w_l, dln_b_l, dW1 * inv, db1 * inv, dW2 * inv, db2 * inv, None, None)
+
+
+def moe_experts_ep(module, x2, noise, noise_scale, cfg):
+    """Entry used by AdaptiveExpertSystem.forward when an expert-parallel group is set."""
+    return _MoEExpertsEP.apply(x2, module.router_norm.weight, module.router_norm.bias, module.router.weight, module.router.bias,
+                               noise, noise_scale, module.expert_ln_weight, module.expert_ln_bias, module.expert_w1,
+                               module.expert_b1, module.expert_w2, module.expert_b2, cfg, module.ep_group)
+
+
+def replicated_parameters(layer: torch.nn.Module) -> List[torch.nn.Parameter]:
+    """Parameters that are replicated across the EP group (everything but the sharded expert tensors);
+    these are the ones a DDP wrapper (pipeline.py:463) must all-reduce."""
+    return [p for n, p in layer.named_parameters() if ".expert_" not in n and not n.startswith("expert_")]

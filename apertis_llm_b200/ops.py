@@ -243,12 +243,13 @@ def moe_topk_from_logits(logits, K):
     return gates, idx, probs, w, lse
 
 
-def moe_plan(idx, w, E, cap, active=None):
-    """Capacity plan on the device (no host sync).  idx [S,K] int32, w [S,K] fp32."""
+def moe_plan(idx, w, E, cap, active=None, fixed_seg=0):
+    """Capacity plan on the device (no host sync).  idx [S,K] int32, w [S,K] fp32.
+    fixed_seg > 0: every expert segment is exactly fixed_seg rows (expert-parallel exchange layout)."""
     S, K = idx.shape
     dev = idx.device
     cap = int(min(cap, S))
-    max_rows = int(query("ab_moe_max_rows", S, K, E, cap, ROW_ALIGN))
+    max_rows = E * fixed_seg if fixed_seg > 0 else int(query("ab_moe_max_rows", S, K, E, cap, ROW_ALIGN))
     i32 = dict(dtype=torch.int32, device=dev)
     p = dict(counts=torch.empty(E, **i32), seg_off=torch.empty(E + 1, **i32), row_of=torch.empty(S, K, **i32),
              tok_of_row=torch.empty(max_rows, **i32), slot_of_row=torch.empty(max_rows, **i32),
@@ -257,7 +258,7 @@ def moe_plan(idx, w, E, cap, active=None):
     ws = _u8(nws, dev)
     call("ab_moe_plan", ptr(idx), ptr(w), ptr(active), cap, ptr(p["counts"]), ptr(p["seg_off"]), ptr(p["row_of"]),
          ptr(p["tok_of_row"]), ptr(p["slot_of_row"]), ptr(p["tile_expert"]), ptr(p["n_rows"]), ptr(ws), ws.numel(),
-         S, K, E, ROW_ALIGN, max_rows, stream_ptr())
+         S, K, E, ROW_ALIGN, max_rows, fixed_seg, stream_ptr())
     return p
 
 
@@ -292,10 +293,10 @@ def grouped_gemm(mode, A, W, plan, N, K, E, *, bias=None, aux=None, epi=_lib.EPI
     return (c, c2) if want_c2 else c
 
 
-def grouped_gemm_tn(A, Bm, seg_off, M, N, E):
-    """Cw[e] = A[seg e]^T @ Bm[seg e]  -> fp32 [E, M, N]."""
+def grouped_gemm_tn(A, Bm, seg_off, M, N, E, nsrc=1, src_stride=0):
+    """Cw[e] = A[seg e]^T @ Bm[seg e]  -> fp32 [E, M, N]; with nsrc > 1 an expert's rows are nsrc strided blocks."""
     out = torch.empty(E, M, N, dtype=torch.float32, device=A.device)
-    call("ab_grouped_gemm_tn", ptr(A), ptr(Bm), ptr(out), ptr(seg_off), A.shape[0], M, N, E, stream_ptr())
+    call("ab_grouped_gemm_tn", ptr(A), ptr(Bm), ptr(out), ptr(seg_off), A.shape[0], M, N, E, nsrc, src_stride, stream_ptr())
     return out
 
 

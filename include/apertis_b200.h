@@ -91,8 +91,8 @@ int ab_selective_scan_fwd(const void* xa, const void* dlog, const void* Bm, cons
                           uint32_t epoch, int mode, int B, int L, int Di, int H, int dtype, cudaStream_t stream);
 /* Backward with in-tile recompute of the states from hstart.  dout = grad of y; dyssm (optional)
  * = grad of y_ssm.  Outputs: dxa, dz contiguous [B,L,Di]; dBm, dCm with dbc_stride;
- * ddlog_parts fp32 [B,L,H*parts] (parts = 16/vec, vec = 8 for bf16, 4 for f32; the caller sums
- * each head's parts -- already multiplied by softplus'); dA_log [Di] and dD [Di] fp32 (overwritten;
+ * ddlog_parts fp32 [B,L,H*4] (the backward works on 4-channel vectors: 4 partial sums per head, already
+ * multiplied by softplus'; the caller adds them); dA_log [Di] and dD [Di] fp32 (overwritten;
  * deterministic two-stage reduction through ws). */
 int ab_selective_scan_bwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride,
                           const void* z, int64_t z_stride, const void* dout, const void* dyssm,
@@ -128,12 +128,15 @@ int ab_moe_topk_from_logits(const float* logits, float* gates, int32_t* idx, flo
  * layout, segments padded to multiples of `row_align` (128, the GEMM tile); row_of[S,K] = permuted row
  * of a kept (token, slot) or -1; tok_of_row[max_rows], slot_of_row[max_rows] (-1 for padding rows);
  * tile_expert[max_rows/row_align] expert of each row tile (-1 beyond the end); n_rows[2] = {padded
- * total rows, kept rows}.  max_rows = ab_moe_max_rows(S,K,E,cap,row_align).  No host synchronisation. */
+ * total rows, kept rows}.  max_rows = ab_moe_max_rows(S,K,E,cap,row_align).  No host synchronisation.
+ * fixed_seg > 0 (expert-parallel exchange layout): every expert segment is exactly fixed_seg rows
+ * (a multiple of row_align, >= cap) at offset e*fixed_seg and max_rows must equal E*fixed_seg. */
 int64_t ab_moe_max_rows(int S, int K, int E, int cap, int row_align);
 size_t ab_moe_plan_workspace_bytes(int S, int K, int E);
 int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* active, int cap, int32_t* counts, int32_t* seg_off,
                 int32_t* row_of, int32_t* tok_of_row, int32_t* slot_of_row, int32_t* tile_expert, int32_t* n_rows,
-                void* ws, size_t ws_bytes, int S, int K, int E, int row_align, int64_t max_rows, cudaStream_t stream);
+                void* ws, size_t ws_bytes, int S, int K, int E, int row_align, int64_t max_rows, int fixed_seg,
+                cudaStream_t stream);
 
 /* ---- MoE: permute (+ per-expert LayerNorm) and weighted unpermute  (core.py:593, :436, :605) -----
  * permute_ln: for every row r < padded total: xn[r,:] = bf16|f32( (x[tok,:]-mean)*rstd*ln_w[e,:]+ln_b[e,:] ),
@@ -200,8 +203,10 @@ int ab_grouped_gemm_nt(const void* A, const void* W, const float* bias, const vo
 int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                        const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
                        int epi, int act, int c_dtype, cudaStream_t stream);
+/* nsrc > 1 (expert-parallel receive layout): expert e's rows are the nsrc blocks
+ * [s*src_stride + seg_off[e], s*src_stride + seg_off[e+1]), s = 0..nsrc-1. */
 int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
-                       int N, int E, cudaStream_t stream);
+                       int N, int E, int nsrc, int64_t src_stride, cudaStream_t stream);
 
 /* ---- block wrappers: pre-norm LayerNorm  (core.py:694-695, 887-888) ------------
  * y = (x - mean) * rstd * w + b per row, eps inside the sqrt; stats [S,2] = (mean, rstd) saved for the backward.
