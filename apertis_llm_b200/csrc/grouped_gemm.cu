@@ -10,7 +10,9 @@
 // Tile 128 x BN x 64 (BN <= 256 chosen per shape on the host and carried in the TMA maps / the
 // instruction descriptor), 4-stage TMA->MMA ring, 2 accumulator stages in TMEM (2 x 256 columns) so the
 // epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM
-// alloc), 2..9 = epilogue (two warps per TMEM lane quarter, splitting the column chunks).
+// alloc), 2..17 = epilogue: four warps per TMEM lane quarter, each taking one 16-column chunk of a 64-column
+// group of the tile (tcgen05.ld -> bias / activation math in registers -> swizzled per-warp staging -> coalesced
+// 16-byte global stores; no CTA-wide synchronisation in the epilogue).
 // Row tiles (128 permuted rows) belong to one expert; the number of valid row tiles is read from device
 // memory (n_rows[0]) so no host synchronisation is needed after the routing plan.
 #include "common.cuh"
@@ -22,10 +24,12 @@ constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES_MAX = 256 * BK * 2;     // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int ATOM_BYTES = 64 * BK * 2;       // one 64(MN) x 64(K) swizzle-128B MN-major atom = 8 KB
-constexpr int NUM_THREADS = 320;
-constexpr int EPI_WARP0 = 2, EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 2, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;
+constexpr int NUM_THREADS = 64 + EPI_THREADS; // warp 0 TMA, warp 1 MMA, 16 epilogue warps
+constexpr int GW = 64;                        // epilogue column group: 4 chunks of 16, one per warp of a TMEM lane quarter
 constexpr int MODE_NT = 0, MODE_NN = 1, MODE_TN = 2;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + 256;
+constexpr int WARP_STG_BYTES = 32 * 64;        // per-warp epilogue staging: 32 rows x 64 B
+constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + (size_t)EPI_WARPS * WARP_STG_BYTES + 256;
 
 struct GemmParams {
     int N, K, E, M;          // M only for MODE_TN (rows of each expert's output)
@@ -45,27 +49,30 @@ struct GemmParams {
 };
 
 // ---- math for the epilogues -------------------------------------------------------------------
-// erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26); enough for the fp32 tolerance and much cheaper than erff
-__device__ __forceinline__ float erf_as(float x) {
-    const float ax = fabsf(x);
-    const float t = ab_rcp(fmaf(0.3275911f, ax, 1.0f));
+// erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26): erf(x/sqrt2) from t = 1/(1+p|x|/sqrt2) and g = exp(-x^2/2)
+__device__ __forceinline__ float erf_core(float ax_s, float g) {     // ax_s = |x|/sqrt(2), g = exp(-ax_s^2)
+    const float t = ab_rcp(fmaf(0.3275911f, ax_s, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float y = 1.0f - p * t * ab_ex2(-ax * ax * AB_LOG2E);
-    return copysignf(y, x);
+    return 1.0f - p * t * g;
 }
 __device__ __forceinline__ float act_fwd(float x, int act) {
-    if (act == AB_ACT_GELU) return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f));
+    if (act == AB_ACT_GELU) {
+        const float a = fabsf(x) * 0.70710678118654752f;
+        const float er = copysignf(erf_core(a, ab_ex2(-a * a * AB_LOG2E)), x);
+        return 0.5f * x * (1.0f + er);
+    }
     if (act == AB_ACT_RELU) return fmaxf(x, 0.f);
     return x * ab_sigmoid(x);
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
-    if (act == AB_ACT_GELU) {
-        const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
-        const float pdf = 0.3989422804014327f * ab_ex2(-0.5f * x * x * AB_LOG2E);
-        return fmaf(x, pdf, cdf);
+    if (act == AB_ACT_GELU) {        // cdf(x) + x*pdf(x); the erf and the pdf share exp(-x^2/2)
+        const float a = fabsf(x) * 0.70710678118654752f;
+        const float g = ab_ex2(-a * a * AB_LOG2E);
+        const float cdf = 0.5f * (1.0f + copysignf(erf_core(a, g), x));
+        return fmaf(x, 0.3989422804014327f * g, cdf);
     }
     if (act == AB_ACT_RELU) return x > 0.f ? 1.f : 0.f;
     const float s = ab_sigmoid(x);
@@ -96,6 +103,120 @@ __host__ __device__ inline uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
     return d;
 }
 
+// ---- epilogue -----------------------------------------------------------------------------------
+// One warp owns 32 accumulator rows (its TMEM lane quarter) x one 64-column group and walks it in units of 64 output
+// bytes per row (32 bf16 or 16 f32 columns): tcgen05.ld -> math -> swizzled per-warp staging -> coalesced 16-byte
+// global stores (8 rows x 64 B per instruction).  No CTA-wide synchronisation; everything is compile-time indexed so the
+// fragments stay in registers.
+__device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+template <int MODE, bool F32>
+__device__ __forceinline__ void stage_and_store(const GemmParams& p, unsigned char* stg, const float (&src)[F32 ? 16 : 32],
+                                                unsigned char* base, int lane, int quarter, int m_tile, int ncol, int ncol_end) {
+    constexpr int ES = F32 ? 4 : 2;
+    constexpr int CPV = 16 / ES;
+    const int N = p.N;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 q;
+        if (F32) q = make_uint4(__float_as_uint(src[j * 4]), __float_as_uint(src[j * 4 + 1]), __float_as_uint(src[j * 4 + 2]), __float_as_uint(src[j * 4 + 3]));
+        else q = ab_vec16<__nv_bfloat16>::pack(&src[j * 8]);
+        *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = q;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), j = lane & 3;
+        const int col = ncol + j * CPV;
+        const size_t grow = (size_t)m_tile * BM + quarter * 32 + r;
+        const bool ok = col < ncol_end && (MODE != MODE_TN || (int)grow < p.M);
+        const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(r, j));
+        if (ok) *reinterpret_cast<uint4*>(base + (grow * N + col) * ES) = q;
+    }
+    __syncwarp();
+}
+
+template <int MODE, bool F32>
+__device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned char* stg, uint32_t t_row, bool have_acc, int lane,
+                                               int quarter, int m_tile, int e, int n0, int g_col0, int g_cols) {
+    constexpr int U = F32 ? 16 : 32;            // columns per unit
+    constexpr int ES = F32 ? 4 : 2;
+    constexpr int CPV = 16 / ES;                // columns per 16-byte vector
+    const int N = p.N;
+    const int ncol_end = min(N, n0 + g_col0 + g_cols);    // columns past the tile (or the matrix) are never touched
+    for (int u0 = 0; u0 < g_cols; u0 += U) {
+        const int tcol = g_col0 + u0;           // column inside the tile
+        const int ncol = n0 + tcol;             // global column
+        if (ncol >= ncol_end) break;
+        float f[U];
+        {
+            uint32_t v[U];
+            if (have_acc) {
+                ab_tmem_ld16(t_row + (uint32_t)tcol, v);
+                if (U == 32) ab_tmem_ld16(t_row + (uint32_t)tcol + 16u, v + 16);
+                ab_tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < U; ++i) v[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < U; ++i) f[i] = __uint_as_float(v[i]);
+        }
+        if (MODE != MODE_TN) {
+            if (p.epi == AB_EPI_BIAS || p.epi == AB_EPI_BIAS_ACT) {
+                const float* bp = p.bias + (size_t)e * N + ncol;
+#pragma unroll
+                for (int i = 0; i < U; i += 4) {
+                    if (ncol + i < ncol_end) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+                        f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                    }
+                }
+            }
+            if (p.epi == AB_EPI_BIAS_ACT) {
+                // the pre-activation (the Linear output, rounded to the activation dtype first) goes out before the
+                // activation is applied in place, so only one fragment is live
+                if (!F32) {
+#pragma unroll
+                    for (int i = 0; i < U; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+                }
+                stage_and_store<MODE, F32>(p, stg, f, reinterpret_cast<unsigned char*>(p.c2), lane, quarter, m_tile, ncol, ncol_end);
+#pragma unroll
+                for (int i = 0; i < U; ++i) f[i] = act_fwd(f[i], p.act);
+            } else if (p.epi == AB_EPI_DACT) {
+                // saved pre-activation tile: coalesced 16-byte loads -> staging -> each thread reads its own row
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it * 8 + (lane >> 2), j = lane & 3;
+                    const int col = ncol + j * CPV;
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                    if (col < ncol_end)
+                        q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.aux) +
+                                                                 (((size_t)m_tile * BM + quarter * 32 + r) * N + col) * ES));
+                    *reinterpret_cast<uint4*>(stg + stg_off(r, j)) = q;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+                    float pre[CPV];
+                    if (F32) { pre[0] = __uint_as_float(q.x); pre[1] = __uint_as_float(q.y); pre[2] = __uint_as_float(q.z); pre[3] = __uint_as_float(q.w); }
+                    else ab_vec16<__nv_bfloat16>::unpack(q, pre);
+#pragma unroll
+                    for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(pre[i], p.act);
+                }
+                __syncwarp();
+            }
+        }
+        // ---- stage this thread's row, then store 8 rows x 64 B per instruction
+        unsigned char* base;
+        if (MODE == MODE_TN) base = reinterpret_cast<unsigned char*>(p.cw) + ((size_t)e * p.M) * N * 4;
+        else base = reinterpret_cast<unsigned char*>(p.c);
+        stage_and_store<MODE, F32>(p, stg, f, base, lane, quarter, m_tile, ncol, ncol_end);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                       const __grid_constant__ CUtensorMap tm_b,
@@ -103,7 +224,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = ab_smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);      // swizzle-128B atoms need 1024 B alignment
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGE * STAGE_BYTES);
+    unsigned char* stg_base = smem + (size_t)NSTAGE * STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (size_t)EPI_WARPS * WARP_STG_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
     uint64_t* tfull = bars + 2 * NSTAGE;
@@ -115,7 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
         ab_prefetch_tmap(&tm_a);
         ab_prefetch_tmap(&tm_b);
         for (int i = 0; i < NSTAGE; ++i) { ab_mbar_init(&full[i], 1); ab_mbar_init(&empty[i], 1); }
-        for (int i = 0; i < NACC; ++i) { ab_mbar_init(&tfull[i], 1); ab_mbar_init(&tempty[i], EPI_WARPS * 32); }
+        for (int i = 0; i < NACC; ++i) { ab_mbar_init(&tfull[i], 1); ab_mbar_init(&tempty[i], EPI_WARPS); }
         ab_fence_mbar_init();
     }
     if (warp == 1) {
@@ -218,10 +340,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
         }
     } else {
         // ================= epilogue =================
-        const int ew = warp - EPI_WARP0;
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                // which half of the column chunks
-        const int row_in_tile = quarter * 32 + lane;
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+        const int sub = (warp - EPI_WARP0) >> 2;      // which 64-column group of the tile this warp owns
+        unsigned char* stg = stg_base + (size_t)(warp - EPI_WARP0) * WARP_STG_BYTES;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int m_tile, n_tile, e, nk;
@@ -241,98 +362,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 ab_tc_fence_after();
             }
             const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-            const int n0 = n_tile * bn;
-            const int nchunks = bn / 16;          // 16-column chunks, split between the two halves
-            for (int ch = half; ch < nchunks; ch += 2) {
-                uint32_t v[16];
-                if (have_acc) {
-                    ab_tmem_ld16(t_row + (uint32_t)(ch * 16), v);
-                    ab_tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = 0u;
-                }
-                const int ncol = n0 + ch * 16;
-                if (ncol >= p.N) continue;
-                if (MODE == MODE_TN) {
-                    const int m = m_tile * BM + row_in_tile;
-                    if (m < p.M) {
-                        float* dst = p.cw + ((size_t)e * p.M + m) * p.N + ncol;
-                        if (ncol + 16 <= p.N) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<uint4*>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        } else {
-                            for (int i = 0; i < 16 && ncol + i < p.N; ++i) dst[i] = __uint_as_float(v[i]);
-                        }
-                    }
-                } else {
-                    const size_t row = (size_t)m_tile * BM + row_in_tile;
-                    float f[16], f2[16];
-                    const int nvalid = min(16, p.N - ncol);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                    if (p.epi == AB_EPI_BIAS || p.epi == AB_EPI_BIAS_ACT) {
-                        const float* bp = p.bias + (size_t)e * p.N + ncol;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] += (i < nvalid) ? __ldg(bp + i) : 0.f;
-                    }
-                    if (p.epi == AB_EPI_BIAS_ACT) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            if (!p.c_f32) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));   // Linear output is rounded first
-                            f2[i] = f[i];
-                            f[i] = act_fwd(f[i], p.act);
-                        }
-                    } else if (p.epi == AB_EPI_DACT) {
-                        float pre[16];
-                        if (p.c_f32) {
-                            const float* ap = reinterpret_cast<const float*>(p.aux) + row * p.N + ncol;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pre[i] = (i < nvalid) ? __ldg(ap + i) : 0.f;
-                        } else {
-                            const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(p.aux) + row * p.N + ncol;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pre[i] = (i < nvalid) ? __bfloat162float(ap[i]) : 0.f;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] *= act_bwd(pre[i], p.act);
-                    }
-                    if (p.c_f32) {
-                        float* dst = reinterpret_cast<float*>(p.c) + row * p.N + ncol;
-                        float* dst2 = reinterpret_cast<float*>(p.c2) + row * p.N + ncol;
-                        if (nvalid == 16) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                            if (p.epi == AB_EPI_BIAS_ACT) {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst2 + i) = make_float4(f2[i], f2[i + 1], f2[i + 2], f2[i + 3]);
-                            }
-                        } else {
-                            for (int i = 0; i < nvalid; ++i) { dst[i] = f[i]; if (p.epi == AB_EPI_BIAS_ACT) dst2[i] = f2[i]; }
-                        }
-                    } else {
-                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.c) + row * p.N + ncol;
-                        __nv_bfloat16* dst2 = reinterpret_cast<__nv_bfloat16*>(p.c2) + row * p.N + ncol;
-                        if (nvalid == 16) {
-                            *reinterpret_cast<uint4*>(dst) = ab_vec16<__nv_bfloat16>::pack(f);
-                            *reinterpret_cast<uint4*>(dst + 8) = ab_vec16<__nv_bfloat16>::pack(f + 8);
-                            if (p.epi == AB_EPI_BIAS_ACT) {
-                                *reinterpret_cast<uint4*>(dst2) = ab_vec16<__nv_bfloat16>::pack(f2);
-                                *reinterpret_cast<uint4*>(dst2 + 8) = ab_vec16<__nv_bfloat16>::pack(f2 + 8);
-                            }
-                        } else {
-                            for (int i = 0; i < nvalid; ++i) {
-                                dst[i] = __float2bfloat16_rn(f[i]);
-                                if (p.epi == AB_EPI_BIAS_ACT) dst2[i] = __float2bfloat16_rn(f2[i]);
-                            }
-                        }
-                    }
-                }
+            const int g_col0 = sub * GW;
+            if (g_col0 < bn) {
+                const int g_cols = min(GW, bn - g_col0);
+                if (p.c_f32) epilogue_group<MODE, true>(p, stg, t_row, have_acc, lane, quarter, m_tile, e, n_tile * bn, g_col0, g_cols);
+                else epilogue_group<MODE, false>(p, stg, t_row, have_acc, lane, quarter, m_tile, e, n_tile * bn, g_col0, g_cols);
             }
             if (have_acc) {
                 ab_tc_fence_before();
-                ab_mbar_arrive(&tempty[acc]);
+                __syncwarp();
+                if (lane == 0) ab_mbar_arrive(&tempty[acc]);       // all of this warp's TMEM reads of the tile are done
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -391,6 +430,8 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
     p.epi = epi; p.act = act; p.c_f32 = c_dtype == AB_F32;
     p.tile_expert = tile_expert; p.n_rows = n_rows; p.bias = bias; p.aux = aux; p.c = c; p.c2 = c2;
+    AB_REQUIRE(((uintptr_t)c % 16) == 0 && (c2 == nullptr || ((uintptr_t)c2 % 16) == 0) && (aux == nullptr || ((uintptr_t)aux % 16) == 0),
+               "grouped_gemm: output / aux pointers must be 16-byte aligned");
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)K, (uint64_t)max_rows, BK, BM)) return e;
     const int64_t max_tiles = (max_rows / BM) * p.num_n_tiles;
@@ -428,8 +469,9 @@ extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, cons
     p.bn = pick_bn(N, true);
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
     p.num_m_tiles = (int)ab_ceil_div(M, BM);
-    p.seg_off = seg_off; p.cw = Cw;
+    p.seg_off = seg_off; p.c_f32 = 1; p.epi = AB_EPI_NONE; p.cw = Cw;
     p.tn_nsrc = nsrc; p.tn_src_stride = src_stride;
+    AB_REQUIRE(((uintptr_t)Cw % 16) == 0, "grouped_gemm_tn: output pointer must be 16-byte aligned");
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)max_rows, 64, BK)) return e;
     if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)max_rows, 64, BK)) return e;

@@ -388,7 +388,7 @@ class _MoEExperts(torch.autograd.Function):
             dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
             dW2 = grouped_gemm_tn(dy, h, seg, Dm, I, E)
             dW1 = grouped_gemm_tn(dhpre, xn, seg, I, Dm, E)
-            dxn = grouped_gemm("nn", dhpre, w1b, plan, Dm, I, E, out_dtype=torch.float32)
+            dxn = grouped_gemm("nn", dhpre, w1b, plan, Dm, I, E, out_dtype=torch.bfloat16)    # bf16 like the reference's autocast Linear backward
         # ---- bias grads
         db2 = torch.empty(E, Dm, **f32)
         db1 = torch.empty(E, I, **f32)

@@ -159,6 +159,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the single JSON line
     import torch.distributed as dist
     from apertis_llm_b200 import ApertisLayerB200, BlockConfig, _lib
     from oracle import apertis_oracle as O   # only for the deterministic parameter factory and the cpu_baseline leg
