@@ -11,9 +11,13 @@
 // of TS=4 tokens; run aggregates (P = prod abar, S = state contribution) are combined across runs in
 // shared memory.  Across tiles of a sequence the incoming state is resolved
 //   * single pass: each tile publishes (P, S) per channel as two self-validating 64-bit words
-//     {epoch|status, fp32}, then walks back over its predecessors with a window of LB_W speculative
-//     loads (decoupled look-back); it overwrites S with the inclusive state when known.  Tiles take
-//     their id from an atomic ticket so every predecessor is already resident or finished.
+//     {epoch|status, fp32}.  A few dedicated SCANNER warps (the first tickets; lane = channel) walk the
+//     tiles of their chain in order, h <- P*h + S, with the aggregate words of the next tiles
+//     prefetched, and publish every tile's incoming state as one more tagged word the tile spins on.
+//     The wait per tile is O(1) regardless of how many tiles of a chain are in flight, the association
+//     is the strict token order (bitwise deterministic, identical to the two-pass mode), and there is no
+//     deadlock by construction: CTAs take their role/tile from an atomic ticket, so the scanners and
+//     every predecessor tile are resident or finished before a tile can wait on them.
 //   * two pass: aggregate kernel -> sequential combine kernel -> apply kernel.
 // The backward recomputes the in-tile states from the saved per-tile incoming state (hstart) and runs
 // the same machinery in reverse time for G_t = g_t + abar_{t+1} G_{t+1}.
@@ -22,7 +26,7 @@
 namespace {
 
 constexpr int TS = 4;            // tokens per thread run
-constexpr int LB_W = 8;          // look-back window (speculative loads in flight)
+constexpr int SCAN_K = 32;       // tile aggregates the scanner polls per round trip (shared-memory ring, cp.async)
 constexpr int MODE_FUSED = 0, MODE_AGG = 1, MODE_APPLY = 2;
 constexpr uint32_t ST_AGG = 1, ST_INCL = 2;
 constexpr int SPIN_LIMIT = 1 << 24;
@@ -76,7 +80,9 @@ struct ScanParams {
     void* y; void* y_ssm;    // [B, L, Di]
     float* h_last;           // [B, Di] or null
     float* hstart;           // [B, nchunks, Di] or null
-    unsigned long long* words;   // [nchains*nchunks][Cs][2]
+    unsigned long long* words;   // [nchains*nchunks][Cs][2]  tile aggregates (P, S)
+    unsigned long long* inclw;   // [nchains*nchunks][Cs]     state entering each tile, published by the scanners
+    int n_scan;                  // scanner CTAs (take the first tickets)
     unsigned int* ticket;
     unsigned int* err_flag;
     float* aggP; float* aggS;    // two-pass: [nchains*nchunks][Cs]
@@ -92,47 +98,108 @@ __device__ __forceinline__ unsigned long long pack_word(uint32_t epoch, uint32_t
     return ((unsigned long long)((epoch << 2) | st) << 32) | (unsigned long long)__float_as_uint(v);
 }
 
-// Walks the chain of already-published tiles.  `dir` = -1 walks towards chunk 0 (forward scan),
-// +1 towards the last chunk (reverse scan).  Returns the state entering this tile.
-__device__ __forceinline__ float lookback(const ScanParams& p, int chain, int j, int c, int dir, float boundary,
-                                          unsigned int* err_flag) {
-    float accP = 1.f, accS = 0.f;
-    int q = j + dir;
-    const int last = dir < 0 ? -1 : p.nchunks;
+// deepest power-of-two ring (<= SCAN_K tiles x Cs channels x 16 B) that fits in the tile area of a scanner CTA
+__device__ __forceinline__ int ring_depth(size_t avail_bytes, int Cs) {
+    int k = SCAN_K;
+    while (k >= 4 && (size_t)k * Cs * sizeof(uint4) > avail_bytes) k >>= 1;
+    return k >= 4 ? k : 0;
+}
+
+__device__ __forceinline__ bool word_valid(unsigned long long w, uint32_t epoch) { return (uint32_t)(w >> 34) == epoch; }
+
+// Tile side: spin until the scanner has published the state entering this tile.
+__device__ __forceinline__ float wait_incoming(const ScanParams& p, size_t tile_lin, int c) {
+    const unsigned long long* w = p.inclw + tile_lin * p.Cs + c;
+    unsigned long long v = ab_ld_relaxed_u64(w);
     int spins = 0;
-    while (true) {
-        unsigned long long wP[LB_W], wS[LB_W];
-#pragma unroll
-        for (int k = 0; k < LB_W; ++k) {
-            const int qq = q + dir * k;
-            if (qq != last && (dir < 0 ? qq > last : qq < last)) {
-                const unsigned long long* w = p.words + (((size_t)chain * p.nchunks + qq) * p.Cs + c) * 2;
-                wP[k] = ab_ld_relaxed_u64(w);
-                wS[k] = ab_ld_relaxed_u64(w + 1);
-            } else { wP[k] = 0; wS[k] = 0; }
-        }
-#pragma unroll
-        for (int k = 0; k < LB_W; ++k) {
-            const int qq = q + dir * k;
-            if (dir < 0 ? qq <= last : qq >= last) return fmaf(accP, boundary, accS);
-            const unsigned long long* w = p.words + (((size_t)chain * p.nchunks + qq) * p.Cs + c) * 2;
-            unsigned long long s = wS[k];
-            while ((uint32_t)(s >> 34) != p.epoch) {
-                if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1u); return 0.f; }
-                s = ab_ld_relaxed_u64(w + 1);
-            }
-            const float sv = __uint_as_float((uint32_t)s);
-            if (((uint32_t)(s >> 32) & 3u) == ST_INCL) return fmaf(accP, sv, accS);
-            unsigned long long pw = wP[k];
-            while ((uint32_t)(pw >> 34) != p.epoch) {
-                if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1u); return 0.f; }
-                pw = ab_ld_relaxed_u64(w);
-            }
-            accS = fmaf(accP, sv, accS);
-            accP *= __uint_as_float((uint32_t)pw);
-        }
-        q += dir * LB_W;
+    while (!word_valid(v, p.epoch)) {
+        if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); return 0.f; }
+        v = ab_ld_relaxed_u64(w);
     }
+    return __uint_as_float((uint32_t)v);
+}
+
+// Scanner role.  One CTA per chain (b, slab); DIR = +1 walks chunk 0 -> last (forward scan, starts from h0),
+// DIR = -1 walks last -> 0 (reverse scan of the backward, starts from 0).  For every tile it first publishes the
+// incoming state (which does not depend on the tile's own aggregate), then consumes the tile's (P, S).
+// Fast path (one channel per thread): every round polls the aggregate words of the next SCAN_K tiles with cp.async
+// into a shared-memory ring (the tile buffers are free in a scanner CTA) and consumes the valid prefix, so up to
+// SCAN_K tiles advance per L2 round trip without holding registers.
+template <int DIR>
+__device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem [K][Cs]*/, int K /*ring depth, power of two, 0 = none*/) {
+    const int n = p.nchunks, Cs = p.Cs;
+    const int slab = chain % p.nslab, b = chain / p.nslab;
+    const int c = threadIdx.x;
+    int spins = 0;
+    if ((int)blockDim.x >= Cs && K >= 4) {
+        if (c >= Cs) return;
+        const int cg = slab * Cs + c;
+        float h = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + cg] : 0.f;
+        // ring[k][thread] in shared memory, filled by cp.async (no registers held while the loads are in flight)
+        uint4* myring = ring + c;
+        const int pitch = Cs;
+        int head = 0;
+        while (head < n) {
+            const int hi = min(head + K, n);
+            for (int s2 = head; s2 < hi; ++s2) {
+                const int j = DIR > 0 ? s2 : n - 1 - s2;
+                const unsigned long long* w = p.words + (((size_t)chain * n + j) * Cs + c) * 2;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ab_smem_u32(myring + (size_t)(s2 & (K - 1)) * pitch)), "l"(w) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            {   // the state entering tile `head` is known now: publish it while the loads fly
+                const int j = DIR > 0 ? head : n - 1 - head;
+                ab_st_relaxed_u64(p.inclw + ((size_t)chain * n + j) * Cs + c, pack_word(p.epoch, ST_INCL, h));
+                if (DIR > 0 && p.hstart) p.hstart[((size_t)b * n + j) * p.Di + cg] = h;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            bool stop = false;
+            while (head < hi && !stop) {
+                uint4 w4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w4[u] = myring[(size_t)((head + u) & (K - 1)) * pitch];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (stop || head >= hi) break;
+                    const unsigned long long wp = ((unsigned long long)w4[u].y << 32) | w4[u].x;
+                    const unsigned long long wsv = ((unsigned long long)w4[u].w << 32) | w4[u].z;
+                    if (!word_valid(wp, p.epoch) || !word_valid(wsv, p.epoch)) { stop = true; break; }
+                    h = fmaf(__uint_as_float(w4[u].x), h, __uint_as_float(w4[u].z));
+                    ++head;
+                    if (head < n) {
+                        const int j = DIR > 0 ? head : n - 1 - head;
+                        ab_st_relaxed_u64(p.inclw + ((size_t)chain * n + j) * Cs + c, pack_word(p.epoch, ST_INCL, h));
+                        if (DIR > 0 && p.hstart) p.hstart[((size_t)b * n + j) * p.Di + cg] = h;
+                    }
+                }
+            }
+            if (stop && ++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+        }
+        if (DIR > 0 && p.h_last) p.h_last[(size_t)b * p.Di + cg] = h;
+        return;
+    }
+    // generic path (blocks narrower than the slab: tiny sequences): state in shared memory, no prefetch
+    for (int cc = c; cc < Cs; cc += blockDim.x) hs[cc] = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + slab * Cs + cc] : 0.f;
+    for (int step = 0; step < n; ++step) {
+        const int j = DIR > 0 ? step : n - 1 - step;
+        const size_t tl = (size_t)chain * n + j;
+        for (int cc = c; cc < Cs; cc += blockDim.x) {
+            const float h = hs[cc];
+            ab_st_relaxed_u64(p.inclw + tl * Cs + cc, pack_word(p.epoch, ST_INCL, h));
+            if (DIR > 0 && p.hstart) p.hstart[((size_t)b * n + j) * p.Di + slab * Cs + cc] = h;
+        }
+        for (int cc = c; cc < Cs; cc += blockDim.x) {
+            const unsigned long long* w = p.words + (tl * Cs + cc) * 2;
+            unsigned long long wp = ab_ld_relaxed_u64(w), wsv = ab_ld_relaxed_u64(w + 1);
+            while (!word_valid(wp, p.epoch) || !word_valid(wsv, p.epoch)) {
+                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+                wp = ab_ld_relaxed_u64(w); wsv = ab_ld_relaxed_u64(w + 1);
+            }
+            hs[cc] = fmaf(__uint_as_float((uint32_t)wp), hs[cc], __uint_as_float((uint32_t)wsv));
+        }
+    }
+    if (DIR > 0 && p.h_last)
+        for (int cc = c; cc < Cs; cc += blockDim.x) p.h_last[(size_t)b * p.Di + slab * Cs + cc] = hs[cc];
 }
 
 // softplus'd delta rows of this tile (plus one extra row for the reverse scan) into shared memory
@@ -213,7 +280,14 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
         ab_fence_mbar_init();
     }
     __syncthreads();
-    const int ticket = (int)s_ticket;
+    int ticket = (int)s_ticket;
+    if (MODE == MODE_FUSED) {
+        if (ticket < p.n_scan) {
+            scanner_role<+1>(p, ticket, hT, reinterpret_cast<uint4*>(smem), ring_depth((size_t)n_tiles_staged * pitch, Cs));
+            return;
+        }
+        ticket -= p.n_scan;
+    }
     const int chain = ticket % p.nchains, j = ticket / p.nchains;
     const int slab = chain % p.nslab, b = chain / p.nslab;
     const int c0 = slab * Cs, row0 = j * Tt;
@@ -280,19 +354,11 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
             hin = p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
         } else {
             unsigned long long* w = p.words + (tile_lin * Cs + c) * 2;
-            const float bnd = p.h0 ? __ldg(p.h0 + (size_t)b * p.Di + c0 + c) : 0.f;
-            if (j == 0) {
-                hin = bnd;
-            } else {
-                ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
-                ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
-                hin = lookback(p, chain, j, c, -1, bnd, p.err_flag);
-            }
-            ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_INCL, fmaf(Pt, hin, St)));
-            if (p.hstart) p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c] = hin;
+            ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
+            ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
+            hin = wait_incoming(p, tile_lin, c);        // hstart / h_last are written by the scanner
         }
         hT[c] = hin;
-        if (p.h_last && j == p.nchunks - 1) p.h_last[(size_t)b * p.Di + c0 + c] = fmaf(Pt, hin, St);
     }
     if (MODE == MODE_AGG) return;
     __syncthreads();
@@ -385,7 +451,14 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
         ab_fence_mbar_init();
     }
     __syncthreads();
-    const int ticket = (int)s_ticket;
+    int ticket = (int)s_ticket;
+    if (MODE == MODE_FUSED) {
+        if (ticket < p.n_scan) {
+            scanner_role<-1>(p, ticket, hT, reinterpret_cast<uint4*>(smem), ring_depth(5 * pitch, Cs));
+            return;
+        }
+        ticket -= p.n_scan;
+    }
     const int chain = ticket % p.nchains;
     const int j = p.nchunks - 1 - ticket / p.nchains;       // reverse time order
     const int slab = chain % p.nslab, b = chain / p.nslab;
@@ -548,14 +621,9 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
             gin = gin_ws[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
         } else {
             unsigned long long* w = p.words + (tile_lin * Cs + c) * 2;
-            if (j == p.nchunks - 1) {
-                gin = 0.f;
-            } else {
-                ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
-                ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
-                gin = lookback(p, chain, j, c, +1, 0.f, p.err_flag);
-            }
-            ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_INCL, fmaf(Pt, gin, St)));
+            ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
+            ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
+            gin = wait_incoming(p, tile_lin, c);
         }
         hT[c] = gin;
     }
@@ -640,7 +708,7 @@ __global__ void __launch_bounds__(256) scan_param_reduce_kernel(const float* __r
 // host side
 // ---------------------------------------------------------------------------------------------
 struct WsLayout {
-    size_t off_ticket, off_err, off_words, off_aggP, off_aggS, off_gin, off_part, total;
+    size_t off_ticket, off_err, off_words, off_incl, off_aggP, off_aggS, off_gin, off_part, total;
 };
 WsLayout ws_layout(const ScanTiling& t, int B, int Di) {
     WsLayout w;
@@ -649,6 +717,7 @@ WsLayout ws_layout(const ScanTiling& t, int B, int Di) {
     w.off_ticket = o; o += 64;
     w.off_err = o; o += 64;
     w.off_words = o; o += ntiles * t.Cs * 2 * sizeof(unsigned long long);
+    w.off_incl = o; o += ntiles * t.Cs * sizeof(unsigned long long);
     w.off_aggP = o; o += ntiles * t.Cs * sizeof(float);
     w.off_aggS = o; o += ntiles * t.Cs * sizeof(float);
     w.off_gin = o; o += (size_t)B * t.nchunks * Di * sizeof(float);
@@ -679,14 +748,26 @@ size_t smem_bytes(const ScanTiling& t, int ntiles_staged_max) {
     return o;
 }
 
+// scanner CTAs: one per chain, all resident for the whole launch
+int scanner_ctas(const ScanParams& p, int threads) { (void)threads; return p.nchains; }
+// single pass only while the scanners occupy a small part of the machine; with that many independent chains the
+// two-pass schedule has all the parallelism it needs
+bool single_pass_ok(int B, const ScanTiling& t, int threads) {
+    ScanParams q;
+    q.nchains = B * t.nslab; q.Cs = t.Cs;
+    return scanner_ctas(q, threads) <= ab_num_sms();
+}
+
 template <typename T, int MODE>
 int launch_fwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
     const size_t smem = smem_bytes(t, n_staged);
     auto kfn = scan_fwd_kernel<T, MODE>;
     AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = t.n_s * (t.Cs / (16 / (int)sizeof(T)));
-    const unsigned grid = (unsigned)(p.nchains * p.nchunks);
-    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    ScanParams q = p;
+    q.n_scan = MODE == MODE_FUSED ? scanner_ctas(p, threads) : 0;
+    const unsigned grid = (unsigned)(p.nchains * p.nchunks + q.n_scan);
+    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], q);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
@@ -697,8 +778,10 @@ int launch_bwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTili
     auto kfn = scan_bwd_kernel<T, MODE>;
     AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = t.n_s * (t.Cs / 4);
-    const unsigned grid = (unsigned)(p.nchains * p.nchunks);
-    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p, gin);
+    ScanParams q = p;
+    q.n_scan = MODE == MODE_FUSED ? scanner_ctas(p, threads) : 0;
+    const unsigned grid = (unsigned)(p.nchains * p.nchunks + q.n_scan);
+    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], q, gin);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
@@ -749,10 +832,15 @@ extern "C" int ab_selective_scan_fwd(const void* xa, const void* dlog, const voi
     p.ticket = (unsigned int*)(w8 + wl.off_ticket);
     p.err_flag = (unsigned int*)(w8 + wl.off_err);
     p.words = (unsigned long long*)(w8 + wl.off_words);
+    p.inclw = (unsigned long long*)(w8 + wl.off_incl);
     p.aggP = (float*)(w8 + wl.off_aggP);
     p.aggS = (float*)(w8 + wl.off_aggS);
     p.epoch = epoch;
     const bool f32 = dtype == AB_F32;
+    if (mode == AB_SCAN_SINGLE_PASS && !single_pass_ok(B, t, t.n_s * (t.Cs / t.V_f))) {
+        AB_REQUIRE(hstart != nullptr, "selective_scan_fwd: this many chains run two-pass, which needs hstart");
+        mode = AB_SCAN_TWO_PASS;
+    }
     if (mode == AB_SCAN_SINGLE_PASS) {
         AB_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), stream));
         return f32 ? launch_fwd_mode<float, MODE_FUSED>(maps, p, t, 4, stream)
@@ -799,12 +887,14 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
     p.ticket = (unsigned int*)(w8 + wl.off_ticket);
     p.err_flag = (unsigned int*)(w8 + wl.off_err);
     p.words = (unsigned long long*)(w8 + wl.off_words);
+    p.inclw = (unsigned long long*)(w8 + wl.off_incl);
     p.aggP = (float*)(w8 + wl.off_aggP);
     p.aggS = (float*)(w8 + wl.off_aggS);
     p.part = (float*)(w8 + wl.off_part);
     float* gin = (float*)(w8 + wl.off_gin);
     p.epoch = epoch;
     const bool f32 = dtype == AB_F32;
+    if (mode == AB_SCAN_SINGLE_PASS && !single_pass_ok(B, t, t.n_s * (t.Cs / 4))) mode = AB_SCAN_TWO_PASS;
     if (mode == AB_SCAN_SINGLE_PASS) {
         AB_CHECK_CUDA(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), stream));
         if (int e = f32 ? launch_bwd_mode<float, MODE_FUSED>(maps, p, t, gin, stream)

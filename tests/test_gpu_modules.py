@@ -194,10 +194,8 @@ def test_state_dict_round_trip_uses_reference_keys():
         assert torch.equal(out_sd[k].cpu(), sd[k]), k
 
 
-def test_block_is_deterministic(monkeypatch):
-    """Bitwise run-to-run determinism (two-pass scan; the single-pass look-back is equal only up to fp32 rounding)."""
-    from apertis_llm_b200 import _lib, ops
-    monkeypatch.setattr(ops, "SCAN_MODE", _lib.SCAN_TWO_PASS)
+def test_block_is_deterministic():
+    """Bitwise run-to-run determinism of the whole block (forward, input and parameter gradients)."""
     spec, g = load_golden("block_small_train")
     outs = []
     for _ in range(2):
