@@ -53,8 +53,8 @@ SIGNATURES = {
     "ab_moe_segment_colsum": (I, [P, P, P, P, P, SZ, I, I, I, I64, I, P]),
     "ab_moe_router_bwd_workspace_bytes": (SZ, [I, I, I]),
     "ab_moe_router_bwd": (I, [P] * 24 + [SZ, I, I, I, I, I, P]),
-    "ab_grouped_gemm_nt": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, P]),
-    "ab_grouped_gemm_nn": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, P]),
+    "ab_grouped_gemm_nt": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, F, P, P]),
+    "ab_grouped_gemm_nn": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, F, P, P]),
     "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, I, I64, P]),
     "ab_layernorm_fwd": (I, [P, P, P, F, P, P, I, I, I, I, P]),
     "ab_layernorm_bwd_workspace_bytes": (SZ, [I, I]),

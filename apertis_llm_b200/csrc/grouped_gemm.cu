@@ -43,6 +43,9 @@ struct GemmParams {
     const int32_t* seg_off;
     const float* bias;
     const void* aux;
+    const uint32_t* drop_seed;   // device [2]: seed of the expert-internal Dropout mask (core.py:439); NULL = no dropout
+    uint32_t drop_thresh;        // drop when hash < thresh (= p * 2^32)
+    float drop_scale;            // 1 / (1 - p)
     void* c;
     void* c2;
     float* cw;
@@ -77,6 +80,18 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     if (act == AB_ACT_RELU) return x > 0.f ? 1.f : 0.f;
     const float s = ab_sigmoid(x);
     return s * fmaf(x, 1.f - s, 1.f);
+}
+
+// Dropout keep-mask of element (row, col) of the expert hidden activation: counter-based hash of the element index and
+// a 64-bit seed, so the backward regenerates exactly the forward's mask without storing it.
+__device__ __forceinline__ bool drop_keep(uint32_t s0, uint32_t s1, uint32_t row, uint32_t col, uint32_t thresh) {
+    uint32_t x = (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u) ^ s0;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16; x += s1;
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12;
+    return x >= thresh;
 }
 
 // ---- descriptors ------------------------------------------------------------------------------
@@ -183,6 +198,12 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
                 stage_and_store<MODE, F32>(p, stg, f, reinterpret_cast<unsigned char*>(p.c2), lane, quarter, m_tile, ncol, ncol_end);
 #pragma unroll
                 for (int i = 0; i < U; ++i) f[i] = act_fwd(f[i], p.act);
+                if (p.drop_seed) {
+                    const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
+                    const uint32_t grow = (uint32_t)(m_tile * BM + quarter * 32 + lane);
+#pragma unroll
+                    for (int i = 0; i < U; ++i) f[i] = drop_keep(s0, s1, grow, (uint32_t)(ncol + i), p.drop_thresh) ? f[i] * p.drop_scale : 0.f;
+                }
             } else if (p.epi == AB_EPI_DACT) {
                 // saved pre-activation tile: coalesced 16-byte loads -> staging -> each thread reads its own row
                 __syncwarp();
@@ -207,6 +228,12 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
                     for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(pre[i], p.act);
                 }
                 __syncwarp();
+                if (p.drop_seed) {
+                    const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
+                    const uint32_t grow = (uint32_t)(m_tile * BM + quarter * 32 + lane);
+#pragma unroll
+                    for (int i = 0; i < U; ++i) f[i] = drop_keep(s0, s1, grow, (uint32_t)(ncol + i), p.drop_thresh) ? f[i] * p.drop_scale : 0.f;
+                }
             }
         }
         // ---- stage this thread's row, then store 8 rows x 64 B per instruction
@@ -415,7 +442,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 
 int gemm_rows(int mode, const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
               const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E, int epi, int act,
-              int c_dtype, cudaStream_t stream) {
+              int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream) {
+    AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "grouped_gemm: dropout probability must be in [0, 1)");
+    AB_REQUIRE(drop_p == 0.f || (drop_seed != nullptr && (epi == AB_EPI_BIAS_ACT || epi == AB_EPI_DACT)),
+               "grouped_gemm: dropout needs a seed and the bias+act / dact epilogue");
     AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm: max_rows must be a positive multiple of %d", BM);
     AB_REQUIRE(N > 0 && K > 0 && E > 0 && N % 8 == 0 && K % 8 == 0, "grouped_gemm: N (%d) and K (%d) must be multiples of 8", N, K);
     AB_REQUIRE(c_dtype == AB_F32 || c_dtype == AB_BF16, "grouped_gemm: bad output dtype");
@@ -430,6 +460,11 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
     p.epi = epi; p.act = act; p.c_f32 = c_dtype == AB_F32;
     p.tile_expert = tile_expert; p.n_rows = n_rows; p.bias = bias; p.aux = aux; p.c = c; p.c2 = c2;
+    if (drop_p > 0.f) {
+        p.drop_seed = drop_seed;
+        p.drop_thresh = (uint32_t)((double)drop_p * 4294967296.0);
+        p.drop_scale = 1.0f / (1.0f - drop_p);
+    }
     AB_REQUIRE(((uintptr_t)c % 16) == 0 && (c2 == nullptr || ((uintptr_t)c2 % 16) == 0) && (aux == nullptr || ((uintptr_t)aux % 16) == 0),
                "grouped_gemm: output / aux pointers must be 16-byte aligned");
     CUtensorMap ta, tb;
@@ -447,14 +482,14 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
 
 extern "C" int ab_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                                   const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
-                                  int epi, int act, int c_dtype, cudaStream_t stream) {
-    return gemm_rows(MODE_NT, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, stream);
+                                  int epi, int act, int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream) {
+    return gemm_rows(MODE_NT, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, drop_p, drop_seed, stream);
 }
 
 extern "C" int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                                   const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
-                                  int epi, int act, int c_dtype, cudaStream_t stream) {
-    return gemm_rows(MODE_NN, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, stream);
+                                  int epi, int act, int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream) {
+    return gemm_rows(MODE_NN, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, drop_p, drop_seed, stream);
 }
 
 extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,

@@ -113,7 +113,10 @@ class _MoEExpertsEP(torch.autograd.Function):
             a1, w1, k1 = ops._split_cols(xr, 0), ops._split_cols(W1.view(El * I, Dm), 1), 3 * Dm
         else:
             a1, w1, k1 = xr, ops._cast_bf16(W1), Dm
-        h, hpre = ops.grouped_gemm("nt", a1, w1, rplan, I, k1, El, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True)
+        drop_p = float(cfg.get("drop_p", 0.0)) if training else 0.0
+        drop_seed = torch.randint(0, 2 ** 31 - 1, (2,), device=dev, dtype=torch.int32) if drop_p > 0.0 else None
+        h, hpre = ops.grouped_gemm("nt", a1, w1, rplan, I, k1, El, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True,
+                                   drop_p=drop_p, drop_seed=drop_seed)
         if precise:
             a2, w2, k2 = ops._split_cols(h, 0), ops._split_cols(W2.view(El * Dm, I), 1), 3 * I
         else:
@@ -127,7 +130,8 @@ class _MoEExpertsEP(torch.autograd.Function):
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
         lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
-        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt)
+        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt, drop_p=drop_p)
+        ctx.drop_seed = drop_seed
         ctx.group = group
         ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
         ctx.rplan = rplan
@@ -158,7 +162,8 @@ class _MoEExpertsEP(torch.autograd.Function):
             G = W * El
             lseg3 = (lseg * 3).contiguous()
             w2r = ops._split_rows(W2.view(El * Dm, I), 1, None, El, Dm)
-            dhpre = ops.grouped_gemm("nn", ops._split_cols(dyr, 0), w2r, rplan, I, 3 * Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dhpre = ops.grouped_gemm("nn", ops._split_cols(dyr, 0), w2r, rplan, I, 3 * Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
+                                     drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             sr = lambda t, which: ops._split_rows(t, which, None, G, seg)
             dW2 = ops.grouped_gemm_tn(sr(dyr, 0), sr(h, 1), lseg3, Dm, I, El, nsrc=W, src_stride=3 * stride)
             dW1 = ops.grouped_gemm_tn(sr(dhpre, 0), sr(xr, 1), lseg3, I, Dm, El, nsrc=W, src_stride=3 * stride)
@@ -166,7 +171,8 @@ class _MoEExpertsEP(torch.autograd.Function):
             dxnr = ops.grouped_gemm("nn", ops._split_cols(dhpre, 0), w1r, rplan, Dm, 3 * I, El, out_dtype=torch.float32)
         else:
             w1b, w2b = ops._cast_bf16(W1), ops._cast_bf16(W2)
-            dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
+                                     drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             dW2 = ops.grouped_gemm_tn(dyr, h, lseg, Dm, I, El, nsrc=W, src_stride=stride)
             dW1 = ops.grouped_gemm_tn(dhpre, xr, lseg, I, Dm, El, nsrc=W, src_stride=stride)
             dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)

@@ -257,9 +257,6 @@ class AdaptiveExpertSystem(nn.Module):
             return hidden_states, zero(), zero()                              # core.py:474-475
         _lib.ensure_device(hidden_states.device)
         ac = _autocast_dtype()
-        if self.training and self.hidden_dropout_prob > 0:
-            raise NotImplementedError("expert-internal Dropout (core.py:439) with p > 0 is not implemented in the B200 path yet; "
-                                      "set hidden_dropout_prob = 0")
         B, L, Dm = hidden_states.shape
         S, E, K = B * L, self.num_experts, self.experts_per_token
         x2 = hidden_states.reshape(S, Dm)
@@ -272,7 +269,7 @@ class AdaptiveExpertSystem(nn.Module):
         cfg = dict(K=K, eps=self.eps, act=_lib.ACT[self.act_name], training=training, cap=cap,
                    lb_coef=self.load_balancing_loss_coef if self.use_load_balancing_loss else 0.0,
                    rz_coef=self.router_z_loss_coef if self.use_router_z_loss else 0.0,
-                   active=self._draw_active_mask(x2.device),
+                   active=self._draw_active_mask(x2.device), drop_p=self.hidden_dropout_prob,
                    precise=(x2.dtype == torch.float32 and ac is None))
         if self.ep_world > 1:
             from . import ep

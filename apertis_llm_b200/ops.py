@@ -283,13 +283,13 @@ def _split_rows(t2d, which, seg_off=None, G=1, rows_per_group=0):
 
 
 def grouped_gemm(mode, A, W, plan, N, K, E, *, bias=None, aux=None, epi=_lib.EPI_NONE, act=0, out_dtype=torch.bfloat16,
-                 want_c2=False):
+                 want_c2=False, drop_p=0.0, drop_seed=None):
     """C = epi(A @ W[e]^T) ('nt', W [E,N,K]) or epi(A @ W[e]) ('nn', W [E,K,N]) over the permuted rows."""
     max_rows = A.shape[0]
     c = torch.empty(max_rows, N, dtype=out_dtype, device=A.device)
     c2 = torch.empty(max_rows, N, dtype=out_dtype, device=A.device) if want_c2 else None
     call("ab_grouped_gemm_" + mode, ptr(A), ptr(W), ptr(bias), ptr(aux), ptr(c), ptr(c2), ptr(plan["tile_expert"]),
-         ptr(plan["n_rows"]), max_rows, N, K, E, epi, act, dt(out_dtype), stream_ptr())
+         ptr(plan["n_rows"]), max_rows, N, K, E, epi, act, dt(out_dtype), float(drop_p), ptr(drop_seed), stream_ptr())
     return (c, c2) if want_c2 else c
 
 
@@ -335,7 +335,12 @@ class _MoEExperts(torch.autograd.Function):
             k1 = 3 * Dm
         else:
             a1, w1, k1 = xn, _cast_bf16(W1), Dm
-        h, hpre = grouped_gemm("nt", a1, w1, plan, I, k1, E, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True)
+        drop_p = float(cfg.get("drop_p", 0.0)) if training else 0.0
+        drop_seed = None
+        if drop_p > 0.0:      # seed from torch's CUDA generator (restored by torch.utils.checkpoint on recompute), kept on device
+            drop_seed = torch.randint(0, 2 ** 31 - 1, (2,), device=dev, dtype=torch.int32)
+        h, hpre = grouped_gemm("nt", a1, w1, plan, I, k1, E, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True,
+                               drop_p=drop_p, drop_seed=drop_seed)
         if precise:
             a2 = _split_cols(h, 0)
             w2 = _split_cols(W2.view(E * Dm, I), 1)
@@ -350,7 +355,8 @@ class _MoEExperts(torch.autograd.Function):
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
         lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
-        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt)
+        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt, drop_p=drop_p)
+        ctx.drop_seed = drop_seed
         ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
         ctx.save_for_backward(x2, rn_w, rn_b, Wr, br, ln_w, W1, W2, noise if use_noise else None,
                               r["stats"], r["gates"], r["idx"], r["probs"], r["lse"], r["lclean"], r["w"], aux,
@@ -378,14 +384,16 @@ class _MoEExperts(torch.autograd.Function):
         if precise:
             seg3 = (seg * 3).contiguous()
             w2r = _split_rows(W2.view(E * Dm, I), 1, None, E, Dm)                 # [E, 3*Dm, I]
-            dhpre = grouped_gemm("nn", _split_cols(dy, 0), w2r, plan, I, 3 * Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dhpre = grouped_gemm("nn", _split_cols(dy, 0), w2r, plan, I, 3 * Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
+                                 drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             dW2 = grouped_gemm_tn(_split_rows(dy, 0, seg, E), _split_rows(h, 1, seg, E), seg3, Dm, I, E)
             dW1 = grouped_gemm_tn(_split_rows(dhpre, 0, seg, E), _split_rows(xn, 1, seg, E), seg3, I, Dm, E)
             w1r = _split_rows(W1.view(E * I, Dm), 1, None, E, I)                  # [E, 3*I, Dm]
             dxn = grouped_gemm("nn", _split_cols(dhpre, 0), w1r, plan, Dm, 3 * I, E, out_dtype=torch.float32)
         else:
             w1b, w2b = _cast_bf16(W1), _cast_bf16(W2)
-            dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt)
+            dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
+                                 drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             dW2 = grouped_gemm_tn(dy, h, seg, Dm, I, E)
             dW1 = grouped_gemm_tn(dhpre, xn, seg, I, Dm, E)
             dxn = grouped_gemm("nn", dhpre, w1b, plan, Dm, I, E, out_dtype=torch.bfloat16)    # bf16 like the reference's autocast Linear backward

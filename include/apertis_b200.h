@@ -197,12 +197,15 @@ int ab_moe_router_bwd(const void* x, const float* stats, const float* ln_w, cons
 #define AB_EPI_BIAS 1
 #define AB_EPI_BIAS_ACT 2
 #define AB_EPI_DACT 3
+/* drop_p > 0 fuses the expert-internal nn.Dropout (core.py:439) into the epilogue: AB_EPI_BIAS_ACT scales
+ * act(pre) by mask/(1-p), AB_EPI_DACT applies the same mask to the incoming gradient.  The keep-mask is a
+ * counter-based hash of (row, column, drop_seed[0..1]) (drop_seed: device uint32[2]), regenerated, not stored. */
 int ab_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                        const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
-                       int epi, int act, int c_dtype, cudaStream_t stream);
+                       int epi, int act, int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream);
 int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                        const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
-                       int epi, int act, int c_dtype, cudaStream_t stream);
+                       int epi, int act, int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream);
 /* nsrc > 1 (expert-parallel receive layout): expert e's rows are the nsrc blocks
  * [s*src_stride + seg_off[e], s*src_stride + seg_off[e+1]), s = 0..nsrc-1. */
 int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,

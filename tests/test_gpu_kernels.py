@@ -288,3 +288,42 @@ def test_layer_norm(S, Dm, out_dtype):
     tol = TOL[out_dtype]
     assert rel_err(out.float(), ref.detach()) < tol
     assert rel_err(xg.grad, xr.grad) < 1e-4 and rel_err(wg.grad, wr.grad) < 1e-4 and rel_err(bg.grad, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# expert-internal dropout fused into the GEMM epilogues (core.py:439)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_grouped_gemm_dropout_mask_consistent(p):
+    from apertis_llm_b200 import _lib, ops
+    d = dev()
+    N, K, counts = 704, 256, [300, 129, 0, 640]
+    E = len(counts)
+    plan, seg, te, valid = _fake_plan(counts, d)
+    g = torch.Generator().manual_seed(7)
+    A = (torch.randn(plan["max_rows"], K, generator=g) * 0.5).to(torch.bfloat16).to(d)
+    W = (torch.randn(E, N, K, generator=g) * 0.05).to(torch.bfloat16).to(d)
+    bias = (torch.randn(E, N, generator=g) * 0.1).to(d)
+    seed = torch.tensor([12345, 678], dtype=torch.int32, device=d)
+    total = int(seg[-1])
+    h0, pre0 = ops.grouped_gemm("nt", A, W, plan, N, K, E, bias=bias, epi=_lib.EPI_BIAS_ACT, act=0, want_c2=True)
+    h1, pre1 = ops.grouped_gemm("nt", A, W, plan, N, K, E, bias=bias, epi=_lib.EPI_BIAS_ACT, act=0, want_c2=True, drop_p=p, drop_seed=seed)
+    h2, _ = ops.grouped_gemm("nt", A, W, plan, N, K, E, bias=bias, epi=_lib.EPI_BIAS_ACT, act=0, want_c2=True, drop_p=p, drop_seed=seed)
+    assert torch.equal(pre0[:total], pre1[:total]) and torch.equal(h1[:total], h2[:total])   # pre-activation untouched; mask reproducible
+    h0f, h1f = h0[:total].float(), h1[:total].float()
+    keep = h1f != 0
+    frac = 1.0 - keep.float().mean().item()
+    n = keep.numel()
+    assert abs(frac - p) < 5 * (p * (1 - p) / n) ** 0.5 + 2e-3, frac    # gelu(x) == 0 exactly is negligible
+    assert rel_err(h1f[keep], (h0f / (1 - p))[keep]) < 1e-2
+    # a different seed gives a different mask
+    h3, _ = ops.grouped_gemm("nt", A, W, plan, N, K, E, bias=bias, epi=_lib.EPI_BIAS_ACT, act=0, want_c2=True, drop_p=p,
+                             drop_seed=torch.tensor([12346, 678], dtype=torch.int32, device=d))
+    assert not torch.equal(h1[:total], h3[:total])
+    # the dact epilogue regenerates the same mask over the same [rows, N] index space
+    dy = (torch.randn(plan["max_rows"], K, generator=g) * 0.5).to(torch.bfloat16).to(d)
+    W2 = (torch.randn(E, K, N, generator=g) * 0.05).to(torch.bfloat16).to(d)
+    g0 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=pre1, epi=_lib.EPI_DACT, act=0, out_dtype=torch.float32)
+    g1 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=pre1, epi=_lib.EPI_DACT, act=0, out_dtype=torch.float32, drop_p=p, drop_seed=seed)
+    assert torch.equal((g1[:total] != 0) | (g0[:total] == 0), keep | (g0[:total] == 0))
+    assert rel_err(g1[:total][keep], (g0[:total] / (1 - p))[keep]) < 1e-5

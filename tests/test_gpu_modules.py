@@ -232,3 +232,38 @@ def test_no_cpu_fallback():
     m = SelectiveLinearAttention(BlockConfig(hidden_size=64, num_attention_heads=2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 4, 64))
+
+
+def test_expert_dropout_train_vs_eval_statistics():
+    """hidden_dropout_prob > 0: training output is an unbiased, noisier version of the p = 0 output; eval ignores it;
+    the mask follows torch's CUDA generator (same seed -> same output), and gradients flow."""
+    from apertis_llm_b200 import AdaptiveExpertSystem, BlockConfig
+    spec = dict(Dm=128, H=2, I=512, E=8, K=2, B=4, L=512, seed=21)
+    sd = O.make_layer_params(spec["Dm"], spec["H"], spec["I"], spec["E"], seed=spec["seed"])
+    _, moe_sd, _ = O.split_layer_params(sd)
+    x, noise = O.make_inputs(spec["B"], spec["L"], spec["Dm"], spec["E"], seed=spec["seed"])
+    outs = {}
+    for p in (0.0, 0.3):
+        m = AdaptiveExpertSystem(BlockConfig(hidden_size=spec["Dm"], num_attention_heads=spec["H"], intermediate_size=spec["I"],
+                                             hidden_dropout_prob=p))
+        m.load_state_dict(moe_sd, strict=True)
+        m = m.to(dev()).train()
+        m._draw_noise = lambda S, E, device: noise.to(device)
+        xg = x.to(dev()).requires_grad_(True)
+        torch.manual_seed(5)
+        o1, _, _ = m(xg)
+        o1.pow(2).mean().backward()
+        assert torch.isfinite(xg.grad).all() and xg.grad.abs().max() > 0
+        torch.manual_seed(5)
+        o2, _, _ = m(xg)
+        assert torch.equal(o1, o2)
+        m.eval()
+        oe, _, _ = m(xg)
+        outs[p] = (o1.detach(), oe.detach())
+    assert torch.equal(outs[0.0][1], outs[0.3][1])                     # eval ignores dropout
+    a, b = outs[0.3][0], outs[0.0][0]
+    assert not torch.equal(a, b)
+    # unbiased: the mean difference over ~260k outputs is far below the per-element noise
+    diff = (a - b)
+    assert diff.mean().abs().item() < 0.05 * diff.std().item() + 1e-6
+    assert rel_err(a, b) < 1.0
