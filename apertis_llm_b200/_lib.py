@@ -59,6 +59,7 @@ SIGNATURES = {
     "ab_layernorm_fwd": (I, [P, P, P, F, P, P, I, I, I, I, P]),
     "ab_layernorm_bwd_workspace_bytes": (SZ, [I, I]),
     "ab_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, P]),
+    "ab_dropout_add": (I, [P, P, P, F, P, I64, I, I, P]),
     "ab_cast_f32_to_bf16": (I, [P, P, I64, P]),
     "ab_split_f32_to_bf16x3": (I, [P, P, I64, I64, I, P]),
     "ab_split_f32_to_bf16x3_rows": (I, [P, P, P, I, I64, I64, I, P]),

@@ -208,3 +208,58 @@ extern "C" int ab_layernorm_bwd(const void* dy, const void* x, const float* stat
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// output dropout + residual add of the block wrappers (core.py:836-837, 918-919):  out = dropout(sub) + res
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ bool out_keep(uint32_t s0, uint32_t s1, uint64_t i, uint32_t thresh) {
+    uint32_t x = ((uint32_t)i * 0x9E3779B1u) ^ ((uint32_t)(i >> 32) * 0x85EBCA77u) ^ s0;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16; x += s1;
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12;
+    return x >= thresh;
+}
+
+// out[i] = (keep ? sub[i]*scale : 0) + (res ? res[i] : 0); 4 elements per thread
+template <typename TS, typename TR>
+__global__ void __launch_bounds__(256) dropout_add_kernel(const TS* __restrict__ sub, const TR* __restrict__ res, TR* __restrict__ out,
+                                                          const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int64_t n) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float a[4], r[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+    ld4<TS>(sub + i, a);
+    if (res) ld4<TR>(res + i, r);
+    uint32_t s0 = 0, s1 = 0;
+    if (seed) { s0 = __ldg(seed); s1 = __ldg(seed + 1); }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const bool keep = !seed || out_keep(s0, s1, (uint64_t)(i + v), thresh);
+        o[v] = (keep ? a[v] * scale : 0.f) + r[v];
+    }
+    st4<TR>(out + i, o);
+}
+
+}  // namespace
+
+extern "C" int ab_dropout_add(const void* sub, const void* res, void* out, float p, const uint32_t* seed, int64_t n, int sub_dtype,
+                              int out_dtype, cudaStream_t stream) {
+    AB_REQUIRE(n > 0 && n % 4 == 0, "dropout_add: element count must be a positive multiple of 4");
+    AB_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || seed), "dropout_add: p must be in [0,1) and needs a seed when > 0");
+    const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+    const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    const uint32_t* sd = p > 0.f ? seed : nullptr;
+    const unsigned grid = (unsigned)ab_ceil_div(n / 4, 256);
+#define AB_DA(TS, TR) dropout_add_kernel<TS, TR><<<grid, 256, 0, stream>>>((const TS*)sub, (const TR*)res, (TR*)out, sd, thresh, scale, n)
+    if (sub_dtype == AB_F32 && out_dtype == AB_F32) AB_DA(float, float);
+    else if (sub_dtype == AB_BF16 && out_dtype == AB_F32) AB_DA(__nv_bfloat16, float);
+    else if (sub_dtype == AB_BF16 && out_dtype == AB_BF16) AB_DA(__nv_bfloat16, __nv_bfloat16);
+    else if (sub_dtype == AB_F32 && out_dtype == AB_BF16) AB_DA(float, __nv_bfloat16);
+    else AB_REQUIRE(false, "dropout_add: bad dtypes");
+#undef AB_DA
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}

@@ -304,7 +304,7 @@ class _AttentionWrapper(nn.Module):
                                 out_dtype=ac if (ac is not None and hidden_s.dtype == torch.float32) else None)
         out, proxy, cache = self.attention_mechanism_impl(normed, attention_mask=att_mask, position_ids=pos_ids,
                                                           past_key_value=past_kv, output_attentions=output_att, use_cache=use_c)
-        return self.output_dropout(out) + hidden_s, proxy, cache
+        return ops.dropout_add(out, hidden_s, self.output_dropout.p, self.training), proxy, cache
 
 
 class _FeedForwardWrapper(nn.Module):
@@ -321,7 +321,7 @@ class _FeedForwardWrapper(nn.Module):
     def forward(self, hidden_s):
         normed = ops.layer_norm(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
         out, lb, rz = self.ffn(normed)
-        return self.output_dropout(out) + hidden_s, lb, rz
+        return ops.dropout_add(out, hidden_s, self.output_dropout.p, self.training), lb, rz
 
 
 class ApertisLayerB200(nn.Module):

@@ -95,6 +95,33 @@ class _LayerNorm(torch.autograd.Function):
         return dx.view(ctx.shape), dw, db, None, None
 
 
+class _DropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sub, res, p):
+        _lib.ensure_device(sub.device)
+        sub = sub.contiguous()
+        res = res.contiguous()
+        out = torch.empty_like(res)
+        seed = torch.randint(0, 2 ** 31 - 1, (2,), device=sub.device, dtype=torch.int32) if p > 0 else None
+        call("ab_dropout_add", ptr(sub), ptr(res), ptr(out), float(p), ptr(seed), sub.numel(), dt(sub), dt(out), stream_ptr())
+        ctx.p, ctx.seed, ctx.sub_dtype = p, seed, sub.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.p == 0:
+            return dout.to(ctx.sub_dtype), dout, None
+        dout = dout.contiguous()
+        dsub = torch.empty(dout.shape, dtype=ctx.sub_dtype, device=dout.device)
+        call("ab_dropout_add", ptr(dout), None, ptr(dsub), float(ctx.p), ptr(ctx.seed), dout.numel(), dt(dout), dt(dsub), stream_ptr())
+        return dsub, dout, None
+
+
+def dropout_add(sub, res, p: float, training: bool):
+    """nn.Dropout(p)(sub) + res of the block wrappers (core.py:836-837, 918-919) as one kernel."""
+    return _DropoutAdd.apply(sub, res, float(p) if training else 0.0)
+
+
 def layer_norm(x, weight, bias, eps, out_dtype=None):
     """nn.LayerNorm over the last dim (core.py:694-695, 887-888) through the sm_100a kernel."""
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype if out_dtype is not None else x.dtype)

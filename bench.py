@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2_1p5b", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=8, help="sequences per GPU per step")
-    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--dropout", type=float, default=0.1, help="hidden_dropout_prob (reference default 0.1; parity tests use 0)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-sample-tokens", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,9 +281,16 @@ def main():
     scan_bytes = tokens_per_step * (14 * 16 * H + 3 * H) * es           # fwd+bwd algorithmic bytes
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    traffic = None
+    try:        # mean dram__bytes_read+write per launch of the one `ncu --set full` capture summarised under profiles/
+        if args.workload == "c2_1p5b" and args.batch == 8 and world == 1:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1e_gemm_traffic.json")))["mean_dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roofline = {"kernel": "grouped_gemm_kernel<NT|NN|TN> (tcgen05 expert GEMM: 2 fwd + 2 dgrad + 2 wgrad launches per step)",
                 "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_src + ", sustained bf16",
+                "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "traffic_note": "bytes per launch, profiles/r1e_gemm_ncu_summary.md; algorithmic bytes per launch ~ 0.3-0.55 GB", "peak_source": pk_src + ", sustained bf16",
                 "ms_per_step_in_kernel": gemm_ms, "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms,
                 "algorithmic_flops_per_step": gemm_flops, "kept_rows_per_step": kept_total / world}
     kernels = {"selective_scan_fwd+bwd": {"bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -222,6 +222,12 @@ int ab_layernorm_bwd(const void* dy, const void* x, const float* stats, const fl
                      float* dw, float* db, void* ws, size_t ws_bytes, int S, int Dm, int x_dtype, int dy_dtype,
                      cudaStream_t stream);
 
+/* output Dropout + residual add of the wrappers (core.py:836-837, 918-919): out = dropout_p(sub) + res.
+ * res may be NULL (then it is the dropout alone: used for the backward, dsub = dropout-mask(dout)).  The mask is
+ * a counter-based hash of (element index, seed[0..1]); seed is a device uint32[2], ignored when p == 0. */
+int ab_dropout_add(const void* sub, const void* res, void* out, float p, const uint32_t* seed, int64_t n, int sub_dtype,
+                   int out_dtype, cudaStream_t stream);
+
 /* ---- helpers ----------------------------------------------------------------------------------- */
 /* fp32 -> bf16 cast of n elements (weight shadows for the tensor-core path) */
 int ab_cast_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t stream);

@@ -327,3 +327,28 @@ def test_grouped_gemm_dropout_mask_consistent(p):
     g1 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=pre1, epi=_lib.EPI_DACT, act=0, out_dtype=torch.float32, drop_p=p, drop_seed=seed)
     assert torch.equal((g1[:total] != 0) | (g0[:total] == 0), keep | (g0[:total] == 0))
     assert rel_err(g1[:total][keep], (g0[:total] / (1 - p))[keep]) < 1e-5
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1])
+@pytest.mark.parametrize("sub_dtype", [torch.float32, torch.bfloat16])
+def test_dropout_add(p, sub_dtype):
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    sub = torch.randn(257, 64, generator=g).to(dev(), sub_dtype).requires_grad_(True)
+    res = torch.randn(257, 64, generator=g).to(dev()).requires_grad_(True)
+    torch.manual_seed(11)
+    out = ops.dropout_add(sub, res, p, True)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    d = (out - res).detach()
+    keep = d != 0
+    if p == 0:
+        assert rel_err(out, sub.float() + res) < (1e-6 if sub_dtype == torch.float32 else 1e-2)
+        assert torch.equal(res.grad, dout) and rel_err(sub.grad.float(), dout) < 1e-2
+        return
+    frac = 1 - keep.float().mean().item()
+    assert abs(frac - p) < 0.02
+    assert rel_err(d[keep], (sub.detach().float() / (1 - p))[keep]) < 1e-2
+    assert torch.equal(res.grad, dout)
+    assert rel_err(sub.grad.float()[keep], (dout / (1 - p))[keep]) < 1e-2 and float(sub.grad.float()[~keep].abs().max()) == 0.0
+    assert torch.equal(ops.dropout_add(sub, res, p, False), sub.float() + res) or sub_dtype == torch.bfloat16
