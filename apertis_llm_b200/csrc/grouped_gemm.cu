@@ -44,7 +44,7 @@ struct GemmParams {
     const float* bias;
     const void* aux;
     const uint32_t* drop_seed;   // device [2]: seed of the expert-internal Dropout mask (core.py:439); NULL = no dropout
-    uint32_t drop_thresh;        // drop when hash < thresh (= p * 2^32)
+    uint32_t drop_thresh;        // drop when the 16-bit uniform < thresh (= p * 65536)
     float drop_scale;            // 1 / (1 - p)
     void* c;
     void* c2;
@@ -82,16 +82,21 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     return s * fmaf(x, 1.f - s, 1.f);
 }
 
-// Dropout keep-mask of element (row, col) of the expert hidden activation: counter-based hash of the element index and
-// a 64-bit seed, so the backward regenerates exactly the forward's mask without storing it.
-__device__ __forceinline__ bool drop_keep(uint32_t s0, uint32_t s1, uint32_t row, uint32_t col, uint32_t thresh) {
-    uint32_t x = (row * 0x9E3779B1u) ^ (col * 0x85EBCA77u) ^ s0;
-    x ^= x >> 16; x *= 0x7FEB352Du;
-    x ^= x >> 15; x *= 0x846CA68Bu;
-    x ^= x >> 16; x += s1;
-    x ^= x >> 15; x *= 0x2C1B3C6Du;
-    x ^= x >> 12;
-    return x >= thresh;
+// Dropout keep-mask of the expert hidden activation: counter-based hash of the element index and a 64-bit seed, so the
+// backward regenerates exactly the forward's mask without storing it.  One hash serves 4 consecutive columns (four
+// 16-bit uniforms, drop when < p * 65536), ~6 integer ops per element.
+__device__ __forceinline__ void drop_mask4(uint32_t s0, uint32_t s1, uint32_t row, uint32_t col, uint32_t n_cols, uint32_t thresh16,
+                                           bool (&keep)[4]) {
+    uint32_t x = ((row * n_cols + col) >> 2) * 0x9E3779B1u + s0;
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    uint32_t y = x * 0x27D4EB2Fu + s1;
+    y ^= y >> 15;
+    keep[0] = (x & 0xffffu) >= thresh16;
+    keep[1] = (x >> 16) >= thresh16;
+    keep[2] = (y & 0xffffu) >= thresh16;
+    keep[3] = (y >> 16) >= thresh16;
 }
 
 // ---- descriptors ------------------------------------------------------------------------------
@@ -202,7 +207,12 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
                     const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
                     const uint32_t grow = (uint32_t)(m_tile * BM + quarter * 32 + lane);
 #pragma unroll
-                    for (int i = 0; i < U; ++i) f[i] = drop_keep(s0, s1, grow, (uint32_t)(ncol + i), p.drop_thresh) ? f[i] * p.drop_scale : 0.f;
+                    for (int i = 0; i < U; i += 4) {
+                        bool keep[4];
+                        drop_mask4(s0, s1, grow, (uint32_t)(ncol + i), (uint32_t)N, p.drop_thresh, keep);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) f[i + u] = keep[u] ? f[i + u] * p.drop_scale : 0.f;
+                    }
                 }
             } else if (p.epi == AB_EPI_DACT) {
                 // saved pre-activation tile: coalesced 16-byte loads -> staging -> each thread reads its own row
@@ -232,7 +242,12 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
                     const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
                     const uint32_t grow = (uint32_t)(m_tile * BM + quarter * 32 + lane);
 #pragma unroll
-                    for (int i = 0; i < U; ++i) f[i] = drop_keep(s0, s1, grow, (uint32_t)(ncol + i), p.drop_thresh) ? f[i] * p.drop_scale : 0.f;
+                    for (int i = 0; i < U; i += 4) {
+                        bool keep[4];
+                        drop_mask4(s0, s1, grow, (uint32_t)(ncol + i), (uint32_t)N, p.drop_thresh, keep);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) f[i + u] = keep[u] ? f[i + u] * p.drop_scale : 0.f;
+                    }
                 }
             }
         }
@@ -462,7 +477,7 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     p.tile_expert = tile_expert; p.n_rows = n_rows; p.bias = bias; p.aux = aux; p.c = c; p.c2 = c2;
     if (drop_p > 0.f) {
         p.drop_seed = drop_seed;
-        p.drop_thresh = (uint32_t)((double)drop_p * 4294967296.0);
+        p.drop_thresh = (uint32_t)((double)drop_p * 65536.0 + 0.5);
         p.drop_scale = 1.0f / (1.0f - drop_p);
     }
     AB_REQUIRE(((uintptr_t)c % 16) == 0 && (c2 == nullptr || ((uintptr_t)c2 % 16) == 0) && (aux == nullptr || ((uintptr_t)aux % 16) == 0),

@@ -9,8 +9,6 @@ namespace {
 
 constexpr int PLAN_THREADS = 1024;
 
-constexpr int TPT = 4;   // tokens per thread per sweep iteration
-
 // exclusive prefix of a small per-thread count over the CTA (thread order) + CTA total; two __syncthreads
 __device__ __forceinline__ int block_excl_scan(int cnt, int* warp_tot /*[32]*/, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -35,85 +33,127 @@ __device__ __forceinline__ int block_excl_scan(int cnt, int* warp_tot /*[32]*/, 
 }
 
 // One CTA per expert.  row_local[s,k] = position of the kept (token, slot) inside the expert's segment, -1 if dropped.
-// A thread owns TPT consecutive tokens per sweep iteration, so positions stay in token order.
+// Per slot: (A) the expert's candidates are compacted in token order into a shared-memory list (token id, weight bits)
+// while the top-byte histogram is built; (B) on overflow of the capacity the rem-th largest weight is radix-selected on
+// the list; (C) positions are assigned in list (= token) order.  If the candidates do not fit the list the slot falls
+// back to the same algorithm over global memory.
+constexpr int TPT = 8;   // consecutive tokens per thread per compaction sweep
+
+__device__ __forceinline__ void radix_select_bin(int* hist, int& need, int& sel_bin, int* s_sel_bin, int* s_need) {
+    if (threadIdx.x == 0) {
+        int nd = need, bin = 255;
+        for (; bin > 0; --bin) {
+            if (hist[bin] >= nd) break;
+            nd -= hist[bin];
+        }
+        *s_sel_bin = bin;
+        *s_need = nd;
+    }
+    __syncthreads();
+    sel_bin = *s_sel_bin;
+    need = *s_need;
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w,
                                                                   const int32_t* __restrict__ active, int cap,
                                                                   int32_t* __restrict__ counts, int32_t* __restrict__ row_local,
-                                                                  int S, int K) {
+                                                                  int S, int K, int list_cap) {
+    extern __shared__ uint2 s_list[];          // [list_cap] (token, weight bits) of the current slot's candidates
     __shared__ int hist[256];
     __shared__ int warp_tot[32];
-    __shared__ int s_sel_bin, s_need, s_ncand;
+    __shared__ int s_sel_bin, s_need;
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
     const bool is_active = active == nullptr || active[e] != 0;
-    const int span = blockDim.x * TPT;
     int kept_total = 0;
     for (int k = 0; k < K; ++k) {
-        // ---- candidates of this (slot, expert) group + histogram of the top byte in the same sweep
+        // ---- (A) compaction in token order + histogram of the top byte
         for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-        if (tid == 0) s_ncand = 0;
         __syncthreads();
-        int mine = 0;
-        for (int s = tid; s < S; s += blockDim.x) {
-            if (idx[(size_t)s * K + k] == e) {
-                ++mine;
-                atomicAdd(&hist[__float_as_uint(w[(size_t)s * K + k]) >> 24], 1);
+        int n_cand = 0;
+        const int span = blockDim.x * TPT;
+        for (int s0 = 0; s0 < S; s0 += span) {
+            const int sb = s0 + tid * TPT;
+            uint32_t wb[TPT];
+            bool c[TPT];
+            int mine = 0;
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                const int s = sb + t;
+                c[t] = s < S && idx[(size_t)s * K + k] == e;
+                wb[t] = c[t] ? __float_as_uint(w[(size_t)s * K + k]) : 0u;
+                mine += c[t];
             }
+            int tot;
+            int pos = n_cand + block_excl_scan(mine, warp_tot, tot);
+#pragma unroll
+            for (int t = 0; t < TPT; ++t) {
+                if (c[t]) {
+                    if (pos < list_cap) s_list[pos] = make_uint2((uint32_t)(sb + t), wb[t]);
+                    atomicAdd(&hist[wb[t] >> 24], 1);
+                    ++pos;
+                }
+            }
+            n_cand += tot;
         }
-        mine = (int)ab_warp_sum((float)mine);      // exact: counts < 2^24
-        if ((tid & 31) == 0 && mine) atomicAdd(&s_ncand, mine);
         __syncthreads();
-        const int n_cand = s_ncand;
+        const bool in_smem = n_cand <= list_cap;
         const int rem = cap - kept_total;
         int mode = 0;                       // 0 none, 1 all, 2 select the `rem` largest
         if (is_active && n_cand > 0 && rem > 0) mode = n_cand <= rem ? 1 : 2;
         uint32_t tau = 0;
         int n_eq_take = 0;
         if (mode == 2) {
-            // radix select of the rem-th largest weight (positive floats order like their bit patterns)
+            // ---- (B) radix select of the rem-th largest weight (positive floats order like their bit patterns)
             uint32_t prefix = 0, mask = 0;
-            int need = rem;
+            int need = rem, bin;
             for (int pass = 3; pass >= 0; --pass) {
                 if (pass != 3) {
                     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
                     __syncthreads();
-                    for (int s = tid; s < S; s += blockDim.x) {
-                        if (idx[(size_t)s * K + k] == e) {
-                            const uint32_t b = __float_as_uint(w[(size_t)s * K + k]);
+                    if (in_smem) {
+                        for (int i = tid; i < n_cand; i += blockDim.x) {
+                            const uint32_t b = s_list[i].y;
                             if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
+                        }
+                    } else {
+                        for (int s = tid; s < S; s += blockDim.x) {
+                            if (idx[(size_t)s * K + k] == e) {
+                                const uint32_t b = __float_as_uint(w[(size_t)s * K + k]);
+                                if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
+                            }
                         }
                     }
                     __syncthreads();
                 }
-                if (tid == 0) {
-                    int nd = need, bin = 255;
-                    for (; bin > 0; --bin) {
-                        if (hist[bin] >= nd) break;
-                        nd -= hist[bin];
-                    }
-                    s_sel_bin = bin;
-                    s_need = nd;
-                }
-                __syncthreads();
-                prefix |= (uint32_t)s_sel_bin << (8 * pass);
+                radix_select_bin(hist, need, bin, &s_sel_bin, &s_need);
+                prefix |= (uint32_t)bin << (8 * pass);
                 mask |= 0xffu << (8 * pass);
-                need = s_need;
-                __syncthreads();
             }
             tau = prefix;
             n_eq_take = need;
         }
-        // ---- positions in token order
+        // ---- (C) positions in token order
         int run_eq = 0, run_kept = 0;
-        for (int s0 = 0; s0 < S; s0 += span) {
-            const int sb = s0 + tid * TPT;
+        const int n_items = in_smem ? n_cand : S;
+        for (int s0 = 0; s0 < n_items; s0 += span) {
+            const int ib = s0 + tid * TPT;
             bool c[TPT], gt[TPT], eq[TPT];
+            int tokv[TPT];
             int n_eq = 0;
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
-                const int s = sb + t;
-                c[t] = s < S && idx[(size_t)s * K + k] == e;
-                const uint32_t b = c[t] ? __float_as_uint(w[(size_t)s * K + k]) : 0u;
+                const int i = ib + t;
+                uint32_t b = 0u;
+                if (in_smem) {
+                    c[t] = i < n_cand;
+                    if (c[t]) { const uint2 it = s_list[i]; tokv[t] = (int)it.x; b = it.y; } else tokv[t] = 0;
+                } else {
+                    c[t] = i < S && idx[(size_t)i * K + k] == e;
+                    tokv[t] = i;
+                    if (c[t]) b = __float_as_uint(w[(size_t)i * K + k]);
+                }
                 gt[t] = c[t] && (mode == 1 || (mode == 2 && b > tau));
                 eq[t] = c[t] && mode == 2 && b == tau;
                 n_eq += eq[t];
@@ -132,7 +172,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t*
             int pos = kept_total + run_kept + block_excl_scan(n_kept, warp_tot, tot_kept);
 #pragma unroll
             for (int t = 0; t < TPT; ++t) {
-                if (c[t]) row_local[(size_t)(sb + t) * K + k] = kept[t] ? pos : -1;
+                if (c[t]) row_local[(size_t)tokv[t] * K + k] = kept[t] ? pos : -1;
                 pos += kept[t];
             }
             run_eq += tot_eq;
@@ -467,7 +507,12 @@ extern "C" int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* ac
     int32_t* row_local = (int32_t*)ws;
     AB_CHECK_CUDA(cudaMemsetAsync(tok_of_row, 0xFF, (size_t)max_rows * sizeof(int32_t), stream));
     AB_CHECK_CUDA(cudaMemsetAsync(slot_of_row, 0xFF, (size_t)max_rows * sizeof(int32_t), stream));
-    plan_count_kernel<<<E, PLAN_THREADS, 0, stream>>>(idx, w, active, cap, counts, row_local, S, K);
+    // candidate list in shared memory: as many entries as fit (8 B each), at most S
+    int list_cap = (200 * 1024) / 8;
+    if (list_cap > S) list_cap = S;
+    const size_t plan_smem = (size_t)list_cap * sizeof(uint2);
+    AB_CHECK_CUDA(cudaFuncSetAttribute(plan_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
+    plan_count_kernel<<<E, PLAN_THREADS, plan_smem, stream>>>(idx, w, active, cap, counts, row_local, S, K, list_cap);
     AB_LAUNCH_CHECK();
     const int64_t want = ab_ceil_div((int64_t)S * K, 256);
     const int grid = (int)(want < ab_num_sms() * 4 ? want : ab_num_sms() * 4);

@@ -17,9 +17,10 @@ __device__ __forceinline__ void row_load(const T* row, int i, float* f) {   // v
     ab_vec16<T>::unpack(__ldg(reinterpret_cast<const uint4*>(row) + i), f);
 }
 
-// softmax / top-K / weights on lanes (lane e < E holds logit e).  Returns gate in g.
-__device__ __forceinline__ void select_topk(float logit, int lane, int E, int K, float& g, float& lse, int* sel_idx,
-                                            float* sel_p) {
+// softmax / top-K / weights on lanes (lane e < E holds logit e).  Returns the gate in g; lane k < K ends up holding
+// slot k's expert id and probability (my_idx, my_p) -- no per-thread arrays, so nothing spills to local memory.
+__device__ __forceinline__ void select_topk(float logit, int lane, int E, int K, float& g, float& lse, int& my_idx, float& my_p,
+                                            float& den, unsigned& sel_mask) {
     const float lv = lane < E ? logit : -INFINITY;
     const float m = ab_warp_max(lv);
     const float ex = lane < E ? expf(lv - m) : 0.f;
@@ -27,29 +28,26 @@ __device__ __forceinline__ void select_topk(float logit, int lane, int E, int K,
     g = ex / sum;
     lse = m + logf(sum);
     float cand = lane < E ? g : -INFINITY;
+    my_idx = 0; my_p = 0.f; den = 0.f; sel_mask = 0u;
     for (int k = 0; k < K; ++k) {
         const float best = ab_warp_max(cand);
         const unsigned ball = __ballot_sync(0xffffffffu, cand == best);
         const int win = __ffs(ball) - 1;               // lowest expert id among equals
-        sel_idx[k] = win;
-        sel_p[k] = best;
+        if (lane == k) { my_idx = win; my_p = best; }
+        den += best;                                   // summed in slot order like torch.sum over K
+        sel_mask |= 1u << win;
         if (lane == win) cand = -INFINITY;
     }
+    den += 1e-6f;
 }
 
-__device__ __forceinline__ void write_selection(int s, int lane, int E, int K, float g, float lse, const int* sel_idx,
-                                                const float* sel_p, float* gates, int32_t* idx, float* probs, float* w,
-                                                float* lse_out) {
+__device__ __forceinline__ void write_selection(int s, int lane, int E, int K, float g, float lse, int my_idx, float my_p, float den,
+                                                float* gates, int32_t* idx, float* probs, float* w, float* lse_out) {
     if (lane < E) gates[(size_t)s * E + lane] = g;
-    float den = 0.f;
-    for (int k = 0; k < K; ++k) den += sel_p[k];       // (sum probs) + 1e-6, summed in slot order like torch.sum over K
-    den += 1e-6f;
     if (lane < K) {
-        int myi = 0; float myp = 0.f;
-        for (int k = 0; k < K; ++k) if (k == lane) { myi = sel_idx[k]; myp = sel_p[k]; }
-        idx[(size_t)s * K + lane] = myi;
-        probs[(size_t)s * K + lane] = myp;
-        w[(size_t)s * K + lane] = myp / den;
+        idx[(size_t)s * K + lane] = my_idx;
+        probs[(size_t)s * K + lane] = my_p;
+        w[(size_t)s * K + lane] = my_p / den;
     }
     if (lane == 0) lse_out[s] = lse;
 }
@@ -100,13 +98,17 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
             float f[V];
             row_load<T>(row, i, f);
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float c = f[v] - mean;
-                var = fmaf(c, c, var);
-                const int d = i * V + v;
+            for (int v = 0; v < V; ++v) { f[v] -= mean; var = fmaf(f[v], f[v], var); }
 #pragma unroll
-                for (int e = 0; e < EM; ++e)
-                    if (e < E) dot[e] = fmaf(c, G[(size_t)e * Dm + d], dot[e]);
+            for (int e = 0; e < EM; ++e) {
+                if (e < E) {
+#pragma unroll
+                    for (int v4 = 0; v4 < V; v4 += 4) {
+                        const float4 gq = *reinterpret_cast<const float4*>(G + (size_t)e * Dm + i * V + v4);
+                        dot[e] = fmaf(f[v4], gq.x, dot[e]); dot[e] = fmaf(f[v4 + 1], gq.y, dot[e]);
+                        dot[e] = fmaf(f[v4 + 2], gq.z, dot[e]); dot[e] = fmaf(f[v4 + 3], gq.w, dot[e]);
+                    }
+                }
             }
         }
         var = ab_warp_sum(var) / (float)Dm;
@@ -128,14 +130,14 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
             if (logits) logits[(size_t)s * E + lane] = mylogit;
         }
         if (lane == 0) { stats[2 * (size_t)s] = mean; stats[2 * (size_t)s + 1] = rstd; }
-        float g, lse;
-        int sel_idx[MAX_K];
-        float sel_p[MAX_K];
-        select_topk(mylogit, lane, E, K, g, lse, sel_idx, sel_p);
-        write_selection(s, lane, E, K, g, lse, sel_idx, sel_p, gates, idx, probs, w, lse_out);
+        float g, lse, my_p, den;
+        int my_idx;
+        unsigned sel_mask;
+        select_topk(mylogit, lane, E, K, g, lse, my_idx, my_p, den, sel_mask);
+        write_selection(s, lane, E, K, g, lse, my_idx, my_p, den, gates, idx, probs, w, lse_out);
         if (lane < E) {
             a_g += g;
-            for (int k = 0; k < K; ++k) a_cnt += (sel_idx[k] == lane) ? 1.f : 0.f;
+            a_cnt += (sel_mask >> lane) & 1u ? 1.f : 0.f;
         }
         if (lane == 0) a_l2 = fmaf(lse, lse, a_l2);
     }
@@ -168,11 +170,11 @@ __global__ void __launch_bounds__(WARPS * 32) topk_from_logits_kernel(const floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int s = blockIdx.x * WARPS + warp; s < S; s += gridDim.x * WARPS) {
         const float l = lane < E ? logits[(size_t)s * E + lane] : 0.f;
-        float g, lse;
-        int sel_idx[MAX_K];
-        float sel_p[MAX_K];
-        select_topk(l, lane, E, K, g, lse, sel_idx, sel_p);
-        write_selection(s, lane, E, K, g, lse, sel_idx, sel_p, gates, idx, probs, w, lse_out);
+        float g, lse, my_p, den;
+        int my_idx;
+        unsigned sel_mask;
+        select_topk(l, lane, E, K, g, lse, my_idx, my_p, den, sel_mask);
+        write_selection(s, lane, E, K, g, lse, my_idx, my_p, den, gates, idx, probs, w, lse_out);
     }
 }
 
@@ -216,26 +218,32 @@ __global__ void __launch_bounds__(WARPS * 32) router_bwd_kernel(const T* __restr
     const int nvec = Dm / V;
     float a_db = 0.f, a_dn = 0.f;
     for (int s = blockIdx.x * WARPS + warp; s < S; s += gridDim.x * WARPS) {
-        // ---- d weights -> d probs
-        float dwk[MAX_K], pk[MAX_K];
-        int ik[MAX_K], rk[MAX_K];
-        float den = 0.f, dot = 0.f;
-        for (int k = 0; k < K; ++k) {
-            rk[k] = row_of[(size_t)s * K + k];
-            ik[k] = idx[(size_t)s * K + k];
-            pk[k] = probs[(size_t)s * K + k];
-            dwk[k] = rk[k] >= 0 ? dw_row[rk[k]] : 0.f;
-            den += pk[k];
-            dot = fmaf(dwk[k], pk[k], dot);
+        // ---- d weights -> d probs (lane k < K holds slot k)
+        int my_r = -1, my_i = 0;
+        float my_dw = 0.f, my_pk = 0.f;
+        if (lane < K) {
+            my_r = row_of[(size_t)s * K + lane];
+            my_i = idx[(size_t)s * K + lane];
+            my_pk = probs[(size_t)s * K + lane];
+            my_dw = my_r >= 0 ? dw_row[my_r] : 0.f;
         }
+        float den = 0.f;
+        for (int k = 0; k < K; ++k) den += __shfl_sync(0xffffffffu, my_pk, k);    // slot order, as in the forward
         den += 1e-6f;
+        const float dot = ab_warp_sum(my_dw * my_pk);
         const float inv = 1.f / den;
+        const float my_dp = my_dw * inv - dot * inv * inv;       // d prob of slot `lane`
         float dgate = 0.f, g = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const int ik = __shfl_sync(0xffffffffu, my_i, k);
+            const float dpk = __shfl_sync(0xffffffffu, my_dp, k);
+            if (lane == ik) dgate += dpk;
+        }
         if (lane < E) {
             g = gates[(size_t)s * E + lane];
-            for (int k = 0; k < K; ++k)
-                if (ik[k] == lane) dgate += dwk[k] * inv - dot * inv * inv;
             dgate = fmaf(g_lb, f[lane], dgate);
+        } else {
+            dgate = 0.f;
         }
         const float gd = ab_warp_sum(g * dgate);
         float dl = 0.f;
@@ -257,24 +265,43 @@ __global__ void __launch_bounds__(WARPS * 32) router_bwd_kernel(const T* __restr
         float dle[EM];
 #pragma unroll
         for (int e = 0; e < EM; ++e) dle[e] = __shfl_sync(0xffffffffu, dl, e);
+        int rk[MAX_K];                                   // rows of the K slots, broadcast once (the vector loop below diverges)
+#pragma unroll
+        for (int k = 0; k < MAX_K; ++k) { const int r = __shfl_sync(0xffffffffu, my_r, k); rk[k] = k < K ? r : -1; }
         const T* row = x + (size_t)s * Dm;
         T* orow = dx + (size_t)s * Dm;
         for (int i = lane; i < nvec; i += 32) {
             float fx[V], o[V];
             row_load<T>(row, i, fx);
+            float dxn[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int d = i * V + v;
-                float dxn = 0.f;
+            for (int v = 0; v < V; ++v) dxn[v] = 0.f;
 #pragma unroll
-                for (int e = 0; e < EM; ++e)
-                    if (e < E) dxn = fmaf(dle[e], Wsm[(size_t)e * Dm + d], dxn);
-                const float xh = (fx[v] - mean) * rstd;
-                o[v] = rstd * (dxn * gam[d] - m1 - xh * m2);
+            for (int e = 0; e < EM; ++e) {
+                if (e < E) {
+#pragma unroll
+                    for (int v4 = 0; v4 < V; v4 += 4) {
+                        const float4 wq = *reinterpret_cast<const float4*>(Wsm + (size_t)e * Dm + i * V + v4);
+                        dxn[v4] = fmaf(dle[e], wq.x, dxn[v4]); dxn[v4 + 1] = fmaf(dle[e], wq.y, dxn[v4 + 1]);
+                        dxn[v4 + 2] = fmaf(dle[e], wq.z, dxn[v4 + 2]); dxn[v4 + 3] = fmaf(dle[e], wq.w, dxn[v4 + 3]);
+                    }
+                }
             }
-            for (int k = 0; k < K; ++k) {
-                if (rk[k] >= 0) {
-                    const float* er = dxrow + (size_t)rk[k] * Dm + i * V;
+#pragma unroll
+            for (int v4 = 0; v4 < V; v4 += 4) {
+                const float4 gq = *reinterpret_cast<const float4*>(gam + i * V + v4);
+                const float gg[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float xh = (fx[v4 + u] - mean) * rstd;
+                    o[v4 + u] = rstd * (dxn[v4 + u] * gg[u] - m1 - xh * m2);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MAX_K; ++k) {
+                const int rkk = rk[k];
+                if (rkk >= 0) {
+                    const float* er = dxrow + (size_t)rkk * Dm + i * V;
 #pragma unroll
                     for (int v4 = 0; v4 < V; v4 += 4) {
                         const float4 q = __ldg(reinterpret_cast<const float4*>(er + v4));
@@ -296,7 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32) router_bwd_kernel(const T* __restr
 }
 
 // kernel C: Q[e,d] = sum_s dlogits[s,e] * xhat[s,d]; thread per column d, token blocks of QB tokens
-constexpr int qb_for(int em) { return 4096 / em; }     // tokens per partial block (smem [QB][EM] floats)
+constexpr int qb_for(int em) { return 2048 / em; }     // tokens per partial block (smem [QB][EM] floats)
 int em_for(int E) { return E <= 8 ? 8 : (E <= 16 ? 16 : 32); }
 template <typename T, int EM>
 __global__ void __launch_bounds__(256) router_q_kernel(const T* __restrict__ x, const float* __restrict__ stats,

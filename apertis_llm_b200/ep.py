@@ -132,6 +132,7 @@ class _MoEExpertsEP(torch.autograd.Function):
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
         ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt, drop_p=drop_p)
         ctx.drop_seed = drop_seed
+        ctx.shadows = None if precise else (w1, w2)
         ctx.group = group
         ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
         ctx.rplan = rplan
@@ -170,7 +171,7 @@ class _MoEExpertsEP(torch.autograd.Function):
             w1r = ops._split_rows(W1.view(El * I, Dm), 1, None, El, I)
             dxnr = ops.grouped_gemm("nn", ops._split_cols(dhpre, 0), w1r, rplan, Dm, 3 * I, El, out_dtype=torch.float32)
         else:
-            w1b, w2b = ops._cast_bf16(W1), ops._cast_bf16(W2)
+            w1b, w2b = ctx.shadows
             dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             dW2 = ops.grouped_gemm_tn(dyr, h, lseg, Dm, I, El, nsrc=W, src_stride=stride)

@@ -384,6 +384,7 @@ class _MoEExperts(torch.autograd.Function):
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
         ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt, drop_p=drop_p)
         ctx.drop_seed = drop_seed
+        ctx.shadows = None if precise else (w1, w2)        # bf16 weight shadows cast in this forward, reused by the backward
         ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
         ctx.save_for_backward(x2, rn_w, rn_b, Wr, br, ln_w, W1, W2, noise if use_noise else None,
                               r["stats"], r["gates"], r["idx"], r["probs"], r["lse"], r["lclean"], r["w"], aux,
@@ -418,7 +419,7 @@ class _MoEExperts(torch.autograd.Function):
             w1r = _split_rows(W1.view(E * I, Dm), 1, None, E, I)                  # [E, 3*I, Dm]
             dxn = grouped_gemm("nn", _split_cols(dhpre, 0), w1r, plan, Dm, 3 * I, E, out_dtype=torch.float32)
         else:
-            w1b, w2b = _cast_bf16(W1), _cast_bf16(W2)
+            w1b, w2b = ctx.shadows
             dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                  drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             dW2 = grouped_gemm_tn(dy, h, seg, Dm, I, E)

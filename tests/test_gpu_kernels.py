@@ -154,7 +154,9 @@ def test_topk_from_logits_bit_exact_with_ties():
 
 @pytest.mark.parametrize("S,E,K,cap,ties,inactive", [(96, 8, 2, 15, False, None), (4096, 8, 2, 640, False, None),
                                                       (1000, 4, 2, 300, True, None), (777, 10, 3, 200, False, [3]),
-                                                      (512, 8, 2, 512, False, None), (300, 8, 2, 1, True, [0, 5])])
+                                                      (512, 8, 2, 512, False, None), (300, 8, 2, 1, True, [0, 5]),
+                                                      (60000, 2, 2, 20000, False, None),      # candidates overflow the smem list
+                                                      (32768, 8, 2, 5120, True, None)])
 def test_plan_bit_exact(S, E, K, cap, ties, inactive):
     from apertis_llm_b200 import ops
     rng = np.random.default_rng(S + cap)
