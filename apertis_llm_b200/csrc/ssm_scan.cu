@@ -206,12 +206,28 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, flo
 template <typename T>
 __device__ __forceinline__ void stage_delta(const ScanParams& p, float* sdel, int b, int row0, int nrows, int h_lo, int nh) {
     const T* dl = reinterpret_cast<const T*>(p.dlog);
-    for (int i = threadIdx.x; i < nrows * nh; i += blockDim.x) {
-        const int r = i / nh, hh = i % nh;
+    // thread -> (row, head) without integer division: nh <= blockDim in every tiling
+    const int hh = threadIdx.x % nh, r0 = threadIdx.x / nh, rstep = blockDim.x / nh;
+    if (r0 >= rstep) return;                      // the last partial group of threads sits out
+    const bool head_ok = h_lo + hh < p.H;
+    for (int r = r0; r < nrows; r += rstep) {
         const int row = row0 + r;
         float d = 0.f;
-        if (row < p.L && h_lo + hh < p.H) d = ab_softplus(ab_to_float(dl[((size_t)b * p.L + row) * p.H + h_lo + hh]));
-        sdel[i] = d;
+        if (row < p.L && head_ok) d = ab_softplus_fast(ab_to_float(dl[((size_t)b * p.L + row) * p.H + h_lo + hh]));
+        sdel[r * nh + hh] = d;
+    }
+}
+
+// sigmoid for the SiLU gate: f32 activations use ex2 + rcp; bf16 activations use the single-MUFU tanh.approx form
+// (relative error ~5e-4, an order below bf16 resolution)
+template <typename T>
+__device__ __forceinline__ float gate_sigmoid(float x) {
+    if constexpr (sizeof(T) == 2) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        return fmaf(0.5f, t, 0.5f);
+    } else {
+        return ab_sigmoid(x);
     }
 }
 
@@ -251,7 +267,7 @@ __device__ __forceinline__ void ldg_vec(const T* p, float* f) {
 // smem: [tiles: nT x T x Cs of T] [sdel: (T+1) x nh] [sP: n_s x Cs] [sS: n_s x Cs] [hT: Cs] [bar] [tile id]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
+__global__ void __launch_bounds__(256, 3) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
                                                        const __grid_constant__ CUtensorMap tm_b,
                                                        const __grid_constant__ CUtensorMap tm_c,
                                                        const __grid_constant__ CUtensorMap tm_z, const ScanParams p) {
@@ -316,8 +332,8 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
     __syncthreads();            // sdel visible
     ab_mbar_wait(bar, 0);       // TMA tiles landed
 
-    // ---- sweep 1: per-run decay factors and aggregates
-    float a[TS][V];
+    // ---- sweep 1: per-run aggregates (the decay factors are recomputed in sweep 2: one MUFU is cheaper than
+    //      holding TS x V registers across the hand-shake with the scanner)
     {
         float P[V], S[V];
 #pragma unroll
@@ -330,9 +346,9 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
             lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                a[t][v] = ab_ex2(A2[v] * d);
-                P[v] *= a[t][v];
-                S[v] = fmaf(a[t][v], S[v], bv[v]);
+                const float at = ab_ex2(A2[v] * d);
+                P[v] *= at;
+                S[v] = fmaf(at, S[v], bv[v]);
             }
         }
 #pragma unroll
@@ -344,6 +360,7 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
     const size_t tile_lin = (size_t)chain * p.nchunks + j;
     for (int c = tid; c < Cs; c += blockDim.x) {
         float Pt = 1.f, St = 0.f;
+#pragma unroll 4
         for (int i = 0; i < n_s; ++i) { St = fmaf(St, sP[i * Cs + c], sS[i * Cs + c]); Pt *= sP[i * Cs + c]; }
         float hin;
         if (MODE == MODE_AGG) {
@@ -358,7 +375,15 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
             ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
             hin = wait_incoming(p, tile_lin, c);        // hstart / h_last are written by the scanner
         }
-        hT[c] = hin;
+        // state entering every run of this channel, in place of the run aggregates S (one serial pass by the channel's
+        // thread instead of an O(n_s) prefix loop in every thread)
+        float hr = hin;
+#pragma unroll 4
+        for (int i = 0; i < n_s; ++i) {
+            const float pi = sP[i * Cs + c], si = sS[i * Cs + c];
+            sS[i * Cs + c] = hr;
+            hr = fmaf(pi, hr, si);
+        }
     }
     if (MODE == MODE_AGG) return;
     __syncthreads();
@@ -366,11 +391,7 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
     // ---- state entering this thread's run, then sweep 2
     float h[V], Dv[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) { h[v] = hT[cl + v]; Dv[v] = __ldg(p.Dp + c0 + cl + v); }
-    for (int i = 0; i < i_run; ++i) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) h[v] = fmaf(h[v], sP[i * Cs + cl + v], sS[i * Cs + cl + v]);
-    }
+    for (int v = 0; v < V; ++v) { h[v] = sS[i_run * Cs + cl + v]; Dv[v] = __ldg(p.Dp + c0 + cl + v); }
     T* yo = reinterpret_cast<T*>(p.y);
     T* yso = reinterpret_cast<T*>(p.y_ssm);
 #pragma unroll
@@ -382,11 +403,12 @@ __global__ void __launch_bounds__(256) scan_fwd_kernel(const __grid_constant__ C
         lds_vec<T, V>(s_c + (size_t)r * Cs + cl, cvv);
         lds_vec<T, V>(s_xa + (size_t)r * Cs + cl, xv);
         lds_vec<T, V>(s_z + (size_t)r * Cs + cl, zv);
+        const float d = sdel[r * nh + hh];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            h[v] = fmaf(a[t][v], h[v], bv[v]);
+            h[v] = fmaf(ab_ex2(A2[v] * d), h[v], bv[v]);
             os[v] = cvv[v] * h[v];
-            o[v] = fmaf(Dv[v], xv[v], os[v]) * (zv[v] * ab_sigmoid(zv[v]));
+            o[v] = fmaf(Dv[v], xv[v], os[v]) * (zv[v] * gate_sigmoid<T>(zv[v]));
         }
         if (row < p.L) {
             const size_t off = ((size_t)b * p.L + row) * p.Di + c0 + cl;
@@ -562,7 +584,7 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
             float o_dxa[V], o_dc[V], o_dz[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float sg = ab_sigmoid(zv[v]);
+                const float sg = gate_sigmoid<T>(zv[v]);
                 const float gate = zv[v] * sg;
                 const float dyv = dov[v] * gate;           // grad of (y_ssm + D*xa)
                 const float dtot = dyv + dys[v];           // grad of y_ssm
@@ -611,6 +633,7 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
     const size_t tile_lin = (size_t)chain * p.nchunks + j;
     for (int c = tid; c < Cs; c += blockDim.x) {
         float Pt = 1.f, St = 0.f;
+#pragma unroll 4
         for (int i = n_s - 1; i >= 0; --i) { St = fmaf(St, sP[i * Cs + c], sS[i * Cs + c]); Pt *= sP[i * Cs + c]; }
         float gin;
         if (MODE == MODE_AGG) {
