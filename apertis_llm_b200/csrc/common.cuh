@@ -232,3 +232,7 @@ __device__ __forceinline__ unsigned long long ab_ld_relaxed_u64(const unsigned l
 __device__ __forceinline__ void ab_st_relaxed_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// same store without the compiler barrier: for self-validating words whose order against other accesses is irrelevant
+__device__ __forceinline__ void ab_st_relaxed_u64_unordered(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+}

@@ -40,7 +40,7 @@ struct ScanTiling {
 
 int make_tiling(int L, int Di, int dtype, ScanTiling& t) {
     t.esize = dtype == AB_F32 ? 4 : 2;
-    t.V_f = 16 / t.esize;
+    t.V_f = getenv("AB_SCAN_VF8") ? 16 / t.esize : 4;
     t.V_b = 4;
     const int unit = t.V_f > t.V_b ? t.V_f : t.V_b;
     int Cs = 0;
@@ -107,6 +107,25 @@ __device__ __forceinline__ int ring_depth(size_t avail_bytes, int Cs) {
 
 __device__ __forceinline__ bool word_valid(unsigned long long w, uint32_t epoch) { return (uint32_t)(w >> 34) == epoch; }
 
+#ifdef AB_SCAN_TRACE
+// debug build only (make TRACE=1): per-tile phase timestamps of the forward kernel, read back by tools/scan_trace.py
+constexpr int TRACE_SLOTS = 8, TRACE_TILES = 16384;
+__device__ unsigned long long g_scan_trace[TRACE_TILES * TRACE_SLOTS];
+__device__ __forceinline__ void trace_mark(size_t tile_lin, int slot) {
+    if (threadIdx.x == 0 && tile_lin < TRACE_TILES) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_scan_trace[tile_lin * TRACE_SLOTS + slot] = t;
+    }
+}
+#define TRACE_MARK(tl, s) trace_mark(tl, s)
+constexpr int STRACE_ROUNDS = 2048;
+__device__ unsigned long long g_scanner_trace[64 * STRACE_ROUNDS * 4];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#else
+#define TRACE_MARK(tl, s)
+#endif
+
 // Tile side: spin until the scanner has published the state entering this tile.
 __device__ __forceinline__ float wait_incoming(const ScanParams& p, size_t tile_lin, int c) {
     const unsigned long long* w = p.inclw + tile_lin * p.Cs + c;
@@ -138,9 +157,19 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, flo
         // ring[k][thread] in shared memory, filled by cp.async (no registers held while the loads are in flight)
         uint4* myring = ring + c;
         const int pitch = Cs;
+        unsigned long long* incl_base = p.inclw + (size_t)chain * n * Cs + c;
+        const unsigned long long tag_incl = (unsigned long long)((p.epoch << 2) | ST_INCL) << 32;
         int head = 0;
+#ifdef AB_SCAN_TRACE
+        int round = 0;
+        long long cyc_chain = 0, cyc_store = 0, n_iter = 0;
+#endif
         while (head < n) {
             const int hi = min(head + K, n);
+#ifdef AB_SCAN_TRACE
+            const unsigned long long tr0 = gtime();
+            const int head0 = head;
+#endif
             for (int s2 = head; s2 < hi; ++s2) {
                 const int j = DIR > 0 ? s2 : n - 1 - s2;
                 const unsigned long long* w = p.words + (((size_t)chain * n + j) * Cs + c) * 2;
@@ -150,31 +179,59 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, flo
             {   // the state entering tile `head` is known now: publish it while the loads fly
                 const int j = DIR > 0 ? head : n - 1 - head;
                 ab_st_relaxed_u64(p.inclw + ((size_t)chain * n + j) * Cs + c, pack_word(p.epoch, ST_INCL, h));
-                if (DIR > 0 && p.hstart) p.hstart[((size_t)b * n + j) * p.Di + cg] = h;
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef AB_SCAN_TRACE
+            const unsigned long long tr1 = gtime();
+#endif
             bool stop = false;
             while (head < hi && !stop) {
-                uint4 w4[4];
+                // 8 ring slots at a time: loads, then the dependent FMA chain over the valid prefix, then the stores
+                uint4 w4[8];
+#ifdef AB_SCAN_TRACE
+                const long long ck0 = clock64();
+#endif
 #pragma unroll
-                for (int u = 0; u < 4; ++u) w4[u] = myring[(size_t)((head + u) & (K - 1)) * pitch];
+                for (int u = 0; u < 8; ++u) w4[u] = myring[(size_t)((head + u) & (K - 1)) * pitch];
+                float hv[8];
+                int m = 0;
+                bool ok = true;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (stop || head >= hi) break;
-                    const unsigned long long wp = ((unsigned long long)w4[u].y << 32) | w4[u].x;
-                    const unsigned long long wsv = ((unsigned long long)w4[u].w << 32) | w4[u].z;
-                    if (!word_valid(wp, p.epoch) || !word_valid(wsv, p.epoch)) { stop = true; break; }
-                    h = fmaf(__uint_as_float(w4[u].x), h, __uint_as_float(w4[u].z));
-                    ++head;
-                    if (head < n) {
-                        const int j = DIR > 0 ? head : n - 1 - head;
-                        ab_st_relaxed_u64(p.inclw + ((size_t)chain * n + j) * Cs + c, pack_word(p.epoch, ST_INCL, h));
-                        if (DIR > 0 && p.hstart) p.hstart[((size_t)b * n + j) * p.Di + cg] = h;
+                for (int u = 0; u < 8; ++u) {
+                    ok = ok && head + u < hi && (w4[u].y >> 2) == p.epoch && (w4[u].w >> 2) == p.epoch;
+                    if (ok) { h = fmaf(__uint_as_float(w4[u].x), h, __uint_as_float(w4[u].z)); m = u + 1; }
+                    hv[u] = h;
+                }
+#ifdef AB_SCAN_TRACE
+                const long long ck1 = clock64();
+#endif
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int jn = head + u + 1;            // hv[u] is the state entering tile jn
+                    if (u < m && jn < n) {
+                        const int j = DIR > 0 ? jn : n - 1 - jn;
+                        ab_st_relaxed_u64_unordered(incl_base + (size_t)j * Cs, tag_incl | __float_as_uint(hv[u]));
                     }
                 }
+                head += m;
+                stop = m < 8 && head < hi;
+#ifdef AB_SCAN_TRACE
+                const long long ck2 = clock64();
+                cyc_chain += ck1 - ck0; cyc_store += ck2 - ck1; ++n_iter;
+#endif
             }
+#ifdef AB_SCAN_TRACE
+            if (c == 0 && chain < 64 && round < STRACE_ROUNDS) {
+                unsigned long long* o = g_scanner_trace + ((size_t)chain * STRACE_ROUNDS + round) * 4;
+                o[0] = tr0; o[1] = tr1; o[2] = gtime(); o[3] = (unsigned long long)(head - head0);
+            }
+            ++round;
+#endif
             if (stop && ++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
         }
+#ifdef AB_SCAN_TRACE
+        if (c == 0 && chain == 0) printf("scanner chain 0: %lld consume iterations, %lld cycles load+chain, %lld cycles stores per iteration\n", n_iter, cyc_chain / max(n_iter, 1LL), cyc_store / max(n_iter, 1LL));
+#endif
         if (DIR > 0 && p.h_last) p.h_last[(size_t)b * p.Di + cg] = h;
         return;
     }
@@ -186,7 +243,6 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, flo
         for (int cc = c; cc < Cs; cc += blockDim.x) {
             const float h = hs[cc];
             ab_st_relaxed_u64(p.inclw + tl * Cs + cc, pack_word(p.epoch, ST_INCL, h));
-            if (DIR > 0 && p.hstart) p.hstart[((size_t)b * n + j) * p.Di + slab * Cs + cc] = h;
         }
         for (int cc = c; cc < Cs; cc += blockDim.x) {
             const unsigned long long* w = p.words + (tl * Cs + cc) * 2;
@@ -263,74 +319,98 @@ __device__ __forceinline__ void ldg_vec(const T* p, float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward
-// smem: [tiles: nT x T x Cs of T] [sdel: (T+1) x nh] [sP: n_s x Cs] [sS: n_s x Cs] [hT: Cs] [bar] [tile id]
+// tile coordinates from the ticket / block index: chains interleaved, chunks in scan order
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MODE>
-__global__ void __launch_bounds__(256, 3) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
-                                                       const __grid_constant__ CUtensorMap tm_b,
-                                                       const __grid_constant__ CUtensorMap tm_c,
-                                                       const __grid_constant__ CUtensorMap tm_z, const ScanParams p) {
-    constexpr int V = 16 / (int)sizeof(T);
+// floats reserved for the staged dt rows, rounded so that the aggregate arrays behind them stay 16-byte aligned
+__host__ __device__ __forceinline__ int sdel_floats(int T, int nh_max) { return ((T + 1) * nh_max + 3) & ~3; }
+
+struct TileCoord { int chain, j, b, c0, row0, h_lo, nh; size_t tile_lin; };
+__device__ __forceinline__ TileCoord decode_tile(const ScanParams& p, int tile, bool reverse) {
+    TileCoord t;
+    t.chain = tile % p.nchains;
+    const int jj = tile / p.nchains;
+    t.j = reverse ? p.nchunks - 1 - jj : jj;
+    const int slab = t.chain % p.nslab;
+    t.b = t.chain / p.nslab;
+    t.c0 = slab * p.Cs;
+    t.row0 = t.j * p.T;
+    t.h_lo = t.c0 / 16;
+    t.nh = (t.c0 + p.Cs - 1) / 16 - t.h_lo + 1;
+    t.tile_lin = (size_t)t.chain * p.nchunks + t.j;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward, one tile per CTA (many small CTAs per SM hide the TMA latency and the scanner hand-shake)
+// smem: [NT tiles of T x Cs] [sdel: (T+1) x nh] [sP, sS: n_s x Cs] [hT: Cs] [mbarrier]
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int V, int CS>
+__global__ void __launch_bounds__(V == 4 ? 256 : 128, V == 4 ? 4 : 6) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
+                                                          const __grid_constant__ CUtensorMap tm_b,
+                                                          const __grid_constant__ CUtensorMap tm_c,
+                                                          const __grid_constant__ CUtensorMap tm_z, const ScanParams p) {
+    constexpr int NT = MODE == MODE_AGG ? 1 : 4;      // the aggregate pass only needs Bm
     extern __shared__ __align__(128) unsigned char smem[];
-    const int Cs = p.Cs, Tt = p.T, n_s = p.n_s;
+    const int Cs = CS ? CS : p.Cs;                          // CS != 0: slab width known at compile time
+    const int Tt = p.T, n_s = p.n_s;
     const size_t tile_bytes = (size_t)Tt * Cs * sizeof(T);
     const size_t pitch = (tile_bytes + 127) / 128 * 128;     // TMA destinations are 128-byte aligned
-    constexpr int n_tiles_staged = MODE == MODE_AGG ? 1 : 4; // the aggregate pass only needs Bm
-    T* s_b = reinterpret_cast<T*>(smem);
-    T* s_xa = reinterpret_cast<T*>(smem + pitch);
-    T* s_c = reinterpret_cast<T*>(smem + 2 * pitch);
-    T* s_z = reinterpret_cast<T*>(smem + 3 * pitch);
-    float* sdel = reinterpret_cast<float*>(smem + (size_t)n_tiles_staged * pitch);
     const int nh_max = Cs / 16 + 2;
-    float* sP = sdel + (size_t)(Tt + 1) * nh_max;
+    float* sdel = reinterpret_cast<float*>(smem + (size_t)NT * pitch);
+    float* sP = sdel + sdel_floats(Tt, nh_max);
     float* sS = sP + (size_t)n_s * Cs;
     float* hT = sS + (size_t)n_s * Cs;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + Cs + (((uintptr_t)(hT + Cs)) % 8 ? 1 : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hT + Cs + (((uintptr_t)(hT + Cs)) % 8 ? 1 : 0));
     __shared__ unsigned int s_ticket;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        if (MODE == MODE_FUSED) s_ticket = atomicAdd(p.ticket, 1u); else s_ticket = blockIdx.x;
-        ab_mbar_init(bar, 1);
+        s_ticket = MODE == MODE_FUSED ? atomicAdd(p.ticket, 1u) : blockIdx.x;
+        ab_mbar_init(&bars[0], 1);
         ab_fence_mbar_init();
     }
     __syncthreads();
-    int ticket = (int)s_ticket;
+    int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
-        if (ticket < p.n_scan) {
-            scanner_role<+1>(p, ticket, hT, reinterpret_cast<uint4*>(smem), ring_depth((size_t)n_tiles_staged * pitch, Cs));
+        if (tile < p.n_scan) {
+            scanner_role<+1>(p, tile, hT, reinterpret_cast<uint4*>(smem), ring_depth((size_t)NT * pitch, Cs));
             return;
         }
-        ticket -= p.n_scan;
+        tile -= p.n_scan;
     }
-    const int chain = ticket % p.nchains, j = ticket / p.nchains;
-    const int slab = chain % p.nslab, b = chain / p.nslab;
-    const int c0 = slab * Cs, row0 = j * Tt;
-    const int h_lo = c0 / 16;
-    const int nh = (c0 + Cs - 1) / 16 - h_lo + 1;
+    if (tile >= p.nchains * p.nchunks) return;
 
+    const TileCoord tc = decode_tile(p, tile, false);
+    const size_t tile_lin = tc.tile_lin;
+    const int c0 = tc.c0, row0 = tc.row0, b = tc.b, nh = tc.nh, j = tc.j;
+    TRACE_MARK(tile_lin, 0);
     if (tid == 0) {
-        ab_mbar_expect_tx(bar, (uint32_t)(n_tiles_staged * tile_bytes));
-        ab_tma_load_3d(s_b, &tm_b, bar, c0, row0, b);
+        ab_mbar_expect_tx(&bars[0], (uint32_t)(NT * tile_bytes));
+        ab_tma_load_3d(smem, &tm_b, &bars[0], c0, row0, b);
         if (MODE != MODE_AGG) {
-            ab_tma_load_3d(s_xa, &tm_xa, bar, c0, row0, b);
-            ab_tma_load_3d(s_c, &tm_c, bar, c0, row0, b);
-            ab_tma_load_3d(s_z, &tm_z, bar, c0, row0, b);
+            ab_tma_load_3d(smem + pitch, &tm_xa, &bars[0], c0, row0, b);
+            ab_tma_load_3d(smem + 2 * pitch, &tm_c, &bars[0], c0, row0, b);
+            ab_tma_load_3d(smem + 3 * pitch, &tm_z, &bars[0], c0, row0, b);
         }
     }
-    stage_delta<T>(p, sdel, b, row0, Tt, h_lo, nh);
+    stage_delta<T>(p, sdel, b, row0, Tt, tc.h_lo, nh);
 
     const int ncv = Cs / V;
     const int i_run = tid / ncv, cv = tid % ncv;       // blockDim.x == n_s * ncv
     const int cl = cv * V;                             // channel offset inside the slab
-    const int hh = (c0 + cl) / 16 - h_lo;              // head slot of this thread's channels (V divides 16)
+    const T* s_b = reinterpret_cast<const T*>(smem);
+    const T* s_xa = reinterpret_cast<const T*>(smem + pitch);
+    const T* s_c = reinterpret_cast<const T*>(smem + 2 * pitch);
+    const T* s_z = reinterpret_cast<const T*>(smem + 3 * pitch);
+    const int hh = (c0 + cl) / 16 - tc.h_lo;           // head slot of this thread's channels (V divides 16)
     float A2[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) A2[v] = -__expf(__ldg(p.A_log + c0 + cl + v)) * AB_LOG2E;
 
     __syncthreads();            // sdel visible
-    ab_mbar_wait(bar, 0);       // TMA tiles landed
+    TRACE_MARK(tile_lin, 1);
+    ab_mbar_wait(&bars[0], 0);  // TMA tiles landed
+    TRACE_MARK(tile_lin, 2);
 
     // ---- sweep 1: per-run aggregates (the decay factors are recomputed in sweep 2: one MUFU is cheaper than
     //      holding TS x V registers across the hand-shake with the scanner)
@@ -355,13 +435,23 @@ __global__ void __launch_bounds__(256, 3) scan_fwd_kernel(const __grid_constant_
         for (int v = 0; v < V; ++v) { sP[i_run * Cs + cl + v] = P[v]; sS[i_run * Cs + cl + v] = S[v]; }
     }
     __syncthreads();
+    TRACE_MARK(tile_lin, 3);
 
     // ---- tile aggregate, publish, resolve incoming state (one thread per channel)
-    const size_t tile_lin = (size_t)chain * p.nchunks + j;
     for (int c = tid; c < Cs; c += blockDim.x) {
+        // run aggregates are read 8 at a time (independent loads first, then the dependent FMA chain)
         float Pt = 1.f, St = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < n_s; ++i) { St = fmaf(St, sP[i * Cs + c], sS[i * Cs + c]); Pt *= sP[i * Cs + c]; }
+        for (int i0 = 0; i0 < n_s; i0 += 8) {
+            float P8[8], S8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = i0 + u < n_s;
+                P8[u] = ok ? sP[(i0 + u) * Cs + c] : 1.f;
+                S8[u] = ok ? sS[(i0 + u) * Cs + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { St = fmaf(St, P8[u], S8[u]); Pt *= P8[u]; }
+        }
         float hin;
         if (MODE == MODE_AGG) {
             p.aggP[tile_lin * Cs + c] = Pt;
@@ -373,27 +463,40 @@ __global__ void __launch_bounds__(256, 3) scan_fwd_kernel(const __grid_constant_
             unsigned long long* w = p.words + (tile_lin * Cs + c) * 2;
             ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
             ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
-            hin = wait_incoming(p, tile_lin, c);        // hstart / h_last are written by the scanner
+            TRACE_MARK(tile_lin, 4);
+            hin = wait_incoming(p, tile_lin, c);        // h_last is written by the scanner
+            TRACE_MARK(tile_lin, 5);
+            if (p.hstart) p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c] = hin;     // kept for the backward
         }
-        // state entering every run of this channel, in place of the run aggregates S (one serial pass by the channel's
-        // thread instead of an O(n_s) prefix loop in every thread)
+        // state entering every run of this channel, in place of the run aggregates S (one serial pass by the
+        // channel's thread instead of an O(n_s) prefix loop in every thread)
         float hr = hin;
-#pragma unroll 4
-        for (int i = 0; i < n_s; ++i) {
-            const float pi = sP[i * Cs + c], si = sS[i * Cs + c];
-            sS[i * Cs + c] = hr;
-            hr = fmaf(pi, hr, si);
+        for (int i0 = 0; i0 < n_s; i0 += 8) {
+            float P8[8], S8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = i0 + u < n_s;
+                P8[u] = ok ? sP[(i0 + u) * Cs + c] : 1.f;
+                S8[u] = ok ? sS[(i0 + u) * Cs + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i0 + u < n_s) sS[(i0 + u) * Cs + c] = hr;
+                hr = fmaf(P8[u], hr, S8[u]);
+            }
         }
     }
     if (MODE == MODE_AGG) return;
     __syncthreads();
+    TRACE_MARK(tile_lin, 6);
 
     // ---- state entering this thread's run, then sweep 2
     float h[V], Dv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { h[v] = sS[i_run * Cs + cl + v]; Dv[v] = __ldg(p.Dp + c0 + cl + v); }
-    T* yo = reinterpret_cast<T*>(p.y);
-    T* yso = reinterpret_cast<T*>(p.y_ssm);
+    const size_t off0 = ((size_t)b * p.L + row0 + i_run * TS) * p.Di + c0 + cl;
+    T* yo = reinterpret_cast<T*>(p.y) + off0;
+    T* yso = p.y_ssm ? reinterpret_cast<T*>(p.y_ssm) + off0 : nullptr;
 #pragma unroll
     for (int t = 0; t < TS; ++t) {
         const int r = i_run * TS + t;
@@ -411,36 +514,86 @@ __global__ void __launch_bounds__(256, 3) scan_fwd_kernel(const __grid_constant_
             o[v] = fmaf(Dv[v], xv[v], os[v]) * (zv[v] * gate_sigmoid<T>(zv[v]));
         }
         if (row < p.L) {
-            const size_t off = ((size_t)b * p.L + row) * p.Di + c0 + cl;
-            st_vec<T, V>(yo + off, o);
-            if (yso) st_vec<T, V>(yso + off, os);
+            st_vec<T, V>(yo + (size_t)t * p.Di, o);
+            if (yso) st_vec<T, V>(yso + (size_t)t * p.Di, os);
         }
     }
+    TRACE_MARK(tile_lin, 7);
 }
 
-// two-pass: hstart[b][j][c] for all j, sequential over chunks (forward direction) or reversed
-__global__ void scan_combine_kernel(const float* __restrict__ aggP, const float* __restrict__ aggS,
-                                    const float* __restrict__ h0, float* __restrict__ hstart, float* __restrict__ h_last,
-                                    int B, int Di, int Cs, int nslab, int nchunks, int reverse) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B * Di) return;
-    const int b = g / Di, cg = g % Di;
+// two-pass: state entering every tile.  A block owns COMB_CH channels; the chunk axis is cut into COMB_SEG segments that
+// are composed in parallel (pass 1), chained through shared memory, and re-walked to emit the per-tile states (pass 2;
+// the aggregates are L2 hits by then).  Loads of 8 tiles are issued ahead of the 8 dependent FMAs.
+constexpr int COMB_CH = 16, COMB_SEG = 32;
+__global__ void __launch_bounds__(COMB_CH * COMB_SEG) scan_combine_kernel(
+    const float* __restrict__ aggP, const float* __restrict__ aggS, const float* __restrict__ h0,
+    float* __restrict__ hstart, float* __restrict__ h_last, int B, int Di, int Cs, int nslab, int nchunks, int reverse) {
+    __shared__ float segP[COMB_SEG][COMB_CH], segS[COMB_SEG][COMB_CH];
+    const int cx = threadIdx.x % COMB_CH, sg = threadIdx.x / COMB_CH;
+    const int g = blockIdx.x * COMB_CH + cx;
+    const bool live = g < B * Di;
+    const int b = live ? g / Di : 0, cg = live ? g % Di : 0;
     const int slab = cg / Cs, c = cg % Cs;
-    const int chain = b * nslab + slab;
-    float h = (!reverse && h0) ? h0[(size_t)b * Di + cg] : 0.f;
-    for (int jj = 0; jj < nchunks; ++jj) {
-        const int j = reverse ? nchunks - 1 - jj : jj;
-        hstart[((size_t)b * nchunks + j) * Di + cg] = h;
-        const size_t o = ((size_t)chain * nchunks + j) * Cs + c;
-        h = fmaf(aggP[o], h, aggS[o]);
+    const size_t chain_base = (size_t)(b * nslab + slab) * nchunks;
+    const int seglen = (nchunks + COMB_SEG - 1) / COMB_SEG;
+    const int lo = min(sg * seglen, nchunks), hi = min(lo + seglen, nchunks);
+    float Pa = 1.f, Sa = 0.f;
+    if (live) {
+        for (int j0 = lo; j0 < hi; j0 += 8) {
+            float P[8], S[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jj = j0 + u;
+                P[u] = 1.f; S[u] = 0.f;
+                if (jj < hi) {
+                    const size_t o = (chain_base + (reverse ? nchunks - 1 - jj : jj)) * Cs + c;
+                    P[u] = aggP[o]; S[u] = aggS[o];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { Sa = fmaf(P[u], Sa, S[u]); Pa *= P[u]; }
+        }
     }
-    if (h_last) h_last[(size_t)b * Di + cg] = h;
+    segP[sg][cx] = Pa; segS[sg][cx] = Sa;
+    __syncthreads();
+    if (!live) return;
+    float h = (!reverse && h0) ? h0[(size_t)b * Di + cg] : 0.f;
+    for (int i = 0; i < sg; ++i) h = fmaf(segP[i][cx], h, segS[i][cx]);
+    for (int j0 = lo; j0 < hi; j0 += 8) {
+        float P[8], S[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jj = j0 + u;
+            P[u] = 1.f; S[u] = 0.f;
+            if (jj < hi) {
+                const size_t o = (chain_base + (reverse ? nchunks - 1 - jj : jj)) * Cs + c;
+                P[u] = aggP[o]; S[u] = aggS[o];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int jj = j0 + u;
+            if (jj < hi) {
+                const int j = reverse ? nchunks - 1 - jj : jj;
+                hstart[((size_t)b * nchunks + j) * Di + cg] = h;
+                h = fmaf(P[u], h, S[u]);
+            }
+        }
+    }
+    if (h_last && sg == COMB_SEG - 1) h_last[(size_t)b * Di + cg] = h;
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward (V = 4 channels per thread for both dtypes)
+// backward (V = 4 channels per thread for both dtypes), one tile per CTA, tiles taken in REVERSE time order.
+// Phase order (the hand-shake of the reverse scan is hidden behind the forward recompute):
+//   A  one sweep: decay factors, g_t = d(y_ssm)_t * C_t, reverse run aggregates (sP/sS) and forward run aggregates (fP/fS)
+//   B  channel threads: reverse tile aggregate -> publish (single pass) / store (aggregate pass)
+//   C  forward recompute from hstart: states, dxa / dCm / dz, keeps h_{t-1}
+//   D  channel threads: wait for G entering the tile (scanner / combine kernel)
+//   E  reverse sweep: G_t, dBm, d(dt), per-tile partials of dA_log and dD
+// smem: [5 tiles of T x Cs] [sdel: (T+1) x nh] [sP, sS, fP, fS: n_s x Cs] [hT, gT: Cs] [mbarrier]
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+template <typename T, int MODE, int CS>
 __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
                                                        const __grid_constant__ CUtensorMap tm_b,
                                                        const __grid_constant__ CUtensorMap tm_c,
@@ -448,60 +601,65 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
                                                        const __grid_constant__ CUtensorMap tm_do, const ScanParams p,
                                                        float* __restrict__ gin_ws) {
     constexpr int V = 4;
+    constexpr int NT = 5;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int Cs = p.Cs, Tt = p.T, n_s = p.n_s;
+    const int Cs = CS ? CS : p.Cs;
+    const int Tt = p.T, n_s = p.n_s;
     const size_t tile_bytes = (size_t)Tt * Cs * sizeof(T);
     const size_t pitch = (tile_bytes + 127) / 128 * 128;
-    T* s_b = reinterpret_cast<T*>(smem);
-    T* s_c = reinterpret_cast<T*>(smem + pitch);
-    T* s_z = reinterpret_cast<T*>(smem + 2 * pitch);
-    T* s_do = reinterpret_cast<T*>(smem + 3 * pitch);
-    T* s_xa = reinterpret_cast<T*>(smem + 4 * pitch);
-    const int n_staged = MODE == MODE_AGG ? 4 : 5;
+    constexpr int n_staged = MODE == MODE_AGG ? 3 : 5;      // the aggregate pass needs Cm, z, dout only
     const int nh_max = Cs / 16 + 2;
-    float* sdel = reinterpret_cast<float*>(smem + 5 * pitch);
-    float* sP = sdel + (size_t)(Tt + 1) * nh_max;
+    float* sdel = reinterpret_cast<float*>(smem + (size_t)NT * pitch);
+    float* sP = sdel + sdel_floats(Tt, nh_max);
     float* sS = sP + (size_t)n_s * Cs;
-    float* hT = sS + (size_t)n_s * Cs;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(hT + Cs + (((uintptr_t)(hT + Cs)) % 8 ? 1 : 0));
+    float* fP = sS + (size_t)n_s * Cs;
+    float* fS = fP + (size_t)n_s * Cs;
+    float* hT = fS + (size_t)n_s * Cs;
+    float* gT = hT + Cs;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gT + Cs + (((uintptr_t)(gT + Cs)) % 8 ? 1 : 0));
     __shared__ unsigned int s_ticket;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        if (MODE == MODE_FUSED) s_ticket = atomicAdd(p.ticket, 1u); else s_ticket = blockIdx.x;
-        ab_mbar_init(bar, 1);
+        s_ticket = MODE == MODE_FUSED ? atomicAdd(p.ticket, 1u) : blockIdx.x;
+        ab_mbar_init(&bars[0], 1);
         ab_fence_mbar_init();
     }
     __syncthreads();
-    int ticket = (int)s_ticket;
+    int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
-        if (ticket < p.n_scan) {
-            scanner_role<-1>(p, ticket, hT, reinterpret_cast<uint4*>(smem), ring_depth(5 * pitch, Cs));
+        if (tile < p.n_scan) {
+            scanner_role<-1>(p, tile, hT, reinterpret_cast<uint4*>(smem), ring_depth((size_t)NT * pitch, Cs));
             return;
         }
-        ticket -= p.n_scan;
+        tile -= p.n_scan;
     }
-    const int chain = ticket % p.nchains;
-    const int j = p.nchunks - 1 - ticket / p.nchains;       // reverse time order
-    const int slab = chain % p.nslab, b = chain / p.nslab;
-    const int c0 = slab * Cs, row0 = j * Tt;
-    const int h_lo = c0 / 16;
-    const int nh = (c0 + Cs - 1) / 16 - h_lo + 1;
+    if (tile >= p.nchains * p.nchunks) return;
 
+    const TileCoord tc = decode_tile(p, tile, true);
+    const size_t tile_lin = tc.tile_lin;
+    const int c0 = tc.c0, row0 = tc.row0, b = tc.b, nh = tc.nh, j = tc.j;
+    TRACE_MARK(tile_lin, 0);
     if (tid == 0) {
-        ab_mbar_expect_tx(bar, (uint32_t)(n_staged * tile_bytes));
-        ab_tma_load_3d(s_b, &tm_b, bar, c0, row0, b);
-        ab_tma_load_3d(s_c, &tm_c, bar, c0, row0, b);
-        ab_tma_load_3d(s_z, &tm_z, bar, c0, row0, b);
-        ab_tma_load_3d(s_do, &tm_do, bar, c0, row0, b);
-        if (MODE != MODE_AGG) ab_tma_load_3d(s_xa, &tm_xa, bar, c0, row0, b);
+        ab_mbar_expect_tx(&bars[0], (uint32_t)(n_staged * tile_bytes));
+        if (MODE != MODE_AGG) ab_tma_load_3d(smem, &tm_b, &bars[0], c0, row0, b);
+        ab_tma_load_3d(smem + pitch, &tm_c, &bars[0], c0, row0, b);
+        ab_tma_load_3d(smem + 2 * pitch, &tm_z, &bars[0], c0, row0, b);
+        ab_tma_load_3d(smem + 3 * pitch, &tm_do, &bars[0], c0, row0, b);
+        if (MODE != MODE_AGG) ab_tma_load_3d(smem + 4 * pitch, &tm_xa, &bars[0], c0, row0, b);
     }
-    stage_delta<T>(p, sdel, b, row0, Tt + 1, h_lo, nh);
+    stage_delta<T>(p, sdel, b, row0, Tt + 1, tc.h_lo, nh);
 
     const int ncv = Cs / V;
     const int i_run = tid / ncv, cv = tid % ncv;
     const int cl = cv * V;
-    const int hh = (c0 + cl) / 16 - h_lo;
+    const T* s_b = reinterpret_cast<const T*>(smem);
+    const T* s_c = reinterpret_cast<const T*>(smem + pitch);
+    const T* s_z = reinterpret_cast<const T*>(smem + 2 * pitch);
+    const T* s_do = reinterpret_cast<const T*>(smem + 3 * pitch);
+    const T* s_xa = reinterpret_cast<const T*>(smem + 4 * pitch);
+    const T* dys_i = reinterpret_cast<const T*>(p.dyssm);
+    const int hh = (c0 + cl) / 16 - tc.h_lo;
     float A2[V], Dv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -511,12 +669,14 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
     if (MODE != MODE_AGG)
         for (int c = tid; c < Cs; c += blockDim.x) hT[c] = p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
 
-    __syncthreads();
-    ab_mbar_wait(bar, 0);
+    __syncthreads();            // sdel + hT visible
+    ab_mbar_wait(&bars[0], 0);
+    TRACE_MARK(tile_lin, 1);
 
-    // ---- F1: decay factors + forward run aggregates
-    float a[TS][V];
+    // ---- A: decay factors, g, reverse and forward run aggregates
+    float a[TS][V], g[TS][V];
     float dl[TS];
+    float anext[V];
     {
         float P[V], S[V];
 #pragma unroll
@@ -524,96 +684,36 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
 #pragma unroll
         for (int t = 0; t < TS; ++t) {
             const int r = i_run * TS + t;
-            dl[t] = sdel[r * nh + hh];
-            float bv[V];
-            lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                a[t][v] = ab_ex2(A2[v] * dl[t]);
-                P[v] *= a[t][v];
-                S[v] = fmaf(a[t][v], S[v], bv[v]);
-            }
-        }
-        if (MODE != MODE_AGG) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) { sP[i_run * Cs + cl + v] = P[v]; sS[i_run * Cs + cl + v] = S[v]; }
-        }
-    }
-    float anext[V];
-    {
-        const float dn = sdel[(i_run * TS + TS) * nh + hh];
-#pragma unroll
-        for (int v = 0; v < V; ++v) anext[v] = ab_ex2(A2[v] * dn);
-    }
-    __syncthreads();
-
-    // ---- F2: recompute states, emit dxa / dCm / dz, keep hprev and g
-    float hprev[TS][V], g[TS][V];
-    float accD[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) accD[v] = 0.f;
-    {
-        float h[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) h[v] = MODE != MODE_AGG ? hT[cl + v] : 0.f;
-        if (MODE != MODE_AGG) {
-            for (int i = 0; i < i_run; ++i) {
-#pragma unroll
-                for (int v = 0; v < V; ++v) h[v] = fmaf(h[v], sP[i * Cs + cl + v], sS[i * Cs + cl + v]);
-            }
-        }
-        T* dxa_o = reinterpret_cast<T*>(p.dxa);
-        T* dc_o = reinterpret_cast<T*>(p.dCm);
-        T* dz_o = reinterpret_cast<T*>(p.dz);
-        const T* dys_i = reinterpret_cast<const T*>(p.dyssm);
-#pragma unroll
-        for (int t = 0; t < TS; ++t) {
-            const int r = i_run * TS + t;
             const int row = row0 + r;
-            float bv[V], cvv[V], zv[V], dov[V], xv[V], dys[V];
+            dl[t] = sdel[r * nh + hh];
+            float bv[V], cvv[V], zv[V], dov[V], dys[V];
             lds_vec<T, V>(s_c + (size_t)r * Cs + cl, cvv);
             lds_vec<T, V>(s_z + (size_t)r * Cs + cl, zv);
             lds_vec<T, V>(s_do + (size_t)r * Cs + cl, dov);
+            if (MODE != MODE_AGG) lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
 #pragma unroll
             for (int v = 0; v < V; ++v) dys[v] = 0.f;
             if (dys_i && row < p.L) ldg_vec<T, V>(dys_i + ((size_t)b * p.L + row) * p.Di + c0 + cl, dys);
-            if (MODE != MODE_AGG) {
-                lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
-                lds_vec<T, V>(s_xa + (size_t)r * Cs + cl, xv);
-            }
-            float o_dxa[V], o_dc[V], o_dz[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float sg = gate_sigmoid<T>(zv[v]);
-                const float gate = zv[v] * sg;
-                const float dyv = dov[v] * gate;           // grad of (y_ssm + D*xa)
-                const float dtot = dyv + dys[v];           // grad of y_ssm
-                g[t][v] = dtot * cvv[v];
+                a[t][v] = ab_ex2(A2[v] * dl[t]);
+                g[t][v] = fmaf(dov[v], zv[v] * gate_sigmoid<T>(zv[v]), dys[v]) * cvv[v];
                 if (MODE != MODE_AGG) {
-                    hprev[t][v] = h[v];
-                    h[v] = fmaf(a[t][v], h[v], bv[v]);
-                    const float yv = fmaf(Dv[v], xv[v], cvv[v] * h[v]);
-                    o_dxa[v] = dyv * Dv[v];
-                    o_dc[v] = dtot * h[v];
-                    o_dz[v] = dov[v] * yv * (sg * fmaf(zv[v], 1.f - sg, 1.f));
-                    accD[v] = fmaf(dyv, xv[v], accD[v]);
+                    P[v] *= a[t][v];
+                    S[v] = fmaf(a[t][v], S[v], bv[v]);
                 }
             }
-            if (MODE != MODE_AGG && row < p.L) {
-                const size_t off = ((size_t)b * p.L + row) * p.Di + c0 + cl;
-                st_vec<T, V>(dxa_o + off, o_dxa);
-                st_vec<T, V>(dz_o + off, o_dz);
-                st_vec<T, V>(dc_o + ((size_t)b * p.L + row) * p.dbc_stride + c0 + cl, o_dc);
-            }
         }
-    }
-    __syncthreads();     // all forward-prefix reads of sP/sS done before they are reused
-
-    // ---- reverse run aggregates:  G(run start) = Sr + Pr * G(next run start)
-    {
+        if (MODE != MODE_AGG) {
+            *reinterpret_cast<float4*>(fP + i_run * Cs + cl) = make_float4(P[0], P[1], P[2], P[3]);
+            *reinterpret_cast<float4*>(fS + i_run * Cs + cl) = make_float4(S[0], S[1], S[2], S[3]);
+        }
+        // reverse:  G(run start) = Gs + Pr * G(next run start)
+        const float dn = sdel[(i_run * TS + TS) * nh + hh];
         float Gs[V], Pr[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
+            anext[v] = ab_ex2(A2[v] * dn);
             Gs[v] = g[TS - 1][v];
             Pr[v] = anext[v];
         }
@@ -625,49 +725,117 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
                 Pr[v] *= a[t + 1][v];
             }
         }
-#pragma unroll
-        for (int v = 0; v < V; ++v) { sP[i_run * Cs + cl + v] = Pr[v]; sS[i_run * Cs + cl + v] = Gs[v]; }
+        *reinterpret_cast<float4*>(sP + i_run * Cs + cl) = make_float4(Pr[0], Pr[1], Pr[2], Pr[3]);
+        *reinterpret_cast<float4*>(sS + i_run * Cs + cl) = make_float4(Gs[0], Gs[1], Gs[2], Gs[3]);
     }
     __syncthreads();
+    TRACE_MARK(tile_lin, 2);
 
-    const size_t tile_lin = (size_t)chain * p.nchunks + j;
+    // ---- B: reverse tile aggregate (one thread per channel); the single pass publishes it and collects the answer in D
     for (int c = tid; c < Cs; c += blockDim.x) {
         float Pt = 1.f, St = 0.f;
-#pragma unroll 4
-        for (int i = n_s - 1; i >= 0; --i) { St = fmaf(St, sP[i * Cs + c], sS[i * Cs + c]); Pt *= sP[i * Cs + c]; }
-        float gin;
+        for (int i0 = n_s - 1; i0 >= 0; i0 -= 8) {
+            float P8[8], S8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = i0 - u >= 0;
+                P8[u] = ok ? sP[(i0 - u) * Cs + c] : 1.f;
+                S8[u] = ok ? sS[(i0 - u) * Cs + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { St = fmaf(St, P8[u], S8[u]); Pt *= P8[u]; }
+        }
         if (MODE == MODE_AGG) {
             p.aggP[tile_lin * Cs + c] = Pt;
             p.aggS[tile_lin * Cs + c] = St;
-            continue;
-        } else if (MODE == MODE_APPLY) {
-            gin = gin_ws[((size_t)b * p.nchunks + j) * p.Di + c0 + c];
-        } else {
+        } else if (MODE == MODE_FUSED) {
             unsigned long long* w = p.words + (tile_lin * Cs + c) * 2;
             ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
             ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
-            gin = wait_incoming(p, tile_lin, c);
         }
-        hT[c] = gin;
     }
     if (MODE == MODE_AGG) return;
-    __syncthreads();
+    TRACE_MARK(tile_lin, 3);
 
-    // ---- G entering this run from later runs, then the reverse sweep
+    // ---- C: recompute states, emit dxa / dCm / dz, keep h_{t-1}
+    float hprev[TS][V];
+    float accD[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) accD[v] = 0.f;
+    {
+        float h[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) h[v] = hT[cl + v];
+#pragma unroll 4
+        for (int i = 0; i < i_run; ++i) {
+            const float4 pp = *reinterpret_cast<const float4*>(fP + i * Cs + cl), ss = *reinterpret_cast<const float4*>(fS + i * Cs + cl);
+            h[0] = fmaf(h[0], pp.x, ss.x); h[1] = fmaf(h[1], pp.y, ss.y); h[2] = fmaf(h[2], pp.z, ss.z); h[3] = fmaf(h[3], pp.w, ss.w);
+        }
+        const size_t tok0 = (size_t)b * p.L + row0 + i_run * TS;          // first token of this run
+        T* dxa_o = reinterpret_cast<T*>(p.dxa) + tok0 * p.Di + c0 + cl;
+        T* dz_o = reinterpret_cast<T*>(p.dz) + tok0 * p.Di + c0 + cl;
+        T* dc_o = reinterpret_cast<T*>(p.dCm) + tok0 * p.dbc_stride + c0 + cl;
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+            const int r = i_run * TS + t;
+            const int row = row0 + r;
+            float bv[V], cvv[V], zv[V], dov[V], xv[V], dys[V];
+            lds_vec<T, V>(s_c + (size_t)r * Cs + cl, cvv);
+            lds_vec<T, V>(s_z + (size_t)r * Cs + cl, zv);
+            lds_vec<T, V>(s_do + (size_t)r * Cs + cl, dov);
+            lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
+            lds_vec<T, V>(s_xa + (size_t)r * Cs + cl, xv);
+#pragma unroll
+            for (int v = 0; v < V; ++v) dys[v] = 0.f;
+            if (dys_i && row < p.L) ldg_vec<T, V>(dys_i + ((size_t)b * p.L + row) * p.Di + c0 + cl, dys);
+            float o_dxa[V], o_dc[V], o_dz[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float sg = gate_sigmoid<T>(zv[v]);
+                const float dyv = dov[v] * (zv[v] * sg);       // grad of (y_ssm + D*xa)
+                const float dtot = dyv + dys[v];               // grad of y_ssm
+                hprev[t][v] = h[v];
+                h[v] = fmaf(a[t][v], h[v], bv[v]);
+                const float yv = fmaf(Dv[v], xv[v], cvv[v] * h[v]);
+                o_dxa[v] = dyv * Dv[v];
+                o_dc[v] = dtot * h[v];
+                o_dz[v] = dov[v] * yv * (sg * fmaf(zv[v], 1.f - sg, 1.f));
+                accD[v] = fmaf(dyv, xv[v], accD[v]);
+            }
+            if (row < p.L) {
+                st_vec<T, V>(dxa_o + (size_t)t * p.Di, o_dxa);
+                st_vec<T, V>(dz_o + (size_t)t * p.Di, o_dz);
+                st_vec<T, V>(dc_o + (size_t)t * p.dbc_stride, o_dc);
+            }
+        }
+    }
+    TRACE_MARK(tile_lin, 4);
+
+    // ---- D: G entering the tile from the later tiles
+    for (int c = tid; c < Cs; c += blockDim.x)
+        gT[c] = MODE == MODE_APPLY ? gin_ws[((size_t)b * p.nchunks + j) * p.Di + c0 + c] : wait_incoming(p, tile_lin, c);
+    TRACE_MARK(tile_lin, 5);
+    __syncthreads();
+    TRACE_MARK(tile_lin, 6);
+
+    // ---- E: G entering this run from later runs, then the reverse sweep
     float accA[V];
     {
         float G[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) { G[v] = hT[cl + v]; accA[v] = 0.f; }
+        for (int v = 0; v < V; ++v) { G[v] = gT[cl + v]; accA[v] = 0.f; }
+#pragma unroll 4
         for (int i = n_s - 1; i > i_run; --i) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) G[v] = fmaf(G[v], sP[i * Cs + cl + v], sS[i * Cs + cl + v]);
+            const float4 pp = *reinterpret_cast<const float4*>(sP + i * Cs + cl), ss = *reinterpret_cast<const float4*>(sS + i * Cs + cl);
+            G[0] = fmaf(G[0], pp.x, ss.x); G[1] = fmaf(G[1], pp.y, ss.y); G[2] = fmaf(G[2], pp.z, ss.z); G[3] = fmaf(G[3], pp.w, ss.w);
         }
         float q[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) q[v] = anext[v] * G[v];
-        T* db_o = reinterpret_cast<T*>(p.dBm);
+        const size_t tok0 = (size_t)b * p.L + row0 + i_run * TS;
+        T* db_o = reinterpret_cast<T*>(p.dBm) + tok0 * p.dbc_stride + c0 + cl;
         const int nparts = p.Di / V;
+        float* dd_o = p.ddlog_parts + tok0 * nparts + (c0 + cl) / V;
 #pragma unroll
         for (int t = TS - 1; t >= 0; --t) {
             const int row = row0 + i_run * TS + t;
@@ -683,27 +851,27 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
                 q[v] = a[t][v] * Gt;
             }
             if (row < p.L) {
-                st_vec<T, V>(db_o + ((size_t)b * p.L + row) * p.dbc_stride + c0 + cl, o_db);
+                st_vec<T, V>(db_o + (size_t)t * p.dbc_stride, o_db);
                 // d delta = sum_n e * A  (A = A2 / log2e);  d dlog = d delta * sigmoid(dlog) = d delta * (1 - exp(-delta))
                 const float sp = 1.f - __expf(-dl[t]);
-                p.ddlog_parts[((size_t)b * p.L + row) * nparts + (c0 + cl) / V] = dd * (1.f / AB_LOG2E) * sp;
+                dd_o[(size_t)t * nparts] = dd * (1.f / AB_LOG2E) * sp;
             }
         }
     }
-    __syncthreads();     // reverse-prefix reads of sP/sS done
-    // ---- per-tile partial sums of dA_log (= A * sum e*delta) and dD
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        sP[i_run * Cs + cl + v] = accA[v] * A2[v] * (1.f / AB_LOG2E);
-        sS[i_run * Cs + cl + v] = accD[v];
-    }
+    // ---- per-tile partial sums of dA_log (= A * sum e*delta) and dD; the forward aggregates are dead (every thread is
+    //      past phase C once it left the barrier above)
+    *reinterpret_cast<float4*>(fP + i_run * Cs + cl) = make_float4(accA[0] * A2[0] * (1.f / AB_LOG2E), accA[1] * A2[1] * (1.f / AB_LOG2E),
+                                                                  accA[2] * A2[2] * (1.f / AB_LOG2E), accA[3] * A2[3] * (1.f / AB_LOG2E));
+    *reinterpret_cast<float4*>(fS + i_run * Cs + cl) = make_float4(accD[0], accD[1], accD[2], accD[3]);
     __syncthreads();
     for (int c = tid; c < Cs; c += blockDim.x) {
         float sa = 0.f, sd = 0.f;
-        for (int i = 0; i < n_s; ++i) { sa += sP[i * Cs + c]; sd += sS[i * Cs + c]; }
+#pragma unroll 4
+        for (int i = 0; i < n_s; ++i) { sa += fP[i * Cs + c]; sd += fS[i * Cs + c]; }
         p.part[(tile_lin * 2 + 0) * Cs + c] = sa;
         p.part[(tile_lin * 2 + 1) * Cs + c] = sd;
     }
+    TRACE_MARK(tile_lin, 7);
 }
 
 // dA_log[c], dD[c] = sum over (b, j) of the tile partials; one warp per channel, fixed order -> deterministic
@@ -760,14 +928,14 @@ int make_map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di,
                           dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
-size_t smem_bytes(const ScanTiling& t, int ntiles_staged_max) {
+size_t smem_bytes(const ScanTiling& t, int ntiles_staged, bool bwd) {
     const size_t tile_bytes = (size_t)t.T * t.Cs * t.esize;
     const size_t pitch = (tile_bytes + 127) / 128 * 128;
     const int nh_max = t.Cs / 16 + 2;
-    size_t o = ntiles_staged_max * pitch;
-    o += (size_t)(t.T + 1) * nh_max * 4;
-    o += (size_t)2 * t.n_s * t.Cs * 4;
-    o += (size_t)t.Cs * 4 + 8 + 16;
+    size_t o = (size_t)ntiles_staged * pitch;
+    o += (size_t)sdel_floats(t.T, nh_max) * 4;
+    o += (size_t)(bwd ? 4 : 2) * t.n_s * t.Cs * 4;      // run aggregates (the backward keeps forward and reverse ones)
+    o += (size_t)(bwd ? 2 : 1) * t.Cs * 4 + 8 + 32;
     return o;
 }
 
@@ -781,32 +949,58 @@ bool single_pass_ok(int B, const ScanTiling& t, int threads) {
     return scanner_ctas(q, threads) <= ab_num_sms();
 }
 
-template <typename T, int MODE>
-int launch_fwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
-    const size_t smem = smem_bytes(t, n_staged);
-    auto kfn = scan_fwd_kernel<T, MODE>;
+template <typename K>
+int prepare_kernel(K kfn, size_t smem) {
     AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = t.n_s * (t.Cs / (16 / (int)sizeof(T)));
-    ScanParams q = p;
-    q.n_scan = MODE == MODE_FUSED ? scanner_ctas(p, threads) : 0;
-    const unsigned grid = (unsigned)(p.nchains * p.nchunks + q.n_scan);
-    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], q);
-    AB_LAUNCH_CHECK();
+    // without this the driver may pick a carve-out that admits fewer CTAs per SM than the shared memory allows
+    AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return AB_OK;
 }
 
-template <typename T, int MODE>
-int launch_bwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, float* gin, cudaStream_t st) {
-    const size_t smem = smem_bytes(t, 5);
-    auto kfn = scan_bwd_kernel<T, MODE>;
-    AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = t.n_s * (t.Cs / 4);
+template <typename T, int MODE, int V, int CS>
+int launch_fwd_cs(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
     ScanParams q = p;
+    const size_t smem = smem_bytes(t, n_staged, false);
+    auto kfn = scan_fwd_kernel<T, MODE, V, CS>;
+    if (int e = prepare_kernel(kfn, smem)) return e;
+    const int threads = t.n_s * (t.Cs / V);
     q.n_scan = MODE == MODE_FUSED ? scanner_ctas(p, threads) : 0;
-    const unsigned grid = (unsigned)(p.nchains * p.nchunks + q.n_scan);
-    kfn<<<grid, threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], q, gin);
+    kfn<<<(unsigned)(p.nchains * p.nchunks + q.n_scan), threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], q);
     AB_LAUNCH_CHECK();
     return AB_OK;
+}
+// slab widths with a specialised kernel: 64 (d_inner a multiple of 64) and 88 (the 1.5B text block, d_inner 176)
+template <typename T, int MODE, int V>
+int launch_fwd_v(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
+    if (t.Cs == 64) return launch_fwd_cs<T, MODE, V, 64>(maps, p, t, n_staged, st);
+    if (t.Cs == 88) return launch_fwd_cs<T, MODE, V, 88>(maps, p, t, n_staged, st);
+    return launch_fwd_cs<T, MODE, V, 0>(maps, p, t, n_staged, st);
+}
+template <typename T, int MODE>
+int launch_fwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
+    if constexpr (sizeof(T) == 2) {
+        if (t.V_f == 8) return launch_fwd_v<T, MODE, 8>(maps, p, t, n_staged, st);
+    }
+    return launch_fwd_v<T, MODE, 4>(maps, p, t, n_staged, st);
+}
+
+template <typename T, int MODE, int CS>
+int launch_bwd_cs(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, float* gin, cudaStream_t st) {
+    ScanParams q = p;
+    const size_t smem = smem_bytes(t, 5, true);
+    auto kfn = scan_bwd_kernel<T, MODE, CS>;
+    if (int e = prepare_kernel(kfn, smem)) return e;
+    const int threads = t.n_s * (t.Cs / 4);
+    q.n_scan = MODE == MODE_FUSED ? scanner_ctas(p, threads) : 0;
+    kfn<<<(unsigned)(p.nchains * p.nchunks + q.n_scan), threads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], q, gin);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+template <typename T, int MODE>
+int launch_bwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, float* gin, cudaStream_t st) {
+    if (t.Cs == 64) return launch_bwd_cs<T, MODE, 64>(maps, p, t, gin, st);
+    if (t.Cs == 88) return launch_bwd_cs<T, MODE, 88>(maps, p, t, gin, st);
+    return launch_bwd_cs<T, MODE, 0>(maps, p, t, gin, st);
 }
 
 int check_common(int B, int L, int Di, int H, int dtype, ScanTiling& t) {
@@ -871,7 +1065,7 @@ extern "C" int ab_selective_scan_fwd(const void* xa, const void* dlog, const voi
     }
     if (int e = f32 ? launch_fwd_mode<float, MODE_AGG>(maps, p, t, 1, stream)
                     : launch_fwd_mode<__nv_bfloat16, MODE_AGG>(maps, p, t, 1, stream)) return e;
-    scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, 128), 128, 0, stream>>>(p.aggP, p.aggS, h0, hstart, h_last, B, Di,
+    scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, COMB_CH), COMB_CH * COMB_SEG, 0, stream>>>(p.aggP, p.aggS, h0, hstart, h_last, B, Di,
                                                                                    t.Cs, t.nslab, t.nchunks, 0);
     AB_LAUNCH_CHECK();
     p.h_last = nullptr;
@@ -925,7 +1119,7 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
     } else {
         if (int e = f32 ? launch_bwd_mode<float, MODE_AGG>(maps, p, t, gin, stream)
                         : launch_bwd_mode<__nv_bfloat16, MODE_AGG>(maps, p, t, gin, stream)) return e;
-        scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, 128), 128, 0, stream>>>(p.aggP, p.aggS, nullptr, gin, nullptr, B,
+        scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, COMB_CH), COMB_CH * COMB_SEG, 0, stream>>>(p.aggP, p.aggS, nullptr, gin, nullptr, B,
                                                                                        Di, t.Cs, t.nslab, t.nchunks, 1);
         AB_LAUNCH_CHECK();
         if (int e = f32 ? launch_bwd_mode<float, MODE_APPLY>(maps, p, t, gin, stream)
@@ -935,3 +1129,17 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
+
+#ifdef AB_SCAN_TRACE
+extern "C" int ab_scan_trace_dump(unsigned long long* host, int ntiles) {
+    if (ntiles > TRACE_TILES) ntiles = TRACE_TILES;
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(host, g_scan_trace, (size_t)ntiles * TRACE_SLOTS * sizeof(unsigned long long));
+}
+extern "C" int ab_scanner_trace_dump(unsigned long long* host, int clear) {
+    cudaDeviceSynchronize();
+    int rc = (int)cudaMemcpyFromSymbol(host, g_scanner_trace, sizeof(unsigned long long) * 64 * STRACE_ROUNDS * 4);
+    if (clear) { void* d; cudaGetSymbolAddress(&d, g_scanner_trace); cudaMemset(d, 0, sizeof(unsigned long long) * 64 * STRACE_ROUNDS * 4); }
+    return rc;
+}
+#endif

@@ -98,14 +98,16 @@ def test_selective_scan_modes_agree_and_deterministic():
     xa, z, BC, dlog = mk(B, L, Di), mk(B, L, Di), mk(B, L, 2 * Di), (torch.randn(B, L, H, generator=g) - 3).to(dev(), torch.bfloat16)
     A_log = (torch.rand(H, 16, generator=g) * 0.6 - 0.7).to(dev())
     D = torch.ones(Di, device=dev())
-    # both schedules compose the tile aggregates in strict token order: bitwise equal and reproducible
+    # each schedule composes the tile aggregates in a fixed order: bitwise reproducible; the two schedules associate the
+    # cross-tile products differently (the two-pass combine works on segments), so they agree to fp32 rounding only
     outs = [ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=m)[0] for m in (1, 1, 0, 0)]
     assert torch.equal(outs[0], outs[1]), "two-pass scan is not bitwise deterministic"
     assert torch.equal(outs[2], outs[3]), "single-pass scan is not bitwise deterministic"
-    assert torch.equal(outs[0], outs[2]), "single-pass and two-pass scans differ"
+    assert rel_err(outs[0].float(), outs[2].float()) < 8e-3, "single-pass and two-pass scans differ"   # one bf16 ulp
     xa32, z32, BC32, dl32 = xa.float(), z.float(), BC.float(), dlog.float()
-    o32 = [ops.selective_scan(xa32, dl32, BC32, z32, A_log, D, mode=m)[0] for m in (1, 0, 0)]
-    assert torch.equal(o32[1], o32[0]) and torch.equal(o32[2], o32[0])
+    o32 = [ops.selective_scan(xa32, dl32, BC32, z32, A_log, D, mode=m)[0] for m in (1, 1, 0, 0)]
+    assert torch.equal(o32[0], o32[1]) and torch.equal(o32[2], o32[3])
+    assert rel_err(o32[0], o32[2]) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------
