@@ -42,7 +42,7 @@ int make_tiling(int L, int Di, int dtype, ScanTiling& t) {
     t.esize = dtype == AB_F32 ? 4 : 2;
     t.V_f = getenv("AB_SCAN_VF8") ? 16 / t.esize : 4;
     t.V_b = 4;
-    const int unit = t.V_f > t.V_b ? t.V_f : t.V_b;
+    const int unit = 16 / t.esize > t.V_b ? 16 / t.esize : t.V_b;    // slab rows are whole 16-byte units (TMA box)
     int Cs = 0;
     for (int k = Di / unit; k >= 1; --k) {           // smallest slab first
         if (Di % k) continue;
