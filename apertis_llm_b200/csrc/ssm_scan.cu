@@ -11,16 +11,19 @@
 // of TS=4 tokens; run aggregates (P = prod abar, S = state contribution) are combined across runs in
 // shared memory.  Across tiles of a sequence the incoming state is resolved
 //   * single pass: each tile publishes (P, S) per channel as two self-validating 64-bit words
-//     {epoch|status, fp32}.  A few dedicated SCANNER warps (the first tickets; lane = channel) walk the
-//     tiles of their chain in order, h <- P*h + S, with the aggregate words of the next tiles
-//     prefetched, and publish every tile's incoming state as one more tagged word the tile spins on.
-//     The wait per tile is O(1) regardless of how many tiles of a chain are in flight, the association
-//     is the strict token order (bitwise deterministic, identical to the two-pass mode), and there is no
-//     deadlock by construction: CTAs take their role/tile from an atomic ticket, so the scanners and
-//     every predecessor tile are resident or finished before a tile can wait on them.
-//   * two pass: aggregate kernel -> sequential combine kernel -> apply kernel.
-// The backward recomputes the in-tile states from the saved per-tile incoming state (hstart) and runs
-// the same machinery in reverse time for G_t = g_t + abar_{t+1} G_{t+1}.
+//     {epoch|status, fp32}.  One SCANNER CTA per chain (the first tickets) polls the aggregate words of the
+//     next tiles into a shared-memory ring, composes them in token order (its threads split every round
+//     into consecutive segments that are chained through shared memory) and publishes every tile's
+//     incoming state as one more tagged word the tile spins on.  The wait per tile is O(1) regardless of
+//     how many tiles of a chain are in flight, the composition order is fixed (bitwise reproducible), and
+//     there is no deadlock by construction: CTAs take their role/tile from an atomic ticket, so the
+//     scanners and every predecessor tile are resident or finished before a tile can wait on them.
+//   * two pass: aggregate kernel -> segmented combine kernel -> apply kernel (no inter-CTA waits; used when
+//     there are more chains than SMs, and selectable for debugging).
+// The backward recomputes the in-tile states from the saved per-tile incoming state (hstart) and runs the
+// same machinery in reverse time for G_t = g_t + abar_{t+1} G_{t+1}; the reverse aggregates are published
+// first, so the hand-shake overlaps the forward recompute.
+// tools/scan_trace.py (with `make TRACE=1`) prints the per-phase timeline of the tiles and the scanner.
 #include "common.cuh"
 
 namespace {
@@ -40,7 +43,7 @@ struct ScanTiling {
 
 int make_tiling(int L, int Di, int dtype, ScanTiling& t) {
     t.esize = dtype == AB_F32 ? 4 : 2;
-    t.V_f = getenv("AB_SCAN_VF8") ? 16 / t.esize : 4;
+    t.V_f = 4;
     t.V_b = 4;
     const int unit = 16 / t.esize > t.V_b ? 16 / t.esize : t.V_b;    // slab rows are whole 16-byte units (TMA box)
     int Cs = 0;
@@ -139,102 +142,132 @@ __device__ __forceinline__ float wait_incoming(const ScanParams& p, size_t tile_
 }
 
 // Scanner role.  One CTA per chain (b, slab); DIR = +1 walks chunk 0 -> last (forward scan, starts from h0),
-// DIR = -1 walks last -> 0 (reverse scan of the backward, starts from 0).  For every tile it first publishes the
-// incoming state (which does not depend on the tile's own aggregate), then consumes the tile's (P, S).
-// Fast path (one channel per thread): every round polls the aggregate words of the next SCAN_K tiles with cp.async
-// into a shared-memory ring (the tile buffers are free in a scanner CTA) and consumes the valid prefix, so up to
-// SCAN_K tiles advance per L2 round trip without holding registers.
+// DIR = -1 walks last -> 0 (reverse scan of the backward, starts from 0).  It publishes, for every tile, the state
+// entering it (which does not depend on the tile's own aggregate).
+// Fast path: the CTA's threads form R replicas of the slab's channels.  Every round polls the aggregate words of the
+// next K tiles with cp.async into a shared-memory ring (the tile buffers are free in a scanner CTA), K / R consecutive
+// tiles per replica.  Each replica composes the valid prefix of its segment, the segment aggregates are chained
+// through shared memory (every thread derives the same new head and state), and each replica then walks its own
+// segment again to publish the per-tile states: loads, FMA chains and stores of a round are spread over R warps sets.
+// The composition order is fixed by the tile order, so results are bitwise reproducible.
 template <int DIR>
-__device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem [K][Cs]*/, int K /*ring depth, power of two, 0 = none*/) {
+__device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem below hs*/, size_t ring_bytes) {
     const int n = p.nchunks, Cs = p.Cs;
     const int slab = chain % p.nslab, b = chain / p.nslab;
-    const int c = threadIdx.x;
     int spins = 0;
-    if ((int)blockDim.x >= Cs && K >= 4) {
-        if (c >= Cs) return;
+    int R = (int)blockDim.x / Cs;
+    R = R >= 4 ? 4 : (R >= 2 ? 2 : R);
+    // shared memory: ring [K][Cs] uint4, then segP / segS / segN [R][Cs]
+    const size_t seg_bytes = (size_t)3 * 4 * Cs * sizeof(float);
+    const int K = ring_bytes > seg_bytes ? ring_depth(ring_bytes - seg_bytes, Cs) : 0;
+    if (R >= 1 && K >= 8) {
+        const int S = K / R;                           // tiles per replica and round (>= 2)
+        float* segP = reinterpret_cast<float*>(ring + (size_t)K * Cs);
+        float* segS = segP + 4 * Cs;
+        int* segN = reinterpret_cast<int*>(segS + 4 * Cs);
+        const int c = threadIdx.x % Cs, r = threadIdx.x / Cs;
+        const bool active = r < R;
         const int cg = slab * Cs + c;
         float h = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + cg] : 0.f;
-        // ring[k][thread] in shared memory, filled by cp.async (no registers held while the loads are in flight)
         uint4* myring = ring + c;
-        const int pitch = Cs;
         unsigned long long* incl_base = p.inclw + (size_t)chain * n * Cs + c;
+        const unsigned long long* word_base = p.words + ((size_t)chain * n * Cs + c) * 2;
         const unsigned long long tag_incl = (unsigned long long)((p.epoch << 2) | ST_INCL) << 32;
-        int head = 0;
+        if (r == 0) ab_st_relaxed_u64_unordered(incl_base + (size_t)(DIR > 0 ? 0 : n - 1) * Cs, tag_incl | __float_as_uint(h));
+        // Fixed two-level association (independent of timing, hence bitwise reproducible): the chain is cut into
+        // aligned segments of S tiles; H(g+1) = Pseg(g) * H(g) + Sseg(g) with the segment aggregate composed in tile
+        // order, and the states inside a segment follow sequentially from H(g).
+        int gh = 0;                                    // first segment that is not folded into h yet
+        const int nseg = (n + S - 1) / S;
 #ifdef AB_SCAN_TRACE
         int round = 0;
-        long long cyc_chain = 0, cyc_store = 0, n_iter = 0;
 #endif
-        while (head < n) {
-            const int hi = min(head + K, n);
+        while (gh < nseg) {
 #ifdef AB_SCAN_TRACE
             const unsigned long long tr0 = gtime();
-            const int head0 = head;
 #endif
-            for (int s2 = head; s2 < hi; ++s2) {
+            const int lo = min((gh + r) * S, n), hi = active ? min(lo + S, n) : lo;     // my segment of this round
+            for (int s2 = lo; s2 < hi; ++s2) {
                 const int j = DIR > 0 ? s2 : n - 1 - s2;
-                const unsigned long long* w = p.words + (((size_t)chain * n + j) * Cs + c) * 2;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ab_smem_u32(myring + (size_t)(s2 & (K - 1)) * pitch)), "l"(w) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ab_smem_u32(myring + (size_t)(s2 & (K - 1)) * Cs)),
+                             "l"(word_base + (size_t)j * Cs * 2) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            {   // the state entering tile `head` is known now: publish it while the loads fly
-                const int j = DIR > 0 ? head : n - 1 - head;
-                ab_st_relaxed_u64(p.inclw + ((size_t)chain * n + j) * Cs + c, pack_word(p.epoch, ST_INCL, h));
-            }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #ifdef AB_SCAN_TRACE
             const unsigned long long tr1 = gtime();
 #endif
-            bool stop = false;
-            while (head < hi && !stop) {
-                // 8 ring slots at a time: loads, then the dependent FMA chain over the valid prefix, then the stores
-                uint4 w4[8];
-#ifdef AB_SCAN_TRACE
-                const long long ck0 = clock64();
-#endif
-#pragma unroll
-                for (int u = 0; u < 8; ++u) w4[u] = myring[(size_t)((head + u) & (K - 1)) * pitch];
-                float hv[8];
-                int m = 0;
+            // valid prefix of my segment and its aggregate
+            float Pa = 1.f, Sa = 0.f;
+            int cnt = 0;
+            {
                 bool ok = true;
+                for (int u0 = lo; u0 < hi && ok; u0 += 8) {
+                    uint4 w4[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    ok = ok && head + u < hi && (w4[u].y >> 2) == p.epoch && (w4[u].w >> 2) == p.epoch;
-                    if (ok) { h = fmaf(__uint_as_float(w4[u].x), h, __uint_as_float(w4[u].z)); m = u + 1; }
-                    hv[u] = h;
-                }
-#ifdef AB_SCAN_TRACE
-                const long long ck1 = clock64();
-#endif
+                    for (int u = 0; u < 8; ++u) w4[u] = myring[(size_t)((u0 + u) & (K - 1)) * Cs];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int jn = head + u + 1;            // hv[u] is the state entering tile jn
-                    if (u < m && jn < n) {
-                        const int j = DIR > 0 ? jn : n - 1 - jn;
-                        ab_st_relaxed_u64_unordered(incl_base + (size_t)j * Cs, tag_incl | __float_as_uint(hv[u]));
+                    for (int u = 0; u < 8; ++u) {
+                        ok = ok && u0 + u < hi && (w4[u].y >> 2) == p.epoch && (w4[u].w >> 2) == p.epoch;
+                        if (ok) {
+                            Sa = fmaf(__uint_as_float(w4[u].x), Sa, __uint_as_float(w4[u].z));
+                            Pa *= __uint_as_float(w4[u].x);
+                            ++cnt;
+                        }
                     }
                 }
-                head += m;
-                stop = m < 8 && head < hi;
-#ifdef AB_SCAN_TRACE
-                const long long ck2 = clock64();
-                cyc_chain += ck1 - ck0; cyc_store += ck2 - ck1; ++n_iter;
-#endif
             }
+            const bool full = cnt == hi - lo;          // every tile of the segment has published
+            if (active) { segP[r * Cs + c] = Pa; segS[r * Cs + c] = Sa; segN[r * Cs + c] = full ? 1 : 0; }
+            __syncthreads();
+            // chain the complete segments: every replica of a channel derives the same new gh / state
+            float hin = h, hnew = h;
+            bool reach = true, mine = false;
+            int adv = 0;
+            for (int r2 = 0; r2 < R; ++r2) {
+                if (r2 == r) { hin = hnew; mine = reach; }
+                if (reach && gh + r2 < nseg && segN[r2 * Cs + c]) {
+                    hnew = fmaf(segP[r2 * Cs + c], hnew, segS[r2 * Cs + c]);
+                    ++adv;
+                } else {
+                    reach = false;
+                }
+            }
+            // publish the states entering the tiles behind my valid prefix (idempotent when a segment is polled again)
+            if (mine) {
+                float hh = hin;
+                for (int u0 = 0; u0 < cnt; u0 += 8) {
+                    uint4 w4[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) w4[u] = myring[(size_t)((lo + u0 + u) & (K - 1)) * Cs];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int jn = lo + u0 + u + 1;             // state entering tile jn
+                        if (u0 + u < cnt) {
+                            hh = fmaf(__uint_as_float(w4[u].x), hh, __uint_as_float(w4[u].z));
+                            // the first tile of the next segment gets H(g+1) exactly as the chain carries it on
+                            const float hv = (full && jn == hi) ? fmaf(Pa, hin, Sa) : hh;
+                            if (jn < n) ab_st_relaxed_u64_unordered(incl_base + (size_t)(DIR > 0 ? jn : n - 1 - jn) * Cs, tag_incl | __float_as_uint(hv));
+                        }
+                    }
+                }
+            }
+            gh += adv;
+            h = hnew;
 #ifdef AB_SCAN_TRACE
-            if (c == 0 && chain < 64 && round < STRACE_ROUNDS) {
+            if (threadIdx.x == 0 && chain < 64 && round < STRACE_ROUNDS) {
                 unsigned long long* o = g_scanner_trace + ((size_t)chain * STRACE_ROUNDS + round) * 4;
-                o[0] = tr0; o[1] = tr1; o[2] = gtime(); o[3] = (unsigned long long)(head - head0);
+                o[0] = tr0; o[1] = tr1; o[2] = gtime(); o[3] = (unsigned long long)(adv * S);
             }
             ++round;
 #endif
-            if (stop && ++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+            if (adv == 0 && ++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+            __syncthreads();        // ring slots and segment words are rewritten next round
         }
-#ifdef AB_SCAN_TRACE
-        if (c == 0 && chain == 0) printf("scanner chain 0: %lld consume iterations, %lld cycles load+chain, %lld cycles stores per iteration\n", n_iter, cyc_chain / max(n_iter, 1LL), cyc_store / max(n_iter, 1LL));
-#endif
-        if (DIR > 0 && p.h_last) p.h_last[(size_t)b * p.Di + cg] = h;
+        if (DIR > 0 && p.h_last && r == 0) p.h_last[(size_t)b * p.Di + cg] = h;
         return;
     }
+    const int c = threadIdx.x;
     // generic path (blocks narrower than the slab: tiny sequences): state in shared memory, no prefetch
     for (int cc = c; cc < Cs; cc += blockDim.x) hs[cc] = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + slab * Cs + cc] : 0.f;
     for (int step = 0; step < n; ++step) {
@@ -345,7 +378,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ScanParams& p, int tile, 
 // smem: [NT tiles of T x Cs] [sdel: (T+1) x nh] [sP, sS: n_s x Cs] [hT: Cs] [mbarrier]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int V, int CS>
-__global__ void __launch_bounds__(V == 4 ? 256 : 128, V == 4 ? 4 : 6) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
+__global__ void __launch_bounds__(256, 4) scan_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
                                                           const __grid_constant__ CUtensorMap tm_b,
                                                           const __grid_constant__ CUtensorMap tm_c,
                                                           const __grid_constant__ CUtensorMap tm_z, const ScanParams p) {
@@ -373,7 +406,7 @@ __global__ void __launch_bounds__(V == 4 ? 256 : 128, V == 4 ? 4 : 6) scan_fwd_k
     int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
         if (tile < p.n_scan) {
-            scanner_role<+1>(p, tile, hT, reinterpret_cast<uint4*>(smem), ring_depth((size_t)NT * pitch, Cs));
+            scanner_role<+1>(p, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
             return;
         }
         tile -= p.n_scan;
@@ -594,7 +627,7 @@ __global__ void __launch_bounds__(COMB_CH * COMB_SEG) scan_combine_kernel(
 // smem: [5 tiles of T x Cs] [sdel: (T+1) x nh] [sP, sS, fP, fS: n_s x Cs] [hT, gT: Cs] [mbarrier]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CS>
-__global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
+__global__ void __launch_bounds__(256, 3) scan_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa,
                                                        const __grid_constant__ CUtensorMap tm_b,
                                                        const __grid_constant__ CUtensorMap tm_c,
                                                        const __grid_constant__ CUtensorMap tm_z,
@@ -629,7 +662,7 @@ __global__ void __launch_bounds__(256) scan_bwd_kernel(const __grid_constant__ C
     int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
         if (tile < p.n_scan) {
-            scanner_role<-1>(p, tile, hT, reinterpret_cast<uint4*>(smem), ring_depth((size_t)NT * pitch, Cs));
+            scanner_role<-1>(p, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
             return;
         }
         tile -= p.n_scan;
@@ -978,9 +1011,6 @@ int launch_fwd_v(const CUtensorMap* maps, const ScanParams& p, const ScanTiling&
 }
 template <typename T, int MODE>
 int launch_fwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, int n_staged, cudaStream_t st) {
-    if constexpr (sizeof(T) == 2) {
-        if (t.V_f == 8) return launch_fwd_v<T, MODE, 8>(maps, p, t, n_staged, st);
-    }
     return launch_fwd_v<T, MODE, 4>(maps, p, t, n_staged, st);
 }
 
