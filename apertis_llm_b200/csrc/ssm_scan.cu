@@ -907,25 +907,45 @@ __global__ void __launch_bounds__(256, 3) scan_bwd_kernel(const __grid_constant_
     TRACE_MARK(tile_lin, 7);
 }
 
-// dA_log[c], dD[c] = sum over (b, j) of the tile partials; one warp per channel, fixed order -> deterministic
-__global__ void __launch_bounds__(256) scan_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dA,
-                                                                float* __restrict__ dD, int B, int Di, int Cs, int nslab,
-                                                                int nchunks) {
-    const int cg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (cg >= Di) return;
-    const int slab = cg / Cs, c = cg % Cs;
+// dA_log[c], dD[c] = sum over (b, j) of the tile partials.  A block owns PR_CH channels (adjacent threads = adjacent
+// channels: coalesced rows); PR_Q threads per channel each add every PR_Q-th tile, then one thread per channel adds
+// the PR_Q partial sums in index order: fixed order -> deterministic.
+constexpr int PR_CH = 16, PR_Q = 64;
+__global__ void __launch_bounds__(PR_CH * PR_Q) scan_param_reduce_kernel(const float* __restrict__ part, float* __restrict__ dA,
+                                                                         float* __restrict__ dD, int B, int Di, int Cs, int nslab,
+                                                                         int nchunks) {
+    __shared__ float sA[PR_Q][PR_CH], sD[PR_Q][PR_CH];
+    const int cx = threadIdx.x % PR_CH, q = threadIdx.x / PR_CH;
+    const int cg = blockIdx.x * PR_CH + cx;
     float sa = 0.f, sd = 0.f;
-    const int n = B * nchunks;
-    for (int i = lane; i < n; i += 32) {
-        const int b = i / nchunks, j = i % nchunks;
-        const size_t tl = (size_t)(b * nslab + slab) * nchunks + j;
-        sa += part[(tl * 2 + 0) * Cs + c];
-        sd += part[(tl * 2 + 1) * Cs + c];
+    if (cg < Di) {
+        const int slab = cg / Cs, c = cg % Cs;
+        const int n = B * nchunks;
+        for (int i0 = q; i0 < n; i0 += PR_Q * 4) {
+            float va[4], vd[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * PR_Q;
+                va[u] = 0.f; vd[u] = 0.f;
+                if (i < n) {
+                    const int b = i / nchunks, j = i % nchunks;
+                    const size_t tl = (size_t)(b * nslab + slab) * nchunks + j;
+                    va[u] = part[(tl * 2 + 0) * Cs + c];
+                    vd[u] = part[(tl * 2 + 1) * Cs + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { sa += va[u]; sd += vd[u]; }
+        }
     }
-    sa = ab_warp_sum(sa);
-    sd = ab_warp_sum(sd);
-    if (lane == 0) { dA[cg] = sa; dD[cg] = sd; }
+    sA[q][cx] = sa; sD[q][cx] = sd;
+    __syncthreads();
+    if (q == 0 && cg < Di) {
+        float ta = 0.f, td = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < PR_Q; ++i) { ta += sA[i][cx]; td += sD[i][cx]; }
+        dA[cg] = ta; dD[cg] = td;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1155,7 +1175,7 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
         if (int e = f32 ? launch_bwd_mode<float, MODE_APPLY>(maps, p, t, gin, stream)
                         : launch_bwd_mode<__nv_bfloat16, MODE_APPLY>(maps, p, t, gin, stream)) return e;
     }
-    scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, 8), 256, 0, stream>>>(p.part, dA_log, dD, B, Di, t.Cs, t.nslab, t.nchunks);
+    scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, PR_CH), PR_CH * PR_Q, 0, stream>>>(p.part, dA_log, dD, B, Di, t.Cs, t.nslab, t.nchunks);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
