@@ -212,9 +212,9 @@ class AdaptiveExpertSystem(nn.Module):
         if module.num_experts <= 0:
             return state_dict
         base = module.ep_rank * module.local_experts
-        for name, suffix in module._STACKED.items():
-            t = state_dict.pop(prefix + name)
-            for e in range(module.local_experts):
+        stacked = {suffix: state_dict.pop(prefix + name) for name, suffix in module._STACKED.items()}
+        for e in range(module.local_experts):                 # expert-major, like the reference's ModuleList
+            for suffix, t in stacked.items():
                 state_dict[f"{prefix}experts.{base + e}.{suffix}"] = t[e]
         return state_dict
 

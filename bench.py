@@ -22,6 +22,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import torch
@@ -46,24 +47,65 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML polled from a thread every ~2 ms
+    (nvidia-smi's fastest loop is too coarse for a region of tens of milliseconds); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop = threading.Event()
+        self.thread = None
         self.p = None
+        self.f = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        try:
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop.wait(0.002)
 
     def __enter__(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return self
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except Exception:
             self.p = None
         return self
 
     def __exit__(self, *a):
+        self.stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         if self.p is not None:
             self.p.terminate()
             try:
@@ -72,27 +114,29 @@ class ClockSampler:
                 self.p.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        try:
-            self.f.flush()
-            for line in open(self.f.name):
-                c = [t.strip() for t in line.split(",")]
-                if len(c) < 8:
-                    continue
-                try:
-                    sm.append(float(c[1])); mx.append(float(c[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.f.name)
-        except Exception:
-            pass
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
+        if self.f is not None:
+            try:
+                self.f.flush()
+                for line in open(self.f.name):
+                    c = [t.strip() for t in line.split(",")]
+                    if len(c) < 8:
+                        continue
+                    try:
+                        sm.append(float(c[1])); mx.append(float(c[2]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                os.unlink(self.f.name)
+            except Exception:
+                pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         busy = [s for s in sm if s > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def cpu_reference_arm(args, wl, steps, warmup, sample_tokens):
