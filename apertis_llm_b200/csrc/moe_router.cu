@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
     float* cvec = G + (size_t)E * Dm;   // [E]
     float* red = cvec + 32;        // [WARPS][2E+1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < E * Dm; i += blockDim.x) G[i] = ln_w[i % Dm] * Wr[i];
+    for (int e = 0; e < E; ++e)
+        for (int d = tid; d < Dm; d += blockDim.x) G[(size_t)e * Dm + d] = ln_w[d] * Wr[(size_t)e * Dm + d];
     for (int e = warp; e < E; e += WARPS) {
         float acc = 0.f;
         for (int d = lane; d < Dm; d += 32) acc = fmaf(ln_b[d], Wr[(size_t)e * Dm + d], acc);
@@ -362,15 +363,36 @@ __global__ void router_param_kernel(const float* __restrict__ qpart, int nqb, co
                                     float* __restrict__ dln_b, float* __restrict__ dnoise_scale, int Dm, int E) {
     __shared__ float sdb[64];
     __shared__ float sgw[32][33], sgb[32][33];
+    __shared__ float spart[16][64];
     const int tx = threadIdx.x, e = threadIdx.y;
     const int tid = e * 32 + tx;
-    if (tid < 2 * E) {
-        float s = 0.f;
-        for (int r = 0; r < nparts; ++r) s += part[(size_t)r * 2 * E + tid];
-        sdb[tid] = s;
-        if (blockIdx.x == 0) {
-            if (tid < E) dbr[tid] = s;
-            else if (dnoise_scale) dnoise_scale[tid - E] = s;
+    const int nthr = 32 * E;
+    // column sums of the per-CTA partials: up to 16 thread groups add interleaved rows, then one thread per column adds
+    // the groups in index order (fixed order -> deterministic)
+    {
+        const int ncol = 2 * E;
+        const int ngrp = min(16, nthr / ncol);
+        const int col = tid % ncol, grp = tid / ncol;
+        if (grp < ngrp) {
+            float s = 0.f;
+            for (int r0 = grp; r0 < nparts; r0 += ngrp * 4) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = r0 + u * ngrp < nparts ? part[(size_t)(r0 + u * ngrp) * ncol + col] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s += v[u];
+            }
+            spart[grp][col] = s;
+        }
+        __syncthreads();
+        if (tid < ncol) {
+            float s = 0.f;
+            for (int g2 = 0; g2 < ngrp; ++g2) s += spart[g2][tid];
+            sdb[tid] = s;
+            if (blockIdx.x == 0) {
+                if (tid < E) dbr[tid] = s;
+                else if (dnoise_scale) dnoise_scale[tid - E] = s;
+            }
         }
     }
     __syncthreads();
@@ -378,7 +400,13 @@ __global__ void router_param_kernel(const float* __restrict__ qpart, int nqb, co
     float gw = 0.f, gb = 0.f;
     if (d < Dm) {
         float q = 0.f;
-        for (int r = 0; r < nqb; ++r) q += qpart[((size_t)r * E + e) * Dm + d];
+        for (int r0 = 0; r0 < nqb; r0 += 8) {
+            float qv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) qv[u] = r0 + u < nqb ? qpart[((size_t)(r0 + u) * E + e) * Dm + d] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) q += qv[u];
+        }
         const float wv = Wr[(size_t)e * Dm + d];
         dWr[(size_t)e * Dm + d] = fmaf(ln_w[d], q, ln_b[d] * sdb[e]);
         gw = wv * q;
