@@ -155,6 +155,11 @@ __device__ __forceinline__ bool ab_mbar_try_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void ab_mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!ab_mbar_try_wait(bar, parity)) {}
 }
+// same, for single-thread roles that run ahead of the rest of the CTA (TMA producer, MMA issuer): sleep between polls so
+// the spin does not take issue slots from the warps that share the scheduler
+__device__ __forceinline__ void ab_mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!ab_mbar_try_wait(bar, parity)) __nanosleep(40);
+}
 
 __device__ __forceinline__ void ab_prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
