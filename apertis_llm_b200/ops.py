@@ -232,7 +232,12 @@ def selective_scan(xa, dlog, BC, z, A_log, D, h0=None, want_yssm=False, want_hla
 
     xa, z [B,L,Di]; BC [B,L,2*Di] = [B-term | C-term]; dlog [B,L,H]; A_log [H,16]; D [Di]; h0 [B,H,16] or None.
     Returns (y [B,L,Di], y_ssm | None, h_last [B,Di] fp32 | None)."""
-    return _SelectiveScan.apply(xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, SCAN_MODE if mode is None else mode)
+    mode = SCAN_MODE if mode is None else mode
+    if torch.cuda.is_current_stream_capturing():
+        # the single-pass hand-shake validates its words with a launch epoch passed by value, which a replayed CUDA graph
+        # would freeze: captured steps use the two-pass schedule (no inter-CTA waits, nothing to validate)
+        mode = _lib.SCAN_TWO_PASS
+    return _SelectiveScan.apply(xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, mode)
 
 
 # --------------------------------------------------------------------------------------------

@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-sample-tokens", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as a CUDA graph (auto: use it when capture and a replay check succeed)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     Dm, H, I, E, K, seq = wl
@@ -271,22 +273,76 @@ def main():
         step(dev_x[i % nbuf])
     barrier()
 
-    # ---- timed region: device-resident inputs, CUDA events, per-kernel events for the roofline
+    # ---- optional: the whole step (forward, loss, backward, gradient all-reduce) captured once per input buffer as a CUDA
+    #      graph and replayed, which removes the host launch path from the step (the block is ~120 launches of 3-300 us)
+    graphs, graph_note = None, "off"
+    if args.graph != "off":
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    step(dev_x[i % nbuf])
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            pool = None
+            graphs = []
+            for i in range(nbuf):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    gl = step(dev_x[i])
+                pool = g.pool()
+                graphs.append((g, gl))
+            barrier()
+            eager = float(step(dev_x[0]))
+            graphs[0][0].replay()
+            replayed = float(graphs[0][1])
+            if not (replayed == replayed and abs(replayed - eager) <= 0.05 * abs(eager)):
+                raise RuntimeError(f"graph replay loss {replayed} vs eager {eager}")
+            graph_note = "on"
+        except Exception as ex:            # capture is an optimisation, never a requirement
+            graphs, graph_note = None, f"unavailable ({type(ex).__name__}: {str(ex)[:120]})"
+            if args.graph == "on":
+                raise
+            barrier()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % nbuf][0].replay()
+            return graphs[i % nbuf][1]
+        return step(dev_x[i % nbuf])
+
+    # ---- timed region: device-resident inputs, CUDA events
     timed_names = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_selective_scan_fwd", "ab_selective_scan_bwd"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count
+    for i in range(2):
+        run_step(i)
     with ClockSampler(local_rank) as clk:
         barrier()
-        _lib.start_timing(timed_names)
+        if graphs is None:
+            launches0 = _lib.launch_count
+            _lib.start_timing(timed_names)
         e0.record()
         for i in range(args.steps):
-            step(dev_x[i % nbuf])
+            run_step(i)
         e1.record()
         barrier()
-        per_kernel = _lib.stop_timing()
+        if graphs is None:
+            per_kernel = _lib.stop_timing()
+            launches = _lib.launch_count - launches0
     ms = e0.elapsed_time(e1) / args.steps
-    launches = _lib.launch_count - launches0
     clocks = clk.summary()
+    if graphs is not None:
+        # per-kernel CUDA events cannot be read inside a replayed graph: the same steps once more, eagerly, for the
+        # roofline figures and the launch count (the kernels and their inputs are identical)
+        barrier()
+        launches0 = _lib.launch_count
+        _lib.start_timing(timed_names)
+        for i in range(args.steps):
+            step(dev_x[i % nbuf])
+        barrier()
+        per_kernel = _lib.stop_timing()
+        launches = _lib.launch_count - launches0
     kept = int(layer.feed_forward.ffn.last_counts.sum().item())        # A_kept of the last step (rows through the experts)
 
     # ---- end to end: pinned host input -> device every step (prefetched on a copy stream), loss read back
@@ -311,9 +367,14 @@ def main():
         if i + 1 < args.steps:
             prefetch(i + 1)
         torch.cuda.current_stream().wait_event(ready[i % 2])
-        x = stage[i % 2].detach().requires_grad_(True)
-        loss = step(x)
-        consumed[i % 2].record()
+        if graphs is not None:
+            dev_x[i % nbuf].detach().copy_(stage[i % 2])           # the graph reads its own static input buffer
+            consumed[i % 2].record()
+            loss = run_step(i)
+        else:
+            x = stage[i % 2].detach().requires_grad_(True)
+            loss = step(x)
+            consumed[i % 2].record()
         last = loss.item()                              # device -> host read of the step's result
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -363,7 +424,7 @@ def main():
                           parallelism=("single GPU" if world == 1 else f"ep{world} (experts sharded, all-to-all) + dp{world}"),
                           precision="bf16 autocast over fp32 master weights" if amp else "fp32 (3x bf16-split tensor-core GEMMs)",
                           l2="inputs rotate over 4 buffers (%.0f MB > 126 MB L2); per-step activations ~GBs" % (nbuf * B * seq * Dm * 4 / 1e6)),
-           "clocks": clocks,
+           "clocks": clocks, "cuda_graph": graph_note,
            "e2e": {"value": tokens_per_step * world / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": B * seq * Dm * 4, "d2h_bytes_per_step": 4,
                    "how": "pinned host x -> device each step (prefetched on a copy stream), block fwd+bwd through the module API, loss.item()"},
