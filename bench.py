@@ -389,8 +389,20 @@ def main():
         kept_total = int(k.item())
     else:
         kept_total = kept
+    def shutdown():
+        """Multi-GPU exit without the collective teardown: the captured graphs hold NCCL work and the ranks leave at
+        different times (rank 0 still runs the CPU baseline), so destroy_process_group() can block; every timed and
+        reduced number is final before this point."""
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            if graphs is not None:
+                graphs.clear()
+            torch.cuda.synchronize()
+            os._exit(0)
+
     if rank != 0:
-        dist.destroy_process_group()
+        shutdown()
         return
 
     pk, pk_src = peaks()
@@ -433,8 +445,7 @@ def main():
         v, cms, cores, sample = cpu_reference_arm(args, wl, 3, 1, args.cpu_sample_tokens)
         out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":
