@@ -554,6 +554,91 @@ __global__ void __launch_bounds__(256, 4) scan_fwd_kernel(const __grid_constant_
     TRACE_MARK(tile_lin, 7);
 }
 
+// ---------------------------------------------------------------------------------------------
+// two-pass forward, aggregate pass: reads dt and Bm only.  A CTA owns AGG_G consecutive tiles of one chain; all of their
+// TMA loads and dt rows are in flight from the start (one exposed load latency per AGG_G tiles), then the tiles are
+// reduced one after the other.  smem: [AGG_G tiles of T x Cs] [sdel: AGG_G*T x nh] [sP, sS: n_s x Cs] [mbarrier]
+// ---------------------------------------------------------------------------------------------
+constexpr int AGG_G = 4;
+template <typename T, int CS>
+__global__ void __launch_bounds__(256, 4) scan_fwd_agg_kernel(const __grid_constant__ CUtensorMap tm_b, const ScanParams p) {
+    constexpr int V = 4;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Cs = CS ? CS : p.Cs;
+    const int Tt = p.T, n_s = p.n_s;
+    const size_t tile_bytes = (size_t)Tt * Cs * sizeof(T);
+    const size_t pitch = (tile_bytes + 127) / 128 * 128;
+    const int nh_max = Cs / 16 + 2;
+    float* sdel = reinterpret_cast<float*>(smem + (size_t)AGG_G * pitch);
+    float* sP = sdel + sdel_floats(AGG_G * Tt, nh_max);
+    float* sS = sP + (size_t)n_s * Cs;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (size_t)n_s * Cs + (((uintptr_t)(sS + (size_t)n_s * Cs)) % 8 ? 1 : 0));
+    const int tid = threadIdx.x;
+    const int ngrp = (p.nchunks + AGG_G - 1) / AGG_G;
+    const int chain = blockIdx.x % p.nchains, jg = blockIdx.x / p.nchains;
+    if (jg >= ngrp) return;
+    const int j0 = jg * AGG_G, ng = min(AGG_G, p.nchunks - j0);
+    const int slab = chain % p.nslab, b = chain / p.nslab;
+    const int c0 = slab * Cs, row0 = j0 * Tt;
+    const int h_lo = c0 / 16, nh = (c0 + Cs - 1) / 16 - h_lo + 1;
+    if (tid == 0) {
+        ab_mbar_init(&bars[0], 1);
+        ab_fence_mbar_init();
+        ab_mbar_expect_tx(&bars[0], (uint32_t)(ng * tile_bytes));
+        for (int g = 0; g < ng; ++g) ab_tma_load_3d(smem + (size_t)g * pitch, &tm_b, &bars[0], c0, row0 + g * Tt, b);
+    }
+    stage_delta<T>(p, sdel, b, row0, ng * Tt, h_lo, nh);
+    const int ncv = Cs / V;
+    const int i_run = tid / ncv, cv = tid % ncv;
+    const int cl = cv * V;
+    const int hh = (c0 + cl) / 16 - h_lo;
+    float A2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) A2[v] = -__expf(__ldg(p.A_log + c0 + cl + v)) * AB_LOG2E;
+    __syncthreads();            // sdel and the barrier initialisation visible
+    ab_mbar_wait(&bars[0], 0);
+    for (int g = 0; g < ng; ++g) {
+        const T* s_b = reinterpret_cast<const T*>(smem + (size_t)g * pitch);
+        float P[V], S[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { P[v] = 1.f; S[v] = 0.f; }
+#pragma unroll
+        for (int t = 0; t < TS; ++t) {
+            const int r = i_run * TS + t;
+            const float d = sdel[(g * Tt + r) * nh + hh];
+            float bv[V];
+            lds_vec<T, V>(s_b + (size_t)r * Cs + cl, bv);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float at = ab_ex2(A2[v] * d);
+                P[v] *= at;
+                S[v] = fmaf(at, S[v], bv[v]);
+            }
+        }
+        if (g) __syncthreads();                     // the previous tile's aggregates have been consumed
+        *reinterpret_cast<float4*>(sP + i_run * Cs + cl) = make_float4(P[0], P[1], P[2], P[3]);
+        *reinterpret_cast<float4*>(sS + i_run * Cs + cl) = make_float4(S[0], S[1], S[2], S[3]);
+        __syncthreads();
+        const size_t tile_lin = (size_t)chain * p.nchunks + j0 + g;
+        for (int c = tid; c < Cs; c += blockDim.x) {
+            float Pt = 1.f, St = 0.f;
+            for (int i0 = 0; i0 < n_s; i0 += 8) {
+                float P8[8], S8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = i0 + u < n_s;
+                    P8[u] = ok ? sP[(i0 + u) * Cs + c] : 1.f;
+                    S8[u] = ok ? sS[(i0 + u) * Cs + c] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { St = fmaf(St, P8[u], S8[u]); Pt *= P8[u]; }
+            }
+            p.aggP[tile_lin * Cs + c] = Pt;
+            p.aggS[tile_lin * Cs + c] = St;
+        }
+    }
+}
+
 // two-pass: state entering every tile.  A block owns COMB_CH channels; the chunk axis is cut into COMB_SEG segments that
 // are composed in parallel (pass 1), chained through shared memory, and re-walked to emit the per-tile states (pass 2;
 // the aggregates are L2 hits by then).  Loads of 8 tiles are issued ahead of the 8 dependent FMAs.
@@ -1046,6 +1131,25 @@ int launch_bwd_cs(const CUtensorMap* maps, const ScanParams& p, const ScanTiling
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
+template <typename T, int CS>
+int launch_fwd_agg_cs(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, cudaStream_t st) {
+    const size_t tile_bytes = (size_t)t.T * t.Cs * t.esize;
+    const size_t pitch = (tile_bytes + 127) / 128 * 128;
+    const size_t smem = (size_t)AGG_G * pitch + (size_t)sdel_floats(AGG_G * t.T, t.Cs / 16 + 2) * 4 + (size_t)2 * t.n_s * t.Cs * 4 + 8 + 32;
+    auto kfn = scan_fwd_agg_kernel<T, CS>;
+    if (int e = prepare_kernel(kfn, smem)) return e;
+    const int ngrp = (p.nchunks + AGG_G - 1) / AGG_G;
+    kfn<<<(unsigned)(p.nchains * ngrp), t.n_s * (t.Cs / 4), smem, st>>>(maps[1], p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+template <typename T>
+int launch_fwd_agg(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, cudaStream_t st) {
+    if (t.Cs == 64) return launch_fwd_agg_cs<T, 64>(maps, p, t, st);
+    if (t.Cs == 88) return launch_fwd_agg_cs<T, 88>(maps, p, t, st);
+    return launch_fwd_agg_cs<T, 0>(maps, p, t, st);
+}
+
 template <typename T, int MODE>
 int launch_bwd_mode(const CUtensorMap* maps, const ScanParams& p, const ScanTiling& t, float* gin, cudaStream_t st) {
     if (t.Cs == 64) return launch_bwd_cs<T, MODE, 64>(maps, p, t, gin, st);
@@ -1113,8 +1217,7 @@ extern "C" int ab_selective_scan_fwd(const void* xa, const void* dlog, const voi
         return f32 ? launch_fwd_mode<float, MODE_FUSED>(maps, p, t, 4, stream)
                    : launch_fwd_mode<__nv_bfloat16, MODE_FUSED>(maps, p, t, 4, stream);
     }
-    if (int e = f32 ? launch_fwd_mode<float, MODE_AGG>(maps, p, t, 1, stream)
-                    : launch_fwd_mode<__nv_bfloat16, MODE_AGG>(maps, p, t, 1, stream)) return e;
+    if (int e = f32 ? launch_fwd_agg<float>(maps, p, t, stream) : launch_fwd_agg<__nv_bfloat16>(maps, p, t, stream)) return e;
     scan_combine_kernel<<<(unsigned)ab_ceil_div((int64_t)B * Di, COMB_CH), COMB_CH * COMB_SEG, 0, stream>>>(p.aggP, p.aggS, h0, hstart, h_last, B, Di,
                                                                                    t.Cs, t.nslab, t.nchunks, 0);
     AB_LAUNCH_CHECK();
