@@ -108,6 +108,90 @@ __global__ void __launch_bounds__(256) ln_bwd_rows_kernel(const TG* __restrict__
     }
 }
 
+// Row pass and column pass in one kernel (hidden sizes up to NIT * 128): a lane always owns the same columns, so the
+// products dy * xhat and dy of its rows accumulate in registers while the row pass streams; the warps of a CTA then add
+// their sums in warp order through shared memory and the CTA writes one partial row of `part` -- the second read of dy
+// and x by ln_bwd_cols_kernel disappears.  Fixed order -> deterministic.
+template <typename TX, typename TG, int NIT>
+__global__ void __launch_bounds__(256) ln_bwd_fused_kernel(const TG* __restrict__ dy, const TX* __restrict__ x,
+                                                           const float* __restrict__ stats, const float* __restrict__ w,
+                                                           const TX* __restrict__ dres, TX* __restrict__ dx,
+                                                           float* __restrict__ part, int S, int Dm) {
+    __shared__ float sacc[2][NIT * 128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float gw[NIT][4], gb[NIT][4];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { gw[it][v] = 0.f; gb[it][v] = 0.f; }
+    }
+    for (int s = blockIdx.x * wpb + warp; s < S; s += gridDim.x * wpb) {
+        const float mean = stats[2 * (size_t)s], rstd = stats[2 * (size_t)s + 1];
+        const TX* xr = x + (size_t)s * Dm;
+        const TG* gr = dy + (size_t)s * Dm;
+        float fx[NIT][4], fg[NIT][4];
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int d = it * 128 + lane * 4;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { fx[it][v] = 0.f; fg[it][v] = 0.f; }
+            if (d < Dm) {
+                ld4<TX>(xr + d, fx[it]);
+                ld4<TG>(gr + d, fg[it]);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int d = it * 128 + lane * 4;
+            if (d < Dm) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(w + d));
+                const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    fx[it][v] = (fx[it][v] - mean) * rstd;            // xhat
+                    gw[it][v] = fmaf(fg[it][v], fx[it][v], gw[it][v]);
+                    gb[it][v] += fg[it][v];
+                    fg[it][v] *= ww[v];                               // d xhat
+                    a1 += fg[it][v];
+                    a2 = fmaf(fg[it][v], fx[it][v], a2);
+                }
+            }
+        }
+        const float m1 = ab_warp_sum(a1) / (float)Dm, m2 = ab_warp_sum(a2) / (float)Dm;
+        TX* orow = dx + (size_t)s * Dm;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int d = it * 128 + lane * 4;
+            if (d < Dm) {
+                float o[4], r[4] = {0.f, 0.f, 0.f, 0.f};
+                if (dres) ld4<TX>(dres + (size_t)s * Dm + d, r);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) o[v] = fmaf(rstd, fg[it][v] - m1 - fx[it][v] * m2, r[v]);
+                st4<TX>(orow + d, o);
+            }
+        }
+    }
+    for (int wv = 0; wv < wpb; ++wv) {
+        if (warp == wv) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int i = it * 128 + lane * 4 + v;
+                    sacc[0][i] = wv ? sacc[0][i] + gw[it][v] : gw[it][v];
+                    sacc[1][i] = wv ? sacc[1][i] + gb[it][v] : gb[it][v];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 2 * Dm; i += blockDim.x) {
+        const int q = i / Dm, d = i % Dm;
+        part[((size_t)blockIdx.x * 2 + q) * Dm + d] = sacc[q][d];
+    }
+}
+
 // grid (ceil(S/RB), ceil(Dm/128)); block 256 = 8 warps over rows x (32 lanes x 4 columns)
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(256) ln_bwd_cols_kernel(const TG* __restrict__ dy, const TX* __restrict__ x,
@@ -180,7 +264,8 @@ extern "C" int ab_layernorm_fwd(const void* x, const float* w, const float* b, f
 }
 
 extern "C" size_t ab_layernorm_bwd_workspace_bytes(int S, int Dm) {
-    return (size_t)ab_round_up(ab_ceil_div(S, RB) * 2 * (int64_t)Dm * sizeof(float), 256);
+    const int64_t rows = ab_ceil_div(S, RB) > grid_rows(S) ? ab_ceil_div(S, RB) : grid_rows(S);     // partial rows of either path
+    return (size_t)ab_round_up(rows * 2 * (int64_t)Dm * sizeof(float), 256);
 }
 
 extern "C" int ab_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* w, const void* dres, void* dx,
@@ -189,13 +274,22 @@ extern "C" int ab_layernorm_bwd(const void* dy, const void* x, const float* stat
     AB_REQUIRE(S > 0 && Dm > 0 && Dm % 4 == 0, "layernorm_bwd: need S > 0 and hidden size a multiple of 4");
     AB_REQUIRE(ws && ws_bytes >= ab_layernorm_bwd_workspace_bytes(S, Dm), "layernorm_bwd: workspace too small");
     const int g = grid_rows(S);
-    const int nblocks = (int)ab_ceil_div(S, RB);
+    const int nit = (int)ab_ceil_div(Dm, 128);
+    const bool fused = nit <= 8;                     // column sums fit in registers next to the row pass
+    const int nblocks = fused ? g : (int)ab_ceil_div(S, RB);
     dim3 cgrid(nblocks, (unsigned)ab_ceil_div(Dm, 128));
     float* part = (float*)ws;
+#define AB_LNB_F(TX, TG, NIT) \
+    ln_bwd_fused_kernel<TX, TG, NIT><<<g, 256, 0, stream>>>((const TG*)dy, (const TX*)x, stats, w, (const TX*)dres, (TX*)dx, part, S, Dm)
 #define AB_LNB(TX, TG)                                                                                                     \
     {                                                                                                                      \
-        ln_bwd_rows_kernel<TX, TG><<<g, 256, 0, stream>>>((const TG*)dy, (const TX*)x, stats, w, (const TX*)dres, (TX*)dx, S, Dm); \
-        ln_bwd_cols_kernel<TX, TG><<<cgrid, 256, 0, stream>>>((const TG*)dy, (const TX*)x, stats, part, S, Dm);           \
+        if (fused) {                                                                                                       \
+            if (nit <= 2) AB_LNB_F(TX, TG, 2); else if (nit <= 4) AB_LNB_F(TX, TG, 4);                                     \
+            else if (nit <= 6) AB_LNB_F(TX, TG, 6); else AB_LNB_F(TX, TG, 8);                                              \
+        } else {                                                                                                           \
+            ln_bwd_rows_kernel<TX, TG><<<g, 256, 0, stream>>>((const TG*)dy, (const TX*)x, stats, w, (const TX*)dres, (TX*)dx, S, Dm); \
+            ln_bwd_cols_kernel<TX, TG><<<cgrid, 256, 0, stream>>>((const TG*)dy, (const TX*)x, stats, part, S, Dm);       \
+        }                                                                                                                  \
     }
     if (x_dtype == AB_F32 && dy_dtype == AB_F32) AB_LNB(float, float)
     else if (x_dtype == AB_F32 && dy_dtype == AB_BF16) AB_LNB(float, __nv_bfloat16)
@@ -203,6 +297,7 @@ extern "C" int ab_layernorm_bwd(const void* dy, const void* x, const float* stat
     else if (x_dtype == AB_BF16 && dy_dtype == AB_F32) AB_LNB(__nv_bfloat16, float)
     else AB_REQUIRE(false, "layernorm_bwd: bad dtypes");
 #undef AB_LNB
+#undef AB_LNB_F
     AB_LAUNCH_CHECK();
     ln_param_reduce_kernel<<<(unsigned)ab_ceil_div(2 * Dm, 8), 256, 0, stream>>>(part, nblocks, Dm, dw, db);
     AB_LAUNCH_CHECK();
