@@ -273,9 +273,10 @@ extern "C" int ab_layernorm_bwd(const void* dy, const void* x, const float* stat
                                 cudaStream_t stream) {
     AB_REQUIRE(S > 0 && Dm > 0 && Dm % 4 == 0, "layernorm_bwd: need S > 0 and hidden size a multiple of 4");
     AB_REQUIRE(ws && ws_bytes >= ab_layernorm_bwd_workspace_bytes(S, Dm), "layernorm_bwd: workspace too small");
-    const int g = grid_rows(S);
+    int g = grid_rows(S);
     const int nit = (int)ab_ceil_div(Dm, 128);
     const bool fused = nit <= 8;                     // column sums fit in registers next to the row pass
+    if (fused && g > 2 * ab_num_sms()) g = 2 * ab_num_sms();      // two CTAs per SM are resident: one wave, few partial rows
     const int nblocks = fused ? g : (int)ab_ceil_div(S, RB);
     dim3 cgrid(nblocks, (unsigned)ab_ceil_div(Dm, 128));
     float* part = (float*)ws;

@@ -7,6 +7,18 @@
 
 namespace {
 
+template <typename T>
+__device__ __forceinline__ void ld4g(const T* p, float* f) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+    } else {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+}
+
 constexpr int PLAN_THREADS = 1024;
 
 // exclusive prefix of a small per-thread count over the CTA (thread order) + CTA total; two __syncthreads
@@ -378,6 +390,94 @@ __global__ void __launch_bounds__(256) permute_ln_bwd_rows_kernel(const TG* __re
     }
 }
 
+// Row pass and per-tile column partials in one kernel (hidden sizes up to NIT * 128): one CTA per 128-row tile (one
+// expert), a lane always owns the same columns, so dxn * xhat and dxn accumulate in registers while the rows stream; the
+// warps then add their sums in warp order.  Replaces the rows + cols kernel pair (one read of dxn and x instead of two).
+template <typename TX, typename TG, int NIT>
+__global__ void __launch_bounds__(256, NIT <= 6 ? 3 : 2) permute_ln_bwd_fused_kernel(const TG* __restrict__ dxn, const TX* __restrict__ x,
+                                                                   const float* __restrict__ stats, const float* __restrict__ ln_w,
+                                                                   const int32_t* __restrict__ tok_of_row,
+                                                                   const int32_t* __restrict__ tile_expert,
+                                                                   const int32_t* __restrict__ n_rows, float* __restrict__ dxrow,
+                                                                   float* __restrict__ part, int Dm, int align) {
+    __shared__ float sacc[2][NIT * 128];
+    const int t = blockIdx.x;
+    if ((int64_t)t * align >= n_rows[0]) return;
+    const int e = tile_expert[t];
+    if (e < 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const float* g = ln_w + (size_t)e * Dm;
+    float gw[NIT][4], gb[NIT][4];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { gw[it][v] = 0.f; gb[it][v] = 0.f; }
+    }
+    for (int i = warp; i < align; i += wpb) {
+        const int r = t * align + i;
+        const int tok = tok_of_row[r];
+        if (tok < 0) continue;
+        const float mean = stats[2 * (size_t)tok], rstd = stats[2 * (size_t)tok + 1];
+        const TX* xr = x + (size_t)tok * Dm;
+        const TG* gr = dxn + (size_t)r * Dm;
+        // pass 1: column partials and the two row sums (the row is read again in pass 2 from L1 / L2: keeping it in
+        // registers would halve the resident warps)
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int d = it * 128 + lane * 4;
+            if (d < Dm) {
+                float fx[4], fg[4], gg[4];
+                ld4g<TX>(xr + d, fx);
+                ld4g<TG>(gr + d, fg);
+                ld4g<float>(g + d, gg);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float xh = (fx[v] - mean) * rstd;
+                    gw[it][v] = fmaf(fg[v], xh, gw[it][v]);
+                    gb[it][v] += fg[v];
+                    const float dh = fg[v] * gg[v];
+                    a1 += dh;
+                    a2 = fmaf(dh, xh, a2);
+                }
+            }
+        }
+        const float m1 = ab_warp_sum(a1) / (float)Dm, m2 = ab_warp_sum(a2) / (float)Dm;
+        float* orow = dxrow + (size_t)r * Dm;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int d = it * 128 + lane * 4;
+            if (d < Dm) {
+                float fx[4], fg[4], gg[4], o[4];
+                ld4g<TX>(xr + d, fx);
+                ld4g<TG>(gr + d, fg);
+                ld4g<float>(g + d, gg);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) o[v] = rstd * (fg[v] * gg[v] - m1 - (fx[v] - mean) * rstd * m2);
+                *reinterpret_cast<float4*>(orow + d) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    for (int wv = 0; wv < wpb; ++wv) {
+        if (warp == wv) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int i = it * 128 + lane * 4 + v;
+                    sacc[0][i] = wv ? sacc[0][i] + gw[it][v] : gw[it][v];
+                    sacc[1][i] = wv ? sacc[1][i] + gb[it][v] : gb[it][v];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < 2 * Dm; i += blockDim.x) {
+        const int q = i / Dm, d = i % Dm;
+        part[((size_t)t * 2 + q) * Dm + d] = sacc[q][d];
+    }
+}
+
 // grid (tiles, ceil(Dm/128)); block (32 lanes x 4 columns, 8 warps over the tile's rows)
 template <typename TX, typename TG>
 __global__ void __launch_bounds__(256) permute_ln_bwd_cols_kernel(const TG* __restrict__ dxn, const TX* __restrict__ x,
@@ -454,20 +554,42 @@ __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t
                                    const int32_t* __restrict__ n_rows, float* __restrict__ out_a, float* __restrict__ out_b,
                                    int split, int ncols, int align) {
     __shared__ int s_t0, s_t1;
+    __shared__ int s_list[1024];                       // tile ids of this expert, in order (the common case fits)
+    __shared__ int s_n;
     const int e = blockIdx.y;
-    if (threadIdx.x == 0) {
-        const int ntiles = n_rows[0] / align;
-        int t0 = ntiles, t1 = 0;
-        for (int t = 0; t < ntiles; ++t)
-            if (tile_expert[t] == e) { if (t < t0) t0 = t; t1 = t + 1; }
-        s_t0 = t0; s_t1 = t1;
+    const int ntiles = n_rows[0] / align;
+    if (threadIdx.x < 32) {                            // one warp builds the ordered list with ballots
+        int n = 0, t0 = ntiles, t1 = 0;
+        for (int base = 0; base < ntiles; base += 32) {
+            const int t = base + (int)threadIdx.x;
+            const bool mine = t < ntiles && tile_expert[t] == e;
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const int pos = n + __popc(m & ((1u << threadIdx.x) - 1u));
+                if (pos < 1024) s_list[pos] = t;
+            }
+            if (m) { t0 = min(t0, base + __ffs(m) - 1); t1 = base + 32 - __clz(m); }
+            n += __popc(m);
+        }
+        if (threadIdx.x == 0) { s_t0 = t0; s_t1 = t1; s_n = n; }
     }
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ncols) return;
     float s = 0.f;
-    for (int t = s_t0; t < s_t1; ++t)
-        if (tile_expert[t] == e) s += part[(size_t)t * ncols + j];      // tiles of an expert may be interleaved (EP layout)
+    if (s_n <= 1024) {
+        // loads of 8 tiles are issued before the 8 dependent adds; order = tile order -> deterministic
+        for (int i0 = 0; i0 < s_n; i0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = i0 + u < s_n ? part[(size_t)s_list[i0 + u] * ncols + j] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+    } else {
+        for (int t = s_t0; t < s_t1; ++t)
+            if (tile_expert[t] == e) s += part[(size_t)t * ncols + j];  // tiles of an expert may be interleaved (EP layout)
+    }
     if (j < split) out_a[(size_t)e * split + j] = s;
     else out_b[(size_t)e * (ncols - split) + (j - split)] = s;
 }
@@ -590,12 +712,21 @@ extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float
     float* part = (float*)ws;
     const int rgrid = rows_grid(max_rows);
     dim3 cgrid(ntiles, (unsigned)ab_ceil_div(Dm, 128));
+    const int nit = (int)ab_ceil_div(Dm, 128);
+#define AB_LNB_F(TX, TG, NIT)                                                                                                    \
+    permute_ln_bwd_fused_kernel<TX, TG, NIT><<<ntiles, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row, \
+                                                                         tile_expert, n_rows, dxrow, part, Dm, row_align)
 #define AB_LNB(TX, TG)                                                                                                           \
     {                                                                                                                            \
-        permute_ln_bwd_rows_kernel<TX, TG><<<rgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row,   \
-                                                                      tile_expert, n_rows, dxrow, Dm, row_align);              \
-        permute_ln_bwd_cols_kernel<TX, TG><<<cgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, tok_of_row,         \
-                                                                      tile_expert, n_rows, part, Dm, row_align);               \
+        if (nit <= 8) {                                                                                                          \
+            if (nit <= 2) AB_LNB_F(TX, TG, 2); else if (nit <= 4) AB_LNB_F(TX, TG, 4);                                           \
+            else if (nit <= 6) AB_LNB_F(TX, TG, 6); else AB_LNB_F(TX, TG, 8);                                                    \
+        } else {                                                                                                                 \
+            permute_ln_bwd_rows_kernel<TX, TG><<<rgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row, \
+                                                                          tile_expert, n_rows, dxrow, Dm, row_align);            \
+            permute_ln_bwd_cols_kernel<TX, TG><<<cgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, tok_of_row,       \
+                                                                          tile_expert, n_rows, part, Dm, row_align);             \
+        }                                                                                                                        \
     }
     if (dtype == AB_F32 && dxn_dtype == AB_F32) AB_LNB(float, float)
     else if (dtype == AB_F32 && dxn_dtype == AB_BF16) AB_LNB(float, __nv_bfloat16)
@@ -603,6 +734,7 @@ extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float
     else if (dtype == AB_BF16 && dxn_dtype == AB_F32) AB_LNB(__nv_bfloat16, float)
     else AB_REQUIRE(false, "moe_permute_ln_bwd: bad dtypes");
 #undef AB_LNB
+#undef AB_LNB_F
     AB_LAUNCH_CHECK();
     dim3 grid((unsigned)ab_ceil_div(2 * Dm, 128), E);       // part is [tile][2][Dm]: reduce as 2*Dm columns, split in two
     tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, dln_w, dln_b, Dm, 2 * Dm, row_align);
