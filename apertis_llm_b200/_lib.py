@@ -21,7 +21,7 @@ CSRC = os.path.join(_HERE, "csrc")
 AB_F32, AB_BF16 = 0, 1
 ACT = {"gelu": 0, "relu": 1, "silu": 2, "swish": 2}
 EPI_NONE, EPI_BIAS, EPI_BIAS_ACT, EPI_DACT = 0, 1, 2, 3
-SCAN_SINGLE_PASS, SCAN_TWO_PASS = 0, 1
+SCAN_SINGLE_PASS, SCAN_TWO_PASS, SCAN_PIPELINED = 0, 1, 2
 ROW_ALIGN = 128
 
 P, I, I64, SZ, F, U32 = c_void_p, c_int, c_int64, c_size_t, c_float, c_uint32
@@ -34,7 +34,7 @@ SIGNATURES = {
     "ab_causal_conv1d_silu_fwd": (I, [P, I64, P, P, P, I, I, I, I, I, P]),
     "ab_causal_conv1d_silu_bwd_workspace_bytes": (SZ, [I, I, I]),
     "ab_causal_conv1d_silu_bwd": (I, [P, I64, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
-    "ab_selective_scan_plan": (I, [I, I, I, I, P, P, P, P]),
+    "ab_selective_scan_plan": (I, [I, I, I, I, P, P, P, P, P]),
     "ab_selective_scan_fwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, SZ, U32, I, I, I, I, I, I, P]),
     "ab_selective_scan_bwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, I64, P, P, P, P, P, SZ, U32, I,
                                   I, I, I, I, I, P]),

@@ -50,6 +50,13 @@ int ab_encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, cons
     for (uint32_t i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = g_encode(map, dt, rank, const_cast<void*>(base), gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT) {
+        // a thread that has not touched the runtime yet (autograd's backward thread served from the caching allocator):
+        // bind the primary context and try again
+        cudaFree(nullptr);
+        r = g_encode(map, dt, rank, const_cast<void*>(base), gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
         ab_set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %u dims [%llu,%llu,%llu] box [%u,%u,%u] stride0 %llu base %p",
                      (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),

@@ -26,13 +26,10 @@
 // tools/scan_trace.py (with `make TRACE=1`) prints the per-phase timeline of the tiles and the scanner.
 #include "common.cuh"
 
-namespace {
+#include "ssm_scan_shared.cuh"
 
-constexpr int TS = 4;            // tokens per thread run
-constexpr int SCAN_K = 32;       // tile aggregates the scanner polls per round trip (shared-memory ring, cp.async)
-constexpr int MODE_FUSED = 0, MODE_AGG = 1, MODE_APPLY = 2;
-constexpr uint32_t ST_AGG = 1, ST_INCL = 2;
-constexpr int SPIN_LIMIT = 1 << 24;
+namespace {
+using namespace ab_scan;
 
 struct ScanTiling {
     int V_f, V_b;     // channel-vector width of the forward / backward kernels
@@ -73,283 +70,6 @@ int make_tiling(int L, int Di, int dtype, ScanTiling& t) {
     return 1;
 }
 
-struct ScanParams {
-    int B, L, Di, H;
-    int Cs, T, n_s, nslab, nchunks, nchains;
-    const void* dlog;        // [B, L, H] activation dtype
-    const float* A_log;      // [Di]
-    const float* Dp;         // [Di]
-    const float* h0;         // [B, Di] or null
-    void* y; void* y_ssm;    // [B, L, Di]
-    float* h_last;           // [B, Di] or null
-    float* hstart;           // [B, nchunks, Di] or null
-    unsigned long long* words;   // [nchains*nchunks][Cs][2]  tile aggregates (P, S)
-    unsigned long long* inclw;   // [nchains*nchunks][Cs]     state entering each tile, published by the scanners
-    int n_scan;                  // scanner CTAs (take the first tickets)
-    unsigned int* ticket;
-    unsigned int* err_flag;
-    float* aggP; float* aggS;    // two-pass: [nchains*nchunks][Cs]
-    uint32_t epoch;
-    // backward only
-    const void* dyssm;       // optional grad of y_ssm, [B, L, Di]
-    void* dxa; void* dBm; void* dCm; void* dz; int64_t dbc_stride;
-    float* ddlog_parts;      // [B, L, Di / V_b]
-    float* part;             // [ntiles][2][Cs] partial dA_log / dD sums
-};
-
-__device__ __forceinline__ unsigned long long pack_word(uint32_t epoch, uint32_t st, float v) {
-    return ((unsigned long long)((epoch << 2) | st) << 32) | (unsigned long long)__float_as_uint(v);
-}
-
-// deepest power-of-two ring (<= SCAN_K tiles x Cs channels x 16 B) that fits in the tile area of a scanner CTA
-__device__ __forceinline__ int ring_depth(size_t avail_bytes, int Cs) {
-    int k = SCAN_K;
-    while (k >= 4 && (size_t)k * Cs * sizeof(uint4) > avail_bytes) k >>= 1;
-    return k >= 4 ? k : 0;
-}
-
-__device__ __forceinline__ bool word_valid(unsigned long long w, uint32_t epoch) { return (uint32_t)(w >> 34) == epoch; }
-
-#ifdef AB_SCAN_TRACE
-// debug build only (make TRACE=1): per-tile phase timestamps of the forward kernel, read back by tools/scan_trace.py
-constexpr int TRACE_SLOTS = 8, TRACE_TILES = 16384;
-__device__ unsigned long long g_scan_trace[TRACE_TILES * TRACE_SLOTS];
-__device__ __forceinline__ void trace_mark(size_t tile_lin, int slot) {
-    if (threadIdx.x == 0 && tile_lin < TRACE_TILES) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_scan_trace[tile_lin * TRACE_SLOTS + slot] = t;
-    }
-}
-#define TRACE_MARK(tl, s) trace_mark(tl, s)
-constexpr int STRACE_ROUNDS = 2048;
-__device__ unsigned long long g_scanner_trace[64 * STRACE_ROUNDS * 4];
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#else
-#define TRACE_MARK(tl, s)
-#endif
-
-// Tile side: spin until the scanner has published the state entering this tile.
-__device__ __forceinline__ float wait_incoming(const ScanParams& p, size_t tile_lin, int c) {
-    const unsigned long long* w = p.inclw + tile_lin * p.Cs + c;
-    unsigned long long v = ab_ld_relaxed_u64(w);
-    int spins = 0;
-    while (!word_valid(v, p.epoch)) {
-        if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); return 0.f; }
-        v = ab_ld_relaxed_u64(w);
-    }
-    return __uint_as_float((uint32_t)v);
-}
-
-// Scanner role.  One CTA per chain (b, slab); DIR = +1 walks chunk 0 -> last (forward scan, starts from h0),
-// DIR = -1 walks last -> 0 (reverse scan of the backward, starts from 0).  It publishes, for every tile, the state
-// entering it (which does not depend on the tile's own aggregate).
-// Fast path: the CTA's threads form R replicas of the slab's channels.  Every round polls the aggregate words of the
-// next K tiles with cp.async into a shared-memory ring (the tile buffers are free in a scanner CTA), K / R consecutive
-// tiles per replica.  Each replica composes the valid prefix of its segment, the segment aggregates are chained
-// through shared memory (every thread derives the same new head and state), and each replica then walks its own
-// segment again to publish the per-tile states: loads, FMA chains and stores of a round are spread over R warps sets.
-// The composition order is fixed by the tile order, so results are bitwise reproducible.
-template <int DIR>
-__device__ __forceinline__ void scanner_role(const ScanParams& p, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem below hs*/, size_t ring_bytes) {
-    const int n = p.nchunks, Cs = p.Cs;
-    const int slab = chain % p.nslab, b = chain / p.nslab;
-    int spins = 0;
-    int R = (int)blockDim.x / Cs;
-    R = R >= 4 ? 4 : (R >= 2 ? 2 : R);
-    // shared memory: ring [K][Cs] uint4, then segP / segS / segN [R][Cs]
-    const size_t seg_bytes = (size_t)3 * 4 * Cs * sizeof(float);
-    const int K = ring_bytes > seg_bytes ? ring_depth(ring_bytes - seg_bytes, Cs) : 0;
-    if (R >= 1 && K >= 8) {
-        const int S = K / R;                           // tiles per replica and round (>= 2)
-        float* segP = reinterpret_cast<float*>(ring + (size_t)K * Cs);
-        float* segS = segP + 4 * Cs;
-        int* segN = reinterpret_cast<int*>(segS + 4 * Cs);
-        const int c = threadIdx.x % Cs, r = threadIdx.x / Cs;
-        const bool active = r < R;
-        const int cg = slab * Cs + c;
-        float h = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + cg] : 0.f;
-        uint4* myring = ring + c;
-        unsigned long long* incl_base = p.inclw + (size_t)chain * n * Cs + c;
-        const unsigned long long* word_base = p.words + ((size_t)chain * n * Cs + c) * 2;
-        const unsigned long long tag_incl = (unsigned long long)((p.epoch << 2) | ST_INCL) << 32;
-        if (r == 0) ab_st_relaxed_u64_unordered(incl_base + (size_t)(DIR > 0 ? 0 : n - 1) * Cs, tag_incl | __float_as_uint(h));
-        // Fixed two-level association (independent of timing, hence bitwise reproducible): the chain is cut into
-        // aligned segments of S tiles; H(g+1) = Pseg(g) * H(g) + Sseg(g) with the segment aggregate composed in tile
-        // order, and the states inside a segment follow sequentially from H(g).
-        int gh = 0;                                    // first segment that is not folded into h yet
-        const int nseg = (n + S - 1) / S;
-#ifdef AB_SCAN_TRACE
-        int round = 0;
-#endif
-        while (gh < nseg) {
-#ifdef AB_SCAN_TRACE
-            const unsigned long long tr0 = gtime();
-#endif
-            const int lo = min((gh + r) * S, n), hi = active ? min(lo + S, n) : lo;     // my segment of this round
-            for (int s2 = lo; s2 < hi; ++s2) {
-                const int j = DIR > 0 ? s2 : n - 1 - s2;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ab_smem_u32(myring + (size_t)(s2 & (K - 1)) * Cs)),
-                             "l"(word_base + (size_t)j * Cs * 2) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-#ifdef AB_SCAN_TRACE
-            const unsigned long long tr1 = gtime();
-#endif
-            // valid prefix of my segment and its aggregate
-            float Pa = 1.f, Sa = 0.f;
-            int cnt = 0;
-            {
-                bool ok = true;
-                for (int u0 = lo; u0 < hi && ok; u0 += 8) {
-                    uint4 w4[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) w4[u] = myring[(size_t)((u0 + u) & (K - 1)) * Cs];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        ok = ok && u0 + u < hi && (w4[u].y >> 2) == p.epoch && (w4[u].w >> 2) == p.epoch;
-                        if (ok) {
-                            Sa = fmaf(__uint_as_float(w4[u].x), Sa, __uint_as_float(w4[u].z));
-                            Pa *= __uint_as_float(w4[u].x);
-                            ++cnt;
-                        }
-                    }
-                }
-            }
-            const bool full = cnt == hi - lo;          // every tile of the segment has published
-            if (active) { segP[r * Cs + c] = Pa; segS[r * Cs + c] = Sa; segN[r * Cs + c] = full ? 1 : 0; }
-            __syncthreads();
-            // chain the complete segments: every replica of a channel derives the same new gh / state
-            float hin = h, hnew = h;
-            bool reach = true, mine = false;
-            int adv = 0;
-            for (int r2 = 0; r2 < R; ++r2) {
-                if (r2 == r) { hin = hnew; mine = reach; }
-                if (reach && gh + r2 < nseg && segN[r2 * Cs + c]) {
-                    hnew = fmaf(segP[r2 * Cs + c], hnew, segS[r2 * Cs + c]);
-                    ++adv;
-                } else {
-                    reach = false;
-                }
-            }
-            // publish the states entering the tiles behind my valid prefix (idempotent when a segment is polled again)
-            if (mine) {
-                float hh = hin;
-                for (int u0 = 0; u0 < cnt; u0 += 8) {
-                    uint4 w4[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) w4[u] = myring[(size_t)((lo + u0 + u) & (K - 1)) * Cs];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int jn = lo + u0 + u + 1;             // state entering tile jn
-                        if (u0 + u < cnt) {
-                            hh = fmaf(__uint_as_float(w4[u].x), hh, __uint_as_float(w4[u].z));
-                            // the first tile of the next segment gets H(g+1) exactly as the chain carries it on
-                            const float hv = (full && jn == hi) ? fmaf(Pa, hin, Sa) : hh;
-                            if (jn < n) ab_st_relaxed_u64_unordered(incl_base + (size_t)(DIR > 0 ? jn : n - 1 - jn) * Cs, tag_incl | __float_as_uint(hv));
-                        }
-                    }
-                }
-            }
-            gh += adv;
-            h = hnew;
-#ifdef AB_SCAN_TRACE
-            if (threadIdx.x == 0 && chain < 64 && round < STRACE_ROUNDS) {
-                unsigned long long* o = g_scanner_trace + ((size_t)chain * STRACE_ROUNDS + round) * 4;
-                o[0] = tr0; o[1] = tr1; o[2] = gtime(); o[3] = (unsigned long long)(adv * S);
-            }
-            ++round;
-#endif
-            if (adv == 0 && ++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
-            __syncthreads();        // ring slots and segment words are rewritten next round
-        }
-        if (DIR > 0 && p.h_last && r == 0) p.h_last[(size_t)b * p.Di + cg] = h;
-        return;
-    }
-    const int c = threadIdx.x;
-    // generic path (blocks narrower than the slab: tiny sequences): state in shared memory, no prefetch
-    for (int cc = c; cc < Cs; cc += blockDim.x) hs[cc] = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + slab * Cs + cc] : 0.f;
-    for (int step = 0; step < n; ++step) {
-        const int j = DIR > 0 ? step : n - 1 - step;
-        const size_t tl = (size_t)chain * n + j;
-        for (int cc = c; cc < Cs; cc += blockDim.x) {
-            const float h = hs[cc];
-            ab_st_relaxed_u64(p.inclw + tl * Cs + cc, pack_word(p.epoch, ST_INCL, h));
-        }
-        for (int cc = c; cc < Cs; cc += blockDim.x) {
-            const unsigned long long* w = p.words + (tl * Cs + cc) * 2;
-            unsigned long long wp = ab_ld_relaxed_u64(w), wsv = ab_ld_relaxed_u64(w + 1);
-            while (!word_valid(wp, p.epoch) || !word_valid(wsv, p.epoch)) {
-                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
-                wp = ab_ld_relaxed_u64(w); wsv = ab_ld_relaxed_u64(w + 1);
-            }
-            hs[cc] = fmaf(__uint_as_float((uint32_t)wp), hs[cc], __uint_as_float((uint32_t)wsv));
-        }
-    }
-    if (DIR > 0 && p.h_last)
-        for (int cc = c; cc < Cs; cc += blockDim.x) p.h_last[(size_t)b * p.Di + slab * Cs + cc] = hs[cc];
-}
-
-// softplus'd delta rows of this tile (plus one extra row for the reverse scan) into shared memory
-template <typename T>
-__device__ __forceinline__ void stage_delta(const ScanParams& p, float* sdel, int b, int row0, int nrows, int h_lo, int nh) {
-    const T* dl = reinterpret_cast<const T*>(p.dlog);
-    // thread -> (row, head) without integer division: nh <= blockDim in every tiling
-    const int hh = threadIdx.x % nh, r0 = threadIdx.x / nh, rstep = blockDim.x / nh;
-    if (r0 >= rstep) return;                      // the last partial group of threads sits out
-    const bool head_ok = h_lo + hh < p.H;
-    for (int r = r0; r < nrows; r += rstep) {
-        const int row = row0 + r;
-        float d = 0.f;
-        if (row < p.L && head_ok) d = ab_softplus_fast(ab_to_float(dl[((size_t)b * p.L + row) * p.H + h_lo + hh]));
-        sdel[r * nh + hh] = d;
-    }
-}
-
-// sigmoid for the SiLU gate: f32 activations use ex2 + rcp; bf16 activations use the single-MUFU tanh.approx form
-// (relative error ~5e-4, an order below bf16 resolution)
-template <typename T>
-__device__ __forceinline__ float gate_sigmoid(float x) {
-    if constexpr (sizeof(T) == 2) {
-        float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-        return fmaf(0.5f, t, 0.5f);
-    } else {
-        return ab_sigmoid(x);
-    }
-}
-
-template <typename T, int V>
-__device__ __forceinline__ void lds_vec(const T* p, float* f) {
-    if constexpr (sizeof(T) * V == 16) {
-        ab_vec16<T>::unpack(*reinterpret_cast<const uint4*>(p), f);
-    } else {   // 4 x bf16 = 8 bytes
-        const uint2 r = *reinterpret_cast<const uint2*>(p);
-        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
-        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
-    }
-}
-template <typename T, int V>
-__device__ __forceinline__ void st_vec(T* p, const float* f) {
-    if constexpr (sizeof(T) * V == 16) {
-        *reinterpret_cast<uint4*>(p) = ab_vec16<T>::pack(f);
-    } else {
-        __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b2 = __floats2bfloat162_rn(f[2], f[3]);
-        uint2 r; r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b2);
-        *reinterpret_cast<uint2*>(p) = r;
-    }
-}
-template <typename T, int V>
-__device__ __forceinline__ void ldg_vec(const T* p, float* f) {
-    if constexpr (sizeof(T) * V == 16) {
-        ab_vec16<T>::unpack(__ldg(reinterpret_cast<const uint4*>(p)), f);
-    } else {
-        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
-        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // tile coordinates from the ticket / block index: chains interleaved, chunks in scan order
@@ -406,7 +126,7 @@ __global__ void __launch_bounds__(256, 4) scan_fwd_kernel(const __grid_constant_
     int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
         if (tile < p.n_scan) {
-            scanner_role<+1>(p, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
+            scanner_role<+1>(p, p.epoch, SCAN_K, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
             return;
         }
         tile -= p.n_scan;
@@ -497,7 +217,7 @@ __global__ void __launch_bounds__(256, 4) scan_fwd_kernel(const __grid_constant_
             ab_st_relaxed_u64(w, pack_word(p.epoch, ST_AGG, Pt));
             ab_st_relaxed_u64(w + 1, pack_word(p.epoch, ST_AGG, St));
             TRACE_MARK(tile_lin, 4);
-            hin = wait_incoming(p, tile_lin, c);        // h_last is written by the scanner
+            hin = wait_incoming(p, p.epoch, tile_lin, c);        // h_last is written by the scanner
             TRACE_MARK(tile_lin, 5);
             if (p.hstart) p.hstart[((size_t)b * p.nchunks + j) * p.Di + c0 + c] = hin;     // kept for the backward
         }
@@ -747,7 +467,7 @@ __global__ void __launch_bounds__(256, 3) scan_bwd_kernel(const __grid_constant_
     int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
         if (tile < p.n_scan) {
-            scanner_role<-1>(p, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
+            scanner_role<-1>(p, p.epoch, SCAN_K, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
             return;
         }
         tile -= p.n_scan;
@@ -931,7 +651,7 @@ __global__ void __launch_bounds__(256, 3) scan_bwd_kernel(const __grid_constant_
 
     // ---- D: G entering the tile from the later tiles
     for (int c = tid; c < Cs; c += blockDim.x)
-        gT[c] = MODE == MODE_APPLY ? gin_ws[((size_t)b * p.nchunks + j) * p.Di + c0 + c] : wait_incoming(p, tile_lin, c);
+        gT[c] = MODE == MODE_APPLY ? gin_ws[((size_t)b * p.nchunks + j) * p.Di + c0 + c] : wait_incoming(p, p.epoch, tile_lin, c);
     TRACE_MARK(tile_lin, 5);
     __syncthreads();
     TRACE_MARK(tile_lin, 6);
@@ -1166,10 +886,26 @@ int check_common(int B, int L, int Di, int H, int dtype, ScanTiling& t) {
 
 }  // namespace
 
-extern "C" int ab_selective_scan_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_chunks,
+// pipelined persistent schedule (ssm_scan_pipe.cu)
+bool ab_scan_pipe_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_states, size_t* ws_bytes,
+                       int* bwd_tile_rows);
+int ab_scan_pipe_fwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride, const void* z,
+                     int64_t z_stride, const float* A_log, const float* D, const float* h0, void* y, float* h_last,
+                     float* hrun, void* ws, size_t ws_bytes, int B, int L, int Di, int H, int dtype, cudaStream_t stream);
+int ab_scan_pipe_bwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride, const void* z,
+                     int64_t z_stride, const void* dout, const float* A_log, const float* D, const float* hrun, void* dxa,
+                     void* dBm, void* dCm, int64_t dbc_stride, void* dz, float* ddlog, float** part_out, void* ws,
+                     size_t ws_bytes, int B, int L, int Di, int H, int dtype, cudaStream_t stream);
+
+extern "C" int ab_selective_scan_plan(int B, int L, int Di, int dtype, int* mode, int* tile_rows, int* slab, int* n_chunks,
                                       size_t* ws_bytes) {
     ScanTiling t;
     AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "selective_scan_plan: bad dtype");
+    AB_REQUIRE(mode && (*mode == AB_SCAN_SINGLE_PASS || *mode == AB_SCAN_TWO_PASS || *mode == AB_SCAN_PIPELINED), "selective_scan_plan: bad mode");
+    if (*mode == AB_SCAN_PIPELINED) {
+        if (B > 0 && L > 0 && Di > 0 && Di % 16 == 0 && ab_scan_pipe_plan(B, L, Di, dtype, tile_rows, slab, n_chunks, ws_bytes, nullptr)) return AB_OK;
+        *mode = AB_SCAN_SINGLE_PASS;          // shapes the pipelined schedule does not cover
+    }
     AB_REQUIRE(B > 0 && L > 0 && Di > 0 && make_tiling(L, Di, dtype, t), "selective_scan_plan: no tiling for Di=%d", Di);
     if (tile_rows) *tile_rows = t.T;
     if (slab) *slab = t.Cs;
@@ -1184,6 +920,11 @@ extern "C" int ab_selective_scan_fwd(const void* xa, const void* dlog, const voi
                                      uint32_t epoch, int mode, int B, int L, int Di, int H, int dtype, cudaStream_t stream) {
     ScanTiling t;
     if (int e = check_common(B, L, Di, H, dtype, t)) return e;
+    if (mode == AB_SCAN_PIPELINED) {
+        AB_REQUIRE(y_ssm == nullptr, "selective_scan_fwd: the pipelined mode does not emit y_ssm (plan another mode)");
+        return ab_scan_pipe_fwd(xa, dlog, Bm, Cm, bc_stride, z, z_stride, A_log, D, h0, y, h_last, hstart, ws, ws_bytes, B, L, Di, H,
+                                dtype, stream);
+    }
     const WsLayout wl = ws_layout(t, B, Di);
     AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_fwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
     AB_REQUIRE(mode == AB_SCAN_SINGLE_PASS || mode == AB_SCAN_TWO_PASS, "selective_scan_fwd: bad mode %d", mode);
@@ -1234,6 +975,18 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
                                      int dtype, cudaStream_t stream) {
     ScanTiling t;
     if (int e = check_common(B, L, Di, H, dtype, t)) return e;
+    if (mode == AB_SCAN_PIPELINED) {
+        AB_REQUIRE(dyssm == nullptr && hstart != nullptr, "selective_scan_bwd: the pipelined mode takes no dyssm and needs the run states");
+        float* part = nullptr;
+        if (int e = ab_scan_pipe_bwd(xa, dlog, Bm, Cm, bc_stride, z, z_stride, dout, A_log, D, hstart, dxa, dBm, dCm, dbc_stride, dz,
+                                     ddlog_parts, &part, ws, ws_bytes, B, L, Di, H, dtype, stream)) return e;
+        int T2 = 0, Cs2 = 0;
+        ab_scan_pipe_plan(B, L, Di, dtype, nullptr, &Cs2, nullptr, nullptr, &T2);
+        scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, PR_CH), PR_CH * PR_Q, 0, stream>>>(part, dA_log, dD, B, Di, Cs2, Di / Cs2,
+                                                                                                (int)ab_ceil_div(L, T2));
+        AB_LAUNCH_CHECK();
+        return AB_OK;
+    }
     const WsLayout wl = ws_layout(t, B, Di);
     AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
     AB_REQUIRE(hstart != nullptr, "selective_scan_bwd: hstart (saved by the forward) is required");

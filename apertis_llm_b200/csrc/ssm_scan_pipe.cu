@@ -1,0 +1,923 @@
+// Pipelined persistent selective scan, forward and backward (sm_100a): AB_SCAN_PIPELINED.
+//
+// Same math and the same scanner hand-shake as ssm_scan.cu (core.py:324-353, :383, :394-396), different schedule.
+// The one-tile-per-CTA kernels spend half of a tile's life waiting for the state that enters it; here a CTA is
+// persistent, takes tiles from an atomic ticket (tile order = scan order, chains interleaved) and software-pipelines
+// them so that the wait of tile k-1 lies behind the whole first stage of tile k:
+//
+//   stage 1 (tile k, operands in shared memory, staged by TMA NST tiles ahead):  everything that does not depend on
+//            the state entering the tile.  The recurrence is linear in that state, so the forward evaluates, per
+//            element, y_t = alpha_t * h_in(run) + beta_t with alpha/beta kept in REGISTERS; the backward runs the whole
+//            forward recompute (from the per-run states saved by the forward: no intra-tile dependency), emits
+//            dxa / dC / dz and keeps (abar, g, h_{t-1}) in registers.  The run aggregates go to shared memory.
+//   barrier  (one __syncthreads per tile).  The tile's operand buffers are free from here on: the next TMA load is
+//            issued into them immediately.
+//   duty warp (one per 64-channel column, rotating): composes the run aggregates in run order, leaves the per-run
+//            coefficients in shared memory and publishes the tile aggregate (self-validating 64-bit words).
+//   stage 2 (tile k-1, registers only): collect the incoming state (its word was prefetched before stage 1), apply it,
+//            store.  forward: one FMA per element; backward: the reverse sweep (dB, d dt, dA_log partials).
+//
+// A thread owns 2 adjacent channels x TSP = 4 consecutive tokens (a "run"); a warp is one run of a 64-channel column,
+// so every shared-memory access is a conflict-free 128-byte row and every global store a full 128-byte line.  Channel
+// pairs are processed with packed f32x2 arithmetic (FFMA2 / FMUL2).  d dt is reduced over the 16 channels of a head
+// with a transposing shuffle butterfly inside the warp and written once, final, as [B, L, H].
+//
+// Deadlock freedom: a CTA's tile indices increase with its pipeline position and a tile's aggregate is published
+// before the CTA waits on any tile with a larger index minus one, so by induction over the tile index every wait is
+// on words whose producers are running; the scanners hold the first tickets.  The launch epoch lives in device memory
+// and is advanced by the last CTA to finish, which also resets the ticket: replayed CUDA graphs stay valid.
+#include "ssm_scan_shared.cuh"
+
+namespace {
+using namespace ab_scan;
+
+constexpr int TSP = 4;             // tokens per run
+constexpr int PIPE_SCAN_K = 32;    // tile aggregates a scanner polls per round
+constexpr int INFO_RING = 8;
+constexpr int PIPE_SPIN_LIMIT = 1 << 19;   // ~0.5 s of polling: a protocol error raises the flag instead of hanging the GPU
+
+typedef unsigned long long f2;     // two packed fp32 (channel pair)
+
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_bcast(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_ex2(f2 v) { float a, b; f2_unpack(v, a, b); return f2_pack(ab_ex2(a), ab_ex2(b)); }
+
+// sigmoid of a channel pair.  bf16 activations: single-MUFU tanh form (rel. error ~5e-4, below bf16 resolution);
+// f32 activations: ex2 + rcp
+template <typename T>
+__device__ __forceinline__ f2 f2_sigmoid(f2 z) {
+    if constexpr (sizeof(T) == 2) {
+        float a, b;
+        f2_unpack(f2_mul(z, f2_bcast(0.5f)), a, b);
+        float ta, tb;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+        return f2_fma(f2_pack(ta, tb), f2_bcast(0.5f), f2_bcast(0.5f));
+    } else {
+        float a, b;
+        f2_unpack(z, a, b);
+        return f2_pack(ab_sigmoid(a), ab_sigmoid(b));
+    }
+}
+
+// two adjacent channels from shared memory / to global memory
+template <typename T>
+__device__ __forceinline__ f2 lds_pair(const T* p) {
+    if constexpr (sizeof(T) == 2) {
+        const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+        return f2_pack(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+    } else {
+        return *reinterpret_cast<const f2*>(p);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void stg_pair(T* p, f2 v) {
+    if constexpr (sizeof(T) == 2) {
+        float a, b;
+        f2_unpack(v, a, b);
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        *reinterpret_cast<f2*>(p) = v;
+    }
+}
+
+__device__ __forceinline__ void ld_relaxed_v2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+struct __align__(16) TileInfo { int b, c0, row0, tile_lin; };      // b < 0: no tile
+
+struct PipeParams {
+    ScanParams s;
+    unsigned int* sync;          // [0] ticket, [1] finished CTAs, [2] launch epoch - 1
+    float* hrun;                 // [B, ceil(L/TSP), Di] state entering every run (written by the forward)
+    float* ddlog;                // backward: [B, L, H] fp32, final
+    int ntiles;
+    int scan_k;                  // tile aggregates a scanner polls per round
+    unsigned int poll_ns;        // back-off between polls of the incoming-state word
+};
+
+__device__ __forceinline__ TileInfo decode_tile_info(const PipeParams& p, int tile, int TT, bool reverse) {
+    TileInfo t;
+    if (tile < 0 || tile >= p.ntiles) { t.b = -1; t.c0 = 0; t.row0 = 0; t.tile_lin = 0; return t; }
+    const int chain = tile % p.s.nchains, jj = tile / p.s.nchains;
+    const int j = reverse ? p.s.nchunks - 1 - jj : jj;
+    t.b = chain / p.s.nslab;
+    t.c0 = (chain % p.s.nslab) * p.s.Cs;
+    t.row0 = j * TT;
+    t.tile_lin = chain * p.s.nchunks + j;
+    return t;
+}
+
+// shared-memory carve-up, identical on host and device
+struct PipeSmem {
+    uint32_t pitch, off_sdel, sdel_stride, off_runP, off_runS, off_partA, off_partD, off_bars, off_info, total;
+};
+__host__ __device__ inline PipeSmem pipe_smem(int Cs, int TT, int NR, int NST, int nops, int esize, bool bwd) {
+    PipeSmem m;
+    const uint32_t tile_bytes = (uint32_t)TT * Cs * esize;
+    m.pitch = (tile_bytes + 127u) & ~127u;
+    uint32_t o = (uint32_t)NST * nops * m.pitch;
+    m.off_sdel = o;
+    m.sdel_stride = (((uint32_t)(TT + 1) * (Cs >> 4)) + 3u) & ~3u;      // floats per stage
+    o += (uint32_t)NST * m.sdel_stride * 4;
+    m.off_runP = o; o += 2u * NR * Cs * 4;
+    m.off_runS = o; o += 2u * NR * Cs * 4;
+    m.off_partA = o; if (bwd) o += 2u * NR * Cs * 4;
+    m.off_partD = o; if (bwd) o += 2u * NR * Cs * 4;
+    o = (o + 15u) & ~15u;
+    m.off_info = o; o += INFO_RING * 16;
+    m.off_bars = o; o += (uint32_t)NST * 8;
+    m.total = (o + 127u) & ~127u;
+    return m;
+}
+
+// last CTA out advances the device epoch and resets the ticket / finished counters for the next launch
+__device__ __forceinline__ void grid_finish(unsigned int* sync) {
+    __threadfence();
+    const unsigned int done = atomicAdd(sync + 1, 1u);
+    if (done == gridDim.x - 1) {
+        const unsigned int e = *reinterpret_cast<volatile unsigned int*>(sync + 2);
+        sync[0] = 0; sync[1] = 0;
+        sync[2] = (e + 1u) % ((1u << 30) - 2u);
+        __threadfence();
+    }
+}
+__device__ __forceinline__ void cta_finish(unsigned int* sync) {
+    __syncthreads();
+    if (threadIdx.x == 0) grid_finish(sync);
+}
+// The scanner's threads leave their loop at different times (a channel is done when its last tile has published), so
+// lanes of one warp may arrive here while their siblings still execute the loop's barriers: no __syncthreads on this
+// path (two different aligned barriers inside one diverged warp are undefined behaviour); the last thread to arrive,
+// counted in shared memory, signs the CTA off.
+__device__ __forceinline__ void scanner_finish(unsigned int* sync, unsigned int* s_left) {
+    __threadfence();
+    if (atomicAdd(s_left, 1u) == blockDim.x - 1) grid_finish(sync);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+struct FwdSet { f2 al[TSP], be[TSP]; };
+
+template <typename T, int NWC, int NR, int NST, int CS>
+__global__ void __launch_bounds__(32 * NWC * NR, (768 / (32 * NWC * NR) > 0 ? 768 / (32 * NWC * NR) : 1)) scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa,
+                                                                     const __grid_constant__ CUtensorMap tm_b,
+                                                                     const __grid_constant__ CUtensorMap tm_c,
+                                                                     const __grid_constant__ CUtensorMap tm_z,
+                                                                     const __grid_constant__ PipeParams p) {
+    constexpr int TT = NR * TSP;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ScanParams& sp = p.s;
+    const int Cs = CS ? CS : sp.Cs, nh = Cs >> 4;          // CS != 0: slab width known at compile time
+    const PipeSmem lay = pipe_smem(Cs, TT, NR, NST, 4, (int)sizeof(T), false);
+    const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T);
+    float* sdel = reinterpret_cast<float*>(smem + lay.off_sdel);
+    float* runP = reinterpret_cast<float*>(smem + lay.off_runP);
+    float* runS = reinterpret_cast<float*>(smem + lay.off_runS);
+    TileInfo* s_info = reinterpret_cast<TileInfo*>(smem + lay.off_info);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    __shared__ unsigned int s_first, s_epoch, s_left;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wc = warp % NWC, run = warp / NWC;
+    int cl = wc * 64 + 2 * lane;
+    const bool act = cl < Cs;
+    if (!act) cl = Cs - 2;
+    const int hh = cl >> 4;
+    const int d_row = tid / nh, d_hh = tid - d_row * nh;       // dt staging element of this thread
+    const bool d_act = tid < TT * nh;
+
+    if (tid == 0) {
+        s_epoch = *reinterpret_cast<volatile unsigned int*>(p.sync + 2) + 1u;
+        s_first = atomicAdd(p.sync, 1u);
+        s_left = 0;
+        for (int s = 0; s < NST; ++s) ab_mbar_init(&bars[s], 1);
+        ab_fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    if ((int)s_first < sp.n_scan) {
+        float* hs = runS + 2 * NR * Cs - Cs;          // generic scanner path only; the ring may use everything below
+        scanner_role<+1>(sp, epoch, p.scan_k, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
+        scanner_finish(p.sync, &s_left);
+        return;
+    }
+
+    auto issue_tile = [&](int s, const TileInfo& ti) {         // thread 0 only
+        ab_mbar_expect_tx(&bars[s], 4u * tile_bytes);
+        unsigned char* dst = smem + (size_t)s * 4 * lay.pitch;
+        ab_tma_load_3d(dst, &tm_b, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &bars[s], ti.c0, ti.row0, ti.b);
+    };
+    auto load_dlog = [&](const TileInfo& ti) -> float {        // raw dt logit of this thread's staging element
+        const int row = ti.row0 + d_row;
+        if (!d_act || ti.b < 0 || row >= sp.L) return -1e30f;
+        return ab_to_float(reinterpret_cast<const T*>(sp.dlog)[((size_t)ti.b * sp.L + row) * sp.H + (ti.c0 >> 4) + d_hh]);
+    };
+    auto store_sdel = [&](int s, float raw) {
+        if (d_act) sdel[s * lay.sdel_stride + tid] = raw < -1e29f ? 0.f : ab_softplus_fast(raw);
+    };
+
+    // ---- prologue: tickets and loads of the first NST pipeline positions
+    int pending = -1;
+    if (tid == 0) {
+        const int first = (int)s_first - sp.n_scan;
+        const int base = (int)atomicAdd(p.sync, (unsigned)NST) - sp.n_scan;
+        for (int s = 0; s < NST; ++s) {
+            const TileInfo ti = decode_tile_info(p, s == 0 ? first : base + s - 1, TT, false);
+            s_info[s] = ti;
+            if (ti.b >= 0) issue_tile(s, ti);
+        }
+        pending = base + NST - 1;
+    }
+    __syncthreads();
+    for (int s = 0; s < NST; ++s) store_sdel(s, load_dlog(s_info[s]));
+    __syncthreads();
+
+    const int nrt = (sp.L + TSP - 1) / TSP;   // saved run states per sequence
+    uint32_t phase_bits = 0;                // mbarrier parity per stage
+
+    bool prev_valid = false;
+    auto body = [&](int k, int s, FwdSet& cur, FwdSet& prv) -> bool {
+        const TileInfo cti = s_info[k & (INFO_RING - 1)];
+        const bool valid = cti.b >= 0, have_prev = prev_valid;
+        if (!valid && !have_prev) return false;
+        prev_valid = valid;
+        if (tid == 0) {
+            s_info[(k + NST) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, false);
+            if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - sp.n_scan;
+        }
+        // the word that carries the state entering the previous tile: requested now, looked at after stage 1
+        unsigned long long w0 = 0, w1 = 0;
+        const unsigned long long* wprev = sp.inclw + (size_t)s_info[(k - 1) & (INFO_RING - 1)].tile_lin * Cs + cl;
+        if (have_prev) ld_relaxed_v2(wprev, w0, w1);
+
+        // ---- stage 1
+        if (valid) {
+            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + cti.c0 + cl));
+            const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + cti.c0 + cl));
+            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E), Dv = f2_pack(dv2.x, dv2.y);
+            const unsigned char* st = smem + (size_t)s * 4 * lay.pitch;
+            const T* sB = reinterpret_cast<const T*>(st) + cl;
+            const T* sX = reinterpret_cast<const T*>(st + lay.pitch) + cl;
+            const T* sC = reinterpret_cast<const T*>(st + 2 * lay.pitch) + cl;
+            const T* sZ = reinterpret_cast<const T*>(st + 3 * lay.pitch) + cl;
+            const float* sd = sdel + s * lay.sdel_stride + hh;
+            ab_mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            f2 h0 = f2_bcast(0.f), pc = f2_bcast(1.f);
+#pragma unroll
+            for (int t = 0; t < TSP; ++t) {
+                const int r = run * TSP + t;
+                const f2 a = f2_ex2(f2_mul(A2, f2_bcast(sd[r * nh])));
+                const f2 bv = lds_pair<T>(sB + (size_t)r * Cs), cv = lds_pair<T>(sC + (size_t)r * Cs);
+                const f2 xv = lds_pair<T>(sX + (size_t)r * Cs), zv = lds_pair<T>(sZ + (size_t)r * Cs);
+                pc = f2_mul(pc, a);
+                h0 = f2_fma(a, h0, bv);
+                const f2 gate = f2_mul(zv, f2_sigmoid<T>(zv));
+                const f2 cg = f2_mul(cv, gate);
+                cur.al[t] = f2_mul(cg, pc);
+                cur.be[t] = f2_fma(cg, h0, f2_mul(f2_mul(Dv, xv), gate));
+            }
+            if (act) {
+                *reinterpret_cast<f2*>(runP + ((k & 1) * NR + run) * Cs + cl) = pc;
+                *reinterpret_cast<f2*>(runS + ((k & 1) * NR + run) * Cs + cl) = h0;
+            }
+        }
+        __syncthreads();
+        phase_bits ^= valid ? (1u << s) : 0u;
+
+        // ---- refill the freed stage, request the dt logits of that tile
+        const TileInfo nx = s_info[(k + NST) & (INFO_RING - 1)];
+        if (tid == 0 && nx.b >= 0) issue_tile(s, nx);
+        const float draw = load_dlog(nx);
+
+        // ---- duty warp of this column: run prefixes in place, tile aggregate -> scanner
+        if (valid && run == k % NR && act) {
+            float* rp = runP + (k & 1) * NR * Cs + cl;
+            float* rs = runS + (k & 1) * NR * Cs + cl;
+            f2 Pa = f2_bcast(1.f), Sa = f2_bcast(0.f);
+#pragma unroll
+            for (int r0 = 0; r0 < NR; r0 += 4) {
+                f2 P4[4], S4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + u < NR) { P4[u] = *reinterpret_cast<const f2*>(rp + (r0 + u) * Cs); S4[u] = *reinterpret_cast<const f2*>(rs + (r0 + u) * Cs); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + u < NR) {
+                        *reinterpret_cast<f2*>(rp + (r0 + u) * Cs) = Pa;
+                        *reinterpret_cast<f2*>(rs + (r0 + u) * Cs) = Sa;
+                        Sa = f2_fma(P4[u], Sa, S4[u]);
+                        Pa = f2_mul(Pa, P4[u]);
+                    }
+            }
+            float p0, p1, s0, s1;
+            f2_unpack(Pa, p0, p1); f2_unpack(Sa, s0, s1);
+            unsigned long long* w = sp.words + ((size_t)cti.tile_lin * Cs + cl) * 2;
+            st_relaxed_v2(w, pack_word(epoch, ST_AGG, p0), pack_word(epoch, ST_AGG, s0));
+            st_relaxed_v2(w + 2, pack_word(epoch, ST_AGG, p1), pack_word(epoch, ST_AGG, s1));
+        }
+
+        // ---- stage 2 of the previous tile
+        if (have_prev) {
+            const TileInfo pti = s_info[(k - 1) & (INFO_RING - 1)];
+            int spins = 0;
+            while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
+                if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
+                __nanosleep(p.poll_ns);
+                ld_relaxed_v2(wprev, w0, w1);
+            }
+            const f2 hin = f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1));
+            const int pb = ((k - 1) & 1) * NR + run;
+            const f2 h = f2_fma(*reinterpret_cast<const f2*>(runP + pb * Cs + cl), hin, *reinterpret_cast<const f2*>(runS + pb * Cs + cl));
+            if (act) {
+                const int rg = pti.row0 / TSP + run;
+                if (rg < nrt) *reinterpret_cast<f2*>(p.hrun + ((size_t)pti.b * nrt + rg) * sp.Di + pti.c0 + cl) = h;
+                const int row = pti.row0 + run * TSP;
+                T* yo = reinterpret_cast<T*>(sp.y) + ((size_t)pti.b * sp.L + row) * sp.Di + pti.c0 + cl;
+#pragma unroll
+                for (int t = 0; t < TSP; ++t)
+                    if (row + t < sp.L) stg_pair<T>(yo + (size_t)t * sp.Di, f2_fma(prv.al[t], h, prv.be[t]));
+            }
+        }
+        if (nx.b >= 0) store_sdel(s, draw);
+        return true;
+    };
+
+    FwdSet A, Bq;
+#pragma unroll
+    for (int t = 0; t < TSP; ++t) { A.al[t] = 0; A.be[t] = 0; Bq.al[t] = 0; Bq.be[t] = 0; }
+    int s = 0;
+    for (int k = 0;; k += 2) {
+        if (!body(k, s, A, Bq)) break;
+        s = s + 1 == NST ? 0 : s + 1;
+        if (!body(k + 1, s, Bq, A)) break;
+        s = s + 1 == NST ? 0 : s + 1;
+    }
+    cta_finish(p.sync);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct BwdSet { f2 a[TSP], g[TSP], hp[TSP]; float dl[TSP]; f2 anext, accD, A2; };
+
+template <typename T, int NWC, int NR, int NST, int CS>
+__global__ void __launch_bounds__(32 * NWC * NR, 512 / (32 * NWC * NR) > 0 ? 512 / (32 * NWC * NR) : 1) scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa,
+                                                                     const __grid_constant__ CUtensorMap tm_b,
+                                                                     const __grid_constant__ CUtensorMap tm_c,
+                                                                     const __grid_constant__ CUtensorMap tm_z,
+                                                                     const __grid_constant__ CUtensorMap tm_do,
+                                                                     const __grid_constant__ PipeParams p) {
+    constexpr int TT = NR * TSP;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ScanParams& sp = p.s;
+    const int Cs = CS ? CS : sp.Cs, nh = Cs >> 4;          // CS != 0: slab width known at compile time
+    const PipeSmem lay = pipe_smem(Cs, TT, NR, NST, 5, (int)sizeof(T), true);
+    const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T);
+    float* sdel = reinterpret_cast<float*>(smem + lay.off_sdel);
+    float* runP = reinterpret_cast<float*>(smem + lay.off_runP);
+    float* runS = reinterpret_cast<float*>(smem + lay.off_runS);
+    float* partA = reinterpret_cast<float*>(smem + lay.off_partA);
+    float* partD = reinterpret_cast<float*>(smem + lay.off_partD);
+    TileInfo* s_info = reinterpret_cast<TileInfo*>(smem + lay.off_info);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    __shared__ unsigned int s_first, s_epoch, s_left;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wc = warp % NWC, run = warp / NWC;
+    int cl = wc * 64 + 2 * lane;
+    const bool act = cl < Cs;
+    if (!act) cl = Cs - 2;
+    const int hh = cl >> 4;
+    const int d_row = tid / nh, d_hh = tid - d_row * nh;
+    const bool d_act = tid < (TT + 1) * nh;
+
+    if (tid == 0) {
+        s_epoch = *reinterpret_cast<volatile unsigned int*>(p.sync + 2) + 1u;
+        s_first = atomicAdd(p.sync, 1u);
+        s_left = 0;
+        for (int s = 0; s < NST; ++s) ab_mbar_init(&bars[s], 1);
+        ab_fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    if ((int)s_first < sp.n_scan) {
+        float* hs = partD + 2 * NR * Cs - Cs;
+        scanner_role<-1>(sp, epoch, p.scan_k, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
+        scanner_finish(p.sync, &s_left);
+        return;
+    }
+
+    auto issue_tile = [&](int s, const TileInfo& ti) {
+        ab_mbar_expect_tx(&bars[s], 5u * tile_bytes);
+        unsigned char* dst = smem + (size_t)s * 5 * lay.pitch;
+        ab_tma_load_3d(dst, &tm_b, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &bars[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 4 * lay.pitch, &tm_do, &bars[s], ti.c0, ti.row0, ti.b);
+    };
+    auto load_dlog = [&](const TileInfo& ti) -> float {
+        const int row = ti.row0 + d_row;
+        if (!d_act || ti.b < 0 || row >= sp.L) return -1e30f;
+        return ab_to_float(reinterpret_cast<const T*>(sp.dlog)[((size_t)ti.b * sp.L + row) * sp.H + (ti.c0 >> 4) + d_hh]);
+    };
+    auto store_sdel = [&](int s, float raw) {
+        if (d_act) sdel[s * lay.sdel_stride + tid] = raw < -1e29f ? 0.f : ab_softplus_fast(raw);
+    };
+
+    int pending = -1;
+    if (tid == 0) {
+        const int first = (int)s_first - sp.n_scan;
+        const int base = (int)atomicAdd(p.sync, (unsigned)NST) - sp.n_scan;
+        for (int s = 0; s < NST; ++s) {
+            const TileInfo ti = decode_tile_info(p, s == 0 ? first : base + s - 1, TT, true);
+            s_info[s] = ti;
+            if (ti.b >= 0) issue_tile(s, ti);
+        }
+        pending = base + NST - 1;
+    }
+    __syncthreads();
+    for (int s = 0; s < NST; ++s) store_sdel(s, load_dlog(s_info[s]));
+    __syncthreads();
+
+    const int nrt = (sp.L + TSP - 1) / TSP;
+    uint32_t phase_bits = 0;
+    int part_tile = -1;          // tile whose per-run dA_log / dD partials sit in shared memory (CTA-uniform)
+    int part_buf = 0;
+    const float inv_log2e = 1.f / AB_LOG2E;
+
+    // sum the per-run partials of a finished tile in run order (deterministic) -> per-tile partials in global memory
+    auto reduce_parts = [&](int tile_lin, int buf) {
+        const float* pa = partA + buf * NR * Cs + cl;
+        const float* pd = partD + buf * NR * Cs + cl;
+        f2 sa = f2_bcast(0.f), sd2 = f2_bcast(0.f);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            sa = f2_add(sa, *reinterpret_cast<const f2*>(pa + r * Cs));
+            sd2 = f2_add(sd2, *reinterpret_cast<const f2*>(pd + r * Cs));
+        }
+        *reinterpret_cast<f2*>(sp.part + ((size_t)tile_lin * 2 + 0) * Cs + cl) = sa;
+        *reinterpret_cast<f2*>(sp.part + ((size_t)tile_lin * 2 + 1) * Cs + cl) = sd2;
+    };
+
+    bool prev_valid = false;
+    auto body = [&](int k, int s, BwdSet& cur, BwdSet& prv) -> bool {
+        const TileInfo cti = s_info[k & (INFO_RING - 1)];
+        const bool valid = cti.b >= 0, have_prev = prev_valid;
+        if (!valid && !have_prev) return false;
+        prev_valid = valid;
+        if (tid == 0) {
+            s_info[(k + NST) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, true);
+            if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - sp.n_scan;
+        }
+        unsigned long long w0 = 0, w1 = 0;
+        const unsigned long long* wprev = sp.inclw + (size_t)s_info[(k - 1) & (INFO_RING - 1)].tile_lin * Cs + cl;
+        if (have_prev) ld_relaxed_v2(wprev, w0, w1);
+
+        // ---- stage 1: forward recompute from the saved run state, dxa / dC / dz, reverse run aggregates
+        if (valid) {
+            const size_t tok0 = (size_t)cti.b * sp.L + cti.row0 + run * TSP;
+            const int cg0 = cti.c0 + cl;
+            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + cg0));
+            const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + cg0));
+            const int rg = cti.row0 / TSP + run;
+            f2 h = rg < nrt ? *reinterpret_cast<const f2*>(p.hrun + ((size_t)cti.b * nrt + rg) * sp.Di + cg0) : f2_bcast(0.f);
+            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E), Dv = f2_pack(dv2.x, dv2.y);
+            cur.A2 = A2;
+            const unsigned char* st = smem + (size_t)s * 5 * lay.pitch;
+            const T* sB = reinterpret_cast<const T*>(st) + cl;
+            const T* sX = reinterpret_cast<const T*>(st + lay.pitch) + cl;
+            const T* sC = reinterpret_cast<const T*>(st + 2 * lay.pitch) + cl;
+            const T* sZ = reinterpret_cast<const T*>(st + 3 * lay.pitch) + cl;
+            const T* sO = reinterpret_cast<const T*>(st + 4 * lay.pitch) + cl;
+            const float* sd = sdel + s * lay.sdel_stride + hh;
+            T* dxa_o = reinterpret_cast<T*>(sp.dxa) + tok0 * sp.Di + cg0;
+            T* dz_o = reinterpret_cast<T*>(sp.dz) + tok0 * sp.Di + cg0;
+            T* dc_o = reinterpret_cast<T*>(sp.dCm) + tok0 * sp.dbc_stride + cg0;
+            const int row = cti.row0 + run * TSP;
+            ab_mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            f2 accD = f2_bcast(0.f);
+            const f2 one = f2_bcast(1.f), neg1 = f2_bcast(-1.f);
+#pragma unroll
+            for (int t = 0; t < TSP; ++t) {
+                const int r = run * TSP + t;
+                cur.dl[t] = sd[r * nh];
+                cur.a[t] = f2_ex2(f2_mul(A2, f2_bcast(cur.dl[t])));
+                const f2 bv = lds_pair<T>(sB + (size_t)r * Cs), cv = lds_pair<T>(sC + (size_t)r * Cs);
+                const f2 xv = lds_pair<T>(sX + (size_t)r * Cs), zv = lds_pair<T>(sZ + (size_t)r * Cs);
+                const f2 dov = lds_pair<T>(sO + (size_t)r * Cs);
+                const f2 sg = f2_sigmoid<T>(zv);
+                const f2 dyv = f2_mul(dov, f2_mul(zv, sg));            // grad of (y_ssm + D*xa)
+                cur.hp[t] = h;
+                h = f2_fma(cur.a[t], h, bv);
+                const f2 yv = f2_fma(Dv, xv, f2_mul(cv, h));
+                // silu'(z) = sg * (1 + z * (1 - sg))
+                const f2 dsilu = f2_mul(sg, f2_fma(zv, f2_fma(sg, neg1, one), one));
+                accD = f2_fma(dyv, xv, accD);
+                cur.g[t] = f2_mul(dyv, cv);
+                if (act && row + t < sp.L) {
+                    stg_pair<T>(dxa_o + (size_t)t * sp.Di, f2_mul(dyv, Dv));
+                    stg_pair<T>(dz_o + (size_t)t * sp.Di, f2_mul(f2_mul(dov, yv), dsilu));
+                    stg_pair<T>(dc_o + (size_t)t * sp.dbc_stride, f2_mul(dyv, h));
+                }
+            }
+            cur.accD = accD;
+            // reverse:  G(first token of the run) = Gs + Pr * G(first token of the next run)
+            cur.anext = f2_ex2(f2_mul(A2, f2_bcast(sd[(run * TSP + TSP) * nh])));
+            f2 Gs = cur.g[TSP - 1], Pr = cur.anext;
+#pragma unroll
+            for (int t = TSP - 2; t >= 0; --t) {
+                Gs = f2_fma(cur.a[t + 1], Gs, cur.g[t]);
+                Pr = f2_mul(Pr, cur.a[t + 1]);
+            }
+            if (act) {
+                *reinterpret_cast<f2*>(runP + ((k & 1) * NR + run) * Cs + cl) = Pr;
+                *reinterpret_cast<f2*>(runS + ((k & 1) * NR + run) * Cs + cl) = Gs;
+            }
+        }
+        __syncthreads();
+        phase_bits ^= valid ? (1u << s) : 0u;
+
+        const TileInfo nx = s_info[(k + NST) & (INFO_RING - 1)];
+        if (tid == 0 && nx.b >= 0) issue_tile(s, nx);
+        const float draw = load_dlog(nx);
+
+        // ---- duty warp: reverse run prefixes in place, publish; per-tile dA_log / dD partials of the tile before last
+        if (run == k % NR && act) {
+            if (valid) {
+                float* rp = runP + (k & 1) * NR * Cs + cl;
+                float* rs = runS + (k & 1) * NR * Cs + cl;
+                f2 Pa = f2_bcast(1.f), Sa = f2_bcast(0.f);
+#pragma unroll
+                for (int r0 = NR - 1; r0 >= 0; r0 -= 4) {
+                    f2 P4[4], S4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (r0 - u >= 0) { P4[u] = *reinterpret_cast<const f2*>(rp + (r0 - u) * Cs); S4[u] = *reinterpret_cast<const f2*>(rs + (r0 - u) * Cs); }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (r0 - u >= 0) {
+                            *reinterpret_cast<f2*>(rp + (r0 - u) * Cs) = Pa;
+                            *reinterpret_cast<f2*>(rs + (r0 - u) * Cs) = Sa;
+                            Sa = f2_fma(P4[u], Sa, S4[u]);
+                            Pa = f2_mul(Pa, P4[u]);
+                        }
+                }
+                float p0, p1, s0, s1;
+                f2_unpack(Pa, p0, p1); f2_unpack(Sa, s0, s1);
+                unsigned long long* w = sp.words + ((size_t)cti.tile_lin * Cs + cl) * 2;
+                st_relaxed_v2(w, pack_word(epoch, ST_AGG, p0), pack_word(epoch, ST_AGG, s0));
+                st_relaxed_v2(w + 2, pack_word(epoch, ST_AGG, p1), pack_word(epoch, ST_AGG, s1));
+            }
+            if (part_tile >= 0) reduce_parts(part_tile, part_buf);
+        }
+        part_tile = -1;
+
+        // ---- stage 2 of the previous tile: reverse sweep from registers
+        if (have_prev) {
+            const TileInfo pti = s_info[(k - 1) & (INFO_RING - 1)];
+            int spins = 0;
+            while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
+                if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
+                __nanosleep(p.poll_ns);
+                ld_relaxed_v2(wprev, w0, w1);
+            }
+            const f2 Gin = f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1));
+            const int pb = ((k - 1) & 1) * NR + run;
+            const f2 Gn = f2_fma(*reinterpret_cast<const f2*>(runP + pb * Cs + cl), Gin, *reinterpret_cast<const f2*>(runS + pb * Cs + cl));
+            f2 q = f2_mul(prv.anext, Gn);
+            f2 accA = f2_bcast(0.f);
+            float dd[TSP];
+            const int row = pti.row0 + run * TSP;
+            T* db_o = reinterpret_cast<T*>(sp.dBm) + ((size_t)pti.b * sp.L + row) * sp.dbc_stride + pti.c0 + cl;
+#pragma unroll
+            for (int t = TSP - 1; t >= 0; --t) {
+                const f2 Gt = f2_add(prv.g[t], q);
+                if (act && row + t < sp.L) stg_pair<T>(db_o + (size_t)t * sp.dbc_stride, Gt);
+                const f2 e = f2_mul(f2_mul(Gt, prv.hp[t]), prv.a[t]);          // d abar * abar
+                float e0, e1;
+                f2_unpack(f2_mul(e, prv.A2), e0, e1);
+                dd[t] = e0 + e1;
+                accA = f2_fma(e, f2_bcast(prv.dl[t]), accA);
+                q = f2_mul(prv.a[t], Gt);
+            }
+            // d delta of a head = sum over its 16 channels = 8 lanes: transposing butterfly, one token per lane pair
+            {
+                const bool b2 = lane & 4, b1 = lane & 2;
+                float v0 = b2 ? dd[2] : dd[0], v1 = b2 ? dd[3] : dd[1];
+                const float s0 = b2 ? dd[0] : dd[2], s1 = b2 ? dd[1] : dd[3];
+                v0 += __shfl_xor_sync(0xffffffffu, s0, 4);
+                v1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+                float wv = b1 ? v1 : v0;
+                const float sv = b1 ? v0 : v1;
+                wv += __shfl_xor_sync(0xffffffffu, sv, 2);
+                wv += __shfl_xor_sync(0xffffffffu, wv, 1);
+                const int tt = (b2 ? 2 : 0) + (b1 ? 1 : 0);
+                const float dlt = b2 ? (b1 ? prv.dl[3] : prv.dl[2]) : (b1 ? prv.dl[1] : prv.dl[0]);
+                // d dlog = d delta * sigmoid(dlog) = d delta * (1 - exp(-delta));  A = A2 / log2e
+                if (act && !(lane & 1) && row + tt < sp.L)
+                    p.ddlog[((size_t)pti.b * sp.L + row + tt) * sp.H + ((pti.c0 + cl) >> 4)] = wv * inv_log2e * (1.f - __expf(-dlt));
+            }
+            if (act) {
+                const int qb = ((k - 1) & 1) * NR + run;
+                *reinterpret_cast<f2*>(partA + qb * Cs + cl) = f2_mul(f2_mul(accA, prv.A2), f2_bcast(inv_log2e));
+                *reinterpret_cast<f2*>(partD + qb * Cs + cl) = prv.accD;
+            }
+            part_tile = pti.tile_lin;
+            part_buf = (k - 1) & 1;
+        }
+        if (nx.b >= 0) store_sdel(s, draw);
+        return true;
+    };
+
+    BwdSet A, Bq;
+    int s = 0;
+    for (int k = 0;; k += 2) {
+        if (!body(k, s, A, Bq)) break;
+        s = s + 1 == NST ? 0 : s + 1;
+        if (!body(k + 1, s, Bq, A)) break;
+        s = s + 1 == NST ? 0 : s + 1;
+    }
+    // partials of the last tile
+    __syncthreads();
+    if (part_tile >= 0 && run == 0 && act) reduce_parts(part_tile, part_buf);
+    cta_finish(p.sync);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct PipeTiling { int Cs, NWC, NR, TT, nslab, nchunks, esize; };
+
+int pipe_env(const char* name, int dflt, int alt, int alt2 = -1) {
+    const char* e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return (v == alt || v == alt2) ? v : dflt;
+}
+int pipe_nst(bool bwd) {
+    static const int f = pipe_env("APERTIS_B200_SCAN_NST_FWD", 2, 3), b = pipe_env("APERTIS_B200_SCAN_NST_BWD", 3, 2);
+    return bwd ? b : f;
+}
+// bf16, 64-channel slab: 16 runs (512 threads, 128 registers, a few spills) or 12 runs (384 threads, no spills)
+int pipe_nr_bwd16() {
+    static const int v = pipe_env("APERTIS_B200_SCAN_NR_BWD", 16, 12);
+    return v;
+}
+
+// slab = 64 channels when the width allows it, else the widest head-aligned divisor of Di that one CTA row covers.
+// Forward and backward tile the sequence independently (the saved states are per run of TSP tokens).
+bool pipe_tiling(int L, int Di, int dtype, bool bwd, PipeTiling& t) {
+    t.esize = dtype == AB_F32 ? 4 : 2;
+    int Cs = 0;
+    if (Di % 64 == 0) Cs = 64;
+    else
+        for (int c = 256; c >= 16; c -= 16)
+            if (Di % c == 0) { Cs = c; break; }
+    if (!Cs) return false;
+    t.Cs = Cs;
+    t.NWC = (Cs + 63) / 64;
+    if (Cs * 2 < t.NWC * 64) return false;                      // more than half of the lanes would idle
+    static const int nr_f_bf16[5] = {0, 12, 6, 4, 3}, nr_b_bf16[5] = {0, 16, 8, 5, 4}, nr_f32[5] = {0, 8, 4, 3, 2};
+    t.NR = dtype == AB_F32 ? nr_f32[t.NWC] : (bwd ? nr_b_bf16[t.NWC] : nr_f_bf16[t.NWC]);
+    if (dtype == AB_BF16 && bwd && t.NWC == 1) t.NR = pipe_nr_bwd16();
+    t.TT = t.NR * TSP;
+    t.nslab = Di / Cs;
+    t.nchunks = (int)ab_ceil_div(L, t.TT);
+    return true;
+}
+
+constexpr int PIPE_SMS = 148;          // B200; the plan must not need a device
+// CTAs per SM the shared memory and the register budget of the launch bounds admit
+int pipe_occ_static(const PipeTiling& t, bool bwd) {
+    const PipeSmem m = pipe_smem(t.Cs, t.TT, t.NR, pipe_nst(bwd), bwd ? 5 : 4, t.esize, bwd);
+    int occ = (int)((227u * 1024u) / (m.total + 1024u));
+    const int thr = 32 * t.NWC * t.NR;
+    const int by_reg = bwd ? (512 / thr > 0 ? 512 / thr : 1) : (768 / thr > 0 ? 768 / thr : 1);
+    if (occ > by_reg) occ = by_reg;
+    return occ;
+}
+// one scanner CTA per chain: worth it while the scanners are a small part of the persistent grid
+bool pipe_supported(int B, int L, int Di, int dtype, PipeTiling& tf, PipeTiling& tb) {
+    if (!pipe_tiling(L, Di, dtype, false, tf) || !pipe_tiling(L, Di, dtype, true, tb)) return false;
+    const int occ_b = pipe_occ_static(tb, true), occ_f = pipe_occ_static(tf, false);
+    if (occ_b < 1 || occ_f < 1) return false;
+    const int nchains = B * tf.nslab;
+    return nchains * 4 <= PIPE_SMS * occ_b && nchains * 4 <= PIPE_SMS * occ_f;
+}
+
+struct PipeWs { size_t off_sync, off_err, off_words, off_incl, off_part, total; };
+PipeWs pipe_ws(const PipeTiling& tf, const PipeTiling& tb, int B) {
+    PipeWs w;
+    const PipeTiling& t = tf;
+    const size_t ntiles = (size_t)B * t.nslab * (tf.nchunks > tb.nchunks ? tf.nchunks : tb.nchunks);
+    size_t o = 0;
+    w.off_sync = o; o += 64;
+    w.off_err = o; o += 64;
+    w.off_words = o; o += ntiles * t.Cs * 2 * sizeof(unsigned long long);
+    w.off_incl = o; o += ntiles * t.Cs * sizeof(unsigned long long);
+    w.off_part = o; o += ntiles * 2 * t.Cs * sizeof(float);
+    w.total = (size_t)ab_round_up((int64_t)o, 256);
+    return w;
+}
+
+int pipe_map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di, int64_t row_stride, int Cs, int T) {
+    const int es = dtype == AB_F32 ? 4 : 2;
+    AB_REQUIRE(((uintptr_t)base % 16) == 0 && (row_stride * es) % 16 == 0,
+               "selective_scan: tensor base and row stride must be 16-byte aligned for TMA (stride %lld elems)", (long long)row_stride);
+    uint64_t dims[3] = {(uint64_t)Di, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)row_stride * es, (uint64_t)row_stride * es * L};
+    uint32_t box[3] = {(uint32_t)Cs, (uint32_t)T, 1};
+    return ab_encode_tmap(m, dtype == AB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base,
+                          dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+template <typename K>
+int pipe_grid(K kfn, int threads, size_t smem, int want, int* grid) {
+    // attributes and occupancy are queried once per kernel and shared-memory size (the calls cost tens of microseconds)
+    static thread_local size_t cached_smem = 0;
+    static thread_local int cached_occ = 0, cached_dev = -1;
+    int dev = 0;
+    AB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (cached_smem != smem || cached_dev != dev) {
+        AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AB_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int o = 0;
+        AB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kfn, threads, smem));
+        cached_occ = o; cached_smem = smem; cached_dev = dev;
+    }
+    const int occ = cached_occ;
+    AB_REQUIRE(occ >= 1, "selective_scan (pipelined): kernel does not fit on an SM (smem %zu)", smem);
+    int g = occ * ab_num_sms();
+    if (g > want) g = want;
+    *grid = g;
+    return AB_OK;
+}
+
+template <typename T, int NWC, int NR, int NST, int CS>
+int launch_fwd_pipe_cs(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    const PipeSmem m = pipe_smem(t.Cs, t.TT, NR, NST, 4, (int)sizeof(T), false);
+    auto kfn = scan_fwd_pipe_kernel<T, NWC, NR, NST, CS>;
+    int grid = 0;
+    if (int e = pipe_grid(kfn, 32 * NWC * NR, m.total, p.s.n_scan + p.ntiles, &grid)) return e;
+    AB_REQUIRE(grid > p.s.n_scan, "selective_scan (pipelined): %d chains leave no worker CTA", p.s.n_scan);
+    kfn<<<grid, 32 * NWC * NR, m.total, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+template <typename T, int NWC, int NR, int NST, int CS>
+int launch_bwd_pipe_cs(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    const PipeSmem m = pipe_smem(t.Cs, t.TT, NR, NST, 5, (int)sizeof(T), true);
+    auto kfn = scan_bwd_pipe_kernel<T, NWC, NR, NST, CS>;
+    int grid = 0;
+    if (int e = pipe_grid(kfn, 32 * NWC * NR, m.total, p.s.n_scan + p.ntiles, &grid)) return e;
+    AB_REQUIRE(grid > p.s.n_scan, "selective_scan (pipelined): %d chains leave no worker CTA", p.s.n_scan);
+    kfn<<<grid, 32 * NWC * NR, m.total, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+// slab widths with a specialised kernel: 64 (d_inner a multiple of 64) and 176 (the 1.5B text block)
+template <typename T, int NWC, int NR, int NST>
+int launch_fwd_pipe(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    if (NWC == 1 && t.Cs == 64) return launch_fwd_pipe_cs<T, NWC, NR, NST, NWC == 1 ? 64 : 0>(maps, p, t, st);
+    if (NWC == 3 && t.Cs == 176) return launch_fwd_pipe_cs<T, NWC, NR, NST, NWC == 3 ? 176 : 0>(maps, p, t, st);
+    return launch_fwd_pipe_cs<T, NWC, NR, NST, 0>(maps, p, t, st);
+}
+template <typename T, int NWC, int NR, int NST>
+int launch_bwd_pipe(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    if (NWC == 1 && t.Cs == 64) return launch_bwd_pipe_cs<T, NWC, NR, NST, NWC == 1 ? 64 : 0>(maps, p, t, st);
+    if (NWC == 3 && t.Cs == 176) return launch_bwd_pipe_cs<T, NWC, NR, NST, NWC == 3 ? 176 : 0>(maps, p, t, st);
+    return launch_bwd_pipe_cs<T, NWC, NR, NST, 0>(maps, p, t, st);
+}
+template <typename T, int NWC, int NR>
+int dispatch_fwd(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    return pipe_nst(false) == 2 ? launch_fwd_pipe<T, NWC, NR, 2>(maps, p, t, st) : launch_fwd_pipe<T, NWC, NR, 3>(maps, p, t, st);
+}
+template <typename T, int NWC, int NR>
+int dispatch_bwd(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    return pipe_nst(true) == 2 ? launch_bwd_pipe<T, NWC, NR, 2>(maps, p, t, st) : launch_bwd_pipe<T, NWC, NR, 3>(maps, p, t, st);
+}
+int dispatch_pipe(bool bwd, int dtype, const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    if (dtype == AB_BF16) {
+        if (!bwd) switch (t.NWC) {
+            case 1: return dispatch_fwd<__nv_bfloat16, 1, 12>(maps, p, t, st);
+            case 2: return dispatch_fwd<__nv_bfloat16, 2, 6>(maps, p, t, st);
+            case 3: return dispatch_fwd<__nv_bfloat16, 3, 4>(maps, p, t, st);
+            default: return dispatch_fwd<__nv_bfloat16, 4, 3>(maps, p, t, st);
+        }
+        switch (t.NWC) {
+            case 1: return t.NR == 12 ? dispatch_bwd<__nv_bfloat16, 1, 12>(maps, p, t, st) : dispatch_bwd<__nv_bfloat16, 1, 16>(maps, p, t, st);
+            case 2: return dispatch_bwd<__nv_bfloat16, 2, 8>(maps, p, t, st);
+            case 3: return dispatch_bwd<__nv_bfloat16, 3, 5>(maps, p, t, st);
+            default: return dispatch_bwd<__nv_bfloat16, 4, 4>(maps, p, t, st);
+        }
+    }
+    if (!bwd) switch (t.NWC) {
+        case 1: return dispatch_fwd<float, 1, 8>(maps, p, t, st);
+        case 2: return dispatch_fwd<float, 2, 4>(maps, p, t, st);
+        case 3: return dispatch_fwd<float, 3, 3>(maps, p, t, st);
+        default: return dispatch_fwd<float, 4, 2>(maps, p, t, st);
+    }
+    switch (t.NWC) {
+        case 1: return dispatch_bwd<float, 1, 8>(maps, p, t, st);
+        case 2: return dispatch_bwd<float, 2, 4>(maps, p, t, st);
+        case 3: return dispatch_bwd<float, 3, 3>(maps, p, t, st);
+        default: return dispatch_bwd<float, 4, 2>(maps, p, t, st);
+    }
+}
+
+void fill_common(PipeParams& p, const PipeTiling& t, const PipeWs& wl, void* ws, int B, int L, int Di, int H) {
+    memset(&p, 0, sizeof(p));
+    ScanParams& s = p.s;
+    s.B = B; s.L = L; s.Di = Di; s.H = H;
+    s.Cs = t.Cs; s.T = t.TT; s.n_s = t.NR; s.nslab = t.nslab; s.nchunks = t.nchunks; s.nchains = B * t.nslab;
+    unsigned char* w8 = (unsigned char*)ws;
+    p.sync = (unsigned int*)(w8 + wl.off_sync);
+    s.ticket = p.sync;
+    s.err_flag = (unsigned int*)(w8 + wl.off_err);
+    s.words = (unsigned long long*)(w8 + wl.off_words);
+    s.inclw = (unsigned long long*)(w8 + wl.off_incl);
+    s.part = (float*)(w8 + wl.off_part);
+    s.n_scan = s.nchains;
+    p.ntiles = s.nchains * t.nchunks;
+    static const int scan_k = pipe_env("APERTIS_B200_SCAN_K", PIPE_SCAN_K, 16, 64);
+    p.scan_k = scan_k;
+    static const char* pe = getenv("APERTIS_B200_SCAN_POLL_NS");
+    p.poll_ns = pe ? (unsigned)atoi(pe) : 200u;
+}
+
+}  // namespace
+
+// entry points used by ssm_scan.cu
+bool ab_scan_pipe_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_states, size_t* ws_bytes,
+                       int* bwd_tile_rows) {
+    PipeTiling tf, tb;
+    if (!pipe_supported(B, L, Di, dtype, tf, tb)) return false;
+    if (tile_rows) *tile_rows = tf.TT;
+    if (bwd_tile_rows) *bwd_tile_rows = tb.TT;
+    if (slab) *slab = tf.Cs;
+    if (n_states) *n_states = (int)ab_ceil_div(L, TSP);          // saved states per sequence: one per run of TSP tokens
+    if (ws_bytes) *ws_bytes = pipe_ws(tf, tb, B).total;
+    return true;
+}
+
+int ab_scan_pipe_fwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride, const void* z,
+                     int64_t z_stride, const float* A_log, const float* D, const float* h0, void* y, float* h_last,
+                     float* hrun, void* ws, size_t ws_bytes, int B, int L, int Di, int H, int dtype, cudaStream_t stream) {
+    PipeTiling t, tb;
+    AB_REQUIRE(pipe_supported(B, L, Di, dtype, t, tb), "selective_scan_fwd: the pipelined mode does not cover B=%d L=%d Di=%d (ask ab_selective_scan_plan)", B, L, Di);
+    const PipeWs wl = pipe_ws(t, tb, B);
+    AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_fwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
+    AB_REQUIRE(hrun != nullptr, "selective_scan_fwd: the pipelined mode needs the run-state buffer (hstart)");
+    CUtensorMap maps[4];
+    if (int e = pipe_map3(&maps[0], xa, dtype, B, L, Di, Di, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[1], Bm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[2], Cm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[3], z, dtype, B, L, Di, z_stride, t.Cs, t.TT)) return e;
+    PipeParams p;
+    fill_common(p, t, wl, ws, B, L, Di, H);
+    p.s.dlog = dlog; p.s.A_log = A_log; p.s.Dp = D; p.s.h0 = h0; p.s.y = y; p.s.h_last = h_last;
+    p.hrun = hrun;
+    return dispatch_pipe(false, dtype, maps, p, t, stream);
+}
+
+int ab_scan_pipe_bwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride, const void* z,
+                     int64_t z_stride, const void* dout, const float* A_log, const float* D, const float* hrun, void* dxa,
+                     void* dBm, void* dCm, int64_t dbc_stride, void* dz, float* ddlog, float** part_out, void* ws,
+                     size_t ws_bytes, int B, int L, int Di, int H, int dtype, cudaStream_t stream) {
+    PipeTiling tf, t;
+    AB_REQUIRE(pipe_supported(B, L, Di, dtype, tf, t), "selective_scan_bwd: the pipelined mode does not cover B=%d L=%d Di=%d", B, L, Di);
+    const PipeWs wl = pipe_ws(tf, t, B);
+    AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
+    const int es = dtype == AB_F32 ? 4 : 2;
+    AB_REQUIRE((dbc_stride * es) % 8 == 0, "selective_scan_bwd: dB/dC row stride must be 8-byte aligned");
+    CUtensorMap maps[5];
+    if (int e = pipe_map3(&maps[0], xa, dtype, B, L, Di, Di, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[1], Bm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[2], Cm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[3], z, dtype, B, L, Di, z_stride, t.Cs, t.TT)) return e;
+    if (int e = pipe_map3(&maps[4], dout, dtype, B, L, Di, Di, t.Cs, t.TT)) return e;
+    PipeParams p;
+    fill_common(p, t, wl, ws, B, L, Di, H);
+    p.s.dlog = dlog; p.s.A_log = A_log; p.s.Dp = D;
+    p.s.dxa = dxa; p.s.dBm = dBm; p.s.dCm = dCm; p.s.dz = dz; p.s.dbc_stride = dbc_stride;
+    p.hrun = const_cast<float*>(hrun);
+    p.ddlog = ddlog;
+    *part_out = p.s.part;
+    return dispatch_pipe(true, dtype, maps, p, t, stream);
+}

@@ -20,13 +20,15 @@ from ._lib import AB_BF16, AB_F32, ROW_ALIGN, call, dt, ptr, query, stream_ptr
 # --------------------------------------------------------------------------------------------
 # workspaces
 # --------------------------------------------------------------------------------------------
-_scan_ws = {}       # (device index, stream) -> [tensor, epoch]
-SCAN_MODE = _lib.SCAN_TWO_PASS if os.environ.get("APERTIS_B200_SCAN", "single") == "two_pass" else _lib.SCAN_SINGLE_PASS
+_scan_ws = {}       # (device index, stream, pipelined?) -> [tensor, epoch]
+SCAN_MODE = {"two_pass": _lib.SCAN_TWO_PASS, "single": _lib.SCAN_SINGLE_PASS}.get(
+    os.environ.get("APERTIS_B200_SCAN", "single"), _lib.SCAN_PIPELINED)
 
 
-def _scan_workspace(device, nbytes: int):
-    """Persistent, zero-initialised look-back workspace per (device, stream) with its launch epoch."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+def _scan_workspace(device, nbytes: int, mode: int = _lib.SCAN_SINGLE_PASS):
+    """Persistent, zero-initialised hand-shake workspace per (device, stream) with its launch epoch.  The pipelined
+    schedule keeps its epoch inside the workspace (valid under CUDA-graph replay) and gets a workspace of its own."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, mode == _lib.SCAN_PIPELINED)
     ent = _scan_ws.get(key)
     if ent is None or ent[0].numel() < nbytes:
         epoch = ent[1] if ent is not None else 0
@@ -39,11 +41,13 @@ def _scan_workspace(device, nbytes: int):
     return ent[0], ent[1]
 
 
-def scan_plan(B: int, L: int, Di: int, dtype: torch.dtype):
-    t, s, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+def scan_plan(B: int, L: int, Di: int, dtype: torch.dtype, mode: int = _lib.SCAN_SINGLE_PASS):
+    """-> (tile rows, slab channels, saved states per sequence, workspace bytes, effective mode): a pipelined request
+    the schedule does not cover comes back as single-pass."""
+    t, s, n, m = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(mode)
     ws = ctypes.c_size_t()
-    call("ab_selective_scan_plan", B, L, Di, dt(dtype), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
-    return t.value, s.value, n.value, ws.value
+    call("ab_selective_scan_plan", B, L, Di, dt(dtype), ctypes.byref(m), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    return t.value, s.value, n.value, ws.value, m.value
 
 
 def _row_stride(t: torch.Tensor) -> int:
@@ -184,8 +188,14 @@ class _SelectiveScan(torch.autograd.Function):
         dev = xa.device
         A = A_log.reshape(-1).float().contiguous()
         Dv = D.float().contiguous()
-        T, Cs, nchunks, nws = scan_plan(B, L, Di, xa.dtype)
-        ws, epoch = _scan_workspace(dev, nws)
+        if want_yssm and mode == _lib.SCAN_PIPELINED:
+            mode = _lib.SCAN_SINGLE_PASS                     # y_ssm (output_attentions) is not emitted by the pipelined kernels
+        T, Cs, nchunks, nws, mode = scan_plan(B, L, Di, xa.dtype, mode)
+        if mode != _lib.SCAN_PIPELINED and torch.cuda.is_current_stream_capturing():
+            # the non-pipelined single pass validates its words with a launch epoch passed by value, which a replayed
+            # CUDA graph would freeze: captured steps use the two-pass schedule (no inter-CTA waits, nothing to validate)
+            mode = _lib.SCAN_TWO_PASS
+        ws, epoch = _scan_workspace(dev, nws, mode)
         y = torch.empty_like(xa)
         y_ssm = torch.empty_like(xa) if want_yssm else None
         h_last = torch.empty(B, Di, dtype=torch.float32, device=dev) if want_hlast else None
@@ -210,12 +220,12 @@ class _SelectiveScan(torch.autograd.Function):
         Bm, Cm = BC[..., :Di], BC[..., Di:]
         dy = dy.contiguous()
         dys = dyssm.contiguous() if (dyssm is not None and ctx.want_yssm) else None
-        T, Cs, nchunks, nws = scan_plan(B, L, Di, xa.dtype)
-        ws, epoch = _scan_workspace(dev, nws)
+        T, Cs, nchunks, nws, _ = scan_plan(B, L, Di, xa.dtype, ctx.mode)
+        ws, epoch = _scan_workspace(dev, nws, ctx.mode)
         dxa = torch.empty_like(xa)
         dz = torch.empty_like(xa)
         dbc = torch.empty(B, L, 2 * Di, dtype=xa.dtype, device=dev)       # [dB | dC] rows, ready for the x_param_proj GEMM
-        parts = Di // 4
+        parts = H if ctx.mode == _lib.SCAN_PIPELINED else Di // 4     # pipelined: d dlog comes back final
         ddl = torch.empty(B, L, parts, dtype=torch.float32, device=dev)
         dA = torch.empty(Di, dtype=torch.float32, device=dev)
         dD = torch.empty(Di, dtype=torch.float32, device=dev)
@@ -223,7 +233,7 @@ class _SelectiveScan(torch.autograd.Function):
         call("ab_selective_scan_bwd", ptr(xa), ptr(dlog), ptr(Bm), ptr(Cm), 2 * Di, ptr(z), _row_stride(z), ptr(dy),
              ptr(dys), ptr(A), ptr(Dv), ptr(hstart), ptr(dxa), ptr(dB), ptr(dC), 2 * Di, ptr(dz), ptr(ddl), ptr(dA), ptr(dD),
              ptr(ws), ws.numel(), epoch, ctx.mode, B, L, Di, H, dt(xa), stream_ptr())
-        ddlog = ddl.view(B, L, H, parts // H).sum(-1).to(dlog.dtype)
+        ddlog = (ddl if parts == H else ddl.view(B, L, H, parts // H).sum(-1)).to(dlog.dtype)
         return dxa, ddlog, dbc, dz, dA.reshape(ctx.a_shape), dD, None, None, None, None
 
 
@@ -233,10 +243,6 @@ def selective_scan(xa, dlog, BC, z, A_log, D, h0=None, want_yssm=False, want_hla
     xa, z [B,L,Di]; BC [B,L,2*Di] = [B-term | C-term]; dlog [B,L,H]; A_log [H,16]; D [Di]; h0 [B,H,16] or None.
     Returns (y [B,L,Di], y_ssm | None, h_last [B,Di] fp32 | None)."""
     mode = SCAN_MODE if mode is None else mode
-    if torch.cuda.is_current_stream_capturing():
-        # the single-pass hand-shake validates its words with a launch epoch passed by value, which a replayed CUDA graph
-        # would freeze: captured steps use the two-pass schedule (no inter-CTA waits, nothing to validate)
-        mode = _lib.SCAN_TWO_PASS
     return _SelectiveScan.apply(xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, mode)
 
 

@@ -78,10 +78,17 @@ int ab_causal_conv1d_silu_bwd(const void* xp, int64_t xp_stride, const void* dxa
  *   ws_bytes: workspace for fwd/bwd.  For the single-pass mode the workspace must be zero-filled
  *   once when allocated, must not be shared between streams, and every launch that uses it must
  *   pass a strictly larger `epoch` (1, 2, 3, ...) than the previous launch on that workspace. */
-int ab_selective_scan_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_chunks,
-                           size_t* ws_bytes);
 #define AB_SCAN_SINGLE_PASS 0
 #define AB_SCAN_TWO_PASS 1
+/* AB_SCAN_PIPELINED: persistent CTAs take tiles from a ticket and software-pipeline them (stage 1 of tile k, then the
+ * state-dependent stage 2 of tile k-1 from registers); the forward saves the state entering every run of 4 tokens
+ * (n_chunks = that count), the backward returns d dlog final as fp32 [B,L,H].  The launch epoch lives in the workspace
+ * (zero-filled once, one workspace per stream and per mode; the `epoch` argument is ignored), so replayed CUDA graphs
+ * are valid.  No y_ssm / dyssm in this mode.  *mode is in/out: a request the schedule does not cover (too many
+ * chains for scanner CTAs, odd widths) comes back as another mode together with that mode's sizes. */
+#define AB_SCAN_PIPELINED 2
+int ab_selective_scan_plan(int B, int L, int Di, int dtype, int* mode, int* tile_rows, int* slab, int* n_chunks,
+                           size_t* ws_bytes);
 /* y, y_ssm (optional), xa: contiguous [B,L,Di]; dlog contiguous [B,L,H]; Bm/Cm share bc_stride; z has
  * z_stride.  h0 [B,Di] optional initial state, h_last [B,Di] optional final state, hstart optional
  * (required for the backward): state entering every tile. */
@@ -92,7 +99,7 @@ int ab_selective_scan_fwd(const void* xa, const void* dlog, const void* Bm, cons
 /* Backward with in-tile recompute of the states from hstart.  dout = grad of y; dyssm (optional)
  * = grad of y_ssm.  Outputs: dxa, dz contiguous [B,L,Di]; dBm, dCm with dbc_stride;
  * ddlog_parts fp32 [B,L,H*4] (the backward works on 4-channel vectors: 4 partial sums per head, already
- * multiplied by softplus'; the caller adds them); dA_log [Di] and dD [Di] fp32 (overwritten;
+ * multiplied by softplus'; the caller adds them; AB_SCAN_PIPELINED: [B,L,H], final); dA_log [Di] and dD [Di] fp32 (overwritten;
  * deterministic two-stage reduction through ws). */
 int ab_selective_scan_bwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride,
                           const void* z, int64_t z_stride, const void* dout, const void* dyssm,

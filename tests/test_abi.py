@@ -41,9 +41,18 @@ def test_pure_queries_work_without_gpu():
     r = _lib.query("ab_moe_max_rows", 4096, 2, 8, 640, 128)
     assert r % 128 == 0 and r >= 8 * 640
     import ctypes
-    t, s, n = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    t, s, n, m = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(_lib.SCAN_SINGLE_PASS)
     ws = ctypes.c_size_t()
-    rc = _lib.query("ab_selective_scan_plan", 1, 65536, 512, _lib.AB_BF16, ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    plan = lambda *a: _lib.query("ab_selective_scan_plan", *a, ctypes.byref(m), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    rc = plan(1, 65536, 512, _lib.AB_BF16)
     assert rc == 0 and t.value % 4 == 0 and 512 % s.value == 0 and n.value == -(-65536 // t.value)
-    rc = _lib.query("ab_selective_scan_plan", 1, 16, 20, _lib.AB_BF16, ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
+    # pipelined schedule: one saved state per run of 4 tokens; a batch with more chains than scanner CTAs falls back
+    m.value = _lib.SCAN_PIPELINED
+    rc = plan(1, 65536, 512, _lib.AB_BF16)
+    assert rc == 0 and m.value == _lib.SCAN_PIPELINED and s.value == 64 and n.value == 65536 // 4 and ws.value > 0
+    m.value = _lib.SCAN_PIPELINED
+    rc = plan(64, 4096, 512, _lib.AB_BF16)
+    assert rc == 0 and m.value == _lib.SCAN_SINGLE_PASS and n.value == -(-4096 // t.value)
+    m.value = _lib.SCAN_SINGLE_PASS
+    rc = plan(1, 16, 20, _lib.AB_BF16)
     assert rc != 0 and "tiling" in _lib.last_error()

@@ -58,9 +58,9 @@ def _scan_ref(xa, dlog, BC, z, A_log, D, h0):
     return (y_ssm + D * xa) * F.silu(z), y_ssm, hl.reshape(B, Di)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,L,H", [(2, 48, 2), (1, 1000, 11), (2, 333, 4), (1, 5, 3), (1, 2500, 32)])
+@pytest.mark.parametrize("B,L,H", [(2, 48, 2), (1, 1000, 11), (2, 333, 4), (1, 5, 3), (1, 2500, 32), (3, 777, 8)])
 def test_selective_scan(mode, dtype, B, L, H):
     from apertis_llm_b200 import ops
     Di = 16 * H
@@ -77,12 +77,22 @@ def test_selective_scan(mode, dtype, B, L, H):
     y, ys, hl = _scan_ref(*leaves, h0.double())
     (y * dy.double()).sum().add((ys * dys.double()).sum()).backward()
     gl = [t.to(dev(), dtype if i < 4 else torch.float32).requires_grad_(True) for i, t in enumerate((xa, dlog, BC, z, A_log, D))]
-    yg, ysg, hlg = ops.selective_scan(*gl, h0=h0.to(dev()), want_yssm=True, want_hlast=True, mode=mode)
-    torch.autograd.backward([yg, ysg], [dy.to(dev(), dtype), dys.to(dev(), dtype)])
+    pipelined = mode == 2            # the pipelined schedule has no y_ssm output (output_attentions falls back)
+    if pipelined:
+        leaves = [t.clone().double().requires_grad_(True) for t in (xa, dlog, BC, z, A_log, D)]
+        y, ys, hl = _scan_ref(*leaves, h0.double())
+        (y * dy.double()).sum().backward()
+    yg, ysg, hlg = ops.selective_scan(*gl, h0=h0.to(dev()), want_yssm=not pipelined, want_hlast=True, mode=mode)
+    if pipelined:
+        assert ysg is None
+        yg.backward(dy.to(dev(), dtype))
+    else:
+        torch.autograd.backward([yg, ysg], [dy.to(dev(), dtype), dys.to(dev(), dtype)])
     torch.cuda.synchronize()
     tol = TOL[dtype]
     assert rel_err(yg.float(), y.detach()) < tol, "y"
-    assert rel_err(ysg.float(), ys.detach()) < tol, "y_ssm"
+    if not pipelined:
+        assert rel_err(ysg.float(), ys.detach()) < tol, "y_ssm"
     assert rel_err(hlg, hl.detach()) < tol, "h_last"
     names = ["dxa", "ddlog", "dBC", "dz", "dA_log", "dD"]
     for n, a, b in zip(names, gl, leaves):
@@ -100,14 +110,16 @@ def test_selective_scan_modes_agree_and_deterministic():
     D = torch.ones(Di, device=dev())
     # each schedule composes the tile aggregates in a fixed order: bitwise reproducible; the two schedules associate the
     # cross-tile products differently (the two-pass combine works on segments), so they agree to fp32 rounding only
-    outs = [ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=m)[0] for m in (1, 1, 0, 0)]
+    outs = [ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=m)[0] for m in (1, 1, 0, 0, 2, 2)]
     assert torch.equal(outs[0], outs[1]), "two-pass scan is not bitwise deterministic"
     assert torch.equal(outs[2], outs[3]), "single-pass scan is not bitwise deterministic"
+    assert torch.equal(outs[4], outs[5]), "pipelined scan is not bitwise deterministic"
     assert rel_err(outs[0].float(), outs[2].float()) < 8e-3, "single-pass and two-pass scans differ"   # one bf16 ulp
+    assert rel_err(outs[0].float(), outs[4].float()) < 8e-3, "pipelined and two-pass scans differ"
     xa32, z32, BC32, dl32 = xa.float(), z.float(), BC.float(), dlog.float()
-    o32 = [ops.selective_scan(xa32, dl32, BC32, z32, A_log, D, mode=m)[0] for m in (1, 1, 0, 0)]
-    assert torch.equal(o32[0], o32[1]) and torch.equal(o32[2], o32[3])
-    assert rel_err(o32[0], o32[2]) < 1e-5
+    o32 = [ops.selective_scan(xa32, dl32, BC32, z32, A_log, D, mode=m)[0] for m in (1, 1, 0, 0, 2, 2)]
+    assert torch.equal(o32[0], o32[1]) and torch.equal(o32[2], o32[3]) and torch.equal(o32[4], o32[5])
+    assert rel_err(o32[0], o32[2]) < 1e-5 and rel_err(o32[0], o32[4]) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------

@@ -2,7 +2,7 @@
 """Long-context selective-scan sweep (BASELINE.json configs[4]): d_model 2048 -> Di 512, H 32, one SSM layer's scan
 kernels forward + backward, seq 2K..64K, HBM GB/s against the algorithmic bytes of SURVEY.md section 8(d).
 
-    python tools/scan_bench.py [--dtype bf16|f32] [--mode single|two_pass] [--seqs 2048,...] [--batch 1] [--iters 20]
+    python tools/scan_bench.py [--dtype bf16|f32] [--mode pipe|single|two_pass] [--seqs 2048,...] [--batch 1] [--iters 20]
 """
 import argparse
 import json
@@ -18,7 +18,7 @@ from apertis_llm_b200 import _lib, ops  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dtype", default="bf16")
-    ap.add_argument("--mode", default="single")
+    ap.add_argument("--mode", default="pipe")
     ap.add_argument("--seqs", default="2048,4096,8192,16384,32768,65536")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--heads", type=int, default=32)
@@ -28,7 +28,7 @@ def main():
     d = torch.device("cuda:0")
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     es = 2 if dtype == torch.bfloat16 else 4
-    mode = _lib.SCAN_SINGLE_PASS if args.mode == "single" else _lib.SCAN_TWO_PASS
+    mode = {"single": _lib.SCAN_SINGLE_PASS, "two_pass": _lib.SCAN_TWO_PASS, "pipe": _lib.SCAN_PIPELINED}[args.mode]
     H = args.heads
     Di = 16 * H
     B = args.batch
