@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, 4) scan_fwd_kernel(const __grid_constant_
     int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
         if (tile < p.n_scan) {
-            scanner_role<+1>(p, p.epoch, SCAN_K, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
+            scanner_role<+1>(p, p.epoch, SCAN_K, 4, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
             return;
         }
         tile -= p.n_scan;
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256, 3) scan_bwd_kernel(const __grid_constant_
     int tile = (int)s_ticket;
     if (MODE == MODE_FUSED) {
         if (tile < p.n_scan) {
-            scanner_role<-1>(p, p.epoch, SCAN_K, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
+            scanner_role<-1>(p, p.epoch, SCAN_K, 4, tile, hT, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hT) - smem));
             return;
         }
         tile -= p.n_scan;

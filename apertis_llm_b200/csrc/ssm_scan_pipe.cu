@@ -33,7 +33,7 @@ using namespace ab_scan;
 
 constexpr int TSP = 4;             // tokens per run
 constexpr int PIPE_SCAN_K = 32;    // tile aggregates a scanner polls per round
-constexpr int INFO_RING = 8;
+constexpr int INFO_RING = 16;
 constexpr int PIPE_SPIN_LIMIT = 1 << 19;   // ~0.5 s of polling: a protocol error raises the flag instead of hanging the GPU
 
 typedef unsigned long long f2;     // two packed fp32 (channel pair)
@@ -95,13 +95,19 @@ __device__ __forceinline__ void st_relaxed_v2(unsigned long long* p, unsigned lo
 
 struct __align__(16) TileInfo { int b, c0, row0, tile_lin; };      // b < 0: no tile
 
+constexpr int PD = 3;              // the prepass runs PD tiles ahead of the main pass
+constexpr int LA = PD + 2;         // ticket look-ahead
+constexpr int NPRE = 3;            // prepass ring slots
+constexpr int NMAIN = 2;           // main ring stages
+
 struct PipeParams {
     ScanParams s;
     unsigned int* sync;          // [0] ticket, [1] finished CTAs, [2] launch epoch - 1
-    float* hrun;                 // [B, ceil(L/TSP), Di] state entering every run (written by the forward)
+    float* hrun;                 // per batch: [ceil(L/TSP), Di] state entering every run (written by the forward), then delta
+    size_t batch_stride;         // floats between the batches of hrun
     float* ddlog;                // backward: [B, L, H] fp32, final
     int ntiles;
-    int scan_k;                  // tile aggregates a scanner polls per round
+    int scan_k, scan_r;          // tile aggregates a scanner polls per round, replicas (segments) it splits them into
     unsigned int poll_ns;        // back-off between polls of the incoming-state word
 };
 
@@ -117,25 +123,28 @@ __device__ __forceinline__ TileInfo decode_tile_info(const PipeParams& p, int ti
     return t;
 }
 
-// shared-memory carve-up, identical on host and device
+// shared-memory carve-up, identical on host and device.  A main stage holds `nmain` operand tiles and the delta tile,
+// a prepass slot `npre` operand tiles and the delta tile.
 struct PipeSmem {
-    uint32_t pitch, off_sdel, sdel_stride, off_runP, off_runS, off_partA, off_partD, off_bars, off_info, total;
+    uint32_t pitch, dpitch, nhp, main_stride, pre_stride, off_pre, off_runP, off_runS, off_partA, off_partD, off_info, off_bars, total;
 };
-__host__ __device__ inline PipeSmem pipe_smem(int Cs, int TT, int NR, int NST, int nops, int esize, bool bwd) {
+__host__ __device__ inline PipeSmem pipe_smem(int Cs, int TT, int NR, int nmain, int npre, int esize, bool bwd) {
     PipeSmem m;
     const uint32_t tile_bytes = (uint32_t)TT * Cs * esize;
     m.pitch = (tile_bytes + 127u) & ~127u;
-    uint32_t o = (uint32_t)NST * nops * m.pitch;
-    m.off_sdel = o;
-    m.sdel_stride = (((uint32_t)(TT + 1) * (Cs >> 4)) + 3u) & ~3u;      // floats per stage
-    o += (uint32_t)NST * m.sdel_stride * 4;
+    m.nhp = (((uint32_t)Cs >> 4) + 3u) & ~3u;                            // heads per delta row, whole 16-byte units
+    m.dpitch = ((uint32_t)(TT + 1) * m.nhp * 4u + 127u) & ~127u;
+    m.main_stride = nmain * m.pitch + m.dpitch;
+    m.pre_stride = npre * m.pitch + m.dpitch;
+    uint32_t o = NMAIN * m.main_stride;
+    m.off_pre = o; o += NPRE * m.pre_stride;
     m.off_runP = o; o += 2u * NR * Cs * 4;
     m.off_runS = o; o += 2u * NR * Cs * 4;
     m.off_partA = o; if (bwd) o += 2u * NR * Cs * 4;
     m.off_partD = o; if (bwd) o += 2u * NR * Cs * 4;
     o = (o + 15u) & ~15u;
     m.off_info = o; o += INFO_RING * 16;
-    m.off_bars = o; o += (uint32_t)NST * 8;
+    m.off_bars = o; o += (NMAIN + NPRE) * 8;
     m.total = (o + 127u) & ~127u;
     return m;
 }
@@ -164,28 +173,68 @@ __device__ __forceinline__ void scanner_finish(unsigned int* sync, unsigned int*
     if (atomicAdd(s_left, 1u) == blockDim.x - 1) grid_finish(sync);
 }
 
+// delta = softplus(dt logits) as fp32 rows of Hp (whole 16-byte units, TMA-loadable) heads; kept for the backward
+template <typename T>
+__global__ void __launch_bounds__(256) scan_delta_kernel(const T* __restrict__ dlog, float* __restrict__ delta, int L, int H, int Hp,
+                                                         size_t batch_stride, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i % Hp);
+        const size_t tok = i / Hp;
+        const size_t b = tok / L, t = tok % L;
+        delta[b * batch_stride + t * Hp + h] = h < H ? ab_softplus_fast(ab_to_float(dlog[tok * H + h])) : 0.f;
+    }
+}
+
+// duty warp: compose the run aggregates of one tile in run order (forward) or reverse run order (backward), leave the
+// per-run coefficients (state entering the run = P * incoming + S) in their place and publish the tile aggregate
+template <int NR, bool REVERSE>
+__device__ __forceinline__ void compose_and_publish(float* rp, float* rs, int Cs, unsigned long long* w, uint32_t epoch) {
+    f2 Pa = f2_bcast(1.f), Sa = f2_bcast(0.f);
+#pragma unroll
+    for (int q0 = 0; q0 < NR; q0 += 4) {
+        f2 P4[4], S4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (q0 + u < NR) {
+                const int r = REVERSE ? NR - 1 - (q0 + u) : q0 + u;
+                P4[u] = *reinterpret_cast<const f2*>(rp + r * Cs); S4[u] = *reinterpret_cast<const f2*>(rs + r * Cs);
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (q0 + u < NR) {
+                const int r = REVERSE ? NR - 1 - (q0 + u) : q0 + u;
+                *reinterpret_cast<f2*>(rp + r * Cs) = Pa;
+                *reinterpret_cast<f2*>(rs + r * Cs) = Sa;
+                Sa = f2_fma(P4[u], Sa, S4[u]);
+                Pa = f2_mul(Pa, P4[u]);
+            }
+    }
+    float p0, p1, s0, s1;
+    f2_unpack(Pa, p0, p1); f2_unpack(Sa, s0, s1);
+    st_relaxed_v2(w, pack_word(epoch, ST_AGG, p0), pack_word(epoch, ST_AGG, s0));
+    st_relaxed_v2(w + 2, pack_word(epoch, ST_AGG, p1), pack_word(epoch, ST_AGG, s1));
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-struct FwdSet { f2 al[TSP], be[TSP]; };
-
-template <typename T, int NWC, int NR, int NST, int CS>
-__global__ void __launch_bounds__(32 * NWC * NR, (768 / (32 * NWC * NR) > 0 ? 768 / (32 * NWC * NR) : 1)) scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa,
-                                                                     const __grid_constant__ CUtensorMap tm_b,
-                                                                     const __grid_constant__ CUtensorMap tm_c,
-                                                                     const __grid_constant__ CUtensorMap tm_z,
-                                                                     const __grid_constant__ PipeParams p) {
+template <typename T, int NWC, int NR, int CS>
+__global__ void __launch_bounds__(32 * NWC * NR, (1024 / (32 * NWC * NR) > 0 ? 1024 / (32 * NWC * NR) : 1))
+scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b,
+                     const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z,
+                     const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ PipeParams p) {
     constexpr int TT = NR * TSP;
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanParams& sp = p.s;
-    const int Cs = CS ? CS : sp.Cs, nh = Cs >> 4;          // CS != 0: slab width known at compile time
-    const PipeSmem lay = pipe_smem(Cs, TT, NR, NST, 4, (int)sizeof(T), false);
-    const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T);
-    float* sdel = reinterpret_cast<float*>(smem + lay.off_sdel);
+    const int Cs = CS ? CS : sp.Cs;          // CS != 0: slab width known at compile time
+    const PipeSmem lay = pipe_smem(Cs, TT, NR, 4, 1, (int)sizeof(T), false);
+    const int nhp = (int)lay.nhp;
+    const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T), dbytes = (uint32_t)TT * nhp * 4u;
     float* runP = reinterpret_cast<float*>(smem + lay.off_runP);
     float* runS = reinterpret_cast<float*>(smem + lay.off_runS);
     TileInfo* s_info = reinterpret_cast<TileInfo*>(smem + lay.off_info);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    uint64_t* pbar = mbar + NMAIN;
     __shared__ unsigned int s_first, s_epoch, s_left;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -194,177 +243,149 @@ __global__ void __launch_bounds__(32 * NWC * NR, (768 / (32 * NWC * NR) > 0 ? 76
     const bool act = cl < Cs;
     if (!act) cl = Cs - 2;
     const int hh = cl >> 4;
-    const int d_row = tid / nh, d_hh = tid - d_row * nh;       // dt staging element of this thread
-    const bool d_act = tid < TT * nh;
 
     if (tid == 0) {
         s_epoch = *reinterpret_cast<volatile unsigned int*>(p.sync + 2) + 1u;
         s_first = atomicAdd(p.sync, 1u);
         s_left = 0;
-        for (int s = 0; s < NST; ++s) ab_mbar_init(&bars[s], 1);
+        for (int s = 0; s < NMAIN + NPRE; ++s) ab_mbar_init(&mbar[s], 1);
         ab_fence_mbar_init();
     }
     __syncthreads();
     const uint32_t epoch = s_epoch;
     if ((int)s_first < sp.n_scan) {
         float* hs = runS + 2 * NR * Cs - Cs;          // generic scanner path only; the ring may use everything below
-        scanner_role<+1>(sp, epoch, p.scan_k, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
+        scanner_role<+1>(sp, epoch, p.scan_k, p.scan_r, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
         scanner_finish(p.sync, &s_left);
         return;
     }
 
-    auto issue_tile = [&](int s, const TileInfo& ti) {         // thread 0 only
-        ab_mbar_expect_tx(&bars[s], 4u * tile_bytes);
-        unsigned char* dst = smem + (size_t)s * 4 * lay.pitch;
-        ab_tma_load_3d(dst, &tm_b, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &bars[s], ti.c0, ti.row0, ti.b);
+    auto issue_main = [&](int s, const TileInfo& ti) {         // thread 0 only
+        ab_mbar_expect_tx(&mbar[s], 4u * tile_bytes + dbytes);
+        unsigned char* dst = smem + (size_t)s * lay.main_stride;
+        ab_tma_load_3d(dst, &tm_b, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 4 * lay.pitch, &tm_d, &mbar[s], ti.c0 >> 4, ti.row0, ti.b);
     };
-    auto load_dlog = [&](const TileInfo& ti) -> float {        // raw dt logit of this thread's staging element
-        const int row = ti.row0 + d_row;
-        if (!d_act || ti.b < 0 || row >= sp.L) return -1e30f;
-        return ab_to_float(reinterpret_cast<const T*>(sp.dlog)[((size_t)ti.b * sp.L + row) * sp.H + (ti.c0 >> 4) + d_hh]);
-    };
-    auto store_sdel = [&](int s, float raw) {
-        if (d_act) sdel[s * lay.sdel_stride + tid] = raw < -1e29f ? 0.f : ab_softplus_fast(raw);
+    auto issue_pre = [&](int s, const TileInfo& ti) {
+        ab_mbar_expect_tx(&pbar[s], tile_bytes + dbytes);
+        unsigned char* dst = smem + lay.off_pre + (size_t)s * lay.pre_stride;
+        ab_tma_load_3d(dst, &tm_b, &pbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + lay.pitch, &tm_d, &pbar[s], ti.c0 >> 4, ti.row0, ti.b);
     };
 
-    // ---- prologue: tickets and loads of the first NST pipeline positions
+    // ---- prologue: the first two pipeline positions
     int pending = -1;
     if (tid == 0) {
-        const int first = (int)s_first - sp.n_scan;
-        const int base = (int)atomicAdd(p.sync, (unsigned)NST) - sp.n_scan;
-        for (int s = 0; s < NST; ++s) {
-            const TileInfo ti = decode_tile_info(p, s == 0 ? first : base + s - 1, TT, false);
-            s_info[s] = ti;
-            if (ti.b >= 0) issue_tile(s, ti);
-        }
-        pending = base + NST - 1;
+        const int base = (int)atomicAdd(p.sync, 2u) - sp.n_scan;
+        s_info[0] = decode_tile_info(p, (int)s_first - sp.n_scan, TT, false);
+        s_info[1] = decode_tile_info(p, base, TT, false);
+        pending = base + 1;
+        if (s_info[0].b >= 0) issue_pre(0, s_info[0]);
+        if (s_info[1].b >= 0) issue_pre(1, s_info[1]);
     }
-    __syncthreads();
-    for (int s = 0; s < NST; ++s) store_sdel(s, load_dlog(s_info[s]));
     __syncthreads();
 
     const int nrt = (sp.L + TSP - 1) / TSP;   // saved run states per sequence
-    uint32_t phase_bits = 0;                // mbarrier parity per stage
+    uint32_t mphase = 0, pphase = 0;          // mbarrier parities per main stage / prepass slot
+    f2 cq0P = f2_bcast(1.f), cq0S = f2_bcast(0.f), cq1P = cq0P, cq1S = cq0S;      // run coefficients of the next two main tiles
+    int ps = 0;                               // prepass slot of position i + PD
 
-    bool prev_valid = false;
-    auto body = [&](int k, int s, FwdSet& cur, FwdSet& prv) -> bool {
-        const TileInfo cti = s_info[k & (INFO_RING - 1)];
-        const bool valid = cti.b >= 0, have_prev = prev_valid;
-        if (!valid && !have_prev) return false;
-        prev_valid = valid;
+    for (int i = -PD;; ++i) {
+        const TileInfo mi = s_info[(i < 0 ? 0 : i) & (INFO_RING - 1)];
+        if (mi.b < 0) break;                  // positions are handed out in increasing order: nothing left for this CTA
+        const TileInfo pi = s_info[(i + PD) & (INFO_RING - 1)];
         if (tid == 0) {
-            s_info[(k + NST) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, false);
+            s_info[(i + LA) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, false);
             if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - sp.n_scan;
         }
-        // the word that carries the state entering the previous tile: requested now, looked at after stage 1
-        unsigned long long w0 = 0, w1 = 0;
-        const unsigned long long* wprev = sp.inclw + (size_t)s_info[(k - 1) & (INFO_RING - 1)].tile_lin * Cs + cl;
-        if (have_prev) ld_relaxed_v2(wprev, w0, w1);
-
-        // ---- stage 1
-        if (valid) {
-            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + cti.c0 + cl));
-            const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + cti.c0 + cl));
+        // ---- main pass of tile i: the state entering it was requested PD iterations ago
+        if (i >= 0) {
+            const int s = i & 1;
+            unsigned long long w0, w1;
+            const unsigned long long* wp = sp.inclw + (size_t)mi.tile_lin * Cs + cl;
+            ld_relaxed_v2(wp, w0, w1);
+            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + mi.c0 + cl));
+            const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + mi.c0 + cl));
             const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E), Dv = f2_pack(dv2.x, dv2.y);
-            const unsigned char* st = smem + (size_t)s * 4 * lay.pitch;
+            const unsigned char* st = smem + (size_t)s * lay.main_stride;
             const T* sB = reinterpret_cast<const T*>(st) + cl;
             const T* sX = reinterpret_cast<const T*>(st + lay.pitch) + cl;
             const T* sC = reinterpret_cast<const T*>(st + 2 * lay.pitch) + cl;
             const T* sZ = reinterpret_cast<const T*>(st + 3 * lay.pitch) + cl;
-            const float* sd = sdel + s * lay.sdel_stride + hh;
-            ab_mbar_wait(&bars[s], (phase_bits >> s) & 1u);
-            f2 h0 = f2_bcast(0.f), pc = f2_bcast(1.f);
-#pragma unroll
-            for (int t = 0; t < TSP; ++t) {
-                const int r = run * TSP + t;
-                const f2 a = f2_ex2(f2_mul(A2, f2_bcast(sd[r * nh])));
-                const f2 bv = lds_pair<T>(sB + (size_t)r * Cs), cv = lds_pair<T>(sC + (size_t)r * Cs);
-                const f2 xv = lds_pair<T>(sX + (size_t)r * Cs), zv = lds_pair<T>(sZ + (size_t)r * Cs);
-                pc = f2_mul(pc, a);
-                h0 = f2_fma(a, h0, bv);
-                const f2 gate = f2_mul(zv, f2_sigmoid<T>(zv));
-                const f2 cg = f2_mul(cv, gate);
-                cur.al[t] = f2_mul(cg, pc);
-                cur.be[t] = f2_fma(cg, h0, f2_mul(f2_mul(Dv, xv), gate));
-            }
-            if (act) {
-                *reinterpret_cast<f2*>(runP + ((k & 1) * NR + run) * Cs + cl) = pc;
-                *reinterpret_cast<f2*>(runS + ((k & 1) * NR + run) * Cs + cl) = h0;
-            }
-        }
-        __syncthreads();
-        phase_bits ^= valid ? (1u << s) : 0u;
-
-        // ---- refill the freed stage, request the dt logits of that tile
-        const TileInfo nx = s_info[(k + NST) & (INFO_RING - 1)];
-        if (tid == 0 && nx.b >= 0) issue_tile(s, nx);
-        const float draw = load_dlog(nx);
-
-        // ---- duty warp of this column: run prefixes in place, tile aggregate -> scanner
-        if (valid && run == k % NR && act) {
-            float* rp = runP + (k & 1) * NR * Cs + cl;
-            float* rs = runS + (k & 1) * NR * Cs + cl;
-            f2 Pa = f2_bcast(1.f), Sa = f2_bcast(0.f);
-#pragma unroll
-            for (int r0 = 0; r0 < NR; r0 += 4) {
-                f2 P4[4], S4[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (r0 + u < NR) { P4[u] = *reinterpret_cast<const f2*>(rp + (r0 + u) * Cs); S4[u] = *reinterpret_cast<const f2*>(rs + (r0 + u) * Cs); }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (r0 + u < NR) {
-                        *reinterpret_cast<f2*>(rp + (r0 + u) * Cs) = Pa;
-                        *reinterpret_cast<f2*>(rs + (r0 + u) * Cs) = Sa;
-                        Sa = f2_fma(P4[u], Sa, S4[u]);
-                        Pa = f2_mul(Pa, P4[u]);
-                    }
-            }
-            float p0, p1, s0, s1;
-            f2_unpack(Pa, p0, p1); f2_unpack(Sa, s0, s1);
-            unsigned long long* w = sp.words + ((size_t)cti.tile_lin * Cs + cl) * 2;
-            st_relaxed_v2(w, pack_word(epoch, ST_AGG, p0), pack_word(epoch, ST_AGG, s0));
-            st_relaxed_v2(w + 2, pack_word(epoch, ST_AGG, p1), pack_word(epoch, ST_AGG, s1));
-        }
-
-        // ---- stage 2 of the previous tile
-        if (have_prev) {
-            const TileInfo pti = s_info[(k - 1) & (INFO_RING - 1)];
+            const float* sd = reinterpret_cast<const float*>(st + 4 * lay.pitch) + hh;
             int spins = 0;
             while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
                 if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
                 __nanosleep(p.poll_ns);
-                ld_relaxed_v2(wprev, w0, w1);
+                ld_relaxed_v2(wp, w0, w1);
             }
-            const f2 hin = f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1));
-            const int pb = ((k - 1) & 1) * NR + run;
-            const f2 h = f2_fma(*reinterpret_cast<const f2*>(runP + pb * Cs + cl), hin, *reinterpret_cast<const f2*>(runS + pb * Cs + cl));
-            if (act) {
-                const int rg = pti.row0 / TSP + run;
-                if (rg < nrt) *reinterpret_cast<f2*>(p.hrun + ((size_t)pti.b * nrt + rg) * sp.Di + pti.c0 + cl) = h;
-                const int row = pti.row0 + run * TSP;
-                T* yo = reinterpret_cast<T*>(sp.y) + ((size_t)pti.b * sp.L + row) * sp.Di + pti.c0 + cl;
+            f2 h = f2_fma(cq0P, f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1)), cq0S);
+            const int row = mi.row0 + run * TSP;
+            const int rg = mi.row0 / TSP + run;
+            if (act && rg < nrt) *reinterpret_cast<f2*>(p.hrun + (size_t)mi.b * p.batch_stride + (size_t)rg * sp.Di + mi.c0 + cl) = h;
+            T* yo = reinterpret_cast<T*>(sp.y) + ((size_t)mi.b * sp.L + row) * sp.Di + mi.c0 + cl;
+            ab_mbar_wait(&mbar[s], (mphase >> s) & 1u);
+            mphase ^= 1u << s;
 #pragma unroll
-                for (int t = 0; t < TSP; ++t)
-                    if (row + t < sp.L) stg_pair<T>(yo + (size_t)t * sp.Di, f2_fma(prv.al[t], h, prv.be[t]));
+            for (int t = 0; t < TSP; ++t) {
+                const int r = run * TSP + t;
+                const f2 a = f2_ex2(f2_mul(A2, f2_bcast(sd[r * nhp])));
+                const f2 bv = lds_pair<T>(sB + (size_t)r * Cs), cv = lds_pair<T>(sC + (size_t)r * Cs);
+                const f2 xv = lds_pair<T>(sX + (size_t)r * Cs), zv = lds_pair<T>(sZ + (size_t)r * Cs);
+                h = f2_fma(a, h, bv);
+                const f2 o = f2_mul(f2_fma(Dv, xv, f2_mul(cv, h)), f2_mul(zv, f2_sigmoid<T>(zv)));
+                if (act && row + t < sp.L) stg_pair<T>(yo + (size_t)t * sp.Di, o);
             }
         }
-        if (nx.b >= 0) store_sdel(s, draw);
-        return true;
-    };
-
-    FwdSet A, Bq;
+        // ---- prepass of tile i + PD: run aggregates from Bm and delta only
+        if (pi.b >= 0) {
+            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + pi.c0 + cl));
+            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E);
+            const unsigned char* st = smem + lay.off_pre + (size_t)ps * lay.pre_stride;
+            const T* sB = reinterpret_cast<const T*>(st) + cl;
+            const float* sd = reinterpret_cast<const float*>(st + lay.pitch) + hh;
+            ab_mbar_wait(&pbar[ps], (pphase >> ps) & 1u);
+            pphase ^= 1u << ps;
+            f2 S = f2_bcast(0.f), P = f2_bcast(1.f);
 #pragma unroll
-    for (int t = 0; t < TSP; ++t) { A.al[t] = 0; A.be[t] = 0; Bq.al[t] = 0; Bq.be[t] = 0; }
-    int s = 0;
-    for (int k = 0;; k += 2) {
-        if (!body(k, s, A, Bq)) break;
-        s = s + 1 == NST ? 0 : s + 1;
-        if (!body(k + 1, s, Bq, A)) break;
-        s = s + 1 == NST ? 0 : s + 1;
+            for (int t = 0; t < TSP; ++t) {
+                const int r = run * TSP + t;
+                const f2 a = f2_ex2(f2_mul(A2, f2_bcast(sd[r * nhp])));
+                P = f2_mul(P, a);
+                S = f2_fma(a, S, lds_pair<T>(sB + (size_t)r * Cs));
+            }
+            if (act) {
+                const int bi = (((i + PD) & 1) * NR + run) * Cs + cl;
+                *reinterpret_cast<f2*>(runP + bi) = P;
+                *reinterpret_cast<f2*>(runS + bi) = S;
+            }
+        }
+        __syncthreads();
+
+        // ---- refill: the main stage tile i leaves goes to tile i + 2, the free prepass slot to tile i + PD + 2
+        if (tid == 0) {
+            if (i + 2 >= 0) {
+                const TileInfo nm = s_info[(i + 2) & (INFO_RING - 1)];
+                if (nm.b >= 0) issue_main(i & 1, nm);
+            }
+            const TileInfo np = s_info[(i + LA) & (INFO_RING - 1)];
+            if (np.b >= 0) issue_pre((ps + 2) % NPRE, np);
+        }
+        // ---- duty warp of this column: run prefixes in place, tile aggregate -> scanner
+        if (pi.b >= 0 && run == (i + PD) % NR && act)
+            compose_and_publish<NR, false>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs,
+                                           sp.words + ((size_t)pi.tile_lin * Cs + cl) * 2, epoch);
+        // ---- run coefficients of tile i + 2 (composed during the previous iteration)
+        cq0P = cq1P; cq0S = cq1S;
+        if (i + 2 >= 0) {
+            const int bi = (((i + 2) & 1) * NR + run) * Cs + cl;
+            cq1P = *reinterpret_cast<const f2*>(runP + bi);
+            cq1S = *reinterpret_cast<const f2*>(runS + bi);
+        }
+        ps = ps + 1 == NPRE ? 0 : ps + 1;
     }
     cta_finish(p.sync);
 }
@@ -372,28 +393,26 @@ __global__ void __launch_bounds__(32 * NWC * NR, (768 / (32 * NWC * NR) > 0 ? 76
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-struct BwdSet { f2 a[TSP], g[TSP], hp[TSP]; float dl[TSP]; f2 anext, accD, A2; };
-
-template <typename T, int NWC, int NR, int NST, int CS>
-__global__ void __launch_bounds__(32 * NWC * NR, 512 / (32 * NWC * NR) > 0 ? 512 / (32 * NWC * NR) : 1) scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa,
-                                                                     const __grid_constant__ CUtensorMap tm_b,
-                                                                     const __grid_constant__ CUtensorMap tm_c,
-                                                                     const __grid_constant__ CUtensorMap tm_z,
-                                                                     const __grid_constant__ CUtensorMap tm_do,
-                                                                     const __grid_constant__ PipeParams p) {
+template <typename T, int NWC, int NR, int CS>
+__global__ void __launch_bounds__(32 * NWC * NR, (512 / (32 * NWC * NR) > 0 ? 512 / (32 * NWC * NR) : 1))
+scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b,
+                     const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z,
+                     const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_d,
+                     const __grid_constant__ PipeParams p) {
     constexpr int TT = NR * TSP;
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanParams& sp = p.s;
-    const int Cs = CS ? CS : sp.Cs, nh = Cs >> 4;          // CS != 0: slab width known at compile time
-    const PipeSmem lay = pipe_smem(Cs, TT, NR, NST, 5, (int)sizeof(T), true);
-    const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T);
-    float* sdel = reinterpret_cast<float*>(smem + lay.off_sdel);
+    const int Cs = CS ? CS : sp.Cs;
+    const PipeSmem lay = pipe_smem(Cs, TT, NR, 5, 3, (int)sizeof(T), true);
+    const int nhp = (int)lay.nhp;
+    const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T), dbytes = (uint32_t)(TT + 1) * nhp * 4u;
     float* runP = reinterpret_cast<float*>(smem + lay.off_runP);
     float* runS = reinterpret_cast<float*>(smem + lay.off_runS);
     float* partA = reinterpret_cast<float*>(smem + lay.off_partA);
     float* partD = reinterpret_cast<float*>(smem + lay.off_partD);
     TileInfo* s_info = reinterpret_cast<TileInfo*>(smem + lay.off_info);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+    uint64_t* pbar = mbar + NMAIN;
     __shared__ unsigned int s_first, s_epoch, s_left;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -402,62 +421,57 @@ __global__ void __launch_bounds__(32 * NWC * NR, 512 / (32 * NWC * NR) > 0 ? 512
     const bool act = cl < Cs;
     if (!act) cl = Cs - 2;
     const int hh = cl >> 4;
-    const int d_row = tid / nh, d_hh = tid - d_row * nh;
-    const bool d_act = tid < (TT + 1) * nh;
 
     if (tid == 0) {
         s_epoch = *reinterpret_cast<volatile unsigned int*>(p.sync + 2) + 1u;
         s_first = atomicAdd(p.sync, 1u);
         s_left = 0;
-        for (int s = 0; s < NST; ++s) ab_mbar_init(&bars[s], 1);
+        for (int s = 0; s < NMAIN + NPRE; ++s) ab_mbar_init(&mbar[s], 1);
         ab_fence_mbar_init();
     }
     __syncthreads();
     const uint32_t epoch = s_epoch;
     if ((int)s_first < sp.n_scan) {
         float* hs = partD + 2 * NR * Cs - Cs;
-        scanner_role<-1>(sp, epoch, p.scan_k, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
+        scanner_role<-1>(sp, epoch, p.scan_k, p.scan_r, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
         scanner_finish(p.sync, &s_left);
         return;
     }
 
-    auto issue_tile = [&](int s, const TileInfo& ti) {
-        ab_mbar_expect_tx(&bars[s], 5u * tile_bytes);
-        unsigned char* dst = smem + (size_t)s * 5 * lay.pitch;
-        ab_tma_load_3d(dst, &tm_b, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &bars[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 4 * lay.pitch, &tm_do, &bars[s], ti.c0, ti.row0, ti.b);
+    auto issue_main = [&](int s, const TileInfo& ti) {
+        ab_mbar_expect_tx(&mbar[s], 5u * tile_bytes + dbytes);
+        unsigned char* dst = smem + (size_t)s * lay.main_stride;
+        ab_tma_load_3d(dst, &tm_b, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 4 * lay.pitch, &tm_do, &mbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 5 * lay.pitch, &tm_d, &mbar[s], ti.c0 >> 4, ti.row0, ti.b);
     };
-    auto load_dlog = [&](const TileInfo& ti) -> float {
-        const int row = ti.row0 + d_row;
-        if (!d_act || ti.b < 0 || row >= sp.L) return -1e30f;
-        return ab_to_float(reinterpret_cast<const T*>(sp.dlog)[((size_t)ti.b * sp.L + row) * sp.H + (ti.c0 >> 4) + d_hh]);
-    };
-    auto store_sdel = [&](int s, float raw) {
-        if (d_act) sdel[s * lay.sdel_stride + tid] = raw < -1e29f ? 0.f : ab_softplus_fast(raw);
+    auto issue_pre = [&](int s, const TileInfo& ti) {
+        ab_mbar_expect_tx(&pbar[s], 3u * tile_bytes + dbytes);
+        unsigned char* dst = smem + lay.off_pre + (size_t)s * lay.pre_stride;
+        ab_tma_load_3d(dst, &tm_c, &pbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + lay.pitch, &tm_z, &pbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_do, &pbar[s], ti.c0, ti.row0, ti.b);
+        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_d, &pbar[s], ti.c0 >> 4, ti.row0, ti.b);
     };
 
     int pending = -1;
     if (tid == 0) {
-        const int first = (int)s_first - sp.n_scan;
-        const int base = (int)atomicAdd(p.sync, (unsigned)NST) - sp.n_scan;
-        for (int s = 0; s < NST; ++s) {
-            const TileInfo ti = decode_tile_info(p, s == 0 ? first : base + s - 1, TT, true);
-            s_info[s] = ti;
-            if (ti.b >= 0) issue_tile(s, ti);
-        }
-        pending = base + NST - 1;
+        const int base = (int)atomicAdd(p.sync, 2u) - sp.n_scan;
+        s_info[0] = decode_tile_info(p, (int)s_first - sp.n_scan, TT, true);
+        s_info[1] = decode_tile_info(p, base, TT, true);
+        pending = base + 1;
+        if (s_info[0].b >= 0) issue_pre(0, s_info[0]);
+        if (s_info[1].b >= 0) issue_pre(1, s_info[1]);
     }
-    __syncthreads();
-    for (int s = 0; s < NST; ++s) store_sdel(s, load_dlog(s_info[s]));
     __syncthreads();
 
     const int nrt = (sp.L + TSP - 1) / TSP;
-    uint32_t phase_bits = 0;
-    int part_tile = -1;          // tile whose per-run dA_log / dD partials sit in shared memory (CTA-uniform)
-    int part_buf = 0;
+    uint32_t mphase = 0, pphase = 0;
+    f2 cq0P = f2_bcast(1.f), cq0S = f2_bcast(0.f), cq1P = cq0P, cq1S = cq0S;
+    int ps = 0;
     const float inv_log2e = 1.f / AB_LOG2E;
 
     // sum the per-run partials of a finished tile in run order (deterministic) -> per-tile partials in global memory
@@ -474,146 +488,89 @@ __global__ void __launch_bounds__(32 * NWC * NR, 512 / (32 * NWC * NR) > 0 ? 512
         *reinterpret_cast<f2*>(sp.part + ((size_t)tile_lin * 2 + 1) * Cs + cl) = sd2;
     };
 
-    bool prev_valid = false;
-    auto body = [&](int k, int s, BwdSet& cur, BwdSet& prv) -> bool {
-        const TileInfo cti = s_info[k & (INFO_RING - 1)];
-        const bool valid = cti.b >= 0, have_prev = prev_valid;
-        if (!valid && !have_prev) return false;
-        prev_valid = valid;
+    for (int i = -PD;; ++i) {
+        const TileInfo mi = s_info[(i < 0 ? 0 : i) & (INFO_RING - 1)];
+        if (mi.b < 0) break;
+        const TileInfo pi = s_info[(i + PD) & (INFO_RING - 1)];
         if (tid == 0) {
-            s_info[(k + NST) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, true);
+            s_info[(i + LA) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, true);
             if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - sp.n_scan;
         }
-        unsigned long long w0 = 0, w1 = 0;
-        const unsigned long long* wprev = sp.inclw + (size_t)s_info[(k - 1) & (INFO_RING - 1)].tile_lin * Cs + cl;
-        if (have_prev) ld_relaxed_v2(wprev, w0, w1);
-
-        // ---- stage 1: forward recompute from the saved run state, dxa / dC / dz, reverse run aggregates
-        if (valid) {
-            const size_t tok0 = (size_t)cti.b * sp.L + cti.row0 + run * TSP;
-            const int cg0 = cti.c0 + cl;
+        // ---- main pass of tile i: forward recompute from the saved run state, then the reverse sweep
+        if (i >= 0) {
+            const int s = i & 1;
+            unsigned long long w0, w1;
+            const unsigned long long* wp = sp.inclw + (size_t)mi.tile_lin * Cs + cl;
+            ld_relaxed_v2(wp, w0, w1);
+            const int cg0 = mi.c0 + cl;
             const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + cg0));
             const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + cg0));
-            const int rg = cti.row0 / TSP + run;
-            f2 h = rg < nrt ? *reinterpret_cast<const f2*>(p.hrun + ((size_t)cti.b * nrt + rg) * sp.Di + cg0) : f2_bcast(0.f);
+            const int rg = mi.row0 / TSP + run;
+            f2 h = rg < nrt ? *reinterpret_cast<const f2*>(p.hrun + (size_t)mi.b * p.batch_stride + (size_t)rg * sp.Di + cg0) : f2_bcast(0.f);
             const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E), Dv = f2_pack(dv2.x, dv2.y);
-            cur.A2 = A2;
-            const unsigned char* st = smem + (size_t)s * 5 * lay.pitch;
+            const unsigned char* st = smem + (size_t)s * lay.main_stride;
             const T* sB = reinterpret_cast<const T*>(st) + cl;
             const T* sX = reinterpret_cast<const T*>(st + lay.pitch) + cl;
             const T* sC = reinterpret_cast<const T*>(st + 2 * lay.pitch) + cl;
             const T* sZ = reinterpret_cast<const T*>(st + 3 * lay.pitch) + cl;
             const T* sO = reinterpret_cast<const T*>(st + 4 * lay.pitch) + cl;
-            const float* sd = sdel + s * lay.sdel_stride + hh;
+            const float* sd = reinterpret_cast<const float*>(st + 5 * lay.pitch) + hh;
+            const int row = mi.row0 + run * TSP;
+            const size_t tok0 = (size_t)mi.b * sp.L + row;
             T* dxa_o = reinterpret_cast<T*>(sp.dxa) + tok0 * sp.Di + cg0;
             T* dz_o = reinterpret_cast<T*>(sp.dz) + tok0 * sp.Di + cg0;
             T* dc_o = reinterpret_cast<T*>(sp.dCm) + tok0 * sp.dbc_stride + cg0;
-            const int row = cti.row0 + run * TSP;
-            ab_mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+            T* db_o = reinterpret_cast<T*>(sp.dBm) + tok0 * sp.dbc_stride + cg0;
+            ab_mbar_wait(&mbar[s], (mphase >> s) & 1u);
+            mphase ^= 1u << s;
+            f2 a[TSP], g[TSP], hp[TSP];
+            float dl[TSP];
             f2 accD = f2_bcast(0.f);
             const f2 one = f2_bcast(1.f), neg1 = f2_bcast(-1.f);
 #pragma unroll
             for (int t = 0; t < TSP; ++t) {
                 const int r = run * TSP + t;
-                cur.dl[t] = sd[r * nh];
-                cur.a[t] = f2_ex2(f2_mul(A2, f2_bcast(cur.dl[t])));
+                dl[t] = sd[r * nhp];
+                a[t] = f2_ex2(f2_mul(A2, f2_bcast(dl[t])));
                 const f2 bv = lds_pair<T>(sB + (size_t)r * Cs), cv = lds_pair<T>(sC + (size_t)r * Cs);
                 const f2 xv = lds_pair<T>(sX + (size_t)r * Cs), zv = lds_pair<T>(sZ + (size_t)r * Cs);
                 const f2 dov = lds_pair<T>(sO + (size_t)r * Cs);
                 const f2 sg = f2_sigmoid<T>(zv);
                 const f2 dyv = f2_mul(dov, f2_mul(zv, sg));            // grad of (y_ssm + D*xa)
-                cur.hp[t] = h;
-                h = f2_fma(cur.a[t], h, bv);
+                hp[t] = h;
+                h = f2_fma(a[t], h, bv);
                 const f2 yv = f2_fma(Dv, xv, f2_mul(cv, h));
-                // silu'(z) = sg * (1 + z * (1 - sg))
-                const f2 dsilu = f2_mul(sg, f2_fma(zv, f2_fma(sg, neg1, one), one));
+                const f2 dsilu = f2_mul(sg, f2_fma(zv, f2_fma(sg, neg1, one), one));     // silu'(z) = sg * (1 + z * (1 - sg))
                 accD = f2_fma(dyv, xv, accD);
-                cur.g[t] = f2_mul(dyv, cv);
+                g[t] = f2_mul(dyv, cv);
                 if (act && row + t < sp.L) {
                     stg_pair<T>(dxa_o + (size_t)t * sp.Di, f2_mul(dyv, Dv));
                     stg_pair<T>(dz_o + (size_t)t * sp.Di, f2_mul(f2_mul(dov, yv), dsilu));
                     stg_pair<T>(dc_o + (size_t)t * sp.dbc_stride, f2_mul(dyv, h));
                 }
             }
-            cur.accD = accD;
-            // reverse:  G(first token of the run) = Gs + Pr * G(first token of the next run)
-            cur.anext = f2_ex2(f2_mul(A2, f2_bcast(sd[(run * TSP + TSP) * nh])));
-            f2 Gs = cur.g[TSP - 1], Pr = cur.anext;
-#pragma unroll
-            for (int t = TSP - 2; t >= 0; --t) {
-                Gs = f2_fma(cur.a[t + 1], Gs, cur.g[t]);
-                Pr = f2_mul(Pr, cur.a[t + 1]);
-            }
-            if (act) {
-                *reinterpret_cast<f2*>(runP + ((k & 1) * NR + run) * Cs + cl) = Pr;
-                *reinterpret_cast<f2*>(runS + ((k & 1) * NR + run) * Cs + cl) = Gs;
-            }
-        }
-        __syncthreads();
-        phase_bits ^= valid ? (1u << s) : 0u;
-
-        const TileInfo nx = s_info[(k + NST) & (INFO_RING - 1)];
-        if (tid == 0 && nx.b >= 0) issue_tile(s, nx);
-        const float draw = load_dlog(nx);
-
-        // ---- duty warp: reverse run prefixes in place, publish; per-tile dA_log / dD partials of the tile before last
-        if (run == k % NR && act) {
-            if (valid) {
-                float* rp = runP + (k & 1) * NR * Cs + cl;
-                float* rs = runS + (k & 1) * NR * Cs + cl;
-                f2 Pa = f2_bcast(1.f), Sa = f2_bcast(0.f);
-#pragma unroll
-                for (int r0 = NR - 1; r0 >= 0; r0 -= 4) {
-                    f2 P4[4], S4[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (r0 - u >= 0) { P4[u] = *reinterpret_cast<const f2*>(rp + (r0 - u) * Cs); S4[u] = *reinterpret_cast<const f2*>(rs + (r0 - u) * Cs); }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (r0 - u >= 0) {
-                            *reinterpret_cast<f2*>(rp + (r0 - u) * Cs) = Pa;
-                            *reinterpret_cast<f2*>(rs + (r0 - u) * Cs) = Sa;
-                            Sa = f2_fma(P4[u], Sa, S4[u]);
-                            Pa = f2_mul(Pa, P4[u]);
-                        }
-                }
-                float p0, p1, s0, s1;
-                f2_unpack(Pa, p0, p1); f2_unpack(Sa, s0, s1);
-                unsigned long long* w = sp.words + ((size_t)cti.tile_lin * Cs + cl) * 2;
-                st_relaxed_v2(w, pack_word(epoch, ST_AGG, p0), pack_word(epoch, ST_AGG, s0));
-                st_relaxed_v2(w + 2, pack_word(epoch, ST_AGG, p1), pack_word(epoch, ST_AGG, s1));
-            }
-            if (part_tile >= 0) reduce_parts(part_tile, part_buf);
-        }
-        part_tile = -1;
-
-        // ---- stage 2 of the previous tile: reverse sweep from registers
-        if (have_prev) {
-            const TileInfo pti = s_info[(k - 1) & (INFO_RING - 1)];
+            const f2 anext = f2_ex2(f2_mul(A2, f2_bcast(sd[(run * TSP + TSP) * nhp])));
+            // G entering this run from the later ones
             int spins = 0;
             while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
                 if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
                 __nanosleep(p.poll_ns);
-                ld_relaxed_v2(wprev, w0, w1);
+                ld_relaxed_v2(wp, w0, w1);
             }
-            const f2 Gin = f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1));
-            const int pb = ((k - 1) & 1) * NR + run;
-            const f2 Gn = f2_fma(*reinterpret_cast<const f2*>(runP + pb * Cs + cl), Gin, *reinterpret_cast<const f2*>(runS + pb * Cs + cl));
-            f2 q = f2_mul(prv.anext, Gn);
+            const f2 Gn = f2_fma(cq0P, f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1)), cq0S);
+            f2 q = f2_mul(anext, Gn);
             f2 accA = f2_bcast(0.f);
             float dd[TSP];
-            const int row = pti.row0 + run * TSP;
-            T* db_o = reinterpret_cast<T*>(sp.dBm) + ((size_t)pti.b * sp.L + row) * sp.dbc_stride + pti.c0 + cl;
 #pragma unroll
             for (int t = TSP - 1; t >= 0; --t) {
-                const f2 Gt = f2_add(prv.g[t], q);
+                const f2 Gt = f2_add(g[t], q);
                 if (act && row + t < sp.L) stg_pair<T>(db_o + (size_t)t * sp.dbc_stride, Gt);
-                const f2 e = f2_mul(f2_mul(Gt, prv.hp[t]), prv.a[t]);          // d abar * abar
+                const f2 e = f2_mul(f2_mul(Gt, hp[t]), a[t]);          // d abar * abar
                 float e0, e1;
-                f2_unpack(f2_mul(e, prv.A2), e0, e1);
+                f2_unpack(f2_mul(e, A2), e0, e1);
                 dd[t] = e0 + e1;
-                accA = f2_fma(e, f2_bcast(prv.dl[t]), accA);
-                q = f2_mul(prv.a[t], Gt);
+                accA = f2_fma(e, f2_bcast(dl[t]), accA);
+                q = f2_mul(a[t], Gt);
             }
             // d delta of a head = sum over its 16 channels = 8 lanes: transposing butterfly, one token per lane pair
             {
@@ -627,36 +584,77 @@ __global__ void __launch_bounds__(32 * NWC * NR, 512 / (32 * NWC * NR) > 0 ? 512
                 wv += __shfl_xor_sync(0xffffffffu, sv, 2);
                 wv += __shfl_xor_sync(0xffffffffu, wv, 1);
                 const int tt = (b2 ? 2 : 0) + (b1 ? 1 : 0);
-                const float dlt = b2 ? (b1 ? prv.dl[3] : prv.dl[2]) : (b1 ? prv.dl[1] : prv.dl[0]);
+                const float dlt = b2 ? (b1 ? dl[3] : dl[2]) : (b1 ? dl[1] : dl[0]);
                 // d dlog = d delta * sigmoid(dlog) = d delta * (1 - exp(-delta));  A = A2 / log2e
                 if (act && !(lane & 1) && row + tt < sp.L)
-                    p.ddlog[((size_t)pti.b * sp.L + row + tt) * sp.H + ((pti.c0 + cl) >> 4)] = wv * inv_log2e * (1.f - __expf(-dlt));
+                    p.ddlog[(tok0 + tt) * sp.H + (cg0 >> 4)] = wv * inv_log2e * (1.f - __expf(-dlt));
             }
             if (act) {
-                const int qb = ((k - 1) & 1) * NR + run;
-                *reinterpret_cast<f2*>(partA + qb * Cs + cl) = f2_mul(f2_mul(accA, prv.A2), f2_bcast(inv_log2e));
-                *reinterpret_cast<f2*>(partD + qb * Cs + cl) = prv.accD;
+                const int qb = ((i & 1) * NR + run) * Cs + cl;
+                *reinterpret_cast<f2*>(partA + qb) = f2_mul(f2_mul(accA, A2), f2_bcast(inv_log2e));
+                *reinterpret_cast<f2*>(partD + qb) = accD;
             }
-            part_tile = pti.tile_lin;
-            part_buf = (k - 1) & 1;
         }
-        if (nx.b >= 0) store_sdel(s, draw);
-        return true;
-    };
+        // ---- prepass of tile i + PD: g = d(y_ssm) * C and the reverse run aggregates
+        if (pi.b >= 0) {
+            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + pi.c0 + cl));
+            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E);
+            const unsigned char* st = smem + lay.off_pre + (size_t)ps * lay.pre_stride;
+            const T* sC = reinterpret_cast<const T*>(st) + cl;
+            const T* sZ = reinterpret_cast<const T*>(st + lay.pitch) + cl;
+            const T* sO = reinterpret_cast<const T*>(st + 2 * lay.pitch) + cl;
+            const float* sd = reinterpret_cast<const float*>(st + 3 * lay.pitch) + hh;
+            ab_mbar_wait(&pbar[ps], (pphase >> ps) & 1u);
+            pphase ^= 1u << ps;
+            // reverse:  G(first token of the run) = Gs + Pr * G(first token of the next run)
+            f2 Gs = f2_bcast(0.f), Pr = f2_bcast(1.f);
+            f2 an = f2_ex2(f2_mul(A2, f2_bcast(sd[(run * TSP + TSP) * nhp])));
+#pragma unroll
+            for (int t = TSP - 1; t >= 0; --t) {
+                const int r = run * TSP + t;
+                const f2 cv = lds_pair<T>(sC + (size_t)r * Cs), zv = lds_pair<T>(sZ + (size_t)r * Cs), dov = lds_pair<T>(sO + (size_t)r * Cs);
+                const f2 gt = f2_mul(f2_mul(dov, f2_mul(zv, f2_sigmoid<T>(zv))), cv);
+                // G_t = g_t + a_{t+1} G_{t+1}:  with G_{t+1} = Gs + Pr * Gin
+                Gs = f2_fma(an, Gs, gt);
+                Pr = f2_mul(Pr, an);
+                an = f2_ex2(f2_mul(A2, f2_bcast(sd[r * nhp])));
+            }
+            if (act) {
+                const int bi = (((i + PD) & 1) * NR + run) * Cs + cl;
+                *reinterpret_cast<f2*>(runP + bi) = Pr;
+                *reinterpret_cast<f2*>(runS + bi) = Gs;
+            }
+        }
+        __syncthreads();
 
-    BwdSet A, Bq;
-    int s = 0;
-    for (int k = 0;; k += 2) {
-        if (!body(k, s, A, Bq)) break;
-        s = s + 1 == NST ? 0 : s + 1;
-        if (!body(k + 1, s, Bq, A)) break;
-        s = s + 1 == NST ? 0 : s + 1;
+        if (tid == 0) {
+            if (i + 2 >= 0) {
+                const TileInfo nm = s_info[(i + 2) & (INFO_RING - 1)];
+                if (nm.b >= 0) issue_main(i & 1, nm);
+            }
+            const TileInfo np = s_info[(i + LA) & (INFO_RING - 1)];
+            if (np.b >= 0) issue_pre((ps + 2) % NPRE, np);
+        }
+        if (run == (i + PD) % NR && act) {
+            if (pi.b >= 0)
+                compose_and_publish<NR, true>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs,
+                                              sp.words + ((size_t)pi.tile_lin * Cs + cl) * 2, epoch);
+            if (i >= 0) reduce_parts(mi.tile_lin, i & 1);
+        }
+        cq0P = cq1P; cq0S = cq1S;
+        if (i + 2 >= 0) {
+            const int bi = (((i + 2) & 1) * NR + run) * Cs + cl;
+            cq1P = *reinterpret_cast<const f2*>(runP + bi);
+            cq1S = *reinterpret_cast<const f2*>(runS + bi);
+        }
+        ps = ps + 1 == NPRE ? 0 : ps + 1;
     }
-    // partials of the last tile
-    __syncthreads();
-    if (part_tile >= 0 && run == 0 && act) reduce_parts(part_tile, part_buf);
     cta_finish(p.sync);
 }
+
+}  // namespace
+
+namespace {
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -668,15 +666,6 @@ int pipe_env(const char* name, int dflt, int alt, int alt2 = -1) {
     if (!e) return dflt;
     const int v = atoi(e);
     return (v == alt || v == alt2) ? v : dflt;
-}
-int pipe_nst(bool bwd) {
-    static const int f = pipe_env("APERTIS_B200_SCAN_NST_FWD", 2, 3), b = pipe_env("APERTIS_B200_SCAN_NST_BWD", 3, 2);
-    return bwd ? b : f;
-}
-// bf16, 64-channel slab: 16 runs (512 threads, 128 registers, a few spills) or 12 runs (384 threads, no spills)
-int pipe_nr_bwd16() {
-    static const int v = pipe_env("APERTIS_B200_SCAN_NR_BWD", 16, 12);
-    return v;
 }
 
 // slab = 64 channels when the width allows it, else the widest head-aligned divisor of Di that one CTA row covers.
@@ -692,9 +681,9 @@ bool pipe_tiling(int L, int Di, int dtype, bool bwd, PipeTiling& t) {
     t.Cs = Cs;
     t.NWC = (Cs + 63) / 64;
     if (Cs * 2 < t.NWC * 64) return false;                      // more than half of the lanes would idle
-    static const int nr_f_bf16[5] = {0, 12, 6, 4, 3}, nr_b_bf16[5] = {0, 16, 8, 5, 4}, nr_f32[5] = {0, 8, 4, 3, 2};
-    t.NR = dtype == AB_F32 ? nr_f32[t.NWC] : (bwd ? nr_b_bf16[t.NWC] : nr_f_bf16[t.NWC]);
-    if (dtype == AB_BF16 && bwd && t.NWC == 1) t.NR = pipe_nr_bwd16();
+    static const int nr_bf16[5] = {0, 16, 8, 5, 4}, nr_f32[5] = {0, 8, 4, 3, 2};
+    t.NR = dtype == AB_F32 ? nr_f32[t.NWC] : nr_bf16[t.NWC];
+    (void)bwd;
     t.TT = t.NR * TSP;
     t.nslab = Di / Cs;
     t.nchunks = (int)ab_ceil_div(L, t.TT);
@@ -704,10 +693,10 @@ bool pipe_tiling(int L, int Di, int dtype, bool bwd, PipeTiling& t) {
 constexpr int PIPE_SMS = 148;          // B200; the plan must not need a device
 // CTAs per SM the shared memory and the register budget of the launch bounds admit
 int pipe_occ_static(const PipeTiling& t, bool bwd) {
-    const PipeSmem m = pipe_smem(t.Cs, t.TT, t.NR, pipe_nst(bwd), bwd ? 5 : 4, t.esize, bwd);
+    const PipeSmem m = pipe_smem(t.Cs, t.TT, t.NR, bwd ? 5 : 4, bwd ? 3 : 1, t.esize, bwd);
     int occ = (int)((227u * 1024u) / (m.total + 1024u));
     const int thr = 32 * t.NWC * t.NR;
-    const int by_reg = bwd ? (512 / thr > 0 ? 512 / thr : 1) : (768 / thr > 0 ? 768 / thr : 1);
+    const int by_reg = bwd ? (512 / thr > 0 ? 512 / thr : 1) : (1024 / thr > 0 ? 1024 / thr : 1);
     if (occ > by_reg) occ = by_reg;
     return occ;
 }
@@ -718,6 +707,17 @@ bool pipe_supported(int B, int L, int Di, int dtype, PipeTiling& tf, PipeTiling&
     if (occ_b < 1 || occ_f < 1) return false;
     const int nchains = B * tf.nslab;
     return nchains * 4 <= PIPE_SMS * occ_b && nchains * 4 <= PIPE_SMS * occ_f;
+}
+
+// saved-state buffer per batch (fp32, rows of Di): ceil(L/TSP) run states, then delta [L, Hp]
+struct PipeSaved { int Hp, n_run, n_rows; };
+PipeSaved pipe_saved(int L, int Di) {
+    PipeSaved v;
+    const int H = Di / 16;
+    v.Hp = (H + 3) & ~3;
+    v.n_run = (int)ab_ceil_div(L, TSP);
+    v.n_rows = v.n_run + (int)ab_ceil_div((int64_t)L * v.Hp, Di);
+    return v;
 }
 
 struct PipeWs { size_t off_sync, off_err, off_words, off_incl, off_part, total; };
@@ -745,6 +745,14 @@ int pipe_map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di,
     return ab_encode_tmap(m, dtype == AB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base,
                           dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
+// delta [B][L, Hp] fp32 inside the saved-state buffer: box = (heads of the slab in whole 16-byte units) x rows
+int pipe_map_delta(CUtensorMap* m, const float* delta, int B, int L, int Hp, size_t batch_stride, int Cs, int rows) {
+    AB_REQUIRE(((uintptr_t)delta % 16) == 0 && (batch_stride * 4) % 16 == 0, "selective_scan: saved-state buffer must be 16-byte aligned");
+    uint64_t dims[3] = {(uint64_t)Hp, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)Hp * 4, (uint64_t)batch_stride * 4};
+    uint32_t box[3] = {(uint32_t)((((uint32_t)Cs >> 4) + 3u) & ~3u), (uint32_t)rows, 1};
+    return ab_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, delta, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
 
 template <typename K>
 int pipe_grid(K kfn, int threads, size_t smem, int want, int* grid) {
@@ -768,76 +776,47 @@ int pipe_grid(K kfn, int threads, size_t smem, int want, int* grid) {
     return AB_OK;
 }
 
-template <typename T, int NWC, int NR, int NST, int CS>
+template <typename T, int NWC, int NR, int CS>
 int launch_fwd_pipe_cs(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    const PipeSmem m = pipe_smem(t.Cs, t.TT, NR, NST, 4, (int)sizeof(T), false);
-    auto kfn = scan_fwd_pipe_kernel<T, NWC, NR, NST, CS>;
+    const PipeSmem m = pipe_smem(t.Cs, t.TT, NR, 4, 1, (int)sizeof(T), false);
+    auto kfn = scan_fwd_pipe_kernel<T, NWC, NR, CS>;
     int grid = 0;
     if (int e = pipe_grid(kfn, 32 * NWC * NR, m.total, p.s.n_scan + p.ntiles, &grid)) return e;
     AB_REQUIRE(grid > p.s.n_scan, "selective_scan (pipelined): %d chains leave no worker CTA", p.s.n_scan);
-    kfn<<<grid, 32 * NWC * NR, m.total, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    kfn<<<grid, 32 * NWC * NR, m.total, st>>>(maps[0], maps[1], maps[2], maps[3], maps[5], p);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
-template <typename T, int NWC, int NR, int NST, int CS>
+template <typename T, int NWC, int NR, int CS>
 int launch_bwd_pipe_cs(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    const PipeSmem m = pipe_smem(t.Cs, t.TT, NR, NST, 5, (int)sizeof(T), true);
-    auto kfn = scan_bwd_pipe_kernel<T, NWC, NR, NST, CS>;
+    const PipeSmem m = pipe_smem(t.Cs, t.TT, NR, 5, 3, (int)sizeof(T), true);
+    auto kfn = scan_bwd_pipe_kernel<T, NWC, NR, CS>;
     int grid = 0;
     if (int e = pipe_grid(kfn, 32 * NWC * NR, m.total, p.s.n_scan + p.ntiles, &grid)) return e;
     AB_REQUIRE(grid > p.s.n_scan, "selective_scan (pipelined): %d chains leave no worker CTA", p.s.n_scan);
-    kfn<<<grid, 32 * NWC * NR, m.total, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    kfn<<<grid, 32 * NWC * NR, m.total, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
-
 // slab widths with a specialised kernel: 64 (d_inner a multiple of 64) and 176 (the 1.5B text block)
-template <typename T, int NWC, int NR, int NST>
-int launch_fwd_pipe(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    if (NWC == 1 && t.Cs == 64) return launch_fwd_pipe_cs<T, NWC, NR, NST, NWC == 1 ? 64 : 0>(maps, p, t, st);
-    if (NWC == 3 && t.Cs == 176) return launch_fwd_pipe_cs<T, NWC, NR, NST, NWC == 3 ? 176 : 0>(maps, p, t, st);
-    return launch_fwd_pipe_cs<T, NWC, NR, NST, 0>(maps, p, t, st);
-}
-template <typename T, int NWC, int NR, int NST>
-int launch_bwd_pipe(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    if (NWC == 1 && t.Cs == 64) return launch_bwd_pipe_cs<T, NWC, NR, NST, NWC == 1 ? 64 : 0>(maps, p, t, st);
-    if (NWC == 3 && t.Cs == 176) return launch_bwd_pipe_cs<T, NWC, NR, NST, NWC == 3 ? 176 : 0>(maps, p, t, st);
-    return launch_bwd_pipe_cs<T, NWC, NR, NST, 0>(maps, p, t, st);
-}
 template <typename T, int NWC, int NR>
-int dispatch_fwd(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    return pipe_nst(false) == 2 ? launch_fwd_pipe<T, NWC, NR, 2>(maps, p, t, st) : launch_fwd_pipe<T, NWC, NR, 3>(maps, p, t, st);
-}
-template <typename T, int NWC, int NR>
-int dispatch_bwd(const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    return pipe_nst(true) == 2 ? launch_bwd_pipe<T, NWC, NR, 2>(maps, p, t, st) : launch_bwd_pipe<T, NWC, NR, 3>(maps, p, t, st);
+int launch_pipe(bool bwd, const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
+    constexpr int CSS = NWC == 1 ? 64 : (NWC == 3 ? 176 : 0);
+    if (CSS && t.Cs == CSS) return bwd ? launch_bwd_pipe_cs<T, NWC, NR, CSS>(maps, p, t, st) : launch_fwd_pipe_cs<T, NWC, NR, CSS>(maps, p, t, st);
+    return bwd ? launch_bwd_pipe_cs<T, NWC, NR, 0>(maps, p, t, st) : launch_fwd_pipe_cs<T, NWC, NR, 0>(maps, p, t, st);
 }
 int dispatch_pipe(bool bwd, int dtype, const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
-    if (dtype == AB_BF16) {
-        if (!bwd) switch (t.NWC) {
-            case 1: return dispatch_fwd<__nv_bfloat16, 1, 12>(maps, p, t, st);
-            case 2: return dispatch_fwd<__nv_bfloat16, 2, 6>(maps, p, t, st);
-            case 3: return dispatch_fwd<__nv_bfloat16, 3, 4>(maps, p, t, st);
-            default: return dispatch_fwd<__nv_bfloat16, 4, 3>(maps, p, t, st);
-        }
-        switch (t.NWC) {
-            case 1: return t.NR == 12 ? dispatch_bwd<__nv_bfloat16, 1, 12>(maps, p, t, st) : dispatch_bwd<__nv_bfloat16, 1, 16>(maps, p, t, st);
-            case 2: return dispatch_bwd<__nv_bfloat16, 2, 8>(maps, p, t, st);
-            case 3: return dispatch_bwd<__nv_bfloat16, 3, 5>(maps, p, t, st);
-            default: return dispatch_bwd<__nv_bfloat16, 4, 4>(maps, p, t, st);
-        }
-    }
-    if (!bwd) switch (t.NWC) {
-        case 1: return dispatch_fwd<float, 1, 8>(maps, p, t, st);
-        case 2: return dispatch_fwd<float, 2, 4>(maps, p, t, st);
-        case 3: return dispatch_fwd<float, 3, 3>(maps, p, t, st);
-        default: return dispatch_fwd<float, 4, 2>(maps, p, t, st);
+    if (dtype == AB_BF16) switch (t.NWC) {
+        case 1: return launch_pipe<__nv_bfloat16, 1, 16>(bwd, maps, p, t, st);
+        case 2: return launch_pipe<__nv_bfloat16, 2, 8>(bwd, maps, p, t, st);
+        case 3: return launch_pipe<__nv_bfloat16, 3, 5>(bwd, maps, p, t, st);
+        default: return launch_pipe<__nv_bfloat16, 4, 4>(bwd, maps, p, t, st);
     }
     switch (t.NWC) {
-        case 1: return dispatch_bwd<float, 1, 8>(maps, p, t, st);
-        case 2: return dispatch_bwd<float, 2, 4>(maps, p, t, st);
-        case 3: return dispatch_bwd<float, 3, 3>(maps, p, t, st);
-        default: return dispatch_bwd<float, 4, 2>(maps, p, t, st);
+        case 1: return launch_pipe<float, 1, 8>(bwd, maps, p, t, st);
+        case 2: return launch_pipe<float, 2, 4>(bwd, maps, p, t, st);
+        case 3: return launch_pipe<float, 3, 3>(bwd, maps, p, t, st);
+        default: return launch_pipe<float, 4, 2>(bwd, maps, p, t, st);
     }
 }
 
@@ -855,10 +834,13 @@ void fill_common(PipeParams& p, const PipeTiling& t, const PipeWs& wl, void* ws,
     s.part = (float*)(w8 + wl.off_part);
     s.n_scan = s.nchains;
     p.ntiles = s.nchains * t.nchunks;
-    static const int scan_k = pipe_env("APERTIS_B200_SCAN_K", PIPE_SCAN_K, 16, 64);
-    p.scan_k = scan_k;
+    static const char* ke = getenv("APERTIS_B200_SCAN_K");
+    static const char* re = getenv("APERTIS_B200_SCAN_R");
+    p.scan_k = ke ? atoi(ke) : PIPE_SCAN_K;
+    if (p.scan_k != 16 && p.scan_k != 32 && p.scan_k != 64 && p.scan_k != 128) p.scan_k = PIPE_SCAN_K;
+    p.scan_r = re && atoi(re) == 4 ? 4 : 8;
     static const char* pe = getenv("APERTIS_B200_SCAN_POLL_NS");
-    p.poll_ns = pe ? (unsigned)atoi(pe) : 200u;
+    p.poll_ns = pe ? (unsigned)atoi(pe) : 100u;
 }
 
 }  // namespace
@@ -871,7 +853,7 @@ bool ab_scan_pipe_plan(int B, int L, int Di, int dtype, int* tile_rows, int* sla
     if (tile_rows) *tile_rows = tf.TT;
     if (bwd_tile_rows) *bwd_tile_rows = tb.TT;
     if (slab) *slab = tf.Cs;
-    if (n_states) *n_states = (int)ab_ceil_div(L, TSP);          // saved states per sequence: one per run of TSP tokens
+    if (n_states) *n_states = pipe_saved(L, Di).n_rows;          // rows of Di floats per batch: run states, then delta
     if (ws_bytes) *ws_bytes = pipe_ws(tf, tb, B).total;
     return true;
 }
@@ -883,16 +865,27 @@ int ab_scan_pipe_fwd(const void* xa, const void* dlog, const void* Bm, const voi
     AB_REQUIRE(pipe_supported(B, L, Di, dtype, t, tb), "selective_scan_fwd: the pipelined mode does not cover B=%d L=%d Di=%d (ask ab_selective_scan_plan)", B, L, Di);
     const PipeWs wl = pipe_ws(t, tb, B);
     AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_fwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
-    AB_REQUIRE(hrun != nullptr, "selective_scan_fwd: the pipelined mode needs the run-state buffer (hstart)");
-    CUtensorMap maps[4];
+    AB_REQUIRE(hrun != nullptr, "selective_scan_fwd: the pipelined mode needs the saved-state buffer (hstart)");
+    const PipeSaved sv = pipe_saved(L, Di);
+    const size_t batch_stride = (size_t)sv.n_rows * Di;
+    float* delta = hrun + (size_t)sv.n_run * Di;
+    {
+        const size_t total = (size_t)B * L * sv.Hp;
+        const unsigned blocks = (unsigned)(ab_ceil_div((int64_t)total, 256) < 4096 ? ab_ceil_div((int64_t)total, 256) : 4096);
+        if (dtype == AB_F32) scan_delta_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dlog, delta, L, H, sv.Hp, batch_stride, total);
+        else scan_delta_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)dlog, delta, L, H, sv.Hp, batch_stride, total);
+        AB_LAUNCH_CHECK();
+    }
+    CUtensorMap maps[6];
     if (int e = pipe_map3(&maps[0], xa, dtype, B, L, Di, Di, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[1], Bm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[2], Cm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[3], z, dtype, B, L, Di, z_stride, t.Cs, t.TT)) return e;
+    if (int e = pipe_map_delta(&maps[5], delta, B, L, sv.Hp, batch_stride, t.Cs, t.TT)) return e;
     PipeParams p;
     fill_common(p, t, wl, ws, B, L, Di, H);
     p.s.dlog = dlog; p.s.A_log = A_log; p.s.Dp = D; p.s.h0 = h0; p.s.y = y; p.s.h_last = h_last;
-    p.hrun = hrun;
+    p.hrun = hrun; p.batch_stride = batch_stride;
     return dispatch_pipe(false, dtype, maps, p, t, stream);
 }
 
@@ -906,17 +899,22 @@ int ab_scan_pipe_bwd(const void* xa, const void* dlog, const void* Bm, const voi
     AB_REQUIRE(ws && ws_bytes >= wl.total, "selective_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, wl.total);
     const int es = dtype == AB_F32 ? 4 : 2;
     AB_REQUIRE((dbc_stride * es) % 8 == 0, "selective_scan_bwd: dB/dC row stride must be 8-byte aligned");
-    CUtensorMap maps[5];
+    const PipeSaved sv = pipe_saved(L, Di);
+    const size_t batch_stride = (size_t)sv.n_rows * Di;
+    const float* delta = hrun + (size_t)sv.n_run * Di;
+    CUtensorMap maps[6];
     if (int e = pipe_map3(&maps[0], xa, dtype, B, L, Di, Di, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[1], Bm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[2], Cm, dtype, B, L, Di, bc_stride, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[3], z, dtype, B, L, Di, z_stride, t.Cs, t.TT)) return e;
     if (int e = pipe_map3(&maps[4], dout, dtype, B, L, Di, Di, t.Cs, t.TT)) return e;
+    if (int e = pipe_map_delta(&maps[5], delta, B, L, sv.Hp, batch_stride, t.Cs, t.TT + 1)) return e;
     PipeParams p;
     fill_common(p, t, wl, ws, B, L, Di, H);
-    p.s.dlog = dlog; p.s.A_log = A_log; p.s.Dp = D;
+    (void)dlog;
+    p.s.A_log = A_log; p.s.Dp = D;
     p.s.dxa = dxa; p.s.dBm = dBm; p.s.dCm = dCm; p.s.dz = dz; p.s.dbc_stride = dbc_stride;
-    p.hrun = const_cast<float*>(hrun);
+    p.hrun = const_cast<float*>(hrun); p.batch_stride = batch_stride;
     p.ddlog = ddlog;
     *part_out = p.s.part;
     return dispatch_pipe(true, dtype, maps, p, t, stream);

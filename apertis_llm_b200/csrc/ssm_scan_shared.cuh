@@ -89,20 +89,20 @@ __device__ __forceinline__ float wait_incoming(const ScanParams& p, uint32_t epo
 // segment again to publish the per-tile states: loads, FMA chains and stores of a round are spread over R warps sets.
 // The composition order is fixed by the tile order, so results are bitwise reproducible.
 template <int DIR>
-__device__ __forceinline__ void scanner_role(const ScanParams& p, uint32_t epoch, int kmax, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem below hs*/, size_t ring_bytes) {
+__device__ __forceinline__ void scanner_role(const ScanParams& p, uint32_t epoch, int kmax, int rmax, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem below hs*/, size_t ring_bytes) {
     const int n = p.nchunks, Cs = p.Cs;
     const int slab = chain % p.nslab, b = chain / p.nslab;
     int spins = 0;
     int R = (int)blockDim.x / Cs;
-    R = R >= 4 ? 4 : (R >= 2 ? 2 : R);
-    // shared memory: ring [K][Cs] uint4, then segP / segS / segN [R][Cs]
-    const size_t seg_bytes = (size_t)3 * 4 * Cs * sizeof(float);
+    R = R >= rmax ? rmax : (R >= 4 ? 4 : (R >= 2 ? 2 : R));
+    // shared memory: ring [K][Cs] uint4, then segP / segS / segN [8][Cs]
+    const size_t seg_bytes = (size_t)3 * 8 * Cs * sizeof(float);
     const int K = ring_bytes > seg_bytes ? ring_depth(ring_bytes - seg_bytes, Cs, kmax) : 0;
     if (R >= 1 && K >= 8) {
         const int S = K / R;                           // tiles per replica and round (>= 2)
         float* segP = reinterpret_cast<float*>(ring + (size_t)K * Cs);
-        float* segS = segP + 4 * Cs;
-        int* segN = reinterpret_cast<int*>(segS + 4 * Cs);
+        float* segS = segP + 8 * Cs;
+        int* segN = reinterpret_cast<int*>(segS + 8 * Cs);
         const int c = threadIdx.x % Cs, r = threadIdx.x / Cs;
         const bool active = r < R;
         const int cg = slab * Cs + c;

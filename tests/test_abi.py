@@ -46,10 +46,10 @@ def test_pure_queries_work_without_gpu():
     plan = lambda *a: _lib.query("ab_selective_scan_plan", *a, ctypes.byref(m), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ws))
     rc = plan(1, 65536, 512, _lib.AB_BF16)
     assert rc == 0 and t.value % 4 == 0 and 512 % s.value == 0 and n.value == -(-65536 // t.value)
-    # pipelined schedule: one saved state per run of 4 tokens; a batch with more chains than scanner CTAs falls back
+    # pipelined schedule: per batch one saved state per run of 4 tokens, then delta [L, H] (rows of Di floats); a batch with more chains than scanner CTAs falls back
     m.value = _lib.SCAN_PIPELINED
     rc = plan(1, 65536, 512, _lib.AB_BF16)
-    assert rc == 0 and m.value == _lib.SCAN_PIPELINED and s.value == 64 and n.value == 65536 // 4 and ws.value > 0
+    assert rc == 0 and m.value == _lib.SCAN_PIPELINED and s.value == 64 and n.value == 65536 // 4 + 65536 // 16 and ws.value > 0
     m.value = _lib.SCAN_PIPELINED
     rc = plan(64, 4096, 512, _lib.AB_BF16)
     assert rc == 0 and m.value == _lib.SCAN_SINGLE_PASS and n.value == -(-4096 // t.value)
