@@ -888,7 +888,7 @@ int check_common(int B, int L, int Di, int H, int dtype, ScanTiling& t) {
 
 // pipelined persistent schedule (ssm_scan_pipe.cu)
 bool ab_scan_pipe_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_states, size_t* ws_bytes,
-                       int* bwd_tile_rows);
+                       int* bwd_tile_rows, int* bwd_tiles_per_chain);
 int ab_scan_pipe_fwd(const void* xa, const void* dlog, const void* Bm, const void* Cm, int64_t bc_stride, const void* z,
                      int64_t z_stride, const float* A_log, const float* D, const float* h0, void* y, float* h_last,
                      float* hrun, void* ws, size_t ws_bytes, int B, int L, int Di, int H, int dtype, cudaStream_t stream);
@@ -903,7 +903,7 @@ extern "C" int ab_selective_scan_plan(int B, int L, int Di, int dtype, int* mode
     AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "selective_scan_plan: bad dtype");
     AB_REQUIRE(mode && (*mode == AB_SCAN_SINGLE_PASS || *mode == AB_SCAN_TWO_PASS || *mode == AB_SCAN_PIPELINED), "selective_scan_plan: bad mode");
     if (*mode == AB_SCAN_PIPELINED) {
-        if (B > 0 && L > 0 && Di > 0 && Di % 16 == 0 && ab_scan_pipe_plan(B, L, Di, dtype, tile_rows, slab, n_chunks, ws_bytes, nullptr)) return AB_OK;
+        if (B > 0 && L > 0 && Di > 0 && Di % 16 == 0 && ab_scan_pipe_plan(B, L, Di, dtype, tile_rows, slab, n_chunks, ws_bytes, nullptr, nullptr)) return AB_OK;
         *mode = AB_SCAN_SINGLE_PASS;          // shapes the pipelined schedule does not cover
     }
     AB_REQUIRE(B > 0 && L > 0 && Di > 0 && make_tiling(L, Di, dtype, t), "selective_scan_plan: no tiling for Di=%d", Di);
@@ -980,10 +980,9 @@ extern "C" int ab_selective_scan_bwd(const void* xa, const void* dlog, const voi
         float* part = nullptr;
         if (int e = ab_scan_pipe_bwd(xa, dlog, Bm, Cm, bc_stride, z, z_stride, dout, A_log, D, hstart, dxa, dBm, dCm, dbc_stride, dz,
                                      ddlog_parts, &part, ws, ws_bytes, B, L, Di, H, dtype, stream)) return e;
-        int T2 = 0, Cs2 = 0;
-        ab_scan_pipe_plan(B, L, Di, dtype, nullptr, &Cs2, nullptr, nullptr, &T2);
-        scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, PR_CH), PR_CH * PR_Q, 0, stream>>>(part, dA_log, dD, B, Di, Cs2, Di / Cs2,
-                                                                                                (int)ab_ceil_div(L, T2));
+        int T2 = 0, Cs2 = 0, ntile2 = 0;
+        ab_scan_pipe_plan(B, L, Di, dtype, nullptr, &Cs2, nullptr, nullptr, &T2, &ntile2);
+        scan_param_reduce_kernel<<<(unsigned)ab_ceil_div(Di, PR_CH), PR_CH * PR_Q, 0, stream>>>(part, dA_log, dD, B, Di, Cs2, Di / Cs2, ntile2);
         AB_LAUNCH_CHECK();
         return AB_OK;
     }

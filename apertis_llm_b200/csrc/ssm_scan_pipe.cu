@@ -93,11 +93,22 @@ __device__ __forceinline__ void st_relaxed_v2(unsigned long long* p, unsigned lo
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
-struct __align__(16) TileInfo { int b, c0, row0, tile_lin; };      // b < 0: no tile
+struct __align__(16) TileInfo { int b, c0, row0, tile_lin; };      // b < 0: no tile; tile_lin = super-tile * SG + position inside it
 
-constexpr int PD = 3;              // the prepass runs PD tiles ahead of the main pass
-constexpr int LA = PD + 2;         // ticket look-ahead
-constexpr int NPRE = 3;            // prepass ring slots
+#ifndef PIPE_PD
+#define PIPE_PD 8
+#endif
+#ifndef PIPE_LOG_SG
+#define PIPE_LOG_SG 2
+#endif
+#ifndef PIPE_NPRE
+#define PIPE_NPRE 3
+#endif
+constexpr int PD = PIPE_PD;        // the prepass runs PD tiles ahead of the main pass (>= 2)
+constexpr int NPRE = PIPE_NPRE;    // prepass ring slots: its loads are issued NPRE - 1 tiles ahead of the prepass
+constexpr int LA = PD + NPRE - 1;  // ticket look-ahead
+constexpr int LOG_SG = PIPE_LOG_SG, SG = 1 << LOG_SG;   // consecutive tiles of a chain one CTA takes per ticket (a super-tile):
+                                                      // one hand-shake with the scanner per SG tiles
 constexpr int NMAIN = 2;           // main ring stages
 
 struct PipeParams {
@@ -111,22 +122,34 @@ struct PipeParams {
     unsigned int poll_ns;        // back-off between polls of the incoming-state word
 };
 
-__device__ __forceinline__ TileInfo decode_tile_info(const PipeParams& p, int tile, int TT, bool reverse) {
+__device__ __forceinline__ TileInfo decode_tile_info(const PipeParams& p, int ticket, int TT, bool reverse) {
     TileInfo t;
-    if (tile < 0 || tile >= p.ntiles) { t.b = -1; t.c0 = 0; t.row0 = 0; t.tile_lin = 0; return t; }
-    const int chain = tile % p.s.nchains, jj = tile / p.s.nchains;
-    const int j = reverse ? p.s.nchunks - 1 - jj : jj;
+    if (ticket < 0 || ticket >= p.ntiles) { t.b = -1; t.c0 = 0; t.row0 = 0; t.tile_lin = 0; return t; }
+    const int chain = ticket % p.s.nchains, jj = ticket / p.s.nchains;
+    const int js = reverse ? p.s.nchunks - 1 - jj : jj;                 // p.s.nchunks counts super-tiles (the scanner's units)
     t.b = chain / p.s.nslab;
     t.c0 = (chain % p.s.nslab) * p.s.Cs;
-    t.row0 = j * TT;
-    t.tile_lin = chain * p.s.nchunks + j;
+    t.row0 = (js * SG + (reverse ? SG - 1 : 0)) * TT;                   // rows beyond L are zero-filled by TMA: identity tiles
+    t.tile_lin = (chain * p.s.nchunks + js) * SG;
+    return t;
+}
+// thread 0: tile of pipeline position q (a new ticket every SG positions, else the successor of position q - 1)
+__device__ __forceinline__ TileInfo next_tile_info(const PipeParams& p, const TileInfo* s_info, int q, int& pending, int TT, bool reverse) {
+    TileInfo t;
+    if ((q & (SG - 1)) == 0) {
+        t = decode_tile_info(p, pending, TT, reverse);
+        if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - p.s.n_scan;
+    } else {
+        t = s_info[(q - 1) & (INFO_RING - 1)];
+        if (t.b >= 0) { t.row0 += reverse ? -TT : TT; t.tile_lin += 1; }
+    }
     return t;
 }
 
 // shared-memory carve-up, identical on host and device.  A main stage holds `nmain` operand tiles and the delta tile,
 // a prepass slot `npre` operand tiles and the delta tile.
 struct PipeSmem {
-    uint32_t pitch, dpitch, nhp, main_stride, pre_stride, off_pre, off_runP, off_runS, off_partA, off_partD, off_info, off_bars, total;
+    uint32_t pitch, dpitch, nhp, main_stride, pre_stride, off_pre, off_runP, off_runS, off_partA, off_partD, off_carry, off_acc, off_info, off_bars, total;
 };
 __host__ __device__ inline PipeSmem pipe_smem(int Cs, int TT, int NR, int nmain, int npre, int esize, bool bwd) {
     PipeSmem m;
@@ -142,6 +165,8 @@ __host__ __device__ inline PipeSmem pipe_smem(int Cs, int TT, int NR, int nmain,
     m.off_runS = o; o += 2u * NR * Cs * 4;
     m.off_partA = o; if (bwd) o += 2u * NR * Cs * 4;
     m.off_partD = o; if (bwd) o += 2u * NR * Cs * 4;
+    m.off_carry = o; o += 2u * Cs * 4;        // state leaving a tile -> next tile of the super-tile (two buffers)
+    m.off_acc = o; o += 2u * Cs * 4;          // aggregate of the super-tile so far (P, S)
     o = (o + 15u) & ~15u;
     m.off_info = o; o += INFO_RING * 16;
     m.off_bars = o; o += (NMAIN + NPRE) * 8;
@@ -168,9 +193,9 @@ __device__ __forceinline__ void cta_finish(unsigned int* sync) {
 // lanes of one warp may arrive here while their siblings still execute the loop's barriers: no __syncthreads on this
 // path (two different aligned barriers inside one diverged warp are undefined behaviour); the last thread to arrive,
 // counted in shared memory, signs the CTA off.
-__device__ __forceinline__ void scanner_finish(unsigned int* sync, unsigned int* s_left) {
+__device__ __forceinline__ void scanner_finish(unsigned int* sync, unsigned int* s_left, int participants) {
     __threadfence();
-    if (atomicAdd(s_left, 1u) == blockDim.x - 1) grid_finish(sync);
+    if (atomicAdd(s_left, 1u) == (unsigned)participants - 1u) grid_finish(sync);
 }
 
 // delta = softplus(dt logits) as fp32 rows of Hp (whole 16-byte units, TMA-loadable) heads; kept for the backward
@@ -185,10 +210,27 @@ __global__ void __launch_bounds__(256) scan_delta_kernel(const T* __restrict__ d
     }
 }
 
+#ifdef AB_SCAN_TRACE
+// debug build only (make TRACE=1): per-warp phase timestamps of the first worker CTAs, read back by tools/scan_trace_pipe.py
+constexpr int PT_CTAS = 8, PT_ITERS = 48, PT_WARPS = 16, PT_SLOTS = 8;
+__device__ unsigned long long g_pipe_trace[PT_CTAS * PT_ITERS * PT_WARPS * PT_SLOTS];
+__device__ unsigned int g_pipe_trace_cta;
+__device__ __forceinline__ void pt_mark(int cta, int it, int slot) {
+    if ((threadIdx.x & 31) == 0 && cta >= 0 && cta < PT_CTAS && it >= 0 && it < PT_ITERS && (threadIdx.x >> 5) < PT_WARPS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_pipe_trace[(((size_t)cta * PT_ITERS + it) * PT_WARPS + (threadIdx.x >> 5)) * PT_SLOTS + slot] = t;
+    }
+}
+#define PT_MARK(slot) pt_mark(pt_cta, i + PD, slot)
+#else
+#define PT_MARK(slot)
+#endif
+
 // duty warp: compose the run aggregates of one tile in run order (forward) or reverse run order (backward), leave the
 // per-run coefficients (state entering the run = P * incoming + S) in their place and publish the tile aggregate
 template <int NR, bool REVERSE>
-__device__ __forceinline__ void compose_and_publish(float* rp, float* rs, int Cs, unsigned long long* w, uint32_t epoch) {
+__device__ __forceinline__ void compose_and_publish(float* rp, float* rs, int Cs, float* acc, int sub, unsigned long long* w, uint32_t epoch) {
     f2 Pa = f2_bcast(1.f), Sa = f2_bcast(0.f);
 #pragma unroll
     for (int q0 = 0; q0 < NR; q0 += 4) {
@@ -208,6 +250,17 @@ __device__ __forceinline__ void compose_and_publish(float* rp, float* rs, int Cs
                 Sa = f2_fma(P4[u], Sa, S4[u]);
                 Pa = f2_mul(Pa, P4[u]);
             }
+    }
+    // fold the tile into the aggregate of its super-tile; the last tile publishes it
+    if (sub > 0) {
+        const f2 aP = *reinterpret_cast<const f2*>(acc), aS = *reinterpret_cast<const f2*>(acc + Cs);
+        Sa = f2_fma(Pa, aS, Sa);
+        Pa = f2_mul(aP, Pa);
+    }
+    if (sub < SG - 1) {
+        *reinterpret_cast<f2*>(acc) = Pa;
+        *reinterpret_cast<f2*>(acc + Cs) = Sa;
+        return;
     }
     float p0, p1, s0, s1;
     f2_unpack(Pa, p0, p1); f2_unpack(Sa, s0, s1);
@@ -232,6 +285,8 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T), dbytes = (uint32_t)TT * nhp * 4u;
     float* runP = reinterpret_cast<float*>(smem + lay.off_runP);
     float* runS = reinterpret_cast<float*>(smem + lay.off_runS);
+    float* carry = reinterpret_cast<float*>(smem + lay.off_carry);
+    float* accb = reinterpret_cast<float*>(smem + lay.off_acc);
     TileInfo* s_info = reinterpret_cast<TileInfo*>(smem + lay.off_info);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
     uint64_t* pbar = mbar + NMAIN;
@@ -255,8 +310,8 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     const uint32_t epoch = s_epoch;
     if ((int)s_first < sp.n_scan) {
         float* hs = runS + 2 * NR * Cs - Cs;          // generic scanner path only; the ring may use everything below
-        scanner_role<+1>(sp, epoch, p.scan_k, p.scan_r, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
-        scanner_finish(p.sync, &s_left);
+        const int np = scanner_role<+1>(sp, epoch, p.scan_k, p.scan_r, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
+        if (np) scanner_finish(p.sync, &s_left, np);
         return;
     }
 
@@ -279,56 +334,78 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     // ---- prologue: the first two pipeline positions
     int pending = -1;
     if (tid == 0) {
-        const int base = (int)atomicAdd(p.sync, 2u) - sp.n_scan;
-        s_info[0] = decode_tile_info(p, (int)s_first - sp.n_scan, TT, false);
-        s_info[1] = decode_tile_info(p, base, TT, false);
-        pending = base + 1;
-        if (s_info[0].b >= 0) issue_pre(0, s_info[0]);
-        if (s_info[1].b >= 0) issue_pre(1, s_info[1]);
+        pending = (int)s_first - sp.n_scan;
+        for (int q = 0; q < NPRE - 1; ++q) {
+            s_info[q] = next_tile_info(p, s_info, q, pending, TT, false);
+            if (s_info[q].b >= 0) issue_pre(q, s_info[q]);
+        }
     }
     __syncthreads();
 
     const int nrt = (sp.L + TSP - 1) / TSP;   // saved run states per sequence
     uint32_t mphase = 0, pphase = 0;          // mbarrier parities per main stage / prepass slot
-    f2 cq0P = f2_bcast(1.f), cq0S = f2_bcast(0.f), cq1P = cq0P, cq1S = cq0S;      // run coefficients of the next two main tiles
+    f2 cqP[PD - 1], cqS[PD - 1];          // run coefficients of the next PD - 1 main tiles
+#pragma unroll
+    for (int q = 0; q < PD - 1; ++q) { cqP[q] = f2_bcast(1.f); cqS[q] = f2_bcast(0.f); }
     int ps = 0;                               // prepass slot of position i + PD
 
+#ifdef AB_SCAN_TRACE
+    __shared__ int s_pt_cta;
+    if (tid == 0) s_pt_cta = (int)atomicAdd(&g_pipe_trace_cta, 1u);
+    __syncthreads();
+    const int pt_cta = s_pt_cta;
+#endif
     for (int i = -PD;; ++i) {
         const TileInfo mi = s_info[(i < 0 ? 0 : i) & (INFO_RING - 1)];
         if (mi.b < 0) break;                  // positions are handed out in increasing order: nothing left for this CTA
+        PT_MARK(0);
         const TileInfo pi = s_info[(i + PD) & (INFO_RING - 1)];
         if (tid == 0) {
-            s_info[(i + LA) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, false);
-            if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - sp.n_scan;
+            s_info[(i + LA) & (INFO_RING - 1)] = next_tile_info(p, s_info, i + LA, pending, TT, false);
         }
+        // per-channel parameters of both tiles: requested here, consumed behind the waits (their latency stays hidden)
+        float2 m_al = make_float2(0.f, 0.f), m_dv = m_al, p_al = m_al;
+        if (i >= 0) {
+            m_al = __ldg(reinterpret_cast<const float2*>(sp.A_log + mi.c0 + cl));
+            m_dv = __ldg(reinterpret_cast<const float2*>(sp.Dp + mi.c0 + cl));
+        }
+        if (pi.b >= 0) p_al = __ldg(reinterpret_cast<const float2*>(sp.A_log + pi.c0 + cl));
         // ---- main pass of tile i: the state entering it was requested PD iterations ago
         if (i >= 0) {
             const int s = i & 1;
-            unsigned long long w0, w1;
-            const unsigned long long* wp = sp.inclw + (size_t)mi.tile_lin * Cs + cl;
-            ld_relaxed_v2(wp, w0, w1);
-            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + mi.c0 + cl));
-            const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + mi.c0 + cl));
-            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E), Dv = f2_pack(dv2.x, dv2.y);
+            const bool first = (mi.tile_lin & (SG - 1)) == 0;          // first tile of a super-tile: state from the scanner
+            unsigned long long w0 = 0, w1 = 0;
+            const unsigned long long* wp = sp.inclw + (size_t)(mi.tile_lin >> LOG_SG) * Cs + cl;
+            if (first) ld_relaxed_v2(wp, w0, w1);
             const unsigned char* st = smem + (size_t)s * lay.main_stride;
             const T* sB = reinterpret_cast<const T*>(st) + cl;
             const T* sX = reinterpret_cast<const T*>(st + lay.pitch) + cl;
             const T* sC = reinterpret_cast<const T*>(st + 2 * lay.pitch) + cl;
             const T* sZ = reinterpret_cast<const T*>(st + 3 * lay.pitch) + cl;
             const float* sd = reinterpret_cast<const float*>(st + 4 * lay.pitch) + hh;
-            int spins = 0;
-            while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
-                if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
-                __nanosleep(p.poll_ns);
-                ld_relaxed_v2(wp, w0, w1);
+            f2 hin;
+            if (first) {
+                int spins = 0;
+                while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
+                    if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
+                    __nanosleep(p.poll_ns);
+                    ld_relaxed_v2(wp, w0, w1);
+                }
+                hin = f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1));
+            } else {
+                hin = *reinterpret_cast<const f2*>(carry + ((i - 1) & 1) * Cs + cl);       // left by the previous tile's last run
             }
-            f2 h = f2_fma(cq0P, f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1)), cq0S);
+            PT_MARK(1);
+            f2 h = f2_fma(cqP[0], hin, cqS[0]);
             const int row = mi.row0 + run * TSP;
             const int rg = mi.row0 / TSP + run;
             if (act && rg < nrt) *reinterpret_cast<f2*>(p.hrun + (size_t)mi.b * p.batch_stride + (size_t)rg * sp.Di + mi.c0 + cl) = h;
             T* yo = reinterpret_cast<T*>(sp.y) + ((size_t)mi.b * sp.L + row) * sp.Di + mi.c0 + cl;
             ab_mbar_wait(&mbar[s], (mphase >> s) & 1u);
             mphase ^= 1u << s;
+            PT_MARK(2);
+            asm volatile("" : "+f"(m_al.x), "+f"(m_al.y), "+f"(m_dv.x), "+f"(m_dv.y));
+            const f2 A2 = f2_pack(-__expf(m_al.x) * AB_LOG2E, -__expf(m_al.y) * AB_LOG2E), Dv = f2_pack(m_dv.x, m_dv.y);
 #pragma unroll
             for (int t = 0; t < TSP; ++t) {
                 const int r = run * TSP + t;
@@ -339,16 +416,19 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
                 const f2 o = f2_mul(f2_fma(Dv, xv, f2_mul(cv, h)), f2_mul(zv, f2_sigmoid<T>(zv)));
                 if (act && row + t < sp.L) stg_pair<T>(yo + (size_t)t * sp.Di, o);
             }
+            if (run == NR - 1 && act) *reinterpret_cast<f2*>(carry + (i & 1) * Cs + cl) = h;
         }
+        PT_MARK(3);
         // ---- prepass of tile i + PD: run aggregates from Bm and delta only
         if (pi.b >= 0) {
-            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + pi.c0 + cl));
-            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E);
             const unsigned char* st = smem + lay.off_pre + (size_t)ps * lay.pre_stride;
             const T* sB = reinterpret_cast<const T*>(st) + cl;
             const float* sd = reinterpret_cast<const float*>(st + lay.pitch) + hh;
             ab_mbar_wait(&pbar[ps], (pphase >> ps) & 1u);
             pphase ^= 1u << ps;
+            PT_MARK(4);
+            asm volatile("" : "+f"(p_al.x), "+f"(p_al.y));
+            const f2 A2 = f2_pack(-__expf(p_al.x) * AB_LOG2E, -__expf(p_al.y) * AB_LOG2E);
             f2 S = f2_bcast(0.f), P = f2_bcast(1.f);
 #pragma unroll
             for (int t = 0; t < TSP; ++t) {
@@ -363,7 +443,9 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
                 *reinterpret_cast<f2*>(runS + bi) = S;
             }
         }
+        PT_MARK(5);
         __syncthreads();
+        PT_MARK(6);
 
         // ---- refill: the main stage tile i leaves goes to tile i + 2, the free prepass slot to tile i + PD + 2
         if (tid == 0) {
@@ -372,20 +454,22 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
                 if (nm.b >= 0) issue_main(i & 1, nm);
             }
             const TileInfo np = s_info[(i + LA) & (INFO_RING - 1)];
-            if (np.b >= 0) issue_pre((ps + 2) % NPRE, np);
+            if (np.b >= 0) issue_pre((ps + NPRE - 1) % NPRE, np);
         }
         // ---- duty warp of this column: run prefixes in place, tile aggregate -> scanner
         if (pi.b >= 0 && run == (i + PD) % NR && act)
-            compose_and_publish<NR, false>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs,
-                                           sp.words + ((size_t)pi.tile_lin * Cs + cl) * 2, epoch);
-        // ---- run coefficients of tile i + 2 (composed during the previous iteration)
-        cq0P = cq1P; cq0S = cq1S;
-        if (i + 2 >= 0) {
-            const int bi = (((i + 2) & 1) * NR + run) * Cs + cl;
-            cq1P = *reinterpret_cast<const f2*>(runP + bi);
-            cq1S = *reinterpret_cast<const f2*>(runS + bi);
+            compose_and_publish<NR, false>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs, accb + cl,
+                                           pi.tile_lin & (SG - 1), sp.words + ((size_t)(pi.tile_lin >> LOG_SG) * Cs + cl) * 2, epoch);
+        // ---- run coefficients of tile i + PD - 1 (composed during the previous iteration)
+#pragma unroll
+        for (int q = 0; q + 1 < PD - 1; ++q) { cqP[q] = cqP[q + 1]; cqS[q] = cqS[q + 1]; }
+        if (i + PD - 1 >= 0) {
+            const int bi = (((i + PD - 1) & 1) * NR + run) * Cs + cl;
+            cqP[PD - 2] = *reinterpret_cast<const f2*>(runP + bi);
+            cqS[PD - 2] = *reinterpret_cast<const f2*>(runS + bi);
         }
         ps = ps + 1 == NPRE ? 0 : ps + 1;
+        PT_MARK(7);
     }
     cta_finish(p.sync);
 }
@@ -408,6 +492,8 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     const uint32_t tile_bytes = (uint32_t)TT * Cs * sizeof(T), dbytes = (uint32_t)(TT + 1) * nhp * 4u;
     float* runP = reinterpret_cast<float*>(smem + lay.off_runP);
     float* runS = reinterpret_cast<float*>(smem + lay.off_runS);
+    float* carry = reinterpret_cast<float*>(smem + lay.off_carry);
+    float* accb = reinterpret_cast<float*>(smem + lay.off_acc);
     float* partA = reinterpret_cast<float*>(smem + lay.off_partA);
     float* partD = reinterpret_cast<float*>(smem + lay.off_partD);
     TileInfo* s_info = reinterpret_cast<TileInfo*>(smem + lay.off_info);
@@ -433,8 +519,8 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     const uint32_t epoch = s_epoch;
     if ((int)s_first < sp.n_scan) {
         float* hs = partD + 2 * NR * Cs - Cs;
-        scanner_role<-1>(sp, epoch, p.scan_k, p.scan_r, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
-        scanner_finish(p.sync, &s_left);
+        const int np = scanner_role<-1>(sp, epoch, p.scan_k, p.scan_r, (int)s_first, hs, reinterpret_cast<uint4*>(smem), (size_t)(reinterpret_cast<unsigned char*>(hs) - smem));
+        if (np) scanner_finish(p.sync, &s_left, np);
         return;
     }
 
@@ -459,18 +545,19 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
 
     int pending = -1;
     if (tid == 0) {
-        const int base = (int)atomicAdd(p.sync, 2u) - sp.n_scan;
-        s_info[0] = decode_tile_info(p, (int)s_first - sp.n_scan, TT, true);
-        s_info[1] = decode_tile_info(p, base, TT, true);
-        pending = base + 1;
-        if (s_info[0].b >= 0) issue_pre(0, s_info[0]);
-        if (s_info[1].b >= 0) issue_pre(1, s_info[1]);
+        pending = (int)s_first - sp.n_scan;
+        for (int q = 0; q < NPRE - 1; ++q) {
+            s_info[q] = next_tile_info(p, s_info, q, pending, TT, true);
+            if (s_info[q].b >= 0) issue_pre(q, s_info[q]);
+        }
     }
     __syncthreads();
 
     const int nrt = (sp.L + TSP - 1) / TSP;
     uint32_t mphase = 0, pphase = 0;
-    f2 cq0P = f2_bcast(1.f), cq0S = f2_bcast(0.f), cq1P = cq0P, cq1S = cq0S;
+    f2 cqP[PD - 1], cqS[PD - 1];
+#pragma unroll
+    for (int q = 0; q < PD - 1; ++q) { cqP[q] = f2_bcast(1.f); cqS[q] = f2_bcast(0.f); }
     int ps = 0;
     const float inv_log2e = 1.f / AB_LOG2E;
 
@@ -493,21 +580,25 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
         if (mi.b < 0) break;
         const TileInfo pi = s_info[(i + PD) & (INFO_RING - 1)];
         if (tid == 0) {
-            s_info[(i + LA) & (INFO_RING - 1)] = decode_tile_info(p, pending, TT, true);
-            if (pending < p.ntiles) pending = (int)atomicAdd(p.sync, 1u) - sp.n_scan;
+            s_info[(i + LA) & (INFO_RING - 1)] = next_tile_info(p, s_info, i + LA, pending, TT, true);
         }
+        float2 m_al = make_float2(0.f, 0.f), m_dv = m_al, p_al = m_al, m_h = m_al;
+        if (i >= 0) {
+            const int cg0 = mi.c0 + cl;
+            m_al = __ldg(reinterpret_cast<const float2*>(sp.A_log + cg0));
+            m_dv = __ldg(reinterpret_cast<const float2*>(sp.Dp + cg0));
+            const int rg = mi.row0 / TSP + run;
+            if (rg < nrt) m_h = __ldg(reinterpret_cast<const float2*>(p.hrun + (size_t)mi.b * p.batch_stride + (size_t)rg * sp.Di + cg0));
+        }
+        if (pi.b >= 0) p_al = __ldg(reinterpret_cast<const float2*>(sp.A_log + pi.c0 + cl));
         // ---- main pass of tile i: forward recompute from the saved run state, then the reverse sweep
         if (i >= 0) {
             const int s = i & 1;
-            unsigned long long w0, w1;
-            const unsigned long long* wp = sp.inclw + (size_t)mi.tile_lin * Cs + cl;
-            ld_relaxed_v2(wp, w0, w1);
+            const bool first = (mi.tile_lin & (SG - 1)) == 0;
+            unsigned long long w0 = 0, w1 = 0;
+            const unsigned long long* wp = sp.inclw + (size_t)(mi.tile_lin >> LOG_SG) * Cs + cl;
+            if (first) ld_relaxed_v2(wp, w0, w1);
             const int cg0 = mi.c0 + cl;
-            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + cg0));
-            const float2 dv2 = __ldg(reinterpret_cast<const float2*>(sp.Dp + cg0));
-            const int rg = mi.row0 / TSP + run;
-            f2 h = rg < nrt ? *reinterpret_cast<const f2*>(p.hrun + (size_t)mi.b * p.batch_stride + (size_t)rg * sp.Di + cg0) : f2_bcast(0.f);
-            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E), Dv = f2_pack(dv2.x, dv2.y);
             const unsigned char* st = smem + (size_t)s * lay.main_stride;
             const T* sB = reinterpret_cast<const T*>(st) + cl;
             const T* sX = reinterpret_cast<const T*>(st + lay.pitch) + cl;
@@ -523,6 +614,9 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
             T* db_o = reinterpret_cast<T*>(sp.dBm) + tok0 * sp.dbc_stride + cg0;
             ab_mbar_wait(&mbar[s], (mphase >> s) & 1u);
             mphase ^= 1u << s;
+            asm volatile("" : "+f"(m_al.x), "+f"(m_al.y), "+f"(m_dv.x), "+f"(m_dv.y), "+f"(m_h.x), "+f"(m_h.y));
+            const f2 A2 = f2_pack(-__expf(m_al.x) * AB_LOG2E, -__expf(m_al.y) * AB_LOG2E), Dv = f2_pack(m_dv.x, m_dv.y);
+            f2 h = f2_pack(m_h.x, m_h.y);
             f2 a[TSP], g[TSP], hp[TSP];
             float dl[TSP];
             f2 accD = f2_bcast(0.f);
@@ -551,13 +645,19 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
             }
             const f2 anext = f2_ex2(f2_mul(A2, f2_bcast(sd[(run * TSP + TSP) * nhp])));
             // G entering this run from the later ones
-            int spins = 0;
-            while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
-                if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
-                __nanosleep(p.poll_ns);
-                ld_relaxed_v2(wp, w0, w1);
+            f2 Gin;
+            if (first) {
+                int spins = 0;
+                while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
+                    if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
+                    __nanosleep(p.poll_ns);
+                    ld_relaxed_v2(wp, w0, w1);
+                }
+                Gin = f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1));
+            } else {
+                Gin = *reinterpret_cast<const f2*>(carry + ((i - 1) & 1) * Cs + cl);       // G at the first token of the previous (later) tile
             }
-            const f2 Gn = f2_fma(cq0P, f2_pack(__uint_as_float((uint32_t)w0), __uint_as_float((uint32_t)w1)), cq0S);
+            const f2 Gn = f2_fma(cqP[0], Gin, cqS[0]);
             f2 q = f2_mul(anext, Gn);
             f2 accA = f2_bcast(0.f);
             float dd[TSP];
@@ -571,6 +671,7 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
                 dd[t] = e0 + e1;
                 accA = f2_fma(e, f2_bcast(dl[t]), accA);
                 q = f2_mul(a[t], Gt);
+                if (t == 0 && run == 0 && act) *reinterpret_cast<f2*>(carry + (i & 1) * Cs + cl) = Gt;
             }
             // d delta of a head = sum over its 16 channels = 8 lanes: transposing butterfly, one token per lane pair
             {
@@ -597,8 +698,6 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
         }
         // ---- prepass of tile i + PD: g = d(y_ssm) * C and the reverse run aggregates
         if (pi.b >= 0) {
-            const float2 al2 = __ldg(reinterpret_cast<const float2*>(sp.A_log + pi.c0 + cl));
-            const f2 A2 = f2_pack(-__expf(al2.x) * AB_LOG2E, -__expf(al2.y) * AB_LOG2E);
             const unsigned char* st = smem + lay.off_pre + (size_t)ps * lay.pre_stride;
             const T* sC = reinterpret_cast<const T*>(st) + cl;
             const T* sZ = reinterpret_cast<const T*>(st + lay.pitch) + cl;
@@ -606,6 +705,8 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
             const float* sd = reinterpret_cast<const float*>(st + 3 * lay.pitch) + hh;
             ab_mbar_wait(&pbar[ps], (pphase >> ps) & 1u);
             pphase ^= 1u << ps;
+            asm volatile("" : "+f"(p_al.x), "+f"(p_al.y));
+            const f2 A2 = f2_pack(-__expf(p_al.x) * AB_LOG2E, -__expf(p_al.y) * AB_LOG2E);
             // reverse:  G(first token of the run) = Gs + Pr * G(first token of the next run)
             f2 Gs = f2_bcast(0.f), Pr = f2_bcast(1.f);
             f2 an = f2_ex2(f2_mul(A2, f2_bcast(sd[(run * TSP + TSP) * nhp])));
@@ -633,19 +734,20 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
                 if (nm.b >= 0) issue_main(i & 1, nm);
             }
             const TileInfo np = s_info[(i + LA) & (INFO_RING - 1)];
-            if (np.b >= 0) issue_pre((ps + 2) % NPRE, np);
+            if (np.b >= 0) issue_pre((ps + NPRE - 1) % NPRE, np);
         }
         if (run == (i + PD) % NR && act) {
             if (pi.b >= 0)
-                compose_and_publish<NR, true>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs,
-                                              sp.words + ((size_t)pi.tile_lin * Cs + cl) * 2, epoch);
+                compose_and_publish<NR, true>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs, accb + cl,
+                                              pi.tile_lin & (SG - 1), sp.words + ((size_t)(pi.tile_lin >> LOG_SG) * Cs + cl) * 2, epoch);
             if (i >= 0) reduce_parts(mi.tile_lin, i & 1);
         }
-        cq0P = cq1P; cq0S = cq1S;
-        if (i + 2 >= 0) {
-            const int bi = (((i + 2) & 1) * NR + run) * Cs + cl;
-            cq1P = *reinterpret_cast<const f2*>(runP + bi);
-            cq1S = *reinterpret_cast<const f2*>(runS + bi);
+#pragma unroll
+        for (int q = 0; q + 1 < PD - 1; ++q) { cqP[q] = cqP[q + 1]; cqS[q] = cqS[q + 1]; }
+        if (i + PD - 1 >= 0) {
+            const int bi = (((i + PD - 1) & 1) * NR + run) * Cs + cl;
+            cqP[PD - 2] = *reinterpret_cast<const f2*>(runP + bi);
+            cqS[PD - 2] = *reinterpret_cast<const f2*>(runS + bi);
         }
         ps = ps + 1 == NPRE ? 0 : ps + 1;
     }
@@ -659,7 +761,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct PipeTiling { int Cs, NWC, NR, TT, nslab, nchunks, esize; };
+struct PipeTiling { int Cs, NWC, NR, TT, nslab, nchunks, nsuper, esize; };
 
 int pipe_env(const char* name, int dflt, int alt, int alt2 = -1) {
     const char* e = getenv(name);
@@ -683,10 +785,14 @@ bool pipe_tiling(int L, int Di, int dtype, bool bwd, PipeTiling& t) {
     if (Cs * 2 < t.NWC * 64) return false;                      // more than half of the lanes would idle
     static const int nr_bf16[5] = {0, 16, 8, 5, 4}, nr_f32[5] = {0, 8, 4, 3, 2};
     t.NR = dtype == AB_F32 ? nr_f32[t.NWC] : nr_bf16[t.NWC];
-    (void)bwd;
+    if (dtype == AB_BF16 && t.NWC == 1) {           // tuning knob: 8 runs = 256-thread CTAs, twice as many per SM
+        static const int nf = pipe_env("APERTIS_B200_SCAN_NR_FWD", 16, 8), nb = pipe_env("APERTIS_B200_SCAN_NR_BWD", 16, 8);
+        t.NR = bwd ? nb : nf;
+    }
     t.TT = t.NR * TSP;
     t.nslab = Di / Cs;
     t.nchunks = (int)ab_ceil_div(L, t.TT);
+    t.nsuper = (int)ab_ceil_div(t.nchunks, SG);          // the scanner's units; tiles are padded to nsuper * SG per chain
     return true;
 }
 
@@ -724,7 +830,7 @@ struct PipeWs { size_t off_sync, off_err, off_words, off_incl, off_part, total; 
 PipeWs pipe_ws(const PipeTiling& tf, const PipeTiling& tb, int B) {
     PipeWs w;
     const PipeTiling& t = tf;
-    const size_t ntiles = (size_t)B * t.nslab * (tf.nchunks > tb.nchunks ? tf.nchunks : tb.nchunks);
+    const size_t ntiles = (size_t)B * t.nslab * (tf.nsuper > tb.nsuper ? tf.nsuper : tb.nsuper) * SG;
     size_t o = 0;
     w.off_sync = o; o += 64;
     w.off_err = o; o += 64;
@@ -807,7 +913,7 @@ int launch_pipe(bool bwd, const CUtensorMap* maps, const PipeParams& p, const Pi
 }
 int dispatch_pipe(bool bwd, int dtype, const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
     if (dtype == AB_BF16) switch (t.NWC) {
-        case 1: return launch_pipe<__nv_bfloat16, 1, 16>(bwd, maps, p, t, st);
+        case 1: return t.NR == 8 ? launch_pipe<__nv_bfloat16, 1, 8>(bwd, maps, p, t, st) : launch_pipe<__nv_bfloat16, 1, 16>(bwd, maps, p, t, st);
         case 2: return launch_pipe<__nv_bfloat16, 2, 8>(bwd, maps, p, t, st);
         case 3: return launch_pipe<__nv_bfloat16, 3, 5>(bwd, maps, p, t, st);
         default: return launch_pipe<__nv_bfloat16, 4, 4>(bwd, maps, p, t, st);
@@ -824,7 +930,7 @@ void fill_common(PipeParams& p, const PipeTiling& t, const PipeWs& wl, void* ws,
     memset(&p, 0, sizeof(p));
     ScanParams& s = p.s;
     s.B = B; s.L = L; s.Di = Di; s.H = H;
-    s.Cs = t.Cs; s.T = t.TT; s.n_s = t.NR; s.nslab = t.nslab; s.nchunks = t.nchunks; s.nchains = B * t.nslab;
+    s.Cs = t.Cs; s.T = t.TT; s.n_s = t.NR; s.nslab = t.nslab; s.nchunks = t.nsuper; s.nchains = B * t.nslab;
     unsigned char* w8 = (unsigned char*)ws;
     p.sync = (unsigned int*)(w8 + wl.off_sync);
     s.ticket = p.sync;
@@ -833,12 +939,12 @@ void fill_common(PipeParams& p, const PipeTiling& t, const PipeWs& wl, void* ws,
     s.inclw = (unsigned long long*)(w8 + wl.off_incl);
     s.part = (float*)(w8 + wl.off_part);
     s.n_scan = s.nchains;
-    p.ntiles = s.nchains * t.nchunks;
+    p.ntiles = s.nchains * t.nsuper;          // tickets = super-tiles
     static const char* ke = getenv("APERTIS_B200_SCAN_K");
     static const char* re = getenv("APERTIS_B200_SCAN_R");
     p.scan_k = ke ? atoi(ke) : PIPE_SCAN_K;
     if (p.scan_k != 16 && p.scan_k != 32 && p.scan_k != 64 && p.scan_k != 128) p.scan_k = PIPE_SCAN_K;
-    p.scan_r = re && atoi(re) == 4 ? 4 : 8;
+    p.scan_r = re && atoi(re) == 8 ? 8 : 4;
     static const char* pe = getenv("APERTIS_B200_SCAN_POLL_NS");
     p.poll_ns = pe ? (unsigned)atoi(pe) : 100u;
 }
@@ -847,11 +953,12 @@ void fill_common(PipeParams& p, const PipeTiling& t, const PipeWs& wl, void* ws,
 
 // entry points used by ssm_scan.cu
 bool ab_scan_pipe_plan(int B, int L, int Di, int dtype, int* tile_rows, int* slab, int* n_states, size_t* ws_bytes,
-                       int* bwd_tile_rows) {
+                       int* bwd_tile_rows, int* bwd_tiles_per_chain) {
     PipeTiling tf, tb;
     if (!pipe_supported(B, L, Di, dtype, tf, tb)) return false;
     if (tile_rows) *tile_rows = tf.TT;
     if (bwd_tile_rows) *bwd_tile_rows = tb.TT;
+    if (bwd_tiles_per_chain) *bwd_tiles_per_chain = tb.nsuper * SG;
     if (slab) *slab = tf.Cs;
     if (n_states) *n_states = pipe_saved(L, Di).n_rows;          // rows of Di floats per batch: run states, then delta
     if (ws_bytes) *ws_bytes = pipe_ws(tf, tb, B).total;
@@ -919,3 +1026,15 @@ int ab_scan_pipe_bwd(const void* xa, const void* dlog, const void* Bm, const voi
     *part_out = p.s.part;
     return dispatch_pipe(true, dtype, maps, p, t, stream);
 }
+
+#ifdef AB_SCAN_TRACE
+extern "C" int ab_pipe_trace_dump(unsigned long long* host, int clear) {
+    cudaDeviceSynchronize();
+    int rc = (int)cudaMemcpyFromSymbol(host, g_pipe_trace, sizeof(unsigned long long) * PT_CTAS * PT_ITERS * PT_WARPS * PT_SLOTS);
+    if (clear) {
+        void* d; cudaGetSymbolAddress(&d, g_pipe_trace); cudaMemset(d, 0, sizeof(unsigned long long) * PT_CTAS * PT_ITERS * PT_WARPS * PT_SLOTS);
+        cudaGetSymbolAddress(&d, g_pipe_trace_cta); cudaMemset(d, 0, 4);
+    }
+    return rc;
+}
+#endif

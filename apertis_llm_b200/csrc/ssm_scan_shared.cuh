@@ -89,7 +89,7 @@ __device__ __forceinline__ float wait_incoming(const ScanParams& p, uint32_t epo
 // segment again to publish the per-tile states: loads, FMA chains and stores of a round are spread over R warps sets.
 // The composition order is fixed by the tile order, so results are bitwise reproducible.
 template <int DIR>
-__device__ __forceinline__ void scanner_role(const ScanParams& p, uint32_t epoch, int kmax, int rmax, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem below hs*/, size_t ring_bytes) {
+__device__ __forceinline__ int scanner_role(const ScanParams& p, uint32_t epoch, int kmax, int rmax, int chain, float* hs /*smem [Cs]*/, uint4* ring /*smem below hs*/, size_t ring_bytes) {
     const int n = p.nchunks, Cs = p.Cs;
     const int slab = chain % p.nslab, b = chain / p.nslab;
     int spins = 0;
@@ -104,7 +104,8 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, uint32_t epoch
         float* segS = segP + 8 * Cs;
         int* segN = reinterpret_cast<int*>(segS + 8 * Cs);
         const int c = threadIdx.x % Cs, r = threadIdx.x / Cs;
-        const bool active = r < R;
+        if (r >= R) return 0;                          // surplus warps leave: they would only take issue slots and barrier time
+        const bool active = true;
         const int cg = slab * Cs + c;
         float h = (DIR > 0 && p.h0) ? p.h0[(size_t)b * p.Di + cg] : 0.f;
         uint4* myring = ring + c;
@@ -199,11 +200,14 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, uint32_t epoch
             }
             ++round;
 #endif
-            if (adv == 0 && ++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+            if (adv == 0) {
+                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+                __nanosleep(100);   // nothing new yet: leave the issue slots to the CTA that shares this SM
+            }
             __syncthreads();        // ring slots and segment words are rewritten next round
         }
         if (DIR > 0 && p.h_last && r == 0) p.h_last[(size_t)b * p.Di + cg] = h;
-        return;
+        return R * Cs;
     }
     const int c = threadIdx.x;
     // generic path (blocks narrower than the slab: tiny sequences): state in shared memory, no prefetch
@@ -227,6 +231,7 @@ __device__ __forceinline__ void scanner_role(const ScanParams& p, uint32_t epoch
     }
     if (DIR > 0 && p.h_last)
         for (int cc = c; cc < Cs; cc += blockDim.x) p.h_last[(size_t)b * p.Di + slab * Cs + cc] = hs[cc];
+    return (int)blockDim.x;
 }
 
 // softplus'd delta rows of this tile (plus one extra row for the reverse scan) into shared memory

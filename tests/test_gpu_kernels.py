@@ -122,6 +122,33 @@ def test_selective_scan_modes_agree_and_deterministic():
     assert rel_err(o32[0], o32[2]) < 1e-5 and rel_err(o32[0], o32[4]) < 1e-5
 
 
+@pytest.mark.parametrize("B,L,H", [(1, 50000, 32), (2, 9000, 16), (8, 4096, 12)])
+def test_selective_scan_pipelined_long(B, L, H):
+    """Steady state of the pipelined schedule (many super-tiles per CTA, ticket recycling, repeated launches on one
+    workspace) against the two-pass schedule: outputs and every gradient, twice in a row, bitwise repeatable."""
+    from apertis_llm_b200 import _lib, ops
+    Di = 16 * H
+    g = torch.Generator().manual_seed(L)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev(), torch.bfloat16)
+    xa, z, BC = mk(B, L, Di), mk(B, L, Di), mk(B, L, 2 * Di) * 0.5
+    dlog = (torch.randn(B, L, H, generator=g) - 3).to(dev(), torch.bfloat16)
+    A_log = (torch.rand(H, 16, generator=g) * 0.6 - 0.7).to(dev())
+    D = (1.0 + 0.1 * torch.randn(Di, generator=g)).to(dev())
+    dy = mk(B, L, Di)
+    res = {}
+    for mode in (_lib.SCAN_TWO_PASS, _lib.SCAN_PIPELINED, _lib.SCAN_PIPELINED):
+        leaves = [t.detach().clone().requires_grad_(True) for t in (xa, dlog, BC, z, A_log, D)]
+        y, _, hl = ops.selective_scan(*leaves, want_hlast=True, mode=mode)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        res.setdefault(mode, []).append([y.detach().float(), hl] + [t.grad.float() for t in leaves])
+    ref, (p1, p2) = res[_lib.SCAN_TWO_PASS][0], res[_lib.SCAN_PIPELINED]
+    names = ["y", "h_last", "dxa", "ddlog", "dBC", "dz", "dA_log", "dD"]
+    for n, a, b, c in zip(names, ref, p1, p2):
+        assert torch.equal(b, c), f"{n}: pipelined scan is not bitwise repeatable"
+        assert rel_err(b, a) < (2e-3 if n in ("dA_log", "dD", "h_last") else 1.6e-2), n
+
+
 # ------------------------------------------------------------------------------------------------
 # router, top-k, plan
 # ------------------------------------------------------------------------------------------------
