@@ -93,6 +93,18 @@ __device__ __forceinline__ void st_relaxed_v2(unsigned long long* p, unsigned lo
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 
+// L2 residency control.  The prepass reads a tile's operands PD tiles before the main pass reads them again: those loads
+// ask L2 to keep the lines (evict_last) and everything that is touched once (the main pass's loads, the outputs) asks to
+// be evicted first, so that the second read is served by L2 instead of DRAM.
+__device__ __forceinline__ uint64_t l2_policy_keep() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_stream() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(ab_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ab_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+
 struct __align__(16) TileInfo { int b, c0, row0, tile_lin; };      // b < 0: no tile; tile_lin = super-tile * SG + position inside it
 
 #ifndef PIPE_PD
@@ -318,17 +330,19 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     auto issue_main = [&](int s, const TileInfo& ti) {         // thread 0 only
         ab_mbar_expect_tx(&mbar[s], 4u * tile_bytes + dbytes);
         unsigned char* dst = smem + (size_t)s * lay.main_stride;
-        ab_tma_load_3d(dst, &tm_b, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 4 * lay.pitch, &tm_d, &mbar[s], ti.c0 >> 4, ti.row0, ti.b);
+        const uint64_t pol = l2_policy_stream();                // last use of every line
+        tma_load_3d_hint(dst, &tm_b, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + lay.pitch, &tm_xa, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 2 * lay.pitch, &tm_c, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 3 * lay.pitch, &tm_z, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 4 * lay.pitch, &tm_d, &mbar[s], ti.c0 >> 4, ti.row0, ti.b, pol);
     };
     auto issue_pre = [&](int s, const TileInfo& ti) {
         ab_mbar_expect_tx(&pbar[s], tile_bytes + dbytes);
         unsigned char* dst = smem + lay.off_pre + (size_t)s * lay.pre_stride;
-        ab_tma_load_3d(dst, &tm_b, &pbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + lay.pitch, &tm_d, &pbar[s], ti.c0 >> 4, ti.row0, ti.b);
+        const uint64_t pol = l2_policy_keep();                  // read again by the main pass
+        tma_load_3d_hint(dst, &tm_b, &pbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + lay.pitch, &tm_d, &pbar[s], ti.c0 >> 4, ti.row0, ti.b, pol);
     };
 
     // ---- prologue: the first two pipeline positions
@@ -527,20 +541,22 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
     auto issue_main = [&](int s, const TileInfo& ti) {
         ab_mbar_expect_tx(&mbar[s], 5u * tile_bytes + dbytes);
         unsigned char* dst = smem + (size_t)s * lay.main_stride;
-        ab_tma_load_3d(dst, &tm_b, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + lay.pitch, &tm_xa, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_c, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_z, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 4 * lay.pitch, &tm_do, &mbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 5 * lay.pitch, &tm_d, &mbar[s], ti.c0 >> 4, ti.row0, ti.b);
+        const uint64_t pol = l2_policy_stream();
+        tma_load_3d_hint(dst, &tm_b, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + lay.pitch, &tm_xa, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 2 * lay.pitch, &tm_c, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 3 * lay.pitch, &tm_z, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 4 * lay.pitch, &tm_do, &mbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 5 * lay.pitch, &tm_d, &mbar[s], ti.c0 >> 4, ti.row0, ti.b, pol);
     };
     auto issue_pre = [&](int s, const TileInfo& ti) {
         ab_mbar_expect_tx(&pbar[s], 3u * tile_bytes + dbytes);
         unsigned char* dst = smem + lay.off_pre + (size_t)s * lay.pre_stride;
-        ab_tma_load_3d(dst, &tm_c, &pbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + lay.pitch, &tm_z, &pbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 2 * lay.pitch, &tm_do, &pbar[s], ti.c0, ti.row0, ti.b);
-        ab_tma_load_3d(dst + 3 * lay.pitch, &tm_d, &pbar[s], ti.c0 >> 4, ti.row0, ti.b);
+        const uint64_t pol = l2_policy_keep();
+        tma_load_3d_hint(dst, &tm_c, &pbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + lay.pitch, &tm_z, &pbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 2 * lay.pitch, &tm_do, &pbar[s], ti.c0, ti.row0, ti.b, pol);
+        tma_load_3d_hint(dst + 3 * lay.pitch, &tm_d, &pbar[s], ti.c0 >> 4, ti.row0, ti.b, pol);
     };
 
     int pending = -1;

@@ -80,9 +80,11 @@ int ab_causal_conv1d_silu_bwd(const void* xp, int64_t xp_stride, const void* dxa
  *   pass a strictly larger `epoch` (1, 2, 3, ...) than the previous launch on that workspace. */
 #define AB_SCAN_SINGLE_PASS 0
 #define AB_SCAN_TWO_PASS 1
-/* AB_SCAN_PIPELINED: persistent CTAs take tiles from a ticket and software-pipeline them (stage 1 of tile k, then the
- * state-dependent stage 2 of tile k-1 from registers); the forward saves the state entering every run of 4 tokens
- * (n_chunks = that count), the backward returns d dlog final as fp32 [B,L,H].  The launch epoch lives in the workspace
+/* AB_SCAN_PIPELINED: persistent CTAs take super-tiles (4 consecutive tiles of a chain) from a ticket; a prepass running 8
+ * tiles ahead publishes the aggregates, the main pass streams every tile once with its incoming state resolved.  The
+ * forward saves, per batch, the state entering every run of 4 tokens and then delta = softplus(dt) as [L, Hp] rows
+ * (hstart is [B, n_chunks, Di] with n_chunks = ceil(L/4) + ceil(L*Hp/Di), Hp = H rounded up to 4); the backward reads both
+ * and returns d dlog final as fp32 [B,L,H].  The launch epoch lives in the workspace
  * (zero-filled once, one workspace per stream and per mode; the `epoch` argument is ignored), so replayed CUDA graphs
  * are valid.  No y_ssm / dyssm in this mode.  *mode is in/out: a request the schedule does not cover (too many
  * chains for scanner CTAs, odd widths) comes back as another mode together with that mode's sizes. */
