@@ -269,11 +269,14 @@ def test_expert_dropout_train_vs_eval_statistics():
     assert rel_err(a, b) < 1.0
 
 
-def test_cuda_graph_replay_matches_eager():
+@pytest.mark.parametrize("Dm", [128, 256])
+def test_cuda_graph_replay_matches_eager(Dm):
     """The whole step (forward, loss, backward) captured as a CUDA graph and replayed gives the eager results: nothing in
-    the path synchronises with the host or bakes per-launch host state into the graph (the scan switches to its two-pass
-    schedule under capture, which differs from the single pass only in the association of the cross-tile products)."""
-    spec = dict(Dm=128, H=4, I=256, E=4, K=2, B=2, L=640, seed=5)
+    the path synchronises with the host or bakes per-launch host state into the graph.  Dm 128 (d_inner 32): the
+    one-tile-per-CTA scan switches to its two-pass schedule under capture (it differs from the single pass only in the
+    association of the cross-tile products); Dm 256 (d_inner 64): the pipelined scan, whose launch epoch lives in the
+    workspace, is captured as it is."""
+    spec = dict(Dm=Dm, H=4, I=256, E=4, K=2, B=2, L=640, seed=5)
     layer, _ = build_layer(spec)
     x, noise = O.make_inputs(spec["B"], spec["L"], spec["Dm"], spec["E"], seed=spec["seed"])
     layer.train()

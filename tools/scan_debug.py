@@ -35,24 +35,6 @@ for L in [int(s) for s in (sys.argv[1] if len(sys.argv) > 1 else "2500,4096,8192
         t2 = time.time()
         res[mode] = [y.detach().float()] + ([t.grad.float() for t in leaves] if not only_fwd else [])
         print(f"L={L} mode={mode} fwd {1e3 * (t1 - t0):.1f} ms bwd {1e3 * (t2 - t1):.1f} ms", flush=True)
-    for key, ent in ops._scan_ws.items():
-        hdr = ent[0][:128].view(torch.int32)[[0, 1, 2, 16]].tolist()
-        print("   ws", key[2], "sync/err words:", hdr, flush=True)
-        if key[2] and hdr[3]:
-            # protocol error: first tile per chain (in backward scan order) without aggregate / without incoming state
-            TTb, Cs = int(os.environ.get("TTB", "64")), 64
-            nch_b, nch_f = -(-L // TTb), -(-L // 48)
-            ntiles = B * (Di // Cs) * max(nch_b, nch_f)
-            words = ent[0][128:128 + ntiles * Cs * 16].view(torch.int64).view(ntiles, Cs, 2)
-            incl = ent[0][128 + ntiles * Cs * 16:128 + ntiles * Cs * 24].view(torch.int64).view(ntiles, Cs)
-            ep = hdr[2]          # epoch of the last finished launch = stored value (launch used stored + 1 before increment)
-            wv = ((words >> 34) == ep).all(dim=2).all(dim=1).cpu()
-            iv = ((incl >> 34) == ep).all(dim=1).cpu()
-            for chain in range(B * (Di // Cs)):
-                a = wv[chain * nch_b:(chain + 1) * nch_b].flip(0)
-                i = iv[chain * nch_b:(chain + 1) * nch_b].flip(0)
-                print(f"   chain {chain}: aggregates valid {int(a.sum())}/{nch_b}, first missing (scan order) {int((~a).nonzero()[0]) if (~a).any() else -1};"
-                      f" incoming valid {int(i.sum())}/{nch_b}, first missing {int((~i).nonzero()[0]) if (~i).any() else -1}", flush=True)
     names = ["y", "dxa", "ddlog", "dBC", "dz", "dA_log", "dD"]
     for n, a, b in zip(names, res[_lib.SCAN_TWO_PASS], res[_lib.SCAN_PIPELINED]):
         print(f"   {n}: rel {float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)):.2e}", flush=True)
