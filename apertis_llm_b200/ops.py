@@ -22,16 +22,17 @@ from ._lib import AB_BF16, AB_F32, ROW_ALIGN, call, dt, ptr, query, stream_ptr
 # --------------------------------------------------------------------------------------------
 _scan_ws = {}       # (device index, stream, pipelined?) -> [tensor, epoch]
 # APERTIS_B200_SCAN = auto (default) | pipelined | single | two_pass.  auto: the pipelined persistent schedule when the
-# inner width is a multiple of 64 channels (one warp column per slab: its measured win, see
+# inner width is a multiple of 64 channels and the sequence has at least 1024 tokens (one warp column per slab: its measured win, see
 # profiles/r1j_scan_*), the one-tile-per-CTA single pass otherwise.
 _SCAN_ENV = os.environ.get("APERTIS_B200_SCAN", "auto")
 SCAN_MODE = {"two_pass": _lib.SCAN_TWO_PASS, "single": _lib.SCAN_SINGLE_PASS, "pipelined": _lib.SCAN_PIPELINED}.get(_SCAN_ENV)
 
 
-def default_scan_mode(dtype: torch.dtype, Di: int) -> int:
+def default_scan_mode(dtype: torch.dtype, Di: int, L: int = 1 << 20) -> int:
     if SCAN_MODE is not None:
         return SCAN_MODE
-    return _lib.SCAN_PIPELINED if Di % 64 == 0 else _lib.SCAN_SINGLE_PASS
+    # short sequences (cached decode steps, tiny prompts) do not fill a persistent grid: one tile per CTA there
+    return _lib.SCAN_PIPELINED if (Di % 64 == 0 and L >= 1024) else _lib.SCAN_SINGLE_PASS
 
 
 def _scan_workspace(device, nbytes: int, mode: int = _lib.SCAN_SINGLE_PASS):
@@ -251,7 +252,7 @@ def selective_scan(xa, dlog, BC, z, A_log, D, h0=None, want_yssm=False, want_hla
 
     xa, z [B,L,Di]; BC [B,L,2*Di] = [B-term | C-term]; dlog [B,L,H]; A_log [H,16]; D [Di]; h0 [B,H,16] or None.
     Returns (y [B,L,Di], y_ssm | None, h_last [B,Di] fp32 | None)."""
-    mode = default_scan_mode(xa.dtype, xa.shape[-1]) if mode is None else mode
+    mode = default_scan_mode(xa.dtype, xa.shape[-1], xa.shape[1]) if mode is None else mode
     return _SelectiveScan.apply(xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, mode)
 
 

@@ -429,6 +429,11 @@ def main():
     kernels = {"selective_scan_fwd+bwd": {"bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                            "frac": scan_gbs / pk["hbm_gbs"], "ms_per_step_in_kernel": scan_ms,
                                            "algorithmic_bytes_per_step": scan_bytes, "share_of_step": scan_ms / ms}}
+    if world == 1:
+        try:        # the long-context point of the scan sweep, next to the scan inside the block
+            kernels["selective_scan_L64K"] = scan_long_context(pk["hbm_gbs"])
+        except Exception as e:      # never lose the bench line over the extra measurement
+            kernels["selective_scan_L64K"] = {"error": repr(e)[:200]}
     out = {"metric": METRIC, "value": tokens_per_step * world / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -446,6 +451,47 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
     print(json.dumps(out))
     shutdown()
+
+
+
+def scan_long_context(pk_hbm, L=65536, Hh=32, iters=8):
+    """BASELINE.json configs[4] at its longest point (d_model 2048 -> d_inner 512, B 1, L 64K, bf16): one SSM layer's scan
+    forward + backward through the C ABI, CUDA events on the launching stream, L2 flushed between iterations, against the
+    algorithmic bytes of SURVEY.md 8(d).  The event windows also hold the host-side tensor-map encodes (about 20 us)."""
+    import torch
+    from apertis_llm_b200 import _lib, ops
+    d = torch.device("cuda", torch.cuda.current_device())
+    Di = 16 * Hh
+    g = torch.Generator().manual_seed(L)
+    mk = lambda *s: torch.randn(*s, generator=g).to(d, torch.bfloat16)
+    xa, z, BC, dy = mk(1, L, Di), mk(1, L, Di), mk(1, L, 2 * Di), mk(1, L, Di)
+    dlog = (torch.randn(1, L, Hh, generator=g) - 3.0).to(d, torch.bfloat16)
+    A_log = (torch.rand(Hh, 16, generator=g) * 0.68 - 0.69).to(d)
+    D = torch.ones(Di, device=d)
+    leaves = [t.requires_grad_(True) for t in (xa, dlog, BC, z, A_log, D)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=d)
+    names = ["ab_selective_scan_fwd", "ab_selective_scan_bwd"]
+
+    def run():
+        y = ops.selective_scan(*leaves)[0]
+        torch.autograd.grad(y, leaves, dy)
+
+    for _ in range(3):
+        run()
+    tf, tb = [], []
+    for _ in range(iters):
+        flush.zero_()
+        _lib.start_timing(names)
+        run()
+        t = _lib.stop_timing()
+        tf.append(sum(t[names[0]])); tb.append(sum(t[names[1]]))
+    tf.sort(); tb.sort()
+    mf, mb = tf[len(tf) // 2], tb[len(tb) // 2]
+    nbytes = L * (14 * Di + 3 * Hh) * 2
+    gbs = nbytes / ((mf + mb) * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": pk_hbm, "unit": "GB/s", "frac": gbs / pk_hbm, "fwd_us": mf * 1e3, "bwd_us": mb * 1e3,
+            "algorithmic_bytes": nbytes, "workload": "configs[4]: d_model 2048 (d_inner 512, 32 heads), B 1, L 65536, bf16, one layer's scan fwd+bwd",
+            "schedule": {0: "single pass", 1: "two pass", 2: "pipelined persistent"}[ops.default_scan_mode(torch.bfloat16, Di)]}
 
 
 if __name__ == "__main__":
