@@ -300,11 +300,11 @@ class _AttentionWrapper(nn.Module):
         # under autocast the projections consume bf16: emit the normalised rows in that type directly (same rounding
         # point as the reference's fp32 LayerNorm followed by the autocast cast inside nn.Linear)
         ac = _autocast_dtype()
-        normed = ops.layer_norm(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps,
-                                out_dtype=ac if (ac is not None and hidden_s.dtype == torch.float32) else None)
+        normed, skip = ops.layer_norm_skip(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps,
+                                           out_dtype=ac if (ac is not None and hidden_s.dtype == torch.float32) else None)
         out, proxy, cache = self.attention_mechanism_impl(normed, attention_mask=att_mask, position_ids=pos_ids,
                                                           past_key_value=past_kv, output_attentions=output_att, use_cache=use_c)
-        return ops.dropout_add(out, hidden_s, self.output_dropout.p, self.training), proxy, cache
+        return ops.dropout_add(out, skip, self.output_dropout.p, self.training), proxy, cache
 
 
 class _FeedForwardWrapper(nn.Module):
@@ -319,9 +319,9 @@ class _FeedForwardWrapper(nn.Module):
         self.output_dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_s):
-        normed = ops.layer_norm(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
+        normed, skip = ops.layer_norm_skip(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
         out, lb, rz = self.ffn(normed)
-        return ops.dropout_add(out, hidden_s, self.output_dropout.p, self.training), lb, rz
+        return ops.dropout_add(out, skip, self.output_dropout.p, self.training), lb, rz
 
 
 class ApertisLayerB200(nn.Module):

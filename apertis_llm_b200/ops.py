@@ -109,6 +109,44 @@ class _LayerNorm(torch.autograd.Function):
         return dx.view(ctx.shape), dw, db, None, None
 
 
+class _LayerNormSkip(torch.autograd.Function):
+    """LayerNorm that also hands its input on as the residual: x then has ONE consumer in the autograd graph, and the
+    backward adds the residual path's gradient inside the LayerNorm-backward kernel (`dres` of ab_layernorm_bwd) instead of
+    leaving the sum of the two branches to a separate elementwise pass over [tokens, Dm]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        _lib.ensure_device(x.device)
+        shape = x.shape
+        Dm = shape[-1]
+        x2 = x.reshape(-1, Dm).contiguous()
+        S = x2.shape[0]
+        w, b = weight.float().contiguous(), bias.float().contiguous()
+        y = torch.empty(S, Dm, dtype=out_dtype, device=x.device)
+        stats = torch.empty(S, 2, dtype=torch.float32, device=x.device)
+        call("ab_layernorm_fwd", ptr(x2), ptr(w), ptr(b), float(eps), ptr(y), ptr(stats), S, Dm, dt(x2), dt(out_dtype), stream_ptr())
+        ctx.save_for_backward(x2, stats, w)
+        ctx.shape = shape
+        return y.view(shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x2, stats, w = ctx.saved_tensors
+        S, Dm = x2.shape
+        if dy is None:
+            return dskip, None, None, None, None
+        dy2 = dy.reshape(S, Dm).contiguous()
+        dres = dskip.reshape(S, Dm).to(x2.dtype).contiguous() if dskip is not None else None
+        dx = torch.empty_like(x2)
+        dw = torch.empty(Dm, dtype=torch.float32, device=x2.device)
+        db = torch.empty(Dm, dtype=torch.float32, device=x2.device)
+        nws = query("ab_layernorm_bwd_workspace_bytes", S, Dm)
+        ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=x2.device)
+        call("ab_layernorm_bwd", ptr(dy2), ptr(x2), ptr(stats), ptr(w), ptr(dres), ptr(dx), ptr(dw), ptr(db), ptr(ws), ws.numel(), S, Dm,
+             dt(x2), dt(dy2), stream_ptr())
+        return dx.view(ctx.shape), dw, db, None, None
+
+
 class _DropoutAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sub, res, p):
@@ -139,6 +177,12 @@ def dropout_add(sub, res, p: float, training: bool):
 def layer_norm(x, weight, bias, eps, out_dtype=None):
     """nn.LayerNorm over the last dim (core.py:694-695, 887-888) through the sm_100a kernel."""
     return _LayerNorm.apply(x, weight, bias, eps, out_dtype if out_dtype is not None else x.dtype)
+
+
+def layer_norm_skip(x, weight, bias, eps, out_dtype=None):
+    """(LayerNorm(x), x) for the pre-norm residual wrappers: use the second result as the residual operand, so that the
+    two gradients meeting at x are added inside the LayerNorm-backward kernel."""
+    return _LayerNormSkip.apply(x, weight, bias, eps, out_dtype if out_dtype is not None else x.dtype)
 
 
 # --------------------------------------------------------------------------------------------
