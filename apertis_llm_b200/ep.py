@@ -92,8 +92,10 @@ class _MoEExpertsEP(torch.autograd.Function):
         x2 = x2.contiguous()
         f = lambda t: t.float().contiguous()
         rn_w, rn_b, Wr, br, b1, b2, W1, W2 = map(f, (rn_w, rn_b, Wr, br, b1, b2, W1, W2))
-        ln_w_full = all_gather_cat(f(ln_w), group)          # [E, Dm]
-        ln_b_full = all_gather_cat(f(ln_b), group)
+        # every source rank normalises the rows it dispatches: all experts' LayerNorm parameters, one collective for both
+        ln_wb = all_gather_cat(torch.stack([f(ln_w), f(ln_b)]).unsqueeze(0), group)           # [W, 2, El, Dm]
+        ln_w_full = ln_wb[:, 0].reshape(E, Dm).contiguous()   # [E, Dm]
+        ln_b_full = ln_wb[:, 1].reshape(E, Dm).contiguous()
         use_noise = noise is not None and noise_scale is not None
         r = ops.moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
                           f(noise_scale) if use_noise else None, K)
