@@ -110,15 +110,18 @@ struct __align__(16) TileInfo { int b, c0, row0, tile_lin; };      // b < 0: no 
 #ifndef PIPE_PD
 #define PIPE_PD 8
 #endif
+#ifndef PIPE_PD_BWD
+#define PIPE_PD_BWD 8
+#endif
 #ifndef PIPE_LOG_SG
 #define PIPE_LOG_SG 2
 #endif
 #ifndef PIPE_NPRE
 #define PIPE_NPRE 3
 #endif
-constexpr int PD = PIPE_PD;        // the prepass runs PD tiles ahead of the main pass (>= 2)
+constexpr int PD_FWD = PIPE_PD;     // the prepass runs PD tiles ahead of the main pass.  A super-tile's aggregate is published with the
+constexpr int PD_BWD = PIPE_PD_BWD; // prepass of its LAST tile, so PD - (SG - 1) tiles of work hide the scanner's latency: keep PD > SG
 constexpr int NPRE = PIPE_NPRE;    // prepass ring slots: its loads are issued NPRE - 1 tiles ahead of the prepass
-constexpr int LA = PD + NPRE - 1;  // ticket look-ahead
 constexpr int LOG_SG = PIPE_LOG_SG, SG = 1 << LOG_SG;   // consecutive tiles of a chain one CTA takes per ticket (a super-tile):
                                                       // one hand-shake with the scanner per SG tiles
 constexpr int NMAIN = 2;           // main ring stages
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(32 * NWC * NR, (1024 / (32 * NWC * NR) > 0 ? 1
 scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z,
                      const __grid_constant__ CUtensorMap tm_d, const __grid_constant__ PipeParams p) {
-    constexpr int TT = NR * TSP;
+    constexpr int TT = NR * TSP, PD = PD_FWD, LA = PD + NPRE - 1;       // LA: ticket look-ahead
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanParams& sp = p.s;
     const int Cs = CS ? CS : sp.Cs;          // CS != 0: slab width known at compile time
@@ -497,7 +500,7 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
                      const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z,
                      const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_d,
                      const __grid_constant__ PipeParams p) {
-    constexpr int TT = NR * TSP;
+    constexpr int TT = NR * TSP, PD = PD_BWD, LA = PD + NPRE - 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const ScanParams& sp = p.s;
     const int Cs = CS ? CS : sp.Cs;
