@@ -66,6 +66,17 @@ def all_to_all_equal(send: torch.Tensor, group) -> torch.Tensor:
     return recv
 
 
+def all_to_all_equal_start(send: torch.Tensor, group):
+    """Same exchange, started asynchronously on NCCL's stream: returns (recv, wait) and the caller launches independent
+    kernels before calling wait() (other backends: exchanged synchronously, wait is a no-op)."""
+    if dist.get_backend(group) != "nccl":
+        return all_to_all_equal(send, group), (lambda: None)
+    assert send.shape[0] == dist.get_world_size(group) and send.is_contiguous()
+    recv = torch.empty_like(send)
+    work = dist.all_to_all_single(recv.view(-1), send.view(-1), group=group, async_op=True)
+    return recv, work.wait
+
+
 def all_gather_cat(t: torch.Tensor, group) -> torch.Tensor:
     W = dist.get_world_size(group)
     out = torch.empty((W,) + tuple(t.shape), dtype=t.dtype, device=t.device)
@@ -107,22 +118,27 @@ class _MoEExpertsEP(torch.autograd.Function):
         call("ab_moe_permute_ln", ptr(x2), ptr(r["stats"]), ptr(ln_w_full), ptr(ln_b_full), ptr(plan["tok_of_row"]),
              ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(xn), Dm, ROW_ALIGN, rows_local, dt(x2), dt(cdt), stream_ptr())
         # ---- dispatch
-        xr = all_to_all_equal(xn.view(W, El * seg, Dm), group).view(rows_local, Dm)
+        xr_w, xr_wait = all_to_all_equal_start(xn.view(W, El * seg, Dm), group)
+        # while the rows travel: receive-side plan and the bf16 weight shadows
         rplan = dict(tile_expert=recv_tile_expert(W, El, seg, dev),
                      n_rows=torch.full((2,), rows_local, dtype=torch.int32, device=dev),
                      seg_off=local_seg_off(El, seg, dev))
+        w1 = ops._split_cols(W1.view(El * I, Dm), 1) if precise else ops._cast_bf16(W1)
+        w2 = ops._split_cols(W2.view(El * Dm, I), 1) if precise else ops._cast_bf16(W2)
+        xr_wait()
+        xr = xr_w.view(rows_local, Dm)
         if precise:
-            a1, w1, k1 = ops._split_cols(xr, 0), ops._split_cols(W1.view(El * I, Dm), 1), 3 * Dm
+            a1, k1 = ops._split_cols(xr, 0), 3 * Dm
         else:
-            a1, w1, k1 = xr, ops._cast_bf16(W1), Dm
+            a1, k1 = xr, Dm
         drop_p = float(cfg.get("drop_p", 0.0)) if training else 0.0
         drop_seed = torch.randint(0, 2 ** 31 - 1, (2,), device=dev, dtype=torch.int32) if drop_p > 0.0 else None
         h, hpre = ops.grouped_gemm("nt", a1, w1, rplan, I, k1, El, bias=b1, epi=_lib.EPI_BIAS_ACT, act=act, out_dtype=cdt, want_c2=True,
                                    drop_p=drop_p, drop_seed=drop_seed)
         if precise:
-            a2, w2, k2 = ops._split_cols(h, 0), ops._split_cols(W2.view(El * Dm, I), 1), 3 * I
+            a2, k2 = ops._split_cols(h, 0), 3 * I
         else:
-            a2, w2, k2 = h, ops._cast_bf16(W2), I
+            a2, k2 = h, I
         yr = ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
         # ---- combine
         y = all_to_all_equal(yr.view(W, El * seg, Dm), group).view(rows_local, Dm)
@@ -168,17 +184,20 @@ class _MoEExpertsEP(torch.autograd.Function):
             dhpre = ops.grouped_gemm("nn", ops._split_cols(dyr, 0), w2r, rplan, I, 3 * Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             sr = lambda t, which: ops._split_rows(t, which, None, G, seg)
-            dW2 = ops.grouped_gemm_tn(sr(dyr, 0), sr(h, 1), lseg3, Dm, I, El, nsrc=W, src_stride=3 * stride)
-            dW1 = ops.grouped_gemm_tn(sr(dhpre, 0), sr(xr, 1), lseg3, I, Dm, El, nsrc=W, src_stride=3 * stride)
             w1r = ops._split_rows(W1.view(El * I, Dm), 1, None, El, I)
             dxnr = ops.grouped_gemm("nn", ops._split_cols(dhpre, 0), w1r, rplan, Dm, 3 * I, El, out_dtype=torch.float32)
+            # the gradient rows travel back to their source ranks while the weight gradients are computed
+            dxn_w, dxn_wait = all_to_all_equal_start(dxnr.view(W, El * seg, Dm), group)
+            dW2 = ops.grouped_gemm_tn(sr(dyr, 0), sr(h, 1), lseg3, Dm, I, El, nsrc=W, src_stride=3 * stride)
+            dW1 = ops.grouped_gemm_tn(sr(dhpre, 0), sr(xr, 1), lseg3, I, Dm, El, nsrc=W, src_stride=3 * stride)
         else:
             w1b, w2b = ctx.shadows
             dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
+            dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)
+            dxn_w, dxn_wait = all_to_all_equal_start(dxnr.view(W, El * seg, Dm), group)
             dW2 = ops.grouped_gemm_tn(dyr, h, lseg, Dm, I, El, nsrc=W, src_stride=stride)
             dW1 = ops.grouped_gemm_tn(dhpre, xr, lseg, I, Dm, El, nsrc=W, src_stride=stride)
-            dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)
         db2 = torch.empty(El, Dm, **f32)
         db1 = torch.empty(El, I, **f32)
         nws = max(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, rows),
@@ -189,8 +208,9 @@ class _MoEExpertsEP(torch.autograd.Function):
              ROW_ALIGN, rows, dt(dyr), stream_ptr())
         call("ab_moe_segment_colsum", ptr(dhpre), ptr(rplan["tile_expert"]), ptr(rplan["n_rows"]), ptr(db1), ptr(ws), ws.numel(), I, El,
              ROW_ALIGN, rows, dt(dhpre), stream_ptr())
-        # ---- gradient rows back to their source ranks
-        dxn = all_to_all_equal(dxnr.view(W, El * seg, Dm), group).view(rows, Dm)
+        # ---- gradient rows are back on their source ranks
+        dxn_wait()
+        dxn = dxn_w.view(rows, Dm)
         dxrow = torch.empty(rows, Dm, **f32)
         dln_w = torch.empty(E, Dm, **f32)
         dln_b = torch.empty(E, Dm, **f32)
@@ -198,11 +218,9 @@ class _MoEExpertsEP(torch.autograd.Function):
              ptr(plan["n_rows"]), ptr(dxrow), ptr(dln_w), ptr(dln_b), ptr(ws), ws.numel(), Dm, E, ROW_ALIGN, rows, dt(x2), dt(dxn),
              stream_ptr())
         dln = torch.stack([dln_w, dln_b])                      # [2, E, Dm]: sum over source ranks, keep the local experts
-        dist.all_reduce(dln, group=group)
+        dln_work = dist.all_reduce(dln, group=group, async_op=True)        # overlaps the router backward below
         rank = dist.get_rank(group)
         inv = 1.0 / W
-        dln_w_l = dln[0, rank * El:(rank + 1) * El] * inv
-        dln_b_l = dln[1, rank * El:(rank + 1) * El] * inv
         training = cfg["training"]
         g_lb = (dlb.float() * (cfg["lb_coef"] * E / S)) if (training and cfg["lb_coef"] > 0) else torch.zeros((), **f32)
         g_rz = (drz.float() * (cfg["rz_coef"] / S)) if (training and cfg["rz_coef"] > 0) else torch.zeros((), **f32)
@@ -218,6 +236,9 @@ class _MoEExpertsEP(torch.autograd.Function):
              ptr(lse), ptr(lclean), ptr(noise.float().contiguous()) if cfg["use_noise"] else None, ptr(fvec), ptr(scal), ptr(dw_row),
              ptr(dxrow), ptr(plan["row_of"]), ptr(dx), ptr(dWr), ptr(dbr), ptr(drn_w), ptr(drn_b), ptr(dns), ptr(ws2), ws2.numel(),
              S, Dm, E, K, dt(x2), stream_ptr())
+        dln_work.wait()
+        dln_w_l = dln[0, rank * El:(rank + 1) * El] * inv
+        dln_b_l = dln[1, rank * El:(rank + 1) * El] * inv
         return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w_l, dln_b_l, dW1 * inv, db1 * inv, dW2 * inv, db2 * inv, None, None)
 
 
