@@ -1,31 +1,40 @@
 // Pipelined persistent selective scan, forward and backward (sm_100a): AB_SCAN_PIPELINED.
 //
 // Same math and the same scanner hand-shake as ssm_scan.cu (core.py:324-353, :383, :394-396), different schedule.
-// The one-tile-per-CTA kernels spend half of a tile's life waiting for the state that enters it; here a CTA is
-// persistent, takes tiles from an atomic ticket (tile order = scan order, chains interleaved) and software-pipelines
-// them so that the wait of tile k-1 lies behind the whole first stage of tile k:
+// The one-tile-per-CTA kernels spend half of a tile's life waiting for the state that enters it.  Here a CTA is
+// persistent and takes SUPER-TILES (SG = 4 consecutive tiles of one chain) from an atomic ticket, in scan order with
+// the chains interleaved.  Every iteration it runs two passes over two different tiles, one __syncthreads per iteration:
 //
-//   stage 1 (tile k, operands in shared memory, staged by TMA NST tiles ahead):  everything that does not depend on
-//            the state entering the tile.  The recurrence is linear in that state, so the forward evaluates, per
-//            element, y_t = alpha_t * h_in(run) + beta_t with alpha/beta kept in REGISTERS; the backward runs the whole
-//            forward recompute (from the per-run states saved by the forward: no intra-tile dependency), emits
-//            dxa / dC / dz and keeps (abar, g, h_{t-1}) in registers.  The run aggregates go to shared memory.
-//   barrier  (one __syncthreads per tile).  The tile's operand buffers are free from here on: the next TMA load is
-//            issued into them immediately.
-//   duty warp (one per 64-channel column, rotating): composes the run aggregates in run order, leaves the per-run
-//            coefficients in shared memory and publishes the tile aggregate (self-validating 64-bit words).
-//   stage 2 (tile k-1, registers only): collect the incoming state (its word was prefetched before stage 1), apply it,
-//            store.  forward: one FMA per element; backward: the reverse sweep (dB, d dt, dA_log partials).
+//   main pass, tile i:       the state entering the tile is already known - for the first tile of a super-tile it is
+//            the scanner's word (requested at the top of the iteration), for the others the state the previous tile's
+//            last run left in shared memory - so the tile is streamed exactly once.  Forward: h = abar*h + B,
+//            y = (C*h + D*x) * silu(z).  Backward: forward recompute from the run state saved by the forward (dxa, dC,
+//            dz; no intra-tile dependency), then the reverse sweep (dB, d dt, dA_log / dD partials) with (abar, g,
+//            h_{t-1}) of the thread's 4 tokens in registers.
+//   prepass, tile i + PD:    run aggregates only, from Bm and delta (forward) or C, z, dout and delta (backward).
+//   barrier.                 The stage the main pass used and one prepass slot are free: thread 0 issues the TMA loads
+//            of tile i + 2 (main ring, 2 stages) and tile i + PD + 2 (prepass ring, 3 slots) into them.
+//   duty warp (one per 64-channel column, rotating): composes the prepass's run aggregates in run order, leaves the
+//            per-run coefficients (state entering the run = P * incoming + S) in shared memory, folds the tile into
+//            the aggregate of its super-tile; the super-tile's last tile publishes it (self-validating 64-bit words).
+//   every warp picks up the coefficients of tile i + PD - 1 into a small register queue: they are used PD - 1
+//            iterations later by the main pass.
+//
+// The prepass reads its operands a second time (L2 eviction hints keep about half of those reads out of DRAM); in
+// exchange nothing state-dependent has to be carried between the passes, the scanner's latency is covered by
+// PD - (SG - 1) tiles of work and a super-tile costs one hand-shake.
 //
 // A thread owns 2 adjacent channels x TSP = 4 consecutive tokens (a "run"); a warp is one run of a 64-channel column,
 // so every shared-memory access is a conflict-free 128-byte row and every global store a full 128-byte line.  Channel
-// pairs are processed with packed f32x2 arithmetic (FFMA2 / FMUL2).  d dt is reduced over the 16 channels of a head
-// with a transposing shuffle butterfly inside the warp and written once, final, as [B, L, H].
+// pairs are processed with packed f32x2 arithmetic (FFMA2 / FMUL2).  delta = softplus(dt) is computed once by a small
+// kernel into the saved-state buffer and arrives by TMA with the operands.  d dt is reduced over the 16 channels of a
+// head with a transposing shuffle butterfly inside the warp and written once, final, as [B, L, H].
 //
-// Deadlock freedom: a CTA's tile indices increase with its pipeline position and a tile's aggregate is published
-// before the CTA waits on any tile with a larger index minus one, so by induction over the tile index every wait is
-// on words whose producers are running; the scanners hold the first tickets.  The launch epoch lives in device memory
-// and is advanced by the last CTA to finish, which also resets the ticket: replayed CUDA graphs stay valid.
+// Deadlock freedom: a CTA's tiles increase with its pipeline position and an aggregate is published before the CTA
+// waits on any smaller tile, so by induction over the tile index every wait is on words whose producers are running;
+// the scanners hold the first tickets.  Every spin is bounded (error flag, no hang).  The launch epoch lives in device
+// memory and is advanced by the last CTA to finish, which also resets the ticket: replayed CUDA graphs stay valid.
+// tools/scan_trace_pipe.py (with `make TRACE=1`) prints the per-phase timeline of the forward kernel.
 #include "ssm_scan_shared.cuh"
 
 namespace {
@@ -782,13 +791,6 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 struct PipeTiling { int Cs, NWC, NR, TT, nslab, nchunks, nsuper, esize; };
 
-int pipe_env(const char* name, int dflt, int alt, int alt2 = -1) {
-    const char* e = getenv(name);
-    if (!e) return dflt;
-    const int v = atoi(e);
-    return (v == alt || v == alt2) ? v : dflt;
-}
-
 // slab = 64 channels when the width allows it, else the widest head-aligned divisor of Di that one CTA row covers.
 // Forward and backward tile the sequence independently (the saved states are per run of TSP tokens).
 bool pipe_tiling(int L, int Di, int dtype, bool bwd, PipeTiling& t) {
@@ -804,10 +806,7 @@ bool pipe_tiling(int L, int Di, int dtype, bool bwd, PipeTiling& t) {
     if (Cs * 2 < t.NWC * 64) return false;                      // more than half of the lanes would idle
     static const int nr_bf16[5] = {0, 16, 8, 5, 4}, nr_f32[5] = {0, 8, 4, 3, 2};
     t.NR = dtype == AB_F32 ? nr_f32[t.NWC] : nr_bf16[t.NWC];
-    if (dtype == AB_BF16 && t.NWC == 1) {           // tuning knob: 8 runs = 256-thread CTAs, twice as many per SM
-        static const int nf = pipe_env("APERTIS_B200_SCAN_NR_FWD", 16, 8), nb = pipe_env("APERTIS_B200_SCAN_NR_BWD", 16, 8);
-        t.NR = bwd ? nb : nf;
-    }
+    (void)bwd;      // both directions use the same tiling (256-thread CTAs with twice as many per SM measured slower)
     t.TT = t.NR * TSP;
     t.nslab = Di / Cs;
     t.nchunks = (int)ab_ceil_div(L, t.TT);
@@ -932,7 +931,7 @@ int launch_pipe(bool bwd, const CUtensorMap* maps, const PipeParams& p, const Pi
 }
 int dispatch_pipe(bool bwd, int dtype, const CUtensorMap* maps, const PipeParams& p, const PipeTiling& t, cudaStream_t st) {
     if (dtype == AB_BF16) switch (t.NWC) {
-        case 1: return t.NR == 8 ? launch_pipe<__nv_bfloat16, 1, 8>(bwd, maps, p, t, st) : launch_pipe<__nv_bfloat16, 1, 16>(bwd, maps, p, t, st);
+        case 1: return launch_pipe<__nv_bfloat16, 1, 16>(bwd, maps, p, t, st);
         case 2: return launch_pipe<__nv_bfloat16, 2, 8>(bwd, maps, p, t, st);
         case 3: return launch_pipe<__nv_bfloat16, 3, 5>(bwd, maps, p, t, st);
         default: return launch_pipe<__nv_bfloat16, 4, 4>(bwd, maps, p, t, st);
