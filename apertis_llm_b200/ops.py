@@ -51,6 +51,17 @@ def _scan_workspace(device, nbytes: int, mode: int = _lib.SCAN_SINGLE_PASS):
     return ent[0], ent[1]
 
 
+_SCAN_CHECK = os.environ.get("APERTIS_B200_SCAN_CHECK", "0") == "1"
+
+
+def _scan_check(ws: torch.Tensor, what: str):
+    """Debug aid (APERTIS_B200_SCAN_CHECK=1, synchronises): the hand-shake waits of the scan kernels are bounded and raise a
+    flag in the workspace instead of hanging; turn a raised flag into an exception."""
+    if _SCAN_CHECK and int(ws[64:68].view(torch.int32).item()) != 0:
+        ws[64:68].zero_()
+        raise RuntimeError(f"{what}: a hand-shake wait of the selective scan timed out (protocol error)")
+
+
 def scan_plan(B: int, L: int, Di: int, dtype: torch.dtype, mode: int = _lib.SCAN_SINGLE_PASS):
     """-> (tile rows, slab channels, saved states per sequence, workspace bytes, effective mode): a pipelined request
     the schedule does not cover comes back as single-pass."""
@@ -258,6 +269,7 @@ class _SelectiveScan(torch.autograd.Function):
         call("ab_selective_scan_fwd", ptr(xa), ptr(dlog), ptr(Bm), ptr(Cm), 2 * Di, ptr(z), _row_stride(z), ptr(A),
              ptr(Dv), ptr(h0c), ptr(y), ptr(y_ssm), ptr(h_last), ptr(hstart), ptr(ws), ws.numel(), epoch, mode,
              B, L, Di, H, dt(xa), stream_ptr())
+        _scan_check(ws, "ab_selective_scan_fwd")
         ctx.save_for_backward(xa, dlog, BC, z, A, Dv, hstart)
         ctx.mode = mode
         ctx.a_shape, ctx.want_yssm = A_log.shape, want_yssm
@@ -287,6 +299,7 @@ class _SelectiveScan(torch.autograd.Function):
         call("ab_selective_scan_bwd", ptr(xa), ptr(dlog), ptr(Bm), ptr(Cm), 2 * Di, ptr(z), _row_stride(z), ptr(dy),
              ptr(dys), ptr(A), ptr(Dv), ptr(hstart), ptr(dxa), ptr(dB), ptr(dC), 2 * Di, ptr(dz), ptr(ddl), ptr(dA), ptr(dD),
              ptr(ws), ws.numel(), epoch, ctx.mode, B, L, Di, H, dt(xa), stream_ptr())
+        _scan_check(ws, "ab_selective_scan_bwd")
         ddlog = (ddl if parts == H else ddl.view(B, L, H, parts // H).sum(-1)).to(dlog.dtype)
         return dxa, ddlog, dbc, dz, dA.reshape(ctx.a_shape), dD, None, None, None, None
 
