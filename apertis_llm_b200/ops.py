@@ -57,7 +57,7 @@ _SCAN_CHECK = os.environ.get("APERTIS_B200_SCAN_CHECK", "0") == "1"
 def _scan_check(ws: torch.Tensor, what: str):
     """Debug aid (APERTIS_B200_SCAN_CHECK=1, synchronises): the hand-shake waits of the scan kernels are bounded and raise a
     flag in the workspace instead of hanging; turn a raised flag into an exception."""
-    if _SCAN_CHECK and int(ws[64:68].view(torch.int32).item()) != 0:
+    if _SCAN_CHECK and not torch.cuda.is_current_stream_capturing() and int(ws[64:68].view(torch.int32).item()) != 0:
         ws[64:68].zero_()
         raise RuntimeError(f"{what}: a hand-shake wait of the selective scan timed out (protocol error)")
 
