@@ -474,16 +474,19 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
         PT_MARK(6);
 
         // ---- refill: the main stage tile i leaves goes to tile i + 2, the free prepass slot to tile i + PD + 2
-        if (tid == 0) {
-            if (i + 2 >= 0) {
-                const TileInfo nm = s_info[(i + 2) & (INFO_RING - 1)];
-                if (nm.b >= 0) issue_main(i & 1, nm);
-            }
+        // (the serial chores after the barrier go to different warps, so that no warp starts its next main pass late by
+        //  the sum of them: warp 0 refills the main ring, warp 1 the prepass ring, the duty rotates over the others)
+        if (tid == 0 && i + 2 >= 0) {
+            const TileInfo nm = s_info[(i + 2) & (INFO_RING - 1)];
+            if (nm.b >= 0) issue_main(i & 1, nm);
+        }
+        if (tid == 32) {
             const TileInfo np = s_info[(i + LA) & (INFO_RING - 1)];
             if (np.b >= 0) issue_pre((ps + NPRE - 1) % NPRE, np);
         }
         // ---- duty warp of this column: run prefixes in place, tile aggregate -> scanner
-        if (pi.b >= 0 && run == (i + PD) % NR && act)
+        const int duty_run = NR > 2 ? 2 + (i + PD) % (NR - 2) : (i + PD) % NR;
+        if (pi.b >= 0 && run == duty_run && act)
             compose_and_publish<NR, false>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs, accb + cl,
                                            pi.tile_lin & (SG - 1), sp.words + ((size_t)(pi.tile_lin >> LOG_SG) * Cs + cl) * 2, epoch);
         // ---- run coefficients of tile i + PD - 1 (composed during the previous iteration)
@@ -756,20 +759,21 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
         }
         __syncthreads();
 
-        if (tid == 0) {
-            if (i + 2 >= 0) {
-                const TileInfo nm = s_info[(i + 2) & (INFO_RING - 1)];
-                if (nm.b >= 0) issue_main(i & 1, nm);
-            }
+        if (tid == 0 && i + 2 >= 0) {
+            const TileInfo nm = s_info[(i + 2) & (INFO_RING - 1)];
+            if (nm.b >= 0) issue_main(i & 1, nm);
+        }
+        if (tid == 32) {
             const TileInfo np = s_info[(i + LA) & (INFO_RING - 1)];
             if (np.b >= 0) issue_pre((ps + NPRE - 1) % NPRE, np);
         }
-        if (run == (i + PD) % NR && act) {
-            if (pi.b >= 0)
-                compose_and_publish<NR, true>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs, accb + cl,
-                                              pi.tile_lin & (SG - 1), sp.words + ((size_t)(pi.tile_lin >> LOG_SG) * Cs + cl) * 2, epoch);
-            if (i >= 0) reduce_parts(mi.tile_lin, i & 1);
-        }
+        // two rotating duties on different warps: compose + publish the prepass tile, reduce the main tile's partials
+        const int duty_run = NR > 2 ? 2 + (i + PD) % (NR - 2) : (i + PD) % NR;
+        const int parts_run = NR > 3 ? 2 + (i + PD + (NR - 2) / 2) % (NR - 2) : (i + PD + 1) % NR;
+        if (run == duty_run && act && pi.b >= 0)
+            compose_and_publish<NR, true>(runP + ((i + PD) & 1) * NR * Cs + cl, runS + ((i + PD) & 1) * NR * Cs + cl, Cs, accb + cl,
+                                          pi.tile_lin & (SG - 1), sp.words + ((size_t)(pi.tile_lin >> LOG_SG) * Cs + cl) * 2, epoch);
+        if (run == parts_run && act && i >= 0) reduce_parts(mi.tile_lin, i & 1);
 #pragma unroll
         for (int q = 0; q + 1 < PD - 1; ++q) { cqP[q] = cqP[q + 1]; cqS[q] = cqS[q + 1]; }
         if (i + PD - 1 >= 0) {
