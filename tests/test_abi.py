@@ -56,3 +56,35 @@ def test_pure_queries_work_without_gpu():
     m.value = _lib.SCAN_SINGLE_PASS
     rc = plan(1, 16, 20, _lib.AB_BF16)
     assert rc != 0 and "tiling" in _lib.last_error()
+
+
+def test_scan_plan_pipelined_host_logic():
+    """Plan of the pipelined scan schedule (pure host code): which shapes it covers, the saved-state rows and that the
+    workspace grows with the problem."""
+    import ctypes
+
+    def plan(B, L, Di, dtype, mode):
+        t, s, n, m = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(mode)
+        ws = ctypes.c_size_t()
+        rc = _lib.query("ab_selective_scan_plan", B, L, Di, dtype, ctypes.byref(m), ctypes.byref(t), ctypes.byref(s), ctypes.byref(n),
+                        ctypes.byref(ws))
+        return rc, m.value, t.value, s.value, n.value, ws.value
+
+    P = _lib.SCAN_PIPELINED
+    prev_ws = 0
+    for L in (1, 5, 63, 64, 1000, 4096, 65536):
+        rc, mode, T, Cs, n, ws = plan(1, L, 512, _lib.AB_BF16, P)
+        assert rc == 0 and mode == P and Cs == 64 and T == 64
+        Hp = 32
+        assert n == -(-L // 4) + -(-L * Hp // 512)          # run states, then delta rows, in rows of Di floats
+        assert ws >= prev_ws and ws > 0
+        prev_ws = ws
+    # fp32 activations: half as many tokens per tile; odd head counts: one slab over the whole width when it fits a CTA row
+    rc, mode, T, Cs, n, ws = plan(2, 4096, 512, _lib.AB_F32, P)
+    assert rc == 0 and mode == P and (T, Cs) == (32, 64)
+    rc, mode, T, Cs, n, ws = plan(8, 4096, 176, _lib.AB_BF16, P)
+    assert rc == 0 and mode == P and Cs == 176 and T == 20 and n == 1024 + -(-4096 * 12 // 176)
+    # more chains than a quarter of the persistent grid, or a width whose slab would idle most lanes: another schedule
+    for args in ((64, 4096, 512), (1, 4096, 16 * 17)):
+        rc, mode, T, Cs, n, ws = plan(*args, _lib.AB_BF16, P)
+        assert rc == 0 and mode == _lib.SCAN_SINGLE_PASS and n == -(-args[1] // T)
