@@ -21,7 +21,7 @@ CSRC = os.path.join(_HERE, "csrc")
 AB_F32, AB_BF16 = 0, 1
 ACT = {"gelu": 0, "relu": 1, "silu": 2, "swish": 2}
 EPI_NONE, EPI_BIAS, EPI_BIAS_ACT, EPI_DACT = 0, 1, 2, 3
-SCAN_SINGLE_PASS, SCAN_TWO_PASS, SCAN_PIPELINED = 0, 1, 2
+SCAN_SINGLE_PASS, SCAN_TWO_PASS, SCAN_PIPELINED, SCAN_ROUNDS = 0, 1, 2, 3
 ROW_ALIGN = 128
 
 P, I, I64, SZ, F, U32 = c_void_p, c_int, c_int64, c_size_t, c_float, c_uint32
@@ -38,6 +38,11 @@ SIGNATURES = {
     "ab_selective_scan_fwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, SZ, U32, I, I, I, I, I, I, P]),
     "ab_selective_scan_bwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, I64, P, P, P, P, P, SZ, U32, I,
                                   I, I, I, I, I, P]),
+    "ab_ssm_scan_plan": (I, [I, I, I, I, P, P]),
+    "ab_ssm_scan_tune": (I, [I, I, I]),
+    "ab_ssm_scan_fwd": (I, [P, I64, P, I64, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
+    "ab_ssm_scan_bwd": (I, [P, I64, P, P, I64, P, I64, P, P, P, P, P, P, I64, P, P, I64, P, I64, P, I64, I, P, P, P, P, SZ,
+                            I, I, I, I, I, P]),
     "ab_moe_router_workspace_bytes": (SZ, [I, I, I]),
     "ab_moe_router_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
     "ab_moe_topk_from_logits": (I, [P, P, P, P, P, P, I, I, I, P]),
@@ -120,8 +125,9 @@ def dt(t_or_dtype) -> int:
     raise TypeError(f"apertis_b200 kernels take float32 or bfloat16 activations, got {d}")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def ensure_device(device) -> None:
@@ -142,6 +148,7 @@ def ensure_device(device) -> None:
 KERNELS_PER_CALL = {
     "ab_causal_conv1d_silu_fwd": 1, "ab_causal_conv1d_silu_bwd": 2,
     "ab_selective_scan_fwd": 1, "ab_selective_scan_bwd": 2,          # single pass; two pass adds 2
+    "ab_ssm_scan_fwd": 1, "ab_ssm_scan_bwd": 2,
     "ab_moe_router_fwd": 2, "ab_moe_topk_from_logits": 1, "ab_moe_plan": 2, "ab_moe_permute_ln": 1, "ab_moe_unpermute": 1,
     "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,
     "ab_layernorm_fwd": 1, "ab_layernorm_bwd": 3,

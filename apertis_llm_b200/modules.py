@@ -58,13 +58,18 @@ class BlockConfig:
 
 
 def _autocast_dtype(device_type: str = "cuda") -> Optional[torch.dtype]:
+    """The active autocast dtype, or None.  torch.float16 is what the reference trainer asks for (pipeline.py:482,533:
+    ``torch.amp.autocast('cuda')`` + ``GradScaler``); the kernels then compute in bf16 / fp32 (same exponent range as fp32,
+    so the scaler's 2^16 loss scale cannot overflow inside the layer) and only the tensors the reference would return
+    as fp16 are cast on the way out."""
     if not torch.is_autocast_enabled(device_type):
         return None
-    d = torch.get_autocast_dtype(device_type)
-    if d == torch.float16:
-        raise NotImplementedError("apertis_llm_b200: fp16 autocast is not supported by the sm_100a kernels; "
-                                  "use torch.autocast('cuda', dtype=torch.bfloat16) or fp32")
-    return d
+    return torch.get_autocast_dtype(device_type)
+
+
+def _compute_dtype(ac: Optional[torch.dtype]) -> Optional[torch.dtype]:
+    """Kernel activation dtype for an autocast dtype: fp16 requests run in bf16."""
+    return torch.bfloat16 if ac == torch.float16 else ac
 
 
 # ================================================================================================
@@ -103,11 +108,20 @@ class SelectiveLinearAttention(nn.Module):
                 output_attentions: bool = False, use_cache: bool = False):
         # attention_mask / position_ids are accepted and ignored, exactly like the reference (core.py:355-401)
         _lib.ensure_device(hidden_states.device)
-        _autocast_dtype()
+        ac = _autocast_dtype()
+        if ac == torch.float16:
+            # the reference trainer's AMP mode (pipeline.py:482,533): run the layer in bf16 and hand back what the reference
+            # would (fp16 out_proj output, fp16 y_ssm / states), so GradScaler and the fp16 callers keep working
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out, y_ssm, cache = self.forward(hidden_states, attention_mask, position_ids, past_key_value, output_attentions, use_cache)
+            h16 = lambda t: t.to(torch.float16) if (t is not None and t.dtype == torch.bfloat16) else t
+            return h16(out), h16(y_ssm), (tuple(h16(c) for c in cache) if cache is not None else None)
         self.use_cache = use_cache
         B, L, _ = hidden_states.shape
         Di, R, Kc = self.d_inner, self.dt_rank, self.conv_kernel_size
         conv_prev, h_prev = (past_key_value if past_key_value is not None else (None, None))
+        if ac is not None and hidden_states.dtype == torch.float16:
+            hidden_states = hidden_states.to(ac)
         xp = self.in_proj_x(hidden_states)                                    # :366
         z = self.in_proj_z(hidden_states)                                     # :367
         x_seq = xp

@@ -25,14 +25,15 @@ _scan_ws = {}       # (device index, stream, pipelined?) -> [tensor, epoch]
 # inner width is a multiple of 64 channels and the sequence has at least 1024 tokens (one warp column per slab: its measured win, see
 # profiles/r1j_scan_*), the one-tile-per-CTA single pass otherwise.
 _SCAN_ENV = os.environ.get("APERTIS_B200_SCAN", "auto")
-SCAN_MODE = {"two_pass": _lib.SCAN_TWO_PASS, "single": _lib.SCAN_SINGLE_PASS, "pipelined": _lib.SCAN_PIPELINED}.get(_SCAN_ENV)
+SCAN_MODE = {"two_pass": _lib.SCAN_TWO_PASS, "single": _lib.SCAN_SINGLE_PASS, "pipelined": _lib.SCAN_PIPELINED,
+             "rounds": _lib.SCAN_ROUNDS}.get(_SCAN_ENV)
 
 
 def default_scan_mode(dtype: torch.dtype, Di: int, L: int = 1 << 20) -> int:
+    """The "rounds" schedule (csrc/ssm_scan_rounds.cu) serves every shape; the older schedules stay selectable."""
     if SCAN_MODE is not None:
         return SCAN_MODE
-    # short sequences (cached decode steps, tiny prompts) do not fill a persistent grid: one tile per CTA there
-    return _lib.SCAN_PIPELINED if (Di % 64 == 0 and L >= 1024) else _lib.SCAN_SINGLE_PASS
+    return _lib.SCAN_ROUNDS
 
 
 def _scan_workspace(device, nbytes: int, mode: int = _lib.SCAN_SINGLE_PASS):
@@ -310,7 +311,110 @@ def selective_scan(xa, dlog, BC, z, A_log, D, h0=None, want_yssm=False, want_hla
     xa, z [B,L,Di]; BC [B,L,2*Di] = [B-term | C-term]; dlog [B,L,H]; A_log [H,16]; D [Di]; h0 [B,H,16] or None.
     Returns (y [B,L,Di], y_ssm | None, h_last [B,Di] fp32 | None)."""
     mode = default_scan_mode(xa.dtype, xa.shape[-1], xa.shape[1]) if mode is None else mode
+    if mode == _lib.SCAN_ROUNDS:
+        return _SelectiveScanRounds.apply(xa, dlog, None, BC, z, A_log, D, h0, want_yssm, want_hlast, dlog.shape[-1])
     return _SelectiveScan.apply(xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, mode)
+
+
+# --------------------------------------------------------------------------------------------
+# selective scan, "rounds" schedule (the default)
+# --------------------------------------------------------------------------------------------
+_rounds_ws = {}      # (device index, stream) -> workspace tensor
+
+
+def _rounds_plan(B, L, Di, dtype):
+    n, ws = ctypes.c_int64(), ctypes.c_size_t()
+    call("ab_ssm_scan_plan", B, L, Di, dt(dtype), ctypes.byref(n), ctypes.byref(ws))
+    return n.value, ws.value
+
+
+def _rounds_workspace(device, nbytes):
+    """One workspace per (device, stream): launches on a stream are ordered, and each launch zeroes its own counters."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _rounds_ws.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _rounds_ws[key] = t
+    return t
+
+
+def _cols(t, lo, hi):
+    return t[..., lo:hi]
+
+
+class _SelectiveScanRounds(torch.autograd.Function):
+    """xa [B,L,Di] and z [B,L,Di] may be column slices of wider buffers (row stride arbitrary).
+    fused layout (dlog is None): prm [B,L,Hp+2Di] = [dt (H, zero padded to Hp) | B | C], dt WITHOUT its bias (dt_bias given);
+    split layout: dlog [B,L,H] contiguous (bias already in, or given separately), prm = [B | C] [B,L,2Di]."""
+
+    @staticmethod
+    def forward(ctx, xa, dlog, dt_bias, prm, z, A_log, D, h0, want_yssm, want_hlast, H):
+        _lib.ensure_device(xa.device)
+        with torch.cuda.device(xa.device):
+            xa, z, prm = _rows(xa), _rows(z), _rows(prm)
+            B, L, Di = xa.shape
+            dev = xa.device
+            fused = dlog is None
+            W = prm.shape[-1]
+            Hp = W - 2 * Di
+            assert Hp >= (H if fused else 0) and (fused or Hp == 0), "bad [dt | B | C] layout"
+            dl = prm if fused else dlog.contiguous()
+            dl_stride = _row_stride(prm) if fused else H
+            Bm, Cm = _cols(prm, Hp, Hp + Di), _cols(prm, Hp + Di, Hp + 2 * Di)
+            A = A_log.reshape(-1).float().contiguous()
+            Dv = D.float().contiguous()
+            bias = dt_bias.float().contiguous() if dt_bias is not None else None
+            nstate, nws = _rounds_plan(B, L, Di, xa.dtype)
+            ws = _rounds_workspace(dev, nws)
+            y = torch.empty(B, L, Di, dtype=xa.dtype, device=dev)
+            y_ssm = torch.empty(B, L, Di, dtype=xa.dtype, device=dev) if want_yssm else None
+            h_last = torch.empty(B, Di, dtype=torch.float32, device=dev) if want_hlast else None
+            state = torch.empty(nstate, dtype=torch.float32, device=dev)
+            h0c = h0.reshape(B, Di).float().contiguous() if h0 is not None else None
+            call("ab_ssm_scan_fwd", ptr(xa), _row_stride(xa), ptr(dl), dl_stride, ptr(bias), ptr(Bm), ptr(Cm), _row_stride(prm),
+                 ptr(z), _row_stride(z), ptr(A), ptr(Dv), ptr(h0c), ptr(y), ptr(y_ssm), ptr(h_last), ptr(state), ptr(ws), ws.numel(),
+                 B, L, Di, H, dt(xa), stream_ptr(dev))
+            ctx.save_for_backward(xa, prm, z, A, Dv, state)
+            ctx.meta = (fused, H, Hp, want_yssm, A_log.shape, dlog.dtype if dlog is not None else None,
+                        dt_bias is not None, dt_bias.dtype if dt_bias is not None else None)
+            if h_last is not None:
+                ctx.mark_non_differentiable(h_last)
+            return y, y_ssm, h_last
+
+    @staticmethod
+    def backward(ctx, dy, dyssm, _dh):
+        xa, prm, z, A, Dv, state = ctx.saved_tensors
+        fused, H, Hp, want_yssm, a_shape, dlog_dtype, has_bias, bias_dtype = ctx.meta
+        with torch.cuda.device(xa.device):
+            B, L, Di = xa.shape
+            dev = xa.device
+            W = prm.shape[-1]
+            Bm, Cm = _cols(prm, Hp, Hp + Di), _cols(prm, Hp + Di, Hp + 2 * Di)
+            dy = dy.contiguous()
+            dys = dyssm.contiguous() if (dyssm is not None and want_yssm) else None
+            nstate, nws = _rounds_plan(B, L, Di, xa.dtype)
+            ws = _rounds_workspace(dev, nws)
+            dxa = torch.empty(B, L, Di, dtype=xa.dtype, device=dev)
+            dz = torch.empty(B, L, Di, dtype=xa.dtype, device=dev)
+            dprm = torch.empty(B, L, W, dtype=xa.dtype, device=dev)
+            ddl = dprm if fused else torch.empty(B, L, H, dtype=xa.dtype, device=dev)
+            dA = torch.empty(Di, dtype=torch.float32, device=dev)
+            dD = torch.empty(Di, dtype=torch.float32, device=dev)
+            dbias = torch.empty(H, dtype=torch.float32, device=dev) if has_bias else None
+            dB, dC = _cols(dprm, Hp, Hp + Di), _cols(dprm, Hp + Di, Hp + 2 * Di)
+            call("ab_ssm_scan_bwd", ptr(xa), _row_stride(xa), ptr(Bm), ptr(Cm), _row_stride(prm), ptr(z), _row_stride(z), ptr(dy),
+                 ptr(dys), ptr(A), ptr(Dv), ptr(state), ptr(dxa), Di, ptr(dB), ptr(dC), W, ptr(dz), Di, ptr(ddl),
+                 W if fused else H, Hp if fused else H, ptr(dbias), ptr(dA), ptr(dD), ptr(ws), ws.numel(), B, L, Di, H, dt(xa),
+                 stream_ptr(dev))
+            ddlog = None if fused else ddl.to(dlog_dtype)
+            return (dxa, ddlog, dbias.to(bias_dtype) if has_bias else None, dprm, dz, dA.reshape(a_shape), dD,
+                    None, None, None, None)
+
+
+def selective_scan_fused(xa, prm, dt_bias, z, A_log, D, H, h0=None, want_yssm=False, want_hlast=False):
+    """Scan over the fused projection output prm [B,L,Hp+2Di] = [dt (no bias) | B | C] (see _SelectiveScanRounds)."""
+    return _SelectiveScanRounds.apply(xa, None, dt_bias, prm, z, A_log, D, h0, want_yssm, want_hlast, H)
+
 
 
 # --------------------------------------------------------------------------------------------

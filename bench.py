@@ -313,7 +313,8 @@ def main():
         return step(dev_x[i % nbuf])
 
     # ---- timed region: device-resident inputs, CUDA events
-    timed_names = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_selective_scan_fwd", "ab_selective_scan_bwd"]
+    timed_names = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_ssm_scan_fwd", "ab_ssm_scan_bwd",
+                   "ab_selective_scan_fwd", "ab_selective_scan_bwd"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(2):
         run_step(i)
@@ -470,7 +471,7 @@ def scan_long_context(pk_hbm, L=65536, Hh=32, iters=8):
     D = torch.ones(Di, device=d)
     leaves = [t.requires_grad_(True) for t in (xa, dlog, BC, z, A_log, D)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=d)
-    names = ["ab_selective_scan_fwd", "ab_selective_scan_bwd"]
+    names = ["ab_ssm_scan_fwd", "ab_ssm_scan_bwd"]
 
     def run():
         y = ops.selective_scan(*leaves)[0]
@@ -491,7 +492,7 @@ def scan_long_context(pk_hbm, L=65536, Hh=32, iters=8):
     gbs = nbytes / ((mf + mb) * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": gbs, "peak": pk_hbm, "unit": "GB/s", "frac": gbs / pk_hbm, "fwd_us": mf * 1e3, "bwd_us": mb * 1e3,
             "algorithmic_bytes": nbytes, "workload": "configs[4]: d_model 2048 (d_inner 512, 32 heads), B 1, L 65536, bf16, one layer's scan fwd+bwd",
-            "schedule": {0: "single pass", 1: "two pass", 2: "pipelined persistent"}[ops.default_scan_mode(torch.bfloat16, Di)]}
+            "schedule": {0: "single pass", 1: "two pass", 2: "pipelined persistent", 3: "rounds (persistent, warp-serial chunks)"}[ops.default_scan_mode(torch.bfloat16, Di)]}
 
 
 if __name__ == "__main__":

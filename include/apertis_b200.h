@@ -110,6 +110,37 @@ int ab_selective_scan_bwd(const void* xa, const void* dlog, const void* Bm, cons
                           float* dA_log, float* dD, void* ws, size_t ws_bytes, uint32_t epoch, int mode,
                           int B, int L, int Di, int H, int dtype, cudaStream_t stream);
 
+/* ---- SSM: selective scan, "rounds" schedule (csrc/ssm_scan_rounds.cu) ------------------------------------------
+ * Same arithmetic as above (core.py:324-353, :383, :394-396), one persistent kernel per direction: warps walk chunks of
+ * one 64-channel slab serially (two channels per lane), every chunk is visited twice (aggregate pass, then the streaming
+ * pass with the incoming state known), a round's chunk aggregates are prefixed by a two-level scan of whoever arrives
+ * last.  Row strides are in elements; every activation may be a column slice of a wider row-major buffer, which is how
+ * the fused projection outputs ([xp | z] and [dt | B | C]) are consumed and produced without copies.
+ *   dlog [B,L,H] (row stride dlog_stride) holds the dt_proj_head output WITHOUT its bias when dt_bias != NULL
+ *   (delta = softplus(dlog + dt_bias[h])), or with it when dt_bias == NULL.
+ *   state: fp32 buffer of `state_floats` elements written by the forward and read by the backward
+ *   (the scan state entering every group of 8 tokens, then delta of every (token, head)).
+ *   ws: workspace of ws_bytes (ab_ssm_scan_plan); its counters are zeroed by a memset enqueued ahead of each launch,
+ *   so the same workspace serves any number of launches on ONE stream and the launch sequence can be captured in a graph.
+ * A wait that cannot complete (protocol error, preempted grid) traps: the launch fails with a CUDA error. */
+int ab_ssm_scan_plan(int B, int L, int Di, int dtype, int64_t* state_floats, size_t* ws_bytes);
+/* tuning knobs (0 = library default): chunk length of the forward / backward (multiple of 8 tokens), resident warps per SM */
+int ab_ssm_scan_tune(int tc_fwd, int tc_bwd, int warps_per_sm);
+int ab_ssm_scan_fwd(const void* xa, int64_t xa_stride, const void* dlog, int64_t dlog_stride, const float* dt_bias,
+                    const void* Bm, const void* Cm, int64_t bc_stride, const void* z, int64_t z_stride,
+                    const float* A_log, const float* D, const float* h0, void* y, void* y_ssm, float* h_last,
+                    float* state, void* ws, size_t ws_bytes, int B, int L, int Di, int H, int dtype,
+                    cudaStream_t stream);
+/* dout = grad of y (contiguous [B,L,Di]); dyssm (optional) = grad of y_ssm.  Outputs: dxa, dz, dBm / dCm (shared stride)
+ * and ddlog (activation dtype, final: already multiplied by softplus'; columns [H, ddlog_cols) are written as zero),
+ * ddt_bias [H] (optional), dA_log [Di], dD [Di] fp32, overwritten (fixed-order reductions: bitwise reproducible). */
+int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm, const void* Cm, int64_t bc_stride,
+                    const void* z, int64_t z_stride, const void* dout, const void* dyssm, const float* A_log,
+                    const float* D, const float* state, void* dxa, int64_t dxa_stride, void* dBm, void* dCm,
+                    int64_t dbc_stride, void* dz, int64_t dz_stride, void* ddlog, int64_t ddlog_stride, int ddlog_cols,
+                    float* ddt_bias, float* dA_log, float* dD, void* ws, size_t ws_bytes, int B, int L, int Di, int H,
+                    int dtype, cudaStream_t stream);
+
 /* ---- MoE: router  (core.py:480-492 LN+Linear+noise+softmax+top-k, :499-505 lb, :524-526 rz, :529) --
  * Per token s: stats (mean, rstd) of x[s,:] (eps inside the sqrt, as nn.LayerNorm);
  *   logits = LN(x)*ln_w+ln_b @ Wr^T + br (+ noise[s,e]*noise_scale[e] when noise != NULL);

@@ -74,9 +74,13 @@ def scan_recurrent(delta: Tensor, A_log: Tensor, Bt: Tensor, Ct: Tensor,
     Bsz, H, L, N = Bt.shape
     h = h0 if h0 is not None else torch.zeros(Bsz, H, N, dtype=Bt.dtype)
     ys = []
+    # same per-step arithmetic as the reference's indexing (abar[:, :, t, :] ...); unbind() hands autograd one
+    # backward node per tensor instead of one zero-filled [B,H,L,N] gradient per step, which is what makes the
+    # L >= 16K parity cases (SURVEY.md 8c caveat 1) tractable on the CPU
+    a_t, b_t, c_t = abar.unbind(2), Bt.unbind(2), Ct.unbind(2)
     for t in range(L):                                        # :347
-        h = abar[:, :, t, :] * h + Bt[:, :, t, :]
-        ys.append(Ct[:, :, t, :] * h)
+        h = a_t[t] * h + b_t[t]
+        ys.append(c_t[t] * h)
     return torch.stack(ys, dim=2), h
 
 

@@ -2,7 +2,7 @@
 """Long-context selective-scan sweep (BASELINE.json configs[4]): d_model 2048 -> Di 512, H 32, one SSM layer's scan
 kernels forward + backward, seq 2K..64K, HBM GB/s against the algorithmic bytes of SURVEY.md section 8(d).
 
-    python tools/scan_bench.py [--dtype bf16|f32] [--mode pipe|single|two_pass] [--seqs 2048,...] [--batch 1] [--iters 20]
+    python tools/scan_bench.py [--dtype bf16|f32] [--mode rounds|pipe|single|two_pass] [--seqs 2048,...] [--batch 1] [--iters 20]
 """
 import argparse
 import json
@@ -18,7 +18,10 @@ from apertis_llm_b200 import _lib, ops  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dtype", default="bf16")
-    ap.add_argument("--mode", default="pipe")
+    ap.add_argument("--mode", default="rounds")
+    ap.add_argument("--tc-fwd", type=int, default=0, help="rounds schedule: forward chunk length (0 = library default)")
+    ap.add_argument("--tc-bwd", type=int, default=0)
+    ap.add_argument("--wps", type=int, default=0, help="rounds schedule: cap on resident warps per SM")
     ap.add_argument("--seqs", default="2048,4096,8192,16384,32768,65536")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--heads", type=int, default=32)
@@ -28,7 +31,8 @@ def main():
     d = torch.device("cuda:0")
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     es = 2 if dtype == torch.bfloat16 else 4
-    mode = {"single": _lib.SCAN_SINGLE_PASS, "two_pass": _lib.SCAN_TWO_PASS, "pipe": _lib.SCAN_PIPELINED}[args.mode]
+    mode = {"single": _lib.SCAN_SINGLE_PASS, "two_pass": _lib.SCAN_TWO_PASS, "pipe": _lib.SCAN_PIPELINED, "rounds": _lib.SCAN_ROUNDS}[args.mode]
+    _lib.load().ab_ssm_scan_tune(args.tc_fwd, args.tc_bwd, args.wps)
     H = args.heads
     Di = 16 * H
     B = args.batch
@@ -49,7 +53,7 @@ def main():
         dy = mk(B, L, Di)
         leaves = [t.requires_grad_(True) for t in (xa, dlog, BC, z)]
         A_log.requires_grad_(True); D.requires_grad_(True)
-        names = ["ab_selective_scan_fwd", "ab_selective_scan_bwd"]
+        names = ["ab_ssm_scan_fwd", "ab_ssm_scan_bwd"] if mode == _lib.SCAN_ROUNDS else ["ab_selective_scan_fwd", "ab_selective_scan_bwd"]
 
         def run():
             y, _, _ = ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=mode)
