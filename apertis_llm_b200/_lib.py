@@ -20,7 +20,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 AB_F32, AB_BF16 = 0, 1
 ACT = {"gelu": 0, "relu": 1, "silu": 2, "swish": 2}
-EPI_NONE, EPI_BIAS, EPI_BIAS_ACT, EPI_DACT = 0, 1, 2, 3
+EPI_NONE, EPI_BIAS, EPI_BIAS_ACT, EPI_DACT, EPI_ADD = 0, 1, 2, 3, 4
 SCAN_SINGLE_PASS, SCAN_TWO_PASS, SCAN_PIPELINED, SCAN_ROUNDS = 0, 1, 2, 3
 ROW_ALIGN = 128
 
@@ -33,7 +33,7 @@ SIGNATURES = {
     "ab_last_error": (I, [c_char_p, SZ]),
     "ab_causal_conv1d_silu_fwd": (I, [P, I64, P, P, P, I, I, I, I, I, P]),
     "ab_causal_conv1d_silu_bwd_workspace_bytes": (SZ, [I, I, I]),
-    "ab_causal_conv1d_silu_bwd": (I, [P, I64, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
+    "ab_causal_conv1d_silu_bwd": (I, [P, I64, P, P, P, P, I64, P, P, P, SZ, I, I, I, I, I, P]),
     "ab_selective_scan_plan": (I, [I, I, I, I, P, P, P, P, P]),
     "ab_selective_scan_fwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, SZ, U32, I, I, I, I, I, I, P]),
     "ab_selective_scan_bwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, I64, P, P, P, P, P, SZ, U32, I,
@@ -61,6 +61,11 @@ SIGNATURES = {
     "ab_grouped_gemm_nt": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, F, P, P]),
     "ab_grouped_gemm_nn": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, F, P, P]),
     "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, I, I64, P]),
+    "ab_dense_gemm_nt": (I, [P, P, P, P, P, I64, I, I, I, I, P]),
+    "ab_dense_gemm_nn": (I, [P, P, P, P, P, I64, I, I, I, I, P]),
+    "ab_dense_gemm_tn": (I, [P, P, P, I64, I, I, P]),
+    "ab_dt_compose_fwd": (I, [P, P, P, I, I, I, I, I, P]),
+    "ab_dt_compose_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "ab_layernorm_fwd": (I, [P, P, P, F, P, P, I, I, I, I, P]),
     "ab_layernorm_bwd_workspace_bytes": (SZ, [I, I]),
     "ab_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, P]),
@@ -148,7 +153,8 @@ def ensure_device(device) -> None:
 KERNELS_PER_CALL = {
     "ab_causal_conv1d_silu_fwd": 1, "ab_causal_conv1d_silu_bwd": 2,
     "ab_selective_scan_fwd": 1, "ab_selective_scan_bwd": 2,          # single pass; two pass adds 2
-    "ab_ssm_scan_fwd": 1, "ab_ssm_scan_bwd": 2,
+    "ab_ssm_scan_fwd": 1, "ab_ssm_scan_bwd": 2, "ab_dense_gemm_nt": 1, "ab_dense_gemm_nn": 1, "ab_dense_gemm_tn": 1,
+    "ab_dt_compose_fwd": 1, "ab_dt_compose_bwd": 2,
     "ab_moe_router_fwd": 2, "ab_moe_topk_from_logits": 1, "ab_moe_plan": 2, "ab_moe_permute_ln": 1, "ab_moe_unpermute": 1,
     "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,
     "ab_layernorm_fwd": 1, "ab_layernorm_bwd": 3,

@@ -38,6 +38,10 @@ struct GemmParams {
     int epi, act, c_f32;
     int tn_nsrc;             // MODE_TN: an expert's rows are nsrc blocks [src*stride + seg_off[e], src*stride + seg_off[e+1])
     int64_t tn_src_stride;
+    // dense use (one "expert", plain row-major matrices; tile_expert / n_rows / seg_off are NULL):
+    int64_t rows_valid;      // MODE_NT / MODE_NN: rows >= rows_valid are never stored (the last row tile may be partial)
+    int dense_m_tiles;       // MODE_NT / MODE_NN: number of row tiles when n_rows is NULL
+    int64_t tn_rows;         // MODE_TN with seg_off NULL: contraction over rows [0, tn_rows), TMA zero-fills past the end
     const int32_t* tile_expert;
     const int32_t* n_rows;
     const int32_t* seg_off;
@@ -157,7 +161,7 @@ __device__ __forceinline__ void stage_and_store(const GemmParams& p, unsigned ch
         const int r = it * 8 + (lane >> 2), j = lane & 3;
         const int col = ncol + j * CPV;
         const size_t grow = (size_t)m_tile * BM + quarter * 32 + r;
-        const bool ok = col < ncol_end && (MODE != MODE_TN || (int)grow < p.M);
+        const bool ok = col < ncol_end && (MODE == MODE_TN ? (int)grow < p.M : (int64_t)grow < p.rows_valid);
         const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(r, j));
         if (ok) *reinterpret_cast<uint4*>(base + (grow * N + col) * ES) = q;
     }
@@ -230,6 +234,30 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
                         for (int u = 0; u < 4; ++u) f[i + u] = keep[u] ? f[i + u] * p.drop_scale : 0.f;
                     }
                 }
+            } else if (p.epi == AB_EPI_ADD) {
+                // C = acc + aux (aux has C's shape and dtype): accumulate a second gradient contribution in the epilogue
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it * 8 + (lane >> 2), j = lane & 3;
+                    const int col = ncol + j * CPV;
+                    const int64_t grow = (int64_t)m_tile * BM + quarter * 32 + r;
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                    if (col < ncol_end && grow < p.rows_valid)
+                        q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.aux) + ((size_t)grow * N + col) * ES));
+                    *reinterpret_cast<uint4*>(stg + stg_off(r, j)) = q;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+                    float add[CPV];
+                    if (F32) { add[0] = __uint_as_float(q.x); add[1] = __uint_as_float(q.y); add[2] = __uint_as_float(q.z); add[3] = __uint_as_float(q.w); }
+                    else ab_vec16<__nv_bfloat16>::unpack(q, add);
+#pragma unroll
+                    for (int i = 0; i < CPV; ++i) f[j * CPV + i] += add[i];
+                }
+                __syncwarp();
             } else if (p.epi == AB_EPI_DACT) {
                 // saved pre-activation tile: coalesced 16-byte loads -> staging -> each thread reads its own row
                 __syncwarp();
@@ -310,7 +338,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
     // ---- tile schedule (identical in every role)
     int total_tiles;
     if (MODE == MODE_TN) total_tiles = p.E * p.num_m_tiles * p.num_n_tiles;
-    else total_tiles = (p.n_rows[0] / BM) * p.num_n_tiles;
+    else total_tiles = (p.n_rows != nullptr ? p.n_rows[0] / BM : p.dense_m_tiles) * p.num_n_tiles;
     const int bn = p.bn;
     const uint32_t b_bytes = MODE == MODE_NT ? (uint32_t)bn * BK * 2 : (uint32_t)(bn / 64) * ATOM_BYTES;
     const uint32_t stage_tx = A_BYTES + b_bytes;
@@ -325,11 +353,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                     e = tile / (p.num_m_tiles * p.num_n_tiles);
                     const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
                     m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                    k_begin = p.seg_off[e];
-                    nk = p.tn_nsrc * ((p.seg_off[e + 1] - k_begin) / BK);
+                    k_begin = p.seg_off != nullptr ? p.seg_off[e] : 0;
+                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - k_begin) / BK) : (int)((p.tn_rows + BK - 1) / BK);
                 } else {
                     m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
-                    e = p.tile_expert[m_tile];
+                    e = p.tile_expert != nullptr ? p.tile_expert[m_tile] : 0;
                     k_begin = 0;
                     nk = (p.K + BK - 1) / BK;
                 }
@@ -368,7 +396,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 int nk;
                 if (MODE == MODE_TN) {
                     const int e = tile / (p.num_m_tiles * p.num_n_tiles);
-                    nk = p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK);
+                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : (int)((p.tn_rows + BK - 1) / BK);
                     if (nk == 0) continue;          // empty expert: the epilogue writes zeros without an accumulator
                 } else {
                     nk = (p.K + BK - 1) / BK;
@@ -408,10 +436,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 e = tile / (p.num_m_tiles * p.num_n_tiles);
                 const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
                 m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                nk = p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK);
+                nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : (int)((p.tn_rows + BK - 1) / BK);
             } else {
                 m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
-                e = p.tile_expert[m_tile];
+                e = p.tile_expert != nullptr ? p.tile_expert[m_tile] : 0;
                 nk = 1;
             }
             const bool have_acc = nk > 0;
@@ -480,10 +508,10 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm: max_rows must be a positive multiple of %d", BM);
     AB_REQUIRE(N > 0 && K > 0 && E > 0 && N % 8 == 0 && K % 8 == 0, "grouped_gemm: N (%d) and K (%d) must be multiples of 8", N, K);
     AB_REQUIRE(c_dtype == AB_F32 || c_dtype == AB_BF16, "grouped_gemm: bad output dtype");
-    AB_REQUIRE(epi >= AB_EPI_NONE && epi <= AB_EPI_DACT, "grouped_gemm: bad epilogue %d", epi);
+    AB_REQUIRE(epi >= AB_EPI_NONE && epi <= AB_EPI_ADD, "grouped_gemm: bad epilogue %d", epi);
     AB_REQUIRE((epi != AB_EPI_BIAS && epi != AB_EPI_BIAS_ACT) || bias, "grouped_gemm: bias epilogue without bias");
     AB_REQUIRE(epi != AB_EPI_BIAS_ACT || c2, "grouped_gemm: bias+act epilogue needs the pre-activation output c2");
-    AB_REQUIRE(epi != AB_EPI_DACT || aux, "grouped_gemm: dact epilogue needs aux");
+    AB_REQUIRE((epi != AB_EPI_DACT && epi != AB_EPI_ADD) || aux, "grouped_gemm: dact / add epilogue needs aux");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.K = K; p.E = E;
@@ -491,6 +519,7 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
     p.epi = epi; p.act = act; p.c_f32 = c_dtype == AB_F32;
     p.tile_expert = tile_expert; p.n_rows = n_rows; p.bias = bias; p.aux = aux; p.c = c; p.c2 = c2;
+    p.rows_valid = max_rows;
     if (drop_p > 0.f) {
         p.drop_seed = drop_seed;
         p.drop_thresh = (uint32_t)((double)drop_p * 65536.0 + 0.5);
@@ -542,4 +571,64 @@ extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, cons
     if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)max_rows, 64, BK)) return e;
     if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)max_rows, 64, BK)) return e;
     return launch<MODE_TN>(ta, tb, p, (int64_t)E * p.num_m_tiles * p.num_n_tiles, stream);
+}
+
+// ---- dense GEMMs on the same kernel (one "expert", plain row-major matrices): the SSM layer's projections
+//      in_proj_x | in_proj_z, x_param_proj (+ dt_proj_head folded in), out_proj (core.py:366-367, 376-383, 397) and their
+//      autograd.  Rows need not be a multiple of the tile: TMA zero-fills what it reads past the matrix, stores are masked.
+namespace {
+int dense_rows(int mode, const void* A, const void* W, const float* bias, const void* aux, void* c, int64_t S, int N, int K, int epi,
+               int c_dtype, cudaStream_t stream) {
+    AB_REQUIRE(S > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, "dense_gemm: S (%lld) must be positive, N (%d) and K (%d) multiples of 8", (long long)S, N, K);
+    AB_REQUIRE(c_dtype == AB_F32 || c_dtype == AB_BF16, "dense_gemm: bad output dtype");
+    AB_REQUIRE(epi == AB_EPI_NONE || epi == AB_EPI_BIAS || epi == AB_EPI_ADD, "dense_gemm: epilogue must be none, bias or add");
+    AB_REQUIRE(epi != AB_EPI_BIAS || bias, "dense_gemm: bias epilogue without bias");
+    AB_REQUIRE(epi != AB_EPI_ADD || aux, "dense_gemm: add epilogue without addend");
+    AB_REQUIRE(((uintptr_t)c % 16) == 0 && (aux == nullptr || ((uintptr_t)aux % 16) == 0), "dense_gemm: output / addend must be 16-byte aligned");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.K = K; p.E = 1;
+    p.bn = pick_bn(N, mode == MODE_NN);
+    p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
+    p.epi = epi; p.c_f32 = c_dtype == AB_F32;
+    p.bias = bias; p.aux = aux; p.c = c;
+    p.rows_valid = S;
+    p.dense_m_tiles = (int)ab_ceil_div(S, BM);
+    CUtensorMap ta, tb;
+    if (int e = make_map2(&ta, A, (uint64_t)K, (uint64_t)S, BK, BM)) return e;
+    const int64_t tiles = (int64_t)p.dense_m_tiles * p.num_n_tiles;
+    if (mode == MODE_NT) {
+        if (int e = make_map2(&tb, W, (uint64_t)K, (uint64_t)N, BK, (uint32_t)p.bn)) return e;
+        return launch<MODE_NT>(ta, tb, p, tiles, stream);
+    }
+    if (int e = make_map2(&tb, W, (uint64_t)N, (uint64_t)K, 64, BK)) return e;
+    return launch<MODE_NN>(ta, tb, p, tiles, stream);
+}
+}  // namespace
+
+extern "C" int ab_dense_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* C, int64_t S, int N, int K,
+                                int epi, int c_dtype, cudaStream_t stream) {
+    return dense_rows(MODE_NT, A, W, bias, aux, C, S, N, K, epi, c_dtype, stream);
+}
+
+extern "C" int ab_dense_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* C, int64_t S, int N, int K,
+                                int epi, int c_dtype, cudaStream_t stream) {
+    return dense_rows(MODE_NN, A, W, bias, aux, C, S, N, K, epi, c_dtype, stream);
+}
+
+extern "C" int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, int64_t S, int M, int N, cudaStream_t stream) {
+    AB_REQUIRE(S > 0 && M > 0 && N > 0 && M % 8 == 0 && N % 8 == 0, "dense_gemm_tn: S (%lld) must be positive, M (%d) and N (%d) multiples of 8", (long long)S, M, N);
+    AB_REQUIRE(((uintptr_t)Cw % 16) == 0, "dense_gemm_tn: output pointer must be 16-byte aligned");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.M = M; p.E = 1; p.K = 0;
+    p.bn = pick_bn(N, true);
+    p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
+    p.num_m_tiles = (int)ab_ceil_div(M, BM);
+    p.c_f32 = 1; p.epi = AB_EPI_NONE; p.cw = Cw;
+    p.tn_nsrc = 1; p.tn_rows = S;
+    CUtensorMap ta, tb;
+    if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)S, 64, BK)) return e;
+    if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)S, 64, BK)) return e;
+    return launch<MODE_TN>(ta, tb, p, (int64_t)p.num_m_tiles * p.num_n_tiles, stream);
 }

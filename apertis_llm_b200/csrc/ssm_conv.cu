@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) conv_silu_fwd_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) conv_silu_bwd_kernel(const T* __restrict__ xp, int64_t xp_stride,
                                                             const T* __restrict__ dxa, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, T* __restrict__ dxp,
+                                                            const float* __restrict__ bias, T* __restrict__ dxp, int64_t dxs,
                                                             float* __restrict__ part, int L, int Di, int n_part_rows) {
     constexpr int V = ab_vec16<T>::N;
     const int cv = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) conv_silu_bwd_kernel(const T* __restrict_
         }
         const T* xrow = xp + (size_t)b * L * xp_stride + c0;
         const T* grow = dxa + ((size_t)b * L) * Di + c0;
-        T* orow = dxp + ((size_t)b * L) * Di + c0;
+        T* orow = dxp + ((size_t)b * L) * dxs + c0;
         float win[KC - 1][V];      // xp[u-3], xp[u-2], xp[u-1]
 #pragma unroll
         for (int j = 0; j < KC - 1; ++j) {
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) conv_silu_bwd_kernel(const T* __restrict_
                     acc = fmaf(wr[v][0], dxc[v], acc);
                     o[v] = acc;
                 }
-                *reinterpret_cast<uint4*>(orow + (size_t)t * Di) = ab_vec16<T>::pack(o);
+                *reinterpret_cast<uint4*>(orow + (size_t)t * dxs) = ab_vec16<T>::pack(o);
             }
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -202,7 +202,7 @@ int launch_fwd(const void* xp, int64_t xs, const float* w, const float* bias, vo
 }
 
 template <typename T>
-int launch_bwd(const void* xp, int64_t xs, const void* dxa, const float* w, const float* bias, void* dxp, float* dw,
+int launch_bwd(const void* xp, int64_t xs, const void* dxa, const float* w, const float* bias, void* dxp, int64_t dxs, float* dw,
                float* dbias, float* part, int B, int L, int Di, cudaStream_t st) {
     constexpr int V = ab_vec16<T>::N;
     const int ncv = Di / V;
@@ -211,7 +211,7 @@ int launch_bwd(const void* xp, int64_t xs, const void* dxa, const float* w, cons
     dim3 grid((unsigned)ab_ceil_div(ncv, bx), (unsigned)ab_ceil_div(L, TT * ROWS_PER_CTA), B);
     const size_t smem = (size_t)ROWS_PER_CTA * bx * V * 5 * sizeof(float);
     const int n_part = grid.y * grid.z;
-    conv_silu_bwd_kernel<T><<<grid, block, smem, st>>>((const T*)xp, xs, (const T*)dxa, w, bias, (T*)dxp, part, L, Di, n_part);
+    conv_silu_bwd_kernel<T><<<grid, block, smem, st>>>((const T*)xp, xs, (const T*)dxa, w, bias, (T*)dxp, dxs, part, L, Di, n_part);
     AB_LAUNCH_CHECK();
     conv_reduce_kernel<<<(unsigned)ab_ceil_div(Di * 5, 128), 128, 0, st>>>(part, n_part, Di, dw, dbias);
     AB_LAUNCH_CHECK();
@@ -241,11 +241,13 @@ extern "C" size_t ab_causal_conv1d_silu_bwd_workspace_bytes(int B, int L, int Di
 }
 
 extern "C" int ab_causal_conv1d_silu_bwd(const void* xp, int64_t xp_stride, const void* dxa, const float* w,
-                                         const float* bias, void* dxp, float* dw, float* dbias, void* ws, size_t ws_bytes,
-                                         int B, int L, int Di, int Kc, int dtype, cudaStream_t stream) {
+                                         const float* bias, void* dxp, int64_t dxp_stride, float* dw, float* dbias, void* ws,
+                                         size_t ws_bytes, int B, int L, int Di, int Kc, int dtype, cudaStream_t stream) {
     if (int e = check_args(B, L, Di, Kc, xp_stride, dtype)) return e;
+    if (int e = check_args(B, L, Di, Kc, dxp_stride, dtype)) return e;
+    AB_REQUIRE(dxp_stride >= Di, "causal_conv1d_bwd: dxp row stride smaller than the row");
     AB_REQUIRE(ws_bytes >= ab_causal_conv1d_silu_bwd_workspace_bytes(B, L, Di), "causal_conv1d_bwd: workspace too small");
     return dtype == AB_F32
-               ? launch_bwd<float>(xp, xp_stride, dxa, w, bias, dxp, dw, dbias, (float*)ws, B, L, Di, stream)
-               : launch_bwd<__nv_bfloat16>(xp, xp_stride, dxa, w, bias, dxp, dw, dbias, (float*)ws, B, L, Di, stream);
+               ? launch_bwd<float>(xp, xp_stride, dxa, w, bias, dxp, dxp_stride, dw, dbias, (float*)ws, B, L, Di, stream)
+               : launch_bwd<__nv_bfloat16>(xp, xp_stride, dxa, w, bias, dxp, dxp_stride, dw, dbias, (float*)ws, B, L, Di, stream);
 }

@@ -23,6 +23,8 @@
 //
 // The forward saves the state entering every group of 8 tokens (hck, fp32, +0.5 B per element) so that the backward
 // needs no forward prefix of its own and recomputes states 8 at a time in registers.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -55,26 +57,11 @@ __device__ __forceinline__ f2 f2_sigmoid(f2 z) {
     }
 }
 
-// ---- global memory access: channel pairs with an L2 eviction policy ------------------------------------------------
+// ---- channel pairs in registers / shared memory ----------------------------------------------------------------------
 template <typename T> struct Raw;
 template <> struct Raw<__nv_bfloat16> { typedef uint32_t type; };
 template <> struct Raw<float> { typedef f2 type; };
 
-__device__ __forceinline__ uint64_t policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-__device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
-
-__device__ __forceinline__ void ldg_raw(uint32_t& r, const void* p, uint64_t pol) {
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void ldg_raw(f2& r, const void* p, uint64_t pol) {
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void stg_raw(void* p, uint32_t v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void stg_raw(void* p, f2 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
-}
 __device__ __forceinline__ f2 up(uint32_t r) { return f2_pack(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
 __device__ __forceinline__ f2 up(f2 r) { return r; }
 template <typename T> __device__ __forceinline__ typename Raw<T>::type down(f2 v);
@@ -87,32 +74,35 @@ template <> __device__ __forceinline__ uint32_t down<__nv_bfloat16>(f2 v) {
 }
 template <> __device__ __forceinline__ f2 down<float>(f2 v) { return v; }
 
-// pair access of row `t` of a [rows, stride] array (base already points at this lane's channel pair).  Loads are
-// unconditional: the callers clamp rows past the sequence to its last row and lanes past the width alias channel 0, so
-// every address is valid and no load sits behind a divergent branch; stores carry their predicate inside the instruction.
-template <typename T>
-__device__ __forceinline__ typename Raw<T>::type ld_pair(const T* base, int stride, int t, uint64_t pol) {
-    typename Raw<T>::type r;
-    ldg_raw(r, base + (int64_t)t * stride, pol);
-    return r;
+// ---- TMA: 3-D tiled loads / stores of [channels, tokens, batch] boxes with an L2 eviction policy -------------------------
+__device__ __forceinline__ uint64_t policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int t, int b, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(t), "r"(b), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void stg_pred(void* p, uint32_t v, uint64_t pol, bool ok) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.L2::cache_hint.b32 [%0], %1, %2;\n\t}" ::"l"(p), "r"(v), "l"(pol), "r"((int)ok) : "memory");
+__device__ __forceinline__ void tma_store(const CUtensorMap* m, uint32_t src, int c, int t, int b, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c), "r"(t), "r"(b), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void stg_pred(void* p, f2 v, uint64_t pol, bool ok) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.L2::cache_hint.b64 [%0], %1, %2;\n\t}" ::"l"(p), "l"(v), "l"(pol), "r"((int)ok) : "memory");
+__device__ __forceinline__ void mbar_init_u32(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-template <typename T>
-__device__ __forceinline__ void st_pair(T* base, int stride, int t, bool ok, f2 v, uint64_t pol) {
-    stg_pred(base + (int64_t)t * stride, down<T>(v), pol, ok);
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
 }
-template <typename R> __device__ __forceinline__ R keep_if(R v, bool ok) { return ok ? v : (R)0; }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 constexpr int RG = 8;                 // tokens per group: spacing of the saved states, unit of the delta shuffles
 constexpr int RSEG = 32;              // chunks per level-1 segment of a round's prefix
-constexpr int RWARPS = 8;             // warps per CTA (warps are independent: the CTA is only an occupancy unit)
 constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;
 
 struct RoundsParams {
@@ -254,19 +244,60 @@ __device__ __forceinline__ f2 incoming_state(const RoundsParams& p, int r, int c
 }
 
 // ====================================================================================================================
+// per-warp TMA pipeline
+//   Every warp owns a private ring of NST stages in shared memory and one mbarrier per stage; lane 0 issues the TMA loads
+//   (boxes of 64 channels x RG tokens per operand, rows / channels past the tensor are zero-filled by the hardware, which
+//   is exactly the masking the recurrences need) and, after the group is computed, the TMA stores of the results, which
+//   are written IN PLACE over the consumed operands (the store clips what lies past the tensor).  No address arithmetic,
+//   no predicates and no bounds checks remain in the token loops: shared-memory offsets are immediates.
+// ====================================================================================================================
+constexpr int NST = 3;                // stages per warp: group g computes from stage g % 3 while g + 1, g + 2 are in flight
+
+template <typename T> struct Tile {
+    static constexpr int ROW_PAIRS = 32;                       // a row = 64 channels = 32 lane pairs
+    static constexpr int BYTES = RG * 64 * (int)sizeof(T);     // one operand of one group
+};
+
+struct Pipe {
+    unsigned char* base;     // generic address of stage 0
+    uint32_t sbase;          // shared-space address of stage 0
+    uint32_t bar;            // shared-space address of mbarrier 0
+    uint32_t phases;         // bit s: parity the next wait on stage s expects
+    uint32_t stage_bytes;
+    __device__ __forceinline__ uint32_t saddr(int st, int off) const { return sbase + (uint32_t)st * stage_bytes + (uint32_t)off; }
+    __device__ __forceinline__ unsigned char* gaddr(int st, int off) const { return base + (size_t)st * stage_bytes + off; }
+    __device__ __forceinline__ uint32_t baddr(int st) const { return bar + 8u * (uint32_t)st; }
+    __device__ __forceinline__ void wait(int st) {
+        mbar_wait_u32(baddr(st), (phases >> st) & 1u);
+        phases ^= 1u << st;
+    }
+};
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ typename Raw<T>::type lds_pair(const unsigned char* stage, int arr, int row, int lane) {
+    return reinterpret_cast<const typename Raw<T>::type*>(stage)[(arr * RG + row) * 32 + lane];
+}
+template <typename T>
+__device__ __forceinline__ void sts_pair(unsigned char* stage, int arr, int row, int lane, f2 v) {
+    reinterpret_cast<typename Raw<T>::type*>(stage)[(arr * RG + row) * 32 + lane] = down<T>(v);
+}
+
+// ====================================================================================================================
 // forward
 // ====================================================================================================================
 template <typename T>
 struct FwdCtx {
-    const T *xa, *Bm, *Cm, *z, *dlog;     // this lane's channel pair of row 0 of the sequence
-    T *y, *yssm;
+    const T* dlog;     // this lane's (token lane >> 2, head lane & 3) column of row 0 of the sequence
     float* delta;      // this (sequence, slab)'s [L8, 4] block + head (lane & 3)
     float* hck;        // this sequence's [nck8, Di] block + channel pair
     f2 A2, Dv;
     float bias;        // dt bias of the head this lane computes delta for
     bool cv, hv;       // channel pair valid; head (lane & 3) valid
-    int lane;
-    int L, sx, sbc, sz, sy;     // sequence length and row strides (elements)
+    int lane, L, b, ch0;     // ch0: first channel of the slab
 };
 
 // delta of 8 tokens x 4 heads, one (token, head) per lane; saved for P2 and the backward
@@ -279,158 +310,176 @@ __device__ __forceinline__ float delta_compute(const FwdCtx<T>& c, int dlog_stri
     return d;
 }
 
-// B rows of one group; rows past the sequence read as zero (they must not change the state)
-template <typename T, bool FULL>
-__device__ __forceinline__ void p1_load(const FwdCtx<T>& c, typename Raw<T>::type (&bv)[RG], int tb, uint64_t pol) {
-#pragma unroll
-    for (int j = 0; j < RG; ++j) {
-        if (FULL) bv[j] = ld_pair<T>(c.Bm, c.sbc, tb + j, pol);
-        else bv[j] = keep_if(ld_pair<T>(c.Bm, c.sbc, min(tb + j, c.L - 1), pol), tb + j < c.L);
-    }
-}
+constexpr int P1_ROWS = 4 * RG;       // forward P1 reads B in pieces of 32 tokens (one stage = 4 operand tiles = 32 rows)
 
 template <typename T>
-__device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c, int r, int chain, int slot, int b, uint64_t pol_keep, f2 init) {
-    typedef typename Raw<T>::type raw_t;
+__device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c, Pipe& pp, const CUtensorMap* tm_b32, int r, int chain, int slot,
+                                       uint64_t pol_keep, f2 init) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
     if (slot >= n_r) return;
     const int t0 = (r * p.cpr + slot) * p.Tc;
     const int tend = min(t0 + p.Tc, c.L);
+    const int npieces = (tend - t0 + P1_ROWS - 1) / P1_ROWS;
     const int dls = p.dlog_stride;
+    const int hsel = c.lane >> 3;
+    if (c.lane == 0) {
+        bulk_wait_read<0>();              // stores of the previous P2 have read their stages
+#pragma unroll
+        for (int i = 0; i < NST - 1; ++i)
+            if (i < npieces) {
+                mbar_expect_tx_u32(pp.baddr(i), 4 * Tile<T>::BYTES);
+                tma_load(pp.saddr(i, 0), tm_b32, pp.baddr(i), c.ch0, t0 + i * P1_ROWS, c.b, pol_keep);
+            }
+    }
     f2 S = f2_bcast(0.f);
     float sumd = 0.f;
-    raw_t bv[RG];
-    const int hsel = c.lane >> 3;
-    if (t0 + RG <= c.L) p1_load<T, true>(c, bv, t0, pol_keep);
-    else p1_load<T, false>(c, bv, t0, pol_keep);
-    for (int tb = t0; tb < tend; tb += RG) {
-        const float dmine = delta_compute<T>(c, dls, tb);
-        raw_t nb[RG];
-        const int tn = tb + RG;
-        if (tn < tend) {
-            if (tn + RG <= c.L) p1_load<T, true>(c, nb, tn, pol_keep);
-            else p1_load<T, false>(c, nb, tn, pol_keep);
+    int st = 0;
+    for (int pc = 0; pc < npieces; ++pc) {
+        const int tp = t0 + pc * P1_ROWS;
+        // delta of the piece's groups first (global loads + MUFU) so that it overlaps the wait for the tile
+        float dm[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dm[g] = (tp + g * RG < tend) ? delta_compute<T>(c, dls, tp + g * RG) : 0.f;
+        pp.wait(st);
+        const unsigned char* sb = pp.gaddr(st, 0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (tp + g * RG < tend) {
+#pragma unroll
+                for (int j = 0; j < RG; ++j) {
+                    const float d = __shfl_sync(0xffffffffu, dm[g], j * 4 + hsel);
+                    const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
+                    S = f2_fma(a, S, up(lds_pair<T>(sb, g, j, c.lane)));
+                    sumd += d;
+                }
+            }
         }
+        __syncwarp();
+        if (c.lane == 0 && pc + NST - 1 < npieces) {
+            const int sn = (st + NST - 1) % NST;
+            mbar_expect_tx_u32(pp.baddr(sn), 4 * Tile<T>::BYTES);
+            tma_load(pp.saddr(sn, 0), tm_b32, pp.baddr(sn), c.ch0, tp + (NST - 1) * P1_ROWS, c.b, pol_keep);
+        }
+        st = (st + 1) % NST;
+    }
+    const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
+    float* fin = (p.h_last != nullptr && c.cv) ? p.h_last + (size_t)c.b * p.Di + c.ch0 + 2 * c.lane : nullptr;
+    publish_and_prefix(p, r, chain, slot, n_r, c.lane, P, S, init, fin);
+}
+
+// operand tiles of a forward P2 stage
+constexpr int FA_B = 0, FA_X = 1, FA_C = 2, FA_Z = 3;
+
+template <typename T, bool YSSM>
+__device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c, Pipe& pp, const CUtensorMap* tm_xa, const CUtensorMap* tm_b,
+                                       const CUtensorMap* tm_c, const CUtensorMap* tm_z, const CUtensorMap* tm_y, const CUtensorMap* tm_ys,
+                                       int r, int chain, int slot, uint64_t pol_stream) {
+    const int n_r = min(p.cpr, p.nck - r * p.cpr);
+    if (slot >= n_r) return;
+    const int t0 = (r * p.cpr + slot) * p.Tc;
+    const int tend = min(t0 + p.Tc, c.L);
+    const int ngroups = (tend - t0 + RG - 1) / RG;
+    const int hsel = c.lane >> 3;
+    auto issue = [&](int st, int t) {
+        mbar_expect_tx_u32(pp.baddr(st), 4 * Tile<T>::BYTES);
+        tma_load(pp.saddr(st, FA_B * Tile<T>::BYTES), tm_b, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, FA_X * Tile<T>::BYTES), tm_xa, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, FA_C * Tile<T>::BYTES), tm_c, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, FA_Z * Tile<T>::BYTES), tm_z, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+    };
+    if (c.lane == 0) {
+        bulk_wait_read<0>();
+#pragma unroll
+        for (int i = 0; i < NST - 1; ++i)
+            if (i < ngroups) issue(i, t0 + i * RG);           // in flight during the wait for the prefix
+    }
+    wait_flag(&p.flag[(size_t)r * p.nchains + chain], c.lane);
+    f2 h = incoming_state(p, r, chain, slot, c.lane);
+    float* hck = c.hck + (size_t)(t0 >> 3) * p.Di;
+    const float* dsrc = c.delta + (int64_t)(t0 + (c.lane >> 2)) * 4;
+    int st = 0;
+    for (int g = 0; g < ngroups; ++g) {
+        const int tb = t0 + g * RG;
+        const float dmine = __ldcg(dsrc);
+        dsrc += RG * 4;
+        if (c.cv) {
+            float h0, h1;
+            f2_unpack(h, h0, h1);
+            *reinterpret_cast<float2*>(hck) = make_float2(h0, h1);
+        }
+        hck += p.Di;
+        pp.wait(st);
+        unsigned char* sb = pp.gaddr(st, 0);
 #pragma unroll
         for (int j = 0; j < RG; ++j) {
             const float d = __shfl_sync(0xffffffffu, dmine, j * 4 + hsel);
             const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
-            S = f2_fma(a, S, up(bv[j]));
-            sumd += d;
+            h = f2_fma(a, h, up(lds_pair<T>(sb, FA_B, j, c.lane)));
+            const f2 ys = f2_mul(up(lds_pair<T>(sb, FA_C, j, c.lane)), h);
+            const f2 yv = f2_fma(c.Dv, up(lds_pair<T>(sb, FA_X, j, c.lane)), ys);
+            const f2 zv = up(lds_pair<T>(sb, FA_Z, j, c.lane));
+            sts_pair<T>(sb, FA_X, j, c.lane, f2_mul(yv, f2_mul(zv, f2_sigmoid<T>(zv))));      // y over the consumed x
+            if (YSSM) sts_pair<T>(sb, FA_C, j, c.lane, ys);
         }
-#pragma unroll
-        for (int j = 0; j < RG; ++j) bv[j] = nb[j];
-    }
-    const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
-    float* fin = (p.h_last != nullptr && c.cv) ? p.h_last + (size_t)b * p.Di + (chain % p.nslab) * 64 + 2 * c.lane : nullptr;
-    publish_and_prefix(p, r, chain, slot, n_r, c.lane, P, S, init, fin);
-}
-
-template <typename T>
-struct FwdBuf {
-    typename Raw<T>::type x[4], b[4], c[4], z[4];
-};
-
-// operands of 4 tokens.  Rows past the sequence are clamped to its last row: what they produce is never stored and the
-// state after the last token of the sequence is not used by P2 (h_last comes from the prefix of the P1 aggregates).
-template <typename T, bool FULL>
-__device__ __forceinline__ void fwd_load4(const FwdCtx<T>& c, FwdBuf<T>& f, int t, uint64_t pol) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int tt = FULL ? t + j : min(t + j, c.L - 1);
-        f.b[j] = ld_pair<T>(c.Bm, c.sbc, tt, pol);
-        f.x[j] = ld_pair<T>(c.xa, c.sx, tt, pol);
-        f.c[j] = ld_pair<T>(c.Cm, c.sbc, tt, pol);
-        f.z[j] = ld_pair<T>(c.z, c.sz, tt, pol);
-    }
-}
-template <typename T>
-__device__ __forceinline__ void fwd_load4_any(const FwdCtx<T>& c, FwdBuf<T>& f, int t, uint64_t pol) {
-    if (t + 4 <= c.L) fwd_load4<T, true>(c, f, t, pol);
-    else fwd_load4<T, false>(c, f, t, pol);
-}
-
-template <typename T, bool YSSM>
-__device__ __forceinline__ void fwd_compute4(const FwdCtx<T>& c, const FwdBuf<T>& f, int t, float dmine, int jbase, f2& h, uint64_t pol) {
-    const int hsel = c.lane >> 3;
-    const int nvalid = c.cv ? c.L - t : 0;          // tokens t + j with j < nvalid are stored
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float d = __shfl_sync(0xffffffffu, dmine, (jbase + j) * 4 + hsel);
-        const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
-        h = f2_fma(a, h, up(f.b[j]));
-        const f2 ys = f2_mul(up(f.c[j]), h);
-        const bool ok = j < nvalid;
-        if (YSSM) st_pair<T>(c.yssm, c.sy, t + j, ok, ys, pol);
-        const f2 yv = f2_fma(c.Dv, up(f.x[j]), ys);
-        const f2 zv = up(f.z[j]);
-        const f2 out = f2_mul(yv, f2_mul(zv, f2_sigmoid<T>(zv)));
-        st_pair<T>(c.y, c.sy, t + j, ok, out, pol);
-    }
-}
-
-template <typename T, bool YSSM>
-__device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c, int r, int chain, int slot, uint64_t pol_stream) {
-    const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (slot >= n_r) return;
-    const int t0 = (r * p.cpr + slot) * p.Tc;
-    const int tend = min(t0 + p.Tc, c.L);
-    FwdBuf<T> fa, fb;
-    fwd_load4_any<T>(c, fa, t0, pol_stream);         // in flight during the wait
-    fwd_load4_any<T>(c, fb, t0 + 4, pol_stream);
-    wait_flag(&p.flag[(size_t)r * p.nchains + chain], c.lane);
-    f2 h = incoming_state(p, r, chain, slot, c.lane);
-    const int Di = p.Di;
-    for (int tb = t0; tb < tend; tb += RG) {
-        if (c.cv) {
-            float h0, h1;
-            f2_unpack(h, h0, h1);
-            *reinterpret_cast<float2*>(c.hck + (size_t)(tb >> 3) * Di) = make_float2(h0, h1);
+        fence_async_smem();
+        __syncwarp();
+        if (c.lane == 0) {
+            tma_store(tm_y, pp.saddr(st, FA_X * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+            if (YSSM) tma_store(tm_ys, pp.saddr(st, FA_C * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+            bulk_commit();
+            if (g + NST - 1 < ngroups) {
+                bulk_wait_read<1>();          // the store issued one group ago (from the stage refilled now) has read its tile
+                issue((st + NST - 1) % NST, tb + (NST - 1) * RG);
+            }
         }
-        const float dmine = __ldcg(c.delta + (int64_t)(tb + (c.lane >> 2)) * 4);
-        const bool more = tb + RG < tend;
-        fwd_compute4<T, YSSM>(c, fa, tb, dmine, 0, h, pol_stream);
-        if (more) fwd_load4_any<T>(c, fa, tb + RG, pol_stream);
-        fwd_compute4<T, YSSM>(c, fb, tb + 4, dmine, 4, h, pol_stream);
-        if (more) fwd_load4_any<T>(c, fb, tb + RG + 4, pol_stream);
+        st = (st + 1) % NST;
     }
 }
 
 template <typename T, bool YSSM>
-__global__ void __launch_bounds__(RWARPS * 32, sizeof(T) == 2 ? 3 : 2) scan_rounds_fwd_kernel(const RoundsParams p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(sizeof(T) == 2 ? 768 : 512, 1)
+scan_rounds_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b32,
+                       const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_y,
+                       const __grid_constant__ CUtensorMap tm_ys, const RoundsParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, nwc = blockDim.x >> 5;
+    const int gw = blockIdx.x * nwc + wic;
+    Pipe pp;
+    pp.stage_bytes = 4 * Tile<T>::BYTES;
+    pp.base = smem_raw + (size_t)wic * NST * pp.stage_bytes;
+    pp.sbase = ab_smem_u32(pp.base);
+    pp.bar = ab_smem_u32(smem_raw + (size_t)nwc * NST * pp.stage_bytes) + (uint32_t)wic * NST * 8u;
+    pp.phases = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) mbar_init_u32(pp.baddr(i), 1);
+        ab_fence_mbar_init();
+    }
+    __syncwarp();
     if (gw >= p.nw_used) return;
     const int chain = gw % p.nchains, slot = gw / p.nchains;
     const int b = chain / p.nslab, slab = chain % p.nslab;
     const int c0 = slab * 64 + 2 * lane;
     FwdCtx<T> c;
-    c.lane = lane;
-    c.L = p.L; c.sx = p.xa_stride; c.sbc = p.bc_stride; c.sz = p.z_stride; c.sy = p.y_stride;
+    c.lane = lane; c.L = p.L; c.b = b; c.ch0 = slab * 64;
     c.cv = c0 < p.Di;
     const int head = slab * 4 + (lane & 3);
     c.hv = head < p.H;
     c.bias = (c.hv && p.dt_bias != nullptr) ? p.dt_bias[head] : 0.f;
-    const int cs = c.cv ? c0 : 0;          // lanes past the width alias channel 0 (loads stay valid, nothing is stored)
+    const int cs = c.cv ? c0 : 0;
     c.A2 = c.cv ? f2_pack(-__expf(p.A_log[c0]) * AB_LOG2E, -__expf(p.A_log[c0 + 1]) * AB_LOG2E) : f2_bcast(0.f);
     c.Dv = c.cv ? f2_pack(p.D[c0], p.D[c0 + 1]) : f2_bcast(0.f);
-    const int64_t row0 = (int64_t)b * p.L;
-    c.xa = reinterpret_cast<const T*>(p.xa) + row0 * p.xa_stride + cs;
-    c.Bm = reinterpret_cast<const T*>(p.Bm) + row0 * p.bc_stride + cs;
-    c.Cm = reinterpret_cast<const T*>(p.Cm) + row0 * p.bc_stride + cs;
-    c.z = reinterpret_cast<const T*>(p.z) + row0 * p.z_stride + cs;
-    c.y = reinterpret_cast<T*>(p.y) + row0 * p.y_stride + cs;
-    c.yssm = YSSM ? reinterpret_cast<T*>(p.yssm) + row0 * p.y_stride + cs : nullptr;
-    c.dlog = reinterpret_cast<const T*>(p.dlog) + row0 * p.dlog_stride + (c.hv ? head : 0);
+    c.dlog = reinterpret_cast<const T*>(p.dlog) + (int64_t)b * p.L * p.dlog_stride + (c.hv ? head : 0);
     c.delta = p.delta + (size_t)chain * p.L8 * 4 + (lane & 3);
     c.hck = p.hck + (size_t)b * p.nck8 * p.Di + cs;
     f2 init = f2_bcast(0.f);
     if (p.h0 != nullptr && c.cv) init = f2_pack(p.h0[(size_t)b * p.Di + c0], p.h0[(size_t)b * p.Di + c0 + 1]);
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     for (int r = -1; r < p.nrounds; ++r) {
-        if (r + 1 < p.nrounds) fwd_p1<T>(p, c, r + 1, chain, slot, b, pol_keep, init);
-        if (r >= 0) fwd_p2<T, YSSM>(p, c, r, chain, slot, pol_stream);
+        if (r + 1 < p.nrounds) fwd_p1<T>(p, c, pp, &tm_b32, r + 1, chain, slot, pol_keep, init);
+        if (r >= 0) fwd_p2<T, YSSM>(p, c, pp, &tm_xa, &tm_b, &tm_c, &tm_z, &tm_y, &tm_ys, r, chain, slot, pol_stream);
     }
+    if (lane == 0) bulk_wait_all();
 }
 
 // ====================================================================================================================
@@ -440,118 +489,113 @@ __global__ void __launch_bounds__(RWARPS * 32, sizeof(T) == 2 ? 3 : 2) scan_roun
 //   d abar = E * h_{t-1};  w = d abar * abar;  d delta[head] += sum_c w * A_c;  dA_log_c += w * delta * A_c
 //   d dlog = d delta * sigmoid(dlog) = d delta * (1 - exp(-delta))
 // Chunks are visited from the end of the sequence; the reverse chunk aggregate is F_first = Pr * F_in + Sr.
-// Rows past the sequence: loads are clamped to the last row and dout (dyssm) read as zero, so they hand F on unchanged.
+// Rows past the sequence arrive as zeros (TMA fill): dout = 0 and delta = 0 make them hand F on unchanged.
 // ====================================================================================================================
 template <typename T>
 struct BwdCtx {
-    const T *xa, *Bm, *Cm, *z, *dout, *dyssm;
-    T *dxa, *dBm, *dCm, *dz, *ddlog;
+    T* ddlog;
     const float* delta;
     const float* hck;
     f2 A2, Dv, An;      // An = natural-log A = -exp(A_log)
     bool cv;
-    int lane;
-    int L, sx, sbc, sz, sy, sdx, sdbc, sdz;
+    int lane, L, b, ch0;
 };
 
-template <typename T>
-struct BwdP1Buf {
-    typename Raw<T>::type c[RG], z[RG], g[RG], s[RG];
-};
+// operand tiles of a backward stage (P1 fills C, Z, G (, S); P2 all); the results overwrite B, X, C, Z in place
+constexpr int BA_B = 0, BA_X = 1, BA_C = 2, BA_Z = 3, BA_G = 4, BA_S = 5;
 
-template <typename T, bool YSSM, bool FULL>
-__device__ __forceinline__ void bwd_p1_load(const BwdCtx<T>& c, BwdP1Buf<T>& f, int tb, uint64_t pol) {
-#pragma unroll
-    for (int j = RG - 1; j >= 0; --j) {
-        const int tt = FULL ? tb + j : min(tb + j, c.L - 1);
-        f.c[j] = ld_pair<T>(c.Cm, c.sbc, tt, pol);
-        f.z[j] = ld_pair<T>(c.z, c.sz, tt, pol);
-        f.g[j] = ld_pair<T>(c.dout, c.sy, tt, pol);
-        if (YSSM) f.s[j] = ld_pair<T>(c.dyssm, c.sy, tt, pol);
-        if (!FULL) {
-            f.g[j] = keep_if(f.g[j], tb + j < c.L);
-            if (YSSM) f.s[j] = keep_if(f.s[j], tb + j < c.L);
-        }
-    }
-}
+struct BwdMaps {
+    const CUtensorMap *xa, *b, *c, *z, *g, *s, *dxa, *db, *dc, *dz;
+};
 
 template <typename T, bool YSSM>
-__device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c, int r, int chain, int slot, uint64_t pol_keep) {
+__device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c, Pipe& pp, const BwdMaps& m, int r, int chain, int slot, uint64_t pol_keep) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
     if (slot >= n_r) return;
     const int pos = p.nck - 1 - (r * p.cpr + slot);
     const int t0 = pos * p.Tc;
+    const int tend = min(t0 + p.Tc, c.L);
+    const int ngroups = (tend - t0 + RG - 1) / RG;          // groups are visited last to first
     const int hsel = c.lane >> 3;
+    auto issue = [&](int st, int t) {
+        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 4 : 3) * Tile<T>::BYTES);
+        tma_load(pp.saddr(st, BA_C * Tile<T>::BYTES), m.c, pp.baddr(st), c.ch0, t, c.b, pol_keep);
+        tma_load(pp.saddr(st, BA_Z * Tile<T>::BYTES), m.z, pp.baddr(st), c.ch0, t, c.b, pol_keep);
+        tma_load(pp.saddr(st, BA_G * Tile<T>::BYTES), m.g, pp.baddr(st), c.ch0, t, c.b, pol_keep);
+        if (YSSM) tma_load(pp.saddr(st, BA_S * Tile<T>::BYTES), m.s, pp.baddr(st), c.ch0, t, c.b, pol_keep);
+    };
+    if (c.lane == 0) {
+        bulk_wait_read<0>();
+#pragma unroll
+        for (int i = 0; i < NST - 1; ++i)
+            if (i < ngroups) issue(i, t0 + (ngroups - 1 - i) * RG);
+    }
     f2 F = f2_bcast(0.f);
     float sumd = 0.f;
-    // groups from the last one that starts inside the sequence down to the first
-    int tb = t0 + p.Tc - RG;
-    while (tb >= c.L) tb -= RG;
-    BwdP1Buf<T> f;
-    if (tb + RG <= c.L) bwd_p1_load<T, YSSM, true>(c, f, tb, pol_keep);
-    else bwd_p1_load<T, YSSM, false>(c, f, tb, pol_keep);
-    for (; tb >= t0; tb -= RG) {
-        const float dmine = __ldg(c.delta + (int64_t)(tb + (c.lane >> 2)) * 4);
-        BwdP1Buf<T> nf;
-        if (tb - RG >= t0) bwd_p1_load<T, YSSM, true>(c, nf, tb - RG, pol_keep);       // every group below the last one is full
+    const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (c.lane >> 2)) * 4;
+    int st = 0;
+    for (int g = ngroups - 1; g >= 0; --g) {
+        const float dmine = __ldg(dsrc);
+        dsrc -= RG * 4;
+        pp.wait(st);
+        const unsigned char* sb = pp.gaddr(st, 0);
 #pragma unroll
         for (int j = RG - 1; j >= 0; --j) {
             const float d = __shfl_sync(0xffffffffu, dmine, j * 4 + hsel);
             const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
-            const f2 zv = up(f.z[j]);
-            f2 dys = f2_mul(up(f.g[j]), f2_mul(zv, f2_sigmoid<T>(zv)));
-            if (YSSM) dys = f2_add(dys, up(f.s[j]));
-            F = f2_mul(a, f2_fma(up(f.c[j]), dys, F));
+            const f2 zv = up(lds_pair<T>(sb, BA_Z, j, c.lane));
+            f2 dys = f2_mul(up(lds_pair<T>(sb, BA_G, j, c.lane)), f2_mul(zv, f2_sigmoid<T>(zv)));
+            if (YSSM) dys = f2_add(dys, up(lds_pair<T>(sb, BA_S, j, c.lane)));
+            F = f2_mul(a, f2_fma(up(lds_pair<T>(sb, BA_C, j, c.lane)), dys, F));
             sumd += d;
         }
-        f = nf;
+        __syncwarp();
+        if (c.lane == 0 && g - (NST - 1) >= 0) issue((st + NST - 1) % NST, t0 + (g - (NST - 1)) * RG);
+        st = (st + 1) % NST;
     }
     const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
     publish_and_prefix(p, r, chain, slot, n_r, c.lane, P, F, f2_bcast(0.f), nullptr);
 }
 
-template <typename T>
-struct BwdP2Buf {
-    typename Raw<T>::type b[RG], x[RG], c[RG], z[RG], g[RG], s[RG];
-};
-
-template <typename T, bool YSSM, bool FULL>
-__device__ __forceinline__ void bwd_p2_load(const BwdCtx<T>& c, BwdP2Buf<T>& f, int tb, uint64_t pol) {
-#pragma unroll
-    for (int j = 0; j < RG; ++j) f.b[j] = ld_pair<T>(c.Bm, c.sbc, FULL ? tb + j : min(tb + j, c.L - 1), pol);
-#pragma unroll
-    for (int j = RG - 1; j >= 0; --j) {
-        const int tt = FULL ? tb + j : min(tb + j, c.L - 1);
-        f.g[j] = ld_pair<T>(c.dout, c.sy, tt, pol);
-        f.z[j] = ld_pair<T>(c.z, c.sz, tt, pol);
-        f.c[j] = ld_pair<T>(c.Cm, c.sbc, tt, pol);
-        f.x[j] = ld_pair<T>(c.xa, c.sx, tt, pol);
-        if (YSSM) f.s[j] = ld_pair<T>(c.dyssm, c.sy, tt, pol);
-        if (!FULL) {
-            f.g[j] = keep_if(f.g[j], tb + j < c.L);
-            if (YSSM) f.s[j] = keep_if(f.s[j], tb + j < c.L);
-        }
-    }
-}
-
 template <typename T, bool YSSM>
-__device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c, int r, int chain, int slot, f2& accA, f2& accD, float& accB, uint64_t pol_stream) {
+__device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c, Pipe& pp, const BwdMaps& m, int r, int chain, int slot, f2& accA,
+                                       f2& accD, float& accB, uint64_t pol_stream) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
     if (slot >= n_r) return;
     const int pos = p.nck - 1 - (r * p.cpr + slot);
     const int t0 = pos * p.Tc;
+    const int tend = min(t0 + p.Tc, c.L);
+    const int ngroups = (tend - t0 + RG - 1) / RG;
     const int hsel = c.lane >> 3;
-    const int Di = p.Di;
-    int tb = t0 + p.Tc - RG;
-    while (tb >= c.L) tb -= RG;
-    BwdP2Buf<T> f;
-    if (tb + RG <= c.L) bwd_p2_load<T, YSSM, true>(c, f, tb, pol_stream);       // in flight during the wait
-    else bwd_p2_load<T, YSSM, false>(c, f, tb, pol_stream);
+    auto issue = [&](int st, int t) {
+        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 6 : 5) * Tile<T>::BYTES);
+        tma_load(pp.saddr(st, BA_B * Tile<T>::BYTES), m.b, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, BA_G * Tile<T>::BYTES), m.g, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, BA_Z * Tile<T>::BYTES), m.z, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, BA_C * Tile<T>::BYTES), m.c, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        tma_load(pp.saddr(st, BA_X * Tile<T>::BYTES), m.xa, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        if (YSSM) tma_load(pp.saddr(st, BA_S * Tile<T>::BYTES), m.s, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+    };
+    if (c.lane == 0) {
+        bulk_wait_read<0>();
+#pragma unroll
+        for (int i = 0; i < NST - 1; ++i)
+            if (i < ngroups) issue(i, t0 + (ngroups - 1 - i) * RG);           // in flight during the wait for the prefix
+    }
     wait_flag(&p.flag[(size_t)r * p.nchains + chain], c.lane);
     f2 F = incoming_state(p, r, chain, slot, c.lane);
-    for (; tb >= t0; tb -= RG) {
-        const float2 hp = __ldg(reinterpret_cast<const float2*>(c.hck + (size_t)(tb >> 3) * Di));
-        const float dmine = __ldg(c.delta + (int64_t)(tb + (c.lane >> 2)) * 4);
+    const float* hck = c.hck + (size_t)((t0 >> 3) + ngroups - 1) * p.Di;
+    const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (c.lane >> 2)) * 4;
+    int st = 0;
+    for (int g = ngroups - 1; g >= 0; --g) {
+        const int tb = t0 + g * RG;
+        float2 hp = make_float2(0.f, 0.f);
+        if (c.cv) hp = __ldg(reinterpret_cast<const float2*>(hck));
+        hck -= p.Di;
+        const float dmine = __ldg(dsrc);
+        dsrc -= RG * 4;
+        pp.wait(st);
+        unsigned char* sb = pp.gaddr(st, 0);
         // ---- forward recompute of the 8 states
         f2 a[RG], h[RG + 1];
         float dl[RG];
@@ -560,35 +604,45 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
         for (int j = 0; j < RG; ++j) {
             dl[j] = __shfl_sync(0xffffffffu, dmine, j * 4 + hsel);
             a[j] = f2_ex2(f2_mul(f2_bcast(dl[j]), c.A2));
-            h[j + 1] = f2_fma(a[j], h[j], up(f.b[j]));
+            h[j + 1] = f2_fma(a[j], h[j], up(lds_pair<T>(sb, BA_B, j, c.lane)));
         }
-        // ---- reverse sweep
-        const int nvalid = c.cv ? c.L - tb : 0;
+        // ---- reverse sweep; every result goes over the operand it replaces
         float dd[RG];          // this lane's share (2 channels) of d delta of each token
 #pragma unroll
         for (int j = RG - 1; j >= 0; --j) {
-            const bool ok = j < nvalid;
-            const f2 zv = up(f.z[j]), go = up(f.g[j]), xx = up(f.x[j]), cc = up(f.c[j]);
+            const f2 zv = up(lds_pair<T>(sb, BA_Z, j, c.lane)), go = up(lds_pair<T>(sb, BA_G, j, c.lane));
+            const f2 xx = up(lds_pair<T>(sb, BA_X, j, c.lane)), cc = up(lds_pair<T>(sb, BA_C, j, c.lane));
             const f2 sg = f2_sigmoid<T>(zv);
             const f2 dyv = f2_mul(go, f2_mul(zv, sg));
             const f2 yv = f2_fma(c.Dv, xx, f2_mul(cc, h[j + 1]));
             // silu'(z) = sg * (1 + z * (1 - sg)) = sg * (1 + z - z * sg)
             const f2 dsilu = f2_mul(sg, f2_fma(f2_mul(zv, sg), f2_bcast(-1.f), f2_add(zv, f2_bcast(1.f))));
-            st_pair<T>(c.dz, c.sdz, tb + j, ok, f2_mul(f2_mul(go, yv), dsilu), pol_stream);
-            st_pair<T>(c.dxa, c.sdx, tb + j, ok, f2_mul(dyv, c.Dv), pol_stream);
+            sts_pair<T>(sb, BA_Z, j, c.lane, f2_mul(f2_mul(go, yv), dsilu));
+            sts_pair<T>(sb, BA_X, j, c.lane, f2_mul(dyv, c.Dv));
             accD = f2_fma(dyv, xx, accD);
             f2 dys = dyv;
-            if (YSSM) dys = f2_add(dys, up(f.s[j]));
-            st_pair<T>(c.dCm, c.sdbc, tb + j, ok, f2_mul(dys, h[j + 1]), pol_stream);
+            if (YSSM) dys = f2_add(dys, up(lds_pair<T>(sb, BA_S, j, c.lane)));
+            sts_pair<T>(sb, BA_C, j, c.lane, f2_mul(dys, h[j + 1]));
             const f2 E = f2_fma(cc, dys, F);
-            st_pair<T>(c.dBm, c.sdbc, tb + j, ok, E, pol_stream);
+            sts_pair<T>(sb, BA_B, j, c.lane, E);
             const f2 w = f2_mul(f2_mul(E, h[j]), a[j]);
             dd[j] = f2_hsum(f2_mul(w, c.An));
             accA = f2_fma(w, f2_bcast(dl[j]), accA);
             F = f2_mul(a[j], E);
         }
-        // next group's operands: in flight during the reduction below and the next iteration's recompute
-        if (tb - RG >= t0) bwd_p2_load<T, YSSM, true>(c, f, tb - RG, pol_stream);
+        fence_async_smem();
+        __syncwarp();
+        if (c.lane == 0) {
+            tma_store(m.db, pp.saddr(st, BA_B * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+            tma_store(m.dxa, pp.saddr(st, BA_X * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+            tma_store(m.dc, pp.saddr(st, BA_C * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+            tma_store(m.dz, pp.saddr(st, BA_Z * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+            bulk_commit();
+            if (g - (NST - 1) >= 0) {
+                bulk_wait_read<1>();
+                issue((st + NST - 1) % NST, t0 + (g - (NST - 1)) * RG);
+            }
+        }
         // ---- d delta: sum over the 8 lanes of a head (16 channels), transposing butterfly over the 8 tokens so that lane
         //      (head hsel, k = lane & 7) ends with the total of token k
         {
@@ -611,61 +665,68 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
             const float send = (k & 1) ? s2[0] : s2[1];
             const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);      // token k of head hsel
             const float dk = __shfl_sync(0xffffffffu, dmine, k * 4 + hsel);       // delta of (token k, head hsel)
-            const int head = (chain % p.nslab) * 4 + hsel;
+            const int head = (c.ch0 >> 4) + hsel;
             const int tok = tb + k;
             if (tok < c.L) {
                 if (head < p.H) {
                     // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x))
-                    const float g = tot * (1.0f - ab_ex2(-dk * AB_LOG2E));
-                    accB += g;
-                    c.ddlog[(int64_t)tok * p.ddlog_stride + head] = ab_from_float<T>(g);
+                    const float gq = tot * (1.0f - ab_ex2(-dk * AB_LOG2E));
+                    accB += gq;
+                    c.ddlog[(int64_t)tok * p.ddlog_stride + head] = ab_from_float<T>(gq);
                 }
                 for (int hh = head; hh < p.ddlog_cols; hh += 4)       // padding columns (covered by the last slab's lanes)
                     if (hh >= p.H) c.ddlog[(int64_t)tok * p.ddlog_stride + hh] = ab_from_float<T>(0.f);
             }
         }
+        st = (st + 1) % NST;
     }
 }
 
 template <typename T, bool YSSM>
-__global__ void __launch_bounds__(RWARPS * 32, sizeof(T) == 2 ? 2 : 1) scan_rounds_bwd_kernel(const RoundsParams p) {
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(sizeof(T) == 2 ? 512 : 256, 1)
+scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
+                       const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_s,
+                       const __grid_constant__ CUtensorMap tm_dxa, const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_dc,
+                       const __grid_constant__ CUtensorMap tm_dz, const RoundsParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, nwc = blockDim.x >> 5;
+    const int gw = blockIdx.x * nwc + wic;
+    Pipe pp;
+    pp.stage_bytes = (YSSM ? 6 : 5) * Tile<T>::BYTES;
+    pp.base = smem_raw + (size_t)wic * NST * pp.stage_bytes;
+    pp.sbase = ab_smem_u32(pp.base);
+    pp.bar = ab_smem_u32(smem_raw + (size_t)nwc * NST * pp.stage_bytes) + (uint32_t)wic * NST * 8u;
+    pp.phases = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) mbar_init_u32(pp.baddr(i), 1);
+        ab_fence_mbar_init();
+    }
+    __syncwarp();
     if (gw >= p.nw_used) return;
     const int chain = gw % p.nchains, slot = gw / p.nchains;
     const int b = chain / p.nslab, slab = chain % p.nslab;
     const int c0 = slab * 64 + 2 * lane;
     BwdCtx<T> c;
-    c.lane = lane;
-    c.L = p.L; c.sx = p.xa_stride; c.sbc = p.bc_stride; c.sz = p.z_stride; c.sy = p.y_stride;
-    c.sdx = p.dxa_stride; c.sdbc = p.dbc_stride; c.sdz = p.dz_stride;
+    c.lane = lane; c.L = p.L; c.b = b; c.ch0 = slab * 64;
     c.cv = c0 < p.Di;
     const int cs = c.cv ? c0 : 0;
     const float a0 = c.cv ? -__expf(p.A_log[c0]) : 0.f, a1 = c.cv ? -__expf(p.A_log[c0 + 1]) : 0.f;
     c.An = f2_pack(a0, a1);
     c.A2 = f2_pack(a0 * AB_LOG2E, a1 * AB_LOG2E);
     c.Dv = c.cv ? f2_pack(p.D[c0], p.D[c0 + 1]) : f2_bcast(0.f);
-    const int64_t row0 = (int64_t)b * p.L;
-    c.xa = reinterpret_cast<const T*>(p.xa) + row0 * p.xa_stride + cs;
-    c.Bm = reinterpret_cast<const T*>(p.Bm) + row0 * p.bc_stride + cs;
-    c.Cm = reinterpret_cast<const T*>(p.Cm) + row0 * p.bc_stride + cs;
-    c.z = reinterpret_cast<const T*>(p.z) + row0 * p.z_stride + cs;
-    c.dout = reinterpret_cast<const T*>(p.dout) + row0 * p.y_stride + cs;
-    c.dyssm = YSSM ? reinterpret_cast<const T*>(p.dyssm) + row0 * p.y_stride + cs : nullptr;
-    c.dxa = reinterpret_cast<T*>(p.dxa) + row0 * p.dxa_stride + cs;
-    c.dBm = reinterpret_cast<T*>(p.dBm) + row0 * p.dbc_stride + cs;
-    c.dCm = reinterpret_cast<T*>(p.dCm) + row0 * p.dbc_stride + cs;
-    c.dz = reinterpret_cast<T*>(p.dz) + row0 * p.dz_stride + cs;
-    c.ddlog = reinterpret_cast<T*>(p.ddlog) + row0 * p.ddlog_stride;
+    c.ddlog = reinterpret_cast<T*>(p.ddlog) + (int64_t)b * p.L * p.ddlog_stride;
     c.delta = p.delta + (size_t)chain * p.L8 * 4 + (lane & 3);
     c.hck = p.hck + (size_t)b * p.nck8 * p.Di + cs;
+    BwdMaps m{&tm_xa, &tm_b, &tm_c, &tm_z, &tm_g, &tm_s, &tm_dxa, &tm_db, &tm_dc, &tm_dz};
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     f2 accA = f2_bcast(0.f), accD = f2_bcast(0.f);
     float accB = 0.f;
     for (int r = -1; r < p.nrounds; ++r) {
-        if (r + 1 < p.nrounds) bwd_p1<T, YSSM>(p, c, r + 1, chain, slot, pol_keep);
-        if (r >= 0) bwd_p2<T, YSSM>(p, c, r, chain, slot, accA, accD, accB, pol_stream);
+        if (r + 1 < p.nrounds) bwd_p1<T, YSSM>(p, c, pp, m, r + 1, chain, slot, pol_keep);
+        if (r >= 0) bwd_p2<T, YSSM>(p, c, pp, m, r, chain, slot, accA, accD, accB, pol_stream);
     }
+    if (lane == 0) bulk_wait_all();
     {
         // dA_log = A * sum(w * delta): accA holds sum(w * delta)
         const f2 da = f2_mul(accA, c.An);
@@ -714,35 +775,24 @@ __global__ void scan_rounds_param_reduce_kernel(const float4* __restrict__ part,
 
 // ---- host ----------------------------------------------------------------------------------------------------------
 struct RoundsCfg {
-    int nslab, nchains, nw, cpr, nw_used, Tc, nck, nrounds, nseg, nck8, L8;
-    size_t off_agg, off_segagg, off_segcarry, off_carry, off_cnt, cnt_bytes, off_part, off_part_b, total;
+    int nslab, nchains, wpc, nw, cpr, nw_used, Tc, nck, nrounds, nseg, nck8, L8;
+    size_t smem, off_agg, off_segagg, off_segcarry, off_carry, off_cnt, cnt_bytes, off_part, off_part_b, total;
 };
 
-template <typename K>
-int occupancy_of(K kernel, int* out) {
-    int n = 0;
-    AB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, RWARPS * 32, 0));
-    *out = n < 1 ? 1 : n;
-    return AB_OK;
-}
+constexpr size_t SMEM_MAX = 227 * 1024;
 
-int ctas_per_sm(int dtype, bool bwd, bool yssm, int* out) {
-    static int cache[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
-    int& slot = cache[dtype == AB_F32 ? 0 : 1][bwd ? 1 : 0][yssm ? 1 : 0];
-    if (slot == 0) {
-        int n = 0, e;
-        if (dtype == AB_F32) {
-            if (!bwd) e = yssm ? occupancy_of(scan_rounds_fwd_kernel<float, true>, &n) : occupancy_of(scan_rounds_fwd_kernel<float, false>, &n);
-            else e = yssm ? occupancy_of(scan_rounds_bwd_kernel<float, true>, &n) : occupancy_of(scan_rounds_bwd_kernel<float, false>, &n);
-        } else {
-            if (!bwd) e = yssm ? occupancy_of(scan_rounds_fwd_kernel<__nv_bfloat16, true>, &n) : occupancy_of(scan_rounds_fwd_kernel<__nv_bfloat16, false>, &n);
-            else e = yssm ? occupancy_of(scan_rounds_bwd_kernel<__nv_bfloat16, true>, &n) : occupancy_of(scan_rounds_bwd_kernel<__nv_bfloat16, false>, &n);
-        }
-        if (e) return e;
-        slot = n;
-    }
-    *out = slot;
-    return AB_OK;
+// warps per CTA (one CTA per SM, warps are independent): as many as the shared-memory rings and the register file admit
+void warps_per_cta(int dtype, bool bwd, bool yssm, int warp_cap, int* wpc, size_t* smem) {
+    const int es = dtype == AB_F32 ? 4 : 2;
+    const size_t tile = (size_t)RG * 64 * es;
+    const size_t per_warp = (size_t)NST * (bwd ? (yssm ? 6 : 5) : 4) * tile + NST * 8;
+    const int reg_cap = bwd ? (es == 2 ? 16 : 8) : (es == 2 ? 24 : 16);       // the kernels' __launch_bounds__
+    int w = (int)((SMEM_MAX - 1024) / per_warp);
+    if (w > reg_cap) w = reg_cap;
+    if (warp_cap > 0 && w > warp_cap) w = warp_cap;
+    if (w < 1) w = 1;
+    *wpc = w;
+    *smem = (size_t)w * per_warp + 128;
 }
 
 // Chunk length: few, well-filled rounds (the grid is persistent: a partly filled last round idles warps), at least two
@@ -752,21 +802,22 @@ int choose_tc(int L, int cpr, int tc_hint) {
     if (tc_hint >= RG) return (tc_hint / RG) * RG;
     int best = RG;
     double best_score = -1.0;
-    for (int tc = RG; tc <= 64; tc += RG) {
+    for (int tc = RG; tc <= 128; tc += RG) {
         const int nck = (int)ab_ceil_div(L, tc);
         const int rounds = (int)ab_ceil_div(nck, cpr);
         double score = (double)L / ((double)rounds * cpr * tc);            // fill
-        score *= (double)tc / (tc + 3.0);                                  // per-chunk overhead ~ 3 tokens of work
+        score *= (double)tc / (tc + 4.0);                                  // per-chunk overhead ~ 4 tokens of work
         if (rounds == 1 && nck > 1) score *= 0.9;                          // exposed prefix
         if (score > best_score) { best_score = score; best = tc; }
     }
     return best;
 }
 
-int make_cfg(int B, int L, int Di, int warps_per_sm_cap, int tc_hint, RoundsCfg& c) {
+int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap, int tc_hint, RoundsCfg& c) {
     c.nslab = (int)ab_ceil_div(Di, 64);
     c.nchains = B * c.nslab;
-    c.nw = ab_num_sms() * warps_per_sm_cap;
+    warps_per_cta(dtype, bwd, yssm, warp_cap, &c.wpc, &c.smem);
+    c.nw = ab_num_sms() * c.wpc;
     AB_REQUIRE(c.nchains <= c.nw, "selective scan: %d chains exceed the %d resident warps; split the batch", c.nchains, c.nw);
     c.cpr = c.nw / c.nchains;
     c.nck8 = (int)ab_ceil_div(L, RG);
@@ -816,13 +867,45 @@ int common_checks(const char* who, int B, int L, int Di, int H, int dtype) {
     return AB_OK;
 }
 
-int resident_warps(int dtype, bool bwd, bool yssm, int* wps) {
-    int ctas = 0;
-    if (int e = ctas_per_sm(dtype, bwd, yssm, &ctas)) return e;
-    int w = ctas * RWARPS;
-    if (g_warp_cap > 0 && w > g_warp_cap) w = (g_warp_cap / RWARPS) * RWARPS;
-    if (w < RWARPS) w = RWARPS;
-    *wps = w;
+// 3-D tensor map over [B, L, Di] rows (row stride in elements), box = 64 channels x `rows` tokens.  Encoding costs a few
+// microseconds of host time per map and a launch uses up to ten: recently used maps are kept (a training loop presents the
+// same buffers again and again through torch's caching allocator).
+struct MapKey {
+    const void* base; int dtype, B, L, Di, rows; int64_t stride;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && dtype == o.dtype && B == o.B && L == o.L && Di == o.Di && rows == o.rows && stride == o.stride;
+    }
+};
+constexpr int MAP_CACHE = 128;
+struct MapCache { MapKey key[MAP_CACHE]; CUtensorMap map[MAP_CACHE]; int used = 0, next = 0; };
+MapCache g_maps;
+std::mutex g_maps_mutex;
+
+int map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di, int64_t stride, int rows) {
+    const int es = dtype == AB_F32 ? 4 : 2;
+    AB_REQUIRE(((uintptr_t)base % 16) == 0 && (stride * es) % 16 == 0 && stride >= Di,
+               "selective scan: activations must be 16-byte aligned with a 16-byte aligned row stride >= Di (stride %lld elements)", (long long)stride);
+    const MapKey k{base, dtype, B, L, Di, rows, stride};
+    {
+        std::lock_guard<std::mutex> g(g_maps_mutex);
+        for (int i = 0; i < g_maps.used; ++i)
+            if (g_maps.key[i] == k) { *m = g_maps.map[i]; return AB_OK; }
+    }
+    uint64_t dims[3] = {(uint64_t)Di, (uint64_t)L, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)stride * es, (uint64_t)stride * es * L};
+    uint32_t box[3] = {64u, (uint32_t)rows, 1u};
+    if (int e = ab_encode_tmap(m, dtype == AB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    std::lock_guard<std::mutex> g(g_maps_mutex);
+    const int slot = g_maps.used < MAP_CACHE ? g_maps.used++ : (g_maps.next++ % MAP_CACHE);
+    g_maps.key[slot] = k;
+    g_maps.map[slot] = *m;
+    return AB_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    AB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return AB_OK;
 }
 
@@ -839,10 +922,8 @@ extern "C" int ab_ssm_scan_plan(int B, int L, int Di, int dtype, int64_t* state_
     size_t total = 0;
     for (int bwd = 0; bwd < 2; ++bwd)
         for (int ys = 0; ys < 2; ++ys) {
-            int wps = 0;
-            if (int e = resident_warps(dtype, bwd != 0, ys != 0, &wps)) return e;
             RoundsCfg c;
-            if (int e = make_cfg(B, L, Di, wps, bwd ? g_tc_hint_bwd : g_tc_hint_fwd, c)) return e;
+            if (int e = make_cfg(B, L, Di, dtype, bwd != 0, ys != 0, g_warp_cap, bwd ? g_tc_hint_bwd : g_tc_hint_fwd, c)) return e;
             if (c.total > total) total = c.total;
         }
     const int64_t nck8 = ab_ceil_div(L, RG), nslab = ab_ceil_div(Di, 64);
@@ -864,29 +945,39 @@ extern "C" int ab_ssm_scan_fwd(const void* xa, int64_t xa_stride, const void* dl
     AB_REQUIRE((xa_stride | bc_stride | z_stride | dlog_stride) < (1 << 30), "ssm_scan_fwd: row strides must be below 2^30 elements");
     AB_REQUIRE(((uintptr_t)xa | (uintptr_t)Bm | (uintptr_t)Cm | (uintptr_t)z | (uintptr_t)y | (uintptr_t)y_ssm) % (2 * es) == 0,
                "ssm_scan_fwd: activations must be aligned to a channel pair");
-    int wps = 0;
-    if (int e = resident_warps(dtype, false, y_ssm != nullptr, &wps)) return e;
     RoundsCfg c;
-    if (int e = make_cfg(B, L, Di, wps, g_tc_hint_fwd, c)) return e;
+    if (int e = make_cfg(B, L, Di, dtype, false, y_ssm != nullptr, g_warp_cap, g_tc_hint_fwd, c)) return e;
     AB_REQUIRE(ws_bytes >= c.total, "ssm_scan_fwd: workspace too small (%zu < %zu)", ws_bytes, c.total);
     RoundsParams p;
     memset(&p, 0, sizeof(p));
     fill_sync(p, c, ws);
     p.B = B; p.L = L; p.Di = Di; p.H = H;
-    p.xa = xa; p.dlog = dlog; p.Bm = Bm; p.Cm = Cm; p.z = z; p.y = y; p.yssm = y_ssm;
-    p.xa_stride = (int)xa_stride; p.dlog_stride = (int)dlog_stride; p.bc_stride = (int)bc_stride; p.z_stride = (int)z_stride; p.y_stride = Di;
+    p.dlog = dlog; p.dlog_stride = (int)dlog_stride;
     p.dt_bias = dt_bias; p.A_log = A_log; p.D = D; p.h0 = h0; p.h_last = h_last;
     p.hck = state;
     p.delta = state + (size_t)B * c.nck8 * Di;
+    CUtensorMap m_xa, m_b, m_b32, m_c, m_z, m_y, m_ys;
+    if (int e = map3(&m_xa, xa, dtype, B, L, Di, xa_stride, RG)) return e;
+    if (int e = map3(&m_b, Bm, dtype, B, L, Di, bc_stride, RG)) return e;
+    if (int e = map3(&m_b32, Bm, dtype, B, L, Di, bc_stride, P1_ROWS)) return e;
+    if (int e = map3(&m_c, Cm, dtype, B, L, Di, bc_stride, RG)) return e;
+    if (int e = map3(&m_z, z, dtype, B, L, Di, z_stride, RG)) return e;
+    if (int e = map3(&m_y, y, dtype, B, L, Di, Di, RG)) return e;
+    m_ys = m_y;
+    if (y_ssm) { if (int e = map3(&m_ys, y_ssm, dtype, B, L, Di, Di, RG)) return e; }
     AB_CHECK_CUDA(cudaMemsetAsync(p.cnt1, 0, c.cnt_bytes, stream));
-    const unsigned grid = (unsigned)ab_ceil_div(c.nw_used, RWARPS);
+    const unsigned grid = (unsigned)ab_ceil_div(c.nw_used, c.wpc), block = (unsigned)c.wpc * 32;
+#define AB_LAUNCH_FWD(T, YS)                                                                                              \
+    do {                                                                                                                 \
+        if (int e = set_smem(scan_rounds_fwd_kernel<T, YS>, c.smem)) return e;                                           \
+        scan_rounds_fwd_kernel<T, YS><<<grid, block, c.smem, stream>>>(m_xa, m_b, m_b32, m_c, m_z, m_y, m_ys, p);        \
+    } while (0)
     if (dtype == AB_F32) {
-        if (y_ssm) scan_rounds_fwd_kernel<float, true><<<grid, RWARPS * 32, 0, stream>>>(p);
-        else scan_rounds_fwd_kernel<float, false><<<grid, RWARPS * 32, 0, stream>>>(p);
+        if (y_ssm) AB_LAUNCH_FWD(float, true); else AB_LAUNCH_FWD(float, false);
     } else {
-        if (y_ssm) scan_rounds_fwd_kernel<__nv_bfloat16, true><<<grid, RWARPS * 32, 0, stream>>>(p);
-        else scan_rounds_fwd_kernel<__nv_bfloat16, false><<<grid, RWARPS * 32, 0, stream>>>(p);
+        if (y_ssm) AB_LAUNCH_FWD(__nv_bfloat16, true); else AB_LAUNCH_FWD(__nv_bfloat16, false);
     }
+#undef AB_LAUNCH_FWD
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
@@ -907,32 +998,42 @@ extern "C" int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm
     AB_REQUIRE((xa_stride | bc_stride | z_stride | dxa_stride | dbc_stride | dz_stride | ddlog_stride) < (1 << 30), "ssm_scan_bwd: row strides must be below 2^30 elements");
     AB_REQUIRE(((uintptr_t)xa | (uintptr_t)Bm | (uintptr_t)Cm | (uintptr_t)z | (uintptr_t)dout | (uintptr_t)dyssm | (uintptr_t)dxa | (uintptr_t)dBm |
                 (uintptr_t)dCm | (uintptr_t)dz) % (2 * es) == 0, "ssm_scan_bwd: activations must be aligned to a channel pair");
-    int wps = 0;
-    if (int e = resident_warps(dtype, true, dyssm != nullptr, &wps)) return e;
     RoundsCfg c;
-    if (int e = make_cfg(B, L, Di, wps, g_tc_hint_bwd, c)) return e;
+    if (int e = make_cfg(B, L, Di, dtype, true, dyssm != nullptr, g_warp_cap, g_tc_hint_bwd, c)) return e;
     AB_REQUIRE(ws_bytes >= c.total, "ssm_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, c.total);
     RoundsParams p;
     memset(&p, 0, sizeof(p));
     fill_sync(p, c, ws);
     p.B = B; p.L = L; p.Di = Di; p.H = H;
-    p.xa = xa; p.Bm = Bm; p.Cm = Cm; p.z = z; p.dout = dout; p.dyssm = dyssm;
-    p.dxa = dxa; p.dBm = dBm; p.dCm = dCm; p.dz = dz; p.ddlog = ddlog;
-    p.xa_stride = (int)xa_stride; p.bc_stride = (int)bc_stride; p.z_stride = (int)z_stride; p.y_stride = Di;
-    p.dxa_stride = (int)dxa_stride; p.dbc_stride = (int)dbc_stride; p.dz_stride = (int)dz_stride; p.ddlog_stride = (int)ddlog_stride;
+    p.ddlog = ddlog; p.ddlog_stride = (int)ddlog_stride; p.ddlog_cols = ddlog_cols;
     p.A_log = A_log; p.D = D;
-    p.ddlog_cols = ddlog_cols;
     p.hck = const_cast<float*>(state);
     p.delta = const_cast<float*>(state) + (size_t)B * c.nck8 * Di;
+    CUtensorMap m_xa, m_b, m_c, m_z, m_g, m_s, m_dxa, m_db, m_dc, m_dz;
+    if (int e = map3(&m_xa, xa, dtype, B, L, Di, xa_stride, RG)) return e;
+    if (int e = map3(&m_b, Bm, dtype, B, L, Di, bc_stride, RG)) return e;
+    if (int e = map3(&m_c, Cm, dtype, B, L, Di, bc_stride, RG)) return e;
+    if (int e = map3(&m_z, z, dtype, B, L, Di, z_stride, RG)) return e;
+    if (int e = map3(&m_g, dout, dtype, B, L, Di, Di, RG)) return e;
+    m_s = m_g;
+    if (dyssm) { if (int e = map3(&m_s, dyssm, dtype, B, L, Di, Di, RG)) return e; }
+    if (int e = map3(&m_dxa, dxa, dtype, B, L, Di, dxa_stride, RG)) return e;
+    if (int e = map3(&m_db, dBm, dtype, B, L, Di, dbc_stride, RG)) return e;
+    if (int e = map3(&m_dc, dCm, dtype, B, L, Di, dbc_stride, RG)) return e;
+    if (int e = map3(&m_dz, dz, dtype, B, L, Di, dz_stride, RG)) return e;
     AB_CHECK_CUDA(cudaMemsetAsync(p.cnt1, 0, c.cnt_bytes, stream));
-    const unsigned grid = (unsigned)ab_ceil_div(c.nw_used, RWARPS);
+    const unsigned grid = (unsigned)ab_ceil_div(c.nw_used, c.wpc), block = (unsigned)c.wpc * 32;
+#define AB_LAUNCH_BWD(T, YS)                                                                                              \
+    do {                                                                                                                 \
+        if (int e = set_smem(scan_rounds_bwd_kernel<T, YS>, c.smem)) return e;                                           \
+        scan_rounds_bwd_kernel<T, YS><<<grid, block, c.smem, stream>>>(m_xa, m_b, m_c, m_z, m_g, m_s, m_dxa, m_db, m_dc, m_dz, p); \
+    } while (0)
     if (dtype == AB_F32) {
-        if (dyssm) scan_rounds_bwd_kernel<float, true><<<grid, RWARPS * 32, 0, stream>>>(p);
-        else scan_rounds_bwd_kernel<float, false><<<grid, RWARPS * 32, 0, stream>>>(p);
+        if (dyssm) AB_LAUNCH_BWD(float, true); else AB_LAUNCH_BWD(float, false);
     } else {
-        if (dyssm) scan_rounds_bwd_kernel<__nv_bfloat16, true><<<grid, RWARPS * 32, 0, stream>>>(p);
-        else scan_rounds_bwd_kernel<__nv_bfloat16, false><<<grid, RWARPS * 32, 0, stream>>>(p);
+        if (dyssm) AB_LAUNCH_BWD(__nv_bfloat16, true); else AB_LAUNCH_BWD(__nv_bfloat16, false);
     }
+#undef AB_LAUNCH_BWD
     AB_LAUNCH_CHECK();
     scan_rounds_param_reduce_kernel<<<c.nslab, 256, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, Di, H, c.nslab, c.nw_used);
     AB_LAUNCH_CHECK();

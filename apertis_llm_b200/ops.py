@@ -227,7 +227,7 @@ class _CausalConv1dSiLU(torch.autograd.Function):
         db = torch.empty(Di, dtype=torch.float32, device=xp.device)
         nws = query("ab_causal_conv1d_silu_bwd_workspace_bytes", B, L, Di)
         ws = torch.empty(nws, dtype=torch.uint8, device=xp.device)
-        call("ab_causal_conv1d_silu_bwd", ptr(xp), _row_stride(xp), ptr(dxa), ptr(w), ptr(b), ptr(dxp), ptr(dw), ptr(db),
+        call("ab_causal_conv1d_silu_bwd", ptr(xp), _row_stride(xp), ptr(dxa), ptr(w), ptr(b), ptr(dxp), Di, ptr(dw), ptr(db),
              ptr(ws), nws, B, L, Di, Kc, dt(xp), stream_ptr())
         return dxp, dw.reshape(ctx.wshape).to(ctx.wdtype), db.to(ctx.bdtype)
 
@@ -415,6 +415,193 @@ def selective_scan_fused(xa, prm, dt_bias, z, A_log, D, H, h0=None, want_yssm=Fa
     """Scan over the fused projection output prm [B,L,Hp+2Di] = [dt (no bias) | B | C] (see _SelectiveScanRounds)."""
     return _SelectiveScanRounds.apply(xa, None, dt_bias, prm, z, A_log, D, h0, want_yssm, want_hlast, H)
 
+
+
+# --------------------------------------------------------------------------------------------
+# dense projections of the SSM layer on the tcgen05 GEMM kernel (core.py:366-367, 376-383, 397)
+# --------------------------------------------------------------------------------------------
+def _as_bf16(t):
+    """bf16 GEMM operand of a contiguous tensor (fp32 masters are cast by the library's own kernel)."""
+    if t.dtype == torch.bfloat16:
+        return t.contiguous()
+    if t.dtype == torch.float32 and t.is_contiguous() and t.numel() % 4 == 0:
+        return _cast_bf16(t)
+    return t.to(torch.bfloat16).contiguous()
+
+
+def dense_nt(x2, w, precise, bias=None, out_dtype=None):
+    """x2 [S,K] @ w[N,K]^T (+ bias) -> [S,N].  precise: fp32 in / out through the 3-product bf16 split."""
+    S, K = x2.shape
+    N = w.shape[0]
+    dev = x2.device
+    if precise:
+        a, b, kk, od = _split_cols(x2.float().contiguous(), 0), _split_cols(w.float().contiguous(), 1), 3 * K, torch.float32
+    else:
+        a, b, kk, od = _as_bf16(x2), _as_bf16(w), K, (out_dtype or torch.bfloat16)
+    c = torch.empty(S, N, dtype=od, device=dev)
+    call("ab_dense_gemm_nt", ptr(a), ptr(b), ptr(bias), None, ptr(c), S, N, kk, _lib.EPI_BIAS if bias is not None else _lib.EPI_NONE,
+         dt(od), stream_ptr(dev))
+    return c
+
+
+def dense_nn(dy2, w, precise, add=None, out_dtype=None):
+    """dy2 [S,N] @ w[N,K] (+ add [S,K]) -> [S,K]: the input gradient of nn.Linear from the weight as stored."""
+    S, N = dy2.shape
+    K = w.shape[1]
+    dev = dy2.device
+    if precise:
+        a, b, nn_, od = _split_cols(dy2.float().contiguous(), 0), _split_rows(w.float().contiguous(), 1, None, 1, N), 3 * N, torch.float32
+    else:
+        a, b, nn_, od = _as_bf16(dy2), _as_bf16(w), N, (out_dtype or torch.bfloat16)
+    if add is not None:
+        add = add.to(od).contiguous()
+    c = torch.empty(S, K, dtype=od, device=dev)
+    call("ab_dense_gemm_nn", ptr(a), ptr(b), None, ptr(add), ptr(c), S, K, nn_, _lib.EPI_ADD if add is not None else _lib.EPI_NONE,
+         dt(od), stream_ptr(dev))
+    return c
+
+
+def dense_tn(dy2, x2, precise):
+    """dy2 [S,N]^T @ x2 [S,K] -> fp32 [N,K]: the weight gradient of nn.Linear."""
+    S, N = dy2.shape
+    K = x2.shape[1]
+    dev = dy2.device
+    if precise:
+        a, b, ss = _split_rows(dy2.float().contiguous(), 0, None, 1, S), _split_rows(x2.float().contiguous(), 1, None, 1, S), 3 * S
+    else:
+        a, b, ss = _as_bf16(dy2), _as_bf16(x2), S
+    c = torch.empty(N, K, dtype=torch.float32, device=dev)
+    call("ab_dense_gemm_tn", ptr(a), ptr(b), ptr(c), ss, N, K, stream_ptr(dev))
+    return c
+
+
+class _Linear(torch.autograd.Function):
+    """nn.Linear (optionally several weights stacked along the output dim) on the library's GEMM: x [..., K] -> [..., N]."""
+
+    @staticmethod
+    def forward(ctx, x, bias, precise, *weights):
+        _lib.ensure_device(x.device)
+        with torch.cuda.device(x.device):
+            K = x.shape[-1]
+            x2 = x.reshape(-1, K)
+            w = weights[0] if len(weights) == 1 else torch.cat([wi.reshape(-1, K) for wi in weights], 0)
+            wb = w.float().contiguous() if precise else _as_bf16(w)
+            xb = x2.float().contiguous() if precise else _as_bf16(x2)
+            y = dense_nt(xb, wb, precise, bias=bias.float().contiguous() if bias is not None else None)
+            ctx.save_for_backward(xb, wb)
+            ctx.meta = (precise, x.shape, x.dtype, [wi.shape[0] for wi in weights], [wi.dtype for wi in weights],
+                        bias.dtype if bias is not None else None)
+            return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        precise, xshape, xdtype, splits, wdtypes, bdtype = ctx.meta
+        with torch.cuda.device(dy.device):
+            N = wb.shape[0]
+            dy2 = dy.reshape(-1, N)
+            dyb = dy2.float().contiguous() if precise else _as_bf16(dy2)
+            dx = dense_nn(dyb, wb, precise).view(xshape) if ctx.needs_input_grad[0] else None
+            dw = dense_tn(dyb, xb, precise)
+            db = dy2.float().sum(0).to(bdtype) if bdtype is not None else None
+            dws = [g.to(d) for g, d in zip(dw.split(splits, 0), wdtypes)]
+            if dx is not None and dx.dtype != xdtype:
+                dx = dx.to(xdtype)
+            return (dx, db, None, *dws)
+
+
+def linear(x, weights, bias=None, precise=False):
+    """F.linear(x, cat(weights), bias) through ab_dense_gemm_*; `weights` is one tensor or a list stacked along dim 0."""
+    if torch.is_tensor(weights):
+        weights = [weights]
+    return _Linear.apply(x, bias, precise, *weights)
+
+
+class _SSMCore(torch.autograd.Function):
+    """conv1d + SiLU -> fused parameter projection -> selective scan (core.py:368-396) as one autograd node, so that the
+    intermediate gradients are written in place: the scan's dz and the conv's dxp land in the two halves of d[xp | z], the
+    scan's direct d xa is added in the epilogue of the projection's input-gradient GEMM.
+
+    xz [B,L,2Di] = [xp | z] (in-projection output); returns y [B,L,Di] (gated scan output)."""
+
+    @staticmethod
+    def forward(ctx, xz, conv_w, conv_b, Wp, Wdt, dt_bias, A_log, D, precise):
+        _lib.ensure_device(xz.device)
+        with torch.cuda.device(xz.device):
+            dev = xz.device
+            B, L, Di2 = xz.shape
+            Di = Di2 // 2
+            H, R = Wdt.shape
+            Hp = (H + 7) // 8 * 8
+            Kc = conv_w.shape[-1]
+            W = Hp + 2 * Di
+            cdt = torch.float32 if precise else torch.bfloat16
+            xz = xz.to(cdt).contiguous()
+            cw, cb = conv_w.reshape(Di, Kc).float().contiguous(), conv_b.float().contiguous()
+            xp, z = xz[..., :Di], xz[..., Di:]
+            xa = torch.empty(B, L, Di, dtype=cdt, device=dev)
+            call("ab_causal_conv1d_silu_fwd", ptr(xp), Di2, ptr(cw), ptr(cb), ptr(xa), B, L, Di, Kc, dt(cdt), stream_ptr(dev))
+            Wp32, Wdt32 = Wp.float().contiguous(), Wdt.float().contiguous()
+            wcat = torch.empty(W, Di, dtype=cdt, device=dev)
+            call("ab_dt_compose_fwd", ptr(Wp32), ptr(Wdt32), ptr(wcat), H, Hp, R, Di, dt(cdt), stream_ptr(dev))
+            prm = dense_nt(xa.view(B * L, Di), wcat, precise).view(B, L, W)
+            A = A_log.reshape(-1).float().contiguous()
+            Dv = D.float().contiguous()
+            bias = dt_bias.float().contiguous()
+            nstate, nws = _rounds_plan(B, L, Di, cdt)
+            ws = _rounds_workspace(dev, nws)
+            y = torch.empty(B, L, Di, dtype=cdt, device=dev)
+            state = torch.empty(nstate, dtype=torch.float32, device=dev)
+            call("ab_ssm_scan_fwd", ptr(xa), Di, ptr(prm), W, ptr(bias), ptr(prm[..., Hp:]), ptr(prm[..., Hp + Di:]), W, ptr(z), Di2,
+                 ptr(A), ptr(Dv), None, ptr(y), None, None, ptr(state), ptr(ws), ws.numel(), B, L, Di, H, dt(cdt), stream_ptr(dev))
+            ctx.save_for_backward(xz, cw, cb, xa, wcat, prm, A, Dv, state, Wp32, Wdt32)
+            ctx.meta = (precise, H, Hp, R, Kc, conv_w.shape, conv_w.dtype, conv_b.dtype, Wp.dtype, Wdt.dtype, dt_bias.dtype, A_log.shape)
+            return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xz, cw, cb, xa, wcat, prm, A, Dv, state, Wp32, Wdt32 = ctx.saved_tensors
+        precise, H, Hp, R, Kc, cw_shape, cw_dtype, cb_dtype, wp_dtype, wdt_dtype, bias_dtype, a_shape = ctx.meta
+        with torch.cuda.device(dy.device):
+            dev = dy.device
+            B, L, Di2 = xz.shape
+            Di = Di2 // 2
+            W = Hp + 2 * Di
+            cdt = xz.dtype
+            S = B * L
+            dy = dy.to(cdt).contiguous()
+            z = xz[..., Di:]
+            nstate, nws = _rounds_plan(B, L, Di, cdt)
+            ws = _rounds_workspace(dev, nws)
+            dxz = torch.empty(B, L, Di2, dtype=cdt, device=dev)
+            dxa_s = torch.empty(B, L, Di, dtype=cdt, device=dev)
+            dprm = torch.empty(B, L, W, dtype=cdt, device=dev)
+            dA = torch.empty(Di, dtype=torch.float32, device=dev)
+            dD = torch.empty(Di, dtype=torch.float32, device=dev)
+            dbias = torch.empty(H, dtype=torch.float32, device=dev)
+            call("ab_ssm_scan_bwd", ptr(xa), Di, ptr(prm[..., Hp:]), ptr(prm[..., Hp + Di:]), W, ptr(z), Di2, ptr(dy), None, ptr(A),
+                 ptr(Dv), ptr(state), ptr(dxa_s), Di, ptr(dprm[..., Hp:]), ptr(dprm[..., Hp + Di:]), W, ptr(dxz[..., Di:]), Di2,
+                 ptr(dprm), W, Hp, ptr(dbias), ptr(dA), ptr(dD), ptr(ws), ws.numel(), B, L, Di, H, dt(cdt), stream_ptr(dev))
+            # projection backward: d xa = d prm @ Wcat + (scan's direct d xa), d Wcat = d prm^T @ xa
+            dprm2, xa2 = dprm.view(S, W), xa.view(S, Di)
+            dxa = dense_nn(dprm2, wcat, precise, add=dxa_s.view(S, Di), out_dtype=cdt)
+            dwcat = dense_tn(dprm2, xa2, precise)
+            dWp = torch.empty(R + 2 * Di, Di, dtype=torch.float32, device=dev)
+            dWdt = torch.empty(H, R, dtype=torch.float32, device=dev)
+            call("ab_dt_compose_bwd", ptr(dwcat), ptr(Wp32), ptr(Wdt32), ptr(dWp), ptr(dWdt), H, Hp, R, Di, stream_ptr(dev))
+            # conv backward writes d xp into the first half of d[xp | z]
+            dcw = torch.empty(Di, Kc, dtype=torch.float32, device=dev)
+            dcb = torch.empty(Di, dtype=torch.float32, device=dev)
+            ncw = query("ab_causal_conv1d_silu_bwd_workspace_bytes", B, L, Di)
+            cws = torch.empty(ncw, dtype=torch.uint8, device=dev)
+            call("ab_causal_conv1d_silu_bwd", ptr(xz), Di2, ptr(dxa), ptr(cw), ptr(cb), ptr(dxz), Di2, ptr(dcw), ptr(dcb), ptr(cws), ncw,
+                 B, L, Di, Kc, dt(cdt), stream_ptr(dev))
+            return (dxz, dcw.reshape(cw_shape).to(cw_dtype), dcb.to(cb_dtype), dWp.to(wp_dtype), dWdt.to(wdt_dtype),
+                    dbias.to(bias_dtype), dA.reshape(a_shape), dD, None)
+
+
+def ssm_core(xz, conv_w, conv_b, Wp, Wdt, dt_bias, A_log, D, precise):
+    return _SSMCore.apply(xz, conv_w, conv_b, Wp, Wdt, dt_bias, A_log, D, precise)
 
 
 # --------------------------------------------------------------------------------------------

@@ -155,32 +155,89 @@ class _MeanSquare(torch.autograd.Function):
         return out * (g * (2.0 / out.numel())).to(out.dtype)
 
 
-def cpu_reference_arm(args, wl, steps, warmup, sample_tokens):
-    """Oracle port of the reference block on the host cores (fp32, dropout 0): tokens/s on a bounded sample."""
+def _reference_layer(wl, dropout, device):
+    """The UNMODIFIED reference ApertisLayer (baseline/_ref, installed by __graft_entry__.build()) with seeded weights of
+    the reference initialiser's distributions; None when the install is absent."""
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return None
     from oracle import apertis_oracle as O
+    core = ref_loader.load_core()
+    Dm, H, I, E, K, seq = wl
+    cfg = core.ApertisConfig(hidden_size=Dm, num_attention_heads=H, intermediate_size=I, num_hidden_layers=1,
+                             attention_type="selective_ssm", use_expert_system=True, num_experts=E, experts_per_token=K,
+                             vocab_size=1000, hidden_dropout_prob=dropout)
+    layer = core.ApertisLayer(cfg)
+    layer.load_state_dict(O.make_layer_params(Dm, H, I, E, seed=0, perturb=False), strict=True)
+    return layer.to(device).train()
+
+
+def reference_time(wl, Bsz, L, dropout, device, steps, warmup, autocast=None, best_of=False):
+    """tokens/s of the reference block (fwd + SURVEY 8(d) loss + bwd) on `device`; falls back to the oracle port on the CPU
+    when baseline/_ref is absent.  -> (tokens/s, ms per step, kind)"""
+    Dm, H, I, E, K, seq = wl
+    layer = _reference_layer(wl, dropout, device)
+    kind = "reference"
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(Bsz, L, Dm, generator=g).to(device).requires_grad_(True)
+    if layer is not None:
+        params = list(layer.parameters())
+
+        def step():
+            for p in params:
+                p.grad = None
+            x.grad = None
+            with torch.autocast(device.type, dtype=autocast, enabled=autocast is not None):
+                out, _, _, lb, rz = layer(x)
+            (out.float().pow(2).mean() + lb + rz).backward()
+    else:
+        from oracle import apertis_oracle as O
+        assert device.type == "cpu", "the oracle port is a CPU restatement"
+        kind = "port"
+        sd = {k: v.requires_grad_(True) for k, v in O.make_layer_params(Dm, H, I, E, seed=0).items()}
+        _, noise = O.make_inputs(Bsz, L, Dm, E, seed=0)
+
+        def step():
+            for p in sd.values():
+                p.grad = None
+            x.grad = None
+            out, lb, rz = O.block_forward(sd, x, num_heads=H, E=E, K=K, training=True, noise=noise)
+            O.block_loss(out, lb, rz).backward()
+
+    sync = (lambda: torch.cuda.synchronize(device)) if device.type == "cuda" else (lambda: None)
+    for _ in range(warmup):
+        step()
+    sync()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        sync()
+        times.append(time.perf_counter() - t0)
+    dt = min(times) if best_of else sum(times) / len(times)
+    return Bsz * L / dt, dt * 1e3, kind
+
+
+def cpu_reference_arm(args, wl, steps, warmup, sample_tokens):
+    """The reference block on the host cores (all threads, fp32) on a bounded sample of the bench workload."""
     Dm, H, I, E, K, seq = wl
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     L = min(seq, sample_tokens)
     Bsz = max(1, sample_tokens // L)
-    sd = {k: v.requires_grad_(True) for k, v in O.make_layer_params(Dm, H, I, E, seed=0).items()}
-    x, noise = O.make_inputs(Bsz, L, Dm, E, seed=0)
-    x.requires_grad_(True)
+    v, ms, kind = reference_time(wl, Bsz, L, args.dropout, torch.device("cpu"), steps, warmup)
+    sample = (f"{Bsz}x{L} tokens per step of the same workload, fp32, hidden_dropout_prob {args.dropout}, {steps} steps after {warmup} warm-up, "
+              f"torch {torch.__version__} CPU ops, " + ("unmodified reference ApertisLayer (baseline/_ref)" if kind == "reference" else "oracle port"))
+    return v, ms, cores, sample, kind
 
-    def step():
-        for p in sd.values():
-            p.grad = None
-        x.grad = None
-        out, lb, rz = O.block_forward(sd, x, num_heads=H, E=E, K=K, training=True, noise=noise)
-        O.block_loss(out, lb, rz).backward()
 
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return Bsz * L / dt, dt * 1e3, cores, f"{Bsz}x{L} tokens per step, fp32, {steps} steps after {warmup} warm-up, torch {torch.__version__} CPU ops"
+def c1_cpu_points(steps=3):
+    """BASELINE.md section 4's mandated CPU point: C1 (125M dims) at B 4 x L 1024, dropout 0.1 and 0.0, best of `steps`."""
+    out = {}
+    for p in (0.1, 0.0):
+        v, ms, kind = reference_time(WORKLOADS["c1_125m"], 4, 1024, p, torch.device("cpu"), steps, 1, best_of=True)
+        out[f"dropout_{p}"] = {"tokens_per_s": v, "ms_per_step": ms, "kind": kind}
+    return out
 
 
 def main():
@@ -211,13 +268,18 @@ def main():
         if rank != 0:
             return
         steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-        v, ms, cores, sample = cpu_reference_arm(args, wl, steps, warmup, args.cpu_sample_tokens)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
-                          "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": dict(cfg_common, tokens_per_step_per_gpu=None, sample=sample),
-                          "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        v, ms, cores, sample, kind = cpu_reference_arm(args, wl, steps, warmup, args.cpu_sample_tokens)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(cfg_common, tokens_per_step_per_gpu=None, sample=sample, hidden_dropout_prob=args.dropout),
+                "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        try:
+            line["c1_cpu_points"] = c1_cpu_points()
+        except Exception as ex:
+            line["c1_cpu_points"] = {"error": repr(ex)[:200]}
+        print(json.dumps(line))
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -448,8 +510,8 @@ def main():
                    "how": "pinned host x -> device each step (prefetched on a copy stream), block fwd+bwd through the module API, loss.item()"},
            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "last_loss": last}
     if not args.no_cpu_baseline:
-        v, cms, cores, sample = cpu_reference_arm(args, wl, 3, 1, args.cpu_sample_tokens)
-        out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
+        v, cms, cores, sample, kind = cpu_reference_arm(args, wl, 3, 1, args.cpu_sample_tokens)
+        out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_step": cms}
     print(json.dumps(out))
     shutdown()
 

@@ -57,10 +57,10 @@ int ab_last_error(char* buf, size_t n);
 int ab_causal_conv1d_silu_fwd(const void* xp, int64_t xp_stride, const float* w, const float* bias, void* xa,
                               int B, int L, int Di, int Kc, int dtype, cudaStream_t stream);
 size_t ab_causal_conv1d_silu_bwd_workspace_bytes(int B, int L, int Di);
-/* backward of the above with recompute of the pre-activation: dxp (contiguous [B,L,Di]),
+/* backward of the above with recompute of the pre-activation: dxp ([B,L,Di] rows, dxp_stride elements apart),
  * dw [Di,Kc] and dbias [Di] (fp32, overwritten).  Deterministic (two-stage reduction in ws). */
 int ab_causal_conv1d_silu_bwd(const void* xp, int64_t xp_stride, const void* dxa, const float* w, const float* bias,
-                              void* dxp, float* dw, float* dbias, void* ws, size_t ws_bytes,
+                              void* dxp, int64_t dxp_stride, float* dw, float* dbias, void* ws, size_t ws_bytes,
                               int B, int L, int Di, int Kc, int dtype, cudaStream_t stream);
 
 /* ---- SSM: chunked selective scan  (core.py:324-353 scans, :383 softplus, :394-396 skip + gate) --
@@ -109,6 +109,16 @@ int ab_selective_scan_bwd(const void* xa, const void* dlog, const void* Bm, cons
                           void* dxa, void* dBm, void* dCm, int64_t dbc_stride, void* dz, float* ddlog_parts,
                           float* dA_log, float* dD, void* ws, size_t ws_bytes, uint32_t epoch, int mode,
                           int B, int L, int Di, int H, int dtype, cudaStream_t stream);
+
+/* ---- SSM: stacked weight of the fused parameter projection  (core.py:376-383) ------------------------------------
+ * p = xa Wp^T is split into (dtf [R] | B | C) and dt = dtf Wdt^T + b; dtf feeds nothing else, so
+ * dt = xa (Wdt Wp[0:R])^T + b.  Wcat [(Hp + 2 Di), Di] = [Wdt Wp[0:R] (H rows); 0 (Hp - H rows); Wp[R:R+2Di]] lets ONE
+ * GEMM produce [dt (no bias) | pad | B | C] rows in the layout the scan reads.  fwd builds Wcat (out_dtype bf16 | f32)
+ * from the fp32 parameters Wp [R+2Di, Di], Wdt [H, R]; bwd maps dWcat (fp32) back to dWp and dWdt (overwritten). */
+int ab_dt_compose_fwd(const float* Wp, const float* Wdt, void* Wcat, int H, int Hp, int R, int Di, int out_dtype,
+                      cudaStream_t stream);
+int ab_dt_compose_bwd(const float* dWcat, const float* Wp, const float* Wdt, float* dWp, float* dWdt, int H, int Hp,
+                      int R, int Di, cudaStream_t stream);
 
 /* ---- SSM: selective scan, "rounds" schedule (csrc/ssm_scan_rounds.cu) ------------------------------------------
  * Same arithmetic as above (core.py:324-353, :383, :394-396), one persistent kernel per direction: warps walk chunks of
@@ -237,6 +247,7 @@ int ab_moe_router_bwd(const void* x, const float* stats, const float* ln_w, cons
 #define AB_EPI_BIAS 1
 #define AB_EPI_BIAS_ACT 2
 #define AB_EPI_DACT 3
+#define AB_EPI_ADD 4    /* C = acc + aux[r,n]  (aux has C's shape and dtype; dense GEMMs) */
 /* drop_p > 0 fuses the expert-internal nn.Dropout (core.py:439) into the epilogue: AB_EPI_BIAS_ACT scales
  * act(pre) by mask/(1-p), AB_EPI_DACT applies the same mask to the incoming gradient.  The keep-mask is a
  * counter-based hash of (row, column, drop_seed[0..1]) (drop_seed: device uint32[2]), regenerated, not stored. */
@@ -250,6 +261,19 @@ int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const vo
  * [s*src_stride + seg_off[e], s*src_stride + seg_off[e+1]), s = 0..nsrc-1. */
 int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
                        int N, int E, int nsrc, int64_t src_stride, cudaStream_t stream);
+
+/* ---- dense GEMMs on the same tcgen05 kernel: the SSM layer's projections (core.py:366-367 in_proj_x | in_proj_z,
+ * :376-383 x_param_proj with dt_proj_head folded in, :397 out_proj) and their autograd.  Row-major bf16 operands,
+ * fp32 accumulation; S need not be a multiple of the 128-row tile.  epi = AB_EPI_NONE | AB_EPI_BIAS (bias [N] fp32) |
+ * AB_EPI_ADD (aux [S,N] of c_dtype is added: a second gradient contribution accumulated in the epilogue).
+ *   ab_dense_gemm_nt:  C[S,N] = epi(A[S,K] * W[N,K]^T)        (forward of nn.Linear)
+ *   ab_dense_gemm_nn:  C[S,N] = epi(A[S,K] * W[K,N])          (input gradient: same weight tensor, no transpose copy)
+ *   ab_dense_gemm_tn:  Cw[M,N] = A[S,M]^T * Bm[S,N]  (fp32)   (weight gradient) */
+int ab_dense_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* C, int64_t S, int N, int K,
+                     int epi, int c_dtype, cudaStream_t stream);
+int ab_dense_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* C, int64_t S, int N, int K,
+                     int epi, int c_dtype, cudaStream_t stream);
+int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, int64_t S, int M, int N, cudaStream_t stream);
 
 /* ---- block wrappers: pre-norm LayerNorm  (core.py:694-695, 887-888) ------------
  * y = (x - mean) * rstd * w + b per row, eps inside the sqrt; stats [S,2] = (mean, rstd) saved for the backward.
