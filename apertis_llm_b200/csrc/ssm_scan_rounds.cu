@@ -4,8 +4,12 @@
 // The recurrence  h_t = abar_t * h_{t-1} + B_t  (abar = exp(-exp(A_log) * softplus(dt)), one chain per channel) has only
 // B * Di independent chains, so the sequence is cut into chunks of Tc tokens.  A warp owns one chunk of one 64-channel
 // slab of one sequence at a time: a lane owns two adjacent channels (packed f32x2 arithmetic) and walks the chunk's
-// tokens serially, straight from global memory (coalesced 128-byte rows per warp and token, operands of the next half
-// group of tokens in flight while the current one is computed), no shared memory, no CTA-level synchronisation.
+// tokens serially.  Up to four warps working on neighbouring slabs of the same chunk form a TEAM that shares its operand
+// tiles: one lane issues TMA loads of [8 tokens x (team slabs * 64) channels] boxes into a two-stage ring in shared
+// memory (rows / channels past the tensor are zero-filled by the hardware, which is exactly the masking the recurrences
+// need), the warps read their slab with immediate offsets, write the results IN PLACE over the consumed operands, and the
+// same lane issues the TMA stores (which clip what lies past the tensor).  The token loops hold no address arithmetic,
+// predicates or bounds checks.
 //
 // Every chunk is visited twice:
 //   P1  reads only dt and B (forward) / C, z, dout (backward), computes delta = softplus(dt) (32 lanes = 8 tokens x 4 heads,
@@ -13,13 +17,13 @@
 //       S = state the chunk produces from 0), publishes it;
 //   P2  streams the chunk once with the state entering it known: h, y = (C*h + D*x) * silu(z)  (backward: forward
 //       recompute of 8 states from the saved checkpoint, reverse sweep, all gradients).
-// The persistent grid works in rounds: in round r warp w handles chunk r * cpr + w / nchains of chain w % nchains, and the
-// order per warp is P1(0), P1(1), P2(0), P1(2), P2(1), ...: the aggregates of round r are published a whole P1 pass before
-// anybody needs their prefix, and the second read of the P1 operands (one round later) comes from the 126 MB L2, so DRAM
-// sees every operand byte once.  The prefix over a round's chunk aggregates is a two-level scan done by whoever arrives
-// last (segments of 32 chunks, then the segment totals chained to the carry of the previous round): fixed association,
-// bitwise reproducible.  All counters / flags are indexed by round and zeroed by a memset node ahead of the launch (graph
-// capture safe); waits are bounded (4 s) and trap, so a protocol error is a CUDA error, never a silent wrong answer.
+// The persistent grid works in rounds: in round r team g handles chunk r * cpr + g / nteamchains of team-chain
+// g % nteamchains, and the order per warp is P1(0), P1(1), P2(0), P1(2), P2(1), ...: the aggregates of round r are
+// published a whole P1 pass before anybody needs their prefix.  The prefix over a round's chunk aggregates is a two-level
+// scan done by whoever arrives last (segments of 32 chunks, then the segment totals chained to the carry of the previous
+// round): fixed association, bitwise reproducible.  All counters / flags are indexed by round and zeroed by a memset node
+// ahead of the launch (graph capture safe); waits are bounded (4 s) and trap, so a protocol error is a CUDA error, never a
+// silent wrong answer.
 //
 // The forward saves the state entering every group of 8 tokens (hck, fp32, +0.5 B per element) so that the backward
 // needs no forward prefix of its own and recomputes states 8 at a time in registers.
@@ -108,6 +112,7 @@ constexpr unsigned long long WAIT_LIMIT_NS = 4000000000ull;
 struct RoundsParams {
     int B, L, Di, H, nslab, nchains;
     int Tc, nck, cpr, nrounds, nseg, nw_used, nck8, L8;
+    int tps, nteamchains;      // teams per sequence, B * tps
     const void *xa, *dlog, *Bm, *Cm, *z, *dout, *dyssm;
     void *y, *yssm, *dxa, *dBm, *dCm, *dz, *ddlog;
     int xa_stride, dlog_stride, bc_stride, z_stride, y_stride, dbc_stride, dz_stride, dxa_stride, ddlog_stride;   // elements (< 2^30, checked on the host)
@@ -244,28 +249,23 @@ __device__ __forceinline__ f2 incoming_state(const RoundsParams& p, int r, int c
 }
 
 // ====================================================================================================================
-// per-warp TMA pipeline
-//   Every warp owns a private ring of NST stages in shared memory and one mbarrier per stage; lane 0 issues the TMA loads
-//   (boxes of 64 channels x RG tokens per operand, rows / channels past the tensor are zero-filled by the hardware, which
-//   is exactly the masking the recurrences need) and, after the group is computed, the TMA stores of the results, which
-//   are written IN PLACE over the consumed operands (the store clips what lies past the tensor).  No address arithmetic,
-//   no predicates and no bounds checks remain in the token loops: shared-memory offsets are immediates.
+// team TMA pipeline
 // ====================================================================================================================
-constexpr int NST = 3;                // stages per warp: group g computes from stage g % 3 while g + 1, g + 2 are in flight
+constexpr int NST = 2;                // stages of a team's ring: group g computes from stage g % NST while g + 1 is in flight
 
-template <typename T> struct Tile {
-    static constexpr int ROW_PAIRS = 32;                       // a row = 64 channels = 32 lane pairs
-    static constexpr int BYTES = RG * 64 * (int)sizeof(T);     // one operand of one group
+template <typename T, int TS> struct Tile {
+    static constexpr int ROW_RAW = TS * 32;                          // row pitch in channel pairs
+    static constexpr int BYTES = RG * TS * 64 * (int)sizeof(T);      // one operand of one group of 8 tokens
 };
 
 struct Pipe {
-    unsigned char* base;     // generic address of stage 0
+    unsigned char* base;     // generic address of stage 0 + this lane's channel pair
     uint32_t sbase;          // shared-space address of stage 0
     uint32_t bar;            // shared-space address of mbarrier 0
     uint32_t phases;         // bit s: parity the next wait on stage s expects
     uint32_t stage_bytes;
     __device__ __forceinline__ uint32_t saddr(int st, int off) const { return sbase + (uint32_t)st * stage_bytes + (uint32_t)off; }
-    __device__ __forceinline__ unsigned char* gaddr(int st, int off) const { return base + (size_t)st * stage_bytes + off; }
+    __device__ __forceinline__ unsigned char* gaddr(int st) const { return base + (size_t)st * stage_bytes; }
     __device__ __forceinline__ uint32_t baddr(int st) const { return bar + 8u * (uint32_t)st; }
     __device__ __forceinline__ void wait(int st) {
         mbar_wait_u32(baddr(st), (phases >> st) & 1u);
@@ -276,15 +276,27 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int TS> __device__ __forceinline__ void team_sync(int team_in_cta) {
+    if (TS == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team_in_cta + 1), "n"(TS * 32) : "memory");
+}
 
-template <typename T>
-__device__ __forceinline__ typename Raw<T>::type lds_pair(const unsigned char* stage, int arr, int row, int lane) {
-    return reinterpret_cast<const typename Raw<T>::type*>(stage)[(arr * RG + row) * 32 + lane];
+// `stage` already points at this lane's channel pair of row 0 of operand 0
+template <typename T, int TS>
+__device__ __forceinline__ typename Raw<T>::type lds_pair(const unsigned char* stage, int arr, int row) {
+    return reinterpret_cast<const typename Raw<T>::type*>(stage)[(arr * RG + row) * Tile<T, TS>::ROW_RAW];
 }
-template <typename T>
-__device__ __forceinline__ void sts_pair(unsigned char* stage, int arr, int row, int lane, f2 v) {
-    reinterpret_cast<typename Raw<T>::type*>(stage)[(arr * RG + row) * 32 + lane] = down<T>(v);
+template <typename T, int TS>
+__device__ __forceinline__ void sts_pair(unsigned char* stage, int arr, int row, f2 v) {
+    reinterpret_cast<typename Raw<T>::type*>(stage)[(arr * RG + row) * Tile<T, TS>::ROW_RAW] = down<T>(v);
 }
+
+// what a warp knows about its place
+struct Who {
+    int lane, member, team_in_cta;     // member: slab inside the team (the team's lane 0 of member 0 drives TMA)
+    int b, ch0_team, slab, chain, slot;
+    bool real, leader, cv;             // real: the slab exists (teams are padded to TS slabs); cv: this lane's channel pair exists
+};
 
 // ====================================================================================================================
 // forward
@@ -296,52 +308,60 @@ struct FwdCtx {
     float* hck;        // this sequence's [nck8, Di] block + channel pair
     f2 A2, Dv;
     float bias;        // dt bias of the head this lane computes delta for
-    bool cv, hv;       // channel pair valid; head (lane & 3) valid
-    int lane, L, b, ch0;     // ch0: first channel of the slab
+    bool hv;           // head (lane & 3) valid
+    int L;
 };
-
-// delta of 8 tokens x 4 heads, one (token, head) per lane; saved for P2 and the backward
-template <typename T>
-__device__ __forceinline__ float delta_compute(const FwdCtx<T>& c, int dlog_stride, int tb) {
-    const int tok = tb + (c.lane >> 2);
-    float d = 0.f;
-    if (c.hv && tok < c.L) d = ab_softplus_fast(ab_to_float(c.dlog[(int64_t)tok * dlog_stride]) + c.bias);
-    c.delta[(int64_t)tok * 4] = d;        // tok < L8 always (tb < L, tb a multiple of 8)
-    return d;
-}
 
 constexpr int P1_ROWS = 4 * RG;       // forward P1 reads B in pieces of 32 tokens (one stage = 4 operand tiles = 32 rows)
 
 template <typename T>
-__device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c, Pipe& pp, const CUtensorMap* tm_b32, int r, int chain, int slot,
+__device__ __forceinline__ float dlog_fetch(const FwdCtx<T>& c, const Who& w, int dls, int tb, int tend) {
+    const int tok = tb + (w.lane >> 2);
+    return (w.real && c.hv && tb < tend && tok < c.L) ? ab_to_float(c.dlog[(int64_t)tok * dls]) : -1e30f;
+}
+// delta of 8 tokens x 4 heads, one (token, head) per lane; saved for P2 and the backward
+template <typename T>
+__device__ __forceinline__ float delta_finish(const FwdCtx<T>& c, const Who& w, float raw, int tb, int tend) {
+    const float d = raw > -1e29f ? ab_softplus_fast(raw + c.bias) : 0.f;
+    if (w.real && tb < tend) c.delta[(int64_t)(tb + (w.lane >> 2)) * 4] = d;        // rows < L8 always (tb < L, tb a multiple of 8)
+    return d;
+}
+
+template <typename T, int TS>
+__device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c, const Who& w, Pipe& pp, const CUtensorMap* tm_b32, int r,
                                        uint64_t pol_keep, f2 init) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (slot >= n_r) return;
-    const int t0 = (r * p.cpr + slot) * p.Tc;
+    if (w.slot >= n_r) return;
+    const int t0 = (r * p.cpr + w.slot) * p.Tc;
     const int tend = min(t0 + p.Tc, c.L);
     const int npieces = (tend - t0 + P1_ROWS - 1) / P1_ROWS;
     const int dls = p.dlog_stride;
-    const int hsel = c.lane >> 3;
-    if (c.lane == 0) {
+    const int hsel = w.lane >> 3;
+    auto issue = [&](int st, int t) {
+        mbar_expect_tx_u32(pp.baddr(st), 4 * Tile<T, TS>::BYTES);
+        tma_load(pp.saddr(st, 0), tm_b32, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+    };
+    if (w.leader) {
         bulk_wait_read<0>();              // stores of the previous P2 have read their stages
 #pragma unroll
-        for (int i = 0; i < NST - 1; ++i)
-            if (i < npieces) {
-                mbar_expect_tx_u32(pp.baddr(i), 4 * Tile<T>::BYTES);
-                tma_load(pp.saddr(i, 0), tm_b32, pp.baddr(i), c.ch0, t0 + i * P1_ROWS, c.b, pol_keep);
-            }
+        for (int i = 0; i < NST; ++i)
+            if (i < npieces) issue(i, t0 + i * P1_ROWS);
     }
     f2 S = f2_bcast(0.f);
     float sumd = 0.f;
-    int st = 0;
+    float raw[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) raw[g] = dlog_fetch<T>(c, w, dls, t0 + g * RG, tend);
     for (int pc = 0; pc < npieces; ++pc) {
+        const int st = pc % NST;
         const int tp = t0 + pc * P1_ROWS;
-        // delta of the piece's groups first (global loads + MUFU) so that it overlaps the wait for the tile
         float dm[4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) dm[g] = (tp + g * RG < tend) ? delta_compute<T>(c, dls, tp + g * RG) : 0.f;
+        for (int g = 0; g < 4; ++g) dm[g] = delta_finish<T>(c, w, raw[g], tp + g * RG, tend);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) raw[g] = dlog_fetch<T>(c, w, dls, tp + P1_ROWS + g * RG, tend);     // next piece: in flight during this one
         pp.wait(st);
-        const unsigned char* sb = pp.gaddr(st, 0);
+        const unsigned char* sb = pp.gaddr(st);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (tp + g * RG < tend) {
@@ -349,137 +369,160 @@ __device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c
                 for (int j = 0; j < RG; ++j) {
                     const float d = __shfl_sync(0xffffffffu, dm[g], j * 4 + hsel);
                     const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
-                    S = f2_fma(a, S, up(lds_pair<T>(sb, g, j, c.lane)));
+                    S = f2_fma(a, S, up(lds_pair<T, TS>(sb, g, j)));
                     sumd += d;
                 }
             }
         }
-        __syncwarp();
-        if (c.lane == 0 && pc + NST - 1 < npieces) {
-            const int sn = (st + NST - 1) % NST;
-            mbar_expect_tx_u32(pp.baddr(sn), 4 * Tile<T>::BYTES);
-            tma_load(pp.saddr(sn, 0), tm_b32, pp.baddr(sn), c.ch0, tp + (NST - 1) * P1_ROWS, c.b, pol_keep);
-        }
-        st = (st + 1) % NST;
+        team_sync<TS>(w.team_in_cta);
+        if (w.leader && pc + NST < npieces) issue(st, tp + NST * P1_ROWS);
     }
+    if (!w.real) return;
     const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
-    float* fin = (p.h_last != nullptr && c.cv) ? p.h_last + (size_t)c.b * p.Di + c.ch0 + 2 * c.lane : nullptr;
-    publish_and_prefix(p, r, chain, slot, n_r, c.lane, P, S, init, fin);
+    float* fin = (p.h_last != nullptr && w.cv) ? p.h_last + (size_t)w.b * p.Di + w.slab * 64 + 2 * w.lane : nullptr;
+    publish_and_prefix(p, r, w.chain, w.slot, n_r, w.lane, P, S, init, fin);
 }
 
 // operand tiles of a forward P2 stage
 constexpr int FA_B = 0, FA_X = 1, FA_C = 2, FA_Z = 3;
 
-template <typename T, bool YSSM>
-__device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c, Pipe& pp, const CUtensorMap* tm_xa, const CUtensorMap* tm_b,
-                                       const CUtensorMap* tm_c, const CUtensorMap* tm_z, const CUtensorMap* tm_y, const CUtensorMap* tm_ys,
-                                       int r, int chain, int slot, uint64_t pol_stream) {
+struct FwdMaps {
+    const CUtensorMap *xa, *b, *b32, *c, *z, *y, *ys;
+};
+
+template <typename T, bool YSSM, int TS>
+__device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c, const Who& w, Pipe& pp, const FwdMaps& m, int r, uint64_t pol_stream) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (slot >= n_r) return;
-    const int t0 = (r * p.cpr + slot) * p.Tc;
+    if (w.slot >= n_r) return;
+    const int t0 = (r * p.cpr + w.slot) * p.Tc;
     const int tend = min(t0 + p.Tc, c.L);
     const int ngroups = (tend - t0 + RG - 1) / RG;
-    const int hsel = c.lane >> 3;
+    const int hsel = w.lane >> 3;
+    constexpr int TB = Tile<T, TS>::BYTES;
     auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), 4 * Tile<T>::BYTES);
-        tma_load(pp.saddr(st, FA_B * Tile<T>::BYTES), tm_b, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, FA_X * Tile<T>::BYTES), tm_xa, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, FA_C * Tile<T>::BYTES), tm_c, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, FA_Z * Tile<T>::BYTES), tm_z, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        mbar_expect_tx_u32(pp.baddr(st), 4 * TB);
+        tma_load(pp.saddr(st, FA_B * TB), m.b, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, FA_X * TB), m.xa, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, FA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, FA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
     };
-    if (c.lane == 0) {
+    if (w.leader) {
         bulk_wait_read<0>();
 #pragma unroll
-        for (int i = 0; i < NST - 1; ++i)
+        for (int i = 0; i < NST; ++i)
             if (i < ngroups) issue(i, t0 + i * RG);           // in flight during the wait for the prefix
     }
-    wait_flag(&p.flag[(size_t)r * p.nchains + chain], c.lane);
-    f2 h = incoming_state(p, r, chain, slot, c.lane);
+    const float* dsrc = c.delta + (int64_t)(t0 + (w.lane >> 2)) * 4;
+    float dnext = w.real ? __ldcg(dsrc) : 0.f;
+    f2 h = f2_bcast(0.f);
+    if (w.real) {
+        wait_flag(&p.flag[(size_t)r * p.nchains + w.chain], w.lane);
+        h = incoming_state(p, r, w.chain, w.slot, w.lane);
+    }
     float* hck = c.hck + (size_t)(t0 >> 3) * p.Di;
-    const float* dsrc = c.delta + (int64_t)(t0 + (c.lane >> 2)) * 4;
-    int st = 0;
     for (int g = 0; g < ngroups; ++g) {
+        const int st = g % NST;
         const int tb = t0 + g * RG;
-        const float dmine = __ldcg(dsrc);
+        const float dmine = dnext;
         dsrc += RG * 4;
-        if (c.cv) {
+        if (w.real && g + 1 < ngroups) dnext = __ldcg(dsrc);          // next group's delta: in flight during this group
+        if (w.real && w.cv) {
             float h0, h1;
             f2_unpack(h, h0, h1);
             *reinterpret_cast<float2*>(hck) = make_float2(h0, h1);
         }
         hck += p.Di;
         pp.wait(st);
-        unsigned char* sb = pp.gaddr(st, 0);
+        unsigned char* sb = pp.gaddr(st);
 #pragma unroll
         for (int j = 0; j < RG; ++j) {
             const float d = __shfl_sync(0xffffffffu, dmine, j * 4 + hsel);
             const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
-            h = f2_fma(a, h, up(lds_pair<T>(sb, FA_B, j, c.lane)));
-            const f2 ys = f2_mul(up(lds_pair<T>(sb, FA_C, j, c.lane)), h);
-            const f2 yv = f2_fma(c.Dv, up(lds_pair<T>(sb, FA_X, j, c.lane)), ys);
-            const f2 zv = up(lds_pair<T>(sb, FA_Z, j, c.lane));
-            sts_pair<T>(sb, FA_X, j, c.lane, f2_mul(yv, f2_mul(zv, f2_sigmoid<T>(zv))));      // y over the consumed x
-            if (YSSM) sts_pair<T>(sb, FA_C, j, c.lane, ys);
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (c.lane == 0) {
-            tma_store(tm_y, pp.saddr(st, FA_X * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
-            if (YSSM) tma_store(tm_ys, pp.saddr(st, FA_C * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
-            bulk_commit();
-            if (g + NST - 1 < ngroups) {
-                bulk_wait_read<1>();          // the store issued one group ago (from the stage refilled now) has read its tile
-                issue((st + NST - 1) % NST, tb + (NST - 1) * RG);
+            h = f2_fma(a, h, up(lds_pair<T, TS>(sb, FA_B, j)));
+            const f2 ys = f2_mul(up(lds_pair<T, TS>(sb, FA_C, j)), h);
+            const f2 yv = f2_fma(c.Dv, up(lds_pair<T, TS>(sb, FA_X, j)), ys);
+            const f2 zv = up(lds_pair<T, TS>(sb, FA_Z, j));
+            sts_pair<T, TS>(sb, FA_X, j, f2_mul(yv, f2_mul(zv, f2_sigmoid<T>(zv))));      // y over the consumed x
+            if (YSSM) sts_pair<T, TS>(sb, FA_C, j, ys);
+            if (j == RG / 2 - 1 && w.leader && g >= 1 && g - 1 + NST < ngroups) {
+                // half a group after the stores of group g - 1 were issued: refill its stage with group g - 1 + NST
+                bulk_wait_read<0>();
+                issue((g - 1) % NST, tb + (NST - 1) * RG);
             }
         }
-        st = (st + 1) % NST;
+        fence_async_smem();
+        team_sync<TS>(w.team_in_cta);
+        if (w.leader) {
+            tma_store(m.y, pp.saddr(st, FA_X * TB), w.ch0_team, tb, w.b, pol_stream);
+            if (YSSM) tma_store(m.ys, pp.saddr(st, FA_C * TB), w.ch0_team, tb, w.b, pol_stream);
+            bulk_commit();
+        }
     }
 }
 
-template <typename T, bool YSSM>
+template <typename T, int TS>
+__device__ __forceinline__ void who_am_i(const RoundsParams& p, Who& w, Pipe& pp, unsigned char* smem_raw, int ntiles) {
+    const int wic = threadIdx.x >> 5, nteams_cta = (blockDim.x >> 5) / TS;
+    w.lane = threadIdx.x & 31;
+    w.member = wic % TS;
+    w.team_in_cta = wic / TS;
+    const int gt = blockIdx.x * nteams_cta + w.team_in_cta;            // global team
+    const int tc = gt % p.nteamchains;
+    w.slot = gt / p.nteamchains;
+    w.b = tc / p.tps;
+    const int tslab = tc % p.tps;
+    w.ch0_team = tslab * TS * 64;
+    w.slab = tslab * TS + w.member;
+    w.real = w.slab < p.nslab;
+    w.chain = w.b * p.nslab + (w.real ? w.slab : 0);
+    w.leader = w.member == 0 && w.lane == 0;
+    w.cv = w.real && (w.slab * 64 + 2 * w.lane) < p.Di;
+    pp.stage_bytes = (uint32_t)ntiles * Tile<T, TS>::BYTES;
+    unsigned char* ring = smem_raw + (size_t)w.team_in_cta * NST * pp.stage_bytes;
+    pp.sbase = ab_smem_u32(ring);
+    pp.base = ring + (size_t)(w.member * 32 + w.lane) * sizeof(typename Raw<T>::type);
+    pp.bar = ab_smem_u32(smem_raw + (size_t)nteams_cta * NST * pp.stage_bytes) + (uint32_t)w.team_in_cta * NST * 8u;
+    pp.phases = 0;
+    if (w.leader) {
+#pragma unroll
+        for (int i = 0; i < NST; ++i) mbar_init_u32(pp.baddr(i), 1);
+        ab_fence_mbar_init();
+    }
+    __syncthreads();
+}
+
+template <typename T, bool YSSM, int TS>
 __global__ void __launch_bounds__(sizeof(T) == 2 ? 768 : 512, 1)
 scan_rounds_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b32,
                        const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_y,
                        const __grid_constant__ CUtensorMap tm_ys, const RoundsParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, nwc = blockDim.x >> 5;
-    const int gw = blockIdx.x * nwc + wic;
+    Who w;
     Pipe pp;
-    pp.stage_bytes = 4 * Tile<T>::BYTES;
-    pp.base = smem_raw + (size_t)wic * NST * pp.stage_bytes;
-    pp.sbase = ab_smem_u32(pp.base);
-    pp.bar = ab_smem_u32(smem_raw + (size_t)nwc * NST * pp.stage_bytes) + (uint32_t)wic * NST * 8u;
-    pp.phases = 0;
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NST; ++i) mbar_init_u32(pp.baddr(i), 1);
-        ab_fence_mbar_init();
-    }
-    __syncwarp();
-    if (gw >= p.nw_used) return;
-    const int chain = gw % p.nchains, slot = gw / p.nchains;
-    const int b = chain / p.nslab, slab = chain % p.nslab;
-    const int c0 = slab * 64 + 2 * lane;
+    who_am_i<T, TS>(p, w, pp, smem_raw, 4);
+    if (w.slot >= p.cpr) return;              // whole teams past the grid's share leave together
+    const int lane = w.lane;
+    const int c0 = w.slab * 64 + 2 * lane;
     FwdCtx<T> c;
-    c.lane = lane; c.L = p.L; c.b = b; c.ch0 = slab * 64;
-    c.cv = c0 < p.Di;
-    const int head = slab * 4 + (lane & 3);
-    c.hv = head < p.H;
+    c.L = p.L;
+    const int head = w.slab * 4 + (lane & 3);
+    c.hv = w.real && head < p.H;
     c.bias = (c.hv && p.dt_bias != nullptr) ? p.dt_bias[head] : 0.f;
-    const int cs = c.cv ? c0 : 0;
-    c.A2 = c.cv ? f2_pack(-__expf(p.A_log[c0]) * AB_LOG2E, -__expf(p.A_log[c0 + 1]) * AB_LOG2E) : f2_bcast(0.f);
-    c.Dv = c.cv ? f2_pack(p.D[c0], p.D[c0 + 1]) : f2_bcast(0.f);
-    c.dlog = reinterpret_cast<const T*>(p.dlog) + (int64_t)b * p.L * p.dlog_stride + (c.hv ? head : 0);
-    c.delta = p.delta + (size_t)chain * p.L8 * 4 + (lane & 3);
-    c.hck = p.hck + (size_t)b * p.nck8 * p.Di + cs;
+    const int cs = w.cv ? c0 : 0;
+    c.A2 = w.cv ? f2_pack(-__expf(p.A_log[c0]) * AB_LOG2E, -__expf(p.A_log[c0 + 1]) * AB_LOG2E) : f2_bcast(0.f);
+    c.Dv = w.cv ? f2_pack(p.D[c0], p.D[c0 + 1]) : f2_bcast(0.f);
+    c.dlog = reinterpret_cast<const T*>(p.dlog) + (int64_t)w.b * p.L * p.dlog_stride + (c.hv ? head : 0);
+    c.delta = p.delta + (size_t)w.chain * p.L8 * 4 + (lane & 3);
+    c.hck = p.hck + (size_t)w.b * p.nck8 * p.Di + cs;
     f2 init = f2_bcast(0.f);
-    if (p.h0 != nullptr && c.cv) init = f2_pack(p.h0[(size_t)b * p.Di + c0], p.h0[(size_t)b * p.Di + c0 + 1]);
+    if (p.h0 != nullptr && w.cv) init = f2_pack(p.h0[(size_t)w.b * p.Di + c0], p.h0[(size_t)w.b * p.Di + c0 + 1]);
+    const FwdMaps m{&tm_xa, &tm_b, &tm_b32, &tm_c, &tm_z, &tm_y, &tm_ys};
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     for (int r = -1; r < p.nrounds; ++r) {
-        if (r + 1 < p.nrounds) fwd_p1<T>(p, c, pp, &tm_b32, r + 1, chain, slot, pol_keep, init);
-        if (r >= 0) fwd_p2<T, YSSM>(p, c, pp, &tm_xa, &tm_b, &tm_c, &tm_z, &tm_y, &tm_ys, r, chain, slot, pol_stream);
+        if (r + 1 < p.nrounds) fwd_p1<T, TS>(p, c, w, pp, m.b32, r + 1, pol_keep, init);
+        if (r >= 0) fwd_p2<T, YSSM, TS>(p, c, w, pp, m, r, pol_stream);
     }
-    if (lane == 0) bulk_wait_all();
+    if (w.leader) bulk_wait_all();
 }
 
 // ====================================================================================================================
@@ -497,8 +540,7 @@ struct BwdCtx {
     const float* delta;
     const float* hck;
     f2 A2, Dv, An;      // An = natural-log A = -exp(A_log)
-    bool cv;
-    int lane, L, b, ch0;
+    int L;
 };
 
 // operand tiles of a backward stage (P1 fills C, Z, G (, S); P2 all); the results overwrite B, X, C, Z in place
@@ -508,94 +550,107 @@ struct BwdMaps {
     const CUtensorMap *xa, *b, *c, *z, *g, *s, *dxa, *db, *dc, *dz;
 };
 
-template <typename T, bool YSSM>
-__device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c, Pipe& pp, const BwdMaps& m, int r, int chain, int slot, uint64_t pol_keep) {
+template <typename T, bool YSSM, int TS>
+__device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c, const Who& w, Pipe& pp, const BwdMaps& m, int r, uint64_t pol_keep) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (slot >= n_r) return;
-    const int pos = p.nck - 1 - (r * p.cpr + slot);
+    if (w.slot >= n_r) return;
+    const int pos = p.nck - 1 - (r * p.cpr + w.slot);
     const int t0 = pos * p.Tc;
     const int tend = min(t0 + p.Tc, c.L);
-    const int ngroups = (tend - t0 + RG - 1) / RG;          // groups are visited last to first
-    const int hsel = c.lane >> 3;
+    const int ngroups = (tend - t0 + RG - 1) / RG;          // groups are visited last to first: step i handles group ngroups - 1 - i
+    const int hsel = w.lane >> 3;
+    constexpr int TB = Tile<T, TS>::BYTES;
     auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 4 : 3) * Tile<T>::BYTES);
-        tma_load(pp.saddr(st, BA_C * Tile<T>::BYTES), m.c, pp.baddr(st), c.ch0, t, c.b, pol_keep);
-        tma_load(pp.saddr(st, BA_Z * Tile<T>::BYTES), m.z, pp.baddr(st), c.ch0, t, c.b, pol_keep);
-        tma_load(pp.saddr(st, BA_G * Tile<T>::BYTES), m.g, pp.baddr(st), c.ch0, t, c.b, pol_keep);
-        if (YSSM) tma_load(pp.saddr(st, BA_S * Tile<T>::BYTES), m.s, pp.baddr(st), c.ch0, t, c.b, pol_keep);
+        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 4 : 3) * TB);
+        tma_load(pp.saddr(st, BA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+        tma_load(pp.saddr(st, BA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+        tma_load(pp.saddr(st, BA_G * TB), m.g, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+        if (YSSM) tma_load(pp.saddr(st, BA_S * TB), m.s, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
     };
-    if (c.lane == 0) {
+    if (w.leader) {
         bulk_wait_read<0>();
 #pragma unroll
-        for (int i = 0; i < NST - 1; ++i)
+        for (int i = 0; i < NST; ++i)
             if (i < ngroups) issue(i, t0 + (ngroups - 1 - i) * RG);
     }
     f2 F = f2_bcast(0.f);
     float sumd = 0.f;
-    const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (c.lane >> 2)) * 4;
-    int st = 0;
-    for (int g = ngroups - 1; g >= 0; --g) {
-        const float dmine = __ldg(dsrc);
+    const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (w.lane >> 2)) * 4;
+    float dnext = w.real ? __ldg(dsrc) : 0.f;
+    for (int i = 0; i < ngroups; ++i) {
+        const int st = i % NST;
+        const float dmine = dnext;
         dsrc -= RG * 4;
+        if (w.real && i + 1 < ngroups) dnext = __ldg(dsrc);
         pp.wait(st);
-        const unsigned char* sb = pp.gaddr(st, 0);
+        const unsigned char* sb = pp.gaddr(st);
 #pragma unroll
         for (int j = RG - 1; j >= 0; --j) {
             const float d = __shfl_sync(0xffffffffu, dmine, j * 4 + hsel);
             const f2 a = f2_ex2(f2_mul(f2_bcast(d), c.A2));
-            const f2 zv = up(lds_pair<T>(sb, BA_Z, j, c.lane));
-            f2 dys = f2_mul(up(lds_pair<T>(sb, BA_G, j, c.lane)), f2_mul(zv, f2_sigmoid<T>(zv)));
-            if (YSSM) dys = f2_add(dys, up(lds_pair<T>(sb, BA_S, j, c.lane)));
-            F = f2_mul(a, f2_fma(up(lds_pair<T>(sb, BA_C, j, c.lane)), dys, F));
+            const f2 zv = up(lds_pair<T, TS>(sb, BA_Z, j));
+            f2 dys = f2_mul(up(lds_pair<T, TS>(sb, BA_G, j)), f2_mul(zv, f2_sigmoid<T>(zv)));
+            if (YSSM) dys = f2_add(dys, up(lds_pair<T, TS>(sb, BA_S, j)));
+            F = f2_mul(a, f2_fma(up(lds_pair<T, TS>(sb, BA_C, j)), dys, F));
             sumd += d;
         }
-        __syncwarp();
-        if (c.lane == 0 && g - (NST - 1) >= 0) issue((st + NST - 1) % NST, t0 + (g - (NST - 1)) * RG);
-        st = (st + 1) % NST;
+        team_sync<TS>(w.team_in_cta);
+        if (w.leader && i + NST < ngroups) issue(st, t0 + (ngroups - 1 - i - NST) * RG);
     }
+    if (!w.real) return;
     const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
-    publish_and_prefix(p, r, chain, slot, n_r, c.lane, P, F, f2_bcast(0.f), nullptr);
+    publish_and_prefix(p, r, w.chain, w.slot, n_r, w.lane, P, F, f2_bcast(0.f), nullptr);
 }
 
-template <typename T, bool YSSM>
-__device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c, Pipe& pp, const BwdMaps& m, int r, int chain, int slot, f2& accA,
-                                       f2& accD, float& accB, uint64_t pol_stream) {
+template <typename T, bool YSSM, int TS>
+__device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c, const Who& w, Pipe& pp, const BwdMaps& m, int r, f2& accA, f2& accD,
+                                       float& accB, uint64_t pol_stream) {
     const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (slot >= n_r) return;
-    const int pos = p.nck - 1 - (r * p.cpr + slot);
+    if (w.slot >= n_r) return;
+    const int pos = p.nck - 1 - (r * p.cpr + w.slot);
     const int t0 = pos * p.Tc;
     const int tend = min(t0 + p.Tc, c.L);
     const int ngroups = (tend - t0 + RG - 1) / RG;
-    const int hsel = c.lane >> 3;
+    const int hsel = w.lane >> 3;
+    constexpr int TB = Tile<T, TS>::BYTES;
     auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 6 : 5) * Tile<T>::BYTES);
-        tma_load(pp.saddr(st, BA_B * Tile<T>::BYTES), m.b, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, BA_G * Tile<T>::BYTES), m.g, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, BA_Z * Tile<T>::BYTES), m.z, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, BA_C * Tile<T>::BYTES), m.c, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        tma_load(pp.saddr(st, BA_X * Tile<T>::BYTES), m.xa, pp.baddr(st), c.ch0, t, c.b, pol_stream);
-        if (YSSM) tma_load(pp.saddr(st, BA_S * Tile<T>::BYTES), m.s, pp.baddr(st), c.ch0, t, c.b, pol_stream);
+        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 6 : 5) * TB);
+        tma_load(pp.saddr(st, BA_B * TB), m.b, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, BA_G * TB), m.g, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, BA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, BA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        tma_load(pp.saddr(st, BA_X * TB), m.xa, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        if (YSSM) tma_load(pp.saddr(st, BA_S * TB), m.s, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
     };
-    if (c.lane == 0) {
+    if (w.leader) {
         bulk_wait_read<0>();
 #pragma unroll
-        for (int i = 0; i < NST - 1; ++i)
+        for (int i = 0; i < NST; ++i)
             if (i < ngroups) issue(i, t0 + (ngroups - 1 - i) * RG);           // in flight during the wait for the prefix
     }
-    wait_flag(&p.flag[(size_t)r * p.nchains + chain], c.lane);
-    f2 F = incoming_state(p, r, chain, slot, c.lane);
     const float* hck = c.hck + (size_t)((t0 >> 3) + ngroups - 1) * p.Di;
-    const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (c.lane >> 2)) * 4;
-    int st = 0;
-    for (int g = ngroups - 1; g >= 0; --g) {
-        const int tb = t0 + g * RG;
-        float2 hp = make_float2(0.f, 0.f);
-        if (c.cv) hp = __ldg(reinterpret_cast<const float2*>(hck));
-        hck -= p.Di;
-        const float dmine = __ldg(dsrc);
+    const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (w.lane >> 2)) * 4;
+    float dnext = w.real ? __ldg(dsrc) : 0.f;
+    float2 hnext = make_float2(0.f, 0.f);
+    if (w.cv) hnext = __ldg(reinterpret_cast<const float2*>(hck));
+    f2 F = f2_bcast(0.f);
+    if (w.real) {
+        wait_flag(&p.flag[(size_t)r * p.nchains + w.chain], w.lane);
+        F = incoming_state(p, r, w.chain, w.slot, w.lane);
+    }
+    for (int i = 0; i < ngroups; ++i) {
+        const int st = i % NST;
+        const int tb = t0 + (ngroups - 1 - i) * RG;
+        const float dmine = dnext;
+        const float2 hp = hnext;
         dsrc -= RG * 4;
+        hck -= p.Di;
+        if (i + 1 < ngroups) {
+            if (w.real) dnext = __ldg(dsrc);
+            if (w.cv) hnext = __ldg(reinterpret_cast<const float2*>(hck));
+        }
         pp.wait(st);
-        unsigned char* sb = pp.gaddr(st, 0);
+        unsigned char* sb = pp.gaddr(st);
         // ---- forward recompute of the 8 states
         f2 a[RG], h[RG + 1];
         float dl[RG];
@@ -604,70 +659,71 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
         for (int j = 0; j < RG; ++j) {
             dl[j] = __shfl_sync(0xffffffffu, dmine, j * 4 + hsel);
             a[j] = f2_ex2(f2_mul(f2_bcast(dl[j]), c.A2));
-            h[j + 1] = f2_fma(a[j], h[j], up(lds_pair<T>(sb, BA_B, j, c.lane)));
+            h[j + 1] = f2_fma(a[j], h[j], up(lds_pair<T, TS>(sb, BA_B, j)));
+        }
+        if (w.leader && i >= 1 && i - 1 + NST < ngroups) {
+            // the stores of the previous group were issued a recompute ago: refill its stage
+            bulk_wait_read<0>();
+            issue((i - 1) % NST, t0 + (ngroups - 1 - (i - 1 + NST)) * RG);
         }
         // ---- reverse sweep; every result goes over the operand it replaces
         float dd[RG];          // this lane's share (2 channels) of d delta of each token
 #pragma unroll
         for (int j = RG - 1; j >= 0; --j) {
-            const f2 zv = up(lds_pair<T>(sb, BA_Z, j, c.lane)), go = up(lds_pair<T>(sb, BA_G, j, c.lane));
-            const f2 xx = up(lds_pair<T>(sb, BA_X, j, c.lane)), cc = up(lds_pair<T>(sb, BA_C, j, c.lane));
+            const f2 zv = up(lds_pair<T, TS>(sb, BA_Z, j)), go = up(lds_pair<T, TS>(sb, BA_G, j));
+            const f2 xx = up(lds_pair<T, TS>(sb, BA_X, j)), cc = up(lds_pair<T, TS>(sb, BA_C, j));
             const f2 sg = f2_sigmoid<T>(zv);
             const f2 dyv = f2_mul(go, f2_mul(zv, sg));
             const f2 yv = f2_fma(c.Dv, xx, f2_mul(cc, h[j + 1]));
             // silu'(z) = sg * (1 + z * (1 - sg)) = sg * (1 + z - z * sg)
             const f2 dsilu = f2_mul(sg, f2_fma(f2_mul(zv, sg), f2_bcast(-1.f), f2_add(zv, f2_bcast(1.f))));
-            sts_pair<T>(sb, BA_Z, j, c.lane, f2_mul(f2_mul(go, yv), dsilu));
-            sts_pair<T>(sb, BA_X, j, c.lane, f2_mul(dyv, c.Dv));
+            sts_pair<T, TS>(sb, BA_Z, j, f2_mul(f2_mul(go, yv), dsilu));
+            sts_pair<T, TS>(sb, BA_X, j, f2_mul(dyv, c.Dv));
             accD = f2_fma(dyv, xx, accD);
             f2 dys = dyv;
-            if (YSSM) dys = f2_add(dys, up(lds_pair<T>(sb, BA_S, j, c.lane)));
-            sts_pair<T>(sb, BA_C, j, c.lane, f2_mul(dys, h[j + 1]));
+            if (YSSM) dys = f2_add(dys, up(lds_pair<T, TS>(sb, BA_S, j)));
+            sts_pair<T, TS>(sb, BA_C, j, f2_mul(dys, h[j + 1]));
             const f2 E = f2_fma(cc, dys, F);
-            sts_pair<T>(sb, BA_B, j, c.lane, E);
-            const f2 w = f2_mul(f2_mul(E, h[j]), a[j]);
-            dd[j] = f2_hsum(f2_mul(w, c.An));
-            accA = f2_fma(w, f2_bcast(dl[j]), accA);
+            sts_pair<T, TS>(sb, BA_B, j, E);
+            const f2 wv = f2_mul(f2_mul(E, h[j]), a[j]);
+            dd[j] = f2_hsum(f2_mul(wv, c.An));
+            accA = f2_fma(wv, f2_bcast(dl[j]), accA);
             F = f2_mul(a[j], E);
         }
         fence_async_smem();
-        __syncwarp();
-        if (c.lane == 0) {
-            tma_store(m.db, pp.saddr(st, BA_B * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
-            tma_store(m.dxa, pp.saddr(st, BA_X * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
-            tma_store(m.dc, pp.saddr(st, BA_C * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
-            tma_store(m.dz, pp.saddr(st, BA_Z * Tile<T>::BYTES), c.ch0, tb, c.b, pol_stream);
+        team_sync<TS>(w.team_in_cta);
+        if (w.leader) {
+            tma_store(m.db, pp.saddr(st, BA_B * TB), w.ch0_team, tb, w.b, pol_stream);
+            tma_store(m.dxa, pp.saddr(st, BA_X * TB), w.ch0_team, tb, w.b, pol_stream);
+            tma_store(m.dc, pp.saddr(st, BA_C * TB), w.ch0_team, tb, w.b, pol_stream);
+            tma_store(m.dz, pp.saddr(st, BA_Z * TB), w.ch0_team, tb, w.b, pol_stream);
             bulk_commit();
-            if (g - (NST - 1) >= 0) {
-                bulk_wait_read<1>();
-                issue((st + NST - 1) % NST, t0 + (g - (NST - 1)) * RG);
-            }
         }
         // ---- d delta: sum over the 8 lanes of a head (16 channels), transposing butterfly over the 8 tokens so that lane
         //      (head hsel, k = lane & 7) ends with the total of token k
         {
-            const int k = c.lane & 7;
+            const int k = w.lane & 7;
             float s4[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float keep = (k & 4) ? dd[i + 4] : dd[i];
-                const float send = (k & 4) ? dd[i] : dd[i + 4];
-                s4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            for (int q = 0; q < 4; ++q) {
+                const float keep = (k & 4) ? dd[q + 4] : dd[q];
+                const float send = (k & 4) ? dd[q] : dd[q + 4];
+                s4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
             float s2[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float keep = (k & 2) ? s4[i + 2] : s4[i];
-                const float send = (k & 2) ? s4[i] : s4[i + 2];
-                s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            for (int q = 0; q < 2; ++q) {
+                const float keep = (k & 2) ? s4[q + 2] : s4[q];
+                const float send = (k & 2) ? s4[q] : s4[q + 2];
+                s2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
             }
             const float keep = (k & 1) ? s2[1] : s2[0];
             const float send = (k & 1) ? s2[0] : s2[1];
             const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);      // token k of head hsel
             const float dk = __shfl_sync(0xffffffffu, dmine, k * 4 + hsel);       // delta of (token k, head hsel)
-            const int head = (c.ch0 >> 4) + hsel;
+            const int head = w.slab * 4 + hsel;
             const int tok = tb + k;
-            if (tok < c.L) {
+            if (w.real && tok < c.L) {
                 if (head < p.H) {
                     // softplus'(x) = sigmoid(x) = 1 - exp(-softplus(x))
                     const float gq = tot * (1.0f - ab_ex2(-dk * AB_LOG2E));
@@ -678,57 +734,44 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
                     if (hh >= p.H) c.ddlog[(int64_t)tok * p.ddlog_stride + hh] = ab_from_float<T>(0.f);
             }
         }
-        st = (st + 1) % NST;
     }
 }
 
-template <typename T, bool YSSM>
+template <typename T, bool YSSM, int TS>
 __global__ void __launch_bounds__(sizeof(T) == 2 ? 512 : 256, 1)
 scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
                        const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_s,
                        const __grid_constant__ CUtensorMap tm_dxa, const __grid_constant__ CUtensorMap tm_db, const __grid_constant__ CUtensorMap tm_dc,
                        const __grid_constant__ CUtensorMap tm_dz, const RoundsParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5, nwc = blockDim.x >> 5;
-    const int gw = blockIdx.x * nwc + wic;
+    Who w;
     Pipe pp;
-    pp.stage_bytes = (YSSM ? 6 : 5) * Tile<T>::BYTES;
-    pp.base = smem_raw + (size_t)wic * NST * pp.stage_bytes;
-    pp.sbase = ab_smem_u32(pp.base);
-    pp.bar = ab_smem_u32(smem_raw + (size_t)nwc * NST * pp.stage_bytes) + (uint32_t)wic * NST * 8u;
-    pp.phases = 0;
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NST; ++i) mbar_init_u32(pp.baddr(i), 1);
-        ab_fence_mbar_init();
-    }
-    __syncwarp();
-    if (gw >= p.nw_used) return;
-    const int chain = gw % p.nchains, slot = gw / p.nchains;
-    const int b = chain / p.nslab, slab = chain % p.nslab;
-    const int c0 = slab * 64 + 2 * lane;
+    who_am_i<T, TS>(p, w, pp, smem_raw, YSSM ? 6 : 5);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w.slot >= p.cpr) return;
+    const int lane = w.lane;
+    const int c0 = w.slab * 64 + 2 * lane;
     BwdCtx<T> c;
-    c.lane = lane; c.L = p.L; c.b = b; c.ch0 = slab * 64;
-    c.cv = c0 < p.Di;
-    const int cs = c.cv ? c0 : 0;
-    const float a0 = c.cv ? -__expf(p.A_log[c0]) : 0.f, a1 = c.cv ? -__expf(p.A_log[c0 + 1]) : 0.f;
+    c.L = p.L;
+    const int cs = w.cv ? c0 : 0;
+    const float a0 = w.cv ? -__expf(p.A_log[c0]) : 0.f, a1 = w.cv ? -__expf(p.A_log[c0 + 1]) : 0.f;
     c.An = f2_pack(a0, a1);
     c.A2 = f2_pack(a0 * AB_LOG2E, a1 * AB_LOG2E);
-    c.Dv = c.cv ? f2_pack(p.D[c0], p.D[c0 + 1]) : f2_bcast(0.f);
-    c.ddlog = reinterpret_cast<T*>(p.ddlog) + (int64_t)b * p.L * p.ddlog_stride;
-    c.delta = p.delta + (size_t)chain * p.L8 * 4 + (lane & 3);
-    c.hck = p.hck + (size_t)b * p.nck8 * p.Di + cs;
-    BwdMaps m{&tm_xa, &tm_b, &tm_c, &tm_z, &tm_g, &tm_s, &tm_dxa, &tm_db, &tm_dc, &tm_dz};
+    c.Dv = w.cv ? f2_pack(p.D[c0], p.D[c0 + 1]) : f2_bcast(0.f);
+    c.ddlog = reinterpret_cast<T*>(p.ddlog) + (int64_t)w.b * p.L * p.ddlog_stride;
+    c.delta = p.delta + (size_t)w.chain * p.L8 * 4 + (lane & 3);
+    c.hck = p.hck + (size_t)w.b * p.nck8 * p.Di + cs;
+    const BwdMaps m{&tm_xa, &tm_b, &tm_c, &tm_z, &tm_g, &tm_s, &tm_dxa, &tm_db, &tm_dc, &tm_dz};
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     f2 accA = f2_bcast(0.f), accD = f2_bcast(0.f);
     float accB = 0.f;
     for (int r = -1; r < p.nrounds; ++r) {
-        if (r + 1 < p.nrounds) bwd_p1<T, YSSM>(p, c, pp, m, r + 1, chain, slot, pol_keep);
-        if (r >= 0) bwd_p2<T, YSSM>(p, c, pp, m, r, chain, slot, accA, accD, accB, pol_stream);
+        if (r + 1 < p.nrounds) bwd_p1<T, YSSM, TS>(p, c, w, pp, m, r + 1, pol_keep);
+        if (r >= 0) bwd_p2<T, YSSM, TS>(p, c, w, pp, m, r, accA, accD, accB, pol_stream);
     }
-    if (lane == 0) bulk_wait_all();
+    if (w.leader) bulk_wait_all();
     {
-        // dA_log = A * sum(w * delta): accA holds sum(w * delta)
+        // dA_log = A * sum(w * delta): accA holds sum(w * delta); phantom slabs contribute zeros
         const f2 da = f2_mul(accA, c.An);
         float x0, x1, y0, y1;
         f2_unpack(da, x0, x1);
@@ -739,31 +782,44 @@ scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
 }
 
 // dA_log[c], dD[c] (and d dt_bias[head]) = sum over the warps that worked on the channel's slab (all sequences, all chunk
-// slots), fixed order: bitwise reproducible
-__global__ void scan_rounds_param_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dA,
-                                                float* __restrict__ dD, float* __restrict__ dbias, int Di, int H, int nslab, int nw_used) {
-    __shared__ float4 red[8][32];
-    __shared__ float redb[8][32];
-    const int slab = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// slots), fixed order: bitwise reproducible.  One CTA of 32 warps per slab; warp v sums partials v, v + 32, ...
+__global__ void __launch_bounds__(1024) scan_rounds_param_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dA,
+                                                                         float* __restrict__ dD, float* __restrict__ dbias, int Di, int H, int B, int TS, int tps,
+                                                                         int nteamchains, int cpr) {
+    __shared__ float4 red[32][32];
+    __shared__ float redb[32][32];
+    const int slab = blockIdx.x, lane = threadIdx.x & 31, v = threadIdx.x >> 5;
+    const int tslab = slab / TS, member = slab % TS;
+    const int n = cpr * B;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float accb = 0.f;
-    // warp gw works on slab (gw % nchains) % nslab = gw % nslab (nchains is a multiple of nslab)
-    int idx = 0;
-    for (int gw = slab; gw < nw_used; gw += nslab, ++idx) {
-        if ((idx & 7) != w) continue;
-        const float4 v = part[(size_t)gw * 32 + lane];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        accb += part_b[(size_t)gw * 32 + lane];
+    for (int q0 = v; q0 < n; q0 += 128) {
+        float4 t[4];
+        float tb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * 32;
+            t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            tb[u] = 0.f;
+            if (q < n) {
+                const int slot = q / B, b = q % B;
+                const size_t gw = ((size_t)slot * nteamchains + (size_t)b * tps + tslab) * TS + member;
+                t[u] = part[gw * 32 + lane];
+                tb[u] = part_b[gw * 32 + lane];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; accb += tb[u]; }
     }
-    red[w][lane] = acc;
-    redb[w][lane] = accb;
+    red[v][lane] = acc;
+    redb[v][lane] = accb;
     __syncthreads();
-    if (w == 0) {
-        float4 s = red[0][lane];
+    if (v == 0) {
+        float4 sum = red[0][lane];
         float sb = redb[0][lane];
-        for (int i = 1; i < 8; ++i) { s.x += red[i][lane].x; s.y += red[i][lane].y; s.z += red[i][lane].z; s.w += red[i][lane].w; sb += redb[i][lane]; }
+        for (int i = 1; i < 32; ++i) { sum.x += red[i][lane].x; sum.y += red[i][lane].y; sum.z += red[i][lane].z; sum.w += red[i][lane].w; sb += redb[i][lane]; }
         const int c0 = slab * 64 + 2 * lane;
-        if (c0 < Di) { dA[c0] = s.x; dA[c0 + 1] = s.y; dD[c0] = s.z; dD[c0 + 1] = s.w; }
+        if (c0 < Di) { dA[c0] = sum.x; dA[c0 + 1] = sum.y; dD[c0] = sum.z; dD[c0 + 1] = sum.w; }
         // lanes (head lane >> 3, token lane & 7): sum the 8 token lanes of a head
         sb += __shfl_xor_sync(0xffffffffu, sb, 4);
         sb += __shfl_xor_sync(0xffffffffu, sb, 2);
@@ -775,38 +831,36 @@ __global__ void scan_rounds_param_reduce_kernel(const float4* __restrict__ part,
 
 // ---- host ----------------------------------------------------------------------------------------------------------
 struct RoundsCfg {
-    int nslab, nchains, wpc, nw, cpr, nw_used, Tc, nck, nrounds, nseg, nck8, L8;
+    int nslab, nchains, TS, tps, nteamchains, teams_per_cta, nteams, cpr, Tc, nck, nrounds, nseg, nck8, L8, grid, block, nw_total;
     size_t smem, off_agg, off_segagg, off_segcarry, off_carry, off_cnt, cnt_bytes, off_part, off_part_b, total;
 };
 
 constexpr size_t SMEM_MAX = 227 * 1024;
 
-// warps per CTA (one CTA per SM, warps are independent): as many as the shared-memory rings and the register file admit
-void warps_per_cta(int dtype, bool bwd, bool yssm, int warp_cap, int* wpc, size_t* smem) {
-    const int es = dtype == AB_F32 ? 4 : 2;
-    const size_t tile = (size_t)RG * 64 * es;
-    const size_t per_warp = (size_t)NST * (bwd ? (yssm ? 6 : 5) : 4) * tile + NST * 8;
-    const int reg_cap = bwd ? (es == 2 ? 16 : 8) : (es == 2 ? 24 : 16);       // the kernels' __launch_bounds__
-    int w = (int)((SMEM_MAX - 1024) / per_warp);
-    if (w > reg_cap) w = reg_cap;
-    if (warp_cap > 0 && w > warp_cap) w = warp_cap;
-    if (w < 1) w = 1;
-    *wpc = w;
-    *smem = (size_t)w * per_warp + 128;
+// slabs per team: wide boxes (few, large TMA requests) against slabs lost to padding the last team of a sequence
+int choose_ts(int nslab) {
+    int best = 1;
+    double best_score = -1.0;
+    for (int ts = 1; ts <= 4 && ts <= nslab; ++ts) {
+        const int tps = (nslab + ts - 1) / ts;
+        const double score = (double)nslab / (tps * ts) * (ts >= 3 ? 1.0 : ts == 2 ? 0.9 : 0.75);
+        if (score >= best_score) { best_score = score; best = ts; }
+    }
+    return best;
 }
 
 // Chunk length: few, well-filled rounds (the grid is persistent: a partly filled last round idles warps), at least two
-// rounds where the sequence allows it (the prefix of round r hides behind P1 of round r + 1), and a round's P1 operands
-// small against L2.
+// rounds where the sequence allows it (the prefix of round r hides behind P1 of round r + 1); every visit of a chunk
+// starts its TMA ring cold, so short chunks pay a latency per visit.
 int choose_tc(int L, int cpr, int tc_hint) {
     if (tc_hint >= RG) return (tc_hint / RG) * RG;
     int best = RG;
     double best_score = -1.0;
-    for (int tc = RG; tc <= 128; tc += RG) {
+    for (int tc = RG; tc <= 256; tc += RG) {
         const int nck = (int)ab_ceil_div(L, tc);
         const int rounds = (int)ab_ceil_div(nck, cpr);
         double score = (double)L / ((double)rounds * cpr * tc);            // fill
-        score *= (double)tc / (tc + 4.0);                                  // per-chunk overhead ~ 4 tokens of work
+        score *= (double)tc / (tc + 24.0);                                 // per-visit overhead ~ 3 groups of work (ring fill, prefix wait)
         if (rounds == 1 && nck > 1) score *= 0.9;                          // exposed prefix
         if (score > best_score) { best_score = score; best = tc; }
     }
@@ -814,19 +868,34 @@ int choose_tc(int L, int cpr, int tc_hint) {
 }
 
 int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap, int tc_hint, RoundsCfg& c) {
+    const int es = dtype == AB_F32 ? 4 : 2;
     c.nslab = (int)ab_ceil_div(Di, 64);
     c.nchains = B * c.nslab;
-    warps_per_cta(dtype, bwd, yssm, warp_cap, &c.wpc, &c.smem);
-    c.nw = ab_num_sms() * c.wpc;
-    AB_REQUIRE(c.nchains <= c.nw, "selective scan: %d chains exceed the %d resident warps; split the batch", c.nchains, c.nw);
-    c.cpr = c.nw / c.nchains;
+    c.TS = choose_ts(c.nslab);
+    c.tps = (c.nslab + c.TS - 1) / c.TS;
+    c.nteamchains = B * c.tps;
+    const size_t tile = (size_t)RG * c.TS * 64 * es;
+    const size_t per_team = (size_t)NST * (bwd ? (yssm ? 6 : 5) : 4) * tile + NST * 8;
+    int reg_cap = bwd ? (es == 2 ? 16 : 8) : (es == 2 ? 24 : 16);          // warps per CTA under the kernels' __launch_bounds__
+    if (warp_cap > 0 && reg_cap > warp_cap) reg_cap = warp_cap;
+    int tpc = (int)((SMEM_MAX - 1024) / per_team);
+    if (tpc > reg_cap / c.TS) tpc = reg_cap / c.TS;
+    if (tpc > 15) tpc = 15;                                                 // named barriers 1..15
+    if (tpc < 1) tpc = 1;
+    c.teams_per_cta = tpc;
+    c.smem = (size_t)tpc * per_team + 128;
+    c.block = tpc * c.TS * 32;
+    c.nteams = ab_num_sms() * tpc;
+    AB_REQUIRE(c.nteamchains <= c.nteams, "selective scan: %d (sequence, slab group) chains exceed the %d resident teams; split the batch", c.nteamchains, c.nteams);
+    c.cpr = c.nteams / c.nteamchains;
     c.nck8 = (int)ab_ceil_div(L, RG);
     c.L8 = c.nck8 * RG;
     if (c.cpr > c.nck8) c.cpr = c.nck8;
     c.Tc = choose_tc(L, c.cpr, tc_hint);
     c.nck = (int)ab_ceil_div(L, c.Tc);
     if (c.cpr > c.nck) c.cpr = c.nck;
-    c.nw_used = c.cpr * c.nchains;
+    c.grid = (int)ab_ceil_div((int64_t)c.cpr * c.nteamchains, tpc);
+    c.nw_total = c.grid * tpc * c.TS;
     c.nrounds = (int)ab_ceil_div(c.nck, c.cpr);
     c.nseg = (int)ab_ceil_div(c.cpr, RSEG);
     size_t o = 0;
@@ -834,8 +903,8 @@ int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap,
     c.off_segagg = o;   o += (size_t)2 * c.nchains * c.nseg * 32 * sizeof(float4);
     c.off_segcarry = o; o += (size_t)2 * c.nchains * c.nseg * 32 * sizeof(float2);
     c.off_carry = o;    o += (size_t)c.nchains * 32 * sizeof(float2);
-    c.off_part = o;     o += (size_t)c.nw_used * 32 * sizeof(float4);
-    c.off_part_b = o;   o += (size_t)c.nw_used * 32 * sizeof(float);
+    c.off_part = o;     o += (size_t)c.nw_total * 32 * sizeof(float4);
+    c.off_part_b = o;   o += (size_t)c.nw_total * 32 * sizeof(float);
     c.off_cnt = o;
     c.cnt_bytes = (size_t)c.nrounds * c.nchains * (c.nseg + 2) * sizeof(unsigned);
     o += ab_round_up((int64_t)c.cnt_bytes, 256);
@@ -855,7 +924,7 @@ void fill_sync(RoundsParams& p, const RoundsCfg& c, void* ws) {
     p.cnt2 = p.cnt1 + (size_t)c.nrounds * c.nchains * c.nseg;
     p.flag = p.cnt2 + (size_t)c.nrounds * c.nchains;
     p.nslab = c.nslab; p.nchains = c.nchains; p.Tc = c.Tc; p.nck = c.nck; p.cpr = c.cpr; p.nrounds = c.nrounds; p.nseg = c.nseg;
-    p.nw_used = c.nw_used; p.nck8 = c.nck8; p.L8 = c.L8;
+    p.nw_used = c.nw_total; p.nck8 = c.nck8; p.L8 = c.L8; p.tps = c.tps; p.nteamchains = c.nteamchains;
 }
 
 int g_tc_hint_fwd = 0, g_tc_hint_bwd = 0, g_warp_cap = 0;
@@ -867,13 +936,13 @@ int common_checks(const char* who, int B, int L, int Di, int H, int dtype) {
     return AB_OK;
 }
 
-// 3-D tensor map over [B, L, Di] rows (row stride in elements), box = 64 channels x `rows` tokens.  Encoding costs a few
-// microseconds of host time per map and a launch uses up to ten: recently used maps are kept (a training loop presents the
-// same buffers again and again through torch's caching allocator).
+// 3-D tensor map over [B, L, Di] rows (row stride in elements), box = `cols` channels x `rows` tokens.  Encoding costs a
+// few microseconds of host time per map and a launch uses up to ten: recently used maps are kept (a training loop presents
+// the same buffers again and again through torch's caching allocator).
 struct MapKey {
-    const void* base; int dtype, B, L, Di, rows; int64_t stride;
+    const void* base; int dtype, B, L, Di, rows, cols; int64_t stride;
     bool operator==(const MapKey& o) const {
-        return base == o.base && dtype == o.dtype && B == o.B && L == o.L && Di == o.Di && rows == o.rows && stride == o.stride;
+        return base == o.base && dtype == o.dtype && B == o.B && L == o.L && Di == o.Di && rows == o.rows && cols == o.cols && stride == o.stride;
     }
 };
 constexpr int MAP_CACHE = 128;
@@ -881,11 +950,11 @@ struct MapCache { MapKey key[MAP_CACHE]; CUtensorMap map[MAP_CACHE]; int used = 
 MapCache g_maps;
 std::mutex g_maps_mutex;
 
-int map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di, int64_t stride, int rows) {
+int map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di, int64_t stride, int rows, int cols) {
     const int es = dtype == AB_F32 ? 4 : 2;
     AB_REQUIRE(((uintptr_t)base % 16) == 0 && (stride * es) % 16 == 0 && stride >= Di,
                "selective scan: activations must be 16-byte aligned with a 16-byte aligned row stride >= Di (stride %lld elements)", (long long)stride);
-    const MapKey k{base, dtype, B, L, Di, rows, stride};
+    const MapKey k{base, dtype, B, L, Di, rows, cols, stride};
     {
         std::lock_guard<std::mutex> g(g_maps_mutex);
         for (int i = 0; i < g_maps.used; ++i)
@@ -893,7 +962,7 @@ int map3(CUtensorMap* m, const void* base, int dtype, int B, int L, int Di, int6
     }
     uint64_t dims[3] = {(uint64_t)Di, (uint64_t)L, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)stride * es, (uint64_t)stride * es * L};
-    uint32_t box[3] = {64u, (uint32_t)rows, 1u};
+    uint32_t box[3] = {(uint32_t)cols, (uint32_t)rows, 1u};
     if (int e = ab_encode_tmap(m, dtype == AB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     std::lock_guard<std::mutex> g(g_maps_mutex);
@@ -907,6 +976,45 @@ template <typename K>
 int set_smem(K kernel, size_t bytes) {
     AB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return AB_OK;
+}
+
+struct FwdLaunch {
+    CUtensorMap xa, b, b32, c, z, y, ys;
+};
+template <typename T, bool YS, int TS>
+int launch_fwd(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    if (int e = set_smem(scan_rounds_fwd_kernel<T, YS, TS>, c.smem)) return e;
+    scan_rounds_fwd_kernel<T, YS, TS><<<c.grid, c.block, c.smem, stream>>>(m.xa, m.b, m.b32, m.c, m.z, m.y, m.ys, p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+template <typename T, bool YS>
+int launch_fwd_ts(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    switch (c.TS) {
+        case 1: return launch_fwd<T, YS, 1>(m, p, c, stream);
+        case 2: return launch_fwd<T, YS, 2>(m, p, c, stream);
+        case 3: return launch_fwd<T, YS, 3>(m, p, c, stream);
+        default: return launch_fwd<T, YS, 4>(m, p, c, stream);
+    }
+}
+struct BwdLaunch {
+    CUtensorMap xa, b, c, z, g, s, dxa, db, dc, dz;
+};
+template <typename T, bool YS, int TS>
+int launch_bwd(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    if (int e = set_smem(scan_rounds_bwd_kernel<T, YS, TS>, c.smem)) return e;
+    scan_rounds_bwd_kernel<T, YS, TS><<<c.grid, c.block, c.smem, stream>>>(m.xa, m.b, m.c, m.z, m.g, m.s, m.dxa, m.db, m.dc, m.dz, p);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+template <typename T, bool YS>
+int launch_bwd_ts(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    switch (c.TS) {
+        case 1: return launch_bwd<T, YS, 1>(m, p, c, stream);
+        case 2: return launch_bwd<T, YS, 2>(m, p, c, stream);
+        case 3: return launch_bwd<T, YS, 3>(m, p, c, stream);
+        default: return launch_bwd<T, YS, 4>(m, p, c, stream);
+    }
 }
 
 }  // namespace
@@ -956,30 +1064,19 @@ extern "C" int ab_ssm_scan_fwd(const void* xa, int64_t xa_stride, const void* dl
     p.dt_bias = dt_bias; p.A_log = A_log; p.D = D; p.h0 = h0; p.h_last = h_last;
     p.hck = state;
     p.delta = state + (size_t)B * c.nck8 * Di;
-    CUtensorMap m_xa, m_b, m_b32, m_c, m_z, m_y, m_ys;
-    if (int e = map3(&m_xa, xa, dtype, B, L, Di, xa_stride, RG)) return e;
-    if (int e = map3(&m_b, Bm, dtype, B, L, Di, bc_stride, RG)) return e;
-    if (int e = map3(&m_b32, Bm, dtype, B, L, Di, bc_stride, P1_ROWS)) return e;
-    if (int e = map3(&m_c, Cm, dtype, B, L, Di, bc_stride, RG)) return e;
-    if (int e = map3(&m_z, z, dtype, B, L, Di, z_stride, RG)) return e;
-    if (int e = map3(&m_y, y, dtype, B, L, Di, Di, RG)) return e;
-    m_ys = m_y;
-    if (y_ssm) { if (int e = map3(&m_ys, y_ssm, dtype, B, L, Di, Di, RG)) return e; }
+    FwdLaunch m;
+    const int cols = c.TS * 64;
+    if (int e = map3(&m.xa, xa, dtype, B, L, Di, xa_stride, RG, cols)) return e;
+    if (int e = map3(&m.b, Bm, dtype, B, L, Di, bc_stride, RG, cols)) return e;
+    if (int e = map3(&m.b32, Bm, dtype, B, L, Di, bc_stride, P1_ROWS, cols)) return e;
+    if (int e = map3(&m.c, Cm, dtype, B, L, Di, bc_stride, RG, cols)) return e;
+    if (int e = map3(&m.z, z, dtype, B, L, Di, z_stride, RG, cols)) return e;
+    if (int e = map3(&m.y, y, dtype, B, L, Di, Di, RG, cols)) return e;
+    m.ys = m.y;
+    if (y_ssm) { if (int e = map3(&m.ys, y_ssm, dtype, B, L, Di, Di, RG, cols)) return e; }
     AB_CHECK_CUDA(cudaMemsetAsync(p.cnt1, 0, c.cnt_bytes, stream));
-    const unsigned grid = (unsigned)ab_ceil_div(c.nw_used, c.wpc), block = (unsigned)c.wpc * 32;
-#define AB_LAUNCH_FWD(T, YS)                                                                                              \
-    do {                                                                                                                 \
-        if (int e = set_smem(scan_rounds_fwd_kernel<T, YS>, c.smem)) return e;                                           \
-        scan_rounds_fwd_kernel<T, YS><<<grid, block, c.smem, stream>>>(m_xa, m_b, m_b32, m_c, m_z, m_y, m_ys, p);        \
-    } while (0)
-    if (dtype == AB_F32) {
-        if (y_ssm) AB_LAUNCH_FWD(float, true); else AB_LAUNCH_FWD(float, false);
-    } else {
-        if (y_ssm) AB_LAUNCH_FWD(__nv_bfloat16, true); else AB_LAUNCH_FWD(__nv_bfloat16, false);
-    }
-#undef AB_LAUNCH_FWD
-    AB_LAUNCH_CHECK();
-    return AB_OK;
+    if (dtype == AB_F32) return y_ssm ? launch_fwd_ts<float, true>(m, p, c, stream) : launch_fwd_ts<float, false>(m, p, c, stream);
+    return y_ssm ? launch_fwd_ts<__nv_bfloat16, true>(m, p, c, stream) : launch_fwd_ts<__nv_bfloat16, false>(m, p, c, stream);
 }
 
 extern "C" int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm, const void* Cm, int64_t bc_stride,
@@ -1009,33 +1106,25 @@ extern "C" int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm
     p.A_log = A_log; p.D = D;
     p.hck = const_cast<float*>(state);
     p.delta = const_cast<float*>(state) + (size_t)B * c.nck8 * Di;
-    CUtensorMap m_xa, m_b, m_c, m_z, m_g, m_s, m_dxa, m_db, m_dc, m_dz;
-    if (int e = map3(&m_xa, xa, dtype, B, L, Di, xa_stride, RG)) return e;
-    if (int e = map3(&m_b, Bm, dtype, B, L, Di, bc_stride, RG)) return e;
-    if (int e = map3(&m_c, Cm, dtype, B, L, Di, bc_stride, RG)) return e;
-    if (int e = map3(&m_z, z, dtype, B, L, Di, z_stride, RG)) return e;
-    if (int e = map3(&m_g, dout, dtype, B, L, Di, Di, RG)) return e;
-    m_s = m_g;
-    if (dyssm) { if (int e = map3(&m_s, dyssm, dtype, B, L, Di, Di, RG)) return e; }
-    if (int e = map3(&m_dxa, dxa, dtype, B, L, Di, dxa_stride, RG)) return e;
-    if (int e = map3(&m_db, dBm, dtype, B, L, Di, dbc_stride, RG)) return e;
-    if (int e = map3(&m_dc, dCm, dtype, B, L, Di, dbc_stride, RG)) return e;
-    if (int e = map3(&m_dz, dz, dtype, B, L, Di, dz_stride, RG)) return e;
+    BwdLaunch m;
+    const int cols = c.TS * 64;
+    if (int e = map3(&m.xa, xa, dtype, B, L, Di, xa_stride, RG, cols)) return e;
+    if (int e = map3(&m.b, Bm, dtype, B, L, Di, bc_stride, RG, cols)) return e;
+    if (int e = map3(&m.c, Cm, dtype, B, L, Di, bc_stride, RG, cols)) return e;
+    if (int e = map3(&m.z, z, dtype, B, L, Di, z_stride, RG, cols)) return e;
+    if (int e = map3(&m.g, dout, dtype, B, L, Di, Di, RG, cols)) return e;
+    m.s = m.g;
+    if (dyssm) { if (int e = map3(&m.s, dyssm, dtype, B, L, Di, Di, RG, cols)) return e; }
+    if (int e = map3(&m.dxa, dxa, dtype, B, L, Di, dxa_stride, RG, cols)) return e;
+    if (int e = map3(&m.db, dBm, dtype, B, L, Di, dbc_stride, RG, cols)) return e;
+    if (int e = map3(&m.dc, dCm, dtype, B, L, Di, dbc_stride, RG, cols)) return e;
+    if (int e = map3(&m.dz, dz, dtype, B, L, Di, dz_stride, RG, cols)) return e;
     AB_CHECK_CUDA(cudaMemsetAsync(p.cnt1, 0, c.cnt_bytes, stream));
-    const unsigned grid = (unsigned)ab_ceil_div(c.nw_used, c.wpc), block = (unsigned)c.wpc * 32;
-#define AB_LAUNCH_BWD(T, YS)                                                                                              \
-    do {                                                                                                                 \
-        if (int e = set_smem(scan_rounds_bwd_kernel<T, YS>, c.smem)) return e;                                           \
-        scan_rounds_bwd_kernel<T, YS><<<grid, block, c.smem, stream>>>(m_xa, m_b, m_c, m_z, m_g, m_s, m_dxa, m_db, m_dc, m_dz, p); \
-    } while (0)
-    if (dtype == AB_F32) {
-        if (dyssm) AB_LAUNCH_BWD(float, true); else AB_LAUNCH_BWD(float, false);
-    } else {
-        if (dyssm) AB_LAUNCH_BWD(__nv_bfloat16, true); else AB_LAUNCH_BWD(__nv_bfloat16, false);
-    }
-#undef AB_LAUNCH_BWD
-    AB_LAUNCH_CHECK();
-    scan_rounds_param_reduce_kernel<<<c.nslab, 256, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, Di, H, c.nslab, c.nw_used);
+    int e;
+    if (dtype == AB_F32) e = dyssm ? launch_bwd_ts<float, true>(m, p, c, stream) : launch_bwd_ts<float, false>(m, p, c, stream);
+    else e = dyssm ? launch_bwd_ts<__nv_bfloat16, true>(m, p, c, stream) : launch_bwd_ts<__nv_bfloat16, false>(m, p, c, stream);
+    if (e) return e;
+    scan_rounds_param_reduce_kernel<<<c.nslab, 1024, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, Di, H, B, c.TS, c.tps, c.nteamchains, c.cpr);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
