@@ -39,7 +39,7 @@ SIGNATURES = {
     "ab_selective_scan_bwd": (I, [P, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, I64, P, P, P, P, P, SZ, U32, I,
                                   I, I, I, I, I, P]),
     "ab_ssm_scan_plan": (I, [I, I, I, I, P, P]),
-    "ab_ssm_scan_tune": (I, [I, I, I]),
+    "ab_ssm_scan_tune": (I, [I, I, I, I, I]),
     "ab_ssm_scan_fwd": (I, [P, I64, P, I64, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
     "ab_ssm_scan_bwd": (I, [P, I64, P, P, I64, P, I64, P, P, P, P, P, P, I64, P, P, I64, P, I64, P, I64, I, P, P, P, P, SZ,
                             I, I, I, I, I, P]),

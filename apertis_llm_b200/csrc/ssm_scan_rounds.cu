@@ -176,23 +176,27 @@ __device__ __forceinline__ void publish_and_prefix(const RoundsParams& p, int r,
     }
     last1 = __shfl_sync(0xffffffffu, last1, 0);
     if (!last1) return;
-    // ---- level 1: exclusive prefixes inside the segment, segment total
+    // ---- level 1: exclusive prefixes inside the segment, segment total (loads in batches of 8: each is an L2 round trip)
     f2 Pex = f2_bcast(1.f), Sex = f2_bcast(0.f);
     {
         const int n_in_seg = min(RSEG, n_r - seg * RSEG);
         float4* a = agg + (size_t)(seg * RSEG) * 32 + lane;
-        float4 v = __ldcg(a);
-        for (int j = 0; j < n_in_seg; ++j) {
-            float4 nv = v;
-            if (j + 1 < n_in_seg) nv = __ldcg(a + (size_t)(j + 1) * 32);
-            float e0, e1, g0, g1;
-            f2_unpack(Pex, e0, e1);
-            f2_unpack(Sex, g0, g1);
-            __stcg(a + (size_t)j * 32, make_float4(e0, e1, g0, g1));
-            const f2 vp = f2_pack(v.x, v.y), vs = f2_pack(v.z, v.w);
-            Sex = f2_fma(vp, Sex, vs);
-            Pex = f2_mul(Pex, vp);
-            v = nv;
+        for (int j0 = 0; j0 < n_in_seg; j0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (j0 + u < n_in_seg) ? __ldcg(a + (size_t)(j0 + u) * 32) : make_float4(1.f, 1.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (j0 + u < n_in_seg) {
+                    float e0, e1, g0, g1;
+                    f2_unpack(Pex, e0, e1);
+                    f2_unpack(Sex, g0, g1);
+                    __stcg(a + (size_t)(j0 + u) * 32, make_float4(e0, e1, g0, g1));
+                    const f2 vp = f2_pack(v[u].x, v[u].y), vs = f2_pack(v[u].z, v[u].w);
+                    Sex = f2_fma(vp, Sex, vs);
+                    Pex = f2_mul(Pex, vp);
+                }
+            }
         }
     }
     float4* segagg = p.segagg + ((size_t)(par * p.nchains + chain) * p.nseg) * 32;
@@ -220,12 +224,19 @@ __device__ __forceinline__ void publish_and_prefix(const RoundsParams& p, int r,
         h = f2_pack(c.x, c.y);
     }
     float2* segcarry = p.segcarry + ((size_t)(par * p.nchains + chain) * p.nseg) * 32;
-    for (int s = 0; s < nseg_r; ++s) {
-        const float4 v = __ldcg(&segagg[(size_t)s * 32 + lane]);
-        float h0, h1;
-        f2_unpack(h, h0, h1);
-        __stcg(&segcarry[(size_t)s * 32 + lane], make_float2(h0, h1));
-        h = f2_fma(f2_pack(v.x, v.y), h, f2_pack(v.z, v.w));
+    for (int s0 = 0; s0 < nseg_r; s0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (s0 + u < nseg_r) ? __ldcg(&segagg[(size_t)(s0 + u) * 32 + lane]) : make_float4(1.f, 1.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (s0 + u < nseg_r) {
+                float h0, h1;
+                f2_unpack(h, h0, h1);
+                __stcg(&segcarry[(size_t)(s0 + u) * 32 + lane], make_float2(h0, h1));
+                h = f2_fma(f2_pack(v[u].x, v[u].y), h, f2_pack(v[u].z, v[u].w));
+            }
+        }
     }
     {
         float h0, h1;
@@ -250,9 +261,12 @@ __device__ __forceinline__ f2 incoming_state(const RoundsParams& p, int r, int c
 
 // ====================================================================================================================
 // team TMA pipeline
+//   A team's work is one stream of ITEMS: P1 of round 0, P1 of round 1, P2 of round 0, P1 of round 2, ... each phase cut
+//   into items of one ring stage (forward P1: 32 tokens of B; everything else: 8 tokens of every operand of the phase).
+//   The team leader issues the loads of item k - 1 + NST while item k is being computed, ACROSS phase boundaries (the
+//   addresses of a phase do not depend on the prefix it waits for), so the ring never drains and a visit of a chunk
+//   costs no cold start.  Results are written in place over the consumed operands and stored by TMA from the stage.
 // ====================================================================================================================
-constexpr int NST = 2;                // stages of a team's ring: group g computes from stage g % NST while g + 1 is in flight
-
 template <typename T, int TS> struct Tile {
     static constexpr int ROW_RAW = TS * 32;                          // row pitch in channel pairs
     static constexpr int BYTES = RG * TS * 64 * (int)sizeof(T);      // one operand of one group of 8 tokens
@@ -264,6 +278,7 @@ struct Pipe {
     uint32_t bar;            // shared-space address of mbarrier 0
     uint32_t phases;         // bit s: parity the next wait on stage s expects
     uint32_t stage_bytes;
+    int k;                   // items consumed so far (item k lives in stage k % NST)
     __device__ __forceinline__ uint32_t saddr(int st, int off) const { return sbase + (uint32_t)st * stage_bytes + (uint32_t)off; }
     __device__ __forceinline__ unsigned char* gaddr(int st) const { return base + (size_t)st * stage_bytes; }
     __device__ __forceinline__ uint32_t baddr(int st) const { return bar + 8u * (uint32_t)st; }
@@ -298,6 +313,43 @@ struct Who {
     bool real, leader, cv;             // real: the slab exists (teams are padded to TS slabs); cv: this lane's channel pair exists
 };
 
+constexpr int P1_ROWS = 4 * RG;       // forward P1 reads B in pieces of 32 tokens (one stage = 4 operand tiles = 32 rows)
+
+// Walks a team's phases in execution order: P1(0), then for r = 0 .. R-1: P1(r+1) (if any), P2(r).  Used twice per team:
+// by every warp to run the phases, and by the leader, NST items ahead, to issue their loads.
+template <bool BWD>
+struct Cursor {
+    int ph, kind, r, i, n, t0, tend, n_r;      // kind: 0 = P1, 1 = P2, -1 = end;  item i of n in chunk [t0, tend)
+    __device__ __forceinline__ void begin(const RoundsParams& p, int slot) { ph = -1; kind = 0; next_phase(p, slot); }
+    __device__ __forceinline__ void next_phase(const RoundsParams& p, int slot) {
+        for (;;) {
+            ++ph;
+            if (ph == 0) { kind = 0; r = 0; }
+            else {
+                const int q = (ph - 1) >> 1;
+                if (q >= p.nrounds) { kind = -1; n = 0; i = 0; return; }
+                if ((ph - 1) & 1) { kind = 1; r = q; }
+                else { kind = 0; r = q + 1; if (r >= p.nrounds) continue; }
+            }
+            n_r = min(p.cpr, p.nck - r * p.cpr);
+            if (slot >= n_r) continue;                       // the last round may not reach this team
+            const int pos = BWD ? p.nck - 1 - (r * p.cpr + slot) : r * p.cpr + slot;
+            t0 = pos * p.Tc;
+            tend = min(t0 + p.Tc, p.L);
+            const int rows = (!BWD && kind == 0) ? P1_ROWS : RG;
+            n = (tend - t0 + rows - 1) / rows;
+            i = 0;
+            if (n > 0) return;
+        }
+    }
+    // first token of item i (the backward walks a chunk's groups last to first)
+    __device__ __forceinline__ int token() const {
+        if (BWD) return t0 + (n - 1 - i) * RG;
+        return t0 + i * (kind == 0 ? P1_ROWS : RG);
+    }
+    __device__ __forceinline__ void advance(const RoundsParams& p, int slot) { if (++i >= n) next_phase(p, slot); }
+};
+
 // ====================================================================================================================
 // forward
 // ====================================================================================================================
@@ -312,7 +364,51 @@ struct FwdCtx {
     int L;
 };
 
-constexpr int P1_ROWS = 4 * RG;       // forward P1 reads B in pieces of 32 tokens (one stage = 4 operand tiles = 32 rows)
+// operand tiles of a forward P2 stage
+constexpr int FA_B = 0, FA_X = 1, FA_C = 2, FA_Z = 3;
+
+struct FwdMaps {
+    const CUtensorMap *xa, *b, *b32, *c, *z, *y, *ys;
+};
+
+template <typename T, int TS, int NST>
+struct FwdFeeder {
+    const RoundsParams& p;
+    const Who& w;
+    Pipe& pp;
+    const FwdMaps& m;
+    Cursor<false> cur;
+    uint64_t pol_keep, pol_stream;
+    __device__ __forceinline__ FwdFeeder(const RoundsParams& p_, const Who& w_, Pipe& pp_, const FwdMaps& m_, uint64_t pk, uint64_t ps)
+        : p(p_), w(w_), pp(pp_), m(m_), pol_keep(pk), pol_stream(ps) {}
+    __device__ __forceinline__ void issue_one(int st) {
+        if (cur.kind < 0) return;
+        constexpr int TB = Tile<T, TS>::BYTES;
+        const int t = cur.token();
+        mbar_expect_tx_u32(pp.baddr(st), 4 * TB);
+        if (cur.kind == 0) {
+            tma_load(pp.saddr(st, 0), m.b32, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+        } else {
+            tma_load(pp.saddr(st, FA_B * TB), m.b, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, FA_X * TB), m.xa, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, FA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, FA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        }
+        cur.advance(p, w.slot);
+    }
+    __device__ __forceinline__ void prime() {
+        cur.begin(p, w.slot);
+#pragma unroll
+        for (int i = 0; i < NST; ++i) issue_one(i);
+    }
+    // called by the leader while item k (k >= 1) is being computed: the stage of item k - 1 (consumed, its stores issued
+    // when it finished) takes item k - 1 + NST
+    __device__ __forceinline__ void refill(int k) {
+        if (k < 1) return;
+        bulk_wait_read<0>();
+        issue_one((k - 1) % NST);
+    }
+};
 
 template <typename T>
 __device__ __forceinline__ float dlog_fetch(const FwdCtx<T>& c, const Who& w, int dls, int tb, int tend) {
@@ -327,33 +423,18 @@ __device__ __forceinline__ float delta_finish(const FwdCtx<T>& c, const Who& w, 
     return d;
 }
 
-template <typename T, int TS>
-__device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c, const Who& w, Pipe& pp, const CUtensorMap* tm_b32, int r,
-                                       uint64_t pol_keep, f2 init) {
-    const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (w.slot >= n_r) return;
-    const int t0 = (r * p.cpr + w.slot) * p.Tc;
-    const int tend = min(t0 + p.Tc, c.L);
-    const int npieces = (tend - t0 + P1_ROWS - 1) / P1_ROWS;
+template <typename T, int TS, int NST, typename Feeder>
+__device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c, const Who& w, Pipe& pp, Feeder& fd, const Cursor<false>& ph, f2 init) {
+    const int t0 = ph.t0, tend = ph.tend, npieces = ph.n;
     const int dls = p.dlog_stride;
     const int hsel = w.lane >> 3;
-    auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), 4 * Tile<T, TS>::BYTES);
-        tma_load(pp.saddr(st, 0), tm_b32, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
-    };
-    if (w.leader) {
-        bulk_wait_read<0>();              // stores of the previous P2 have read their stages
-#pragma unroll
-        for (int i = 0; i < NST; ++i)
-            if (i < npieces) issue(i, t0 + i * P1_ROWS);
-    }
     f2 S = f2_bcast(0.f);
     float sumd = 0.f;
     float raw[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) raw[g] = dlog_fetch<T>(c, w, dls, t0 + g * RG, tend);
     for (int pc = 0; pc < npieces; ++pc) {
-        const int st = pc % NST;
+        const int st = pp.k % NST;
         const int tp = t0 + pc * P1_ROWS;
         float dm[4];
 #pragma unroll
@@ -361,6 +442,7 @@ __device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c
 #pragma unroll
         for (int g = 0; g < 4; ++g) raw[g] = dlog_fetch<T>(c, w, dls, tp + P1_ROWS + g * RG, tend);     // next piece: in flight during this one
         pp.wait(st);
+        if (w.leader) fd.refill(pp.k);
         const unsigned char* sb = pp.gaddr(st);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -375,43 +457,20 @@ __device__ __forceinline__ void fwd_p1(const RoundsParams& p, const FwdCtx<T>& c
             }
         }
         team_sync<TS>(w.team_in_cta);
-        if (w.leader && pc + NST < npieces) issue(st, tp + NST * P1_ROWS);
+        ++pp.k;
     }
     if (!w.real) return;
     const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
     float* fin = (p.h_last != nullptr && w.cv) ? p.h_last + (size_t)w.b * p.Di + w.slab * 64 + 2 * w.lane : nullptr;
-    publish_and_prefix(p, r, w.chain, w.slot, n_r, w.lane, P, S, init, fin);
+    publish_and_prefix(p, ph.r, w.chain, w.slot, ph.n_r, w.lane, P, S, init, fin);
 }
 
-// operand tiles of a forward P2 stage
-constexpr int FA_B = 0, FA_X = 1, FA_C = 2, FA_Z = 3;
-
-struct FwdMaps {
-    const CUtensorMap *xa, *b, *b32, *c, *z, *y, *ys;
-};
-
-template <typename T, bool YSSM, int TS>
-__device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c, const Who& w, Pipe& pp, const FwdMaps& m, int r, uint64_t pol_stream) {
-    const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (w.slot >= n_r) return;
-    const int t0 = (r * p.cpr + w.slot) * p.Tc;
-    const int tend = min(t0 + p.Tc, c.L);
-    const int ngroups = (tend - t0 + RG - 1) / RG;
+template <typename T, bool YSSM, int TS, int NST, typename Feeder>
+__device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c, const Who& w, Pipe& pp, Feeder& fd, const FwdMaps& m,
+                                       const Cursor<false>& ph, uint64_t pol_stream) {
+    const int t0 = ph.t0, ngroups = ph.n, r = ph.r;
     const int hsel = w.lane >> 3;
     constexpr int TB = Tile<T, TS>::BYTES;
-    auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), 4 * TB);
-        tma_load(pp.saddr(st, FA_B * TB), m.b, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, FA_X * TB), m.xa, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, FA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, FA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-    };
-    if (w.leader) {
-        bulk_wait_read<0>();
-#pragma unroll
-        for (int i = 0; i < NST; ++i)
-            if (i < ngroups) issue(i, t0 + i * RG);           // in flight during the wait for the prefix
-    }
     const float* dsrc = c.delta + (int64_t)(t0 + (w.lane >> 2)) * 4;
     float dnext = w.real ? __ldcg(dsrc) : 0.f;
     f2 h = f2_bcast(0.f);
@@ -421,12 +480,12 @@ __device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c
     }
     float* hck = c.hck + (size_t)(t0 >> 3) * p.Di;
     for (int g = 0; g < ngroups; ++g) {
-        const int st = g % NST;
+        const int st = pp.k % NST;
         const int tb = t0 + g * RG;
         const float dmine = dnext;
         dsrc += RG * 4;
         if (w.real && g + 1 < ngroups) dnext = __ldcg(dsrc);          // next group's delta: in flight during this group
-        if (w.real && w.cv) {
+        if (w.cv) {
             float h0, h1;
             f2_unpack(h, h0, h1);
             *reinterpret_cast<float2*>(hck) = make_float2(h0, h1);
@@ -444,11 +503,7 @@ __device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c
             const f2 zv = up(lds_pair<T, TS>(sb, FA_Z, j));
             sts_pair<T, TS>(sb, FA_X, j, f2_mul(yv, f2_mul(zv, f2_sigmoid<T>(zv))));      // y over the consumed x
             if (YSSM) sts_pair<T, TS>(sb, FA_C, j, ys);
-            if (j == RG / 2 - 1 && w.leader && g >= 1 && g - 1 + NST < ngroups) {
-                // half a group after the stores of group g - 1 were issued: refill its stage with group g - 1 + NST
-                bulk_wait_read<0>();
-                issue((g - 1) % NST, tb + (NST - 1) * RG);
-            }
+            if (j == RG / 2 - 1 && w.leader) fd.refill(pp.k);      // half a group after the previous item's stores were issued
         }
         fence_async_smem();
         team_sync<TS>(w.team_in_cta);
@@ -457,10 +512,11 @@ __device__ __forceinline__ void fwd_p2(const RoundsParams& p, const FwdCtx<T>& c
             if (YSSM) tma_store(m.ys, pp.saddr(st, FA_C * TB), w.ch0_team, tb, w.b, pol_stream);
             bulk_commit();
         }
+        ++pp.k;
     }
 }
 
-template <typename T, int TS>
+template <typename T, int TS, int NST>
 __device__ __forceinline__ void who_am_i(const RoundsParams& p, Who& w, Pipe& pp, unsigned char* smem_raw, int ntiles) {
     const int wic = threadIdx.x >> 5, nteams_cta = (blockDim.x >> 5) / TS;
     w.lane = threadIdx.x & 31;
@@ -483,6 +539,7 @@ __device__ __forceinline__ void who_am_i(const RoundsParams& p, Who& w, Pipe& pp
     pp.base = ring + (size_t)(w.member * 32 + w.lane) * sizeof(typename Raw<T>::type);
     pp.bar = ab_smem_u32(smem_raw + (size_t)nteams_cta * NST * pp.stage_bytes) + (uint32_t)w.team_in_cta * NST * 8u;
     pp.phases = 0;
+    pp.k = 0;
     if (w.leader) {
 #pragma unroll
         for (int i = 0; i < NST; ++i) mbar_init_u32(pp.baddr(i), 1);
@@ -491,7 +548,7 @@ __device__ __forceinline__ void who_am_i(const RoundsParams& p, Who& w, Pipe& pp
     __syncthreads();
 }
 
-template <typename T, bool YSSM, int TS>
+template <typename T, bool YSSM, int TS, int NST>
 __global__ void __launch_bounds__(sizeof(T) == 2 ? 768 : 512, 1)
 scan_rounds_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b32,
                        const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_y,
@@ -499,7 +556,7 @@ scan_rounds_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Who w;
     Pipe pp;
-    who_am_i<T, TS>(p, w, pp, smem_raw, 4);
+    who_am_i<T, TS, NST>(p, w, pp, smem_raw, 4);
     if (w.slot >= p.cpr) return;              // whole teams past the grid's share leave together
     const int lane = w.lane;
     const int c0 = w.slab * 64 + 2 * lane;
@@ -518,9 +575,12 @@ scan_rounds_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
     if (p.h0 != nullptr && w.cv) init = f2_pack(p.h0[(size_t)w.b * p.Di + c0], p.h0[(size_t)w.b * p.Di + c0 + 1]);
     const FwdMaps m{&tm_xa, &tm_b, &tm_b32, &tm_c, &tm_z, &tm_y, &tm_ys};
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-    for (int r = -1; r < p.nrounds; ++r) {
-        if (r + 1 < p.nrounds) fwd_p1<T, TS>(p, c, w, pp, m.b32, r + 1, pol_keep, init);
-        if (r >= 0) fwd_p2<T, YSSM, TS>(p, c, w, pp, m, r, pol_stream);
+    FwdFeeder<T, TS, NST> fd(p, w, pp, m, pol_keep, pol_stream);
+    if (w.leader) fd.prime();
+    Cursor<false> ph;
+    for (ph.begin(p, w.slot); ph.kind >= 0; ph.next_phase(p, w.slot)) {
+        if (ph.kind == 0) fwd_p1<T, TS, NST>(p, c, w, pp, fd, ph, init);
+        else fwd_p2<T, YSSM, TS, NST>(p, c, w, pp, fd, m, ph, pol_stream);
     }
     if (w.leader) bulk_wait_all();
 }
@@ -550,35 +610,59 @@ struct BwdMaps {
     const CUtensorMap *xa, *b, *c, *z, *g, *s, *dxa, *db, *dc, *dz;
 };
 
-template <typename T, bool YSSM, int TS>
-__device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c, const Who& w, Pipe& pp, const BwdMaps& m, int r, uint64_t pol_keep) {
-    const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (w.slot >= n_r) return;
-    const int pos = p.nck - 1 - (r * p.cpr + w.slot);
-    const int t0 = pos * p.Tc;
-    const int tend = min(t0 + p.Tc, c.L);
-    const int ngroups = (tend - t0 + RG - 1) / RG;          // groups are visited last to first: step i handles group ngroups - 1 - i
-    const int hsel = w.lane >> 3;
-    constexpr int TB = Tile<T, TS>::BYTES;
-    auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 4 : 3) * TB);
-        tma_load(pp.saddr(st, BA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
-        tma_load(pp.saddr(st, BA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
-        tma_load(pp.saddr(st, BA_G * TB), m.g, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
-        if (YSSM) tma_load(pp.saddr(st, BA_S * TB), m.s, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
-    };
-    if (w.leader) {
-        bulk_wait_read<0>();
-#pragma unroll
-        for (int i = 0; i < NST; ++i)
-            if (i < ngroups) issue(i, t0 + (ngroups - 1 - i) * RG);
+template <typename T, bool YSSM, int TS, int NST>
+struct BwdFeeder {
+    const RoundsParams& p;
+    const Who& w;
+    Pipe& pp;
+    const BwdMaps& m;
+    Cursor<true> cur;
+    uint64_t pol_keep, pol_stream;
+    __device__ __forceinline__ BwdFeeder(const RoundsParams& p_, const Who& w_, Pipe& pp_, const BwdMaps& m_, uint64_t pk, uint64_t ps)
+        : p(p_), w(w_), pp(pp_), m(m_), pol_keep(pk), pol_stream(ps) {}
+    __device__ __forceinline__ void issue_one(int st) {
+        if (cur.kind < 0) return;
+        constexpr int TB = Tile<T, TS>::BYTES;
+        const int t = cur.token();
+        if (cur.kind == 0) {
+            mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 4 : 3) * TB);
+            tma_load(pp.saddr(st, BA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+            tma_load(pp.saddr(st, BA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+            tma_load(pp.saddr(st, BA_G * TB), m.g, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+            if (YSSM) tma_load(pp.saddr(st, BA_S * TB), m.s, pp.baddr(st), w.ch0_team, t, w.b, pol_keep);
+        } else {
+            mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 6 : 5) * TB);
+            tma_load(pp.saddr(st, BA_B * TB), m.b, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, BA_G * TB), m.g, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, BA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, BA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            tma_load(pp.saddr(st, BA_X * TB), m.xa, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+            if (YSSM) tma_load(pp.saddr(st, BA_S * TB), m.s, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
+        }
+        cur.advance(p, w.slot);
     }
+    __device__ __forceinline__ void prime() {
+        cur.begin(p, w.slot);
+#pragma unroll
+        for (int i = 0; i < NST; ++i) issue_one(i);
+    }
+    __device__ __forceinline__ void refill(int k) {
+        if (k < 1) return;
+        bulk_wait_read<0>();
+        issue_one((k - 1) % NST);
+    }
+};
+
+template <typename T, bool YSSM, int TS, int NST, typename Feeder>
+__device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c, const Who& w, Pipe& pp, Feeder& fd, const Cursor<true>& ph) {
+    const int t0 = ph.t0, ngroups = ph.n;          // groups are visited last to first: step i handles group ngroups - 1 - i
+    const int hsel = w.lane >> 3;
     f2 F = f2_bcast(0.f);
     float sumd = 0.f;
     const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (w.lane >> 2)) * 4;
     float dnext = w.real ? __ldg(dsrc) : 0.f;
     for (int i = 0; i < ngroups; ++i) {
-        const int st = i % NST;
+        const int st = pp.k % NST;
         const float dmine = dnext;
         dsrc -= RG * 4;
         if (w.real && i + 1 < ngroups) dnext = __ldg(dsrc);
@@ -593,41 +677,22 @@ __device__ __forceinline__ void bwd_p1(const RoundsParams& p, const BwdCtx<T>& c
             if (YSSM) dys = f2_add(dys, up(lds_pair<T, TS>(sb, BA_S, j)));
             F = f2_mul(a, f2_fma(up(lds_pair<T, TS>(sb, BA_C, j)), dys, F));
             sumd += d;
+            if (j == RG / 2 && w.leader) fd.refill(pp.k);
         }
         team_sync<TS>(w.team_in_cta);
-        if (w.leader && i + NST < ngroups) issue(st, t0 + (ngroups - 1 - i - NST) * RG);
+        ++pp.k;
     }
     if (!w.real) return;
     const f2 P = f2_ex2(f2_mul(f2_bcast(sumd), c.A2));
-    publish_and_prefix(p, r, w.chain, w.slot, n_r, w.lane, P, F, f2_bcast(0.f), nullptr);
+    publish_and_prefix(p, ph.r, w.chain, w.slot, ph.n_r, w.lane, P, F, f2_bcast(0.f), nullptr);
 }
 
-template <typename T, bool YSSM, int TS>
-__device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c, const Who& w, Pipe& pp, const BwdMaps& m, int r, f2& accA, f2& accD,
-                                       float& accB, uint64_t pol_stream) {
-    const int n_r = min(p.cpr, p.nck - r * p.cpr);
-    if (w.slot >= n_r) return;
-    const int pos = p.nck - 1 - (r * p.cpr + w.slot);
-    const int t0 = pos * p.Tc;
-    const int tend = min(t0 + p.Tc, c.L);
-    const int ngroups = (tend - t0 + RG - 1) / RG;
+template <typename T, bool YSSM, int TS, int NST, typename Feeder>
+__device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c, const Who& w, Pipe& pp, Feeder& fd, const BwdMaps& m,
+                                       const Cursor<true>& ph, f2& accA, f2& accD, float& accB, uint64_t pol_stream) {
+    const int t0 = ph.t0, ngroups = ph.n, r = ph.r;
     const int hsel = w.lane >> 3;
     constexpr int TB = Tile<T, TS>::BYTES;
-    auto issue = [&](int st, int t) {
-        mbar_expect_tx_u32(pp.baddr(st), (YSSM ? 6 : 5) * TB);
-        tma_load(pp.saddr(st, BA_B * TB), m.b, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, BA_G * TB), m.g, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, BA_Z * TB), m.z, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, BA_C * TB), m.c, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        tma_load(pp.saddr(st, BA_X * TB), m.xa, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-        if (YSSM) tma_load(pp.saddr(st, BA_S * TB), m.s, pp.baddr(st), w.ch0_team, t, w.b, pol_stream);
-    };
-    if (w.leader) {
-        bulk_wait_read<0>();
-#pragma unroll
-        for (int i = 0; i < NST; ++i)
-            if (i < ngroups) issue(i, t0 + (ngroups - 1 - i) * RG);           // in flight during the wait for the prefix
-    }
     const float* hck = c.hck + (size_t)((t0 >> 3) + ngroups - 1) * p.Di;
     const float* dsrc = c.delta + (int64_t)(t0 + (ngroups - 1) * RG + (w.lane >> 2)) * 4;
     float dnext = w.real ? __ldg(dsrc) : 0.f;
@@ -639,7 +704,7 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
         F = incoming_state(p, r, w.chain, w.slot, w.lane);
     }
     for (int i = 0; i < ngroups; ++i) {
-        const int st = i % NST;
+        const int st = pp.k % NST;
         const int tb = t0 + (ngroups - 1 - i) * RG;
         const float dmine = dnext;
         const float2 hp = hnext;
@@ -661,11 +726,7 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
             a[j] = f2_ex2(f2_mul(f2_bcast(dl[j]), c.A2));
             h[j + 1] = f2_fma(a[j], h[j], up(lds_pair<T, TS>(sb, BA_B, j)));
         }
-        if (w.leader && i >= 1 && i - 1 + NST < ngroups) {
-            // the stores of the previous group were issued a recompute ago: refill its stage
-            bulk_wait_read<0>();
-            issue((i - 1) % NST, t0 + (ngroups - 1 - (i - 1 + NST)) * RG);
-        }
+        if (w.leader) fd.refill(pp.k);            // the previous item's stores were issued a recompute ago
         // ---- reverse sweep; every result goes over the operand it replaces
         float dd[RG];          // this lane's share (2 channels) of d delta of each token
 #pragma unroll
@@ -699,6 +760,7 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
             tma_store(m.dz, pp.saddr(st, BA_Z * TB), w.ch0_team, tb, w.b, pol_stream);
             bulk_commit();
         }
+        ++pp.k;
         // ---- d delta: sum over the 8 lanes of a head (16 channels), transposing butterfly over the 8 tokens so that lane
         //      (head hsel, k = lane & 7) ends with the total of token k
         {
@@ -737,7 +799,7 @@ __device__ __forceinline__ void bwd_p2(const RoundsParams& p, const BwdCtx<T>& c
     }
 }
 
-template <typename T, bool YSSM, int TS>
+template <typename T, bool YSSM, int TS, int NST>
 __global__ void __launch_bounds__(sizeof(T) == 2 ? 512 : 256, 1)
 scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
                        const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_s,
@@ -746,7 +808,7 @@ scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Who w;
     Pipe pp;
-    who_am_i<T, TS>(p, w, pp, smem_raw, YSSM ? 6 : 5);
+    who_am_i<T, TS, NST>(p, w, pp, smem_raw, YSSM ? 6 : 5);
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w.slot >= p.cpr) return;
     const int lane = w.lane;
@@ -765,9 +827,12 @@ scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     f2 accA = f2_bcast(0.f), accD = f2_bcast(0.f);
     float accB = 0.f;
-    for (int r = -1; r < p.nrounds; ++r) {
-        if (r + 1 < p.nrounds) bwd_p1<T, YSSM, TS>(p, c, w, pp, m, r + 1, pol_keep);
-        if (r >= 0) bwd_p2<T, YSSM, TS>(p, c, w, pp, m, r, accA, accD, accB, pol_stream);
+    BwdFeeder<T, YSSM, TS, NST> fd(p, w, pp, m, pol_keep, pol_stream);
+    if (w.leader) fd.prime();
+    Cursor<true> ph;
+    for (ph.begin(p, w.slot); ph.kind >= 0; ph.next_phase(p, w.slot)) {
+        if (ph.kind == 0) bwd_p1<T, YSSM, TS, NST>(p, c, w, pp, fd, ph);
+        else bwd_p2<T, YSSM, TS, NST>(p, c, w, pp, fd, m, ph, accA, accD, accB, pol_stream);
     }
     if (w.leader) bulk_wait_all();
     {
@@ -831,7 +896,7 @@ __global__ void __launch_bounds__(1024) scan_rounds_param_reduce_kernel(const fl
 
 // ---- host ----------------------------------------------------------------------------------------------------------
 struct RoundsCfg {
-    int nslab, nchains, TS, tps, nteamchains, teams_per_cta, nteams, cpr, Tc, nck, nrounds, nseg, nck8, L8, grid, block, nw_total;
+    int nslab, nchains, TS, NST, tps, nteamchains, teams_per_cta, nteams, cpr, Tc, nck, nrounds, nseg, nck8, L8, grid, block, nw_total;
     size_t smem, off_agg, off_segagg, off_segcarry, off_carry, off_cnt, cnt_bytes, off_part, off_part_b, total;
 };
 
@@ -867,6 +932,8 @@ int choose_tc(int L, int cpr, int tc_hint) {
     return best;
 }
 
+int g_nst_fwd = 0, g_nst_bwd = 0;
+
 int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap, int tc_hint, RoundsCfg& c) {
     const int es = dtype == AB_F32 ? 4 : 2;
     c.nslab = (int)ab_ceil_div(Di, 64);
@@ -875,9 +942,15 @@ int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap,
     c.tps = (c.nslab + c.TS - 1) / c.TS;
     c.nteamchains = B * c.tps;
     const size_t tile = (size_t)RG * c.TS * 64 * es;
-    const size_t per_team = (size_t)NST * (bwd ? (yssm ? 6 : 5) : 4) * tile + NST * 8;
     int reg_cap = bwd ? (es == 2 ? 16 : 8) : (es == 2 ? 24 : 16);          // warps per CTA under the kernels' __launch_bounds__
     if (warp_cap > 0 && reg_cap > warp_cap) reg_cap = warp_cap;
+    // ring depth: three stages (two items in flight per team) when that still leaves the register-limited number of
+    // teams or at least four of them, else two
+    const int want = bwd ? g_nst_bwd : g_nst_fwd;
+    const size_t stage = (size_t)(bwd ? (yssm ? 6 : 5) : 4) * tile;
+    const int tpc3 = (int)((SMEM_MAX - 1024) / (3 * stage + 24));
+    c.NST = want == 2 || want == 3 ? want : ((tpc3 >= reg_cap / c.TS || tpc3 >= 4) ? 3 : 2);
+    const size_t per_team = (size_t)c.NST * stage + c.NST * 8;
     int tpc = (int)((SMEM_MAX - 1024) / per_team);
     if (tpc > reg_cap / c.TS) tpc = reg_cap / c.TS;
     if (tpc > 15) tpc = 15;                                                 // named barriers 1..15
@@ -981,12 +1054,20 @@ int set_smem(K kernel, size_t bytes) {
 struct FwdLaunch {
     CUtensorMap xa, b, b32, c, z, y, ys;
 };
-template <typename T, bool YS, int TS>
-int launch_fwd(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
-    if (int e = set_smem(scan_rounds_fwd_kernel<T, YS, TS>, c.smem)) return e;
-    scan_rounds_fwd_kernel<T, YS, TS><<<c.grid, c.block, c.smem, stream>>>(m.xa, m.b, m.b32, m.c, m.z, m.y, m.ys, p);
+template <typename T, bool YS, int TS, int NST>
+int launch_fwd_n(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    static size_t configured = 0;          // cudaFuncSetAttribute is a driver call: only when the requirement grows
+    if (c.smem > configured) {
+        if (int e = set_smem(scan_rounds_fwd_kernel<T, YS, TS, NST>, c.smem)) return e;
+        configured = c.smem;
+    }
+    scan_rounds_fwd_kernel<T, YS, TS, NST><<<c.grid, c.block, c.smem, stream>>>(m.xa, m.b, m.b32, m.c, m.z, m.y, m.ys, p);
     AB_LAUNCH_CHECK();
     return AB_OK;
+}
+template <typename T, bool YS, int TS>
+int launch_fwd(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    return c.NST == 3 ? launch_fwd_n<T, YS, TS, 3>(m, p, c, stream) : launch_fwd_n<T, YS, TS, 2>(m, p, c, stream);
 }
 template <typename T, bool YS>
 int launch_fwd_ts(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
@@ -1000,12 +1081,20 @@ int launch_fwd_ts(const FwdLaunch& m, const RoundsParams& p, const RoundsCfg& c,
 struct BwdLaunch {
     CUtensorMap xa, b, c, z, g, s, dxa, db, dc, dz;
 };
-template <typename T, bool YS, int TS>
-int launch_bwd(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
-    if (int e = set_smem(scan_rounds_bwd_kernel<T, YS, TS>, c.smem)) return e;
-    scan_rounds_bwd_kernel<T, YS, TS><<<c.grid, c.block, c.smem, stream>>>(m.xa, m.b, m.c, m.z, m.g, m.s, m.dxa, m.db, m.dc, m.dz, p);
+template <typename T, bool YS, int TS, int NST>
+int launch_bwd_n(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (c.smem > configured) {
+        if (int e = set_smem(scan_rounds_bwd_kernel<T, YS, TS, NST>, c.smem)) return e;
+        configured = c.smem;
+    }
+    scan_rounds_bwd_kernel<T, YS, TS, NST><<<c.grid, c.block, c.smem, stream>>>(m.xa, m.b, m.c, m.z, m.g, m.s, m.dxa, m.db, m.dc, m.dz, p);
     AB_LAUNCH_CHECK();
     return AB_OK;
+}
+template <typename T, bool YS, int TS>
+int launch_bwd(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
+    return c.NST == 3 ? launch_bwd_n<T, YS, TS, 3>(m, p, c, stream) : launch_bwd_n<T, YS, TS, 2>(m, p, c, stream);
 }
 template <typename T, bool YS>
 int launch_bwd_ts(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c, cudaStream_t stream) {
@@ -1020,8 +1109,8 @@ int launch_bwd_ts(const BwdLaunch& m, const RoundsParams& p, const RoundsCfg& c,
 }  // namespace
 
 // ---- C ABI ---------------------------------------------------------------------------------------------------------
-extern "C" int ab_ssm_scan_tune(int tc_fwd, int tc_bwd, int warps_per_sm) {
-    g_tc_hint_fwd = tc_fwd; g_tc_hint_bwd = tc_bwd; g_warp_cap = warps_per_sm;
+extern "C" int ab_ssm_scan_tune(int tc_fwd, int tc_bwd, int warps_per_sm, int stages_fwd, int stages_bwd) {
+    g_tc_hint_fwd = tc_fwd; g_tc_hint_bwd = tc_bwd; g_warp_cap = warps_per_sm; g_nst_fwd = stages_fwd; g_nst_bwd = stages_bwd;
     return AB_OK;
 }
 

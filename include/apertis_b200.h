@@ -134,8 +134,9 @@ int ab_dt_compose_bwd(const float* dWcat, const float* Wp, const float* Wdt, flo
  *   so the same workspace serves any number of launches on ONE stream and the launch sequence can be captured in a graph.
  * A wait that cannot complete (protocol error, preempted grid) traps: the launch fails with a CUDA error. */
 int ab_ssm_scan_plan(int B, int L, int Di, int dtype, int64_t* state_floats, size_t* ws_bytes);
-/* tuning knobs (0 = library default): chunk length of the forward / backward (multiple of 8 tokens), resident warps per SM */
-int ab_ssm_scan_tune(int tc_fwd, int tc_bwd, int warps_per_sm);
+/* tuning knobs (0 = library default): chunk length of the forward / backward (multiple of 8 tokens), resident warps per SM,
+ * stages (2 or 3) of a team's shared-memory ring in the forward / backward */
+int ab_ssm_scan_tune(int tc_fwd, int tc_bwd, int warps_per_sm, int stages_fwd, int stages_bwd);
 int ab_ssm_scan_fwd(const void* xa, int64_t xa_stride, const void* dlog, int64_t dlog_stride, const float* dt_bias,
                     const void* Bm, const void* Cm, int64_t bc_stride, const void* z, int64_t z_stride,
                     const float* A_log, const float* D, const float* h0, void* y, void* y_ssm, float* h_last,

@@ -169,8 +169,8 @@ def test_rounds_scan_fused_strided_layout(dtype):
     assert rel_err(r["dbias"], o["grads"]["dlog"].sum((0, 1))) < (2e-3 if dtype == torch.bfloat16 else 1e-4)
 
 
-@pytest.mark.parametrize("tc,wps", [(8, 8), (16, 8), (24, 16), (64, 8)])
-def test_rounds_scan_many_rounds(tc, wps):
+@pytest.mark.parametrize("tc,wps,nst", [(8, 8, 2), (16, 8, 3), (24, 16, 2), (64, 8, 3), (32, 4, 3)])
+def test_rounds_scan_many_rounds(tc, wps, nst):
     """Short chunks and few resident warps force many rounds (pipelined P1 / P2, both prefix levels, the carry chain) at a
     size the oracle covers in seconds; results must not depend on the chunking beyond fp32 rounding."""
     from apertis_llm_b200 import _lib
@@ -178,11 +178,11 @@ def test_rounds_scan_many_rounds(tc, wps):
     c = make_case(2, 6000, 8, torch.float32, seed=17)
     o = oracle_scan(c)
     try:
-        lib.ab_ssm_scan_tune(tc, tc, wps)
+        lib.ab_ssm_scan_tune(tc, tc, wps, nst, nst)
         r = run_gpu(c, torch.float32)
         r2 = run_gpu(c, torch.float32)
     finally:
-        lib.ab_ssm_scan_tune(0, 0, 0)
+        lib.ab_ssm_scan_tune(0, 0, 0, 0, 0)
     compare(r, o, torch.float32)
     for k in ("y", "dxa", "ddlog", "dBC", "dz", "dA_log", "dD", "h_last"):
         assert torch.equal(r[k], r2[k]), f"{k}: not bitwise repeatable"

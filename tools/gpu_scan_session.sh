@@ -8,9 +8,9 @@ timeout 900 python -m pytest tests/test_gpu_scan_rounds.py -x -q > $O/scan_tests
 tail -5 $O/scan_tests.log
 timeout 300 python tools/scan_bench.py --mode rounds --json $O/scan_rounds_bf16.json > $O/scan_rounds_sweep.txt 2>&1
 timeout 120 python tools/scan_bench.py --mode pipe --seqs 65536 --iters 10 >> $O/scan_rounds_sweep.txt 2>&1
-for tc in 32 64 128 256; do for wps in 0; do
-  echo "# tc=$tc wps=$wps" >> $O/scan_rounds_tune.txt
-  timeout 120 python tools/scan_bench.py --mode rounds --seqs 16384,65536 --iters 10 --tc-fwd $tc --tc-bwd $tc --wps $wps >> $O/scan_rounds_tune.txt 2>&1
+for nst in 2 3; do for tc in 32 64 128 256; do
+  echo "# tc=$tc nst=$nst" >> $O/scan_rounds_tune.txt
+  timeout 120 python tools/scan_bench.py --mode rounds --seqs 16384,65536 --iters 10 --tc-fwd $tc --tc-bwd $tc --nst-fwd $nst --nst-bwd $nst >> $O/scan_rounds_tune.txt 2>&1
 done; done
 echo "# f32" >> $O/scan_rounds_sweep.txt
 timeout 200 python tools/scan_bench.py --mode rounds --dtype f32 --seqs 16384,65536 --iters 10 >> $O/scan_rounds_sweep.txt 2>&1

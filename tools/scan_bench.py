@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--tc-fwd", type=int, default=0, help="rounds schedule: forward chunk length (0 = library default)")
     ap.add_argument("--tc-bwd", type=int, default=0)
     ap.add_argument("--wps", type=int, default=0, help="rounds schedule: cap on resident warps per SM")
+    ap.add_argument("--nst-fwd", type=int, default=0, help="rounds schedule: ring stages of the forward (2 | 3, 0 = default)")
+    ap.add_argument("--nst-bwd", type=int, default=0)
     ap.add_argument("--seqs", default="2048,4096,8192,16384,32768,65536")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--heads", type=int, default=32)
@@ -32,7 +34,7 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     es = 2 if dtype == torch.bfloat16 else 4
     mode = {"single": _lib.SCAN_SINGLE_PASS, "two_pass": _lib.SCAN_TWO_PASS, "pipe": _lib.SCAN_PIPELINED, "rounds": _lib.SCAN_ROUNDS}[args.mode]
-    _lib.load().ab_ssm_scan_tune(args.tc_fwd, args.tc_bwd, args.wps)
+    _lib.load().ab_ssm_scan_tune(args.tc_fwd, args.tc_bwd, args.wps, args.nst_fwd, args.nst_bwd)
     H = args.heads
     Di = 16 * H
     B = args.batch
