@@ -127,6 +127,8 @@ struct RoundsParams {
     unsigned* cnt1;    // [nrounds][nchains][nseg]
     unsigned* cnt2;    // [nrounds][nchains]
     unsigned* flag;    // [nrounds][nchains]
+    unsigned* done;    // teams that have finished; the last one zeroes the counters for the next launch
+    int cnt_words, nteams_used;
     float4* part;      // backward: [nw_used][32]  (dA0, dA1, dD0, dD1) accumulated by each warp over its chunks
     float* part_b;     // backward: [nw_used][32]  d dt_bias share of lane (head lane >> 3, token lane & 7)
     int ddlog_cols;    // backward: columns [H, ddlog_cols) of the d dlog rows are written as zero (padding of a fused buffer)
@@ -349,6 +351,23 @@ struct Cursor {
     }
     __device__ __forceinline__ void advance(const RoundsParams& p, int slot) { if (++i >= n) next_phase(p, slot); }
 };
+
+
+// A team that has run all its phases signs off; the last one zeroes every counter / flag of this launch, so the next launch
+// on the workspace starts clean without a memset node (the workspace is zero-filled once, when it is allocated).
+__device__ __forceinline__ void team_finish(const RoundsParams& p, int member, int lane) {
+    if (member != 0) return;
+    unsigned last = 0;
+    if (lane == 0) {
+        __threadfence();
+        last = atomicAdd(p.done, 1u) == (unsigned)(p.nteams_used - 1);
+        if (last) __threadfence();
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    for (int i = lane; i < p.cnt_words; i += 32) p.cnt1[i] = 0u;
+    if (lane == 0) *p.done = 0u;
+}
 
 // ====================================================================================================================
 // forward
@@ -583,6 +602,7 @@ scan_rounds_fwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
         else fwd_p2<T, YSSM, TS, NST>(p, c, w, pp, fd, m, ph, pol_stream);
     }
     if (w.leader) bulk_wait_all();
+    team_finish(p, w.member, w.lane);
 }
 
 // ====================================================================================================================
@@ -844,37 +864,38 @@ scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
         p.part[(size_t)gw * 32 + lane] = make_float4(x0, x1, y0, y1);
         p.part_b[(size_t)gw * 32 + lane] = accB;
     }
+    team_finish(p, w.member, w.lane);
 }
 
 // dA_log[c], dD[c] (and d dt_bias[head]) = sum over the warps that worked on the channel's slab (all sequences, all chunk
-// slots), fixed order: bitwise reproducible.  One CTA of 32 warps per slab; warp v sums partials v, v + 32, ...
-__global__ void __launch_bounds__(1024) scan_rounds_param_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dA,
-                                                                         float* __restrict__ dD, float* __restrict__ dbias, int Di, int H, int B, int TS, int tps,
-                                                                         int nteamchains, int cpr) {
-    __shared__ float4 red[32][32];
-    __shared__ float redb[32][32];
+// slots), fixed order: bitwise reproducible.  One CTA of 8 warps per slab; warp v sums partials v, v + 8, ... eight at a time.
+__global__ void __launch_bounds__(256) scan_rounds_param_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dA,
+                                                                        float* __restrict__ dD, float* __restrict__ dbias, int Di, int H, int B, int TS, int tps,
+                                                                        int nteamchains, int cpr) {
+    __shared__ float4 red[8][32];
+    __shared__ float redb[8][32];
     const int slab = blockIdx.x, lane = threadIdx.x & 31, v = threadIdx.x >> 5;
     const int tslab = slab / TS, member = slab % TS;
     const int n = cpr * B;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float accb = 0.f;
-    for (int q0 = v; q0 < n; q0 += 128) {
-        float4 t[4];
-        float tb[4];
+    for (int q0 = v; q0 < n; q0 += 64) {
+        float4 t[8];
+        float tb[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int q = q0 + u * 32;
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + u * 8;
             t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             tb[u] = 0.f;
             if (q < n) {
                 const int slot = q / B, b = q % B;
                 const size_t gw = ((size_t)slot * nteamchains + (size_t)b * tps + tslab) * TS + member;
-                t[u] = part[gw * 32 + lane];
-                tb[u] = part_b[gw * 32 + lane];
+                t[u] = __ldcg(&part[gw * 32 + lane]);
+                tb[u] = __ldcg(&part_b[gw * 32 + lane]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; accb += tb[u]; }
+        for (int u = 0; u < 8; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; accb += tb[u]; }
     }
     red[v][lane] = acc;
     redb[v][lane] = accb;
@@ -882,7 +903,8 @@ __global__ void __launch_bounds__(1024) scan_rounds_param_reduce_kernel(const fl
     if (v == 0) {
         float4 sum = red[0][lane];
         float sb = redb[0][lane];
-        for (int i = 1; i < 32; ++i) { sum.x += red[i][lane].x; sum.y += red[i][lane].y; sum.z += red[i][lane].z; sum.w += red[i][lane].w; sb += redb[i][lane]; }
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { sum.x += red[i][lane].x; sum.y += red[i][lane].y; sum.z += red[i][lane].z; sum.w += red[i][lane].w; sb += redb[i][lane]; }
         const int c0 = slab * 64 + 2 * lane;
         if (c0 < Di) { dA[c0] = sum.x; dA[c0 + 1] = sum.y; dD[c0] = sum.z; dD[c0 + 1] = sum.w; }
         // lanes (head lane >> 3, token lane & 7): sum the 8 token lanes of a head
@@ -901,6 +923,7 @@ struct RoundsCfg {
 };
 
 constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr size_t CNT_REGION = 1 << 20;      // head of the workspace: sign-off word, then the per-round counters / flags
 
 // slabs per team: wide boxes (few, large TMA requests) against slabs lost to padding the last team of a sequence
 int choose_ts(int nslab) {
@@ -971,16 +994,17 @@ int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap,
     c.nw_total = c.grid * tpc * c.TS;
     c.nrounds = (int)ab_ceil_div(c.nck, c.cpr);
     c.nseg = (int)ab_ceil_div(c.cpr, RSEG);
-    size_t o = 0;
+    // counters first, at a fixed place: a launch leaves them zeroed for the next one whatever its shape
+    c.cnt_bytes = (size_t)c.nrounds * c.nchains * (c.nseg + 2) * sizeof(unsigned);
+    AB_REQUIRE(c.cnt_bytes + 256 <= CNT_REGION, "selective scan: %zu bytes of round counters exceed the reserved %zu", c.cnt_bytes, (size_t)CNT_REGION);
+    c.off_cnt = 256;
+    size_t o = CNT_REGION;
     c.off_agg = o;      o += (size_t)2 * c.nchains * c.cpr * 32 * sizeof(float4);
     c.off_segagg = o;   o += (size_t)2 * c.nchains * c.nseg * 32 * sizeof(float4);
     c.off_segcarry = o; o += (size_t)2 * c.nchains * c.nseg * 32 * sizeof(float2);
     c.off_carry = o;    o += (size_t)c.nchains * 32 * sizeof(float2);
     c.off_part = o;     o += (size_t)c.nw_total * 32 * sizeof(float4);
     c.off_part_b = o;   o += (size_t)c.nw_total * 32 * sizeof(float);
-    c.off_cnt = o;
-    c.cnt_bytes = (size_t)c.nrounds * c.nchains * (c.nseg + 2) * sizeof(unsigned);
-    o += ab_round_up((int64_t)c.cnt_bytes, 256);
     c.total = o;
     return AB_OK;
 }
@@ -996,6 +1020,9 @@ void fill_sync(RoundsParams& p, const RoundsCfg& c, void* ws) {
     p.cnt1 = reinterpret_cast<unsigned*>(w + c.off_cnt);
     p.cnt2 = p.cnt1 + (size_t)c.nrounds * c.nchains * c.nseg;
     p.flag = p.cnt2 + (size_t)c.nrounds * c.nchains;
+    p.done = reinterpret_cast<unsigned*>(w);
+    p.cnt_words = (int)(c.cnt_bytes / sizeof(unsigned));
+    p.nteams_used = c.cpr * c.nteamchains;
     p.nslab = c.nslab; p.nchains = c.nchains; p.Tc = c.Tc; p.nck = c.nck; p.cpr = c.cpr; p.nrounds = c.nrounds; p.nseg = c.nseg;
     p.nw_used = c.nw_total; p.nck8 = c.nck8; p.L8 = c.L8; p.tps = c.tps; p.nteamchains = c.nteamchains;
 }
@@ -1163,7 +1190,6 @@ extern "C" int ab_ssm_scan_fwd(const void* xa, int64_t xa_stride, const void* dl
     if (int e = map3(&m.y, y, dtype, B, L, Di, Di, RG, cols)) return e;
     m.ys = m.y;
     if (y_ssm) { if (int e = map3(&m.ys, y_ssm, dtype, B, L, Di, Di, RG, cols)) return e; }
-    AB_CHECK_CUDA(cudaMemsetAsync(p.cnt1, 0, c.cnt_bytes, stream));
     if (dtype == AB_F32) return y_ssm ? launch_fwd_ts<float, true>(m, p, c, stream) : launch_fwd_ts<float, false>(m, p, c, stream);
     return y_ssm ? launch_fwd_ts<__nv_bfloat16, true>(m, p, c, stream) : launch_fwd_ts<__nv_bfloat16, false>(m, p, c, stream);
 }
@@ -1208,12 +1234,11 @@ extern "C" int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm
     if (int e = map3(&m.db, dBm, dtype, B, L, Di, dbc_stride, RG, cols)) return e;
     if (int e = map3(&m.dc, dCm, dtype, B, L, Di, dbc_stride, RG, cols)) return e;
     if (int e = map3(&m.dz, dz, dtype, B, L, Di, dz_stride, RG, cols)) return e;
-    AB_CHECK_CUDA(cudaMemsetAsync(p.cnt1, 0, c.cnt_bytes, stream));
     int e;
     if (dtype == AB_F32) e = dyssm ? launch_bwd_ts<float, true>(m, p, c, stream) : launch_bwd_ts<float, false>(m, p, c, stream);
     else e = dyssm ? launch_bwd_ts<__nv_bfloat16, true>(m, p, c, stream) : launch_bwd_ts<__nv_bfloat16, false>(m, p, c, stream);
     if (e) return e;
-    scan_rounds_param_reduce_kernel<<<c.nslab, 1024, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, Di, H, B, c.TS, c.tps, c.nteamchains, c.cpr);
+    scan_rounds_param_reduce_kernel<<<c.nslab, 256, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, Di, H, B, c.TS, c.tps, c.nteamchains, c.cpr);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

@@ -5,9 +5,10 @@ arguments, ``forward()`` signatures, return tuples and ``state_dict`` keys (core
 ``ApertisAttention`` / ``ApertisFeedForward`` (core.py:650, 861-865, 699-704, 894) can hold them unchanged.
 ``patch_apertis_model`` swaps them into an existing reference ``ApertisModel`` in place.
 
-All arithmetic of the two layers runs in the sm_100a kernels behind the C ABI; the five SSM projection
-GEMMs stay plain library GEMMs (F.linear -> cuBLAS), everything else is hand-written CUDA.  There is no
-CPU / other-GPU fallback: calling these modules on a non-sm_100 device raises.
+All arithmetic of the two layers runs in the sm_100a kernels behind the C ABI, the SSM projections
+(core.py:366-367, 376-383, 397) included: they run on the library's tcgen05 GEMM kernel, in_proj_x | in_proj_z as
+one GEMM and x_param_proj with dt_proj_head folded in as one GEMM.  There is no CPU / other-GPU fallback: calling
+these modules on a non-sm_100 device raises.
 """
 from __future__ import annotations
 
@@ -100,7 +101,7 @@ class SelectiveLinearAttention(nn.Module):
         self.D = nn.Parameter(torch.ones(self.d_inner))
         self.out_proj = nn.Linear(self.d_inner, self.hidden_size, bias=False)
         self.use_cache = False
-        self.scan_mode: Optional[int] = None      # None = library default (single-pass look-back)
+        self.scan_mode: Optional[int] = None      # None = library default (the "rounds" schedule); 0 / 1 / 2 select the older ones
 
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 position_ids: Optional[torch.Tensor] = None,
@@ -117,33 +118,45 @@ class SelectiveLinearAttention(nn.Module):
             h16 = lambda t: t.to(torch.float16) if (t is not None and t.dtype == torch.bfloat16) else t
             return h16(out), h16(y_ssm), (tuple(h16(c) for c in cache) if cache is not None else None)
         self.use_cache = use_cache
+        if hidden_states.dtype == torch.float16:
+            hidden_states = hidden_states.to(torch.bfloat16 if ac is not None else torch.float32)
         B, L, _ = hidden_states.shape
-        Di, R, Kc = self.d_inner, self.dt_rank, self.conv_kernel_size
+        Di, R, Kc, H = self.d_inner, self.dt_rank, self.conv_kernel_size, self.num_heads
+        # fp32 activations without autocast: fp32-accurate GEMMs (3-product bf16 split); everything else runs the bf16 kernels
+        precise = hidden_states.dtype == torch.float32 and ac is None
         conv_prev, h_prev = (past_key_value if past_key_value is not None else (None, None))
-        if ac is not None and hidden_states.dtype == torch.float16:
-            hidden_states = hidden_states.to(ac)
-        xp = self.in_proj_x(hidden_states)                                    # :366
-        z = self.in_proj_z(hidden_states)                                     # :367
+        cached = conv_prev is not None and use_cache and conv_prev.shape[1] == Di and conv_prev.shape[2] == Kc - 1
+        recurrent = not (self.training and not use_cache)                     # :388-393
+        # in_proj_x | in_proj_z as one GEMM: [xp | z] rows                     # :366-367
+        xz = ops.linear(hidden_states, [self.in_proj_x.weight, self.in_proj_z.weight], precise=precise)
+        if not (cached or use_cache or output_attentions) and self.scan_mode in (None, _lib.SCAN_ROUNDS):
+            # the hot path (training, plain evaluation): conv + SiLU, fused parameter projection and scan as one autograd node
+            y = ops.ssm_core(xz, self.conv1d.weight, self.conv1d.bias, self.x_param_proj.weight, self.dt_proj_head.weight,
+                             self.dt_proj_head.bias, self.A_log, self.D, precise)
+            return ops.linear(y, self.out_proj.weight, precise=precise), None, None       # :397
+        # general path: cached decoding (:369-373, :391-393, :398-400), output_attentions, explicit scan schedules
+        xp, z = xz[..., :Di], xz[..., Di:]
         x_seq = xp
-        if conv_prev is not None and use_cache and conv_prev.shape[1] == Di and conv_prev.shape[2] == Kc - 1:
+        if cached:
             x_seq = torch.cat([conv_prev.transpose(1, 2).to(xp.dtype), xp], dim=1)      # :369-371 (state goes in FRONT)
         conv_state = x_seq[:, -(Kc - 1):, :].transpose(1, 2).detach() if use_cache else None   # :372
         # the reference convolves the (possibly state-prefixed) sequence and keeps the FIRST L outputs (:373)
         xa = ops.causal_conv1d_silu(x_seq, self.conv1d.weight, self.conv1d.bias)
         if x_seq.shape[1] != L:
             xa = xa[:, :L].contiguous()
-        wp = self.x_param_proj.weight
-        dtf = F.linear(xa, wp[:R])                                            # :376-381, as two GEMMs so that the
-        bc = F.linear(xa, wp[R:])                                             # B|C block is 16-byte aligned for TMA
-        dlog = self.dt_proj_head(dtf)                                         # :382
-        recurrent = not (self.training and not use_cache)                     # :388-393
         h0 = h_prev if (recurrent and use_cache and h_prev is not None) else None
-        if not (xa.dtype == z.dtype == bc.dtype == dlog.dtype):
-            common = xa.dtype
-            z, bc, dlog = z.to(common), bc.to(common), dlog.to(common)
-        y, y_ssm, h_last = ops.selective_scan(xa, dlog, bc, z, self.A_log, self.D, h0=h0, want_yssm=output_attentions,
-                                              want_hlast=use_cache, mode=self.scan_mode)     # :389/391, :394-396
-        out = self.out_proj(y)                                                # :397
+        # x_param_proj with dt_proj_head folded in: one GEMM writes [dt (no bias) | pad | B | C] rows  (:376-383)
+        wcat = ops.dt_compose(self.x_param_proj.weight, self.dt_proj_head.weight, precise)
+        prm = ops.linear(xa, wcat, precise=precise)
+        if self.scan_mode in (None, _lib.SCAN_ROUNDS):
+            y, y_ssm, h_last = ops.selective_scan_fused(xa, prm, self.dt_proj_head.bias, z, self.A_log, self.D, H, h0=h0,
+                                                        want_yssm=output_attentions, want_hlast=use_cache)
+        else:           # the older schedules take separate, contiguous dt and [B | C] tensors
+            Hp = prm.shape[-1] - 2 * Di
+            dlog = (prm[..., :H] + self.dt_proj_head.bias.to(prm.dtype)).contiguous()
+            y, y_ssm, h_last = ops.selective_scan(xa, dlog, prm[..., Hp:].contiguous(), z.contiguous(), self.A_log, self.D, h0=h0,
+                                                  want_yssm=output_attentions, want_hlast=use_cache, mode=self.scan_mode)
+        out = ops.linear(y, self.out_proj.weight, precise=precise)            # :397
         cache = None
         if use_cache:
             cache = (conv_state, h_last.view(B, self.num_heads, self.d_state).to(xa.dtype))      # :398-400
@@ -300,11 +313,21 @@ class AdaptiveExpertSystem(nn.Module):
 # ================================================================================================
 # the callers (boundary; kept as plain PyTorch like the reference's ApertisAttention / ApertisFeedForward)
 # ================================================================================================
+def _require_layernorm(config):
+    """The fused wrappers implement the reference's default pre-norm (nn.LayerNorm, core.py:668-669, 846-847).  With
+    use_rmsnorm=True the reference builds RMSNorm (core.py:666-667, 844-845): refuse instead of silently normalising
+    differently; patch_apertis_model() keeps the reference's own wrappers (and therefore its RMSNorm) and still works."""
+    if getattr(config, "use_rmsnorm", False):
+        raise NotImplementedError("ApertisLayerB200 implements the LayerNorm pre-norm only; for use_rmsnorm=True keep the reference "
+                                  "wrappers and swap the hot-path modules with patch_apertis_model()")
+
+
 class _AttentionWrapper(nn.Module):
     """ApertisAttention for attention_type == 'selective_ssm' (core.py:639-704, 836-838)."""
 
     def __init__(self, config):
         super().__init__()
+        _require_layernorm(config)
         self.config = config
         self.attention_mechanism_impl = SelectiveLinearAttention(config)
         self.pre_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
@@ -313,7 +336,7 @@ class _AttentionWrapper(nn.Module):
     def forward(self, hidden_s, att_mask=None, pos_ids=None, past_kv=None, output_att=False, use_c=False):
         # under autocast the projections consume bf16: emit the normalised rows in that type directly (same rounding
         # point as the reference's fp32 LayerNorm followed by the autocast cast inside nn.Linear)
-        ac = _autocast_dtype()
+        ac = _compute_dtype(_autocast_dtype())
         normed, skip = ops.layer_norm_skip(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps,
                                            out_dtype=ac if (ac is not None and hidden_s.dtype == torch.float32) else None)
         out, proxy, cache = self.attention_mechanism_impl(normed, attention_mask=att_mask, position_ids=pos_ids,
@@ -326,6 +349,7 @@ class _FeedForwardWrapper(nn.Module):
 
     def __init__(self, config, ep_group=None):
         super().__init__()
+        _require_layernorm(config)
         self.config = config
         self.pre_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.ffn = AdaptiveExpertSystem(config, activation_function_override=config.hidden_act, ep_group=ep_group)

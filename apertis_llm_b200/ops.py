@@ -329,11 +329,11 @@ def _rounds_plan(B, L, Di, dtype):
 
 
 def _rounds_workspace(device, nbytes):
-    """One workspace per (device, stream): launches on a stream are ordered, and each launch zeroes its own counters."""
+    """One workspace per (device, stream): launches on a stream are ordered, and each launch leaves the counters zeroed."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _rounds_ws.get(key)
     if t is None or t.numel() < nbytes:
-        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        t = torch.zeros(max(nbytes, 2 << 20), dtype=torch.uint8, device=device)      # zero-filled once (ABI contract)
         _rounds_ws[key] = t
     return t
 
@@ -598,6 +598,41 @@ class _SSMCore(torch.autograd.Function):
                  B, L, Di, Kc, dt(cdt), stream_ptr(dev))
             return (dxz, dcw.reshape(cw_shape).to(cw_dtype), dcb.to(cb_dtype), dWp.to(wp_dtype), dWdt.to(wdt_dtype),
                     dbias.to(bias_dtype), dA.reshape(a_shape), dD, None)
+
+
+class _DtCompose(torch.autograd.Function):
+    """Wcat = [Wdt @ Wp[:R] ; 0 ; Wp[R:]] (csrc/ssm_proj.cu) with its gradient mapped back to the two parameters."""
+
+    @staticmethod
+    def forward(ctx, Wp, Wdt, precise):
+        _lib.ensure_device(Wp.device)
+        with torch.cuda.device(Wp.device):
+            H, R = Wdt.shape
+            Di = Wp.shape[1]
+            Hp = (H + 7) // 8 * 8
+            cdt = torch.float32 if precise else torch.bfloat16
+            Wp32, Wdt32 = Wp.float().contiguous(), Wdt.float().contiguous()
+            wcat = torch.empty(Hp + 2 * Di, Di, dtype=cdt, device=Wp.device)
+            call("ab_dt_compose_fwd", ptr(Wp32), ptr(Wdt32), ptr(wcat), H, Hp, R, Di, dt(cdt), stream_ptr(Wp.device))
+            ctx.save_for_backward(Wp32, Wdt32)
+            ctx.meta = (H, Hp, R, Di, Wp.dtype, Wdt.dtype)
+            return wcat
+
+    @staticmethod
+    def backward(ctx, dwcat):
+        Wp32, Wdt32 = ctx.saved_tensors
+        H, Hp, R, Di, wp_dtype, wdt_dtype = ctx.meta
+        with torch.cuda.device(dwcat.device):
+            dw = dwcat.float().contiguous()
+            dWp = torch.empty(R + 2 * Di, Di, dtype=torch.float32, device=dw.device)
+            dWdt = torch.empty(H, R, dtype=torch.float32, device=dw.device)
+            call("ab_dt_compose_bwd", ptr(dw), ptr(Wp32), ptr(Wdt32), ptr(dWp), ptr(dWdt), H, Hp, R, Di, stream_ptr(dw.device))
+            return dWp.to(wp_dtype), dWdt.to(wdt_dtype), None
+
+
+def dt_compose(Wp, Wdt, precise=False):
+    """Stacked weight of the fused parameter projection: [dt rows (H, padded to a multiple of 8) | B rows | C rows]."""
+    return _DtCompose.apply(Wp, Wdt, precise)
 
 
 def ssm_core(xz, conv_w, conv_b, Wp, Wdt, dt_bias, A_log, D, precise):

@@ -130,8 +130,9 @@ int ab_dt_compose_bwd(const float* dWcat, const float* Wp, const float* Wdt, flo
  *   (delta = softplus(dlog + dt_bias[h])), or with it when dt_bias == NULL.
  *   state: fp32 buffer of `state_floats` elements written by the forward and read by the backward
  *   (the scan state entering every group of 8 tokens, then delta of every (token, head)).
- *   ws: workspace of ws_bytes (ab_ssm_scan_plan); its counters are zeroed by a memset enqueued ahead of each launch,
- *   so the same workspace serves any number of launches on ONE stream and the launch sequence can be captured in a graph.
+ *   ws: workspace of ws_bytes (ab_ssm_scan_plan), ZERO-FILLED ONCE by the caller when it is allocated; every launch
+ *   leaves its counters zeroed for the next one, so the same workspace serves any number of launches (of any shape) on
+ *   ONE stream and the launch sequence can be captured in a graph.
  * A wait that cannot complete (protocol error, preempted grid) traps: the launch fails with a CUDA error. */
 int ab_ssm_scan_plan(int B, int L, int Di, int dtype, int64_t* state_floats, size_t* ws_bytes);
 /* tuning knobs (0 = library default): chunk length of the forward / backward (multiple of 8 tokens), resident warps per SM,

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--heads", type=int, default=32)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--json", default="")
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of the launches (no host code inside the event windows)")
     args = ap.parse_args()
     d = torch.device("cuda:0")
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -67,12 +68,34 @@ def main():
             run()
         torch.cuda.synchronize()
         tf, tb = [], []
-        for _ in range(args.iters):
-            flush.zero_()                       # evict L2 between iterations (inputs of short sequences fit in L2)
-            _lib.start_timing(names)
-            run()
-            t = _lib.stop_timing()
-            tf.append(sum(t[names[0]])); tb.append(sum(t[names[1]]))
+        if args.graph:
+            lv = leaves + [A_log, D]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                yy = ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=mode)[0]
+                torch.autograd.grad(yy, lv, dy)
+                torch.cuda.synchronize()
+                gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gf, stream=side):
+                    yy = ops.selective_scan(xa, dlog, BC, z, A_log, D, mode=mode)[0]
+                with torch.cuda.graph(gb, stream=side, pool=gf.pool()):
+                    gg = torch.autograd.grad(yy, lv, dy)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                for _ in range(args.iters):
+                    flush.zero_()
+                    ev[0].record(side); gf.replay(); ev[1].record(side); gb.replay(); ev[2].record(side)
+                    torch.cuda.synchronize()
+                    tf.append(ev[0].elapsed_time(ev[1])); tb.append(ev[1].elapsed_time(ev[2]))
+            torch.cuda.current_stream().wait_stream(side)
+            del gg
+        else:
+            for _ in range(args.iters):
+                flush.zero_()                       # evict L2 between iterations (inputs of short sequences fit in L2)
+                _lib.start_timing(names)
+                run()
+                t = _lib.stop_timing()
+                tf.append(sum(t[names[0]])); tb.append(sum(t[names[1]]))
         tf.sort(); tb.sort()
         mf, mb = tf[len(tf) // 2], tb[len(tb) // 2]
         tok = B * L
