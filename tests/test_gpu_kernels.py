@@ -432,3 +432,59 @@ def test_dropout_add(p, sub_dtype):
     assert torch.equal(res.grad, dout)
     assert rel_err(sub.grad.float()[keep], (dout / (1 - p))[keep]) < 1e-2 and float(sub.grad.float()[~keep].abs().max()) == 0.0
     assert torch.equal(ops.dropout_add(sub, res, p, False), sub.float() + res) or sub_dtype == torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------
+# dense GEMMs of the SSM projections (core.py:366-367, 376-383, 397) on the tcgen05 kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precise", [False, True])
+@pytest.mark.parametrize("S,N,K", [(4673, 352, 704), (1, 368, 176), (300, 704, 176), (4096, 176, 368), (777, 832, 400), (130, 8, 16)])
+def test_dense_gemm_nt_nn_tn(precise, S, N, K):
+    """C = A W^T (+bias), dX = dY W (+add), dW = dY^T A against torch fp32 matmuls of the same (bf16-rounded) operands."""
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(S + N + K)
+    q = (lambda t: t) if precise else (lambda t: t.to(torch.bfloat16).float())
+    A, W, dY = q(torch.randn(S, K, generator=g)), q(torch.randn(N, K, generator=g) * 0.1), q(torch.randn(S, N, generator=g))
+    bias, add = torch.randn(N, generator=g), q(torch.randn(S, K, generator=g))
+    d = dev()
+    tol = 1e-4 if precise else 2e-2
+    cdt = torch.float32 if precise else torch.bfloat16
+    c = ops.dense_nt(A.to(d, cdt), W.to(d, cdt), precise, bias=bias.to(d))
+    assert rel_err(c.float(), A @ W.t() + bias) < tol
+    dx = ops.dense_nn(dY.to(d, cdt), W.to(d, cdt), precise, add=add.to(d, cdt))
+    assert rel_err(dx.float(), dY @ W + add) < tol
+    dw = ops.dense_tn(dY.to(d, cdt), A.to(d, cdt), precise)
+    assert dw.dtype == torch.float32 and rel_err(dw, dY.t() @ A) < (1e-4 if precise else 5e-3)
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_linear_autograd_matches_torch(autocast):
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 333, 704, generator=g)
+    w1, w2 = torch.randn(176, 704, generator=g) * 0.05, torch.randn(176, 704, generator=g) * 0.05
+    dy = torch.randn(2, 333, 352, generator=g)
+    xr, w1r, w2r = (t.clone().requires_grad_(True) for t in (x, w1, w2))
+    torch.nn.functional.linear(xr, torch.cat([w1r, w2r], 0)).backward(dy)
+    xg, w1g, w2g = (t.to(dev()).requires_grad_(True) for t in (x, w1, w2))
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        y = ops.linear(xg.to(torch.bfloat16) if autocast else xg, [w1g, w2g], precise=not autocast)
+    y.backward(dy.to(dev(), y.dtype))
+    tol = 2e-2 if autocast else 1e-4
+    assert rel_err(xg.grad, xr.grad) < tol and rel_err(w1g.grad, w1r.grad) < tol and rel_err(w2g.grad, w2r.grad) < tol
+
+
+def test_dt_compose_fwd_bwd():
+    from apertis_llm_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    H, R, Di = 11, 44, 176
+    Wp, Wdt = torch.randn(R + 2 * Di, Di, generator=g), torch.randn(H, R, generator=g)
+    Wpr, Wdtr = Wp.clone().requires_grad_(True), Wdt.clone().requires_grad_(True)
+    ref = torch.cat([Wdtr @ Wpr[:R], torch.zeros(16 - H, Di), Wpr[R:]], 0)
+    dW = torch.randn(ref.shape, generator=g)
+    ref.backward(dW)
+    Wpg, Wdtg = Wp.to(dev()).requires_grad_(True), Wdt.to(dev()).requires_grad_(True)
+    out = ops.dt_compose(Wpg, Wdtg, precise=True)
+    out.backward(dW.to(dev()))
+    assert rel_err(out, ref.detach()) < 1e-5
+    assert rel_err(Wpg.grad, Wpr.grad) < 1e-5 and rel_err(Wdtg.grad, Wdtr.grad) < 1e-5
