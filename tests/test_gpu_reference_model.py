@@ -56,9 +56,12 @@ def grads_by_reference_name(model):
     return out
 
 
-def step(model, batch, autocast=None, scaler=None):
+def step(model, batch, autocast=None, scaler=None, seed=1234):
     for p in model.parameters():
         p.grad = None
+    # both models consume torch's CUDA generator identically (embedding / vision-encoder dropout, routing noise): the same
+    # seed before each forward gives them the same draws
+    torch.manual_seed(seed)
     with torch.autocast("cuda", dtype=autocast, enabled=autocast is not None):
         out = model(**batch)
     loss, logits = out[0], out[1]
