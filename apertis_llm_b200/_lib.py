@@ -23,6 +23,7 @@ ACT = {"gelu": 0, "relu": 1, "silu": 2, "swish": 2}
 EPI_NONE, EPI_BIAS, EPI_BIAS_ACT, EPI_DACT, EPI_ADD = 0, 1, 2, 3, 4
 SCAN_SINGLE_PASS, SCAN_TWO_PASS, SCAN_PIPELINED, SCAN_ROUNDS = 0, 1, 2, 3
 ROW_ALIGN = 128
+ROUTER_EXACT, ROUTER_BF16, ROUTER_FP16 = 0, 1, 2
 
 P, I, I64, SZ, F, U32 = c_void_p, c_int, c_int64, c_size_t, c_float, c_uint32
 
@@ -44,7 +45,7 @@ SIGNATURES = {
     "ab_ssm_scan_bwd": (I, [P, I64, P, P, I64, P, I64, P, P, P, P, P, P, I64, P, P, I64, P, I64, P, I64, I, P, P, P, P, SZ,
                             I, I, I, I, I, P]),
     "ab_moe_router_workspace_bytes": (SZ, [I, I, I]),
-    "ab_moe_router_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
+    "ab_moe_router_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),
     "ab_moe_topk_from_logits": (I, [P, P, P, P, P, P, I, I, I, P]),
     "ab_moe_max_rows": (I64, [I, I, I, I, I]),
     "ab_moe_plan_workspace_bytes": (SZ, [I, I, I]),
@@ -63,7 +64,8 @@ SIGNATURES = {
     "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, I, I64, P]),
     "ab_dense_gemm_nt": (I, [P, P, P, P, P, I64, I, I, I, I, P]),
     "ab_dense_gemm_nn": (I, [P, P, P, P, P, I64, I, I, I, I, P]),
-    "ab_dense_gemm_tn": (I, [P, P, P, I64, I, I, P]),
+    "ab_dense_gemm_tn_workspace_bytes": (SZ, [I64, I, I]),
+    "ab_dense_gemm_tn": (I, [P, P, P, P, SZ, I64, I, I, P]),
     "ab_dt_compose_fwd": (I, [P, P, P, I, I, I, I, I, P]),
     "ab_dt_compose_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "ab_layernorm_fwd": (I, [P, P, P, F, P, P, I, I, I, I, P]),
@@ -153,7 +155,7 @@ def ensure_device(device) -> None:
 KERNELS_PER_CALL = {
     "ab_causal_conv1d_silu_fwd": 1, "ab_causal_conv1d_silu_bwd": 2,
     "ab_selective_scan_fwd": 1, "ab_selective_scan_bwd": 2,          # single pass; two pass adds 2
-    "ab_ssm_scan_fwd": 1, "ab_ssm_scan_bwd": 2, "ab_dense_gemm_nt": 1, "ab_dense_gemm_nn": 1, "ab_dense_gemm_tn": 1,
+    "ab_ssm_scan_fwd": 1, "ab_ssm_scan_bwd": 2, "ab_dense_gemm_nt": 1, "ab_dense_gemm_nn": 1, "ab_dense_gemm_tn": 2,
     "ab_dt_compose_fwd": 1, "ab_dt_compose_bwd": 2,
     "ab_moe_router_fwd": 2, "ab_moe_topk_from_logits": 1, "ab_moe_plan": 2, "ab_moe_permute_ln": 1, "ab_moe_unpermute": 1,
     "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,

@@ -42,6 +42,7 @@ struct GemmParams {
     int64_t rows_valid;      // MODE_NT / MODE_NN: rows >= rows_valid are never stored (the last row tile may be partial)
     int dense_m_tiles;       // MODE_NT / MODE_NN: number of row tiles when n_rows is NULL
     int64_t tn_rows;         // MODE_TN with seg_off NULL: contraction over rows [0, tn_rows), TMA zero-fills past the end
+    int64_t tn_split;        // ... cut into E slices of tn_split rows (a multiple of BK): Cw[e] holds slice e's partial product
     const int32_t* tile_expert;
     const int32_t* n_rows;
     const int32_t* seg_off;
@@ -54,6 +55,13 @@ struct GemmParams {
     void* c2;
     float* cw;
 };
+
+// dense weight gradient: 64-row blocks of slice e of the contraction (the last block of the last slice may be partial: TMA zero-fills)
+__device__ __forceinline__ int dense_tn_blocks(const GemmParams& p, int e) {
+    const int64_t lo = (int64_t)e * p.tn_split;
+    const int64_t hi = lo + p.tn_split < p.tn_rows ? lo + p.tn_split : p.tn_rows;
+    return hi > lo ? (int)((hi - lo + BK - 1) / BK) : 0;
+}
 
 // ---- math for the epilogues -------------------------------------------------------------------
 // erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26): erf(x/sqrt2) from t = 1/(1+p|x|/sqrt2) and g = exp(-x^2/2)
@@ -353,8 +361,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                     e = tile / (p.num_m_tiles * p.num_n_tiles);
                     const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
                     m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                    k_begin = p.seg_off != nullptr ? p.seg_off[e] : 0;
-                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - k_begin) / BK) : (int)((p.tn_rows + BK - 1) / BK);
+                    k_begin = p.seg_off != nullptr ? p.seg_off[e] : (int)(e * p.tn_split);
+                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - k_begin) / BK) : dense_tn_blocks(p, e);
                 } else {
                     m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
                     e = p.tile_expert != nullptr ? p.tile_expert[m_tile] : 0;
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 int nk;
                 if (MODE == MODE_TN) {
                     const int e = tile / (p.num_m_tiles * p.num_n_tiles);
-                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : (int)((p.tn_rows + BK - 1) / BK);
+                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : dense_tn_blocks(p, e);
                     if (nk == 0) continue;          // empty expert: the epilogue writes zeros without an accumulator
                 } else {
                     nk = (p.K + BK - 1) / BK;
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 e = tile / (p.num_m_tiles * p.num_n_tiles);
                 const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
                 m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : (int)((p.tn_rows + BK - 1) / BK);
+                nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : dense_tn_blocks(p, e);
             } else {
                 m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
                 e = p.tile_expert != nullptr ? p.tile_expert[m_tile] : 0;
@@ -616,19 +624,59 @@ extern "C" int ab_dense_gemm_nn(const void* A, const void* W, const float* bias,
     return dense_rows(MODE_NN, A, W, bias, aux, C, S, N, K, epi, c_dtype, stream);
 }
 
-extern "C" int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, int64_t S, int M, int N, cudaStream_t stream) {
+// sum of the split-K partial products, fixed order (bitwise reproducible)
+namespace {
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int nsplit) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 acc = *reinterpret_cast<const float4*>(part + i);
+    for (int s = 1; s < nsplit; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)s * n + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = acc;
+}
+}  // namespace
+
+extern "C" size_t ab_dense_gemm_tn_workspace_bytes(int64_t S, int M, int N) {
+    const int tiles = (int)(ab_ceil_div(M, BM) * ab_ceil_div(N, 256));
+    int nsplit = tiles > 0 ? ab_num_sms() / tiles : 1;            // one wave of (slice, tile) work items
+    const int64_t kblocks = ab_ceil_div(S, BK);
+    if (nsplit > kblocks / 4) nsplit = (int)(kblocks / 4);          // at least 4 blocks of 64 rows per slice
+    if (nsplit < 2) return 0;
+    return (size_t)nsplit * M * N * sizeof(float);
+}
+
+extern "C" int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, void* ws, size_t ws_bytes, int64_t S, int M, int N,
+                                cudaStream_t stream) {
     AB_REQUIRE(S > 0 && M > 0 && N > 0 && M % 8 == 0 && N % 8 == 0, "dense_gemm_tn: S (%lld) must be positive, M (%d) and N (%d) multiples of 8", (long long)S, M, N);
-    AB_REQUIRE(((uintptr_t)Cw % 16) == 0, "dense_gemm_tn: output pointer must be 16-byte aligned");
+    AB_REQUIRE(((uintptr_t)Cw % 16) == 0 && ((uintptr_t)ws % 16) == 0, "dense_gemm_tn: output / workspace must be 16-byte aligned");
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.N = N; p.M = M; p.E = 1; p.K = 0;
+    p.N = N; p.M = M; p.K = 0;
     p.bn = pick_bn(N, true);
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
     p.num_m_tiles = (int)ab_ceil_div(M, BM);
-    p.c_f32 = 1; p.epi = AB_EPI_NONE; p.cw = Cw;
+    p.c_f32 = 1; p.epi = AB_EPI_NONE;
     p.tn_nsrc = 1; p.tn_rows = S;
+    // the contraction runs over all S rows and the output has only a few tiles: cut S into slices (split-K) so that the
+    // whole chip works, partial products into the workspace, then one fixed-order sum
+    const size_t need = ab_dense_gemm_tn_workspace_bytes(S, M, N);
+    int nsplit = (int)(need / ((size_t)M * N * sizeof(float)));
+    if (nsplit >= 2 && (ws == nullptr || ws_bytes < need)) nsplit = 1;
+    if (nsplit < 2) nsplit = 1;
+    const int64_t kblocks = ab_ceil_div(S, BK);
+    p.E = nsplit;
+    p.tn_split = ab_ceil_div(kblocks, nsplit) * BK;
+    p.cw = nsplit > 1 ? reinterpret_cast<float*>(ws) : Cw;
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)S, 64, BK)) return e;
     if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)S, 64, BK)) return e;
-    return launch<MODE_TN>(ta, tb, p, (int64_t)p.num_m_tiles * p.num_n_tiles, stream);
+    if (int e = launch<MODE_TN>(ta, tb, p, (int64_t)nsplit * p.num_m_tiles * p.num_n_tiles, stream)) return e;
+    if (nsplit > 1) {
+        const int64_t n = (int64_t)M * N;
+        splitk_reduce_kernel<<<(unsigned)ab_ceil_div(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(ws), Cw, n, nsplit);
+        AB_LAUNCH_CHECK();
+    }
+    return AB_OK;
 }

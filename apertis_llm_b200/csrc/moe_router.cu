@@ -5,12 +5,21 @@
 // products in the same pass; the second read hits L1), LayerNorm affine is folded into the router
 // weight once per CTA (G[e,d] = ln_w[d]*Wr[e,d] in shared memory; c[e] = sum_d ln_b[d]*Wr[e,d] + br[e]).
 // Lanes 0..E-1 then own one expert each for softmax / top-K.  Ties in top-K go to the lower expert id.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int WARPS = 8;
 constexpr int MAX_K = 8;
+
+// round-trip through the autocast dtype (round to nearest even, like torch's casts)
+__device__ __forceinline__ float ab_round_to(float v, int quant) {
+    if (quant == AB_ROUTER_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    if (quant == AB_ROUTER_FP16) return __half2float(__float2half_rn(v));
+    return v;
+}
 
 template <typename T>
 __device__ __forceinline__ void row_load(const T* row, int i, float* f) {   // vector i of the row
@@ -63,20 +72,31 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
                                                                 int32_t* __restrict__ idx, float* __restrict__ probs,
                                                                 float* __restrict__ w, float* __restrict__ lse_out,
                                                                 float* __restrict__ stats, float* __restrict__ part, int S,
-                                                                int Dm, int E, int K) {
+                                                                int Dm, int E, int K, int quant) {
     constexpr int V = ab_vec16<T>::N;
     extern __shared__ float sm[];
     float* G = sm;                 // [E][Dm]
     float* cvec = G + (size_t)E * Dm;   // [E]
     float* red = cvec + 32;        // [WARPS][2E+1]
+    float* lnw_s = red + WARPS * (2 * E + 1);      // [Dm], [Dm]: LayerNorm affine (quant modes only)
+    float* lnb_s = lnw_s + Dm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = 0; e < E; ++e)
-        for (int d = tid; d < Dm; d += blockDim.x) G[(size_t)e * Dm + d] = ln_w[d] * Wr[(size_t)e * Dm + d];
-    for (int e = warp; e < E; e += WARPS) {
-        float acc = 0.f;
-        for (int d = lane; d < Dm; d += 32) acc = fmaf(ln_b[d], Wr[(size_t)e * Dm + d], acc);
-        acc = ab_warp_sum(acc);
-        if (lane == 0) cvec[e] = acc + br[e];
+    if (quant == AB_ROUTER_EXACT) {
+        for (int e = 0; e < E; ++e)
+            for (int d = tid; d < Dm; d += blockDim.x) G[(size_t)e * Dm + d] = ln_w[d] * Wr[(size_t)e * Dm + d];
+        for (int e = warp; e < E; e += WARPS) {
+            float acc = 0.f;
+            for (int d = lane; d < Dm; d += 32) acc = fmaf(ln_b[d], Wr[(size_t)e * Dm + d], acc);
+            acc = ab_warp_sum(acc);
+            if (lane == 0) cvec[e] = acc + br[e];
+        }
+    } else {
+        // autocast emulation (core.py:482 under torch.autocast): the router Linear sees its input, weight and bias rounded
+        // to the autocast dtype, accumulates in fp32 and rounds its output once
+        for (int e = 0; e < E; ++e)
+            for (int d = tid; d < Dm; d += blockDim.x) G[(size_t)e * Dm + d] = ab_round_to(Wr[(size_t)e * Dm + d], quant);
+        for (int d = tid; d < Dm; d += blockDim.x) { lnw_s[d] = ln_w[d]; lnb_s[d] = ln_b[d]; }
+        if (tid < E) cvec[tid] = ab_round_to(br[tid], quant);
     }
     __syncthreads();
     const int nvec = Dm / V;
@@ -114,6 +134,24 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
         }
         var = ab_warp_sum(var) / (float)Dm;
         const float rstd = rsqrtf(var + eps);
+        if (quant != AB_ROUTER_EXACT) {
+            // third pass over the (L1-resident) row: the normalised row rounded element by element, then the dot products
+#pragma unroll
+            for (int e = 0; e < EM; ++e) dot[e] = 0.f;
+            for (int i = lane; i < nvec; i += 32) {
+                float f[V];
+                row_load<T>(row, i, f);
+#pragma unroll
+                for (int v = 0; v < V; ++v) f[v] = ab_round_to(fmaf((f[v] - mean) * rstd, lnw_s[i * V + v], lnb_s[i * V + v]), quant);
+#pragma unroll
+                for (int e = 0; e < EM; ++e) {
+                    if (e < E) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) dot[e] = fmaf(f[v], G[(size_t)e * Dm + i * V + v], dot[e]);
+                    }
+                }
+            }
+        }
         float mylogit = 0.f;
 #pragma unroll
         for (int e = 0; e < EM; ++e) {
@@ -124,7 +162,7 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
         }
         float lc = 0.f;
         if (lane < E) {
-            lc = fmaf(rstd, mylogit, cvec[lane]);
+            lc = quant == AB_ROUTER_EXACT ? fmaf(rstd, mylogit, cvec[lane]) : ab_round_to(mylogit + cvec[lane], quant);
             mylogit = lc;
             if (noise) mylogit = fmaf(noise[(size_t)s * E + lane], noise_scale[lane], lc);
             if (lclean) lclean[(size_t)s * E + lane] = lc;
@@ -467,19 +505,20 @@ extern "C" size_t ab_moe_router_workspace_bytes(int S, int Dm, int E) { (void)Dm
 extern "C" int ab_moe_router_fwd(const void* x, const float* ln_w, const float* ln_b, float eps, const float* Wr,
                                  const float* br, const float* noise, const float* noise_scale, float* lclean, float* logits,
                                  float* gates, int32_t* idx, float* probs, float* w, float* lse, float* stats_out, float* aux,
-                                 void* ws, size_t ws_bytes, int S, int Dm, int E, int K, int dtype, cudaStream_t stream) {
+                                 void* ws, size_t ws_bytes, int S, int Dm, int E, int K, int dtype, int quant, cudaStream_t stream) {
     if (int e = check_router(S, Dm, E, K, dtype)) return e;
     const FwdWs wl = fwd_ws(S, E);
     AB_REQUIRE(ws && ws_bytes >= wl.total, "moe_router_fwd: workspace too small");
     AB_REQUIRE(noise == nullptr || noise_scale != nullptr, "moe_router_fwd: noise without noise_scale");
-    const size_t smem = ((size_t)E * Dm + 32 + WARPS * (2 * E + 1)) * sizeof(float);
+    AB_REQUIRE(quant == AB_ROUTER_EXACT || quant == AB_ROUTER_BF16 || quant == AB_ROUTER_FP16, "moe_router_fwd: bad logit rounding mode %d", quant);
+    const size_t smem = ((size_t)E * Dm + 32 + WARPS * (2 * E + 1) + 2 * (size_t)Dm) * sizeof(float);
     float* part = (float*)ws;
 #define AB_ROUTER_FWD(TT, EMV)                                                                                          \
     {                                                                                                                    \
         auto k = router_fwd_kernel<TT, EMV>;                                                                             \
         AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         k<<<wl.grid, WARPS * 32, smem, stream>>>((const TT*)x, ln_w, ln_b, eps, Wr, br, noise, noise_scale, lclean,     \
-                                                 logits, gates, idx, probs, w, lse, stats_out, part, S, Dm, E, K);      \
+                                                 logits, gates, idx, probs, w, lse, stats_out, part, S, Dm, E, K, quant); \
     }
     if (dtype == AB_F32) {
         if (E <= 8) AB_ROUTER_FWD(float, 8) else if (E <= 16) AB_ROUTER_FWD(float, 16) else AB_ROUTER_FWD(float, 32)

@@ -868,23 +868,31 @@ scan_rounds_bwd_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_c
 }
 
 // dA_log[c], dD[c] (and d dt_bias[head]) = sum over the warps that worked on the channel's slab (all sequences, all chunk
-// slots), fixed order: bitwise reproducible.  One CTA of 8 warps per slab; warp v sums partials v, v + 8, ... eight at a time.
+// slots), fixed order: bitwise reproducible.  RED_SPLIT CTAs of 8 warps per slab each sum a fixed share of the partials
+// (eight loads in flight per lane); the CTA that finishes last adds the RED_SPLIT shares in index order.
+constexpr int RED_SPLIT = 8;
+
 __global__ void __launch_bounds__(256) scan_rounds_param_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ part_b, float* __restrict__ dA,
-                                                                        float* __restrict__ dD, float* __restrict__ dbias, int Di, int H, int B, int TS, int tps,
-                                                                        int nteamchains, int cpr) {
+                                                                        float* __restrict__ dD, float* __restrict__ dbias, float4* __restrict__ stage2,
+                                                                        float* __restrict__ stage2_b, unsigned* __restrict__ arrive, int Di, int H, int B,
+                                                                        int TS, int tps, int nteamchains, int cpr) {
     __shared__ float4 red[8][32];
     __shared__ float redb[8][32];
-    const int slab = blockIdx.x, lane = threadIdx.x & 31, v = threadIdx.x >> 5;
+    __shared__ unsigned is_last;
+    const int slab = blockIdx.x, share = blockIdx.y, lane = threadIdx.x & 31, v = threadIdx.x >> 5;
     const int tslab = slab / TS, member = slab % TS;
     const int n = cpr * B;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float accb = 0.f;
-    for (int q0 = v; q0 < n; q0 += 64) {
+    // partial q belongs to share q % RED_SPLIT, warp (q / RED_SPLIT) % 8
+    for (int i0 = v; ; i0 += 64) {
+        const int qbase = i0 * RED_SPLIT + share;
+        if (qbase >= n) break;
         float4 t[8];
         float tb[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int q = q0 + u * 8;
+            const int q = (i0 + u * 8) * RED_SPLIT + share;
             t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             tb[u] = 0.f;
             if (q < n) {
@@ -905,21 +913,41 @@ __global__ void __launch_bounds__(256) scan_rounds_param_reduce_kernel(const flo
         float sb = redb[0][lane];
 #pragma unroll
         for (int i = 1; i < 8; ++i) { sum.x += red[i][lane].x; sum.y += red[i][lane].y; sum.z += red[i][lane].z; sum.w += red[i][lane].w; sb += redb[i][lane]; }
-        const int c0 = slab * 64 + 2 * lane;
-        if (c0 < Di) { dA[c0] = sum.x; dA[c0 + 1] = sum.y; dD[c0] = sum.z; dD[c0 + 1] = sum.w; }
-        // lanes (head lane >> 3, token lane & 7): sum the 8 token lanes of a head
-        sb += __shfl_xor_sync(0xffffffffu, sb, 4);
-        sb += __shfl_xor_sync(0xffffffffu, sb, 2);
-        sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-        const int head = slab * 4 + (lane >> 3);
-        if (dbias != nullptr && (lane & 7) == 0 && head < H) dbias[head] = sb;
+        __stcg(&stage2[((size_t)slab * RED_SPLIT + share) * 32 + lane], sum);
+        __stcg(&stage2_b[((size_t)slab * RED_SPLIT + share) * 32 + lane], sb);
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            const unsigned old = atomicAdd(&arrive[slab], 1u);
+            is_last = old == RED_SPLIT - 1;
+            if (is_last) { __threadfence(); arrive[slab] = 0u; }      // left clean for the next launch
+        }
+        __syncwarp();
+        if (is_last) {
+            float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+            float tb2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < RED_SPLIT; ++i) {
+                const float4 q = __ldcg(&stage2[((size_t)slab * RED_SPLIT + i) * 32 + lane]);
+                tot.x += q.x; tot.y += q.y; tot.z += q.z; tot.w += q.w;
+                tb2 += __ldcg(&stage2_b[((size_t)slab * RED_SPLIT + i) * 32 + lane]);
+            }
+            const int c0 = slab * 64 + 2 * lane;
+            if (c0 < Di) { dA[c0] = tot.x; dA[c0 + 1] = tot.y; dD[c0] = tot.z; dD[c0 + 1] = tot.w; }
+            // lanes (head lane >> 3, token lane & 7): sum the 8 token lanes of a head
+            tb2 += __shfl_xor_sync(0xffffffffu, tb2, 4);
+            tb2 += __shfl_xor_sync(0xffffffffu, tb2, 2);
+            tb2 += __shfl_xor_sync(0xffffffffu, tb2, 1);
+            const int head = slab * 4 + (lane >> 3);
+            if (dbias != nullptr && (lane & 7) == 0 && head < H) dbias[head] = tb2;
+        }
     }
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
 struct RoundsCfg {
     int nslab, nchains, TS, NST, tps, nteamchains, teams_per_cta, nteams, cpr, Tc, nck, nrounds, nseg, nck8, L8, grid, block, nw_total;
-    size_t smem, off_agg, off_segagg, off_segcarry, off_carry, off_cnt, cnt_bytes, off_part, off_part_b, total;
+    size_t smem, off_agg, off_segagg, off_segcarry, off_carry, off_cnt, cnt_bytes, off_part, off_part_b, off_stage2, total;
 };
 
 constexpr size_t SMEM_MAX = 227 * 1024;
@@ -996,8 +1024,8 @@ int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap,
     c.nseg = (int)ab_ceil_div(c.cpr, RSEG);
     // counters first, at a fixed place: a launch leaves them zeroed for the next one whatever its shape
     c.cnt_bytes = (size_t)c.nrounds * c.nchains * (c.nseg + 2) * sizeof(unsigned);
-    AB_REQUIRE(c.cnt_bytes + 256 <= CNT_REGION, "selective scan: %zu bytes of round counters exceed the reserved %zu", c.cnt_bytes, (size_t)CNT_REGION);
-    c.off_cnt = 256;
+    AB_REQUIRE(c.cnt_bytes + 4096 <= CNT_REGION && c.nslab <= 1000, "selective scan: %zu bytes of round counters exceed the reserved %zu", c.cnt_bytes, (size_t)CNT_REGION);
+    c.off_cnt = 4096;                    // [0]: sign-off word; [64 ..): one arrival word per slab of the parameter reduce
     size_t o = CNT_REGION;
     c.off_agg = o;      o += (size_t)2 * c.nchains * c.cpr * 32 * sizeof(float4);
     c.off_segagg = o;   o += (size_t)2 * c.nchains * c.nseg * 32 * sizeof(float4);
@@ -1005,6 +1033,7 @@ int make_cfg(int B, int L, int Di, int dtype, bool bwd, bool yssm, int warp_cap,
     c.off_carry = o;    o += (size_t)c.nchains * 32 * sizeof(float2);
     c.off_part = o;     o += (size_t)c.nw_total * 32 * sizeof(float4);
     c.off_part_b = o;   o += (size_t)c.nw_total * 32 * sizeof(float);
+    c.off_stage2 = o;   o += (size_t)c.nslab * RED_SPLIT * 32 * (sizeof(float4) + sizeof(float));
     c.total = o;
     return AB_OK;
 }
@@ -1238,7 +1267,12 @@ extern "C" int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm
     if (dtype == AB_F32) e = dyssm ? launch_bwd_ts<float, true>(m, p, c, stream) : launch_bwd_ts<float, false>(m, p, c, stream);
     else e = dyssm ? launch_bwd_ts<__nv_bfloat16, true>(m, p, c, stream) : launch_bwd_ts<__nv_bfloat16, false>(m, p, c, stream);
     if (e) return e;
-    scan_rounds_param_reduce_kernel<<<c.nslab, 256, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, Di, H, B, c.TS, c.tps, c.nteamchains, c.cpr);
+    unsigned char* w8 = reinterpret_cast<unsigned char*>(ws);
+    float4* stage2 = reinterpret_cast<float4*>(w8 + c.off_stage2);
+    float* stage2_b = reinterpret_cast<float*>(stage2 + (size_t)c.nslab * RED_SPLIT * 32);
+    scan_rounds_param_reduce_kernel<<<dim3(c.nslab, RED_SPLIT), 256, 0, stream>>>(p.part, p.part_b, dA_log, dD, ddt_bias, stage2, stage2_b,
+                                                                              reinterpret_cast<unsigned*>(w8 + 64), Di, H, B, c.TS, c.tps,
+                                                                              c.nteamchains, c.cpr);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

@@ -109,7 +109,7 @@ class _MoEExpertsEP(torch.autograd.Function):
         ln_b_full = ln_wb[:, 1].reshape(E, Dm).contiguous()
         use_noise = noise is not None and noise_scale is not None
         r = ops.moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
-                          f(noise_scale) if use_noise else None, K)
+                          f(noise_scale) if use_noise else None, K, cfg.get("quant", _lib.ROUTER_EXACT))
         seg = segment_rows(min(cfg["cap"], S))
         plan = ops.moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"], fixed_seg=seg)
         rows_local = E * seg                                  # == W * El * seg

@@ -230,6 +230,10 @@ class AdaptiveExpertSystem(nn.Module):
         self.use_router_z_loss = g("use_router_z_loss", True)
         self.use_load_balancing_loss = g("use_load_balancing_loss", True)
         self.last_counts: Optional[torch.Tensor] = None       # expert_token_counts_post_capacity of the last call (int32 [E])
+        # Under torch.autocast the reference's router Linear runs in the autocast dtype (core.py:482), so its top-k sees
+        # logits rounded to bf16 / fp16.  True (default): round the same way, i.e. pick the experts the reference picks in
+        # that mode; False: route on fp32 logits whatever the autocast state (what the fp32 oracle does).
+        self.router_autocast_rounding = True
         self._register_state_dict_hook(self._to_reference_keys)
         self._register_load_state_dict_pre_hook(self._from_reference_keys)
 
@@ -297,7 +301,10 @@ class AdaptiveExpertSystem(nn.Module):
                    lb_coef=self.load_balancing_loss_coef if self.use_load_balancing_loss else 0.0,
                    rz_coef=self.router_z_loss_coef if self.use_router_z_loss else 0.0,
                    active=self._draw_active_mask(x2.device), drop_p=self.hidden_dropout_prob,
-                   precise=(x2.dtype == torch.float32 and ac is None))
+                   precise=(x2.dtype == torch.float32 and ac is None),
+                   # the reference's router Linear runs in the autocast dtype (core.py:482): pick the experts it picks
+                   quant={torch.bfloat16: _lib.ROUTER_BF16, torch.float16: _lib.ROUTER_FP16}.get(ac, _lib.ROUTER_EXACT)
+                   if self.router_autocast_rounding else _lib.ROUTER_EXACT)
         if self.ep_world > 1:
             from . import ep
             out, lb, rz, counts = ep.moe_experts_ep(self, x2, noise, noise_scale, cfg)

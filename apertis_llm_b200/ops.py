@@ -471,7 +471,9 @@ def dense_tn(dy2, x2, precise):
     else:
         a, b, ss = _as_bf16(dy2), _as_bf16(x2), S
     c = torch.empty(N, K, dtype=torch.float32, device=dev)
-    call("ab_dense_gemm_tn", ptr(a), ptr(b), ptr(c), ss, N, K, stream_ptr(dev))
+    nws = query("ab_dense_gemm_tn_workspace_bytes", ss, N, K)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev) if nws else None
+    call("ab_dense_gemm_tn", ptr(a), ptr(b), ptr(c), ptr(ws), nws, ss, N, K, stream_ptr(dev))
     return c
 
 
@@ -646,7 +648,7 @@ def _u8(n, dev):
     return torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev)
 
 
-def moe_route(x2, ln_w, ln_b, eps, Wr, br, noise, noise_scale, K):
+def moe_route(x2, ln_w, ln_b, eps, Wr, br, noise, noise_scale, K, quant=_lib.ROUTER_EXACT):
     """Router forward (no autograd).  Returns dict of routing tensors."""
     S, Dm = x2.shape
     E = Wr.shape[0]
@@ -660,7 +662,7 @@ def moe_route(x2, ln_w, ln_b, eps, Wr, br, noise, noise_scale, K):
     ws = _u8(nws, dev)
     call("ab_moe_router_fwd", ptr(x2), ptr(ln_w), ptr(ln_b), float(eps), ptr(Wr), ptr(br), ptr(noise), ptr(noise_scale),
          ptr(r["lclean"]), ptr(r["logits"]), ptr(r["gates"]), ptr(r["idx"]), ptr(r["probs"]), ptr(r["w"]), ptr(r["lse"]),
-         ptr(r["stats"]), ptr(r["aux"]), ptr(ws), ws.numel(), S, Dm, E, K, dt(x2), stream_ptr())
+         ptr(r["stats"]), ptr(r["aux"]), ptr(ws), ws.numel(), S, Dm, E, K, dt(x2), quant, stream_ptr())
     return r
 
 
@@ -752,7 +754,7 @@ class _MoEExperts(torch.autograd.Function):
         W1, W2 = f(W1), f(W2)
         use_noise = noise is not None and noise_scale is not None
         r = moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
-                      f(noise_scale) if use_noise else None, K)
+                      f(noise_scale) if use_noise else None, K, cfg.get("quant", _lib.ROUTER_EXACT))
         plan = moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"])
         max_rows = plan["max_rows"]
         cdt = torch.float32 if precise else torch.bfloat16         # dtype of the GEMM outputs that feed later GEMMs

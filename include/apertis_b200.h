@@ -162,12 +162,20 @@ int ab_ssm_scan_bwd(const void* xa, int64_t xa_stride, const void* Bm, const voi
  * aux [2E+1] fp32: sum_s gates[s,e], count of tokens with e in their top-K, sum_s lse^2
  * (deterministic two-stage reduction through ws). */
 size_t ab_moe_router_workspace_bytes(int S, int Dm, int E);
+/* quant: how the clean logits are formed.  AB_ROUTER_EXACT: fp32 throughout (the reference without autocast).
+ * AB_ROUTER_BF16 / AB_ROUTER_FP16: what the reference computes under torch.autocast of that dtype (core.py:482 is an
+ * autocast nn.Linear followed by .float()): LayerNorm output, router weight and bias rounded to the dtype, fp32
+ * accumulation, the sum rounded once -- so that top-k picks the experts the reference picks in that mode. */
+#define AB_ROUTER_EXACT 0
+#define AB_ROUTER_BF16 1
+#define AB_ROUTER_FP16 2
 /* lclean [S,E] (optional unless the backward is needed) = logits before the noise term; logits [S,E]
  * (optional) = the noisy logits that were soft-maxed. */
 int ab_moe_router_fwd(const void* x, const float* ln_w, const float* ln_b, float eps, const float* Wr, const float* br,
                       const float* noise, const float* noise_scale, float* lclean, float* logits, float* gates,
                       int32_t* idx, float* probs, float* w, float* lse, float* stats_out, float* aux, void* ws,
-                      size_t ws_bytes, int S, int Dm, int E, int K, int dtype, cudaStream_t stream);
+                      size_t ws_bytes, int S, int Dm, int E, int K, int dtype, int quant,
+                      cudaStream_t stream);
 /* selection only, from given logits (the bit-exact test boundary of SURVEY.md section 7 hard part 3) */
 int ab_moe_topk_from_logits(const float* logits, float* gates, int32_t* idx, float* probs, float* w, float* lse,
                             int S, int E, int K, cudaStream_t stream);
@@ -270,12 +278,16 @@ int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* 
  * AB_EPI_ADD (aux [S,N] of c_dtype is added: a second gradient contribution accumulated in the epilogue).
  *   ab_dense_gemm_nt:  C[S,N] = epi(A[S,K] * W[N,K]^T)        (forward of nn.Linear)
  *   ab_dense_gemm_nn:  C[S,N] = epi(A[S,K] * W[K,N])          (input gradient: same weight tensor, no transpose copy)
- *   ab_dense_gemm_tn:  Cw[M,N] = A[S,M]^T * Bm[S,N]  (fp32)   (weight gradient) */
+ *   ab_dense_gemm_tn:  Cw[M,N] = A[S,M]^T * Bm[S,N]  (fp32)   (weight gradient; the contraction over S is cut into slices
+ *                      whose partial products go to ws (ab_dense_gemm_tn_workspace_bytes, may be 0) and are summed in a
+ *                      fixed order) */
 int ab_dense_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* C, int64_t S, int N, int K,
                      int epi, int c_dtype, cudaStream_t stream);
 int ab_dense_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, void* C, int64_t S, int N, int K,
                      int epi, int c_dtype, cudaStream_t stream);
-int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, int64_t S, int M, int N, cudaStream_t stream);
+size_t ab_dense_gemm_tn_workspace_bytes(int64_t S, int M, int N);
+int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, void* ws, size_t ws_bytes, int64_t S, int M, int N,
+                     cudaStream_t stream);
 
 /* ---- block wrappers: pre-norm LayerNorm  (core.py:694-695, 887-888) ------------
  * y = (x - mean) * rstd * w + b per row, eps inside the sqrt; stats [S,2] = (mean, rstd) saved for the backward.

@@ -25,6 +25,9 @@ def build_layer(spec, sd=None, dropout=0.0):
     if sd is None:
         sd = O.make_layer_params(spec["Dm"], spec["H"], spec["I"], spec["E"], seed=spec["seed"])
     layer.load_state_dict(sd, strict=True)          # reference key names -> stacked expert parameters
+    # these cases are checked against fp32 recordings of the reference (tests/golden) and the fp32 oracle, whose routing
+    # sees fp32 logits; the autocast-rounded routing is checked against the live reference in test_gpu_reference_model.py
+    layer.feed_forward.ffn.router_autocast_rounding = False
     return layer.to(dev()), sd
 
 
@@ -312,3 +315,53 @@ def test_cuda_graph_replay_matches_eager(Dm):
         assert rel_err(xs.grad, eager_dx) < 1e-2
         for k, v in named_grads(layer).items():
             assert rel_err(v, eager_g[k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("name,Dm,H,I,B,L,autocast", [
+    ("c2_full_fp32", 704, 11, 2816, 8, 4096, False),        # BASELINE.json configs[1] at the size bench.py times
+    ("c2_full_bf16", 704, 11, 2816, 8, 4096, True),
+    ("c3_multimodal_len", 704, 11, 2816, 1, 4673, False),   # configs[2]: 4096 text + 577 image tokens (odd, not a tile multiple)
+    ("c4_7b_dims", 1600, 25, 6400, 1, 4096, False),         # configs[3]: d_inner 400 (6 slabs + 16 channels), I 6400
+    ("c4_7b_dims_bf16", 1600, 25, 6400, 2, 4096, True),
+])
+def test_block_baseline_configs_vs_oracle(name, Dm, H, I, B, L, autocast):
+    """The block at the BASELINE.json shapes against the CPU oracle on the same seeded inputs and weights: output, both
+    aux losses, the post-capacity expert counts (bit-exact), the input gradient and every parameter gradient."""
+    spec = dict(Dm=Dm, H=H, I=I, E=8, K=2, B=B, L=L, seed=29)
+    layer, sd = build_layer(spec)
+    x, noise = O.make_inputs(B, L, Dm, 8, seed=29)
+    layer.train()
+    set_rng_hooks(layer, spec, noise)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    # O.block_forward spelled out so that the routing artefacts of the oracle are at hand
+    ssm, moe, norms = O.split_layer_params(sdr)
+    F = torch.nn.functional
+    n1 = F.layer_norm(xr, (Dm,), norms["attention.pre_norm.weight"], norms["attention.pre_norm.bias"], 1e-12)
+    a_r, _, _ = O.ssm_forward(ssm, n1, num_heads=H, training=True)
+    h_r = a_r + xr
+    n2 = F.layer_norm(h_r, (Dm,), norms["feed_forward.pre_norm.weight"], norms["feed_forward.pre_norm.bias"], 1e-12)
+    m_r, lb_r, rz_r, parts = O.moe_forward(moe, n2, E=8, K=2, training=True, noise=noise, return_parts=True)
+    out_r = m_r + h_r
+    O.block_loss(out_r, lb_r, rz_r).backward()
+    xg = x.to(dev()).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out, _, _, lb, rz = layer(xg)
+    O.block_loss(out, lb, rz).backward()
+    torch.cuda.synchronize()
+    tol = 2e-2 if autocast else 1e-4
+    assert rel_err(out.float(), out_r.detach()) < tol, "out"
+    assert abs(float(lb) - float(lb_r)) < max(tol, 1e-4) * max(abs(float(lb_r)), 1e-3)
+    assert abs(float(rz) - float(rz_r)) < max(tol, 1e-4) * max(abs(float(rz_r)), 1e-3)
+    counts = layer.feed_forward.ffn.last_counts.cpu().numpy()
+    if not autocast:        # fp32: same logits to ~1e-6, so the post-capacity counts are the oracle's, bit for bit
+        assert np.array_equal(counts, parts["counts"].astype(np.int32)), "expert_token_counts_post_capacity"
+    else:
+        assert int(counts.max()) <= parts["cap"] and abs(int(counts.sum()) - int(parts["counts"].sum())) <= 8
+    assert rel_err(xg.grad, xr.grad) < tol, "dx"
+    bad = []
+    for k, gr in named_grads(layer).items():
+        e = rel_err(gr, sdr[k].grad)
+        if not e < (tol if not autocast else 4e-2):
+            bad.append((k, e))
+    assert not bad, bad
