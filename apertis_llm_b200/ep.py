@@ -158,6 +158,7 @@ class _MoEExpertsEP(torch.autograd.Function):
                               r["idx"], r["probs"], r["lse"], r["lclean"], r["w"], aux, xr, h, hpre, y)
         counts = plan["counts"]
         ctx.mark_non_differentiable(counts)
+        cfg["_routing"] = (r["idx"], plan["row_of"])
         return out, lb.to(x2.dtype), rz.to(x2.dtype), counts
 
     @staticmethod

@@ -230,6 +230,7 @@ class AdaptiveExpertSystem(nn.Module):
         self.use_router_z_loss = g("use_router_z_loss", True)
         self.use_load_balancing_loss = g("use_load_balancing_loss", True)
         self.last_counts: Optional[torch.Tensor] = None       # expert_token_counts_post_capacity of the last call (int32 [E])
+        self.last_routing = None
         # Under torch.autocast the reference's router Linear runs in the autocast dtype (core.py:482), so its top-k sees
         # logits rounded to bf16 / fp16.  True (default): round the same way, i.e. pick the experts the reference picks in
         # that mode; False: route on fp32 logits whatever the autocast state (what the fp32 oracle does).
@@ -314,6 +315,7 @@ class AdaptiveExpertSystem(nn.Module):
                                                   self.expert_ln_bias, self.expert_w1, self.expert_b1, self.expert_w2,
                                                   self.expert_b2, cfg)
         self.last_counts = counts
+        self.last_routing = cfg.get("_routing")          # (idx int32 [S,K], row_of int32 [S,K], -1 = dropped by the capacity limit)
         return out.reshape(B, L, Dm), lb, rz
 
 

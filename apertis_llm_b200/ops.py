@@ -798,6 +798,7 @@ class _MoEExperts(torch.autograd.Function):
         ctx.routing = r
         counts = plan["counts"]
         ctx.mark_non_differentiable(counts)
+        cfg["_routing"] = (r["idx"], plan["row_of"])     # for the caller's inspection: chosen experts, permuted row (-1 = dropped)
         return out, lb.to(x2.dtype) if torch.is_tensor(lb) else lb, rz.to(x2.dtype) if torch.is_tensor(rz) else rz, counts
 
     @staticmethod
