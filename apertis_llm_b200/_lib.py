@@ -51,8 +51,8 @@ SIGNATURES = {
     "ab_moe_plan_workspace_bytes": (SZ, [I, I, I]),
     "ab_moe_plan": (I, [P, P, P, I, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I64, I, P]),
     "ab_moe_permute_ln": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, P]),
-    "ab_moe_unpermute": (I, [P, P, P, P, I, I, I, I, I, P]),
-    "ab_moe_unpermute_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, I, P]),
+    "ab_moe_unpermute": (I, [P, P, P, P, P, F, P, I, I, I, I, I, P]),
+    "ab_moe_unpermute_bwd": (I, [P, P, P, P, P, P, P, P, F, P, I, I, I64, I, I, I, P]),
     "ab_moe_permute_ln_bwd_workspace_bytes": (SZ, [I, I, I64]),
     "ab_moe_permute_ln_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I64, I, I, P]),
     "ab_moe_segment_colsum_workspace_bytes": (SZ, [I, I, I64]),

@@ -310,16 +310,6 @@ extern "C" int ab_layernorm_bwd(const void* dy, const void* x, const float* stat
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-__device__ __forceinline__ bool out_keep(uint32_t s0, uint32_t s1, uint64_t i, uint32_t thresh) {
-    uint32_t x = ((uint32_t)i * 0x9E3779B1u) ^ ((uint32_t)(i >> 32) * 0x85EBCA77u) ^ s0;
-    x ^= x >> 16; x *= 0x7FEB352Du;
-    x ^= x >> 15; x *= 0x846CA68Bu;
-    x ^= x >> 16; x += s1;
-    x ^= x >> 15; x *= 0x2C1B3C6Du;
-    x ^= x >> 12;
-    return x >= thresh;
-}
-
 // out[i] = (keep ? sub[i]*scale : 0) + (res ? res[i] : 0); 4 elements per thread
 template <typename TS, typename TR>
 __global__ void __launch_bounds__(256) dropout_add_kernel(const TS* __restrict__ sub, const TR* __restrict__ res, TR* __restrict__ out,
@@ -333,7 +323,7 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const TS* __restrict__
     if (seed) { s0 = __ldg(seed); s1 = __ldg(seed + 1); }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-        const bool keep = !seed || out_keep(s0, s1, (uint64_t)(i + v), thresh);
+        const bool keep = !seed || ab_out_keep(s0, s1, (uint64_t)(i + v), thresh);
         o[v] = (keep ? a[v] * scale : 0.f) + r[v];
     }
     st4<TR>(out + i, o);

@@ -110,6 +110,32 @@ __device__ __forceinline__ float ab_softplus_fast(float x) {
     return l * 0.6931471805599453f;
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two adjacent channels / columns per instruction
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f2;     // two packed fp32
+
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2_bcast(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2_ex2(f2 v) { float a, b; f2_unpack(v, a, b); return f2_pack(ab_ex2(a), ab_ex2(b)); }
+__device__ __forceinline__ f2 f2_rcp(f2 v) { float a, b; f2_unpack(v, a, b); return f2_pack(ab_rcp(a), ab_rcp(b)); }
+__device__ __forceinline__ float f2_hsum(f2 v) { float a, b; f2_unpack(v, a, b); return a + b; }
+
+// keep decision of the wrappers' output dropout (core.py:836, 918): counter-based hash of the element index and a 64-bit seed
+__device__ __forceinline__ bool ab_out_keep(uint32_t s0, uint32_t s1, uint64_t i, uint32_t thresh) {
+    uint32_t x = ((uint32_t)i * 0x9E3779B1u) ^ ((uint32_t)(i >> 32) * 0x85EBCA77u) ^ s0;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16; x += s1;
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12;
+    return x >= thresh;
+}
+
 __device__ __forceinline__ float ab_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -102,6 +102,65 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     return s * fmaf(x, 1.f - s, 1.f);
 }
 
+// ---- the same activations on column pairs (FFMA2 / FMUL2): the epilogue is instruction-issue bound at small K, and packed
+//      arithmetic halves its floating-point instruction count ----------------------------------------------------------
+__device__ __forceinline__ f2 gelu_fwd2(f2 x) {
+    float x0, x1;
+    f2_unpack(x, x0, x1);
+    const f2 a = f2_pack(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+    const f2 g = f2_ex2(f2_mul(x, f2_mul(x, f2_bcast(-0.5f * AB_LOG2E))));
+    const f2 t = f2_rcp(f2_fma(f2_bcast(0.3275911f), a, f2_bcast(1.0f)));
+    f2 q = f2_fma(f2_bcast(0.750526976f), t, f2_bcast(-1.027533652f));        // A&S 7.1.26 coefficients x 1/sqrt2
+    q = f2_fma(q, t, f2_bcast(1.005091295f));
+    q = f2_fma(q, t, f2_bcast(-0.201169571f));
+    q = f2_fma(q, t, f2_bcast(0.180191733f));
+    const f2 h = f2_mul(f2_mul(a, t), f2_mul(q, g));
+    return f2_fma(h, f2_bcast(-1.0f), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+__device__ __forceinline__ f2 gelu_bwd2(f2 x) {        // cdf(x) + x * pdf(x)
+    float x0, x1;
+    f2_unpack(x, x0, x1);
+    const f2 a = f2_pack(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+    const f2 g = f2_ex2(f2_mul(f2_mul(a, a), f2_bcast(-AB_LOG2E)));
+    const f2 t = f2_rcp(f2_fma(f2_bcast(0.3275911f), a, f2_bcast(1.0f)));
+    f2 pl = f2_fma(f2_bcast(1.061405429f), t, f2_bcast(-1.453152027f));
+    pl = f2_fma(pl, t, f2_bcast(1.421413741f));
+    pl = f2_fma(pl, t, f2_bcast(-0.284496736f));
+    pl = f2_fma(pl, t, f2_bcast(0.254829592f));
+    const f2 erfv = f2_fma(f2_mul(pl, t), f2_mul(g, f2_bcast(-1.0f)), f2_bcast(1.0f));      // erf(|x| / sqrt2)
+    float e0, e1;
+    f2_unpack(erfv, e0, e1);
+    const f2 cdf = f2_fma(f2_pack(copysignf(e0, x0), copysignf(e1, x1)), f2_bcast(0.5f), f2_bcast(0.5f));
+    return f2_fma(x, f2_mul(g, f2_bcast(0.3989422804014327f)), cdf);
+}
+template <int U>
+__device__ __forceinline__ void act_fwd_row(float (&f)[U], int act) {
+    if (act == AB_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < U; i += 2) f2_unpack(gelu_fwd2(f2_pack(f[i], f[i + 1])), f[i], f[i + 1]);
+    } else if (act == AB_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) f[i] = fmaxf(f[i], 0.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < U; ++i) f[i] = act_fwd(f[i], AB_ACT_SILU);
+    }
+}
+// bf16 round trip of a row (the value the next kernel will read), two columns per conversion
+template <int U>
+__device__ __forceinline__ void round_row_bf16(float (&f)[U]) {
+#pragma unroll
+    for (int i = 0; i < U; i += 2) {
+        uint32_t r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(f[i + 1]), "f"(f[i]));
+        f[i] = __uint_as_float(r << 16);
+        f[i + 1] = __uint_as_float(r & 0xffff0000u);
+    }
+}
+// dropout on a row: one hash per 4 columns, the keep flags become multipliers (0 or 1 / (1 - p)) applied pairwise
+template <int U>
+__device__ __forceinline__ void dropout_row(float (&f)[U], const GemmParams& p, uint32_t grow, int ncol);
+
 // Dropout keep-mask of the expert hidden activation: counter-based hash of the element index and a 64-bit seed, so the
 // backward regenerates exactly the forward's mask without storing it.  One hash serves 4 consecutive columns (four
 // 16-bit uniforms, drop when < p * 65536), ~6 integer ops per element.
@@ -117,6 +176,20 @@ __device__ __forceinline__ void drop_mask4(uint32_t s0, uint32_t s1, uint32_t ro
     keep[1] = (x >> 16) >= thresh16;
     keep[2] = (y & 0xffffu) >= thresh16;
     keep[3] = (y >> 16) >= thresh16;
+}
+
+template <int U>
+__device__ __forceinline__ void dropout_row(float (&f)[U], const GemmParams& p, uint32_t grow, int ncol) {
+    const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
+#pragma unroll
+    for (int i = 0; i < U; i += 4) {
+        bool keep[4];
+        drop_mask4(s0, s1, grow, (uint32_t)(ncol + i), (uint32_t)p.N, p.drop_thresh, keep);
+        const f2 m0 = f2_pack(keep[0] ? p.drop_scale : 0.f, keep[1] ? p.drop_scale : 0.f);
+        const f2 m1 = f2_pack(keep[2] ? p.drop_scale : 0.f, keep[3] ? p.drop_scale : 0.f);
+        f2_unpack(f2_mul(f2_pack(f[i], f[i + 1]), m0), f[i], f[i + 1]);
+        f2_unpack(f2_mul(f2_pack(f[i + 2], f[i + 3]), m1), f[i + 2], f[i + 3]);
+    }
 }
 
 // ---- descriptors ------------------------------------------------------------------------------
@@ -216,32 +289,10 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
             if (p.epi == AB_EPI_BIAS_ACT) {
                 // the pre-activation (the Linear output, rounded to the activation dtype first) goes out before the
                 // activation is applied in place, so only one fragment is live
-                if (!F32) {
-#pragma unroll
-                    for (int i = 0; i < U; ++i) f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
-                }
+                if (!F32) round_row_bf16<U>(f);
                 stage_and_store<MODE, F32>(p, stg, f, reinterpret_cast<unsigned char*>(p.c2), lane, quarter, m_tile, ncol, ncol_end);
-                if (p.act == AB_ACT_GELU) {
-#pragma unroll
-                    for (int i = 0; i < U; ++i) f[i] = gelu_fwd(f[i]);
-                } else if (p.act == AB_ACT_RELU) {
-#pragma unroll
-                    for (int i = 0; i < U; ++i) f[i] = fmaxf(f[i], 0.f);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < U; ++i) f[i] = act_fwd(f[i], AB_ACT_SILU);
-                }
-                if (p.drop_seed) {
-                    const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
-                    const uint32_t grow = (uint32_t)(m_tile * BM + quarter * 32 + lane);
-#pragma unroll
-                    for (int i = 0; i < U; i += 4) {
-                        bool keep[4];
-                        drop_mask4(s0, s1, grow, (uint32_t)(ncol + i), (uint32_t)N, p.drop_thresh, keep);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) f[i + u] = keep[u] ? f[i + u] * p.drop_scale : 0.f;
-                    }
-                }
+                act_fwd_row<U>(f, p.act);
+                if (p.drop_seed) dropout_row<U>(f, p, (uint32_t)(m_tile * BM + quarter * 32 + lane), ncol);
             } else if (p.epi == AB_EPI_ADD) {
                 // C = acc + aux (aux has C's shape and dtype): accumulate a second gradient contribution in the epilogue
                 __syncwarp();
@@ -286,21 +337,19 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned cha
                     float pre[CPV];
                     if (F32) { pre[0] = __uint_as_float(q.x); pre[1] = __uint_as_float(q.y); pre[2] = __uint_as_float(q.z); pre[3] = __uint_as_float(q.w); }
                     else ab_vec16<__nv_bfloat16>::unpack(q, pre);
+                    if (p.act == AB_ACT_GELU) {
 #pragma unroll
-                    for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(pre[i], p.act);
-                }
-                __syncwarp();
-                if (p.drop_seed) {
-                    const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
-                    const uint32_t grow = (uint32_t)(m_tile * BM + quarter * 32 + lane);
+                        for (int i = 0; i < CPV; i += 2) {
+                            const f2 d = f2_mul(f2_pack(f[j * CPV + i], f[j * CPV + i + 1]), gelu_bwd2(f2_pack(pre[i], pre[i + 1])));
+                            f2_unpack(d, f[j * CPV + i], f[j * CPV + i + 1]);
+                        }
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < U; i += 4) {
-                        bool keep[4];
-                        drop_mask4(s0, s1, grow, (uint32_t)(ncol + i), (uint32_t)N, p.drop_thresh, keep);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) f[i + u] = keep[u] ? f[i + u] * p.drop_scale : 0.f;
+                        for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(pre[i], p.act);
                     }
                 }
+                __syncwarp();
+                if (p.drop_seed) dropout_row<U>(f, p, (uint32_t)(m_tile * BM + quarter * 32 + lane), ncol);
             }
         }
         // ---- stage this thread's row, then store 8 rows x 64 B per instruction

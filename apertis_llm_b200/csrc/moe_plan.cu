@@ -285,9 +285,12 @@ __global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ 
 // out[s,:] = sum_k w[s,k] * y[row_of[s,k],:]   (warp per token, fixed slot order)
 template <typename TY, typename TO>
 __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y, const int32_t* __restrict__ row_of,
-                                                        const float* __restrict__ w, TO* __restrict__ out, int S, int K, int Dm) {
+                                                        const float* __restrict__ w, const float* __restrict__ res, TO* __restrict__ out,
+                                                        const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int S, int K, int Dm) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
+    uint32_t s0 = 0, s1 = 0;
+    if (seed) { s0 = __ldg(seed); s1 = __ldg(seed + 1); }
     for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
         TO* orow = out + (size_t)s * Dm;
         for (int d = lane * 4; d < Dm; d += 128) {
@@ -299,6 +302,15 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y
                 const TY* yr = y + (size_t)r * Dm + d;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) acc[v] += ab_to_float(yr[v]) * wk;   // separate mul and add, as index_add_(y*w)
+            }
+            // the caller's output dropout and residual add (core.py:918-919) in the same pass
+            if (seed) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] = ab_out_keep(s0, s1, (uint64_t)s * Dm + d + v, thresh) ? acc[v] * scale : 0.f;
+            }
+            if (res) {
+                const float4 rr = *reinterpret_cast<const float4*>(res + (size_t)s * Dm + d);
+                acc[0] += rr.x; acc[1] += rr.y; acc[2] += rr.z; acc[3] += rr.w;
             }
 #pragma unroll
             for (int v = 0; v < 4; ++v) orow[d + v] = ab_from_float<TO>(acc[v]);
@@ -312,10 +324,13 @@ __global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict
                                                             const float* __restrict__ w, const int32_t* __restrict__ tok_of_row,
                                                             const int32_t* __restrict__ slot_of_row,
                                                             const int32_t* __restrict__ n_rows, TO* __restrict__ dy,
-                                                            float* __restrict__ dw_row, int K, int Dm) {
+                                                            float* __restrict__ dw_row, const uint32_t* __restrict__ seed, uint32_t thresh,
+                                                            float scale, int K, int Dm) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int total = n_rows[0];
+    uint32_t s0 = 0, s1 = 0;
+    if (seed) { s0 = __ldg(seed); s1 = __ldg(seed + 1); }
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
         const int tok = tok_of_row[r];
         TO* orow = dy + (size_t)r * Dm;
@@ -331,7 +346,8 @@ __global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict
         for (int d = lane * 4; d < Dm; d += 128) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const float g = ab_to_float(drow[d + v]);
+                float g = ab_to_float(drow[d + v]);
+                if (seed) g = ab_out_keep(s0, s1, (uint64_t)tok * Dm + d + v, thresh) ? g * scale : 0.f;      // the forward's output-dropout mask
                 dot = fmaf(g, ab_to_float(yrow[d + v]), dot);
                 orow[d + v] = ab_from_float<TO>(g * wk);
             }
@@ -660,11 +676,16 @@ extern "C" int ab_moe_permute_ln(const void* x, const float* stats, const float*
     return AB_OK;
 }
 
-extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, void* out, int S, int K, int Dm,
-                                int y_dtype, int out_dtype, cudaStream_t stream) {
+extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
+                                const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
     AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute: hidden size must be a multiple of 4");
+    AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "moe_unpermute: dropout p must be in [0,1) and needs a seed when > 0");
+    AB_REQUIRE(res == nullptr || ((uintptr_t)res % 16) == 0, "moe_unpermute: the residual must be 16-byte aligned fp32");
+    const uint32_t thresh = (uint32_t)((double)drop_p * 4294967296.0);
+    const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const uint32_t* sd = drop_p > 0.f ? drop_seed : nullptr;
     const int grid = rows_grid(S);
-#define AB_UNP(TY, TO) unpermute_kernel<TY, TO><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, (TO*)out, S, K, Dm)
+#define AB_UNP(TY, TO) unpermute_kernel<TY, TO><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm)
     if (y_dtype == AB_F32 && out_dtype == AB_F32) AB_UNP(float, float);
     else if (y_dtype == AB_BF16 && out_dtype == AB_F32) AB_UNP(__nv_bfloat16, float);
     else if (y_dtype == AB_BF16 && out_dtype == AB_BF16) AB_UNP(__nv_bfloat16, __nv_bfloat16);
@@ -676,11 +697,16 @@ extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const floa
 }
 
 extern "C" int ab_moe_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row,
-                                    const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, int K, int Dm,
-                                    int64_t max_rows, int dout_dtype, int y_dtype, int dy_dtype, cudaStream_t stream) {
+                                    const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, float drop_p,
+                                    const uint32_t* drop_seed, int K, int Dm, int64_t max_rows, int dout_dtype, int y_dtype,
+                                    int dy_dtype, cudaStream_t stream) {
     AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute_bwd: hidden size must be a multiple of 4");
+    AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "moe_unpermute_bwd: dropout p must be in [0,1) and needs a seed when > 0");
+    const uint32_t thresh = (uint32_t)((double)drop_p * 4294967296.0);
+    const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const uint32_t* sd = drop_p > 0.f ? drop_seed : nullptr;
     const int grid = rows_grid(max_rows);
-#define AB_UB(TD, TY, TO) unpermute_bwd_kernel<TD, TY, TO><<<grid, 256, 0, stream>>>((const TD*)dout, (const TY*)y, w, tok_of_row, slot_of_row, n_rows, (TO*)dy, dw_row, K, Dm)
+#define AB_UB(TD, TY, TO) unpermute_bwd_kernel<TD, TY, TO><<<grid, 256, 0, stream>>>((const TD*)dout, (const TY*)y, w, tok_of_row, slot_of_row, n_rows, (TO*)dy, dw_row, sd, thresh, scale, K, Dm)
     const int key = dout_dtype * 4 + y_dtype * 2 + dy_dtype;
     switch (key) {
         case 0: AB_UB(float, float, float); break;

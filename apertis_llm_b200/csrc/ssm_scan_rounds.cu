@@ -33,17 +33,6 @@
 
 namespace {
 
-typedef unsigned long long f2;     // two packed fp32 (a channel pair)
-
-__device__ __forceinline__ f2 f2_pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f2 f2_bcast(float v) { return f2_pack(v, v); }
-__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2 f2_ex2(f2 v) { float a, b; f2_unpack(v, a, b); return f2_pack(ab_ex2(a), ab_ex2(b)); }
-__device__ __forceinline__ float f2_hsum(f2 v) { float a, b; f2_unpack(v, a, b); return a + b; }
-
 // sigmoid of a channel pair.  bf16 activations: single-MUFU tanh form (relative error ~5e-4, below bf16 resolution);
 // fp32 activations: ex2 + rcp
 template <typename T>

@@ -143,7 +143,7 @@ class _MoEExpertsEP(torch.autograd.Function):
         # ---- combine
         y = all_to_all_equal(yr.view(W, El * seg, Dm), group).view(rows_local, Dm)
         out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
-        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(out), S, K, Dm, dt(y), dt(out), stream_ptr())
+        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None, S, K, Dm, dt(y), dt(out), stream_ptr())
         aux = r["aux"]
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
         lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
@@ -173,7 +173,7 @@ class _MoEExpertsEP(torch.autograd.Function):
         dy = torch.empty(rows, Dm, dtype=cdt, device=dev)
         dw_row = torch.empty(rows, **f32)
         call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
-             ptr(dy), ptr(dw_row), K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+             ptr(dy), ptr(dw_row), 0.0, None, K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
         dyr = all_to_all_equal(dy.view(W, El * seg, Dm), group).view(rows, Dm)
         lseg = rplan["seg_off"]
         stride = El * seg

@@ -283,10 +283,16 @@ class AdaptiveExpertSystem(nn.Module):
         active[perm[:ndrop]] = 0
         return active
 
-    def forward(self, hidden_states: torch.Tensor):
+    def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None, output_dropout_p: float = 0.0):
+        """forward(hidden_states) is the reference's contract (core.py:470).  The two optional arguments let a caller hand
+        in its residual and output-dropout probability (core.py:918-919): the result is then
+        residual + Dropout(p)(moe(hidden_states)), computed inside the combine kernel instead of by two more passes."""
         zero = lambda: torch.tensor(0.0, device=hidden_states.device, dtype=hidden_states.dtype)
         if self.num_experts <= 0 or self.router is None:
-            return hidden_states, zero(), zero()                              # core.py:474-475
+            out = hidden_states
+            if residual is not None:
+                out = residual + F.dropout(out, output_dropout_p, self.training)
+            return out, zero(), zero()                                        # core.py:474-475
         _lib.ensure_device(hidden_states.device)
         ac = _autocast_dtype()
         B, L, Dm = hidden_states.shape
@@ -309,11 +315,14 @@ class AdaptiveExpertSystem(nn.Module):
         if self.ep_world > 1:
             from . import ep
             out, lb, rz, counts = ep.moe_experts_ep(self, x2, noise, noise_scale, cfg)
+            if residual is not None:
+                out = ops.dropout_add(out.reshape(residual.shape), residual, output_dropout_p, training).reshape(S, Dm)
         else:
+            cfg["out_drop_p"] = float(output_dropout_p)
             out, lb, rz, counts = ops.moe_experts(x2, self.router_norm.weight, self.router_norm.bias, self.router.weight,
                                                   self.router.bias, noise, noise_scale, self.expert_ln_weight,
                                                   self.expert_ln_bias, self.expert_w1, self.expert_b1, self.expert_w2,
-                                                  self.expert_b2, cfg)
+                                                  self.expert_b2, cfg, res=residual.reshape(S, Dm) if residual is not None else None)
         self.last_counts = counts
         self.last_routing = cfg.get("_routing")          # (idx int32 [S,K], row_of int32 [S,K], -1 = dropped by the capacity limit)
         return out.reshape(B, L, Dm), lb, rz
@@ -367,8 +376,8 @@ class _FeedForwardWrapper(nn.Module):
 
     def forward(self, hidden_s):
         normed, skip = ops.layer_norm_skip(hidden_s, self.pre_norm.weight, self.pre_norm.bias, self.pre_norm.eps)
-        out, lb, rz = self.ffn(normed)
-        return ops.dropout_add(out, skip, self.output_dropout.p, self.training), lb, rz
+        # output dropout + residual add (core.py:918-919) happen inside the MoE's combine kernel
+        return self.ffn(normed, residual=skip, output_dropout_p=self.output_dropout.p)
 
 
 class ApertisLayerB200(nn.Module):

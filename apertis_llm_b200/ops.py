@@ -742,7 +742,7 @@ class _MoEExperts(torch.autograd.Function):
     returns out [S,Dm], lb, rz, counts (non-differentiable int32 [E])"""
 
     @staticmethod
-    def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg):
+    def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, res, cfg):
         _lib.ensure_device(x2.device)
         dev = x2.device
         S, Dm = x2.shape
@@ -781,15 +781,23 @@ class _MoEExperts(torch.autograd.Function):
         else:
             a2, w2, k2 = h, _cast_bf16(W2), I
         y = grouped_gemm("nt", a2, w2, plan, Dm, k2, E, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
-        out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
-        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(out), S, K, Dm, dt(y), dt(out), stream_ptr())
+        # ---- combine (core.py:605) + the caller's output dropout and residual add (core.py:918-919) when it hands them in
+        out_p = float(cfg.get("out_drop_p", 0.0)) if training else 0.0
+        out_seed = torch.randint(0, 2 ** 31 - 1, (2,), device=dev, dtype=torch.int32) if out_p > 0.0 else None
+        resc = res.reshape(S, Dm).float().contiguous() if res is not None else None
+        out = torch.empty(S, Dm, dtype=x2.dtype if res is None else torch.float32, device=dev)
+        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(resc), ptr(out), out_p, ptr(out_seed), S, K, Dm, dt(y), dt(out),
+             stream_ptr())
         # ---- aux losses (core.py:499-505, 524-526) from the kernel's deterministic sums
         aux = r["aux"]
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
         lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
-        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt, drop_p=drop_p)
+        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt, drop_p=drop_p, out_p=out_p,
+                       has_res=res is not None, res_shape=res.shape if res is not None else None,
+                       res_dtype=res.dtype if res is not None else None)
         ctx.drop_seed = drop_seed
+        ctx.out_seed = out_seed
         ctx.shadows = None if precise else (w1, w2)        # bf16 weight shadows cast in this forward, reused by the backward
         ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
         ctx.save_for_backward(x2, rn_w, rn_b, Wr, br, ln_w, W1, W2, noise if use_noise else None,
@@ -814,7 +822,7 @@ class _MoEExperts(torch.autograd.Function):
         dy = torch.empty(max_rows, Dm, dtype=cdt, device=dev)
         dw_row = torch.empty(max_rows, **f32)
         call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
-             ptr(dy), ptr(dw_row), K, Dm, max_rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+             ptr(dy), ptr(dw_row), cfg["out_p"], ptr(ctx.out_seed), K, Dm, max_rows, dt(dout), dt(y), dt(cdt), stream_ptr())
         seg = plan["seg_off"]
         if precise:
             seg3 = (seg * 3).contiguous()
@@ -866,11 +874,13 @@ class _MoEExperts(torch.autograd.Function):
              ptr(lse), ptr(lclean), ptr(noise.float().contiguous()) if cfg["use_noise"] else None, ptr(fvec), ptr(scal), ptr(dw_row),
              ptr(dxrow), ptr(plan["row_of"]), ptr(dx), ptr(dWr), ptr(dbr), ptr(drn_w), ptr(drn_b), ptr(dns), ptr(ws2), ws2.numel(),
              S, Dm, E, K, dt(x2), stream_ptr())
-        return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w, dln_b, dW1, db1, dW2, db2, None)
+        dres = dout.reshape(cfg["res_shape"]).to(cfg["res_dtype"]) if cfg["has_res"] else None       # the residual passes the gradient on
+        return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w, dln_b, dW1, db1, dW2, db2, dres, None)
 
 
-def moe_experts(x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg):
-    return _MoEExperts.apply(x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg)
+def moe_experts(x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg, res=None):
+    """res (optional, [S, Dm]): the caller's residual; with it the result is res + dropout(cfg['out_drop_p'])(moe(x2))."""
+    return _MoEExperts.apply(x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, res, cfg)
 
 
 def moe_capacity(S: int, E: int, factor: float, training: bool, use_limit: bool) -> int:

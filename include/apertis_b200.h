@@ -204,12 +204,15 @@ int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* active, int c
 int ab_moe_permute_ln(const void* x, const float* stats, const float* ln_w, const float* ln_b,
                       const int32_t* tok_of_row, const int32_t* tile_expert, const int32_t* n_rows, void* xn,
                       int Dm, int row_align, int64_t max_rows, int dtype, int out_dtype, cudaStream_t stream);
-/* unpermute: out[s,:] = sum_k (row_of[s,k] >= 0) * w[s,k] * y[row_of[s,k],:]  in fixed slot order. */
-int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, void* out, int S, int K, int Dm,
-                     int y_dtype, int out_dtype, cudaStream_t stream);
+/* unpermute: m[s,:] = sum_k (row_of[s,k] >= 0) * w[s,k] * y[row_of[s,k],:]  in fixed slot order;
+ * out = res + dropout_p(m): the caller's output dropout and residual add (core.py:918-919) in the same pass
+ * (res NULL: no residual; drop_p 0: no dropout; drop_seed: device uint32[2]). */
+int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
+                     const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, cudaStream_t stream);
 /* backward of unpermute: dy[r,:] = w[r]*dout[tok,:] (dy_dtype), dw_row[r] = <dout[tok,:], y[r,:]>; padding rows -> 0 */
 int ab_moe_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row,
-                         const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, int K, int Dm,
+                         const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, float drop_p,
+                         const uint32_t* drop_seed, int K, int Dm,
                          int64_t max_rows, int dout_dtype, int y_dtype, int dy_dtype, cudaStream_t stream);
 /* backward of permute_ln per row: dxrow[r,:] = LayerNorm-backward(dxn[r,:]) (fp32), and the per-expert
  * affine grads dln_w/dln_b [E,Dm] (deterministic two-stage reduction through ws). */

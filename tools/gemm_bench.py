@@ -33,6 +33,7 @@ def main():
     xn, h, hpre, dy, dh = bf(rows, Dm), bf(rows, I), bf(rows, I), bf(rows, Dm), bf(rows, I)
     w1, w2 = bf(E, I, Dm), bf(E, Dm, I)
     b1, b2 = torch.randn(E, I, device=d), torch.randn(E, Dm, device=d)
+    seed = torch.tensor([12345, 678], dtype=torch.int32, device=d)
     cases = {
         "nt1_fwd_bias_gelu": lambda: ops.grouped_gemm("nt", xn, w1, plan, I, Dm, E, bias=b1, epi=_lib.EPI_BIAS_ACT, act=0, want_c2=True),
         "nt2_fwd_bias": lambda: ops.grouped_gemm("nt", h, w2, plan, Dm, I, E, bias=b2, epi=_lib.EPI_BIAS),
@@ -41,6 +42,10 @@ def main():
         "tn2_wgrad": lambda: ops.grouped_gemm_tn(dy, h, seg, Dm, I, E),
         "tn1_wgrad": lambda: ops.grouped_gemm_tn(dh, xn, seg, I, Dm, E),
         "nt1_plain": lambda: ops.grouped_gemm("nt", xn, w1, plan, I, Dm, E),
+        "nt1_fwd_bias_gelu_drop": lambda: ops.grouped_gemm("nt", xn, w1, plan, I, Dm, E, bias=b1, epi=_lib.EPI_BIAS_ACT, act=0, want_c2=True,
+                                                            drop_p=0.1, drop_seed=seed),
+        "nn2_dgrad_dgelu_drop": lambda: ops.grouped_gemm("nn", dy, w2, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=0, drop_p=0.1,
+                                                          drop_seed=seed),
     }
     only = [c for c in args.only.split(",") if c]
     flops = 2.0 * rows * Dm * I
