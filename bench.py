@@ -252,6 +252,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-sample-tokens", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-batch", type=int, default=4, help="sequences per GPU per step of the additional configs[3] measurement")
+    ap.add_argument("--no-c4", action="store_true", help="skip the additional configs[3] (7B-class) measurement")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the unmodified reference on the GPU")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as a CUDA graph (auto: use it when capture and a replay check succeed)")
     args = ap.parse_args()
@@ -285,8 +288,6 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the single JSON line
     import torch.distributed as dist
-    from apertis_llm_b200 import ApertisLayerB200, BlockConfig, _lib
-    from oracle import apertis_oracle as O   # only for the deterministic parameter factory and the cpu_baseline leg
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -295,22 +296,115 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         ep_group = dist.group.WORLD
     assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun"
+    ctx = dict(dev=dev, world=world, rank=rank, local_rank=local_rank, ep_group=ep_group, args=args)
 
+    # headline: BASELINE.json configs[1] (the configuration the metric is quoted on) at every N, so the driver's
+    # scaling series compares like with like
+    head = measure(args.workload, args.batch, ctx, clocks=True)
+    # configs[3] (7B-class, 8 experts top-2, experts sharded over the ranks) measured in the same run at every N
+    extra = {}
+    if not args.no_c4 and args.workload != "c4_7b":
+        try:
+            extra["c4_7b"] = measure("c4_7b", args.c4_batch, ctx, clocks=False)
+        except Exception as ex:
+            extra["c4_7b"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+    ep_check = None
+    if world > 1:
+        try:
+            ep_check = ep_parity_check(ctx, "c4_7b")
+        except Exception as ex:
+            ep_check = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
+    def shutdown():
+        """Multi-GPU exit without the collective teardown: the captured graphs hold NCCL work and the ranks leave at
+        different times (rank 0 still runs the CPU baseline), so destroy_process_group() can block; every timed and
+        reduced number is final before this point."""
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
+        return
+
+    pk, pk_src = peaks()
+    amp = args.dtype == "bf16"
+    Dm, H, I, E, K, seq = WORKLOADS[args.workload]
+    tokens_per_step = args.batch * seq
+    out = summarise(args.workload, args.batch, head, world, pk, pk_src, amp)
+    out = dict({"metric": METRIC, "value": out.pop("value"), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": out.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": dict(cfg_common, global_batch_tokens=tokens_per_step * world, hidden_dropout_prob=args.dropout,
+                               parallelism=("single GPU" if world == 1 else f"ep{world} (experts sharded, all-to-all) + dp{world}"),
+                               precision="bf16 autocast over fp32 master weights" if amp else "fp32 (3x bf16-split tensor-core GEMMs)",
+                               l2="inputs rotate over 4 buffers (%.0f MB > 126 MB L2); per-step activations ~GBs" % (4 * tokens_per_step * Dm * 4 / 1e6)),
+                "clocks": head["clocks"]}, **out)
+    if world == 1:
+        try:        # the long-context point of the scan sweep, next to the scan inside the block
+            out["kernels"]["selective_scan_L64K"] = scan_long_context(pk["hbm_gbs"])
+        except Exception as e:      # never lose the bench line over the extra measurement
+            out["kernels"]["selective_scan_L64K"] = {"error": repr(e)[:200]}
+    for name, m in extra.items():
+        if "error" in m:
+            out.setdefault("workloads", {})[name] = m
+        else:
+            w = summarise(name, args.c4_batch, m, world, pk, pk_src, amp)
+            w["config"] = {"workload": workload_text(name), "tokens_per_step_per_gpu": args.c4_batch * WORKLOADS[name][5],
+                           "hidden_dropout_prob": args.dropout}
+            out.setdefault("workloads", {})[name] = w
+    if ep_check is not None:
+        out["ep_parity"] = ep_check
+        out["ep_parity_rel_err"] = ep_check.get("max_rel_err")
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            out["gpu_reference"] = gpu_reference_leg(args, dev)
+        except Exception as ex:
+            out["gpu_reference"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    if not args.no_cpu_baseline:
+        v, cms, cores, sample, kind = cpu_reference_arm(args, wl, 3, 1, args.cpu_sample_tokens)
+        out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_step": cms}
+    print(json.dumps(out))
+    shutdown()
+
+
+def workload_text(name):
+    Dm, H, I, E, K, seq = WORKLOADS[name]
+    return f"{name}: Apertis block hidden {Dm}, heads {H}, d_inner {16 * H}, intermediate {I}, {E} experts top-{K}, seq {seq}"
+
+
+TIMED = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_ssm_scan_fwd", "ab_ssm_scan_bwd",
+         "ab_dense_gemm_nt", "ab_dense_gemm_nn", "ab_dense_gemm_tn"]
+
+
+def build_layer(name, ctx, dropout, ep=True):
+    from apertis_llm_b200 import ApertisLayerB200, BlockConfig
+    from oracle import apertis_oracle as O   # only the deterministic parameter factory (reference initialiser's distributions)
+    Dm, H, I, E, K, seq = WORKLOADS[name]
     cfg = BlockConfig(hidden_size=Dm, num_attention_heads=H, intermediate_size=I, num_experts=E, experts_per_token=K,
-                      hidden_dropout_prob=args.dropout)
-    layer = ApertisLayerB200(cfg, ep_group=ep_group)
-    sd = O.make_layer_params(Dm, H, I, E, seed=0, perturb=False)       # the reference initialiser's distributions
-    layer.load_state_dict(sd, strict=True)
-    layer = layer.to(dev).train()
-    replicated = [p for n, p in layer.named_parameters() if ".expert_" not in n]
+                      hidden_dropout_prob=dropout)
+    layer = ApertisLayerB200(cfg, ep_group=ctx["ep_group"] if ep else None)
+    layer.load_state_dict(O.make_layer_params(Dm, H, I, E, seed=0, perturb=False), strict=True)
+    return layer.to(ctx["dev"]).train()
 
-    B = args.batch
-    tokens_per_step = B * seq
+
+def measure(name, B, ctx, clocks):
+    """One workload on this rank's GPU: device-timed steps (CUDA graph replay when it captures), per-kernel times from an
+    eager pass, and the end-to-end loop with host inputs.  Times are the maximum over the ranks."""
+    import torch.distributed as dist
+    from apertis_llm_b200 import _lib
+    args, dev, world, rank = ctx["args"], ctx["dev"], ctx["world"], ctx["rank"]
+    Dm, H, I, E, K, seq = WORKLOADS[name]
+    layer = build_layer(name, ctx, args.dropout)
+    replicated = [p for n, p in layer.named_parameters() if ".expert_" not in n]
     nbuf = 4
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     host_x = [torch.randn(B, seq, Dm, generator=gen).pin_memory() for _ in range(nbuf)]
     dev_x = [h.to(dev, non_blocking=True).requires_grad_(True) for h in host_x]
     amp = args.dtype == "bf16"
+    flat_grad = torch.zeros(sum(p.numel() for p in replicated), device=dev) if world > 1 else None
 
     def step(x):
         for p in layer.parameters():
@@ -320,9 +414,9 @@ def main():
             out, _, _, lb, rz = layer(x)
         loss = _MeanSquare.apply(out) + lb + rz           # mean(out^2) + lb + rz
         loss.backward()
-        if world > 1:                                   # DDP-equivalent all-reduce of the replicated parameters' grads
-            flat = torch.cat([p.grad.reshape(-1) for p in replicated])
-            dist.all_reduce(flat)
+        if world > 1:                                   # DDP-equivalent: one bucket of the replicated parameters' gradients
+            torch._foreach_copy_(list(flat_grad.split([p.numel() for p in replicated])), [p.grad.reshape(-1) for p in replicated])
+            dist.all_reduce(flat_grad)
         return loss
 
     def barrier():
@@ -336,7 +430,7 @@ def main():
     barrier()
 
     # ---- optional: the whole step (forward, loss, backward, gradient all-reduce) captured once per input buffer as a CUDA
-    #      graph and replayed, which removes the host launch path from the step (the block is ~120 launches of 3-300 us)
+    #      graph and replayed, which removes the host launch path from the step
     graphs, graph_note = None, "off"
     if args.graph != "off":
         try:
@@ -356,9 +450,9 @@ def main():
                 pool = g.pool()
                 graphs.append((g, gl))
             barrier()
-            eager = float(step(dev_x[0]))
+            eager = float(step(dev_x[0]).detach())
             graphs[0][0].replay()
-            replayed = float(graphs[0][1])
+            replayed = float(graphs[0][1].detach())
             if not (replayed == replayed and abs(replayed - eager) <= 0.05 * abs(eager)):
                 raise RuntimeError(f"graph replay loss {replayed} vs eager {eager}")
             graph_note = "on"
@@ -375,16 +469,20 @@ def main():
         return step(dev_x[i % nbuf])
 
     # ---- timed region: device-resident inputs, CUDA events
-    timed_names = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_ssm_scan_fwd", "ab_ssm_scan_bwd",
-                   "ab_selective_scan_fwd", "ab_selective_scan_bwd"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(2):
         run_step(i)
-    with ClockSampler(local_rank) as clk:
+
+    class _NoClk:
+        def __enter__(self): return self
+        def __exit__(self, *a): pass
+        def summary(self): return None
+
+    with (ClockSampler(ctx["local_rank"]) if clocks else _NoClk()) as clk:
         barrier()
         if graphs is None:
             launches0 = _lib.launch_count
-            _lib.start_timing(timed_names)
+            _lib.start_timing(TIMED)
         e0.record()
         for i in range(args.steps):
             run_step(i)
@@ -394,13 +492,13 @@ def main():
             per_kernel = _lib.stop_timing()
             launches = _lib.launch_count - launches0
     ms = e0.elapsed_time(e1) / args.steps
-    clocks = clk.summary()
+    clk_summary = clk.summary()
     if graphs is not None:
         # per-kernel CUDA events cannot be read inside a replayed graph: the same steps once more, eagerly, for the
         # roofline figures and the launch count (the kernels and their inputs are identical)
         barrier()
         launches0 = _lib.launch_count
-        _lib.start_timing(timed_names)
+        _lib.start_timing(TIMED)
         for i in range(args.steps):
             step(dev_x[i % nbuf])
         barrier()
@@ -443,6 +541,7 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
 
     # ---- max over ranks
+    kept_total = kept
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -450,71 +549,113 @@ def main():
         k = torch.tensor([kept], device=dev, dtype=torch.int64)
         dist.all_reduce(k)
         kept_total = int(k.item())
-    else:
-        kept_total = kept
-    def shutdown():
-        """Multi-GPU exit without the collective teardown: the captured graphs hold NCCL work and the ranks leave at
-        different times (rank 0 still runs the CPU baseline), so destroy_process_group() can block; every timed and
-        reduced number is final before this point."""
-        sys.stdout.flush()
-        sys.stderr.flush()
-        if world > 1:
-            if graphs is not None:
-                graphs.clear()
-            torch.cuda.synchronize()
-            os._exit(0)
+    if graphs is not None:
+        graphs.clear()
+    del layer, dev_x, stage
+    torch.cuda.empty_cache()
+    return dict(ms=ms, e2e_ms=e2e_ms, kept_total=kept_total, per_kernel=per_kernel, launches=launches, graph_note=graph_note,
+                last_loss=last, clocks=clk_summary, h2d=B * seq * Dm * 4)
 
-    if rank != 0:
-        shutdown()
-        return
 
-    pk, pk_src = peaks()
-    gemm_ms = sum(sum(per_kernel.get(n, [])) for n in timed_names[:3]) / args.steps
-    scan_ms = sum(sum(per_kernel.get(n, [])) for n in timed_names[3:]) / args.steps
-    n_gemm = sum(len(per_kernel.get(n, [])) for n in timed_names[:3]) / args.steps
-    gemm_flops = 12.0 * Dm * I * (kept_total / world)                    # per GPU per step (SURVEY.md 8d)
+def summarise(name, B, m, world, pk, pk_src, amp):
+    """Headline numbers and roofline entries of one measured workload."""
+    Dm, H, I, E, K, seq = WORKLOADS[name]
+    steps = max(1, len(m["per_kernel"].get("ab_ssm_scan_fwd", [1])))
+    tokens_per_step = B * seq
+    ms, e2e_ms = m["ms"], m["e2e_ms"]
+    per = lambda names: sum(sum(m["per_kernel"].get(n, [])) for n in names) / steps
+    cnt = lambda names: sum(len(m["per_kernel"].get(n, [])) for n in names) / steps
+    moe = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn"]
+    dense = ["ab_dense_gemm_nt", "ab_dense_gemm_nn", "ab_dense_gemm_tn"]
+    scan = ["ab_ssm_scan_fwd", "ab_ssm_scan_bwd"]
+    gemm_ms, dense_ms, scan_ms = per(moe), per(dense), per(scan)
+    gemm_flops = 12.0 * Dm * I * (m["kept_total"] / world)                 # per GPU per step (SURVEY.md 8d)
+    Di = 16 * H
+    R = -(-Dm // 16)
+    dense_flops = 6.0 * tokens_per_step * (Dm * 2 * Di + Di * (((H + 7) // 8 * 8) + 2 * Di) + Di * Dm)      # fwd + dgrad + wgrad
     es = 2 if amp else 4
-    scan_bytes = tokens_per_step * (14 * 16 * H + 3 * H) * es           # fwd+bwd algorithmic bytes (SURVEY.md 8d)
+    scan_bytes = tokens_per_step * (14 * Di + 3 * H) * es                  # fwd+bwd algorithmic bytes (SURVEY.md 8d)
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    traffic = None
-    try:        # mean dram__bytes_read+write per launch of the one `ncu --set full` capture summarised under profiles/
-        if args.workload == "c2_1p5b" and args.batch == 8 and world == 1:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1e_gemm_traffic.json")))["mean_dram_bytes_per_launch"]
+    traffic, traffic_src = None, None
+    try:        # mean dram__bytes_read+write per launch of this round's `ncu --set full` capture summarised under profiles/
+        if name == "c2_1p5b" and B == 8 and world == 1:
+            t = json.load(open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")))
+            traffic, traffic_src = t["mean_dram_bytes_per_launch"], t.get("source")
     except Exception:
         traffic = None
     roofline = {"kernel": "grouped_gemm_kernel<NT|NN|TN> (tcgen05 expert GEMM: 2 fwd + 2 dgrad + 2 wgrad launches per step)",
-                "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tflops / pk["bf16_tflops_sustained"], "traffic": traffic,
-                "traffic_note": "bytes per launch, profiles/r1e_gemm_ncu_summary.md; algorithmic bytes per launch ~ 0.3-0.55 GB", "peak_source": pk_src + ", sustained bf16",
-                "ms_per_step_in_kernel": gemm_ms, "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms,
-                "algorithmic_flops_per_step": gemm_flops, "kept_rows_per_step": kept_total / world}
+                "bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": gemm_tflops / pk["bf16_tflops"], "frac_of_sustained_peak": gemm_tflops / pk["bf16_tflops_sustained"],
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk_src + ", burst bf16 (the step is a few ms: clocks stay at their maximum, see `clocks`)",
+                "ms_per_step_in_kernel": gemm_ms, "launches_per_step": cnt(moe), "share_of_step": gemm_ms / ms,
+                "algorithmic_flops_per_step": gemm_flops, "kept_rows_per_step": m["kept_total"] / world}
     kernels = {"selective_scan_fwd+bwd": {"bound": "hbm", "achieved": scan_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                            "frac": scan_gbs / pk["hbm_gbs"], "ms_per_step_in_kernel": scan_ms,
-                                           "algorithmic_bytes_per_step": scan_bytes, "share_of_step": scan_ms / ms}}
-    if world == 1:
-        try:        # the long-context point of the scan sweep, next to the scan inside the block
-            kernels["selective_scan_L64K"] = scan_long_context(pk["hbm_gbs"])
-        except Exception as e:      # never lose the bench line over the extra measurement
-            kernels["selective_scan_L64K"] = {"error": repr(e)[:200]}
-    out = {"metric": METRIC, "value": tokens_per_step * world / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
-           "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-           "config": dict(cfg_common, global_batch_tokens=tokens_per_step * world, hidden_dropout_prob=args.dropout,
-                          parallelism=("single GPU" if world == 1 else f"ep{world} (experts sharded, all-to-all) + dp{world}"),
-                          precision="bf16 autocast over fp32 master weights" if amp else "fp32 (3x bf16-split tensor-core GEMMs)",
-                          l2="inputs rotate over 4 buffers (%.0f MB > 126 MB L2); per-step activations ~GBs" % (nbuf * B * seq * Dm * 4 / 1e6)),
-           "clocks": clocks, "cuda_graph": graph_note,
-           "e2e": {"value": tokens_per_step * world / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": B * seq * Dm * 4, "d2h_bytes_per_step": 4,
-                   "how": "pinned host x -> device each step (prefetched on a copy stream), block fwd+bwd through the module API, loss.item()"},
-           "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "last_loss": last}
-    if not args.no_cpu_baseline:
-        v, cms, cores, sample, kind = cpu_reference_arm(args, wl, 3, 1, args.cpu_sample_tokens)
-        out["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_step": cms}
-    print(json.dumps(out))
-    shutdown()
+                                           "algorithmic_bytes_per_step": scan_bytes, "share_of_step": scan_ms / ms},
+               "ssm_projection_gemms": {"bound": "tensor", "achieved": dense_flops / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0,
+                                        "unit": "TFLOP/s", "ms_per_step_in_kernel": dense_ms, "launches_per_step": cnt(dense),
+                                        "share_of_step": dense_ms / ms, "note": "same tcgen05 kernel, dense entry points; small K (176..704): latency / HBM bound"}}
+    return {"value": tokens_per_step * world / (ms * 1e-3), "ms_per_step": ms, "cuda_graph": m["graph_note"],
+            "e2e": {"value": tokens_per_step * world / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4,
+                    "how": "pinned host x -> device each step (prefetched on a copy stream), block fwd+bwd through the module API, loss.item()"},
+            "gpu_launches": m["launches"], "roofline": roofline, "kernels": kernels, "last_loss": m["last_loss"]}
 
+
+def ep_parity_check(ctx, name, B=1):
+    """Expert parallelism against the same layer with every expert local, on this rank's own batch, before anything is
+    timed: forward output, input gradient and this rank's shard of the expert weight gradients (dropout 0, the same
+    routing noise on both sides).  Returns the largest relative error over the ranks."""
+    import torch.distributed as dist
+    dev, world, rank, group = ctx["dev"], ctx["world"], ctx["rank"], ctx["ep_group"]
+    Dm, H, I, E, K, seq = WORKLOADS[name]
+    ep_layer, loc_layer = build_layer(name, ctx, 0.0, ep=True), build_layer(name, ctx, 0.0, ep=False)
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    x = torch.randn(B, seq, Dm, generator=g).to(dev)
+    noise = torch.randn(B * seq, E, generator=g).to(dev)
+    res = {}
+    for tag, layer in (("ep", ep_layer), ("local", loc_layer)):
+        layer.feed_forward.ffn._draw_noise = lambda S, E_, device: noise
+        xg = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out, _, _, lb, rz = layer(xg)
+        (out.float().pow(2).mean() + lb + rz).backward()
+        res[tag] = (out.detach().float(), xg.grad.float(), layer.feed_forward.ffn.expert_w1.grad.float(),
+                    layer.feed_forward.ffn.last_counts.clone())
+    El = E // world
+    # every expert local: this rank's tokens only.  Under EP the shard holds the sum over all ranks' tokens / world
+    # (what DDP's gradient averaging gives replicated experts): reduce the local-experts gradients the same way
+    w1_all = res["local"][2].clone()
+    dist.all_reduce(w1_all, group=group)
+    w1_ref = w1_all[rank * El:(rank + 1) * El] / world
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    errs = torch.tensor([rel(res["ep"][0], res["local"][0]), rel(res["ep"][1], res["local"][1]), rel(res["ep"][2], w1_ref),
+                         0.0 if torch.equal(res["ep"][3], res["local"][3]) else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX, group=group)
+    out, dx, dw1, cnt = errs.tolist()
+    del ep_layer, loc_layer
+    torch.cuda.empty_cache()
+    return {"workload": workload_text(name), "tokens_per_rank": B * seq, "out_rel_err": out, "dx_rel_err": dx, "expert_w1_grad_rel_err": dw1,
+            "expert_counts_equal": cnt == 0.0, "max_rel_err": max(out, dx, dw1), "precision": "bf16 autocast on both sides",
+            "what": "EP layer vs the same layer with all experts local, per rank, max over ranks"}
+
+
+def gpu_reference_leg(args, dev, steps=3):
+    """The UNMODIFIED reference block on this B200 (CUDA fp32 and bf16 autocast), BASELINE.md section 4's 'real bar'."""
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref is absent"}
+    wl = WORKLOADS[args.workload]
+    B, seq = args.batch, wl[5]
+    out = {"workload": workload_text(args.workload), "tokens_per_step": B * seq, "hidden_dropout_prob": args.dropout,
+           "how": "unmodified reference ApertisLayer on cuda, fwd + SURVEY 8(d) loss + bwd, wall clock with synchronize, mean of %d steps after 1 warm-up" % steps}
+    for tag, ac in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        v, ms, _ = reference_time(wl, B, seq, args.dropout, dev, steps, 1, autocast=ac)
+        out[tag] = {"tokens_per_s": v, "ms_per_step": ms}
+        torch.cuda.empty_cache()
+    return out
 
 
 def scan_long_context(pk_hbm, L=65536, Hh=32, iters=10):

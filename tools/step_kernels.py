@@ -27,7 +27,8 @@ def main():
         x.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out, _, _, lb, rz = layer(x)
-        (out.float().pow(2).mean() + lb + rz).backward()
+        n = torch.linalg.vector_norm(out, 2, dtype=torch.float32)
+        (n * n / out.numel() + lb + rz).backward()
 
     for _ in range(5):
         step()
