@@ -317,6 +317,39 @@ def test_cuda_graph_replay_matches_eager(Dm):
             assert rel_err(v, eager_g[k]) < 1e-2, k
 
 
+def reference_bf16_floor(spec, sd, x, noise, want):
+    """The error the UNMODIFIED reference layer (baseline/_ref) makes on this GPU under bf16 autocast, on the same weights,
+    inputs and routing noise, against the fp32 gradients `want` (metric: tests.util.rel_err per tensor).  It is the noise
+    floor of a bf16 run of this shape: near-tied tokens re-route, sums over tokens cancel.  {} when the reference is absent."""
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return {}
+    core = ref_loader.load_core()
+    cfg = core.ApertisConfig(hidden_size=spec["Dm"], num_attention_heads=spec["H"], intermediate_size=spec["I"],
+                             num_hidden_layers=1, attention_type="selective_ssm", use_expert_system=True,
+                             num_experts=spec["E"], experts_per_token=spec["K"], vocab_size=64, hidden_dropout_prob=0.0,
+                             attention_probs_dropout_prob=0.0, hidden_act=spec.get("act", "gelu"))
+    ref = core.ApertisLayer(cfg)
+    missing, unexpected = ref.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    ref = ref.to(dev()).train()
+    nz = noise.to(dev())
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: nz.to(t.dtype) if tuple(t.shape) == tuple(nz.shape) else orig(t, *a, **k)
+    try:
+        xr = x.to(dev()).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out, _, _, lb, rz = ref(xr)
+        O.block_loss(out.float(), lb.float(), rz.float()).backward()
+    finally:
+        torch.randn_like = orig
+    torch.cuda.synchronize()
+    floor = {k: rel_err(p.grad, want[k]) for k, p in ref.named_parameters() if p.grad is not None and k in want}
+    del ref
+    torch.cuda.empty_cache()
+    return floor
+
+
 @pytest.mark.parametrize("name,Dm,H,I,B,L,autocast", [
     ("c2_full_fp32", 704, 11, 2816, 8, 4096, False),        # BASELINE.json configs[1] at the size bench.py times
     ("c2_full_bf16", 704, 11, 2816, 8, 4096, True),
@@ -378,9 +411,13 @@ def test_block_baseline_configs_vs_oracle(name, Dm, H, I, B, L, autocast):
         # a re-routed token also perturbs its neighbours' input gradients through the scan: bound the error in the L2 sense
         dg, dr = xg.grad.reshape(S, Dm).cpu().double(), xr.grad.reshape(S, Dm).double()
         assert float((dg - dr).norm() / dr.norm()) < 2e-2, "dx"
+    # bf16: parameter gradients are sums over all tokens in which re-routed tokens and cancellation show; the bound is 5e-2
+    # or twice what the unmodified reference's own bf16-autocast run on this GPU deviates from the same fp32 gradients
+    floor = reference_bf16_floor(spec, sd, x, noise, {k: v.grad for k, v in sdr.items()}) if autocast else {}
     bad = []
     for k, gr in named_grads(layer).items():
         e = rel_err(gr, sdr[k].grad)
-        if not e < (tol if not autocast else 5e-2):          # sums over all tokens: a handful of re-routed ones barely move them
-            bad.append((k, e))
-    assert not bad, bad
+        bound = tol if not autocast else max(5e-2, 2.0 * floor.get(k, 0.0))
+        if not e < bound:
+            bad.append((k, round(e, 4), floor.get(k)))
+    assert not bad, "(tensor, error, reference bf16 floor): " + "; ".join(map(str, bad))

@@ -200,21 +200,34 @@ def test_patched_model_under_gradient_checkpointing():
 
 def test_patched_model_fp16_autocast_with_grad_scaler():
     """The reference trainer's AMP mode (pipeline.py:482,533): fp16 autocast + GradScaler.  The drop-in computes in
-    bf16 / fp32 internally and returns what the fp16 callers expect."""
+    bf16 / fp32 internally (documented) and returns what the fp16 callers expect.  Its gradients are
+    therefore as accurate as a bf16 run, not as an fp16 run: they are checked against the reference's fp32 gradients with
+    the reference's own bf16-autocast deviation from them as the yardstick (x2, at least 8e-2: with 192 tokens a single
+    re-routed token moves an expert's gradient by several percent in either implementation), and the loss / logits
+    against the reference's fp16 run."""
     core, ref, mine = make_models(router_gain=6.0)
     ref.train(); mine.train()
     batch = text_batch()
     scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 12)
+    step(ref, batch)
+    g32 = {k: v.clone() for k, v in grads_by_reference_name(ref).items()}
+    step(ref, batch, autocast=torch.bfloat16)
+    floor = {k: l2_err(v, g32[k]) for k, v in grads_by_reference_name(ref).items() if float(g32[k].abs().max()) > 0}
     l_r, lg_r = step(ref, batch, autocast=torch.float16, scaler=scaler)
-    g_r = {k: v.clone() for k, v in grads_by_reference_name(ref).items()}
     l_m, lg_m = step(mine, batch, autocast=torch.float16, scaler=scaler)
     g_m = grads_by_reference_name(mine)
     assert torch.isfinite(l_m) and abs(float(l_r) - float(l_m)) <= 2e-2 * abs(float(l_r))
+    assert lg_m.dtype == lg_r.dtype
     assert l2_err(lg_m, lg_r) < 6e-2          # the drop-in computes in bf16 (8-bit mantissa) where the reference's autocast uses fp16 (11-bit)
-    for k in g_r:
+    inv = 1.0 / scaler.get_scale()
+    bad = []
+    for k in g32:
         assert torch.isfinite(g_m[k]).all(), k
-        if float(g_r[k].abs().max()) > 0:
-            assert l2_err(g_m[k], g_r[k]) < 0.12, k
+        if k in floor:
+            e = l2_err(g_m[k].float() * inv, g32[k])
+            if not e < max(8e-2, 2.0 * floor[k]):
+                bad.append((k, round(e, 4), round(floor[k], 4)))
+    assert not bad, "(tensor, error vs fp32, reference bf16 floor): " + "; ".join(map(str, bad))
     opt = torch.optim.AdamW(mine.parameters(), lr=1e-4)
     scaler.step(opt)          # unscale + inf check + step must work on the drop-in's gradients
     scaler.update()
