@@ -22,7 +22,7 @@ AB_F32, AB_BF16 = 0, 1
 ACT = {"gelu": 0, "relu": 1, "silu": 2, "swish": 2}
 EPI_NONE, EPI_BIAS, EPI_BIAS_ACT, EPI_DACT, EPI_ADD = 0, 1, 2, 3, 4
 SCAN_SINGLE_PASS, SCAN_TWO_PASS, SCAN_PIPELINED, SCAN_ROUNDS = 0, 1, 2, 3
-ROW_ALIGN = 128
+ROW_ALIGN = 256        # AB_GEMM_ROW_TILE: rows of one expert GEMM tile (a CTA pair, 128 rows per CTA)
 ROUTER_EXACT, ROUTER_BF16, ROUTER_FP16 = 0, 1, 2
 
 P, I, I64, SZ, F, U32 = c_void_p, c_int, c_int64, c_size_t, c_float, c_uint32
@@ -44,6 +44,7 @@ SIGNATURES = {
     "ab_ssm_scan_fwd": (I, [P, I64, P, I64, P, P, P, I64, P, I64, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, P]),
     "ab_ssm_scan_bwd": (I, [P, I64, P, P, I64, P, I64, P, P, P, P, P, P, I64, P, P, I64, P, I64, P, I64, I, P, P, P, P, SZ,
                             I, I, I, I, I, P]),
+    "ab_gemm_row_tile": (I, []),
     "ab_moe_router_workspace_bytes": (SZ, [I, I, I]),
     "ab_moe_router_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),
     "ab_moe_topk_from_logits": (I, [P, P, P, P, P, P, I, I, I, P]),

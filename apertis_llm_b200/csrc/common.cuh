@@ -232,6 +232,44 @@ __device__ __forceinline__ void ab_umma_f16(uint32_t tmem_d, uint64_t desc_a, ui
 __device__ __forceinline__ void ab_umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ab_smem_u32(bar)) : "memory");
 }
+// ---- thread-block clusters and CTA pairs (tcgen05 cta_group::2): the two CTAs of a pair run one 256-row MMA; only the
+//      even CTA (cluster rank 0, the "leader") issues it, both CTAs load operands and drain their half of the accumulator
+__device__ __forceinline__ uint32_t ab_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void ab_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void ab_mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(ab_smem_u32(bar)), "r"(cta) : "memory");
+}
+// TMA load issued by either CTA of a pair into its OWN shared memory; the bytes are counted on the LEADER's mbarrier
+// (the pair-rank bit of the barrier address is cleared)
+__device__ __forceinline__ void ab_tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(ab_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ab_smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void ab_tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ab_smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void ab_tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ab_tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs, 256 rows] (+)= A[128 rows from each CTA's smem] * B[N/2 columns from each CTA's smem]
+__device__ __forceinline__ void ab_umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `cta_mask` once all previously issued pair MMAs have completed
+__device__ __forceinline__ void ab_umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(ab_smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns of this warp's TMEM lane quarter
 __device__ __forceinline__ void ab_tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(

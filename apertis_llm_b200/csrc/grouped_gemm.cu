@@ -1,5 +1,5 @@
 // Grouped expert GEMM on 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
-// staged by TMA into 128B-swizzled shared memory, warp-specialised and persistent.
+// staged by TMA into 128B-swizzled shared memory, warp-specialised and persistent, on CTA PAIRS.
 // Replaces the per-(slot, expert) nn.Linear calls of core.py:596 (experts[e] = LN, Linear, act, Dropout,
 // Linear; core.py:434-442) and their autograd (dgrad / wgrad).
 //
@@ -7,40 +7,51 @@
 //   MODE_NN  C[r,n] = epi(sum_k A[r,k] * W[e,k,n])      A [rows,K] K-major,   W [E*K, N] N-major   (dgrad)
 //   MODE_TN  Cw[e,m,n] = sum_{r in seg e} A[r,m]*B[r,n] A [rows,M] M-major,   B [rows,N] N-major   (wgrad)
 //
-// Tile 128 x BN x 64 (BN <= 256 chosen per shape on the host and carried in the TMA maps / the
-// instruction descriptor), 4-stage TMA->MMA ring, 2 accumulator stages in TMEM (2 x 256 columns) so the
-// epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM
-// alloc), 2..17 = epilogue: four warps per TMEM lane quarter, each taking one 16-column chunk of a 64-column
-// group of the tile (tcgen05.ld -> bias / activation math in registers -> swizzled per-warp staging -> coalesced
-// 16-byte global stores; no CTA-wide synchronisation in the epilogue).
-// Row tiles (128 permuted rows) belong to one expert; the number of valid row tiles is read from device
-// memory (n_rows[0]) so no host synchronisation is needed after the routing plan.
+// The kernel runs as clusters of two CTAs (the two SMs of a TPC) and issues `tcgen05.mma.cta_group::2`: one MMA covers
+// 256 rows x BN columns x 16, rows 0..127 accumulate in the TMEM of the even CTA (the leader, which issues the MMAs),
+// rows 128..255 in the TMEM of the odd CTA.  Each CTA loads its own 128 rows of A and only HALF of the B tile (BN/2
+// columns); the tensor core reads both halves.  Against one-CTA 128 x BN tiles this cuts the operand bytes that travel
+// L2 -> shared memory per flop by a third at BN = 256 (the one-CTA kernel moved 14 TB/s of operands, r2a ncu capture).
+// Per CTA: BK = 64, 5-stage TMA -> MMA ring of (16 KB A + up to 16 KB B-half), 2 accumulator stages in TMEM (2 x 256
+// columns) so the epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles in each CTA: 0 = TMA producer, 1 = MMA
+// issuer (leader only; + TMEM alloc), 2..17 = epilogue: four warps per TMEM lane quarter, each owning one 64-column group
+// of the CTA's 128 x BN accumulator (tcgen05.ld -> bias / activation math in registers -> swizzled per-warp staging ->
+// coalesced 16-byte global stores; no CTA-wide synchronisation in the epilogue).  Barriers: `full` lives in the leader and
+// counts the TMA bytes of both CTAs; `empty` and `tfull` exist in both CTAs and are signalled by multicast
+// tcgen05.commit; `tempty` lives in the leader and is arrived on by the epilogue warps of both CTAs.
+// Row tiles (256 permuted rows) belong to one expert; the number of valid rows is read from device memory (n_rows[0])
+// so no host synchronisation is needed after the routing plan.
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BK = 64, NSTAGE = 4, NACC = 2;
+constexpr int BM = 128;                       // accumulator rows per CTA (TMEM lanes)
+constexpr int PM = 2 * BM;                    // rows of a pair tile (AB_GEMM_ROW_TILE)
+constexpr int BK = 64, NSTAGE = 5, NACC = 2;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES_MAX = 256 * BK * 2;     // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int BH_BYTES_MAX = 128 * BK * 2;    // 16 KB: this CTA's half of a 256-column B tile
+constexpr int STAGE_BYTES = A_BYTES + BH_BYTES_MAX;
 constexpr int ATOM_BYTES = 64 * BK * 2;       // one 64(MN) x 64(K) swizzle-128B MN-major atom = 8 KB
 constexpr int EPI_WARP0 = 2, EPI_WARPS = 16, EPI_THREADS = EPI_WARPS * 32;
 constexpr int NUM_THREADS = 64 + EPI_THREADS; // warp 0 TMA, warp 1 MMA, 16 epilogue warps
-constexpr int GW = 64;                        // epilogue column group: 4 chunks of 16, one per warp of a TMEM lane quarter
+constexpr int GW = 64;                        // epilogue column group: one per warp of a TMEM lane quarter
 constexpr int MODE_NT = 0, MODE_NN = 1, MODE_TN = 2;
-constexpr int WARP_STG_BYTES = 32 * 64;        // per-warp epilogue staging: 32 rows x 64 B
-constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + (size_t)EPI_WARPS * WARP_STG_BYTES + 256;
+constexpr int WARP_STG_BYTES = 32 * 64;       // per-warp epilogue staging: 32 rows x 64 B
+constexpr int WARP_BIAS_BYTES = GW * 4;       // per-warp bias slice of the current tile
+constexpr size_t SMEM_BYTES = 1024 + (size_t)NSTAGE * STAGE_BYTES + (size_t)EPI_WARPS * (WARP_STG_BYTES + WARP_BIAS_BYTES) + 256;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(PM == AB_GEMM_ROW_TILE, "row tile of the ABI");
 
 struct GemmParams {
     int N, K, E, M;          // M only for MODE_TN (rows of each expert's output)
-    int bn;                  // N tile
-    int num_n_tiles, num_m_tiles;
+    int bn;                  // N tile (both CTAs together)
+    int num_n_tiles, num_m_tiles;   // num_m_tiles: MODE_TN, 256-row tiles of the output
     int epi, act, c_f32;
     int tn_nsrc;             // MODE_TN: an expert's rows are nsrc blocks [src*stride + seg_off[e], src*stride + seg_off[e+1])
     int64_t tn_src_stride;
     // dense use (one "expert", plain row-major matrices; tile_expert / n_rows / seg_off are NULL):
     int64_t rows_valid;      // MODE_NT / MODE_NN: rows >= rows_valid are never stored (the last row tile may be partial)
-    int dense_m_tiles;       // MODE_NT / MODE_NN: number of row tiles when n_rows is NULL
+    int dense_m_tiles;       // MODE_NT / MODE_NN: number of 256-row tiles when n_rows is NULL
     int64_t tn_rows;         // MODE_TN with seg_off NULL: contraction over rows [0, tn_rows), TMA zero-fills past the end
     int64_t tn_split;        // ... cut into E slices of tn_split rows (a multiple of BK): Cw[e] holds slice e's partial product
     const int32_t* tile_expert;
@@ -203,7 +214,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)2 << 61;          // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: bf16 x bf16 -> f32, M = 128
+// instruction descriptor: bf16 x bf16 -> f32, M = 256 (cta_group::2: 128 rows per CTA)
 __host__ __device__ inline uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
     uint32_t d = 0;
     d |= 1u << 4;                    // D format f32
@@ -212,20 +223,49 @@ __host__ __device__ inline uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
     d |= (uint32_t)a_mn_major << 15;
     d |= (uint32_t)b_mn_major << 16;
     d |= (uint32_t)(n >> 3) << 17;
-    d |= (uint32_t)(BM >> 4) << 24;
+    d |= (uint32_t)(PM >> 4) << 24;
     return d;
+}
+
+// ---- tile schedule (identical in every role of both CTAs of a pair) -------------------------------
+struct Tile { int m_pair, n_tile, e, k_begin, nk; };
+
+template <int MODE>
+__device__ __forceinline__ int total_tiles_of(const GemmParams& p) {
+    if (MODE == MODE_TN) return p.E * p.num_m_tiles * p.num_n_tiles;
+    return (p.n_rows != nullptr ? p.n_rows[0] / PM : p.dense_m_tiles) * p.num_n_tiles;
+}
+template <int MODE>
+__device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
+    Tile t;
+    if (MODE == MODE_TN) {
+        const int per_e = p.num_m_tiles * p.num_n_tiles;
+        t.e = tile / per_e;
+        const int rem = tile % per_e;
+        t.m_pair = rem / p.num_n_tiles; t.n_tile = rem % p.num_n_tiles;
+        t.k_begin = p.seg_off != nullptr ? p.seg_off[t.e] : (int)(t.e * p.tn_split);
+        t.nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[t.e + 1] - t.k_begin) / BK) : dense_tn_blocks(p, t.e);
+    } else {
+        t.m_pair = tile / p.num_n_tiles; t.n_tile = tile % p.num_n_tiles;
+        t.e = p.tile_expert != nullptr ? p.tile_expert[t.m_pair] : 0;
+        t.k_begin = 0;
+        t.nk = (p.K + BK - 1) / BK;
+    }
+    return t;
 }
 
 // ---- epilogue -----------------------------------------------------------------------------------
 // One warp owns 32 accumulator rows (its TMEM lane quarter) x one 64-column group and walks it in units of 64 output
 // bytes per row (32 bf16 or 16 f32 columns): tcgen05.ld -> math -> swizzled per-warp staging -> coalesced 16-byte
 // global stores (8 rows x 64 B per instruction).  No CTA-wide synchronisation; everything is compile-time indexed so the
-// fragments stay in registers.
+// fragments stay in registers.  Operands the math needs from global memory never sit on the critical path: the tile's bias
+// slice is parked in shared memory before the accumulator is waited for, and the saved pre-activation / addend tile of the
+// DACT / ADD epilogues is fetched one unit ahead into registers.
 __device__ __forceinline__ uint32_t stg_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
 template <int MODE, bool F32>
 __device__ __forceinline__ void stage_and_store(const GemmParams& p, unsigned char* stg, const float (&src)[F32 ? 16 : 32],
-                                                unsigned char* base, int lane, int quarter, int m_tile, int ncol, int ncol_end) {
+                                                unsigned char* base, int lane, size_t row0, int ncol, int ncol_end) {
     constexpr int ES = F32 ? 4 : 2;
     constexpr int CPV = 16 / ES;
     const int N = p.N;
@@ -241,7 +281,7 @@ __device__ __forceinline__ void stage_and_store(const GemmParams& p, unsigned ch
     for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2), j = lane & 3;
         const int col = ncol + j * CPV;
-        const size_t grow = (size_t)m_tile * BM + quarter * 32 + r;
+        const size_t grow = row0 + r;
         const bool ok = col < ncol_end && (MODE == MODE_TN ? (int)grow < p.M : (int64_t)grow < p.rows_valid);
         const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(r, j));
         if (ok) *reinterpret_cast<uint4*>(base + (grow * N + col) * ES) = q;
@@ -249,114 +289,161 @@ __device__ __forceinline__ void stage_and_store(const GemmParams& p, unsigned ch
     __syncwarp();
 }
 
-template <int MODE, bool F32>
-__device__ __forceinline__ void epilogue_group(const GemmParams& p, unsigned char* stg, uint32_t t_row, bool have_acc, int lane,
-                                               int quarter, int m_tile, int e, int n0, int g_col0, int g_cols) {
+// 32 rows x 64 B of a row-major [rows, N] tensor (aux), coalesced: 8 rows x 64 B per instruction
+template <bool F32>
+__device__ __forceinline__ void load_aux_unit(const GemmParams& p, uint4 (&q)[4], int lane, size_t row0, int ncol, int ncol_end) {
+    constexpr int ES = F32 ? 4 : 2;
+    constexpr int CPV = 16 / ES;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), j = lane & 3;
+        const int col = ncol + j * CPV;
+        const size_t grow = row0 + r;
+        q[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (col < ncol_end && (int64_t)grow < p.rows_valid)
+            q[it] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.aux) + (grow * p.N + col) * ES));
+    }
+}
+
+struct EpiCtx {
+    unsigned char* stg;      // this warp's staging
+    float* bias_s;           // this warp's bias slice
+    uint64_t* tfull;
+    uint64_t* tempty;
+    uint32_t tmem_base;
+    int warp, lane;
+    uint32_t rank;
+    int pair_id, num_pairs;
+};
+
+template <int MODE, bool F32, int EPI>
+__device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx& c) {
     constexpr int U = F32 ? 16 : 32;            // columns per unit
     constexpr int ES = F32 ? 4 : 2;
     constexpr int CPV = 16 / ES;                // columns per 16-byte vector
-    const int N = p.N;
-    const int ncol_end = min(N, n0 + g_col0 + g_cols);    // columns past the tile (or the matrix) are never touched
-    for (int u0 = 0; u0 < g_cols; u0 += U) {
-        const int tcol = g_col0 + u0;           // column inside the tile
-        const int ncol = n0 + tcol;             // global column
-        if (ncol >= ncol_end) break;
-        float f[U];
-        {
-            uint32_t v[U];
-            if (have_acc) {
-                ab_tmem_ld16(t_row + (uint32_t)tcol, v);
-                if (U == 32) ab_tmem_ld16(t_row + (uint32_t)tcol + 16u, v + 16);
-                ab_tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int i = 0; i < U; ++i) v[i] = 0u;
-            }
-#pragma unroll
-            for (int i = 0; i < U; ++i) f[i] = __uint_as_float(v[i]);
+    constexpr bool HAS_BIAS = EPI == AB_EPI_BIAS || EPI == AB_EPI_BIAS_ACT;
+    constexpr bool HAS_AUX = EPI == AB_EPI_DACT || EPI == AB_EPI_ADD;
+    const int lane = c.lane;
+    const int quarter = c.warp & 3;                 // TMEM lane quarter this warp may read
+    const int sub = (c.warp - EPI_WARP0) >> 2;      // which 64-column group of the tile this warp owns
+    const int N = p.N, bn = p.bn;
+    const int g_col0 = sub * GW;
+    const int g_cols = g_col0 < bn ? min(GW, bn - g_col0) : 0;
+    const int total_tiles = total_tiles_of<MODE>(p);
+    unsigned char* stg = c.stg;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = c.pair_id; tile < total_tiles; tile += c.num_pairs) {
+        const Tile t = decode_tile<MODE>(p, tile);
+        const int m_tile = 2 * t.m_pair + (int)c.rank;          // this CTA's 128 rows of the pair tile
+        const bool have_acc = t.nk > 0;
+        const int n0 = t.n_tile * bn;
+        const int ncol_end = min(N, n0 + g_col0 + g_cols);      // columns past the tile (or the matrix) are never touched
+        const size_t row0 = (size_t)m_tile * BM + quarter * 32;
+        if (HAS_BIAS && g_cols > 0) {
+            const int col = n0 + g_col0 + 2 * lane;
+            float2 b2 = make_float2(0.f, 0.f);
+            if (col < ncol_end) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + (size_t)t.e * N + col));
+            *reinterpret_cast<float2*>(c.bias_s + 2 * lane) = b2;
+            __syncwarp();
         }
-        if (MODE != MODE_TN) {
-            if (p.epi == AB_EPI_BIAS || p.epi == AB_EPI_BIAS_ACT) {
-                const float* bp = p.bias + (size_t)e * N + ncol;
+        uint4 nxt[4];
+        if (HAS_AUX && g_cols > 0 && n0 + g_col0 < ncol_end) load_aux_unit<F32>(p, nxt, lane, row0, n0 + g_col0, ncol_end);
+        if (have_acc) {
+            ab_mbar_wait(&c.tfull[acc], acc_phase);
+            ab_tc_fence_after();
+        }
+        const uint32_t t_row = c.tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
+        for (int u0 = 0; u0 < g_cols; u0 += U) {
+            const int tcol = g_col0 + u0;           // column inside the tile
+            const int ncol = n0 + tcol;             // global column
+            if (ncol >= ncol_end) break;
+            uint4 cur[4];
+            if (HAS_AUX) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
+                if (u0 + U < g_cols && ncol + U < ncol_end) load_aux_unit<F32>(p, nxt, lane, row0, ncol + U, ncol_end);
+            }
+            float f[U];
+            {
+                uint32_t v[U];
+                if (have_acc) {
+                    if (U == 32) ab_tmem_ld32(t_row + (uint32_t)tcol, v);
+                    else ab_tmem_ld16(t_row + (uint32_t)tcol, v);
+                    ab_tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < U; ++i) v[i] = 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < U; ++i) f[i] = __uint_as_float(v[i]);
+            }
+            if (HAS_BIAS) {
 #pragma unroll
                 for (int i = 0; i < U; i += 4) {
-                    if (ncol + i < ncol_end) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-                        f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-                    }
+                    const float4 b4 = *reinterpret_cast<const float4*>(c.bias_s + u0 + i);      // zeros past the last column
+                    f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
                 }
             }
-            if (p.epi == AB_EPI_BIAS_ACT) {
+            if (EPI == AB_EPI_BIAS_ACT) {
                 // the pre-activation (the Linear output, rounded to the activation dtype first) goes out before the
                 // activation is applied in place, so only one fragment is live
                 if (!F32) round_row_bf16<U>(f);
-                stage_and_store<MODE, F32>(p, stg, f, reinterpret_cast<unsigned char*>(p.c2), lane, quarter, m_tile, ncol, ncol_end);
+                stage_and_store<MODE, F32>(p, stg, f, reinterpret_cast<unsigned char*>(p.c2), lane, row0, ncol, ncol_end);
                 act_fwd_row<U>(f, p.act);
-                if (p.drop_seed) dropout_row<U>(f, p, (uint32_t)(m_tile * BM + quarter * 32 + lane), ncol);
-            } else if (p.epi == AB_EPI_ADD) {
-                // C = acc + aux (aux has C's shape and dtype): accumulate a second gradient contribution in the epilogue
-                __syncwarp();
+                if (p.drop_seed) dropout_row<U>(f, p, (uint32_t)row0 + (uint32_t)lane, ncol);
+            } else if (HAS_AUX) {
+                // the prefetched tile goes through the staging so that each thread reads its own row
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int r = it * 8 + (lane >> 2), j = lane & 3;
-                    const int col = ncol + j * CPV;
-                    const int64_t grow = (int64_t)m_tile * BM + quarter * 32 + r;
-                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                    if (col < ncol_end && grow < p.rows_valid)
-                        q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.aux) + ((size_t)grow * N + col) * ES));
-                    *reinterpret_cast<uint4*>(stg + stg_off(r, j)) = q;
-                }
+                for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(stg + stg_off(it * 8 + (lane >> 2), lane & 3)) = cur[it];
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
-                    float add[CPV];
-                    if (F32) { add[0] = __uint_as_float(q.x); add[1] = __uint_as_float(q.y); add[2] = __uint_as_float(q.z); add[3] = __uint_as_float(q.w); }
-                    else ab_vec16<__nv_bfloat16>::unpack(q, add);
+                    float a[CPV];
+                    if (F32) { a[0] = __uint_as_float(q.x); a[1] = __uint_as_float(q.y); a[2] = __uint_as_float(q.z); a[3] = __uint_as_float(q.w); }
+                    else ab_vec16<__nv_bfloat16>::unpack(q, a);
+                    if (EPI == AB_EPI_ADD) {
+                        // C = acc + aux (aux has C's shape and dtype): a second gradient contribution accumulated here
 #pragma unroll
-                    for (int i = 0; i < CPV; ++i) f[j * CPV + i] += add[i];
-                }
-                __syncwarp();
-            } else if (p.epi == AB_EPI_DACT) {
-                // saved pre-activation tile: coalesced 16-byte loads -> staging -> each thread reads its own row
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int r = it * 8 + (lane >> 2), j = lane & 3;
-                    const int col = ncol + j * CPV;
-                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                    if (col < ncol_end)
-                        q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.aux) +
-                                                                 (((size_t)m_tile * BM + quarter * 32 + r) * N + col) * ES));
-                    *reinterpret_cast<uint4*>(stg + stg_off(r, j)) = q;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
-                    float pre[CPV];
-                    if (F32) { pre[0] = __uint_as_float(q.x); pre[1] = __uint_as_float(q.y); pre[2] = __uint_as_float(q.z); pre[3] = __uint_as_float(q.w); }
-                    else ab_vec16<__nv_bfloat16>::unpack(q, pre);
-                    if (p.act == AB_ACT_GELU) {
+                        for (int i = 0; i < CPV; ++i) f[j * CPV + i] += a[i];
+                    } else if (p.act == AB_ACT_GELU) {
 #pragma unroll
                         for (int i = 0; i < CPV; i += 2) {
-                            const f2 d = f2_mul(f2_pack(f[j * CPV + i], f[j * CPV + i + 1]), gelu_bwd2(f2_pack(pre[i], pre[i + 1])));
+                            const f2 d = f2_mul(f2_pack(f[j * CPV + i], f[j * CPV + i + 1]), gelu_bwd2(f2_pack(a[i], a[i + 1])));
                             f2_unpack(d, f[j * CPV + i], f[j * CPV + i + 1]);
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(pre[i], p.act);
+                        for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(a[i], p.act);
                     }
                 }
                 __syncwarp();
-                if (p.drop_seed) dropout_row<U>(f, p, (uint32_t)(m_tile * BM + quarter * 32 + lane), ncol);
+                if (EPI == AB_EPI_DACT && p.drop_seed) dropout_row<U>(f, p, (uint32_t)row0 + (uint32_t)lane, ncol);
             }
+            // ---- stage this thread's row, then store 8 rows x 64 B per instruction
+            unsigned char* base;
+            if (MODE == MODE_TN) base = reinterpret_cast<unsigned char*>(p.cw) + ((size_t)t.e * p.M) * N * 4;
+            else base = reinterpret_cast<unsigned char*>(p.c);
+            stage_and_store<MODE, F32>(p, stg, f, base, lane, row0, ncol, ncol_end);
         }
-        // ---- stage this thread's row, then store 8 rows x 64 B per instruction
-        unsigned char* base;
-        if (MODE == MODE_TN) base = reinterpret_cast<unsigned char*>(p.cw) + ((size_t)e * p.M) * N * 4;
-        else base = reinterpret_cast<unsigned char*>(p.c);
-        stage_and_store<MODE, F32>(p, stg, f, base, lane, quarter, m_tile, ncol, ncol_end);
+        if (have_acc) {
+            ab_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ab_mbar_arrive_cluster(&c.tempty[acc], 0);     // all of this warp's TMEM reads of the tile are done
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+}
+
+template <int MODE, bool F32>
+__device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, const EpiCtx& c) {
+    if (MODE == MODE_TN) { epilogue_role<MODE, F32, AB_EPI_NONE>(p, c); return; }
+    switch (p.epi) {
+        case AB_EPI_BIAS: epilogue_role<MODE, F32, AB_EPI_BIAS>(p, c); break;
+        case AB_EPI_BIAS_ACT: epilogue_role<MODE, F32, AB_EPI_BIAS_ACT>(p, c); break;
+        case AB_EPI_DACT: epilogue_role<MODE, F32, AB_EPI_DACT>(p, c); break;
+        case AB_EPI_ADD: epilogue_role<MODE, F32, AB_EPI_ADD>(p, c); break;
+        default: epilogue_role<MODE, F32, AB_EPI_NONE>(p, c); break;
     }
 }
 
@@ -368,100 +455,89 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
     const uint32_t raw = ab_smem_u32(smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);      // swizzle-128B atoms need 1024 B alignment
     unsigned char* stg_base = smem + (size_t)NSTAGE * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (size_t)EPI_WARPS * WARP_STG_BYTES);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + NSTAGE;
-    uint64_t* tfull = bars + 2 * NSTAGE;
-    uint64_t* tempty = bars + 2 * NSTAGE + NACC;
+    float* bias_base = reinterpret_cast<float*>(stg_base + (size_t)EPI_WARPS * WARP_STG_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bias_base) + (size_t)EPI_WARPS * WARP_BIAS_BYTES);
+    uint64_t* full = bars;                       // leader's: TMA bytes of both CTAs
+    uint64_t* empty = bars + NSTAGE;             // each CTA's own: multicast commit of the MMAs that read the slot
+    uint64_t* tfull = bars + 2 * NSTAGE;         // each CTA's own: multicast commit of the tile's last MMA
+    uint64_t* tempty = bars + 2 * NSTAGE + NACC; // leader's: epilogue warps of both CTAs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ab_cluster_ctarank();          // 0 = leader
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     if (warp == 0 && lane == 0) {
         ab_prefetch_tmap(&tm_a);
         ab_prefetch_tmap(&tm_b);
         for (int i = 0; i < NSTAGE; ++i) { ab_mbar_init(&full[i], 1); ab_mbar_init(&empty[i], 1); }
-        for (int i = 0; i < NACC; ++i) { ab_mbar_init(&tfull[i], 1); ab_mbar_init(&tempty[i], EPI_WARPS); }
+        for (int i = 0; i < NACC; ++i) { ab_mbar_init(&tfull[i], 1); ab_mbar_init(&tempty[i], 2 * EPI_WARPS); }
         ab_fence_mbar_init();
     }
     if (warp == 1) {
-        ab_tmem_alloc(tmem_slot, 512);
-        ab_tmem_relinquish();
+        ab_tmem_alloc_pair(tmem_slot, 512);
+        ab_tmem_relinquish_pair();
     }
     ab_tc_fence_before();
-    __syncthreads();
+    ab_cluster_sync();           // both CTAs' barriers are initialised before any remote arrive / multicast commit
     ab_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- tile schedule (identical in every role)
-    int total_tiles;
-    if (MODE == MODE_TN) total_tiles = p.E * p.num_m_tiles * p.num_n_tiles;
-    else total_tiles = (p.n_rows != nullptr ? p.n_rows[0] / BM : p.dense_m_tiles) * p.num_n_tiles;
-    const int bn = p.bn;
-    const uint32_t b_bytes = MODE == MODE_NT ? (uint32_t)bn * BK * 2 : (uint32_t)(bn / 64) * ATOM_BYTES;
-    const uint32_t stage_tx = A_BYTES + b_bytes;
+    const int total_tiles = total_tiles_of<MODE>(p);
+    const int bn = p.bn, bh = bn >> 1;          // this CTA stages bh columns of B
+    const uint32_t bh_bytes = MODE == MODE_NT ? (uint32_t)bh * BK * 2 : (uint32_t)(bh / 64) * ATOM_BYTES;
+    const uint32_t pair_tx = 2u * (A_BYTES + bh_bytes);
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (both CTAs: own A rows, own half of B) =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int m_tile, n_tile, e, k_begin, nk;
-                if (MODE == MODE_TN) {
-                    e = tile / (p.num_m_tiles * p.num_n_tiles);
-                    const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
-                    m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                    k_begin = p.seg_off != nullptr ? p.seg_off[e] : (int)(e * p.tn_split);
-                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - k_begin) / BK) : dense_tn_blocks(p, e);
-                } else {
-                    m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
-                    e = p.tile_expert != nullptr ? p.tile_expert[m_tile] : 0;
-                    k_begin = 0;
-                    nk = (p.K + BK - 1) / BK;
-                }
-                for (int kb = 0; kb < nk; ++kb) {
+            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+                const Tile t = decode_tile<MODE>(p, tile);
+                const int b_col0 = t.n_tile * bn + (int)rank * bh;
+                for (int kb = 0; kb < t.nk; ++kb) {
                     ab_mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sa = smem + (size_t)stage * STAGE_BYTES;
                     unsigned char* sb = sa + A_BYTES;
-                    ab_mbar_expect_tx(&full[stage], stage_tx);
+                    if (rank == 0) ab_mbar_expect_tx(&full[stage], pair_tx);
                     if (MODE == MODE_TN) {
-                        const int per_src = nk / p.tn_nsrc;
-                        const int r0 = (int)((kb / per_src) * p.tn_src_stride) + k_begin + (kb % per_src) * BK;
-                        ab_tma_load_2d(sa, &tm_a, &full[stage], m_tile * BM, r0);
-                        ab_tma_load_2d(sa + ATOM_BYTES, &tm_a, &full[stage], m_tile * BM + 64, r0);
-                        for (int j = 0; j < bn / 64; ++j)
-                            ab_tma_load_2d(sb + j * ATOM_BYTES, &tm_b, &full[stage], n_tile * bn + j * 64, r0);
+                        const int per_src = t.nk / p.tn_nsrc;
+                        const int r0 = (int)((kb / per_src) * p.tn_src_stride) + t.k_begin + (kb % per_src) * BK;
+                        const int m0 = t.m_pair * PM + (int)rank * BM;
+                        ab_tma_load_2d_pair(sa, &tm_a, &full[stage], m0, r0);
+                        ab_tma_load_2d_pair(sa + ATOM_BYTES, &tm_a, &full[stage], m0 + 64, r0);
+                        for (int j = 0; j < bh / 64; ++j)
+                            ab_tma_load_2d_pair(sb + j * ATOM_BYTES, &tm_b, &full[stage], b_col0 + j * 64, r0);
                     } else {
-                        ab_tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_tile * BM);
+                        ab_tma_load_2d_pair(sa, &tm_a, &full[stage], kb * BK, (2 * t.m_pair + (int)rank) * BM);
                         if (MODE == MODE_NT) {
-                            ab_tma_load_2d(sb, &tm_b, &full[stage], kb * BK, e * p.N + n_tile * bn);
+                            ab_tma_load_2d_pair(sb, &tm_b, &full[stage], kb * BK, t.e * p.N + b_col0);
                         } else {
-                            for (int j = 0; j < bn / 64; ++j)
-                                ab_tma_load_2d(sb + j * ATOM_BYTES, &tm_b, &full[stage], n_tile * bn + j * 64, e * p.K + kb * BK);
+                            for (int j = 0; j < bh / 64; ++j)
+                                ab_tma_load_2d_pair(sb + j * ATOM_BYTES, &tm_b, &full[stage], b_col0 + j * 64, t.e * p.K + kb * BK);
                         }
                     }
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
+            // drain: every slot this CTA filled has been released, i.e. no multicast arrival is still on its way here
+            for (int i = 0; i < NSTAGE; ++i) {
+                ab_mbar_wait(&empty[stage], phase ^ 1);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0 && lane == 0) {
             const uint32_t idesc = make_idesc(bn, MODE == MODE_TN ? 1 : 0, MODE == MODE_NT ? 0 : 1);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int nk;
-                if (MODE == MODE_TN) {
-                    const int e = tile / (p.num_m_tiles * p.num_n_tiles);
-                    nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : dense_tn_blocks(p, e);
-                    if (nk == 0) continue;          // empty expert: the epilogue writes zeros without an accumulator
-                } else {
-                    nk = (p.K + BK - 1) / BK;
-                }
+            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+                const Tile t = decode_tile<MODE>(p, tile);
+                if (t.nk == 0) continue;            // empty expert (MODE_TN): the epilogue writes zeros without an accumulator
                 ab_mbar_wait(&tempty[acc], acc_phase ^ 1);
                 ab_tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-                for (int kb = 0; kb < nk; ++kb) {
+                for (int kb = 0; kb < t.nk; ++kb) {
                     ab_mbar_wait(&full[stage], phase);
                     ab_tc_fence_after();
                     const uint32_t sa = ab_smem_u32(smem + (size_t)stage * STAGE_BYTES);
@@ -473,59 +549,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                     const uint32_t b_step = MODE == MODE_NT ? 32 >> 4 : (16 * 128) >> 4;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        ab_umma_f16(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    ab_umma_commit(&empty[stage]);              // smem slot free once these MMAs retire
-                    if (kb == nk - 1) ab_umma_commit(&tfull[acc]);
+                        ab_umma_f16_pair(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    ab_umma_commit_pair(&empty[stage], 3);              // the slot is free in both CTAs once these MMAs retire
+                    if (kb == t.nk - 1) ab_umma_commit_pair(&tfull[acc], 3);
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ================= epilogue =================
-        const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-        const int sub = (warp - EPI_WARP0) >> 2;      // which 64-column group of the tile this warp owns
-        unsigned char* stg = stg_base + (size_t)(warp - EPI_WARP0) * WARP_STG_BYTES;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int m_tile, n_tile, e, nk;
-            if (MODE == MODE_TN) {
-                e = tile / (p.num_m_tiles * p.num_n_tiles);
-                const int rem = tile % (p.num_m_tiles * p.num_n_tiles);
-                m_tile = rem / p.num_n_tiles; n_tile = rem % p.num_n_tiles;
-                nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[e + 1] - p.seg_off[e]) / BK) : dense_tn_blocks(p, e);
-            } else {
-                m_tile = tile / p.num_n_tiles; n_tile = tile % p.num_n_tiles;
-                e = p.tile_expert != nullptr ? p.tile_expert[m_tile] : 0;
-                nk = 1;
-            }
-            const bool have_acc = nk > 0;
-            if (have_acc) {
-                ab_mbar_wait(&tfull[acc], acc_phase);
-                ab_tc_fence_after();
-            }
-            const uint32_t t_row = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(quarter * 32) << 16);
-            const int g_col0 = sub * GW;
-            if (g_col0 < bn) {
-                const int g_cols = min(GW, bn - g_col0);
-                if (p.c_f32) epilogue_group<MODE, true>(p, stg, t_row, have_acc, lane, quarter, m_tile, e, n_tile * bn, g_col0, g_cols);
-                else epilogue_group<MODE, false>(p, stg, t_row, have_acc, lane, quarter, m_tile, e, n_tile * bn, g_col0, g_cols);
-            }
-            if (have_acc) {
-                ab_tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ab_mbar_arrive(&tempty[acc]);       // all of this warp's TMEM reads of the tile are done
-                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-            }
-        }
+        // ================= epilogue (both CTAs: own 128 rows of the accumulator) =================
+        EpiCtx c;
+        c.stg = stg_base + (size_t)(warp - EPI_WARP0) * WARP_STG_BYTES;
+        c.bias_s = bias_base + (size_t)(warp - EPI_WARP0) * GW;
+        c.tfull = tfull; c.tempty = tempty; c.tmem_base = tmem_base;
+        c.warp = warp; c.lane = lane; c.rank = rank; c.pair_id = pair_id; c.num_pairs = num_pairs;
+        if (p.c_f32) epilogue_dispatch<MODE, true>(p, c);
+        else epilogue_dispatch<MODE, false>(p, c);
     }
     ab_tc_fence_before();
-    __syncthreads();
-    if (warp == 1) ab_tmem_dealloc(tmem_base, 512);
+    ab_cluster_sync();           // neither CTA leaves (or frees tensor memory) while its partner may still signal it
+    if (warp == 1) ab_tmem_dealloc_pair(tmem_base, 512);
 }
 
 int pick_bn(int N, bool mn_major_b) {
-    const int step = mn_major_b ? 64 : 16;
+    // each CTA of the pair stages bn/2 columns: 8-row groups (K-major B) or whole 64-column atoms (MN-major B)
+    const int step = mn_major_b ? 128 : 16;
     int best = step, best_cost = 1 << 30;
     for (int bn = step; bn <= 256; bn += step) {
         const int cost = (int)ab_ceil_div(N, bn) * (bn + 48);
@@ -544,15 +593,50 @@ int make_map2(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, 
     return ab_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// CTA pairs that can be resident at once (one per TPC when every TPC is whole); queried once per kernel and device
 template <int MODE>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int64_t max_tiles, cudaStream_t stream) {
+int resident_pairs(int* out) {
+    static int cached[64] = {0};
+    int dev = 0;
+    AB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) { *out = cached[dev]; return AB_OK; }
     auto k = grouped_gemm_kernel<MODE>;
     AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    int64_t grid = ab_num_sms();
-    if (max_tiles < grid) grid = max_tiles;
-    if (grid < 1) grid = 1;
-    k<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
-    AB_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (unsigned)(ab_num_sms() / 2), 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    AB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, k, &cfg));
+    if (n < 1) n = 1;
+    if (n > ab_num_sms() / 2) n = ab_num_sms() / 2;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    *out = n;
+    return AB_OK;
+}
+
+template <int MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int64_t max_tiles, cudaStream_t stream) {
+    int pairs = 0;
+    if (int e = resident_pairs<MODE>(&pairs)) return e;
+    if (max_tiles < pairs) pairs = (int)max_tiles;
+    if (pairs < 1) pairs = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (unsigned)pairs, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    AB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, grouped_gemm_kernel<MODE>, ta, tb, p));
     return AB_OK;
 }
 
@@ -562,13 +646,14 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "grouped_gemm: dropout probability must be in [0, 1)");
     AB_REQUIRE(drop_p == 0.f || (drop_seed != nullptr && (epi == AB_EPI_BIAS_ACT || epi == AB_EPI_DACT)),
                "grouped_gemm: dropout needs a seed and the bias+act / dact epilogue");
-    AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm: max_rows must be a positive multiple of %d", BM);
+    AB_REQUIRE(max_rows > 0 && max_rows % PM == 0, "grouped_gemm: max_rows must be a positive multiple of %d", PM);
     AB_REQUIRE(N > 0 && K > 0 && E > 0 && N % 8 == 0 && K % 8 == 0, "grouped_gemm: N (%d) and K (%d) must be multiples of 8", N, K);
     AB_REQUIRE(c_dtype == AB_F32 || c_dtype == AB_BF16, "grouped_gemm: bad output dtype");
     AB_REQUIRE(epi >= AB_EPI_NONE && epi <= AB_EPI_ADD, "grouped_gemm: bad epilogue %d", epi);
     AB_REQUIRE((epi != AB_EPI_BIAS && epi != AB_EPI_BIAS_ACT) || bias, "grouped_gemm: bias epilogue without bias");
     AB_REQUIRE(epi != AB_EPI_BIAS_ACT || c2, "grouped_gemm: bias+act epilogue needs the pre-activation output c2");
     AB_REQUIRE((epi != AB_EPI_DACT && epi != AB_EPI_ADD) || aux, "grouped_gemm: dact / add epilogue needs aux");
+    AB_REQUIRE(bias == nullptr || ((uintptr_t)bias % 8) == 0, "grouped_gemm: bias must be 8-byte aligned");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.K = K; p.E = E;
@@ -586,9 +671,9 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
                "grouped_gemm: output / aux pointers must be 16-byte aligned");
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)K, (uint64_t)max_rows, BK, BM)) return e;
-    const int64_t max_tiles = (max_rows / BM) * p.num_n_tiles;
+    const int64_t max_tiles = (max_rows / PM) * p.num_n_tiles;
     if (mode == MODE_NT) {
-        if (int e = make_map2(&tb, W, (uint64_t)K, (uint64_t)E * N, BK, (uint32_t)p.bn)) return e;
+        if (int e = make_map2(&tb, W, (uint64_t)K, (uint64_t)E * N, BK, (uint32_t)(p.bn / 2))) return e;
         return launch<MODE_NT>(ta, tb, p, max_tiles, stream);
     }
     if (int e = make_map2(&tb, W, (uint64_t)N, (uint64_t)E * K, 64, BK)) return e;
@@ -596,6 +681,8 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
 }
 
 }  // namespace
+
+extern "C" int ab_gemm_row_tile(void) { return PM; }
 
 extern "C" int ab_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                                   const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
@@ -613,14 +700,14 @@ extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, cons
                                   int N, int E, int nsrc, int64_t src_stride, cudaStream_t stream) {
     AB_REQUIRE(nsrc >= 1 && (nsrc == 1 || (src_stride > 0 && src_stride % BK == 0 && nsrc * src_stride <= max_rows)),
                "grouped_gemm_tn: bad source blocking nsrc=%d stride=%lld", nsrc, (long long)src_stride);
-    AB_REQUIRE(max_rows > 0 && max_rows % BM == 0, "grouped_gemm_tn: max_rows must be a positive multiple of %d", BM);
+    AB_REQUIRE(max_rows > 0 && max_rows % BK == 0, "grouped_gemm_tn: max_rows must be a positive multiple of %d", BK);
     AB_REQUIRE(M > 0 && N > 0 && E > 0 && M % 8 == 0 && N % 8 == 0, "grouped_gemm_tn: M (%d) and N (%d) must be multiples of 8", M, N);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.M = M; p.E = E; p.K = 0;
     p.bn = pick_bn(N, true);
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
-    p.num_m_tiles = (int)ab_ceil_div(M, BM);
+    p.num_m_tiles = (int)ab_ceil_div(M, PM);
     p.seg_off = seg_off; p.c_f32 = 1; p.epi = AB_EPI_NONE; p.cw = Cw;
     p.tn_nsrc = nsrc; p.tn_src_stride = src_stride;
     AB_REQUIRE(((uintptr_t)Cw % 16) == 0, "grouped_gemm_tn: output pointer must be 16-byte aligned");
@@ -642,6 +729,7 @@ int dense_rows(int mode, const void* A, const void* W, const float* bias, const 
     AB_REQUIRE(epi != AB_EPI_BIAS || bias, "dense_gemm: bias epilogue without bias");
     AB_REQUIRE(epi != AB_EPI_ADD || aux, "dense_gemm: add epilogue without addend");
     AB_REQUIRE(((uintptr_t)c % 16) == 0 && (aux == nullptr || ((uintptr_t)aux % 16) == 0), "dense_gemm: output / addend must be 16-byte aligned");
+    AB_REQUIRE(bias == nullptr || ((uintptr_t)bias % 8) == 0, "dense_gemm: bias must be 8-byte aligned");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.N = N; p.K = K; p.E = 1;
@@ -650,12 +738,12 @@ int dense_rows(int mode, const void* A, const void* W, const float* bias, const 
     p.epi = epi; p.c_f32 = c_dtype == AB_F32;
     p.bias = bias; p.aux = aux; p.c = c;
     p.rows_valid = S;
-    p.dense_m_tiles = (int)ab_ceil_div(S, BM);
+    p.dense_m_tiles = (int)ab_ceil_div(S, PM);
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)K, (uint64_t)S, BK, BM)) return e;
     const int64_t tiles = (int64_t)p.dense_m_tiles * p.num_n_tiles;
     if (mode == MODE_NT) {
-        if (int e = make_map2(&tb, W, (uint64_t)K, (uint64_t)N, BK, (uint32_t)p.bn)) return e;
+        if (int e = make_map2(&tb, W, (uint64_t)K, (uint64_t)N, BK, (uint32_t)(p.bn / 2))) return e;
         return launch<MODE_NT>(ta, tb, p, tiles, stream);
     }
     if (int e = make_map2(&tb, W, (uint64_t)N, (uint64_t)K, 64, BK)) return e;
@@ -685,15 +773,19 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
     }
     *reinterpret_cast<float4*>(out + i) = acc;
 }
+
+int dense_tn_nsplit(int64_t S, int M, int N) {
+    const int tiles = (int)(ab_ceil_div(M, PM) * ab_ceil_div(N, pick_bn(N, true)));
+    int nsplit = tiles > 0 ? (ab_num_sms() / 2) / tiles : 1;        // one wave of (slice, tile) work items over the CTA pairs
+    const int64_t kblocks = ab_ceil_div(S, BK);
+    if (nsplit > kblocks / 4) nsplit = (int)(kblocks / 4);          // at least 4 blocks of 64 rows per slice
+    return nsplit < 2 ? 1 : nsplit;
+}
 }  // namespace
 
 extern "C" size_t ab_dense_gemm_tn_workspace_bytes(int64_t S, int M, int N) {
-    const int tiles = (int)(ab_ceil_div(M, BM) * ab_ceil_div(N, 256));
-    int nsplit = tiles > 0 ? ab_num_sms() / tiles : 1;            // one wave of (slice, tile) work items
-    const int64_t kblocks = ab_ceil_div(S, BK);
-    if (nsplit > kblocks / 4) nsplit = (int)(kblocks / 4);          // at least 4 blocks of 64 rows per slice
-    if (nsplit < 2) return 0;
-    return (size_t)nsplit * M * N * sizeof(float);
+    const int nsplit = dense_tn_nsplit(S, M, N);
+    return nsplit < 2 ? 0 : (size_t)nsplit * M * N * sizeof(float);
 }
 
 extern "C" int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, void* ws, size_t ws_bytes, int64_t S, int M, int N,
@@ -705,15 +797,13 @@ extern "C" int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, void* 
     p.N = N; p.M = M; p.K = 0;
     p.bn = pick_bn(N, true);
     p.num_n_tiles = (int)ab_ceil_div(N, p.bn);
-    p.num_m_tiles = (int)ab_ceil_div(M, BM);
+    p.num_m_tiles = (int)ab_ceil_div(M, PM);
     p.c_f32 = 1; p.epi = AB_EPI_NONE;
     p.tn_nsrc = 1; p.tn_rows = S;
     // the contraction runs over all S rows and the output has only a few tiles: cut S into slices (split-K) so that the
     // whole chip works, partial products into the workspace, then one fixed-order sum
-    const size_t need = ab_dense_gemm_tn_workspace_bytes(S, M, N);
-    int nsplit = (int)(need / ((size_t)M * N * sizeof(float)));
-    if (nsplit >= 2 && (ws == nullptr || ws_bytes < need)) nsplit = 1;
-    if (nsplit < 2) nsplit = 1;
+    int nsplit = dense_tn_nsplit(S, M, N);
+    if (nsplit >= 2 && (ws == nullptr || ws_bytes < (size_t)nsplit * M * N * sizeof(float))) nsplit = 1;
     const int64_t kblocks = ab_ceil_div(S, BK);
     p.E = nsplit;
     p.tn_split = ab_ceil_div(kblocks, nsplit) * BK;

@@ -185,7 +185,7 @@ int ab_moe_topk_from_logits(const float* logits, float* gates, int32_t* idx, flo
  * (slot, expert) group the rows with the largest w[:,slot] stay (ties -> lower token id).  `active`
  * [E] int32 (NULL = all) is the whole-expert dropout mask of core.py:514-521.
  * Outputs (all int32): counts[E]; seg_off[E+1] = start row of each expert's segment in the permuted
- * layout, segments padded to multiples of `row_align` (128, the GEMM tile); row_of[S,K] = permuted row
+ * layout, segments padded to multiples of `row_align` (AB_GEMM_ROW_TILE, the GEMM's row tile); row_of[S,K] = permuted row
  * of a kept (token, slot) or -1; tok_of_row[max_rows], slot_of_row[max_rows] (-1 for padding rows);
  * tile_expert[max_rows/row_align] expert of each row tile (-1 beyond the end); n_rows[2] = {padded
  * total rows, kept rows}.  max_rows = ab_moe_max_rows(S,K,E,cap,row_align).  No host synchronisation.
@@ -242,8 +242,9 @@ int ab_moe_router_bwd(const void* x, const float* stats, const float* ln_w, cons
                       int dtype, cudaStream_t stream);
 
 /* ---- MoE: grouped expert GEMM on tcgen05 / TMEM, operands staged by TMA  (core.py:596 = :437-440) --
- * bf16 operands, fp32 accumulation in tensor memory.  Row tiles of `row_align`=128 permuted rows belong
- * to one expert (tile_expert); tiles past n_rows[0] are skipped on the device (no host sync).
+ * bf16 operands, fp32 accumulation in tensor memory.  The kernel runs on CTA pairs (tcgen05 cta_group::2): a row tile is
+ * AB_GEMM_ROW_TILE = 256 permuted rows (128 per CTA) and belongs to one expert (tile_expert[max_rows / 256]); tiles
+ * past n_rows[0] are skipped on the device (no host sync).  max_rows must be a multiple of AB_GEMM_ROW_TILE.
  *
  * ab_grouped_gemm_nt :  C[r, n] = epi( sum_k A[r,k] * W[e, n, k] )         (forward: W = nn.Linear weight)
  *    A [max_rows, K] bf16 row-major, W stacked [E, N, K] bf16.
@@ -256,6 +257,8 @@ int ab_moe_router_bwd(const void* x, const float* stats, const float* ln_w, cons
  *    AB_EPI_NONE        C = acc
  * ab_grouped_gemm_tn :  Cw[e, m, n] = sum_{r in expert e} A[r,m] * Bm[r,n]   (wgrad; fp32 out [E,M,N])
  */
+#define AB_GEMM_ROW_TILE 256
+int ab_gemm_row_tile(void);   /* = AB_GEMM_ROW_TILE: the `row_align` to plan the permuted layout with */
 #define AB_EPI_NONE 0
 #define AB_EPI_BIAS 1
 #define AB_EPI_BIAS_ACT 2
@@ -277,7 +280,7 @@ int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* 
 
 /* ---- dense GEMMs on the same tcgen05 kernel: the SSM layer's projections (core.py:366-367 in_proj_x | in_proj_z,
  * :376-383 x_param_proj with dt_proj_head folded in, :397 out_proj) and their autograd.  Row-major bf16 operands,
- * fp32 accumulation; S need not be a multiple of the 128-row tile.  epi = AB_EPI_NONE | AB_EPI_BIAS (bias [N] fp32) |
+ * fp32 accumulation; S need not be a multiple of the row tile.  epi = AB_EPI_NONE | AB_EPI_BIAS (bias [N] fp32) |
  * AB_EPI_ADD (aux [S,N] of c_dtype is added: a second gradient contribution accumulated in the epilogue).
  *   ab_dense_gemm_nt:  C[S,N] = epi(A[S,K] * W[N,K]^T)        (forward of nn.Linear)
  *   ab_dense_gemm_nn:  C[S,N] = epi(A[S,K] * W[K,N])          (input gradient: same weight tensor, no transpose copy)

@@ -64,11 +64,12 @@ def run_cpu(rank, world):
     recvd = ep.all_to_all_equal(rows.view(world, El * seg, Dm).contiguous(), g).view(E * seg, Dm)
     te = ep.recv_tile_expert(world, El, seg)
     yr = torch.zeros_like(recvd)
-    for t in range(recvd.shape[0] // 128):
+    RA = ep.ROW_ALIGN
+    for t in range(recvd.shape[0] // RA):
         e = rank * El + int(te[t])
-        blk = recvd[t * 128:(t + 1) * 128]
+        blk = recvd[t * RA:(t + 1) * RA]
         hdn = F.gelu(F.linear(blk, moe[f"experts.{e}.1.weight"], moe[f"experts.{e}.1.bias"]))
-        yr[t * 128:(t + 1) * 128] = F.linear(hdn, moe[f"experts.{e}.4.weight"], moe[f"experts.{e}.4.bias"])
+        yr[t * RA:(t + 1) * RA] = F.linear(hdn, moe[f"experts.{e}.4.weight"], moe[f"experts.{e}.4.bias"])
     y = ep.all_to_all_equal(yr.view(world, El * seg, Dm).contiguous(), g).view(E * seg, Dm)
     out = torch.zeros(S, Dm)
     for k in range(K):

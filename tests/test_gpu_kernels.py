@@ -256,7 +256,8 @@ def test_plan_bit_exact(S, E, K, cap, ties, inactive):
     row_of = p["row_of"].cpu().numpy()
     assert np.array_equal(row_of >= 0, kept), "kept (token, slot) sets"
     seg = p["seg_off"].cpu().numpy()
-    assert seg[0] == 0 and np.all(np.diff(seg) == (counts + 127) // 128 * 128)
+    RA = _lib_row_align()
+    assert seg[0] == 0 and np.all(np.diff(seg) == (counts + RA - 1) // RA * RA)
     n_rows = p["n_rows"].cpu().numpy()
     assert n_rows[0] == seg[-1] and n_rows[1] == counts.sum()
     tok, slot = p["tok_of_row"].cpu().numpy(), p["slot_of_row"].cpu().numpy()
@@ -269,22 +270,29 @@ def test_plan_bit_exact(S, E, K, cap, ties, inactive):
     e_of = idx[s_idx, k_idx]
     assert np.all(rows >= seg[e_of]) and np.all(rows < seg[e_of] + counts[e_of])
     assert (tok[: n_rows[0]] >= 0).sum() == counts.sum()
-    for t in range(n_rows[0] // 128):
-        assert seg[te[t]] <= t * 128 < seg[te[t] + 1]
-    assert np.all(te[n_rows[0] // 128:] == -1)
+    for t in range(n_rows[0] // RA):
+        assert seg[te[t]] <= t * RA < seg[te[t] + 1]
+    assert np.all(te[n_rows[0] // RA:] == -1)
 
 
 # ------------------------------------------------------------------------------------------------
 # grouped GEMM (tcgen05)
 # ------------------------------------------------------------------------------------------------
+def _lib_row_align():
+    from apertis_llm_b200 import _lib
+    assert _lib.query("ab_gemm_row_tile") == _lib.ROW_ALIGN
+    return _lib.ROW_ALIGN
+
+
 def _fake_plan(counts, d):
     E = len(counts)
-    pad = [(c + 127) // 128 * 128 for c in counts]
+    RA = _lib_row_align()
+    pad = [(c + RA - 1) // RA * RA for c in counts]
     seg = np.concatenate([[0], np.cumsum(pad)]).astype(np.int32)
-    max_rows = int(seg[-1]) + 256                        # spare tiles past the end must be skipped
-    te = -np.ones(max_rows // 128, dtype=np.int32)
+    max_rows = int(seg[-1]) + 2 * RA                     # spare tiles past the end must be skipped
+    te = -np.ones(max_rows // RA, dtype=np.int32)
     for e in range(E):
-        te[seg[e] // 128: seg[e + 1] // 128] = e
+        te[seg[e] // RA: seg[e + 1] // RA] = e
     valid = np.zeros(max_rows, dtype=bool)
     for e in range(E):
         valid[seg[e]: seg[e] + counts[e]] = True
@@ -317,7 +325,8 @@ def test_grouped_gemm_rows(mode, N, K, counts):
     torch.cuda.synchronize()
     assert rel_err(c[:total], ref) < 2e-5, "fp32 accumulate of bf16 operands"
     # bias + gelu with bf16 outputs
-    erow = torch.from_numpy(np.repeat(te[: total // 128], 128)).long()
+    RA = _lib_row_align()
+    erow = torch.from_numpy(np.repeat(te[: total // RA], RA)).long()
     pre = (ref + bias[erow]).to(torch.bfloat16).float()
     h, hpre = ops.grouped_gemm(mode, Ad, Wd, plan, N, K, E, bias=bd, epi=_lib.EPI_BIAS_ACT, act=0, out_dtype=torch.bfloat16, want_c2=True)
     assert rel_err(hpre[:total].float(), pre) < 1e-2

@@ -27,7 +27,7 @@ def main():
     E, Dm, I, R = args.experts, args.dm, args.inter, args.rows_per_expert
     rows = E * R
     seg = torch.arange(E + 1, dtype=torch.int32, device=d) * R
-    plan = dict(tile_expert=torch.arange(E, dtype=torch.int32, device=d).repeat_interleave(R // 128),
+    plan = dict(tile_expert=torch.arange(E, dtype=torch.int32, device=d).repeat_interleave(R // _lib.ROW_ALIGN),
                 n_rows=torch.full((2,), rows, dtype=torch.int32, device=d), seg_off=seg)
     bf = lambda *s: (torch.randn(*s, device=d) * 0.1).to(torch.bfloat16)
     xn, h, hpre, dy, dh = bf(rows, Dm), bf(rows, I), bf(rows, I), bf(rows, Dm), bf(rows, I)
