@@ -75,7 +75,8 @@ __device__ __forceinline__ int dense_tn_blocks(const GemmParams& p, int e) {
 }
 
 // ---- math for the epilogues -------------------------------------------------------------------
-// erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26): erf(x/sqrt2) from t = 1/(1+p|x|/sqrt2) and g = exp(-x^2/2)
+// fp32 data path (outputs in fp32: the fp32-parity mode): erf with |error| < 1.5e-7 (Abramowitz & Stegun 7.1.26):
+// erf(x/sqrt2) from t = 1/(1+p|x|/sqrt2) and g = exp(-x^2/2)
 __device__ __forceinline__ float erf_core(float ax_s, float g) {     // ax_s = |x|/sqrt(2), g = exp(-ax_s^2)
     const float t = ab_rcp(fmaf(0.3275911f, ax_s, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
@@ -113,8 +114,8 @@ __device__ __forceinline__ float act_bwd(float x, int act) {
     return s * fmaf(x, 1.f - s, 1.f);
 }
 
-// ---- the same activations on column pairs (FFMA2 / FMUL2): the epilogue is instruction-issue bound at small K, and packed
-//      arithmetic halves its floating-point instruction count ----------------------------------------------------------
+// ---- the same activations on column pairs (FFMA2 / FMUL2): packed arithmetic halves the floating-point instruction count
+//      of the epilogue, which at K = 704 has as many issue slots to fill as the tensor core has cycles ---------------------
 __device__ __forceinline__ f2 gelu_fwd2(f2 x) {
     float x0, x1;
     f2_unpack(x, x0, x1);
@@ -144,17 +145,61 @@ __device__ __forceinline__ f2 gelu_bwd2(f2 x) {        // cdf(x) + x * pdf(x)
     const f2 cdf = f2_fma(f2_pack(copysignf(e0, x0), copysignf(e1, x1)), f2_bcast(0.5f), f2_bcast(0.5f));
     return f2_fma(x, f2_mul(g, f2_bcast(0.3989422804014327f)), cdf);
 }
-template <int U>
-__device__ __forceinline__ void act_fwd_row(float (&f)[U], int act) {
-    if (act == AB_ACT_GELU) {
+
+// ---- bf16 data path: the normal cdf as 0.5 (1 + tanh(u)), u = x (c0 + c1 x^2 + c2 x^4) (least-squares fit on |x| <= 6 with
+//      x^2 clamped at 81; against the erf form |d gelu| < 3e-5 and |d gelu'| < 1.1e-4 before the hardware tanh's own 2^-11,
+//      i.e. together < |x| 2.6e-4: a sixteenth of a bf16 ulp of the value being rounded).  One MUFU and 6 packed
+//      operations per column pair instead of four MUFU and 12; the derivative is the exact derivative of the same
+//      approximation, so forward and backward stay consistent.  `hs` = 0.5 x (the dropout scale 1 / (1 - p), or 1).
+#define AB_GF_C0 0.79746994f
+#define AB_GF_C1 0.037015004f
+#define AB_GF_C2 -3.5035629e-4f
+__device__ __forceinline__ float ab_tanh(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ f2 f2_tanh(f2 v) { float a, b; f2_unpack(v, a, b); return f2_pack(ab_tanh(a), ab_tanh(b)); }
+__device__ __forceinline__ f2 gelu_fast_x2(f2 x) {
+    float a, b;
+    f2_unpack(f2_mul(x, x), a, b);
+    return f2_pack(fminf(a, 81.f), fminf(b, 81.f));
+}
+__device__ __forceinline__ f2 gelu_fwd_fast2(f2 x, f2 hs) {
+    const f2 x2 = gelu_fast_x2(x);
+    f2 p = f2_fma(f2_bcast(AB_GF_C2), x2, f2_bcast(AB_GF_C1));
+    p = f2_fma(p, x2, f2_bcast(AB_GF_C0));
+    const f2 t = f2_tanh(f2_mul(p, x));
+    const f2 hx = f2_mul(x, hs);
+    return f2_fma(hx, t, hx);
+}
+// d/dx [x cdf(x)] = 0.5 (1 + t) [1 + (1 - t) x u'(x)],  u' = c0 + 3 c1 x^2 + 5 c2 x^4
+__device__ __forceinline__ f2 gelu_bwd_fast2(f2 x, f2 hs) {
+    const f2 x2 = gelu_fast_x2(x);
+    f2 p = f2_fma(f2_bcast(AB_GF_C2), x2, f2_bcast(AB_GF_C1));
+    p = f2_fma(p, x2, f2_bcast(AB_GF_C0));
+    const f2 t = f2_tanh(f2_mul(p, x));
+    f2 up = f2_fma(f2_bcast(5.f * AB_GF_C2), x2, f2_bcast(3.f * AB_GF_C1));
+    up = f2_fma(up, x2, f2_bcast(AB_GF_C0));
+    const f2 w = f2_mul(x, up);
+    const f2 e = f2_fma(f2_mul(t, f2_bcast(-1.0f)), w, w);       // (1 - t) w
+    const f2 A = f2_fma(t, hs, hs);                              // 0.5 s (1 + t)
+    return f2_fma(A, e, A);
+}
+
+// activation of a row in place, times `scale` (the expert-internal Dropout's 1 / (1 - p), or 1)
+template <int U, bool F32>
+__device__ __forceinline__ void act_fwd_row(float (&f)[U], int act, float scale) {
+    if (act == AB_ACT_GELU && !F32) {
+        const f2 hs = f2_bcast(0.5f * scale);
 #pragma unroll
-        for (int i = 0; i < U; i += 2) f2_unpack(gelu_fwd2(f2_pack(f[i], f[i + 1])), f[i], f[i + 1]);
+        for (int i = 0; i < U; i += 2) f2_unpack(gelu_fwd_fast2(f2_pack(f[i], f[i + 1]), hs), f[i], f[i + 1]);
+    } else if (act == AB_ACT_GELU) {
+        const f2 sc = f2_bcast(scale);
+#pragma unroll
+        for (int i = 0; i < U; i += 2) f2_unpack(f2_mul(gelu_fwd2(f2_pack(f[i], f[i + 1])), sc), f[i], f[i + 1]);
     } else if (act == AB_ACT_RELU) {
 #pragma unroll
-        for (int i = 0; i < U; ++i) f[i] = fmaxf(f[i], 0.f);
+        for (int i = 0; i < U; ++i) f[i] = fmaxf(f[i], 0.f) * scale;
     } else {
 #pragma unroll
-        for (int i = 0; i < U; ++i) f[i] = act_fwd(f[i], AB_ACT_SILU);
+        for (int i = 0; i < U; ++i) f[i] = act_fwd(f[i], AB_ACT_SILU) * scale;
     }
 }
 // bf16 round trip of a row (the value the next kernel will read), two columns per conversion
@@ -168,38 +213,32 @@ __device__ __forceinline__ void round_row_bf16(float (&f)[U]) {
         f[i + 1] = __uint_as_float(r & 0xffff0000u);
     }
 }
-// dropout on a row: one hash per 4 columns, the keep flags become multipliers (0 or 1 / (1 - p)) applied pairwise
-template <int U>
-__device__ __forceinline__ void dropout_row(float (&f)[U], const GemmParams& p, uint32_t grow, int ncol);
 
 // Dropout keep-mask of the expert hidden activation: counter-based hash of the element index and a 64-bit seed, so the
 // backward regenerates exactly the forward's mask without storing it.  One hash serves 4 consecutive columns (four
-// 16-bit uniforms, drop when < p * 65536), ~6 integer ops per element.
-__device__ __forceinline__ void drop_mask4(uint32_t s0, uint32_t s1, uint32_t row, uint32_t col, uint32_t n_cols, uint32_t thresh16,
-                                           bool (&keep)[4]) {
-    uint32_t x = ((row * n_cols + col) >> 2) * 0x9E3779B1u + s0;
+// 16-bit uniforms, drop when < p * 65536).  Both seed words enter between multiplication rounds, so masks of different
+// seeds are unrelated sequences, not shifted copies.  The survivors' scale 1 / (1 - p) is applied by the activation.
+__device__ __forceinline__ void drop_keep4(uint32_t xb, uint32_t grp, uint32_t s1, uint32_t thi, bool (&keep)[4]) {
+    uint32_t x = xb + grp * 0x9E3779B1u;             // = (index of the 4-column group) * golden ratio + seed word 0
     x ^= x >> 16; x *= 0x85EBCA6Bu;
-    x ^= x >> 13; x *= 0xC2B2AE35u;
-    x ^= x >> 16;
+    x = x ^ (x >> 13) ^ s1; x *= 0xC2B2AE35u;
     uint32_t y = x * 0x27D4EB2Fu + s1;
     y ^= y >> 15;
-    keep[0] = (x & 0xffffu) >= thresh16;
-    keep[1] = (x >> 16) >= thresh16;
-    keep[2] = (y & 0xffffu) >= thresh16;
-    keep[3] = (y >> 16) >= thresh16;
+    keep[0] = (x << 16) >= thi;      // 16-bit uniforms compared in place: low halves shifted up, high halves as they are
+    keep[1] = x >= thi;
+    keep[2] = (y << 16) >= thi;
+    keep[3] = y >= thi;
 }
-
 template <int U>
-__device__ __forceinline__ void dropout_row(float (&f)[U], const GemmParams& p, uint32_t grow, int ncol) {
-    const uint32_t s0 = __ldg(p.drop_seed), s1 = __ldg(p.drop_seed + 1);
+__device__ __forceinline__ void dropout_zero_row(float (&f)[U], uint32_t drop_thresh, uint32_t s0, uint32_t s1, uint32_t grow, int ncol, int n_cols) {
+    const uint32_t xb = ((grow * (uint32_t)n_cols + (uint32_t)ncol) >> 2) * 0x9E3779B1u + s0;
+    const uint32_t thi = drop_thresh << 16;
 #pragma unroll
     for (int i = 0; i < U; i += 4) {
         bool keep[4];
-        drop_mask4(s0, s1, grow, (uint32_t)(ncol + i), (uint32_t)p.N, p.drop_thresh, keep);
-        const f2 m0 = f2_pack(keep[0] ? p.drop_scale : 0.f, keep[1] ? p.drop_scale : 0.f);
-        const f2 m1 = f2_pack(keep[2] ? p.drop_scale : 0.f, keep[3] ? p.drop_scale : 0.f);
-        f2_unpack(f2_mul(f2_pack(f[i], f[i + 1]), m0), f[i], f[i + 1]);
-        f2_unpack(f2_mul(f2_pack(f[i + 2], f[i + 3]), m1), f[i + 2], f[i + 3]);
+        drop_keep4(xb, (uint32_t)(i >> 2), s1, thi, keep);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[i + j] = keep[j] ? f[i + j] : 0.f;
     }
 }
 
@@ -331,6 +370,9 @@ __device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx&
     const int g_cols = g_col0 < bn ? min(GW, bn - g_col0) : 0;
     const int total_tiles = total_tiles_of<MODE>(p);
     unsigned char* stg = c.stg;
+    const bool has_drop = (EPI == AB_EPI_BIAS_ACT || EPI == AB_EPI_DACT) && p.drop_seed != nullptr;
+    const uint32_t drop_s0 = has_drop ? __ldg(p.drop_seed) : 0u, drop_s1 = has_drop ? __ldg(p.drop_seed + 1) : 0u;
+    const float dscale = has_drop ? p.drop_scale : 1.0f;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = c.pair_id; tile < total_tiles; tile += c.num_pairs) {
         const Tile t = decode_tile<MODE>(p, tile);
@@ -347,7 +389,9 @@ __device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx&
             __syncwarp();
         }
         uint4 nxt[4];
-        if (HAS_AUX && g_cols > 0 && n0 + g_col0 < ncol_end) load_aux_unit<F32>(p, nxt, lane, row0, n0 + g_col0, ncol_end);
+        if (HAS_AUX && g_cols > 0 && n0 + g_col0 < ncol_end) {
+            load_aux_unit<F32>(p, nxt, lane, row0, n0 + g_col0, ncol_end);
+        }
         if (have_acc) {
             ab_mbar_wait(&c.tfull[acc], acc_phase);
             ab_tc_fence_after();
@@ -361,7 +405,9 @@ __device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx&
             if (HAS_AUX) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) cur[it] = nxt[it];
-                if (u0 + U < g_cols && ncol + U < ncol_end) load_aux_unit<F32>(p, nxt, lane, row0, ncol + U, ncol_end);
+                if (u0 + U < g_cols && ncol + U < ncol_end) {
+                    load_aux_unit<F32>(p, nxt, lane, row0, ncol + U, ncol_end);
+                }
             }
             float f[U];
             {
@@ -389,16 +435,19 @@ __device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx&
                 // activation is applied in place, so only one fragment is live
                 if (!F32) round_row_bf16<U>(f);
                 stage_and_store<MODE, F32>(p, stg, f, reinterpret_cast<unsigned char*>(p.c2), lane, row0, ncol, ncol_end);
-                act_fwd_row<U>(f, p.act);
-                if (p.drop_seed) dropout_row<U>(f, p, (uint32_t)row0 + (uint32_t)lane, ncol);
+                act_fwd_row<U, F32>(f, p.act, p.drop_seed ? p.drop_scale : 1.0f);
+                if (p.drop_seed) dropout_zero_row<U>(f, p.drop_thresh, drop_s0, drop_s1, (uint32_t)row0 + (uint32_t)lane, ncol, N);
             } else if (HAS_AUX) {
-                // the prefetched tile goes through the staging so that each thread reads its own row
+                // the tile fetched with coalesced accesses goes through the staging so that each thread reads its own row
 #pragma unroll
                 for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(stg + stg_off(it * 8 + (lane >> 2), lane & 3)) = cur[it];
                 __syncwarp();
 #pragma unroll
+                for (int j = 0; j < 4; ++j) cur[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+                __syncwarp();
+#pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+                    const uint4 q = cur[j];
                     float a[CPV];
                     if (F32) { a[0] = __uint_as_float(q.x); a[1] = __uint_as_float(q.y); a[2] = __uint_as_float(q.z); a[3] = __uint_as_float(q.w); }
                     else ab_vec16<__nv_bfloat16>::unpack(q, a);
@@ -409,16 +458,16 @@ __device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx&
                     } else if (p.act == AB_ACT_GELU) {
 #pragma unroll
                         for (int i = 0; i < CPV; i += 2) {
-                            const f2 d = f2_mul(f2_pack(f[j * CPV + i], f[j * CPV + i + 1]), gelu_bwd2(f2_pack(a[i], a[i + 1])));
-                            f2_unpack(d, f[j * CPV + i], f[j * CPV + i + 1]);
+                            const f2 gp = F32 ? f2_mul(gelu_bwd2(f2_pack(a[i], a[i + 1])), f2_bcast(dscale))
+                                              : gelu_bwd_fast2(f2_pack(a[i], a[i + 1]), f2_bcast(0.5f * dscale));
+                            f2_unpack(f2_mul(f2_pack(f[j * CPV + i], f[j * CPV + i + 1]), gp), f[j * CPV + i], f[j * CPV + i + 1]);
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(a[i], p.act);
+                        for (int i = 0; i < CPV; ++i) f[j * CPV + i] *= act_bwd(a[i], p.act) * dscale;
                     }
                 }
-                __syncwarp();
-                if (EPI == AB_EPI_DACT && p.drop_seed) dropout_row<U>(f, p, (uint32_t)row0 + (uint32_t)lane, ncol);
+                if (EPI == AB_EPI_DACT && p.drop_seed) dropout_zero_row<U>(f, p.drop_thresh, drop_s0, drop_s1, (uint32_t)row0 + (uint32_t)lane, ncol, N);
             }
             // ---- stage this thread's row, then store 8 rows x 64 B per instruction
             unsigned char* base;
@@ -489,46 +538,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs: own A rows, own half of B) =================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
-                const Tile t = decode_tile<MODE>(p, tile);
-                const int b_col0 = t.n_tile * bn + (int)rank * bh;
-                for (int kb = 0; kb < t.nk; ++kb) {
+        // The whole warp walks the schedule (warp-uniform control flow keeps coordinates and addresses in uniform
+        // registers); one elected lane issues.  This instruction stream is what feeds the tensor core: it stays lean.
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+            const Tile t = decode_tile<MODE>(p, tile);
+            const int b_col0 = t.n_tile * bn + (int)rank * bh;
+            // MODE_TN walks the expert's row blocks source by source (no division per block); the other modes walk K
+            const int n_src = MODE == MODE_TN ? p.tn_nsrc : 1;
+            const int per_src = t.nk / n_src;
+            const int m0 = MODE == MODE_TN ? t.m_pair * PM + (int)rank * BM : (2 * t.m_pair + (int)rank) * BM;
+            const int b_row0 = MODE == MODE_NN ? t.e * p.K : (MODE == MODE_NT ? t.e * p.N + b_col0 : 0);
+            for (int src = 0; src < n_src; ++src) {
+                int r0 = MODE == MODE_TN ? (int)(src * p.tn_src_stride) + t.k_begin : 0;     // TN: first row of the block; NT / NN: k
+                for (int kk = 0; kk < per_src; ++kk, r0 += BK) {
                     ab_mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char* sa = smem + (size_t)stage * STAGE_BYTES;
                     unsigned char* sb = sa + A_BYTES;
-                    if (rank == 0) ab_mbar_expect_tx(&full[stage], pair_tx);
-                    if (MODE == MODE_TN) {
-                        const int per_src = t.nk / p.tn_nsrc;
-                        const int r0 = (int)((kb / per_src) * p.tn_src_stride) + t.k_begin + (kb % per_src) * BK;
-                        const int m0 = t.m_pair * PM + (int)rank * BM;
-                        ab_tma_load_2d_pair(sa, &tm_a, &full[stage], m0, r0);
-                        ab_tma_load_2d_pair(sa + ATOM_BYTES, &tm_a, &full[stage], m0 + 64, r0);
-                        for (int j = 0; j < bh / 64; ++j)
-                            ab_tma_load_2d_pair(sb + j * ATOM_BYTES, &tm_b, &full[stage], b_col0 + j * 64, r0);
-                    } else {
-                        ab_tma_load_2d_pair(sa, &tm_a, &full[stage], kb * BK, (2 * t.m_pair + (int)rank) * BM);
-                        if (MODE == MODE_NT) {
-                            ab_tma_load_2d_pair(sb, &tm_b, &full[stage], kb * BK, t.e * p.N + b_col0);
+                    if (ab_elect_one()) {
+                        if (rank == 0) ab_mbar_expect_tx(&full[stage], pair_tx);
+                        if (MODE == MODE_TN) {
+                            ab_tma_load_2d_pair(sa, &tm_a, &full[stage], m0, r0);
+                            ab_tma_load_2d_pair(sa + ATOM_BYTES, &tm_a, &full[stage], m0 + 64, r0);
+                            ab_tma_load_2d_pair(sb, &tm_b, &full[stage], b_col0, r0);
+                            if (bh > 64) ab_tma_load_2d_pair(sb + ATOM_BYTES, &tm_b, &full[stage], b_col0 + 64, r0);
                         } else {
-                            for (int j = 0; j < bh / 64; ++j)
-                                ab_tma_load_2d_pair(sb + j * ATOM_BYTES, &tm_b, &full[stage], b_col0 + j * 64, t.e * p.K + kb * BK);
+                            ab_tma_load_2d_pair(sa, &tm_a, &full[stage], r0, m0);
+                            if (MODE == MODE_NT) {
+                                ab_tma_load_2d_pair(sb, &tm_b, &full[stage], r0, b_row0);
+                            } else {
+                                ab_tma_load_2d_pair(sb, &tm_b, &full[stage], b_col0, b_row0 + r0);
+                                if (bh > 64) ab_tma_load_2d_pair(sb + ATOM_BYTES, &tm_b, &full[stage], b_col0 + 64, b_row0 + r0);
+                            }
                         }
                     }
+                    __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
-            // drain: every slot this CTA filled has been released, i.e. no multicast arrival is still on its way here
-            for (int i = 0; i < NSTAGE; ++i) {
-                ab_mbar_wait(&empty[stage], phase ^ 1);
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-            }
+        }
+        // drain: every slot this CTA filled has been released, i.e. no multicast arrival is still on its way here
+        for (int i = 0; i < NSTAGE; ++i) {
+            ab_mbar_wait(&empty[stage], phase ^ 1);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA only) =================
-        if (rank == 0 && lane == 0) {
+        // ================= MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) =================
+        if (rank == 0) {
             const uint32_t idesc = make_idesc(bn, MODE == MODE_TN ? 1 : 0, MODE == MODE_NT ? 0 : 1);
+            // K-major operand: 8-row groups 1024 B apart; MN-major: 64-wide atoms 8 KB apart, 8-k groups 1024 B apart
+            const uint32_t smem0 = ab_smem_u32(smem);
+            const uint64_t da0 = MODE == MODE_TN ? make_smem_desc(smem0, ATOM_BYTES, 1024) : make_smem_desc(smem0, 0, 1024);
+            const uint64_t db0 = MODE == MODE_NT ? make_smem_desc(smem0 + A_BYTES, 0, 1024) : make_smem_desc(smem0 + A_BYTES, ATOM_BYTES, 1024);
+            constexpr uint32_t a_step = MODE == MODE_TN ? (16 * 128) >> 4 : 32 >> 4;     // advance 16 k per MMA
+            constexpr uint32_t b_step = MODE == MODE_NT ? 32 >> 4 : (16 * 128) >> 4;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
@@ -540,18 +603,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) grouped_gemm_kernel(const __gr
                 for (int kb = 0; kb < t.nk; ++kb) {
                     ab_mbar_wait(&full[stage], phase);
                     ab_tc_fence_after();
-                    const uint32_t sa = ab_smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint32_t sb = sa + A_BYTES;
-                    // K-major operand: 8-row groups 1024 B apart; MN-major: 64-wide atoms 8 KB apart, 8-k groups 1024 B apart
-                    const uint64_t da = MODE == MODE_TN ? make_smem_desc(sa, ATOM_BYTES, 1024) : make_smem_desc(sa, 0, 1024);
-                    const uint64_t db = MODE == MODE_NT ? make_smem_desc(sb, 0, 1024) : make_smem_desc(sb, ATOM_BYTES, 1024);
-                    const uint32_t a_step = MODE == MODE_TN ? (16 * 128) >> 4 : 32 >> 4;     // advance 16 k per MMA
-                    const uint32_t b_step = MODE == MODE_NT ? 32 >> 4 : (16 * 128) >> 4;
+                    const uint64_t soff = (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));      // the ring stays below 256 KB: no carry out of the address field
+                    const uint64_t da = da0 + soff, db = db0 + soff;
+                    if (ab_elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        ab_umma_f16_pair(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    ab_umma_commit_pair(&empty[stage], 3);              // the slot is free in both CTAs once these MMAs retire
-                    if (kb == t.nk - 1) ab_umma_commit_pair(&tfull[acc], 3);
+                        for (int k = 0; k < BK / 16; ++k)
+                            ab_umma_f16_pair(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        ab_umma_commit_pair(&empty[stage], 3);              // the slot is free in both CTAs once these MMAs retire
+                        if (kb == t.nk - 1) ab_umma_commit_pair(&tfull[acc], 3);
+                    }
+                    __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
@@ -683,6 +744,8 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
 }  // namespace
 
 extern "C" int ab_gemm_row_tile(void) { return PM; }
+
+
 
 extern "C" int ab_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
                                   const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,

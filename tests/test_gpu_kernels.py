@@ -412,10 +412,48 @@ def test_grouped_gemm_dropout_mask_consistent(p):
     # the dact epilogue regenerates the same mask over the same [rows, N] index space
     dy = (torch.randn(plan["max_rows"], K, generator=g) * 0.5).to(torch.bfloat16).to(d)
     W2 = (torch.randn(E, K, N, generator=g) * 0.05).to(torch.bfloat16).to(d)
-    g0 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=pre1, epi=_lib.EPI_DACT, act=0, out_dtype=torch.float32)
-    g1 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=pre1, epi=_lib.EPI_DACT, act=0, out_dtype=torch.float32, drop_p=p, drop_seed=seed)
-    assert torch.equal((g1[:total] != 0) | (g0[:total] == 0), keep | (g0[:total] == 0))
-    assert rel_err(g1[:total][keep], (g0[:total] / (1 - p))[keep]) < 1e-5
+    for odt, aux, tol in ((torch.float32, pre1.float(), 1e-5), (torch.bfloat16, pre1, 1e-2)):      # aux has the output's dtype
+        g0 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=aux, epi=_lib.EPI_DACT, act=0, out_dtype=odt).float()
+        g1 = ops.grouped_gemm("nn", dy, W2, plan, N, K, E, aux=aux, epi=_lib.EPI_DACT, act=0, out_dtype=odt, drop_p=p, drop_seed=seed).float()
+        assert torch.equal((g1[:total] != 0) | (g0[:total] == 0), keep | (g0[:total] == 0))
+        assert rel_err(g1[:total][keep], (g0[:total] / (1 - p))[keep]) < tol
+
+
+def test_grouped_gemm_gelu_accuracy_per_element():
+    """The bf16 data path evaluates GELU / GELU' through a tanh-form fit of the normal cdf (csrc/grouped_gemm.cu); the fp32
+    path through an erf with |error| < 1.5e-7.  Element by element over pre-activations in [-12, 12]: the bf16 results are
+    the exact-erf values to bf16 rounding plus the fit's 2.6e-4 |x|, the fp32 results to 2e-6."""
+    from apertis_llm_b200 import _lib, ops
+    d = dev()
+    RA = _lib_row_align()
+    N, K, E = 64, 64, 1
+    rows = 4 * RA
+    plan = dict(tile_expert=torch.zeros(rows // RA, dtype=torch.int32, device=d), n_rows=torch.tensor([rows, rows], dtype=torch.int32, device=d))
+    xs = torch.linspace(-12, 12, rows).to(torch.bfloat16)                 # one pre-activation value per row (bf16-exact)
+    A = torch.zeros(rows, K, dtype=torch.bfloat16)
+    A[:, 0] = xs
+    W = torch.zeros(E, N, K, dtype=torch.bfloat16)
+    W[0, :, 0] = 1.0                                                       # pre[r, n] = xs[r]
+    bias = torch.zeros(E, N)
+    x32 = xs.float()[:, None].expand(rows, N)
+    want = F.gelu(x32)
+    xg = x32.clone().requires_grad_(True)
+    F.gelu(xg).sum().backward()
+    want_d = xg.grad
+    ones = torch.zeros(rows, K, dtype=torch.bfloat16)
+    ones[:, 0] = 1.0                                                       # accumulator of the dact GEMM = 1
+    for odt in (torch.bfloat16, torch.float32):
+        h, pre = ops.grouped_gemm("nt", A.to(d), W.to(d), plan, N, K, E, bias=bias.to(d), epi=_lib.EPI_BIAS_ACT, act=0, out_dtype=odt, want_c2=True)
+        assert torch.equal(pre.float().cpu(), x32)
+        dact = ops.grouped_gemm("nt", ones.to(d), W.to(d), plan, N, K, E, aux=x32.to(odt).to(d), epi=_lib.EPI_DACT, act=0, out_dtype=odt)
+        torch.cuda.synchronize()
+        if odt == torch.float32:
+            assert float((h.cpu() - want).abs().max()) < 2e-6 * 12 and float((dact.cpu() - want_d).abs().max()) < 3e-6
+        else:
+            eh = (h.float().cpu() - want).abs()
+            assert bool((eh <= 2.0 ** -8 * want.abs() + 3e-4 * x32.abs() + 1e-4).all()), float(eh.max())
+            ed = (dact.float().cpu() - want_d).abs()
+            assert bool((ed <= 2.0 ** -8 * want_d.abs() + 1.5e-3).all()), float(ed.max())
 
 
 @pytest.mark.parametrize("p", [0.0, 0.1])

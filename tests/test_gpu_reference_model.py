@@ -79,29 +79,48 @@ def l2_err(a, b):
 
 
 def compare_models(ref, mine, batch, tol, autocast=None, grad_tol=None, robust=False):
-    """robust=False: max|a-b| / max|b| per tensor.  robust=True (low-precision runs): two implementations that
-    round activations differently present the router with logits that differ in the last bf16 digits, so now and then a
-    near-tied token picks another expert in one of them and its output moves by O(1) - exactly as the reference under
-    autocast moves against its own fp32 run.  Those runs are therefore bounded in the L2 sense and at the 99th percentile."""
-    l_r, lg_r = step(ref, batch, autocast)
-    l_m, lg_m = step(mine, batch, autocast)
-    assert abs(float(l_r) - float(l_m)) <= tol * abs(float(l_r)), (float(l_r), float(l_m))
-    if robust:
-        d = (lg_m.float() - lg_r.float()).abs().flatten()
-        assert float(d.kthvalue(int(0.99 * d.numel())).values) < tol * float(lg_r.float().abs().max()), "logits (99th percentile)"
-        assert l2_err(lg_m, lg_r) < 1.5 * tol, "logits (L2)"
-    else:
+    """robust=False: max|a-b| / max|b| per tensor against the reference run in the same mode.
+    robust=True (low-precision runs): two implementations that round activations differently present the router with logits
+    that differ in the last bf16 digits, so now and then a near-tied token picks another expert in one of them and its
+    output moves by O(1) - exactly as the reference under autocast moves against its own fp32 run (with 192 tokens one
+    such token is several percent of a tensor's norm).  Both low-precision runs are therefore measured against the
+    reference's fp32 run in the L2 sense, and the drop-in may deviate at most `tol` (gradients: `grad_tol`) or twice (gradients:
+    three times) what the reference's own autocast run deviates, whichever is larger."""
+    if not robust:
+        l_r, lg_r = step(ref, batch, autocast)
+        l_m, lg_m = step(mine, batch, autocast)
+        assert abs(float(l_r) - float(l_m)) <= tol * abs(float(l_r)), (float(l_r), float(l_m))
         assert rel_err(lg_m.float(), lg_r.float()) < tol, "logits"
-    g_r, g_m = grads_by_reference_name(ref), grads_by_reference_name(mine)
+        g_r, g_m = grads_by_reference_name(ref), grads_by_reference_name(mine)
+        assert set(g_r) == set(g_m)
+        bad = []
+        for k in g_r:
+            if float(g_r[k].abs().max()) == 0.0 and float(g_m[k].abs().max()) == 0.0:
+                continue
+            e = rel_err(g_m[k].float(), g_r[k].float())
+            if not e < (grad_tol or tol):
+                bad.append((k, e))
+        assert not bad, bad
+        return
+    l_32, lg_32 = step(ref, batch, None)
+    g_32 = {k: v.clone() for k, v in grads_by_reference_name(ref).items()}
+    l_r, lg_r = step(ref, batch, autocast)
+    g_r = {k: v.clone() for k, v in grads_by_reference_name(ref).items()}
+    l_m, lg_m = step(mine, batch, autocast)
+    g_m = grads_by_reference_name(mine)
     assert set(g_r) == set(g_m)
+    assert lg_m.dtype == lg_r.dtype
+    assert abs(float(l_m) - float(l_32)) <= max(tol, 2 * abs(float(l_r) - float(l_32)) / abs(float(l_32))) * abs(float(l_32)), (float(l_32), float(l_r), float(l_m))
+    floor = l2_err(lg_r, lg_32)
+    assert l2_err(lg_m, lg_32) < max(1.5 * tol, 2 * floor), ("logits (L2)", l2_err(lg_m, lg_32), floor)
     bad = []
-    for k in g_r:
-        if float(g_r[k].abs().max()) == 0.0 and float(g_m[k].abs().max()) == 0.0:
+    for k in g_32:
+        if float(g_32[k].abs().max()) == 0.0:
             continue
-        e = l2_err(g_m[k], g_r[k]) if robust else rel_err(g_m[k].float(), g_r[k].float())
-        if not e < (grad_tol or tol):
-            bad.append((k, e))
-    assert not bad, bad
+        e, fl = l2_err(g_m[k], g_32[k]), l2_err(g_r[k], g_32[k])
+        if not e < max(grad_tol or tol, 3 * fl):
+            bad.append((k, round(e, 4), round(fl, 4)))
+    assert not bad, "(tensor, error vs fp32, reference autocast floor): " + "; ".join(map(str, bad))
 
 
 def text_batch(vocab=211, B=2, L=96, seed=0):

@@ -47,6 +47,10 @@ def main():
         "nn2_dgrad_dgelu_drop": lambda: ops.grouped_gemm("nn", dy, w2, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=0, drop_p=0.1,
                                                           drop_seed=seed),
     }
+    # library reference point: the same flops as one dense bf16 GEMM through cuBLAS (torch.matmul), not part of the product
+    wd1, wd2 = bf(I, Dm), bf(Dm, I)
+    cases["cublas_dense_nt1"] = lambda: torch.matmul(xn, wd1.t())
+    cases["cublas_dense_nt2"] = lambda: torch.matmul(h, wd2.t())
     only = [c for c in args.only.split(",") if c]
     flops = 2.0 * rows * Dm * I
     for name, fn in cases.items():
