@@ -67,6 +67,16 @@ __device__ __forceinline__ void radix_select_bin(int* hist, int& need, int& sel_
     __syncthreads();
 }
 
+// histogram increment with one shared-memory atomic per distinct bin per warp: gate weights share their top bytes, so
+// per-element atomics on the same bin would serialise.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void hist_add_warp(int* hist, bool valid, int bin) {
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const unsigned peers = __match_any_sync(act, bin);
+        if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+    }
+}
+
 __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w,
                                                                   const int32_t* __restrict__ active, int cap,
                                                                   int32_t* __restrict__ counts, int32_t* __restrict__ row_local,
@@ -80,9 +90,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t*
     const bool is_active = active == nullptr || active[e] != 0;
     int kept_total = 0;
     for (int k = 0; k < K; ++k) {
-        // ---- (A) compaction in token order + histogram of the top byte
-        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
+        // ---- (A) compaction in token order (histograms are only built when the capacity overflows, in (B))
         int n_cand = 0;
         const int span = blockDim.x * TPT;
         for (int s0 = 0; s0 < S; s0 += span) {
@@ -103,7 +111,6 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t*
             for (int t = 0; t < TPT; ++t) {
                 if (c[t]) {
                     if (pos < list_cap) s_list[pos] = make_uint2((uint32_t)(sb + t), wb[t]);
-                    atomicAdd(&hist[wb[t] >> 24], 1);
                     ++pos;
                 }
             }
@@ -121,24 +128,23 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_count_kernel(const int32_t*
             uint32_t prefix = 0, mask = 0;
             int need = rem, bin;
             for (int pass = 3; pass >= 0; --pass) {
-                if (pass != 3) {
-                    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-                    __syncthreads();
-                    if (in_smem) {
-                        for (int i = tid; i < n_cand; i += blockDim.x) {
-                            const uint32_t b = s_list[i].y;
-                            if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
-                        }
-                    } else {
-                        for (int s = tid; s < S; s += blockDim.x) {
-                            if (idx[(size_t)s * K + k] == e) {
-                                const uint32_t b = __float_as_uint(w[(size_t)s * K + k]);
-                                if ((b & mask) == prefix) atomicAdd(&hist[(b >> (8 * pass)) & 0xff], 1);
-                            }
-                        }
+                for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+                __syncthreads();
+                if (in_smem) {
+                    for (int i0 = 0; i0 < n_cand; i0 += blockDim.x) {
+                        const int i = i0 + tid;
+                        const uint32_t b = i < n_cand ? s_list[i].y : 0u;
+                        hist_add_warp(hist, i < n_cand && (b & mask) == prefix, (int)((b >> (8 * pass)) & 0xff));
                     }
-                    __syncthreads();
+                } else {
+                    for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+                        const int s = s0 + tid;
+                        const bool c = s < S && idx[(size_t)s * K + k] == e;
+                        const uint32_t b = c ? __float_as_uint(w[(size_t)s * K + k]) : 0u;
+                        hist_add_warp(hist, c && (b & mask) == prefix, (int)((b >> (8 * pass)) & 0xff));
+                    }
                 }
+                __syncthreads();
                 radix_select_bin(hist, need, bin, &s_sel_bin, &s_need);
                 prefix |= (uint32_t)bin << (8 * pass);
                 mask |= 0xffu << (8 * pass);
@@ -415,11 +421,12 @@ __global__ void __launch_bounds__(256, NIT <= 6 ? 3 : 2) permute_ln_bwd_fused_ke
                                                                    const int32_t* __restrict__ tok_of_row,
                                                                    const int32_t* __restrict__ tile_expert,
                                                                    const int32_t* __restrict__ n_rows, float* __restrict__ dxrow,
-                                                                   float* __restrict__ part, int Dm, int align) {
+                                                                   float* __restrict__ part, int Dm, int align, int ratio) {
+    // `align` = rows of this kernel's work tile, `ratio` work tiles per tile_expert entry (the GEMM's row tile)
     __shared__ float sacc[2][NIT * 128];
     const int t = blockIdx.x;
     if ((int64_t)t * align >= n_rows[0]) return;
-    const int e = tile_expert[t];
+    const int e = tile_expert[t / ratio];
     if (e < 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const float* g = ln_w + (size_t)e * Dm;
@@ -501,10 +508,10 @@ __global__ void __launch_bounds__(256) permute_ln_bwd_cols_kernel(const TG* __re
                                                                   const int32_t* __restrict__ tok_of_row,
                                                                   const int32_t* __restrict__ tile_expert,
                                                                   const int32_t* __restrict__ n_rows, float* __restrict__ part,
-                                                                  int Dm, int align) {
+                                                                  int Dm, int align, int ratio) {
     __shared__ float red[8][2][128];
     const int t = blockIdx.x;
-    if ((int64_t)t * align >= n_rows[0] || tile_expert[t] < 0) return;
+    if ((int64_t)t * align >= n_rows[0] || tile_expert[t / ratio] < 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.y * 128 + lane * 4;
     float gw[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -538,10 +545,10 @@ __global__ void __launch_bounds__(256) permute_ln_bwd_cols_kernel(const TG* __re
 template <typename T>
 __global__ void __launch_bounds__(256) tile_colsum_kernel(const T* __restrict__ a, const int32_t* __restrict__ tile_expert,
                                                           const int32_t* __restrict__ n_rows, float* __restrict__ part, int C,
-                                                          int align) {
+                                                          int align, int ratio) {
     __shared__ float red[8][256];
     const int t = blockIdx.x;
-    if ((int64_t)t * align >= n_rows[0] || tile_expert[t] < 0) return;
+    if ((int64_t)t * align >= n_rows[0] || tile_expert[t / ratio] < 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.y * 256 + lane * 8;
     float acc[8];
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(256) tile_colsum_kernel(const T* __restrict__ 
 // out_a [E][split], columns [split, ncols) to out_b [E][ncols-split].
 __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t* __restrict__ tile_expert,
                                    const int32_t* __restrict__ n_rows, float* __restrict__ out_a, float* __restrict__ out_b,
-                                   int split, int ncols, int align) {
+                                   int split, int ncols, int align, int ratio) {
     __shared__ int s_t0, s_t1;
     __shared__ int s_list[1024];                       // tile ids of this expert, in order (the common case fits)
     __shared__ int s_n;
@@ -578,7 +585,7 @@ __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t
         int n = 0, t0 = ntiles, t1 = 0;
         for (int base = 0; base < ntiles; base += 32) {
             const int t = base + (int)threadIdx.x;
-            const bool mine = t < ntiles && tile_expert[t] == e;
+            const bool mine = t < ntiles && tile_expert[t / ratio] == e;
             const unsigned m = __ballot_sync(0xffffffffu, mine);
             if (mine) {
                 const int pos = n + __popc(m & ((1u << threadIdx.x) - 1u));
@@ -604,11 +611,15 @@ __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t
         }
     } else {
         for (int t = s_t0; t < s_t1; ++t)
-            if (tile_expert[t] == e) s += part[(size_t)t * ncols + j];  // tiles of an expert may be interleaved (EP layout)
+            if (tile_expert[t / ratio] == e) s += part[(size_t)t * ncols + j];  // tiles of an expert may be interleaved (EP layout)
     }
     if (j < split) out_a[(size_t)e * split + j] = s;
     else out_b[(size_t)e * (ncols - split) + (j - split)] = s;
 }
+
+// The per-tile reduction kernels work on tiles of at most 128 rows whatever the GEMM's row tile is (more, smaller CTAs:
+// these kernels are latency-bound streams); tile_expert is looked up through the ratio of the two.
+int work_rows(int row_align) { return row_align % 128 == 0 ? 128 : row_align; }
 
 int rows_grid(int64_t max_rows) {
     const int64_t want = ab_ceil_div(max_rows, 8);
@@ -725,7 +736,7 @@ extern "C" int ab_moe_unpermute_bwd(const void* dout, const void* y, const float
 }
 
 extern "C" size_t ab_moe_permute_ln_bwd_workspace_bytes(int Dm, int row_align, int64_t max_rows) {
-    return (size_t)ab_round_up((max_rows / row_align) * 2 * (int64_t)Dm * sizeof(float), 256);
+    return (size_t)ab_round_up((max_rows / work_rows(row_align)) * 2 * (int64_t)Dm * sizeof(float), 256);
 }
 
 extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float* stats, const float* ln_w,
@@ -734,14 +745,15 @@ extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float
                                      int64_t max_rows, int dtype, int dxn_dtype, cudaStream_t stream) {
     AB_REQUIRE(ws && ws_bytes >= ab_moe_permute_ln_bwd_workspace_bytes(Dm, row_align, max_rows), "moe_permute_ln_bwd: workspace too small");
     AB_REQUIRE(Dm % 4 == 0, "moe_permute_ln_bwd: hidden size must be a multiple of 4");
-    const int ntiles = (int)(max_rows / row_align);
+    const int sub = work_rows(row_align), ratio = row_align / sub;
+    const int ntiles = (int)(max_rows / sub);
     float* part = (float*)ws;
     const int rgrid = rows_grid(max_rows);
     dim3 cgrid(ntiles, (unsigned)ab_ceil_div(Dm, 128));
     const int nit = (int)ab_ceil_div(Dm, 128);
 #define AB_LNB_F(TX, TG, NIT)                                                                                                    \
     permute_ln_bwd_fused_kernel<TX, TG, NIT><<<ntiles, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row, \
-                                                                         tile_expert, n_rows, dxrow, part, Dm, row_align)
+                                                                         tile_expert, n_rows, dxrow, part, Dm, sub, ratio)
 #define AB_LNB(TX, TG)                                                                                                           \
     {                                                                                                                            \
         if (nit <= 8) {                                                                                                          \
@@ -751,7 +763,7 @@ extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float
             permute_ln_bwd_rows_kernel<TX, TG><<<rgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, ln_w, tok_of_row, \
                                                                           tile_expert, n_rows, dxrow, Dm, row_align);            \
             permute_ln_bwd_cols_kernel<TX, TG><<<cgrid, 256, 0, stream>>>((const TG*)dxn, (const TX*)x, stats, tok_of_row,       \
-                                                                          tile_expert, n_rows, part, Dm, row_align);             \
+                                                                          tile_expert, n_rows, part, Dm, sub, ratio);            \
         }                                                                                                                        \
     }
     if (dtype == AB_F32 && dxn_dtype == AB_F32) AB_LNB(float, float)
@@ -763,28 +775,29 @@ extern "C" int ab_moe_permute_ln_bwd(const void* dxn, const void* x, const float
 #undef AB_LNB_F
     AB_LAUNCH_CHECK();
     dim3 grid((unsigned)ab_ceil_div(2 * Dm, 128), E);       // part is [tile][2][Dm]: reduce as 2*Dm columns, split in two
-    tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, dln_w, dln_b, Dm, 2 * Dm, row_align);
+    tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, dln_w, dln_b, Dm, 2 * Dm, sub, ratio);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
 
 extern "C" size_t ab_moe_segment_colsum_workspace_bytes(int C, int row_align, int64_t max_rows) {
-    return (size_t)ab_round_up((max_rows / row_align) * (int64_t)C * sizeof(float), 256);
+    return (size_t)ab_round_up((max_rows / work_rows(row_align)) * (int64_t)C * sizeof(float), 256);
 }
 
 extern "C" int ab_moe_segment_colsum(const void* a, const int32_t* tile_expert, const int32_t* n_rows, float* out, void* ws,
                                      size_t ws_bytes, int C, int E, int row_align, int64_t max_rows, int dtype,
                                      cudaStream_t stream) {
     AB_REQUIRE(ws && ws_bytes >= ab_moe_segment_colsum_workspace_bytes(C, row_align, max_rows), "moe_segment_colsum: workspace too small");
-    const int ntiles = (int)(max_rows / row_align);
+    const int sub = work_rows(row_align), ratio = row_align / sub;
+    const int ntiles = (int)(max_rows / sub);
     float* part = (float*)ws;
     AB_REQUIRE(C % 8 == 0, "moe_segment_colsum: column count must be a multiple of 8");
     dim3 cgrid(ntiles, (unsigned)ab_ceil_div(C, 256));
-    if (dtype == AB_F32) tile_colsum_kernel<float><<<cgrid, 256, 0, stream>>>((const float*)a, tile_expert, n_rows, part, C, row_align);
-    else tile_colsum_kernel<__nv_bfloat16><<<cgrid, 256, 0, stream>>>((const __nv_bfloat16*)a, tile_expert, n_rows, part, C, row_align);
+    if (dtype == AB_F32) tile_colsum_kernel<float><<<cgrid, 256, 0, stream>>>((const float*)a, tile_expert, n_rows, part, C, sub, ratio);
+    else tile_colsum_kernel<__nv_bfloat16><<<cgrid, 256, 0, stream>>>((const __nv_bfloat16*)a, tile_expert, n_rows, part, C, sub, ratio);
     AB_LAUNCH_CHECK();
     dim3 grid((unsigned)ab_ceil_div(C, 128), E);
-    tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, out, nullptr, C, C, row_align);
+    tile_reduce_kernel<<<grid, 128, 0, stream>>>(part, tile_expert, n_rows, out, nullptr, C, C, sub, ratio);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

@@ -191,6 +191,175 @@ __global__ void __launch_bounds__(WARPS * 32) router_fwd_kernel(const T* __restr
     }
 }
 
+// Same forward with the token's row held in registers (hidden sizes up to 32 * V * NV): one global read of the row, the
+// E dot products read G as 16-byte vectors, and for E <= 8 the E partial sums of the 32 lanes are reduced by recursive
+// halving (10 shuffles instead of 5 per expert).  The launcher picks this kernel whenever the row fits.
+template <int EM>
+__device__ __forceinline__ float reduce_dots_to_lane(float (&dot)[EM], int lane, int E) {
+    float mine = 0.f;
+    if (EM == 8) {
+        // halve the vector while doubling the lanes per value: after xor 16 / 8 / 4 a lane holds ONE expert's partial sum
+        float v4[4], v2[2], v1;
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float keep = h16 ? dot[4 + j] : dot[j], send = h16 ? dot[j] : dot[4 + j];
+            v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float keep = h8 ? v4[2 + j] : v4[j], send = h8 ? v4[j] : v4[2 + j];
+            v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const float keep = h4 ? v2[1] : v2[0], send = h4 ? v2[0] : v2[1];
+            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        // lanes with bits (4,3,2) = (e2,e1,e0) hold expert e's total: hand it to lane e
+        const int src = ((lane >> 2) & 1) << 4 | ((lane >> 1) & 1) << 3 | (lane & 1) << 2;
+        mine = __shfl_sync(0xffffffffu, v1, src);
+        if (lane >= E) mine = 0.f;
+    } else {
+#pragma unroll
+        for (int e = 0; e < EM; ++e) {
+            if (e < E) {
+                const float t = ab_warp_sum(dot[e]);
+                if (lane == e) mine = t;
+            }
+        }
+    }
+    return mine;
+}
+
+template <typename T, int EM, int NV>
+__global__ void __launch_bounds__(WARPS * 32) router_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
+                                                                    const float* __restrict__ ln_b, float eps,
+                                                                    const float* __restrict__ Wr, const float* __restrict__ br,
+                                                                    const float* __restrict__ noise,
+                                                                    const float* __restrict__ noise_scale, float* __restrict__ lclean,
+                                                                    float* __restrict__ logits, float* __restrict__ gates,
+                                                                    int32_t* __restrict__ idx, float* __restrict__ probs,
+                                                                    float* __restrict__ w, float* __restrict__ lse_out,
+                                                                    float* __restrict__ stats, float* __restrict__ part, int S,
+                                                                    int Dm, int E, int K, int quant) {
+    constexpr int V = ab_vec16<T>::N;
+    extern __shared__ float sm[];
+    float* G = sm;                 // [E][Dm]
+    float* cvec = G + (size_t)E * Dm;   // [E]
+    float* red = cvec + 32;        // [WARPS][2E+1]
+    float* lnw_s = red + WARPS * (2 * E + 1);      // [Dm], [Dm]: LayerNorm affine (quant modes only)
+    float* lnb_s = lnw_s + Dm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (quant == AB_ROUTER_EXACT) {
+        for (int i = tid; i < E * Dm; i += blockDim.x) G[i] = ln_w[i % Dm] * Wr[i];
+        for (int e = warp; e < E; e += WARPS) {
+            float acc = 0.f;
+            for (int d = lane; d < Dm; d += 32) acc = fmaf(ln_b[d], Wr[(size_t)e * Dm + d], acc);
+            acc = ab_warp_sum(acc);
+            if (lane == 0) cvec[e] = acc + br[e];
+        }
+    } else {
+        for (int i = tid; i < E * Dm; i += blockDim.x) G[i] = ab_round_to(Wr[i], quant);
+        for (int d = tid; d < Dm; d += blockDim.x) { lnw_s[d] = ln_w[d]; lnb_s[d] = ln_b[d]; }
+        if (tid < E) cvec[tid] = ab_round_to(br[tid], quant);
+    }
+    __syncthreads();
+    const int nvec = Dm / V;
+    const float inv_dm = 1.0f / (float)Dm;
+    float a_g = 0.f, a_cnt = 0.f, a_l2 = 0.f;
+    for (int s = blockIdx.x * WARPS + warp; s < S; s += gridDim.x * WARPS) {
+        const T* row = x + (size_t)s * Dm;
+        float f[NV][V];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int iv = i * 32 + lane;
+            if (iv < nvec) {
+                row_load<T>(row, iv, f[i]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) sum += f[i][v];
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) f[i][v] = 0.f;
+            }
+        }
+        const float mean = ab_warp_sum(sum) * inv_dm;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (i * 32 + lane < nvec) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) { f[i][v] -= mean; var = fmaf(f[i][v], f[i][v], var); }
+            }
+        }
+        var = ab_warp_sum(var) * inv_dm;
+        const float rstd = rsqrtf(var + eps);
+        float dot[EM];
+#pragma unroll
+        for (int e = 0; e < EM; ++e) dot[e] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int iv = i * 32 + lane;
+            if (iv < nvec) {
+                if (quant != AB_ROUTER_EXACT) {
+                    // autocast emulation: the normalised row rounded element by element before the Linear
+#pragma unroll
+                    for (int v4 = 0; v4 < V; v4 += 4) {
+                        const float4 lw = *reinterpret_cast<const float4*>(lnw_s + iv * V + v4);
+                        const float4 lb = *reinterpret_cast<const float4*>(lnb_s + iv * V + v4);
+                        f[i][v4] = ab_round_to(fmaf(f[i][v4] * rstd, lw.x, lb.x), quant);
+                        f[i][v4 + 1] = ab_round_to(fmaf(f[i][v4 + 1] * rstd, lw.y, lb.y), quant);
+                        f[i][v4 + 2] = ab_round_to(fmaf(f[i][v4 + 2] * rstd, lw.z, lb.z), quant);
+                        f[i][v4 + 3] = ab_round_to(fmaf(f[i][v4 + 3] * rstd, lw.w, lb.w), quant);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < EM; ++e) {
+                    if (e < E) {
+#pragma unroll
+                        for (int v4 = 0; v4 < V; v4 += 4) {
+                            const float4 gq = *reinterpret_cast<const float4*>(G + (size_t)e * Dm + iv * V + v4);
+                            dot[e] = fmaf(f[i][v4], gq.x, dot[e]); dot[e] = fmaf(f[i][v4 + 1], gq.y, dot[e]);
+                            dot[e] = fmaf(f[i][v4 + 2], gq.z, dot[e]); dot[e] = fmaf(f[i][v4 + 3], gq.w, dot[e]);
+                        }
+                    }
+                }
+            }
+        }
+        float mylogit = reduce_dots_to_lane<EM>(dot, lane, E);
+        float lc = 0.f;
+        if (lane < E) {
+            lc = quant == AB_ROUTER_EXACT ? fmaf(rstd, mylogit, cvec[lane]) : ab_round_to(mylogit + cvec[lane], quant);
+            mylogit = lc;
+            if (noise) mylogit = fmaf(noise[(size_t)s * E + lane], noise_scale[lane], lc);
+            if (lclean) lclean[(size_t)s * E + lane] = lc;
+            if (logits) logits[(size_t)s * E + lane] = mylogit;
+        }
+        if (lane == 0) { stats[2 * (size_t)s] = mean; stats[2 * (size_t)s + 1] = rstd; }
+        float g, lse, my_p, den;
+        int my_idx;
+        unsigned sel_mask;
+        select_topk(mylogit, lane, E, K, g, lse, my_idx, my_p, den, sel_mask);
+        write_selection(s, lane, E, K, g, lse, my_idx, my_p, den, gates, idx, probs, w, lse_out);
+        if (lane < E) {
+            a_g += g;
+            a_cnt += (sel_mask >> lane) & 1u ? 1.f : 0.f;
+        }
+        if (lane == 0) a_l2 = fmaf(lse, lse, a_l2);
+    }
+    const int NA = 2 * E + 1;
+    if (lane < E) { red[warp * NA + lane] = a_g; red[warp * NA + E + lane] = a_cnt; }
+    if (lane == 0) red[warp * NA + 2 * E] = a_l2;
+    __syncthreads();
+    if (tid < NA) {
+        float s2 = 0.f;
+        for (int wv = 0; wv < WARPS; ++wv) s2 += red[wv * NA + tid];
+        part[(size_t)blockIdx.x * NA + tid] = s2;
+    }
+}
+
 // out[c] = sum_r part[r][c]; one warp per column, fixed order -> deterministic
 __global__ void reduce_rows_kernel(const float* __restrict__ part, int nrows, int ncols, float* __restrict__ out) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -513,18 +682,31 @@ extern "C" int ab_moe_router_fwd(const void* x, const float* ln_w, const float* 
     AB_REQUIRE(quant == AB_ROUTER_EXACT || quant == AB_ROUTER_BF16 || quant == AB_ROUTER_FP16, "moe_router_fwd: bad logit rounding mode %d", quant);
     const size_t smem = ((size_t)E * Dm + 32 + WARPS * (2 * E + 1) + 2 * (size_t)Dm) * sizeof(float);
     float* part = (float*)ws;
-#define AB_ROUTER_FWD(TT, EMV)                                                                                          \
+    const int V = dtype == AB_F32 ? 4 : 8;
+    const int nv = (int)ab_ceil_div(Dm, 32 * V);          // 16-byte vectors of the row per lane
+#define AB_ROUTER_LAUNCH(KERNEL)                                                                                        \
     {                                                                                                                    \
-        auto k = router_fwd_kernel<TT, EMV>;                                                                             \
+        auto k = KERNEL;                                                                                                 \
         AB_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         k<<<wl.grid, WARPS * 32, smem, stream>>>((const TT*)x, ln_w, ln_b, eps, Wr, br, noise, noise_scale, lclean,     \
                                                  logits, gates, idx, probs, w, lse, stats_out, part, S, Dm, E, K, quant); \
+    }
+    // the row-in-registers kernel whenever the row fits (hidden size <= 2048 fp32 / 4096 bf16), the streaming one otherwise
+#define AB_ROUTER_FWD(TT_, EMV)                                                                                         \
+    {                                                                                                                    \
+        using TT = TT_;                                                                                                  \
+        if (nv <= 4) AB_ROUTER_LAUNCH((router_fwd_reg_kernel<TT, EMV, 4>))                                               \
+        else if (nv <= 6) AB_ROUTER_LAUNCH((router_fwd_reg_kernel<TT, EMV, 6>))                                          \
+        else if (nv <= 8) AB_ROUTER_LAUNCH((router_fwd_reg_kernel<TT, EMV, 8>))                                          \
+        else if (nv <= 16 && EMV <= 8) AB_ROUTER_LAUNCH((router_fwd_reg_kernel<TT, EMV, 16>))                            \
+        else AB_ROUTER_LAUNCH((router_fwd_kernel<TT, EMV>))                                                              \
     }
     if (dtype == AB_F32) {
         if (E <= 8) AB_ROUTER_FWD(float, 8) else if (E <= 16) AB_ROUTER_FWD(float, 16) else AB_ROUTER_FWD(float, 32)
     } else {
         if (E <= 8) AB_ROUTER_FWD(__nv_bfloat16, 8) else if (E <= 16) AB_ROUTER_FWD(__nv_bfloat16, 16) else AB_ROUTER_FWD(__nv_bfloat16, 32)
     }
+#undef AB_ROUTER_LAUNCH
 #undef AB_ROUTER_FWD
     AB_LAUNCH_CHECK();
     reduce_rows_kernel<<<(unsigned)ab_ceil_div(2 * E + 1, 4), 128, 0, stream>>>(part, wl.grid, 2 * E + 1, aux);
