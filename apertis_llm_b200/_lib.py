@@ -45,6 +45,10 @@ SIGNATURES = {
     "ab_ssm_scan_bwd": (I, [P, I64, P, P, I64, P, I64, P, P, P, P, P, P, I64, P, P, I64, P, I64, P, I64, I, P, P, P, P, SZ,
                             I, I, I, I, I, P]),
     "ab_gemm_row_tile": (I, []),
+    "ab_ep_permute_ln": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, I64, I, I, P]),
+    "ab_ep_unpermute": (I, [P, I, I, I64, P, P, P, P, P, F, P, I, I, I, I, I, P]),
+    "ab_ep_unpermute_bwd": (I, [P, P, P, P, P, P, P, I, I, I64, P, F, P, I, I, I64, I, I, I, P]),
+    "ab_ep_pull_rows": (I, [P, I, I, I64, P, P, P, I, I, P]),
     "ab_moe_router_workspace_bytes": (SZ, [I, I, I]),
     "ab_moe_router_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),
     "ab_moe_topk_from_logits": (I, [P, P, P, P, P, P, I, I, I, P]),

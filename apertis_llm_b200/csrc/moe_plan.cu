@@ -19,6 +19,33 @@ __device__ __forceinline__ void ld4g(const T* p, float* f) {
     }
 }
 
+// ---- expert parallelism over peer memory (NVLink): rows of the permuted layout that live in ANOTHER rank's buffer.
+// The local layout is [W destination ranks][rows_per_peer]; row r belongs to rank d = r / rows_per_peer and sits there in
+// block `rank` (the source) of a [W sources][rows_per_peer] buffer whose peer-mapped base address is base[d].
+// n == 0: plain local buffer.
+constexpr int AB_MAX_PEERS = 16;
+struct PeerRows {
+    unsigned char* base[AB_MAX_PEERS];
+    int n, rows_per_peer, rank;
+};
+__device__ __forceinline__ unsigned char* peer_row(const PeerRows& pr, void* local, int64_t r, int Dm, int es) {
+    if (pr.n == 0) return reinterpret_cast<unsigned char*>(local) + (size_t)r * Dm * es;
+    const int d = (int)(r / pr.rows_per_peer);
+    const int64_t j = r - (int64_t)d * pr.rows_per_peer;
+    return pr.base[d] + ((size_t)pr.rank * pr.rows_per_peer + j) * Dm * es;
+}
+
+// four consecutive elements as ONE store (8 bytes bf16 / 16 bytes fp32): whole sectors also when the row is peer memory
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float a, float b, float c, float d) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+        *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+}
+
 constexpr int PLAN_THREADS = 1024;
 
 // exclusive prefix of a small per-thread count over the CTA (thread order) + CTA total; two __syncthreads
@@ -255,18 +282,15 @@ __global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ 
                                                          const int32_t* __restrict__ tok_of_row,
                                                          const int32_t* __restrict__ tile_expert,
                                                          const int32_t* __restrict__ n_rows, TO* __restrict__ xn, int Dm,
-                                                         int align) {
+                                                         int align, const PeerRows pr) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int total = n_rows[0];
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
         const int tok = tok_of_row[r];
-        TO* orow = xn + (size_t)r * Dm;
+        TO* orow = reinterpret_cast<TO*>(peer_row(pr, xn, r, Dm, (int)sizeof(TO)));     // the owner's receive buffer under EP
         if (tok < 0) {
-            for (int d = lane * 4; d < Dm; d += 128) {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) orow[d + v] = ab_from_float<TO>(0.f);
-            }
+            for (int d = lane * 4; d < Dm; d += 128) st4<TO>(orow + d, 0.f, 0.f, 0.f, 0.f);
             continue;
         }
         const int e = tile_expert[r / align];
@@ -280,10 +304,9 @@ __global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ 
             float xv[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) xv[v] = ab_to_float(irow[d + v]);
-            orow[d + 0] = ab_from_float<TO>(fmaf((xv[0] - mean) * rstd, gv.x, bv.x));
-            orow[d + 1] = ab_from_float<TO>(fmaf((xv[1] - mean) * rstd, gv.y, bv.y));
-            orow[d + 2] = ab_from_float<TO>(fmaf((xv[2] - mean) * rstd, gv.z, bv.z));
-            orow[d + 3] = ab_from_float<TO>(fmaf((xv[3] - mean) * rstd, gv.w, bv.w));
+            const float o0 = fmaf((xv[0] - mean) * rstd, gv.x, bv.x), o1 = fmaf((xv[1] - mean) * rstd, gv.y, bv.y);
+            const float o2 = fmaf((xv[2] - mean) * rstd, gv.z, bv.z), o3 = fmaf((xv[3] - mean) * rstd, gv.w, bv.w);
+            st4<TO>(orow + d, o0, o1, o2, o3);
         }
     }
 }
@@ -292,7 +315,9 @@ __global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ 
 template <typename TY, typename TO>
 __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y, const int32_t* __restrict__ row_of,
                                                         const float* __restrict__ w, const float* __restrict__ res, TO* __restrict__ out,
-                                                        const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int S, int K, int Dm) {
+                                                        const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int S, int K, int Dm,
+                                                        const PeerRows pr, TY* __restrict__ y_copy) {
+    // under EP the rows are read from their owners' buffers over NVLink and a local copy is kept for the backward
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     uint32_t s0 = 0, s1 = 0;
@@ -305,9 +330,11 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y
                 const int r = row_of[(size_t)s * K + k];
                 if (r < 0) continue;
                 const float wk = w[(size_t)s * K + k];
-                const TY* yr = y + (size_t)r * Dm + d;
+                float yv[4];
+                ld4g<TY>(reinterpret_cast<const TY*>(peer_row(pr, const_cast<TY*>(y), r, Dm, (int)sizeof(TY))) + d, yv);
+                if (y_copy) st4<TY>(y_copy + (size_t)r * Dm + d, yv[0], yv[1], yv[2], yv[3]);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[v] += ab_to_float(yr[v]) * wk;   // separate mul and add, as index_add_(y*w)
+                for (int v = 0; v < 4; ++v) acc[v] += yv[v] * wk;   // separate mul and add, as index_add_(y*w)
             }
             // the caller's output dropout and residual add (core.py:918-919) in the same pass
             if (seed) {
@@ -331,7 +358,7 @@ __global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict
                                                             const int32_t* __restrict__ slot_of_row,
                                                             const int32_t* __restrict__ n_rows, TO* __restrict__ dy,
                                                             float* __restrict__ dw_row, const uint32_t* __restrict__ seed, uint32_t thresh,
-                                                            float scale, int K, int Dm) {
+                                                            float scale, int K, int Dm, const PeerRows pr) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int total = n_rows[0];
@@ -339,9 +366,9 @@ __global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict
     if (seed) { s0 = __ldg(seed); s1 = __ldg(seed + 1); }
     for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
         const int tok = tok_of_row[r];
-        TO* orow = dy + (size_t)r * Dm;
+        TO* orow = reinterpret_cast<TO*>(peer_row(pr, dy, r, Dm, (int)sizeof(TO)));     // the owner's receive buffer under EP
         if (tok < 0) {
-            for (int d = lane; d < Dm; d += 32) orow[d] = ab_from_float<TO>(0.f);
+            for (int d = lane * 4; d < Dm; d += 128) st4<TO>(orow + d, 0.f, 0.f, 0.f, 0.f);
             if (lane == 0) dw_row[r] = 0.f;
             continue;
         }
@@ -350,13 +377,15 @@ __global__ void __launch_bounds__(256) unpermute_bwd_kernel(const TD* __restrict
         const TY* yrow = y + (size_t)r * Dm;
         float dot = 0.f;
         for (int d = lane * 4; d < Dm; d += 128) {
+            float o[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
                 float g = ab_to_float(drow[d + v]);
                 if (seed) g = ab_out_keep(s0, s1, (uint64_t)tok * Dm + d + v, thresh) ? g * scale : 0.f;      // the forward's output-dropout mask
                 dot = fmaf(g, ab_to_float(yrow[d + v]), dot);
-                orow[d + v] = ab_from_float<TO>(g * wk);
+                o[v] = g * wk;
             }
+            st4<TO>(orow + d, o[0], o[1], o[2], o[3]);
         }
         dot = ab_warp_sum(dot);
         if (lane == 0) dw_row[r] = dot;
@@ -621,6 +650,34 @@ __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t
 // these kernels are latency-bound streams); tile_expert is looked up through the ratio of the two.
 int work_rows(int row_align) { return row_align % 128 == 0 ? 128 : row_align; }
 
+// out[r,:] = the owner's copy of row r (peer memory), for the rows that hold a token: the pull half of an exchange
+template <typename T>
+__global__ void __launch_bounds__(256) ep_pull_rows_kernel(const int32_t* __restrict__ tok_of_row, const int32_t* __restrict__ n_rows,
+                                                           T* __restrict__ out, int Dm, const PeerRows pr) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int total = n_rows[0];
+    constexpr int V = 16 / (int)sizeof(T);
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
+        if (tok_of_row != nullptr && tok_of_row[r] < 0) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(peer_row(pr, nullptr, r, Dm, (int)sizeof(T)));
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)r * Dm);
+        for (int i = lane; i < Dm / V; i += 32) dst[i] = __ldg(src + i);
+    }
+}
+
+int make_peers(PeerRows* pr, const uint64_t* peer_ptrs, int W, int rank, int64_t rows_per_peer) {
+    memset(pr, 0, sizeof(*pr));
+    if (peer_ptrs == nullptr) return AB_OK;
+    AB_REQUIRE(W >= 1 && W <= AB_MAX_PEERS && rank >= 0 && rank < W && rows_per_peer > 0 && rows_per_peer < (1ll << 31),
+               "ep: bad peer table (W=%d, rank=%d, rows_per_peer=%lld; at most %d ranks)", W, rank, (long long)rows_per_peer, AB_MAX_PEERS);
+    for (int i = 0; i < W; ++i) {
+        AB_REQUIRE(peer_ptrs[i] != 0 && peer_ptrs[i] % 16 == 0, "ep: peer buffer %d is null or not 16-byte aligned", i);
+        pr->base[i] = reinterpret_cast<unsigned char*>(peer_ptrs[i]);
+    }
+    pr->n = W; pr->rows_per_peer = (int)rows_per_peer; pr->rank = rank;
+    return AB_OK;
+}
+
 int rows_grid(int64_t max_rows) {
     const int64_t want = ab_ceil_div(max_rows, 8);
     const int64_t cap = (int64_t)ab_num_sms() * 8;
@@ -671,12 +728,13 @@ extern "C" int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* ac
     return AB_OK;
 }
 
-extern "C" int ab_moe_permute_ln(const void* x, const float* stats, const float* ln_w, const float* ln_b,
-                                 const int32_t* tok_of_row, const int32_t* tile_expert, const int32_t* n_rows, void* xn, int Dm,
-                                 int row_align, int64_t max_rows, int dtype, int out_dtype, cudaStream_t stream) {
+namespace {
+int permute_ln_impl(const void* x, const float* stats, const float* ln_w, const float* ln_b, const int32_t* tok_of_row,
+                    const int32_t* tile_expert, const int32_t* n_rows, void* xn, int Dm, int row_align, int64_t max_rows, int dtype,
+                    int out_dtype, const PeerRows& pr, cudaStream_t stream) {
     AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_permute_ln: hidden size must be a multiple of 4");
     const int grid = rows_grid(max_rows);
-#define AB_PLN(TI, TO) permute_ln_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, stats, ln_w, ln_b, tok_of_row, tile_expert, n_rows, (TO*)xn, Dm, row_align)
+#define AB_PLN(TI, TO) permute_ln_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, stats, ln_w, ln_b, tok_of_row, tile_expert, n_rows, (TO*)xn, Dm, row_align, pr)
     if (dtype == AB_F32 && out_dtype == AB_F32) AB_PLN(float, float);
     else if (dtype == AB_F32 && out_dtype == AB_BF16) AB_PLN(float, __nv_bfloat16);
     else if (dtype == AB_BF16 && out_dtype == AB_BF16) AB_PLN(__nv_bfloat16, __nv_bfloat16);
@@ -686,9 +744,30 @@ extern "C" int ab_moe_permute_ln(const void* x, const float* stats, const float*
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
+}  // namespace
 
-extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
-                                const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
+extern "C" int ab_moe_permute_ln(const void* x, const float* stats, const float* ln_w, const float* ln_b,
+                                 const int32_t* tok_of_row, const int32_t* tile_expert, const int32_t* n_rows, void* xn, int Dm,
+                                 int row_align, int64_t max_rows, int dtype, int out_dtype, cudaStream_t stream) {
+    PeerRows pr;
+    make_peers(&pr, nullptr, 0, 0, 0);
+    return permute_ln_impl(x, stats, ln_w, ln_b, tok_of_row, tile_expert, n_rows, xn, Dm, row_align, max_rows, dtype, out_dtype, pr, stream);
+}
+
+extern "C" int ab_ep_permute_ln(const void* x, const float* stats, const float* ln_w, const float* ln_b,
+                                const int32_t* tok_of_row, const int32_t* tile_expert, const int32_t* n_rows,
+                                const uint64_t* peer_xn, int W, int rank, int64_t rows_per_peer, int Dm, int row_align,
+                                int64_t max_rows, int dtype, int out_dtype, cudaStream_t stream) {
+    AB_REQUIRE(peer_xn != nullptr && max_rows == (int64_t)W * rows_per_peer, "ep_permute_ln: max_rows must equal W * rows_per_peer");
+    PeerRows pr;
+    if (int e = make_peers(&pr, peer_xn, W, rank, rows_per_peer)) return e;
+    return permute_ln_impl(x, stats, ln_w, ln_b, tok_of_row, tile_expert, n_rows, nullptr, Dm, row_align, max_rows, dtype, out_dtype, pr, stream);
+}
+
+namespace {
+int unpermute_impl(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
+                   const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, const PeerRows& pr, void* y_copy,
+                   cudaStream_t stream) {
     AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute: hidden size must be a multiple of 4");
     AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "moe_unpermute: dropout p must be in [0,1) and needs a seed when > 0");
     AB_REQUIRE(res == nullptr || ((uintptr_t)res % 16) == 0, "moe_unpermute: the residual must be 16-byte aligned fp32");
@@ -696,7 +775,7 @@ extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const floa
     const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     const uint32_t* sd = drop_p > 0.f ? drop_seed : nullptr;
     const int grid = rows_grid(S);
-#define AB_UNP(TY, TO) unpermute_kernel<TY, TO><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm)
+#define AB_UNP(TY, TO) unpermute_kernel<TY, TO><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy)
     if (y_dtype == AB_F32 && out_dtype == AB_F32) AB_UNP(float, float);
     else if (y_dtype == AB_BF16 && out_dtype == AB_F32) AB_UNP(__nv_bfloat16, float);
     else if (y_dtype == AB_BF16 && out_dtype == AB_BF16) AB_UNP(__nv_bfloat16, __nv_bfloat16);
@@ -706,18 +785,35 @@ extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const floa
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
+}  // namespace
 
-extern "C" int ab_moe_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row,
-                                    const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, float drop_p,
-                                    const uint32_t* drop_seed, int K, int Dm, int64_t max_rows, int dout_dtype, int y_dtype,
-                                    int dy_dtype, cudaStream_t stream) {
+extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
+                                const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
+    PeerRows pr;
+    make_peers(&pr, nullptr, 0, 0, 0);
+    return unpermute_impl(y, row_of, w, res, out, drop_p, drop_seed, S, K, Dm, y_dtype, out_dtype, pr, nullptr, stream);
+}
+
+extern "C" int ab_ep_unpermute(const uint64_t* peer_y, int W, int rank, int64_t rows_per_peer, void* y_copy, const int32_t* row_of,
+                               const float* w, const float* res, void* out, float drop_p, const uint32_t* drop_seed, int S, int K,
+                               int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
+    AB_REQUIRE(peer_y != nullptr, "ep_unpermute: no peer table");
+    PeerRows pr;
+    if (int e = make_peers(&pr, peer_y, W, rank, rows_per_peer)) return e;
+    return unpermute_impl(nullptr, row_of, w, res, out, drop_p, drop_seed, S, K, Dm, y_dtype, out_dtype, pr, y_copy, stream);
+}
+
+namespace {
+int unpermute_bwd_impl(const void* dout, const void* y, const float* w, const int32_t* tok_of_row, const int32_t* slot_of_row,
+                       const int32_t* n_rows, void* dy, float* dw_row, float drop_p, const uint32_t* drop_seed, int K, int Dm,
+                       int64_t max_rows, int dout_dtype, int y_dtype, int dy_dtype, const PeerRows& pr, cudaStream_t stream) {
     AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute_bwd: hidden size must be a multiple of 4");
     AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "moe_unpermute_bwd: dropout p must be in [0,1) and needs a seed when > 0");
     const uint32_t thresh = (uint32_t)((double)drop_p * 4294967296.0);
     const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     const uint32_t* sd = drop_p > 0.f ? drop_seed : nullptr;
     const int grid = rows_grid(max_rows);
-#define AB_UB(TD, TY, TO) unpermute_bwd_kernel<TD, TY, TO><<<grid, 256, 0, stream>>>((const TD*)dout, (const TY*)y, w, tok_of_row, slot_of_row, n_rows, (TO*)dy, dw_row, sd, thresh, scale, K, Dm)
+#define AB_UB(TD, TY, TO) unpermute_bwd_kernel<TD, TY, TO><<<grid, 256, 0, stream>>>((const TD*)dout, (const TY*)y, w, tok_of_row, slot_of_row, n_rows, (TO*)dy, dw_row, sd, thresh, scale, K, Dm, pr)
     const int key = dout_dtype * 4 + y_dtype * 2 + dy_dtype;
     switch (key) {
         case 0: AB_UB(float, float, float); break;
@@ -731,6 +827,42 @@ extern "C" int ab_moe_unpermute_bwd(const void* dout, const void* y, const float
         default: AB_REQUIRE(false, "moe_unpermute_bwd: bad dtypes");
     }
 #undef AB_UB
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+}  // namespace
+
+extern "C" int ab_moe_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row,
+                                    const int32_t* slot_of_row, const int32_t* n_rows, void* dy, float* dw_row, float drop_p,
+                                    const uint32_t* drop_seed, int K, int Dm, int64_t max_rows, int dout_dtype, int y_dtype,
+                                    int dy_dtype, cudaStream_t stream) {
+    PeerRows pr;
+    make_peers(&pr, nullptr, 0, 0, 0);
+    return unpermute_bwd_impl(dout, y, w, tok_of_row, slot_of_row, n_rows, dy, dw_row, drop_p, drop_seed, K, Dm, max_rows, dout_dtype,
+                              y_dtype, dy_dtype, pr, stream);
+}
+
+extern "C" int ab_ep_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row,
+                                   const int32_t* slot_of_row, const int32_t* n_rows, const uint64_t* peer_dy, int W, int rank,
+                                   int64_t rows_per_peer, float* dw_row, float drop_p, const uint32_t* drop_seed, int K, int Dm,
+                                   int64_t max_rows, int dout_dtype, int y_dtype, int dy_dtype, cudaStream_t stream) {
+    AB_REQUIRE(peer_dy != nullptr && max_rows == (int64_t)W * rows_per_peer, "ep_unpermute_bwd: max_rows must equal W * rows_per_peer");
+    PeerRows pr;
+    if (int e = make_peers(&pr, peer_dy, W, rank, rows_per_peer)) return e;
+    return unpermute_bwd_impl(dout, y, w, tok_of_row, slot_of_row, n_rows, nullptr, dw_row, drop_p, drop_seed, K, Dm, max_rows,
+                              dout_dtype, y_dtype, dy_dtype, pr, stream);
+}
+
+extern "C" int ab_ep_pull_rows(const uint64_t* peer_src, int W, int rank, int64_t rows_per_peer, const int32_t* tok_of_row,
+                               const int32_t* n_rows, void* out, int Dm, int dtype, cudaStream_t stream) {
+    AB_REQUIRE(peer_src != nullptr && out != nullptr && ((uintptr_t)out % 16) == 0, "ep_pull_rows: null or misaligned buffers");
+    AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "ep_pull_rows: bad dtype");
+    AB_REQUIRE(Dm > 0 && Dm % (dtype == AB_F32 ? 4 : 8) == 0, "ep_pull_rows: rows must be whole 16-byte vectors");
+    PeerRows pr;
+    if (int e = make_peers(&pr, peer_src, W, rank, rows_per_peer)) return e;
+    const int grid = rows_grid((int64_t)W * rows_per_peer);
+    if (dtype == AB_F32) ep_pull_rows_kernel<float><<<grid, 256, 0, stream>>>(tok_of_row, n_rows, (float*)out, Dm, pr);
+    else ep_pull_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(tok_of_row, n_rows, (__nv_bfloat16*)out, Dm, pr);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }

@@ -14,10 +14,23 @@ SURVEY.md section 8(e) specifies.  Semantics are those of replicated experts und
   numerics equal the single-GPU path bit for bit;
 * backward mirrors it (dY out, dXn back); expert gradients are sums over all ranks' tokens and are scaled by
   1/W so that they equal what DDP's gradient averaging would give for replicated experts.
+
+Two transports move the rows (APERTIS_B200_EP = peer | nccl | auto, default auto):
+
+* ``peer`` (bf16 path, all ranks on one NVLink / NVSwitch node, torch symmetric memory available): no all-to-all at all.
+  Every rank owns four peer-mapped buffers ``[W sources, El*seg, Dm]``; the permute + LayerNorm kernel writes each row
+  straight into its owner's receive buffer (``ab_ep_permute_ln``), the combine kernel reads each expert-output row from
+  its owner's buffer (``ab_ep_unpermute``), and the backward does the same in the other direction.  The exchanges are
+  thereby part of the kernels on either side of them; what remains between the ranks are five ~7 us barriers per step
+  (``_SymmetricMemory.barrier``) that order writers before the owner's GEMMs and the GEMMs before the readers.
+* ``nccl``: ``all_to_all_single`` between the same kernels (any backend NCCL supports; also the fp32-parity mode).
 """
 from __future__ import annotations
 
+import os
 from typing import List
+
+import ctypes
 
 import torch
 import torch.distributed as dist
@@ -86,6 +99,62 @@ def all_gather_cat(t: torch.Tensor, group) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# peer-memory transport
+# ------------------------------------------------------------------------------------------------
+_EP_MODE = os.environ.get("APERTIS_B200_EP", "auto")
+_peer_cache = {}          # (group name, rank, rows, Dm) -> _PeerState
+_peer_failed = False
+
+
+class _PeerState:
+    """The four peer-mapped row buffers of one (group, shape) and their address tables."""
+
+    def __init__(self, group, rows: int, Dm: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.W = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows, self.Dm = rows, Dm
+        names = ("xn", "y", "dy", "dxn")
+        self.buf, self.hdl, self.ptrs = {}, {}, {}
+        for n in names:
+            t = symm_mem.empty(rows, Dm, dtype=torch.bfloat16, device=device)
+            h = symm_mem.rendezvous(t, group)
+            self.buf[n], self.hdl[n] = t, h
+            self.ptrs[n] = (ctypes.c_uint64 * self.W)(*[int(p) for p in h.buffer_ptrs])
+        self.sync = self.hdl["xn"]
+        self.version = 0          # forwards run on these buffers (a backward must see the version its forward left)
+        self.side = torch.cuda.Stream(device=device)      # the backward's row pull runs beside the weight-gradient GEMMs
+
+    def barrier(self, channel: int = 0):
+        """All ranks' preceding work on the current stream is complete and visible (a kernel: CUDA-graph capturable)."""
+        self.sync.barrier(channel=channel)
+
+
+def _peer_state(group, rows: int, Dm: int, device, owner=0):
+    """Buffers of one layer (`owner`) and shape: a layer's receive buffer doubles as its saved activation, so layers do
+    not share them."""
+    global _peer_failed
+    if _EP_MODE == "nccl" or _peer_failed or dist.get_backend(group) != "nccl":
+        return None
+    key = (id(group), dist.get_rank(group), rows, Dm, device.index, owner)
+    st = _peer_cache.get(key)
+    if st is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                       # buffers are created eagerly (warm-up) and reused by captured steps
+        try:
+            st = _PeerState(group, rows, Dm, device)
+        except Exception as ex:               # no symmetric memory on this platform: NCCL transport
+            if _EP_MODE == "peer":
+                raise
+            _peer_failed = True
+            import warnings
+            warnings.warn(f"apertis_b200 EP: peer-memory transport unavailable ({type(ex).__name__}: {ex}); using NCCL all-to-all")
+            return None
+        _peer_cache[key] = st
+    return st
+
+
+# ------------------------------------------------------------------------------------------------
 # the autograd node
 # ------------------------------------------------------------------------------------------------
 class _MoEExpertsEP(torch.autograd.Function):
@@ -114,19 +183,32 @@ class _MoEExpertsEP(torch.autograd.Function):
         plan = ops.moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"], fixed_seg=seg)
         rows_local = E * seg                                  # == W * El * seg
         cdt = torch.float32 if precise else torch.bfloat16
-        xn = torch.empty(rows_local, Dm, dtype=cdt, device=dev)
-        call("ab_moe_permute_ln", ptr(x2), ptr(r["stats"]), ptr(ln_w_full), ptr(ln_b_full), ptr(plan["tok_of_row"]),
-             ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(xn), Dm, ROW_ALIGN, rows_local, dt(x2), dt(cdt), stream_ptr())
-        # ---- dispatch
-        xr_w, xr_wait = all_to_all_equal_start(xn.view(W, El * seg, Dm), group)
-        # while the rows travel: receive-side plan and the bf16 weight shadows
+        peer = None if precise else _peer_state(group, rows_local, Dm, dev, cfg.get("_owner", 0))
+        rank = dist.get_rank(group)
         rplan = dict(tile_expert=recv_tile_expert(W, El, seg, dev),
                      n_rows=torch.full((2,), rows_local, dtype=torch.int32, device=dev),
                      seg_off=local_seg_off(El, seg, dev))
-        w1 = ops._split_cols(W1.view(El * I, Dm), 1) if precise else ops._cast_bf16(W1)
-        w2 = ops._split_cols(W2.view(El * Dm, I), 1) if precise else ops._cast_bf16(W2)
-        xr_wait()
-        xr = xr_w.view(rows_local, Dm)
+        if peer is not None:
+            # ---- dispatch fused into permute + LayerNorm: every row goes straight into its owner's receive buffer
+            peer.version += 1
+            peer.barrier(0)                   # the owners are done with last step's rows
+            call("ab_ep_permute_ln", ptr(x2), ptr(r["stats"]), ptr(ln_w_full), ptr(ln_b_full), ptr(plan["tok_of_row"]),
+                 ptr(plan["tile_expert"]), ptr(plan["n_rows"]), peer.ptrs["xn"], W, rank, El * seg, Dm, ROW_ALIGN, rows_local,
+                 dt(x2), dt(cdt), stream_ptr())
+            w1, w2 = ops._cast_bf16(W1), ops._cast_bf16(W2)      # before the barrier: absorbs the ranks' skew
+            peer.barrier(1)                   # every source has written its rows
+            xr = peer.buf["xn"]
+        else:
+            xn = torch.empty(rows_local, Dm, dtype=cdt, device=dev)
+            call("ab_moe_permute_ln", ptr(x2), ptr(r["stats"]), ptr(ln_w_full), ptr(ln_b_full), ptr(plan["tok_of_row"]),
+                 ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(xn), Dm, ROW_ALIGN, rows_local, dt(x2), dt(cdt), stream_ptr())
+            # ---- dispatch
+            xr_w, xr_wait = all_to_all_equal_start(xn.view(W, El * seg, Dm), group)
+            # while the rows travel: the bf16 weight shadows
+            w1 = ops._split_cols(W1.view(El * I, Dm), 1) if precise else ops._cast_bf16(W1)
+            w2 = ops._split_cols(W2.view(El * Dm, I), 1) if precise else ops._cast_bf16(W2)
+            xr_wait()
+            xr = xr_w.view(rows_local, Dm)
         if precise:
             a1, k1 = ops._split_cols(xr, 0), 3 * Dm
         else:
@@ -139,11 +221,19 @@ class _MoEExpertsEP(torch.autograd.Function):
             a2, k2 = ops._split_cols(h, 0), 3 * I
         else:
             a2, k2 = h, I
-        yr = ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
-        # ---- combine
-        y = all_to_all_equal(yr.view(W, El * seg, Dm), group).view(rows_local, Dm)
         out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
-        call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None, S, K, Dm, dt(y), dt(out), stream_ptr())
+        if peer is not None:
+            ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt, out=peer.buf["y"])
+            # ---- combine fused into the un-permutation: every row is read from its owner's buffer
+            peer.barrier(2)                   # every owner has finished its expert outputs
+            y = torch.empty(rows_local, Dm, dtype=cdt, device=dev)
+            call("ab_ep_unpermute", peer.ptrs["y"], W, rank, El * seg, ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None,
+                 S, K, Dm, dt(cdt), dt(out), stream_ptr())
+        else:
+            yr = ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
+            # ---- combine
+            y = all_to_all_equal(yr.view(W, El * seg, Dm), group).view(rows_local, Dm)
+            call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None, S, K, Dm, dt(y), dt(out), stream_ptr())
         aux = r["aux"]
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
         lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
@@ -152,6 +242,8 @@ class _MoEExpertsEP(torch.autograd.Function):
         ctx.drop_seed = drop_seed
         ctx.shadows = None if precise else (w1, w2)
         ctx.group = group
+        ctx.peer = peer
+        ctx.peer_version = peer.version if peer is not None else 0
         ctx.plan = {k: v for k, v in plan.items() if torch.is_tensor(v)}
         ctx.rplan = rplan
         ctx.save_for_backward(x2, rn_w, rn_b, Wr, br, ln_w_full, W1, W2, noise if use_noise else None, r["stats"], r["gates"],
@@ -170,11 +262,24 @@ class _MoEExpertsEP(torch.autograd.Function):
         dev = x2.device
         f32 = dict(dtype=torch.float32, device=dev)
         dout = dout.contiguous()
-        dy = torch.empty(rows, Dm, dtype=cdt, device=dev)
+        peer = ctx.peer
+        rank = dist.get_rank(group)
         dw_row = torch.empty(rows, **f32)
-        call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
-             ptr(dy), ptr(dw_row), 0.0, None, K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
-        dyr = all_to_all_equal(dy.view(W, El * seg, Dm), group).view(rows, Dm)
+        if peer is not None and ctx.peer_version != peer.version:
+            raise RuntimeError("apertis_b200 EP (peer transport): this layer ran another forward before the backward of this one; "
+                               "the peer-mapped receive buffer doubles as the saved activation, so one step per layer can be in "
+                               "flight.  Set APERTIS_B200_EP=nccl for forward-forward-backward-backward schedules.")
+        if peer is not None:
+            # dY rows go straight into their owners' receive buffers
+            call("ab_ep_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
+                 peer.ptrs["dy"], W, rank, El * seg, ptr(dw_row), 0.0, None, K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+            peer.barrier(3)
+            dyr = peer.buf["dy"]
+        else:
+            dy = torch.empty(rows, Dm, dtype=cdt, device=dev)
+            call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
+                 ptr(dy), ptr(dw_row), 0.0, None, K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+            dyr = all_to_all_equal(dy.view(W, El * seg, Dm), group).view(rows, Dm)
         lseg = rplan["seg_off"]
         stride = El * seg
         if precise:
@@ -195,8 +300,21 @@ class _MoEExpertsEP(torch.autograd.Function):
             w1b, w2b = ctx.shadows
             dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
-            dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)
-            dxn_w, dxn_wait = all_to_all_equal_start(dxnr.view(W, El * seg, Dm), group)
+            if peer is not None:
+                ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16, out=peer.buf["dxn"])
+                peer.barrier(4)               # every owner's input-gradient rows are complete
+                # the sources pull their rows over NVLink on a side stream while the weight gradients are computed
+                dxn_w = torch.empty(rows, Dm, dtype=torch.bfloat16, device=dev)
+                main = torch.cuda.current_stream(dev)
+                peer.side.wait_stream(main)
+                with torch.cuda.stream(peer.side):
+                    call("ab_ep_pull_rows", peer.ptrs["dxn"], W, rank, El * seg, ptr(plan["tok_of_row"]), ptr(plan["n_rows"]), ptr(dxn_w), Dm,
+                         dt(dxn_w), stream_ptr(dev))
+                dxn_w.record_stream(peer.side)
+                dxn_wait = lambda: main.wait_stream(peer.side)
+            else:
+                dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)
+                dxn_w, dxn_wait = all_to_all_equal_start(dxnr.view(W, El * seg, Dm), group)
             dW2 = ops.grouped_gemm_tn(dyr, h, lseg, Dm, I, El, nsrc=W, src_stride=stride)
             dW1 = ops.grouped_gemm_tn(dhpre, xr, lseg, I, Dm, El, nsrc=W, src_stride=stride)
         db2 = torch.empty(El, Dm, **f32)
@@ -220,7 +338,6 @@ class _MoEExpertsEP(torch.autograd.Function):
              stream_ptr())
         dln = torch.stack([dln_w, dln_b])                      # [2, E, Dm]: sum over source ranks, keep the local experts
         dln_work = dist.all_reduce(dln, group=group, async_op=True)        # overlaps the router backward below
-        rank = dist.get_rank(group)
         inv = 1.0 / W
         training = cfg["training"]
         g_lb = (dlb.float() * (cfg["lb_coef"] * E / S)) if (training and cfg["lb_coef"] > 0) else torch.zeros((), **f32)
@@ -245,6 +362,7 @@ class _MoEExpertsEP(torch.autograd.Function):
 
 def moe_experts_ep(module, x2, noise, noise_scale, cfg):
     """Entry used by AdaptiveExpertSystem.forward when an expert-parallel group is set."""
+    cfg["_owner"] = id(module)
     return _MoEExpertsEP.apply(x2, module.router_norm.weight, module.router_norm.bias, module.router.weight, module.router.bias,
                                noise, noise_scale, module.expert_ln_weight, module.expert_ln_bias, module.expert_w1,
                                module.expert_b1, module.expert_w2, module.expert_b2, cfg, module.ep_group)

@@ -716,10 +716,13 @@ def _split_rows(t2d, which, seg_off=None, G=1, rows_per_group=0):
 
 
 def grouped_gemm(mode, A, W, plan, N, K, E, *, bias=None, aux=None, epi=_lib.EPI_NONE, act=0, out_dtype=torch.bfloat16,
-                 want_c2=False, drop_p=0.0, drop_seed=None):
-    """C = epi(A @ W[e]^T) ('nt', W [E,N,K]) or epi(A @ W[e]) ('nn', W [E,K,N]) over the permuted rows."""
+                 want_c2=False, drop_p=0.0, drop_seed=None, out=None):
+    """C = epi(A @ W[e]^T) ('nt', W [E,N,K]) or epi(A @ W[e]) ('nn', W [E,K,N]) over the permuted rows.
+    out: write C into this [max_rows, N] tensor (e.g. a peer-mapped buffer) instead of a fresh one."""
     max_rows = A.shape[0]
-    c = torch.empty(max_rows, N, dtype=out_dtype, device=A.device)
+    if out is not None:
+        assert out.shape == (max_rows, N) and out.dtype == out_dtype and out.is_contiguous()
+    c = out if out is not None else torch.empty(max_rows, N, dtype=out_dtype, device=A.device)
     c2 = torch.empty(max_rows, N, dtype=out_dtype, device=A.device) if want_c2 else None
     call("ab_grouped_gemm_" + mode, ptr(A), ptr(W), ptr(bias), ptr(aux), ptr(c), ptr(c2), ptr(plan["tile_expert"]),
          ptr(plan["n_rows"]), max_rows, N, K, E, epi, act, dt(out_dtype), float(drop_p), ptr(drop_seed), stream_ptr())

@@ -132,7 +132,12 @@ def run_gpu(rank, world, args):
         bad = {k: v for k, v in errs.items() if not v < tol}
         assert not bad, (rank, autocast, bad)
         worst = max(worst, max(errs.values()))
-    print(f"rank {rank}: gpu ep ok, world {world}, worst rel err {worst:.2e}")
+    transport = os.environ.get("APERTIS_B200_EP", "auto")
+    if transport == "peer":
+        assert ep._peer_cache, "the peer-memory transport was requested but never used"
+    if transport == "nccl":
+        assert not ep._peer_cache
+    print(f"rank {rank}: gpu ep ok, world {world}, transport {transport} ({len(ep._peer_cache)} peer buffer sets), worst rel err {worst:.2e}")
 
 
 def main():
