@@ -311,42 +311,66 @@ __global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ 
     }
 }
 
-// out[s,:] = sum_k w[s,k] * y[row_of[s,k],:]   (warp per token, fixed slot order)
-template <typename TY, typename TO>
+// out[s,:] = sum_k w[s,k] * y[row_of[s,k],:]   (warp per token, fixed slot order).  The rows may live in other ranks' memory
+// (NVLink latency of microseconds), so the loads of a chunk - 4 elements of every one of the K rows, for two chunks - are
+// all issued before the first is used.
+template <typename TY, typename TO, int KM>
 __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y, const int32_t* __restrict__ row_of,
                                                         const float* __restrict__ w, const float* __restrict__ res, TO* __restrict__ out,
                                                         const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int S, int K, int Dm,
                                                         const PeerRows pr, TY* __restrict__ y_copy) {
     // under EP the rows are read from their owners' buffers over NVLink and a local copy is kept for the backward
+    constexpr int DU = 8 / KM;           // chunks in flight (KM = upper bound of the experts per token)
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     uint32_t s0 = 0, s1 = 0;
     if (seed) { s0 = __ldg(seed); s1 = __ldg(seed + 1); }
     for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
         TO* orow = out + (size_t)s * Dm;
-        for (int d = lane * 4; d < Dm; d += 128) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int k = 0; k < K; ++k) {
-                const int r = row_of[(size_t)s * K + k];
-                if (r < 0) continue;
-                const float wk = w[(size_t)s * K + k];
-                float yv[4];
-                ld4g<TY>(reinterpret_cast<const TY*>(peer_row(pr, const_cast<TY*>(y), r, Dm, (int)sizeof(TY))) + d, yv);
-                if (y_copy) st4<TY>(y_copy + (size_t)r * Dm + d, yv[0], yv[1], yv[2], yv[3]);
+        const TY* rows[KM];
+        float wk[KM];
+        int rid[KM];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[v] += yv[v] * wk;   // separate mul and add, as index_add_(y*w)
-            }
-            // the caller's output dropout and residual add (core.py:918-919) in the same pass
-            if (seed) {
+        for (int k = 0; k < KM; ++k) {
+            rid[k] = k < K ? row_of[(size_t)s * K + k] : -1;
+            wk[k] = rid[k] >= 0 ? w[(size_t)s * K + k] : 0.f;
+            rows[k] = rid[k] >= 0 ? reinterpret_cast<const TY*>(peer_row(pr, const_cast<TY*>(y), rid[k], Dm, (int)sizeof(TY))) : nullptr;
+        }
+        for (int d0 = lane * 4; d0 < Dm; d0 += 128 * DU) {
+            float yv[DU][KM][4];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[v] = ab_out_keep(s0, s1, (uint64_t)s * Dm + d + v, thresh) ? acc[v] * scale : 0.f;
-            }
-            if (res) {
-                const float4 rr = *reinterpret_cast<const float4*>(res + (size_t)s * Dm + d);
-                acc[0] += rr.x; acc[1] += rr.y; acc[2] += rr.z; acc[3] += rr.w;
+            for (int u = 0; u < DU; ++u) {
+                const int d = d0 + u * 128;
+#pragma unroll
+                for (int k = 0; k < KM; ++k) {
+                    if (k < K && rows[k] != nullptr && d < Dm) ld4g<TY>(rows[k] + d, yv[u][k]);
+                    else { yv[u][k][0] = yv[u][k][1] = yv[u][k][2] = yv[u][k][3] = 0.f; }
+                }
             }
 #pragma unroll
-            for (int v = 0; v < 4; ++v) orow[d + v] = ab_from_float<TO>(acc[v]);
+            for (int u = 0; u < DU; ++u) {
+                const int d = d0 + u * 128;
+                if (d >= Dm) break;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < KM; ++k) {
+                    if (k < K && rows[k] != nullptr) {
+                        if (y_copy) st4<TY>(y_copy + (size_t)rid[k] * Dm + d, yv[u][k][0], yv[u][k][1], yv[u][k][2], yv[u][k][3]);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[v] += yv[u][k][v] * wk[k];   // separate mul and add, as index_add_(y*w)
+                    }
+                }
+                // the caller's output dropout and residual add (core.py:918-919) in the same pass
+                if (seed) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[v] = ab_out_keep(s0, s1, (uint64_t)s * Dm + d + v, thresh) ? acc[v] * scale : 0.f;
+                }
+                if (res) {
+                    const float4 rr = *reinterpret_cast<const float4*>(res + (size_t)s * Dm + d);
+                    acc[0] += rr.x; acc[1] += rr.y; acc[2] += rr.z; acc[3] += rr.w;
+                }
+                st4<TO>(orow + d, acc[0], acc[1], acc[2], acc[3]);
+            }
         }
     }
 }
@@ -775,11 +799,17 @@ int unpermute_impl(const void* y, const int32_t* row_of, const float* w, const f
     const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
     const uint32_t* sd = drop_p > 0.f ? drop_seed : nullptr;
     const int grid = rows_grid(S);
-#define AB_UNP(TY, TO) unpermute_kernel<TY, TO><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy)
-    if (y_dtype == AB_F32 && out_dtype == AB_F32) AB_UNP(float, float);
-    else if (y_dtype == AB_BF16 && out_dtype == AB_F32) AB_UNP(__nv_bfloat16, float);
-    else if (y_dtype == AB_BF16 && out_dtype == AB_BF16) AB_UNP(__nv_bfloat16, __nv_bfloat16);
-    else if (y_dtype == AB_F32 && out_dtype == AB_BF16) AB_UNP(float, __nv_bfloat16);
+#define AB_UNP(TY, TO)                                                                                                          \
+    {                                                                                                                            \
+        if (K <= 2) unpermute_kernel<TY, TO, 2><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy); \
+        else if (K <= 4) unpermute_kernel<TY, TO, 4><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy); \
+        else unpermute_kernel<TY, TO, 8><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy); \
+    }
+    AB_REQUIRE(K >= 1 && K <= 8, "moe_unpermute: experts_per_token must be in [1, 8]");
+    if (y_dtype == AB_F32 && out_dtype == AB_F32) AB_UNP(float, float)
+    else if (y_dtype == AB_BF16 && out_dtype == AB_F32) AB_UNP(__nv_bfloat16, float)
+    else if (y_dtype == AB_BF16 && out_dtype == AB_BF16) AB_UNP(__nv_bfloat16, __nv_bfloat16)
+    else if (y_dtype == AB_F32 && out_dtype == AB_BF16) AB_UNP(float, __nv_bfloat16)
     else AB_REQUIRE(false, "moe_unpermute: bad dtypes");
 #undef AB_UNP
     AB_LAUNCH_CHECK();

@@ -102,6 +102,7 @@ def all_gather_cat(t: torch.Tensor, group) -> torch.Tensor:
 # peer-memory transport
 # ------------------------------------------------------------------------------------------------
 _EP_MODE = os.environ.get("APERTIS_B200_EP", "auto")
+_EP_PULL = os.environ.get("APERTIS_B200_EP_PULL", "copy")        # copy (DMA engines) | kernel (ab_ep_pull_rows)
 _peer_cache = {}          # (group name, rank, rows, Dm) -> _PeerState
 _peer_failed = False
 
@@ -122,6 +123,9 @@ class _PeerState:
             self.buf[n], self.hdl[n] = t, h
             self.ptrs[n] = (ctypes.c_uint64 * self.W)(*[int(p) for p in h.buffer_ptrs])
         self.sync = self.hdl["xn"]
+        rpp = rows // self.W
+        # every rank's input-gradient buffer as a local tensor [W sources, rows per peer, Dm] (peer-mapped views)
+        self.remote_dxn = [self.hdl["dxn"].get_buffer(d, (self.W, rpp, Dm), torch.bfloat16) for d in range(self.W)]
         self.version = 0          # forwards run on these buffers (a backward must see the version its forward left)
         self.side = torch.cuda.Stream(device=device)      # the backward's row pull runs beside the weight-gradient GEMMs
 
@@ -172,10 +176,19 @@ class _MoEExpertsEP(torch.autograd.Function):
         x2 = x2.contiguous()
         f = lambda t: t.float().contiguous()
         rn_w, rn_b, Wr, br, b1, b2, W1, W2 = map(f, (rn_w, rn_b, Wr, br, b1, b2, W1, W2))
-        # every source rank normalises the rows it dispatches: all experts' LayerNorm parameters, one collective for both
-        ln_wb = all_gather_cat(torch.stack([f(ln_w), f(ln_b)]).unsqueeze(0), group)           # [W, 2, El, Dm]
-        ln_w_full = ln_wb[:, 0].reshape(E, Dm).contiguous()   # [E, Dm]
-        ln_b_full = ln_wb[:, 1].reshape(E, Dm).contiguous()
+        # every source rank normalises the rows it dispatches: all experts' LayerNorm parameters, one collective for both,
+        # repeated only when the parameters have changed (in-place optimizer updates bump the version counters; every rank
+        # sees the same sequence of updates, so all ranks gather, or reuse, together)
+        ln_key = (ln_w._version, ln_b._version, ln_w.data_ptr(), ln_b.data_ptr(), E, Dm)
+        ln_cache = cfg.get("_ln_cache")
+        if ln_cache is not None and ln_cache.get("key") == ln_key:
+            ln_w_full, ln_b_full = ln_cache["val"]
+        else:
+            ln_wb = all_gather_cat(torch.stack([f(ln_w), f(ln_b)]).unsqueeze(0), group)           # [W, 2, El, Dm]
+            ln_w_full = ln_wb[:, 0].reshape(E, Dm).contiguous()   # [E, Dm]
+            ln_b_full = ln_wb[:, 1].reshape(E, Dm).contiguous()
+            if ln_cache is not None:
+                ln_cache["key"], ln_cache["val"] = ln_key, (ln_w_full, ln_b_full)
         use_noise = noise is not None and noise_scale is not None
         r = ops.moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
                           f(noise_scale) if use_noise else None, K, cfg.get("quant", _lib.ROUTER_EXACT))
@@ -308,8 +321,15 @@ class _MoEExpertsEP(torch.autograd.Function):
                 main = torch.cuda.current_stream(dev)
                 peer.side.wait_stream(main)
                 with torch.cuda.stream(peer.side):
-                    call("ab_ep_pull_rows", peer.ptrs["dxn"], W, rank, El * seg, ptr(plan["tok_of_row"]), ptr(plan["n_rows"]), ptr(dxn_w), Dm,
-                         dt(dxn_w), stream_ptr(dev))
+                    if _EP_PULL == "kernel":
+                        call("ab_ep_pull_rows", peer.ptrs["dxn"], W, rank, El * seg, ptr(plan["tok_of_row"]), ptr(plan["n_rows"]), ptr(dxn_w), Dm,
+                             dt(dxn_w), stream_ptr(dev))
+                    else:
+                        # block copies by the copy engines: no SM is taken from the persistent weight-gradient GEMMs
+                        dst = dxn_w.view(W, El * seg, Dm)
+                        for i in range(W):
+                            d = (rank + i) % W                    # start with the local block, spread the peers
+                            dst[d].copy_(peer.remote_dxn[d][rank])
                 dxn_w.record_stream(peer.side)
                 dxn_wait = lambda: main.wait_stream(peer.side)
             else:
@@ -363,6 +383,7 @@ class _MoEExpertsEP(torch.autograd.Function):
 def moe_experts_ep(module, x2, noise, noise_scale, cfg):
     """Entry used by AdaptiveExpertSystem.forward when an expert-parallel group is set."""
     cfg["_owner"] = id(module)
+    cfg["_ln_cache"] = module.__dict__.setdefault("_ep_ln_cache", {})
     return _MoEExpertsEP.apply(x2, module.router_norm.weight, module.router_norm.bias, module.router.weight, module.router.bias,
                                noise, noise_scale, module.expert_ln_weight, module.expert_ln_bias, module.expert_w1,
                                module.expert_b1, module.expert_w2, module.expert_b2, cfg, module.ep_group)

@@ -24,7 +24,7 @@ def test_ep_host_logic_gloo_world2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["nccl", "peer"])
+@pytest.mark.parametrize("transport", ["nccl", "peer", "peer+pull_kernel"])
 def test_ep_matches_local_experts_nccl(transport):
     """EP layer against the same layer with every expert local, on >= 2 GPUs, through both row transports: NCCL all-to-all
     and the peer-memory kernels (rows written into / read from the owners' buffers over NVLink, ab_ep_*)."""
@@ -32,6 +32,7 @@ def test_ep_matches_local_experts_nccl(transport):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
-    res = _torchrun(world, "gpu", 29612 if transport == "nccl" else 29613, env_extra={"APERTIS_B200_EP": transport})
+    env = {"APERTIS_B200_EP": transport.split("+")[0], "APERTIS_B200_EP_PULL": "kernel" if "pull_kernel" in transport else "copy"}
+    res = _torchrun(world, "gpu", {"nccl": 29612, "peer": 29613}.get(transport, 29614), env_extra=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("gpu ep ok") == world
