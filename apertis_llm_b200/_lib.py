@@ -66,7 +66,8 @@ SIGNATURES = {
     "ab_moe_router_bwd": (I, [P] * 24 + [SZ, I, I, I, I, I, P]),
     "ab_grouped_gemm_nt": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, F, P, P]),
     "ab_grouped_gemm_nn": (I, [P, P, P, P, P, P, P, P, I64, I, I, I, I, I, I, F, P, P]),
-    "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, I, I64, P]),
+    "ab_grouped_gemm_tn_workspace_bytes": (SZ, [I, I, I, I]),
+    "ab_grouped_gemm_tn": (I, [P, P, P, P, I64, I, I, I, I, I64, P, SZ, P]),
     "ab_dense_gemm_nt": (I, [P, P, P, P, P, I64, I, I, I, I, P]),
     "ab_dense_gemm_nn": (I, [P, P, P, P, P, I64, I, I, I, I, P]),
     "ab_dense_gemm_tn_workspace_bytes": (SZ, [I64, I, I]),

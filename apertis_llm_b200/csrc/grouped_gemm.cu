@@ -48,6 +48,8 @@ struct GemmParams {
     int num_n_tiles, num_m_tiles;   // num_m_tiles: MODE_TN, 256-row tiles of the output
     int epi, act, c_f32;
     int tn_nsrc;             // MODE_TN: an expert's rows are nsrc blocks [src*stride + seg_off[e], src*stride + seg_off[e+1])
+    int tn_e_real;           // MODE_TN split over the source blocks: E counts (slice, expert) pairs, expert = index % tn_e_real,
+                             // slice = index / tn_e_real covers tn_nsrc consecutive blocks; 0 = no split
     int64_t tn_src_stride;
     // dense use (one "expert", plain row-major matrices; tile_expert / n_rows / seg_off are NULL):
     int64_t rows_valid;      // MODE_NT / MODE_NN: rows >= rows_valid are never stored (the last row tile may be partial)
@@ -282,8 +284,15 @@ __device__ __forceinline__ Tile decode_tile(const GemmParams& p, int tile) {
         t.e = tile / per_e;
         const int rem = tile % per_e;
         t.m_pair = rem / p.num_n_tiles; t.n_tile = rem % p.num_n_tiles;
-        t.k_begin = p.seg_off != nullptr ? p.seg_off[t.e] : (int)(t.e * p.tn_split);
-        t.nk = p.seg_off != nullptr ? p.tn_nsrc * ((p.seg_off[t.e + 1] - t.k_begin) / BK) : dense_tn_blocks(p, t.e);
+        if (p.seg_off != nullptr) {
+            const int e = p.tn_e_real > 0 ? t.e % p.tn_e_real : t.e, slice = p.tn_e_real > 0 ? t.e / p.tn_e_real : 0;
+            const int s0 = p.seg_off[e];
+            t.k_begin = s0 + (int)((int64_t)slice * p.tn_nsrc * p.tn_src_stride);
+            t.nk = p.tn_nsrc * ((p.seg_off[e + 1] - s0) / BK);
+        } else {
+            t.k_begin = (int)(t.e * p.tn_split);
+            t.nk = dense_tn_blocks(p, t.e);
+        }
     } else {
         t.m_pair = tile / p.num_n_tiles; t.n_tile = tile % p.num_n_tiles;
         t.e = p.tile_expert != nullptr ? p.tile_expert[t.m_pair] : 0;
@@ -759,8 +768,27 @@ extern "C" int ab_grouped_gemm_nn(const void* A, const void* W, const float* bia
     return gemm_rows(MODE_NN, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, drop_p, drop_seed, stream);
 }
 
+namespace {
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int nsplit);
+// Few output tiles and many source blocks (expert parallelism with one or two local experts): the contraction is cut over
+// the source blocks so that every CTA pair has work; slices = the largest divisor of nsrc that still fits one wave.
+int grouped_tn_slices(int M, int N, int E, int nsrc) {
+    const int tiles = (int)(E * ab_ceil_div(M, PM) * ab_ceil_div(N, pick_bn(N, true)));
+    const int pairs = ab_num_sms() / 2;
+    int best = 1;
+    for (int s = 2; s <= nsrc; ++s)
+        if (nsrc % s == 0 && tiles * s <= pairs + pairs / 8) best = s;
+    return best;
+}
+}  // namespace
+
+extern "C" size_t ab_grouped_gemm_tn_workspace_bytes(int M, int N, int E, int nsrc) {
+    const int slices = nsrc > 1 ? grouped_tn_slices(M, N, E, nsrc) : 1;
+    return slices > 1 ? (size_t)slices * E * M * N * sizeof(float) : 0;
+}
+
 extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
-                                  int N, int E, int nsrc, int64_t src_stride, cudaStream_t stream) {
+                                  int N, int E, int nsrc, int64_t src_stride, void* ws, size_t ws_bytes, cudaStream_t stream) {
     AB_REQUIRE(nsrc >= 1 && (nsrc == 1 || (src_stride > 0 && src_stride % BK == 0 && nsrc * src_stride <= max_rows)),
                "grouped_gemm_tn: bad source blocking nsrc=%d stride=%lld", nsrc, (long long)src_stride);
     AB_REQUIRE(max_rows > 0 && max_rows % BK == 0, "grouped_gemm_tn: max_rows must be a positive multiple of %d", BK);
@@ -773,11 +801,23 @@ extern "C" int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, cons
     p.num_m_tiles = (int)ab_ceil_div(M, PM);
     p.seg_off = seg_off; p.c_f32 = 1; p.epi = AB_EPI_NONE; p.cw = Cw;
     p.tn_nsrc = nsrc; p.tn_src_stride = src_stride;
-    AB_REQUIRE(((uintptr_t)Cw % 16) == 0, "grouped_gemm_tn: output pointer must be 16-byte aligned");
+    AB_REQUIRE(((uintptr_t)Cw % 16) == 0 && ((uintptr_t)ws % 16) == 0, "grouped_gemm_tn: output / workspace must be 16-byte aligned");
+    int slices = nsrc > 1 ? grouped_tn_slices(M, N, E, nsrc) : 1;
+    if (slices > 1 && (ws == nullptr || ws_bytes < (size_t)slices * E * M * N * sizeof(float))) slices = 1;     // no workspace: unsplit
+    if (slices > 1) {
+        p.tn_e_real = E; p.E = E * slices; p.tn_nsrc = nsrc / slices;
+        p.cw = reinterpret_cast<float*>(ws);                 // [slice][expert][M][N] partial products
+    }
     CUtensorMap ta, tb;
     if (int e = make_map2(&ta, A, (uint64_t)M, (uint64_t)max_rows, 64, BK)) return e;
     if (int e = make_map2(&tb, Bm, (uint64_t)N, (uint64_t)max_rows, 64, BK)) return e;
-    return launch<MODE_TN>(ta, tb, p, (int64_t)E * p.num_m_tiles * p.num_n_tiles, stream);
+    if (int e = launch<MODE_TN>(ta, tb, p, (int64_t)p.E * p.num_m_tiles * p.num_n_tiles, stream)) return e;
+    if (slices > 1) {
+        const int64_t n = (int64_t)E * M * N;
+        splitk_reduce_kernel<<<(unsigned)ab_ceil_div(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(ws), Cw, n, slices);
+        AB_LAUNCH_CHECK();
+    }
+    return AB_OK;
 }
 
 // ---- dense GEMMs on the same kernel (one "expert", plain row-major matrices): the SSM layer's projections

@@ -732,7 +732,9 @@ def grouped_gemm(mode, A, W, plan, N, K, E, *, bias=None, aux=None, epi=_lib.EPI
 def grouped_gemm_tn(A, Bm, seg_off, M, N, E, nsrc=1, src_stride=0):
     """Cw[e] = A[seg e]^T @ Bm[seg e]  -> fp32 [E, M, N]; with nsrc > 1 an expert's rows are nsrc strided blocks."""
     out = torch.empty(E, M, N, dtype=torch.float32, device=A.device)
-    call("ab_grouped_gemm_tn", ptr(A), ptr(Bm), ptr(out), ptr(seg_off), A.shape[0], M, N, E, nsrc, src_stride, stream_ptr())
+    nws = query("ab_grouped_gemm_tn_workspace_bytes", M, N, E, nsrc)        # > 0: the contraction is cut over the source blocks
+    ws = torch.empty(nws, dtype=torch.uint8, device=A.device) if nws else None
+    call("ab_grouped_gemm_tn", ptr(A), ptr(Bm), ptr(out), ptr(seg_off), A.shape[0], M, N, E, nsrc, src_stride, ptr(ws), nws, stream_ptr())
     return out
 
 

@@ -301,9 +301,12 @@ int ab_grouped_gemm_nn(const void* A, const void* W, const float* bias, const vo
                        const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
                        int epi, int act, int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream);
 /* nsrc > 1 (expert-parallel receive layout): expert e's rows are the nsrc blocks
- * [s*src_stride + seg_off[e], s*src_stride + seg_off[e+1]), s = 0..nsrc-1. */
+ * [s*src_stride + seg_off[e], s*src_stride + seg_off[e+1]), s = 0..nsrc-1.  With few local experts the output has fewer
+ * tiles than the chip has CTA pairs: given a workspace of ab_grouped_gemm_tn_workspace_bytes (may be 0) the contraction is
+ * cut over the source blocks and the partial products are summed in a fixed order.  ws may be NULL (never split). */
+size_t ab_grouped_gemm_tn_workspace_bytes(int M, int N, int E, int nsrc);
 int ab_grouped_gemm_tn(const void* A, const void* Bm, float* Cw, const int32_t* seg_off, int64_t max_rows, int M,
-                       int N, int E, int nsrc, int64_t src_stride, cudaStream_t stream);
+                       int N, int E, int nsrc, int64_t src_stride, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 /* ---- dense GEMMs on the same tcgen05 kernel: the SSM layer's projections (core.py:366-367 in_proj_x | in_proj_z,
  * :376-383 x_param_proj with dt_proj_head folded in, :397 out_proj) and their autograd.  Row-major bf16 operands,

@@ -357,6 +357,38 @@ def test_grouped_gemm_tn(M, N, counts):
         assert rel_err(out[e], ref) < 2e-5 if counts[e] else float(out[e].abs().max()) == 0.0, e
 
 
+@pytest.mark.parametrize("W,El,M,N", [(8, 1, 704, 2816), (8, 1, 2816, 704), (4, 2, 704, 1408), (2, 4, 160, 96)])
+def test_grouped_gemm_tn_source_blocks(W, El, M, N):
+    """Expert-parallel receive layout: expert e's rows are W blocks (one per source rank) of `seg` rows each, block s at
+    s * El * seg + e * seg.  With one or two local experts the output has fewer tiles than CTA pairs and the library cuts
+    the contraction over the source blocks (ab_grouped_gemm_tn_workspace_bytes > 0): same sums, fixed order."""
+    from apertis_llm_b200 import _lib, ops
+    d = dev()
+    RA = _lib_row_align()
+    seg = 2 * RA
+    rows = W * El * seg
+    g = torch.Generator().manual_seed(W * 100 + El)
+    A = (torch.randn(rows, M, generator=g) * 0.5).to(torch.bfloat16)
+    Bm = (torch.randn(rows, N, generator=g) * 0.5).to(torch.bfloat16)
+    valid = torch.zeros(rows, dtype=torch.bool)
+    cnt = torch.randint(1, seg + 1, (W, El), generator=g)
+    for s_ in range(W):
+        for e in range(El):
+            valid[(s_ * El + e) * seg: (s_ * El + e) * seg + int(cnt[s_, e])] = True
+    A[~valid] = 0
+    seg_off = (torch.arange(El + 1, dtype=torch.int32) * seg).to(d)
+    if W == 8 and El == 1:
+        assert _lib.query("ab_grouped_gemm_tn_workspace_bytes", M, N, El, W) > 0, "one expert per rank: cut over the source blocks"
+    out = ops.grouped_gemm_tn(A.to(d), Bm.to(d), seg_off, M, N, El, nsrc=W, src_stride=El * seg)
+    out2 = ops.grouped_gemm_tn(A.to(d), Bm.to(d), seg_off, M, N, El, nsrc=W, src_stride=El * seg)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "bitwise repeatable"
+    Av, Bv = A.float().view(W, El, seg, M), Bm.float().view(W, El, seg, N)
+    for e in range(El):
+        ref = torch.einsum("srm,srn->mn", Av[:, e], Bv[:, e])
+        assert rel_err(out[e], ref) < 2e-5, e
+
+
 # ------------------------------------------------------------------------------------------------
 # block-wrapper LayerNorm
 # ------------------------------------------------------------------------------------------------
