@@ -46,9 +46,9 @@ SIGNATURES = {
                             I, I, I, I, I, P]),
     "ab_gemm_row_tile": (I, []),
     "ab_ep_permute_ln": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, I64, I, I, P]),
-    "ab_ep_unpermute": (I, [P, I, I, I64, P, P, P, P, P, F, P, I, I, I, I, I, P]),
     "ab_ep_unpermute_bwd": (I, [P, P, P, P, P, P, P, I, I, I64, P, F, P, I, I, I64, I, I, I, P]),
-    "ab_ep_pull_rows": (I, [P, I, I, I64, P, P, P, I, I, P]),
+    "ab_ep_grouped_gemm_nt": (I, [P, P, P, P, P, I, I, I64, P, P, I64, I, I, I, I, I, I, P]),
+    "ab_ep_grouped_gemm_nn": (I, [P, P, P, P, P, I, I, I64, P, P, I64, I, I, I, I, I, I, P]),
     "ab_moe_router_workspace_bytes": (SZ, [I, I, I]),
     "ab_moe_router_fwd": (I, [P, P, P, F, P, P, P, P, P, P, P, P, P, P, P, P, P, P, SZ, I, I, I, I, I, I, P]),
     "ab_moe_topk_from_logits": (I, [P, P, P, P, P, P, I, I, I, P]),
@@ -167,6 +167,7 @@ KERNELS_PER_CALL = {
     "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,
     "ab_layernorm_fwd": 1, "ab_layernorm_bwd": 3,
     "ab_grouped_gemm_nt": 1, "ab_grouped_gemm_nn": 1, "ab_grouped_gemm_tn": 1, "ab_cast_f32_to_bf16": 1,
+    "ab_ep_permute_ln": 1, "ab_ep_unpermute_bwd": 1, "ab_ep_grouped_gemm_nt": 1, "ab_ep_grouped_gemm_nn": 1,
     "ab_split_f32_to_bf16x3": 1, "ab_split_f32_to_bf16x3_rows": 1,
 }
 launch_count = 0          # kernels launched through this binding since import (bench.py reads deltas)

@@ -67,6 +67,10 @@ struct GemmParams {
     void* c;
     void* c2;
     float* cw;
+    // expert parallelism: c is written into OTHER ranks' memory (NVLink): row r of the local [W sources][rows_per_peer] layout
+    // goes to rank r / rows_per_peer, block `peer_rank` of that rank's [W owners][rows_per_peer] buffer.  peer_n == 0: local.
+    unsigned char* peer_base[16];
+    int peer_n, peer_rows, peer_rank;
 };
 
 // dense weight gradient: 64-row blocks of slice e of the contraction (the last block of the last slice may be partial: TMA zero-fills)
@@ -481,7 +485,11 @@ __device__ __forceinline__ void epilogue_role(const GemmParams& p, const EpiCtx&
             // ---- stage this thread's row, then store 8 rows x 64 B per instruction
             unsigned char* base;
             if (MODE == MODE_TN) base = reinterpret_cast<unsigned char*>(p.cw) + ((size_t)t.e * p.M) * N * 4;
-            else base = reinterpret_cast<unsigned char*>(p.c);
+            else if (p.peer_n > 0) {
+                // the whole 128-row tile belongs to one source rank: its buffer, shifted so that `grow` indexes it directly
+                const int dst = (int)(row0 / (size_t)p.peer_rows);
+                base = p.peer_base[dst] + ((int64_t)(p.peer_rank - dst) * p.peer_rows) * (int64_t)N * ES;
+            } else base = reinterpret_cast<unsigned char*>(p.c);
             stage_and_store<MODE, F32>(p, stg, f, base, lane, row0, ncol, ncol_end);
         }
         if (have_acc) {
@@ -712,7 +720,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
 
 int gemm_rows(int mode, const void* A, const void* W, const float* bias, const void* aux, void* c, void* c2,
               const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E, int epi, int act,
-              int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream) {
+              int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream, const uint64_t* peer_c = nullptr,
+              int peer_w = 0, int peer_rank = 0, int64_t peer_rows = 0) {
     AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "grouped_gemm: dropout probability must be in [0, 1)");
     AB_REQUIRE(drop_p == 0.f || (drop_seed != nullptr && (epi == AB_EPI_BIAS_ACT || epi == AB_EPI_DACT)),
                "grouped_gemm: dropout needs a seed and the bias+act / dact epilogue");
@@ -732,6 +741,19 @@ int gemm_rows(int mode, const void* A, const void* W, const float* bias, const v
     p.epi = epi; p.act = act; p.c_f32 = c_dtype == AB_F32;
     p.tile_expert = tile_expert; p.n_rows = n_rows; p.bias = bias; p.aux = aux; p.c = c; p.c2 = c2;
     p.rows_valid = max_rows;
+    if (peer_c != nullptr) {
+        AB_REQUIRE(peer_w >= 1 && peer_w <= 16 && peer_rank >= 0 && peer_rank < peer_w && peer_rows > 0 && peer_rows % PM == 0 &&
+                   (int64_t)peer_w * peer_rows == max_rows && epi != AB_EPI_BIAS_ACT,
+                   "ep_grouped_gemm: bad peer table (W=%d rank=%d rows_per_peer=%lld, max_rows=%lld)", peer_w, peer_rank,
+                   (long long)peer_rows, (long long)max_rows);
+        for (int i = 0; i < peer_w; ++i) {
+            AB_REQUIRE(peer_c[i] != 0 && peer_c[i] % 16 == 0, "ep_grouped_gemm: peer buffer %d is null or misaligned", i);
+            p.peer_base[i] = reinterpret_cast<unsigned char*>(peer_c[i]);
+        }
+        p.peer_n = peer_w; p.peer_rows = (int)peer_rows; p.peer_rank = peer_rank;
+        c = reinterpret_cast<void*>(peer_c[peer_rank]);          // for the alignment check below
+        p.c = c;
+    }
     if (drop_p > 0.f) {
         p.drop_seed = drop_seed;
         p.drop_thresh = (uint32_t)((double)drop_p * 65536.0 + 0.5);
@@ -766,6 +788,24 @@ extern "C" int ab_grouped_gemm_nn(const void* A, const void* W, const float* bia
                                   const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows, int N, int K, int E,
                                   int epi, int act, int c_dtype, float drop_p, const uint32_t* drop_seed, cudaStream_t stream) {
     return gemm_rows(MODE_NN, A, W, bias, aux, c, c2, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, drop_p, drop_seed, stream);
+}
+
+// expert parallelism: the same GEMMs with the result rows written straight into the SOURCE ranks' buffers over NVLink (the
+// return exchange of the expert-parallel MoE fused into the epilogue); see the ab_ep_* section of the header
+extern "C" int ab_ep_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, const uint64_t* peer_c, int peer_w,
+                                     int rank, int64_t rows_per_peer, const int32_t* tile_expert, const int32_t* n_rows,
+                                     int64_t max_rows, int N, int K, int E, int epi, int act, int c_dtype, cudaStream_t stream) {
+    AB_REQUIRE(peer_c != nullptr, "ep_grouped_gemm_nt: no peer table");
+    return gemm_rows(MODE_NT, A, W, bias, aux, nullptr, nullptr, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, 0.f, nullptr,
+                     stream, peer_c, peer_w, rank, rows_per_peer);
+}
+
+extern "C" int ab_ep_grouped_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, const uint64_t* peer_c, int peer_w,
+                                     int rank, int64_t rows_per_peer, const int32_t* tile_expert, const int32_t* n_rows,
+                                     int64_t max_rows, int N, int K, int E, int epi, int act, int c_dtype, cudaStream_t stream) {
+    AB_REQUIRE(peer_c != nullptr, "ep_grouped_gemm_nn: no peer table");
+    return gemm_rows(MODE_NN, A, W, bias, aux, nullptr, nullptr, tile_expert, n_rows, max_rows, N, K, E, epi, act, c_dtype, 0.f, nullptr,
+                     stream, peer_c, peer_w, rank, rows_per_peer);
 }
 
 namespace {

@@ -311,15 +311,12 @@ __global__ void __launch_bounds__(256) permute_ln_kernel(const TI* __restrict__ 
     }
 }
 
-// out[s,:] = sum_k w[s,k] * y[row_of[s,k],:]   (warp per token, fixed slot order).  The rows may live in other ranks' memory
-// (NVLink latency of microseconds), so the loads of a chunk - 4 elements of every one of the K rows, for two chunks - are
-// all issued before the first is used.
+// out[s,:] = sum_k w[s,k] * y[row_of[s,k],:]   (warp per token, fixed slot order).  The loads of a group of chunks - 4
+// elements of every one of the K rows each - are all issued before the first is used.
 template <typename TY, typename TO, int KM>
 __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y, const int32_t* __restrict__ row_of,
                                                         const float* __restrict__ w, const float* __restrict__ res, TO* __restrict__ out,
-                                                        const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int S, int K, int Dm,
-                                                        const PeerRows pr, TY* __restrict__ y_copy) {
-    // under EP the rows are read from their owners' buffers over NVLink and a local copy is kept for the backward
+                                                        const uint32_t* __restrict__ seed, uint32_t thresh, float scale, int S, int K, int Dm) {
     constexpr int DU = 8 / KM;           // chunks in flight (KM = upper bound of the experts per token)
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -334,7 +331,7 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y
         for (int k = 0; k < KM; ++k) {
             rid[k] = k < K ? row_of[(size_t)s * K + k] : -1;
             wk[k] = rid[k] >= 0 ? w[(size_t)s * K + k] : 0.f;
-            rows[k] = rid[k] >= 0 ? reinterpret_cast<const TY*>(peer_row(pr, const_cast<TY*>(y), rid[k], Dm, (int)sizeof(TY))) : nullptr;
+            rows[k] = rid[k] >= 0 ? y + (size_t)rid[k] * Dm : nullptr;
         }
         for (int d0 = lane * 4; d0 < Dm; d0 += 128 * DU) {
             float yv[DU][KM][4];
@@ -355,7 +352,6 @@ __global__ void __launch_bounds__(256) unpermute_kernel(const TY* __restrict__ y
 #pragma unroll
                 for (int k = 0; k < KM; ++k) {
                     if (k < K && rows[k] != nullptr) {
-                        if (y_copy) st4<TY>(y_copy + (size_t)rid[k] * Dm + d, yv[u][k][0], yv[u][k][1], yv[u][k][2], yv[u][k][3]);
 #pragma unroll
                         for (int v = 0; v < 4; ++v) acc[v] += yv[u][k][v] * wk[k];   // separate mul and add, as index_add_(y*w)
                     }
@@ -674,21 +670,6 @@ __global__ void tile_reduce_kernel(const float* __restrict__ part, const int32_t
 // these kernels are latency-bound streams); tile_expert is looked up through the ratio of the two.
 int work_rows(int row_align) { return row_align % 128 == 0 ? 128 : row_align; }
 
-// out[r,:] = the owner's copy of row r (peer memory), for the rows that hold a token: the pull half of an exchange
-template <typename T>
-__global__ void __launch_bounds__(256) ep_pull_rows_kernel(const int32_t* __restrict__ tok_of_row, const int32_t* __restrict__ n_rows,
-                                                           T* __restrict__ out, int Dm, const PeerRows pr) {
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int total = n_rows[0];
-    constexpr int V = 16 / (int)sizeof(T);
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < total; r += gridDim.x * wpb) {
-        if (tok_of_row != nullptr && tok_of_row[r] < 0) continue;
-        const uint4* src = reinterpret_cast<const uint4*>(peer_row(pr, nullptr, r, Dm, (int)sizeof(T)));
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)r * Dm);
-        for (int i = lane; i < Dm / V; i += 32) dst[i] = __ldg(src + i);
-    }
-}
-
 int make_peers(PeerRows* pr, const uint64_t* peer_ptrs, int W, int rank, int64_t rows_per_peer) {
     memset(pr, 0, sizeof(*pr));
     if (peer_ptrs == nullptr) return AB_OK;
@@ -788,10 +769,8 @@ extern "C" int ab_ep_permute_ln(const void* x, const float* stats, const float* 
     return permute_ln_impl(x, stats, ln_w, ln_b, tok_of_row, tile_expert, n_rows, nullptr, Dm, row_align, max_rows, dtype, out_dtype, pr, stream);
 }
 
-namespace {
-int unpermute_impl(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
-                   const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, const PeerRows& pr, void* y_copy,
-                   cudaStream_t stream) {
+extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
+                                const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
     AB_REQUIRE(Dm > 0 && Dm % 4 == 0, "moe_unpermute: hidden size must be a multiple of 4");
     AB_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed), "moe_unpermute: dropout p must be in [0,1) and needs a seed when > 0");
     AB_REQUIRE(res == nullptr || ((uintptr_t)res % 16) == 0, "moe_unpermute: the residual must be 16-byte aligned fp32");
@@ -801,9 +780,9 @@ int unpermute_impl(const void* y, const int32_t* row_of, const float* w, const f
     const int grid = rows_grid(S);
 #define AB_UNP(TY, TO)                                                                                                          \
     {                                                                                                                            \
-        if (K <= 2) unpermute_kernel<TY, TO, 2><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy); \
-        else if (K <= 4) unpermute_kernel<TY, TO, 4><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy); \
-        else unpermute_kernel<TY, TO, 8><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm, pr, (TY*)y_copy); \
+        if (K <= 2) unpermute_kernel<TY, TO, 2><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm); \
+        else if (K <= 4) unpermute_kernel<TY, TO, 4><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm); \
+        else unpermute_kernel<TY, TO, 8><<<grid, 256, 0, stream>>>((const TY*)y, row_of, w, res, (TO*)out, sd, thresh, scale, S, K, Dm); \
     }
     AB_REQUIRE(K >= 1 && K <= 8, "moe_unpermute: experts_per_token must be in [1, 8]");
     if (y_dtype == AB_F32 && out_dtype == AB_F32) AB_UNP(float, float)
@@ -814,23 +793,6 @@ int unpermute_impl(const void* y, const int32_t* row_of, const float* w, const f
 #undef AB_UNP
     AB_LAUNCH_CHECK();
     return AB_OK;
-}
-}  // namespace
-
-extern "C" int ab_moe_unpermute(const void* y, const int32_t* row_of, const float* w, const float* res, void* out, float drop_p,
-                                const uint32_t* drop_seed, int S, int K, int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
-    PeerRows pr;
-    make_peers(&pr, nullptr, 0, 0, 0);
-    return unpermute_impl(y, row_of, w, res, out, drop_p, drop_seed, S, K, Dm, y_dtype, out_dtype, pr, nullptr, stream);
-}
-
-extern "C" int ab_ep_unpermute(const uint64_t* peer_y, int W, int rank, int64_t rows_per_peer, void* y_copy, const int32_t* row_of,
-                               const float* w, const float* res, void* out, float drop_p, const uint32_t* drop_seed, int S, int K,
-                               int Dm, int y_dtype, int out_dtype, cudaStream_t stream) {
-    AB_REQUIRE(peer_y != nullptr, "ep_unpermute: no peer table");
-    PeerRows pr;
-    if (int e = make_peers(&pr, peer_y, W, rank, rows_per_peer)) return e;
-    return unpermute_impl(nullptr, row_of, w, res, out, drop_p, drop_seed, S, K, Dm, y_dtype, out_dtype, pr, y_copy, stream);
 }
 
 namespace {
@@ -881,20 +843,6 @@ extern "C" int ab_ep_unpermute_bwd(const void* dout, const void* y, const float*
     if (int e = make_peers(&pr, peer_dy, W, rank, rows_per_peer)) return e;
     return unpermute_bwd_impl(dout, y, w, tok_of_row, slot_of_row, n_rows, nullptr, dw_row, drop_p, drop_seed, K, Dm, max_rows,
                               dout_dtype, y_dtype, dy_dtype, pr, stream);
-}
-
-extern "C" int ab_ep_pull_rows(const uint64_t* peer_src, int W, int rank, int64_t rows_per_peer, const int32_t* tok_of_row,
-                               const int32_t* n_rows, void* out, int Dm, int dtype, cudaStream_t stream) {
-    AB_REQUIRE(peer_src != nullptr && out != nullptr && ((uintptr_t)out % 16) == 0, "ep_pull_rows: null or misaligned buffers");
-    AB_REQUIRE(dtype == AB_F32 || dtype == AB_BF16, "ep_pull_rows: bad dtype");
-    AB_REQUIRE(Dm > 0 && Dm % (dtype == AB_F32 ? 4 : 8) == 0, "ep_pull_rows: rows must be whole 16-byte vectors");
-    PeerRows pr;
-    if (int e = make_peers(&pr, peer_src, W, rank, rows_per_peer)) return e;
-    const int grid = rows_grid((int64_t)W * rows_per_peer);
-    if (dtype == AB_F32) ep_pull_rows_kernel<float><<<grid, 256, 0, stream>>>(tok_of_row, n_rows, (float*)out, Dm, pr);
-    else ep_pull_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(tok_of_row, n_rows, (__nv_bfloat16*)out, Dm, pr);
-    AB_LAUNCH_CHECK();
-    return AB_OK;
 }
 
 extern "C" size_t ab_moe_permute_ln_bwd_workspace_bytes(int Dm, int row_align, int64_t max_rows) {

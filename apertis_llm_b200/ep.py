@@ -18,11 +18,13 @@ SURVEY.md section 8(e) specifies.  Semantics are those of replicated experts und
 Two transports move the rows (APERTIS_B200_EP = peer | nccl | auto, default auto):
 
 * ``peer`` (bf16 path, all ranks on one NVLink / NVSwitch node, torch symmetric memory available): no all-to-all at all.
-  Every rank owns four peer-mapped buffers ``[W sources, El*seg, Dm]``; the permute + LayerNorm kernel writes each row
-  straight into its owner's receive buffer (``ab_ep_permute_ln``), the combine kernel reads each expert-output row from
-  its owner's buffer (``ab_ep_unpermute``), and the backward does the same in the other direction.  The exchanges are
-  thereby part of the kernels on either side of them; what remains between the ranks are five ~7 us barriers per step
-  (``_SymmetricMemory.barrier``) that order writers before the owner's GEMMs and the GEMMs before the readers.
+  Every rank owns four peer-mapped buffers ``[W, El*seg, Dm]`` and every exchange is fused into the kernel that PRODUCES
+  the rows, which stores them straight into the consuming rank's buffer: permute + LayerNorm into the owners' receive
+  buffers (``ab_ep_permute_ln``), the second expert GEMM's epilogue into the source ranks' buffers
+  (``ab_ep_grouped_gemm_nt``), and in the backward the un-permutation's dY rows (``ab_ep_unpermute_bwd``) and the input-
+  gradient GEMM's epilogue (``ab_ep_grouped_gemm_nn``).  The NVLink transfer overlaps the producing kernel tile by tile;
+  what remains between the ranks are five ~7 us barriers per step (``_SymmetricMemory.barrier``): all producers of a
+  buffer before its consumers.
 * ``nccl``: ``all_to_all_single`` between the same kernels (any backend NCCL supports; also the fp32-parity mode).
 """
 from __future__ import annotations
@@ -102,7 +104,7 @@ def all_gather_cat(t: torch.Tensor, group) -> torch.Tensor:
 # peer-memory transport
 # ------------------------------------------------------------------------------------------------
 _EP_MODE = os.environ.get("APERTIS_B200_EP", "auto")
-_EP_PULL = os.environ.get("APERTIS_B200_EP_PULL", "copy")        # copy (DMA engines) | kernel (ab_ep_pull_rows)
+
 _peer_cache = {}          # (group name, rank, rows, Dm) -> _PeerState
 _peer_failed = False
 
@@ -123,11 +125,8 @@ class _PeerState:
             self.buf[n], self.hdl[n] = t, h
             self.ptrs[n] = (ctypes.c_uint64 * self.W)(*[int(p) for p in h.buffer_ptrs])
         self.sync = self.hdl["xn"]
-        rpp = rows // self.W
-        # every rank's input-gradient buffer as a local tensor [W sources, rows per peer, Dm] (peer-mapped views)
-        self.remote_dxn = [self.hdl["dxn"].get_buffer(d, (self.W, rpp, Dm), torch.bfloat16) for d in range(self.W)]
         self.version = 0          # forwards run on these buffers (a backward must see the version its forward left)
-        self.side = torch.cuda.Stream(device=device)      # the backward's row pull runs beside the weight-gradient GEMMs
+        self.side = torch.cuda.Stream(device=device)      # the backward's last barrier waits beside the weight-gradient GEMMs
 
     def barrier(self, channel: int = 0):
         """All ranks' preceding work on the current stream is complete and visible (a kernel: CUDA-graph capturable)."""
@@ -236,12 +235,12 @@ class _MoEExpertsEP(torch.autograd.Function):
             a2, k2 = h, I
         out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
         if peer is not None:
-            ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt, out=peer.buf["y"])
-            # ---- combine fused into the un-permutation: every row is read from its owner's buffer
-            peer.barrier(2)                   # every owner has finished its expert outputs
-            y = torch.empty(rows_local, Dm, dtype=cdt, device=dev)
-            call("ab_ep_unpermute", peer.ptrs["y"], W, rank, El * seg, ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None,
-                 S, K, Dm, dt(cdt), dt(out), stream_ptr())
+            # ---- combine fused into the second GEMM: its epilogue stores every row into the source rank's buffer
+            call("ab_ep_grouped_gemm_nt", ptr(a2), ptr(w2), ptr(b2), None, peer.ptrs["y"], W, rank, El * seg, ptr(rplan["tile_expert"]),
+                 ptr(rplan["n_rows"]), rows_local, Dm, k2, El, _lib.EPI_BIAS, act, dt(cdt), stream_ptr())
+            peer.barrier(2)                   # every owner has delivered its expert outputs
+            y = peer.buf["y"]                 # this rank's rows, in its own permuted layout; kept for the backward
+            call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None, S, K, Dm, dt(y), dt(out), stream_ptr())
         else:
             yr = ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
             # ---- combine
@@ -314,23 +313,15 @@ class _MoEExpertsEP(torch.autograd.Function):
             dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             if peer is not None:
-                ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16, out=peer.buf["dxn"])
-                peer.barrier(4)               # every owner's input-gradient rows are complete
-                # the sources pull their rows over NVLink on a side stream while the weight gradients are computed
-                dxn_w = torch.empty(rows, Dm, dtype=torch.bfloat16, device=dev)
+                # the input-gradient GEMM's epilogue stores every row into its source rank's buffer; the barrier that
+                # completes the exchange waits on a side stream while the weight gradients are computed
+                call("ab_ep_grouped_gemm_nn", ptr(dhpre), ptr(w1b), None, None, peer.ptrs["dxn"], W, rank, El * seg, ptr(rplan["tile_expert"]),
+                     ptr(rplan["n_rows"]), rows, Dm, I, El, _lib.EPI_NONE, act, dt(torch.bfloat16), stream_ptr())
                 main = torch.cuda.current_stream(dev)
                 peer.side.wait_stream(main)
                 with torch.cuda.stream(peer.side):
-                    if _EP_PULL == "kernel":
-                        call("ab_ep_pull_rows", peer.ptrs["dxn"], W, rank, El * seg, ptr(plan["tok_of_row"]), ptr(plan["n_rows"]), ptr(dxn_w), Dm,
-                             dt(dxn_w), stream_ptr(dev))
-                    else:
-                        # block copies by the copy engines: no SM is taken from the persistent weight-gradient GEMMs
-                        dst = dxn_w.view(W, El * seg, Dm)
-                        for i in range(W):
-                            d = (rank + i) % W                    # start with the local block, spread the peers
-                            dst[d].copy_(peer.remote_dxn[d][rank])
-                dxn_w.record_stream(peer.side)
+                    peer.barrier(4)
+                dxn_w = peer.buf["dxn"]
                 dxn_wait = lambda: main.wait_stream(peer.side)
             else:
                 dxnr = ops.grouped_gemm("nn", dhpre, w1b, rplan, Dm, I, El, out_dtype=torch.bfloat16)

@@ -375,7 +375,8 @@ def workload_text(name):
     return f"{name}: Apertis block hidden {Dm}, heads {H}, d_inner {16 * H}, intermediate {I}, {E} experts top-{K}, seq {seq}"
 
 
-TIMED = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_ssm_scan_fwd", "ab_ssm_scan_bwd",
+TIMED = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_ep_grouped_gemm_nt", "ab_ep_grouped_gemm_nn",
+         "ab_ssm_scan_fwd", "ab_ssm_scan_bwd",
          "ab_dense_gemm_nt", "ab_dense_gemm_nn", "ab_dense_gemm_tn"]
 
 
@@ -565,7 +566,7 @@ def summarise(name, B, m, world, pk, pk_src, amp):
     ms, e2e_ms = m["ms"], m["e2e_ms"]
     per = lambda names: sum(sum(m["per_kernel"].get(n, [])) for n in names) / steps
     cnt = lambda names: sum(len(m["per_kernel"].get(n, [])) for n in names) / steps
-    moe = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn"]
+    moe = ["ab_grouped_gemm_nt", "ab_grouped_gemm_nn", "ab_grouped_gemm_tn", "ab_ep_grouped_gemm_nt", "ab_ep_grouped_gemm_nn"]
     dense = ["ab_dense_gemm_nt", "ab_dense_gemm_nn", "ab_dense_gemm_tn"]
     scan = ["ab_ssm_scan_fwd", "ab_ssm_scan_bwd"]
     gemm_ms, dense_ms, scan_ms = per(moe), per(dense), per(scan)

@@ -243,30 +243,32 @@ int ab_moe_router_bwd(const void* x, const float* stats, const float* ln_w, cons
 
 /* ---- expert parallelism over peer memory (NVLink 5 / NVSwitch)  (no reference counterpart: the reference
  * is DDP only, pipeline.py:435-466) ------------------------------------------------------------------------------------
- * The row exchanges of the expert-parallel MoE fused into the kernels on either side of them: instead of writing the
- * permuted rows locally and handing them to an all-to-all, the kernels address the OWNING rank's buffer directly through
- * peer-mapped pointers.  The local permuted layout is [W destination ranks][rows_per_peer] (fixed expert segments, see
- * ab_moe_plan fixed_seg); every rank exposes buffers of [W source ranks][rows_per_peer][Dm]; `peer_*` is a HOST array of
- * the W peer-mapped device addresses of that buffer (entry `rank` = the local one).  Row r of the local layout is row
- * (rank, r % rows_per_peer) of rank r / rows_per_peer.  The caller orders the ranks with its own barriers (the host side
- * uses torch symmetric memory): writers -> barrier -> owner's GEMMs, owner's GEMMs -> barrier -> readers.
- *   ab_ep_permute_ln     ab_moe_permute_ln writing each normalised row into its owner's receive buffer (dispatch)
- *   ab_ep_unpermute      ab_moe_unpermute reading each expert-output row from its owner's buffer (combine); y_copy
- *                        [max_rows, Dm] keeps the gathered rows for the backward
- *   ab_ep_unpermute_bwd  ab_moe_unpermute_bwd writing each dY row into its owner's receive buffer
- *   ab_ep_pull_rows      out[r,:] = owner's row r for the rows that hold a token (tok_of_row NULL = all rows) */
+ * The four row exchanges of the expert-parallel MoE fused into the kernels that produce the rows: instead of writing them
+ * locally and handing them to an all-to-all, the producer stores every row straight into the consuming rank's buffer
+ * through peer-mapped pointers, so the transfer overlaps the producing kernel and no exchange kernel exists.
+ * Layouts: a SOURCE rank (owner of tokens) keeps the permuted layout [W owners][rows_per_peer] (fixed expert segments,
+ * ab_moe_plan fixed_seg); an OWNER rank (owner of experts) works on [W sources][rows_per_peer].  Row (d, j) of a source
+ * rank s is row (s, j) of owner d and vice versa; `peer_*` is a HOST array of the W peer-mapped device addresses of the
+ * destination buffer on every rank (entry `rank` = the local one).  The caller orders the ranks with its own barriers (the
+ * host side uses torch symmetric memory): all producers -> barrier -> consumers.
+ *   ab_ep_permute_ln       ab_moe_permute_ln, each normalised row stored into its owner's receive buffer        (dispatch)
+ *   ab_ep_grouped_gemm_nt  ab_grouped_gemm_nt, each result row stored into its source rank's buffer            (combine)
+ *   ab_ep_unpermute_bwd    ab_moe_unpermute_bwd, each dY row stored into its owner's receive buffer         (dY dispatch)
+ *   ab_ep_grouped_gemm_nn  ab_grouped_gemm_nn, each input-gradient row stored into its source rank's buffer (dXn return)
+ * The GEMM variants take epi = AB_EPI_NONE | AB_EPI_BIAS | AB_EPI_DACT | AB_EPI_ADD (one output) and no dropout. */
 int ab_ep_permute_ln(const void* x, const float* stats, const float* ln_w, const float* ln_b, const int32_t* tok_of_row,
                      const int32_t* tile_expert, const int32_t* n_rows, const uint64_t* peer_xn, int W, int rank,
                      int64_t rows_per_peer, int Dm, int row_align, int64_t max_rows, int dtype, int out_dtype, cudaStream_t stream);
-int ab_ep_unpermute(const uint64_t* peer_y, int W, int rank, int64_t rows_per_peer, void* y_copy, const int32_t* row_of,
-                    const float* w, const float* res, void* out, float drop_p, const uint32_t* drop_seed, int S, int K, int Dm,
-                    int y_dtype, int out_dtype, cudaStream_t stream);
 int ab_ep_unpermute_bwd(const void* dout, const void* y, const float* w, const int32_t* tok_of_row, const int32_t* slot_of_row,
                         const int32_t* n_rows, const uint64_t* peer_dy, int W, int rank, int64_t rows_per_peer, float* dw_row,
                         float drop_p, const uint32_t* drop_seed, int K, int Dm, int64_t max_rows, int dout_dtype, int y_dtype,
                         int dy_dtype, cudaStream_t stream);
-int ab_ep_pull_rows(const uint64_t* peer_src, int W, int rank, int64_t rows_per_peer, const int32_t* tok_of_row,
-                    const int32_t* n_rows, void* out, int Dm, int dtype, cudaStream_t stream);
+int ab_ep_grouped_gemm_nt(const void* A, const void* W, const float* bias, const void* aux, const uint64_t* peer_c, int peer_w,
+                          int rank, int64_t rows_per_peer, const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows,
+                          int N, int K, int E, int epi, int act, int c_dtype, cudaStream_t stream);
+int ab_ep_grouped_gemm_nn(const void* A, const void* W, const float* bias, const void* aux, const uint64_t* peer_c, int peer_w,
+                          int rank, int64_t rows_per_peer, const int32_t* tile_expert, const int32_t* n_rows, int64_t max_rows,
+                          int N, int K, int E, int epi, int act, int c_dtype, cudaStream_t stream);
 
 /* ---- MoE: grouped expert GEMM on tcgen05 / TMEM, operands staged by TMA  (core.py:596 = :437-440) --
  * bf16 operands, fp32 accumulation in tensor memory.  The kernel runs on CTA pairs (tcgen05 cta_group::2): a row tile is

@@ -24,15 +24,14 @@ def test_ep_host_logic_gloo_world2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["nccl", "peer", "peer+pull_kernel"])
+@pytest.mark.parametrize("transport", ["nccl", "peer"])
 def test_ep_matches_local_experts_nccl(transport):
     """EP layer against the same layer with every expert local, on >= 2 GPUs, through both row transports: NCCL all-to-all
-    and the peer-memory kernels (rows written into / read from the owners' buffers over NVLink, ab_ep_*)."""
+    and the peer-memory kernels (every producer stores its rows into the consuming rank's buffer over NVLink, ab_ep_*)."""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 8 if n >= 8 else (4 if n >= 4 else 2)
-    env = {"APERTIS_B200_EP": transport.split("+")[0], "APERTIS_B200_EP_PULL": "kernel" if "pull_kernel" in transport else "copy"}
-    res = _torchrun(world, "gpu", {"nccl": 29612, "peer": 29613}.get(transport, 29614), env_extra=env)
+    res = _torchrun(world, "gpu", {"nccl": 29612, "peer": 29613}[transport], env_extra={"APERTIS_B200_EP": transport})
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("gpu ep ok") == world
