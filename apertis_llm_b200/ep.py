@@ -164,7 +164,7 @@ class _MoEExpertsEP(torch.autograd.Function):
     """ops._MoEExperts with the expert MLPs executed on the owning ranks."""
 
     @staticmethod
-    def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, cfg, group):
+    def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, res, cfg, group):
         _lib.ensure_device(x2.device)
         dev = x2.device
         W = dist.get_world_size(group)
@@ -233,25 +233,34 @@ class _MoEExpertsEP(torch.autograd.Function):
             a2, k2 = ops._split_cols(h, 0), 3 * I
         else:
             a2, k2 = h, I
-        out = torch.empty(S, Dm, dtype=x2.dtype, device=dev)
+        # the caller's output dropout and residual add (core.py:918-919) happen inside the combine kernel when handed in
+        out_p = float(cfg.get("out_drop_p", 0.0)) if training else 0.0
+        out_seed = torch.randint(0, 2 ** 31 - 1, (2,), device=dev, dtype=torch.int32) if out_p > 0.0 else None
+        resc = res.reshape(S, Dm).float().contiguous() if res is not None else None
+        out = torch.empty(S, Dm, dtype=x2.dtype if res is None else torch.float32, device=dev)
         if peer is not None:
             # ---- combine fused into the second GEMM: its epilogue stores every row into the source rank's buffer
             call("ab_ep_grouped_gemm_nt", ptr(a2), ptr(w2), ptr(b2), None, peer.ptrs["y"], W, rank, El * seg, ptr(rplan["tile_expert"]),
                  ptr(rplan["n_rows"]), rows_local, Dm, k2, El, _lib.EPI_BIAS, act, dt(cdt), stream_ptr())
             peer.barrier(2)                   # every owner has delivered its expert outputs
             y = peer.buf["y"]                 # this rank's rows, in its own permuted layout; kept for the backward
-            call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None, S, K, Dm, dt(y), dt(out), stream_ptr())
+            call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(resc), ptr(out), out_p, ptr(out_seed), S, K, Dm, dt(y), dt(out),
+                 stream_ptr())
         else:
             yr = ops.grouped_gemm("nt", a2, w2, rplan, Dm, k2, El, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
             # ---- combine
             y = all_to_all_equal(yr.view(W, El * seg, Dm), group).view(rows_local, Dm)
-            call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), None, ptr(out), 0.0, None, S, K, Dm, dt(y), dt(out), stream_ptr())
+            call("ab_moe_unpermute", ptr(y), ptr(plan["row_of"]), ptr(r["w"]), ptr(resc), ptr(out), out_p, ptr(out_seed), S, K, Dm, dt(y), dt(out),
+                 stream_ptr())
         aux = r["aux"]
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
         lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
-        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt, drop_p=drop_p)
+        ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt, drop_p=drop_p,
+                       out_p=out_p, has_res=res is not None, res_shape=res.shape if res is not None else None,
+                       res_dtype=res.dtype if res is not None else None)
         ctx.drop_seed = drop_seed
+        ctx.out_seed = out_seed
         ctx.shadows = None if precise else (w1, w2)
         ctx.group = group
         ctx.peer = peer
@@ -284,13 +293,14 @@ class _MoEExpertsEP(torch.autograd.Function):
         if peer is not None:
             # dY rows go straight into their owners' receive buffers
             call("ab_ep_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
-                 peer.ptrs["dy"], W, rank, El * seg, ptr(dw_row), 0.0, None, K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+                 peer.ptrs["dy"], W, rank, El * seg, ptr(dw_row), cfg["out_p"], ptr(ctx.out_seed), K, Dm, rows, dt(dout), dt(y), dt(cdt),
+                 stream_ptr())
             peer.barrier(3)
             dyr = peer.buf["dy"]
         else:
             dy = torch.empty(rows, Dm, dtype=cdt, device=dev)
             call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
-                 ptr(dy), ptr(dw_row), 0.0, None, K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
+                 ptr(dy), ptr(dw_row), cfg["out_p"], ptr(ctx.out_seed), K, Dm, rows, dt(dout), dt(y), dt(cdt), stream_ptr())
             dyr = all_to_all_equal(dy.view(W, El * seg, Dm), group).view(rows, Dm)
         lseg = rplan["seg_off"]
         stride = El * seg
@@ -368,16 +378,18 @@ class _MoEExpertsEP(torch.autograd.Function):
         dln_work.wait()
         dln_w_l = dln[0, rank * El:(rank + 1) * El] * inv
         dln_b_l = dln[1, rank * El:(rank + 1) * El] * inv
-        return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w_l, dln_b_l, dW1 * inv, db1 * inv, dW2 * inv, db2 * inv, None, None)
+        dres = dout.reshape(cfg["res_shape"]).to(cfg["res_dtype"]) if cfg["has_res"] else None       # the residual passes the gradient on
+        return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w_l, dln_b_l, dW1 * inv, db1 * inv, dW2 * inv, db2 * inv, dres, None, None)
 
 
-def moe_experts_ep(module, x2, noise, noise_scale, cfg):
-    """Entry used by AdaptiveExpertSystem.forward when an expert-parallel group is set."""
+def moe_experts_ep(module, x2, noise, noise_scale, cfg, res=None):
+    """Entry used by AdaptiveExpertSystem.forward when an expert-parallel group is set.  res (optional, [S, Dm]): the
+    caller's residual; with it the result is res + dropout(cfg['out_drop_p'])(moe(x2))."""
     cfg["_owner"] = id(module)
     cfg["_ln_cache"] = module.__dict__.setdefault("_ep_ln_cache", {})
     return _MoEExpertsEP.apply(x2, module.router_norm.weight, module.router_norm.bias, module.router.weight, module.router.bias,
                                noise, noise_scale, module.expert_ln_weight, module.expert_ln_bias, module.expert_w1,
-                               module.expert_b1, module.expert_w2, module.expert_b2, cfg, module.ep_group)
+                               module.expert_b1, module.expert_w2, module.expert_b2, res, cfg, module.ep_group)
 
 
 def replicated_parameters(layer: torch.nn.Module) -> List[torch.nn.Parameter]:

@@ -314,9 +314,8 @@ class AdaptiveExpertSystem(nn.Module):
                    if self.router_autocast_rounding else _lib.ROUTER_EXACT)
         if self.ep_world > 1:
             from . import ep
-            out, lb, rz, counts = ep.moe_experts_ep(self, x2, noise, noise_scale, cfg)
-            if residual is not None:
-                out = ops.dropout_add(out.reshape(residual.shape), residual, output_dropout_p, training).reshape(S, Dm)
+            cfg["out_drop_p"] = float(output_dropout_p)
+            out, lb, rz, counts = ep.moe_experts_ep(self, x2, noise, noise_scale, cfg, res=residual.reshape(S, Dm) if residual is not None else None)
         else:
             cfg["out_drop_p"] = float(output_dropout_p)
             out, lb, rz, counts = ops.moe_experts(x2, self.router_norm.weight, self.router_norm.bias, self.router.weight,

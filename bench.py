@@ -602,7 +602,8 @@ def summarise(name, B, m, world, pk, pk_src, amp):
             "e2e": {"value": tokens_per_step * world / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4,
                     "how": "pinned host x -> device each step (prefetched on a copy stream), block fwd+bwd through the module API, loss.item()"},
-            "gpu_launches": m["launches"], "roofline": roofline, "kernels": kernels, "last_loss": m["last_loss"]}
+            "gpu_launches": m["launches"], "roofline": roofline, "kernels": kernels, "last_loss": m["last_loss"],
+            "entry_point_us": {n: [round(1e3 * t, 1) for t in v[-(len(v) // steps):]] for n, v in sorted(m["per_kernel"].items()) if v}}
 
 
 def ep_parity_check(ctx, name, B=1):

@@ -12,10 +12,14 @@ for k, v in d.get("kernels", {}).items():
         print("  ", k, v)
         continue
     print(f"  {k}: {v.get('achieved', 0):.0f} {v.get('unit')} frac {v.get('frac', 0):.3f} {v.get('ms_per_step_in_kernel', '')} {v.get('fwd_us', '')} {v.get('bwd_us', '')}")
+if "entry_point_us" in d:
+    print("   per call (us, last eager step):", {k: v for k, v in d["entry_point_us"].items() if "gemm" in k})
 for n, w in d.get("workloads", {}).items():
     if "error" in w:
         print("  ", n, w)
         continue
+    if "entry_point_us" in w:
+        print("   per call (us):", {k: v for k, v in w["entry_point_us"].items() if "grouped" in k})
     print(f"  [{n}] {w['value'] / 1e6:.2f} M tok/s {w['ms_per_step']:.3f} ms  gemm {w['roofline']['achieved']:.0f} TF/s frac {w['roofline']['frac']:.3f}  scan {w['kernels']['selective_scan_fwd+bwd']['frac']:.3f}")
 for k in ("ep_parity", "gpu_reference", "cpu_baseline"):
     if k in d:

@@ -58,7 +58,7 @@ def main():
         tot = sum(r[1] for r in rows)
         nccl = sum(r[1] for r in rows if "nccl" in r[0].lower())
         print(f"world {world}: eager step {wall:.0f} us on the stream clock; kernel time {tot:.0f} us of which NCCL {nccl:.0f} us")
-        for k, t, c in rows[:34]:
+        for k, t, c in rows[:44]:
             print(f"{t:8.1f} us {c:5.1f}x {100 * t / tot:5.1f}%  {k[:100]}")
     sys.stdout.flush()
     os._exit(0)
