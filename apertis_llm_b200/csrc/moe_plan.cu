@@ -240,6 +240,7 @@ __global__ void plan_finalize_kernel(const int32_t* __restrict__ idx, const int3
         int o = 0, kept = 0;
         for (int e = 0; e < E; ++e) {
             soff[e] = o;
+            if (fixed_seg > 0 && counts[e] > fixed_seg) __trap();      // the caller sized the segments too small: never overflow into a neighbour
             o += fixed_seg > 0 ? fixed_seg : (counts[e] + align - 1) / align * align;
             kept += counts[e];
         }
@@ -708,7 +709,9 @@ extern "C" int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* ac
                            int row_align, int64_t max_rows, int fixed_seg, cudaStream_t stream) {
     AB_REQUIRE(S > 0 && K >= 1 && E >= 1 && E <= 32, "moe_plan: bad shape S=%d K=%d E=%d", S, K, E);
     if (fixed_seg > 0) {
-        AB_REQUIRE(fixed_seg % row_align == 0 && fixed_seg >= (cap < S ? cap : S) && max_rows == (int64_t)E * fixed_seg,
+        // with a capacity limit a segment must hold `cap` rows; without one (cap >= S) the caller sizes it from the counts
+        // it has reduced over the ranks, and the kernel traps rather than overflow a segment
+        AB_REQUIRE(fixed_seg % row_align == 0 && (cap >= S || fixed_seg >= cap) && max_rows == (int64_t)E * fixed_seg,
                    "moe_plan: fixed_seg (%d) must be a multiple of %d, >= cap, and max_rows == E*fixed_seg", fixed_seg, row_align);
     } else {
         AB_REQUIRE(row_align > 0 && max_rows % row_align == 0 && max_rows >= ab_moe_max_rows(S, K, E, cap < S ? cap : S, row_align),

@@ -43,7 +43,8 @@ using namespace ab_scan;
 constexpr int TSP = 4;             // tokens per run
 constexpr int PIPE_SCAN_K = 32;    // tile aggregates a scanner polls per round
 constexpr int INFO_RING = 16;
-constexpr int PIPE_SPIN_LIMIT = 1 << 19;   // ~0.5 s of polling: a protocol error raises the flag instead of hanging the GPU
+constexpr int PIPE_SPIN_LIMIT = 1 << 19;   // ~0.5 s of polling: a protocol error raises the flag and traps (a CUDA error, not a hang,
+                                           // and never a silently wrong result)
 
 // sigmoid of a channel pair.  bf16 activations: single-MUFU tanh form (rel. error ~5e-4, below bf16 resolution);
 // f32 activations: ex2 + rcp
@@ -403,7 +404,7 @@ scan_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
             if (first) {
                 int spins = 0;
                 while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
-                    if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
+                    if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); __trap(); }
                     __nanosleep(p.poll_ns);
                     ld_relaxed_v2(wp, w0, w1);
                 }
@@ -670,7 +671,7 @@ scan_bwd_pipe_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_con
             if (first) {
                 int spins = 0;
                 while (!(word_valid(w0, epoch) && word_valid(w1, epoch))) {
-                    if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); break; }
+                    if (++spins > PIPE_SPIN_LIMIT) { atomicExch(sp.err_flag, 1u); __trap(); }
                     __nanosleep(p.poll_ns);
                     ld_relaxed_v2(wp, w0, w1);
                 }

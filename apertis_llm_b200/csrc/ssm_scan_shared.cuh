@@ -9,7 +9,8 @@ constexpr int TS = 4;            // tokens per thread run
 constexpr int SCAN_K = 32;       // tile aggregates the scanner polls per round trip (shared-memory ring, cp.async)
 constexpr int MODE_FUSED = 0, MODE_AGG = 1, MODE_APPLY = 2;
 constexpr uint32_t ST_AGG = 1, ST_INCL = 2;
-constexpr int SPIN_LIMIT = 1 << 20;   // polls (about a microsecond each) before a wait gives up and raises the error flag
+constexpr int SPIN_LIMIT = 1 << 20;   // polls (about a microsecond each) before a wait gives up: error flag + trap, i.e. a
+                                      // protocol error is a CUDA error at the next synchronisation, never a wrong answer
 
 struct ScanParams {
     int B, L, Di, H;
@@ -73,7 +74,7 @@ __device__ __forceinline__ float wait_incoming(const ScanParams& p, uint32_t epo
     unsigned long long v = ab_ld_relaxed_u64(w);
     int spins = 0;
     while (!word_valid(v, epoch)) {
-        if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); return 0.f; }
+        if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); __trap(); }
         v = ab_ld_relaxed_u64(w);
     }
     return __uint_as_float((uint32_t)v);
@@ -201,7 +202,7 @@ __device__ __forceinline__ int scanner_role(const ScanParams& p, uint32_t epoch,
             ++round;
 #endif
             if (adv == 0) {
-                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); __trap(); }
                 __nanosleep(100);   // nothing new yet: leave the issue slots to the CTA that shares this SM
             }
             __syncthreads();        // ring slots and segment words are rewritten next round
@@ -223,7 +224,7 @@ __device__ __forceinline__ int scanner_role(const ScanParams& p, uint32_t epoch,
             const unsigned long long* w = p.words + (tl * Cs + cc) * 2;
             unsigned long long wp = ab_ld_relaxed_u64(w), wsv = ab_ld_relaxed_u64(w + 1);
             while (!word_valid(wp, epoch) || !word_valid(wsv, epoch)) {
-                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); break; }
+                if (++spins > SPIN_LIMIT) { atomicExch(p.err_flag, 1u); __trap(); }
                 wp = ab_ld_relaxed_u64(w); wsv = ab_ld_relaxed_u64(w + 1);
             }
             hs[cc] = fmaf(__uint_as_float((uint32_t)wp), hs[cc], __uint_as_float((uint32_t)wsv));

@@ -133,6 +133,26 @@ class _PeerState:
         self.sync.barrier(channel=channel)
 
 
+_uniform_checked = set()
+
+
+def _check_uniform(group, S: int, cap: int, training: bool, device):
+    """The exchange has equal splits: every rank must bring the same number of tokens and the same capacity.  Checked with
+    one small all-gather the first time a (tokens, capacity, mode) combination is seen; ragged batches fail here, loudly,
+    instead of hanging NCCL or exchanging misaligned rows."""
+    key = (id(group), S, cap, training)
+    if key in _uniform_checked:
+        return
+    mine = torch.tensor([S, cap, int(training)], dtype=torch.int64, device=device)
+    allv = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(allv, mine, group=group)
+    vals = torch.stack(allv).cpu()
+    if not bool((vals == vals[0]).all()):
+        raise RuntimeError("apertis_b200 EP: every rank of the expert-parallel group must process the same number of tokens with the "
+                           f"same capacity and mode; got (tokens, capacity, training) per rank = {vals.tolist()}")
+    _uniform_checked.add(key)
+
+
 def _peer_state(group, rows: int, Dm: int, device, owner=0):
     """Buffers of one layer (`owner`) and shape: a layer's receive buffer doubles as its saved activation, so layers do
     not share them."""
@@ -164,6 +184,7 @@ class _MoEExpertsEP(torch.autograd.Function):
     """ops._MoEExperts with the expert MLPs executed on the owning ranks."""
 
     @staticmethod
+    @ops._on_tensor_device
     def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, res, cfg, group):
         _lib.ensure_device(x2.device)
         dev = x2.device
@@ -191,7 +212,18 @@ class _MoEExpertsEP(torch.autograd.Function):
         use_noise = noise is not None and noise_scale is not None
         r = ops.moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
                           f(noise_scale) if use_noise else None, K, cfg.get("quant", _lib.ROUTER_EXACT))
-        seg = segment_rows(min(cfg["cap"], S))
+        _check_uniform(group, S, cfg["cap"], training, dev)
+        if cfg["cap"] >= S:
+            # no capacity limit (evaluation, or use_expert_capacity_limit=False): a segment only has to hold the fullest
+            # expert of any rank, not all S tokens - one MAX all-reduce and a host read, off the training path
+            cnt = torch.bincount(r["idx"].reshape(-1).long(), minlength=E)[:E]
+            if cfg["active"] is not None:
+                cnt = cnt * cfg["active"].to(cnt.dtype)
+            mx = cnt.max().reshape(1)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+            seg = segment_rows(max(1, int(mx.item())))
+        else:
+            seg = segment_rows(min(cfg["cap"], S))
         plan = ops.moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"], fixed_seg=seg)
         rows_local = E * seg                                  # == W * El * seg
         cdt = torch.float32 if precise else torch.bfloat16
@@ -275,6 +307,7 @@ class _MoEExpertsEP(torch.autograd.Function):
         return out, lb.to(x2.dtype), rz.to(x2.dtype), counts
 
     @staticmethod
+    @ops._on_tensor_device
     def backward(ctx, dout, dlb, drz, _dcounts):
         (x2, rn_w, rn_b, Wr, br, ln_w_full, W1, W2, noise, stats, gates, idx, probs, lse, lclean, w, aux, xr, h, hpre, y) = ctx.saved_tensors
         cfg, plan, rplan, group = ctx.cfg, ctx.plan, ctx.rplan, ctx.group

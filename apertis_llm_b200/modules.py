@@ -194,6 +194,13 @@ class AdaptiveExpertSystem(nn.Module):
             self.load_balancing_loss_coef = self.router_z_loss_coef = self.expert_dropout_prob = self.noisy_routing_alpha = 0.0
             return
         E, Dm, I = self.num_experts, self.hidden_size, self.intermediate_size
+        # limits of the kernels (the reference has none): say so here, not at the first forward
+        if E > 32 or self.experts_per_token > 8:
+            raise ValueError(f"the B200 MoE kernels support num_experts <= 32 and experts_per_token <= 8 (got {E}, {self.experts_per_token})")
+        if Dm % 8 or I % 8:
+            raise ValueError(f"hidden_size ({Dm}) and intermediate_size ({I}) must be multiples of 8 (16-byte rows for TMA)")
+        if not 0.0 <= float(g("hidden_dropout_prob", 0.0)) < 1.0:
+            raise ValueError("hidden_dropout_prob must be in [0, 1)")
         self.eps = config.layer_norm_eps
         self.router_norm = nn.LayerNorm(Dm, eps=self.eps)
         self.router = nn.Linear(Dm, E)
@@ -399,7 +406,8 @@ def patch_apertis_model(model: nn.Module, ep_group=None) -> nn.Module:
 
     For every layer: ``attention.attention_mechanism_impl`` (core.py:650) is replaced by a
     SelectiveLinearAttention that adopts the SAME Parameter objects, and ``feed_forward.ffn`` (core.py:861)
-    by an AdaptiveExpertSystem whose stacked parameters are filled from the per-expert modules."""
+    by an AdaptiveExpertSystem whose stacked parameters are filled from the per-expert modules (new Parameter
+    objects, in the device and dtype of the old ones): patch BEFORE building the optimizer or wrapping in DDP."""
     layers = model.model.layers if hasattr(model, "model") and hasattr(model.model, "layers") else model.layers
     for layer in layers:
         att = layer.attention
@@ -416,7 +424,8 @@ def patch_apertis_model(model: nn.Module, ep_group=None) -> nn.Module:
         if getattr(ff, "is_expert_system", False) and type(oldf).__name__ == "AdaptiveExpertSystem" \
                 and not isinstance(oldf, AdaptiveExpertSystem):
             newf = AdaptiveExpertSystem(ff.config, activation_function_override=ff.config.hidden_act, ep_group=ep_group)
-            newf.to(next(oldf.parameters()).device)
+            ref_p = next(oldf.parameters())
+            newf.to(device=ref_p.device, dtype=ref_p.dtype)
             newf.load_state_dict(oldf.state_dict(), strict=True)
             newf.train(oldf.training)
             ff.ffn = newf

@@ -17,6 +17,19 @@ import torch
 from . import _lib
 from ._lib import AB_BF16, AB_F32, ROW_ALIGN, call, dt, ptr, query, stream_ptr
 
+def _on_tensor_device(fn):
+    """Runs an autograd Function's forward / backward with the device of its first CUDA tensor argument current: the C ABI
+    launches on the current device and stream, so a module living on cuda:1 while cuda:0 is current must switch first."""
+    def wrapper(ctx, *args):
+        dev = next((a.device for a in args if torch.is_tensor(a) and a.is_cuda), None)
+        if dev is None:
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
 # --------------------------------------------------------------------------------------------
 # workspaces
 # --------------------------------------------------------------------------------------------
@@ -92,6 +105,7 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, weight, bias, eps, out_dtype):
         _lib.ensure_device(x.device)
         shape = x.shape
@@ -107,6 +121,7 @@ class _LayerNorm(torch.autograd.Function):
         return y.view(shape)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy):
         x2, stats, w = ctx.saved_tensors
         S, Dm = x2.shape
@@ -127,6 +142,7 @@ class _LayerNormSkip(torch.autograd.Function):
     leaving the sum of the two branches to a separate elementwise pass over [tokens, Dm]."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, weight, bias, eps, out_dtype):
         _lib.ensure_device(x.device)
         shape = x.shape
@@ -142,6 +158,7 @@ class _LayerNormSkip(torch.autograd.Function):
         return y.view(shape), x.view_as(x)
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy, dskip):
         x2, stats, w = ctx.saved_tensors
         S, Dm = x2.shape
@@ -161,6 +178,7 @@ class _LayerNormSkip(torch.autograd.Function):
 
 class _DropoutAdd(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, sub, res, p):
         _lib.ensure_device(sub.device)
         sub = sub.contiguous()
@@ -172,6 +190,7 @@ class _DropoutAdd(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dout):
         if ctx.p == 0:
             return dout.to(ctx.sub_dtype), dout, None
@@ -202,6 +221,7 @@ def layer_norm_skip(x, weight, bias, eps, out_dtype=None):
 # --------------------------------------------------------------------------------------------
 class _CausalConv1dSiLU(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, xp, weight, bias):
         _lib.ensure_device(xp.device)
         xp = _rows(xp)
@@ -217,6 +237,7 @@ class _CausalConv1dSiLU(torch.autograd.Function):
         return xa
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dxa):
         xp, w, b = ctx.saved_tensors
         B, L, Di = xp.shape
@@ -242,6 +263,7 @@ def causal_conv1d_silu(xp: torch.Tensor, weight: torch.Tensor, bias: torch.Tenso
 # --------------------------------------------------------------------------------------------
 class _SelectiveScan(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, xa, dlog, BC, z, A_log, D, h0, want_yssm, want_hlast, mode):
         _lib.ensure_device(xa.device)
         xa = xa.contiguous()
@@ -279,6 +301,7 @@ class _SelectiveScan(torch.autograd.Function):
         return y, y_ssm, h_last
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy, dyssm, _dh):
         xa, dlog, BC, z, A, Dv, hstart = ctx.saved_tensors
         B, L, Di = xa.shape
@@ -747,6 +770,7 @@ class _MoEExperts(torch.autograd.Function):
     returns out [S,Dm], lb, rz, counts (non-differentiable int32 [E])"""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x2, rn_w, rn_b, Wr, br, noise, noise_scale, ln_w, ln_b, W1, b1, W2, b2, res, cfg):
         _lib.ensure_device(x2.device)
         dev = x2.device
@@ -815,6 +839,7 @@ class _MoEExperts(torch.autograd.Function):
         return out, lb.to(x2.dtype) if torch.is_tensor(lb) else lb, rz.to(x2.dtype) if torch.is_tensor(rz) else rz, counts
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dout, dlb, drz, _dcounts):
         (x2, rn_w, rn_b, Wr, br, ln_w, W1, W2, noise, stats, gates, idx, probs, lse, lclean, w, aux, xn, h, hpre, y) = ctx.saved_tensors
         cfg, plan = ctx.cfg, ctx.plan

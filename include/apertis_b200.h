@@ -190,7 +190,8 @@ int ab_moe_topk_from_logits(const float* logits, float* gates, int32_t* idx, flo
  * tile_expert[max_rows/row_align] expert of each row tile (-1 beyond the end); n_rows[2] = {padded
  * total rows, kept rows}.  max_rows = ab_moe_max_rows(S,K,E,cap,row_align).  No host synchronisation.
  * fixed_seg > 0 (expert-parallel exchange layout): every expert segment is exactly fixed_seg rows
- * (a multiple of row_align, >= cap) at offset e*fixed_seg and max_rows must equal E*fixed_seg. */
+ * (a multiple of row_align; >= cap when cap < S, otherwise at least the largest count - the kernel traps if a segment
+ * would overflow) at offset e*fixed_seg and max_rows must equal E*fixed_seg. */
 int64_t ab_moe_max_rows(int S, int K, int E, int cap, int row_align);
 size_t ab_moe_plan_workspace_bytes(int S, int K, int E);
 int ab_moe_plan(const int32_t* idx, const float* w, const int32_t* active, int cap, int32_t* counts, int32_t* seg_off,
