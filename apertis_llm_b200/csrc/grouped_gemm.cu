@@ -813,11 +813,16 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
 // Few output tiles and many source blocks (expert parallelism with one or two local experts): the contraction is cut over
 // the source blocks so that every CTA pair has work; slices = the largest divisor of nsrc that still fits one wave.
 int grouped_tn_slices(int M, int N, int E, int nsrc) {
-    const int tiles = (int)(E * ab_ceil_div(M, PM) * ab_ceil_div(N, pick_bn(N, true)));
+    const int64_t tiles = (int64_t)E * ab_ceil_div(M, PM) * ab_ceil_div(N, pick_bn(N, true));
     const int pairs = ab_num_sms() / 2;
+    // time ~ waves(s) / s; a finer cut must win at least 12 % (it also costs the sum of the partial products)
     int best = 1;
-    for (int s = 2; s <= nsrc; ++s)
-        if (nsrc % s == 0 && tiles * s <= pairs + pairs / 8) best = s;
+    double best_cost = (double)ab_ceil_div(tiles, pairs);
+    for (int s = 2; s <= nsrc && s <= 4; ++s) {
+        if (nsrc % s) continue;
+        const double cost = (double)ab_ceil_div(tiles * s, pairs) / s;
+        if (cost < 0.88 * best_cost) { best = s; best_cost = cost; }
+    }
     return best;
 }
 }  // namespace

@@ -132,6 +132,12 @@ def run_gpu(rank, world, args):
         bad = {k: v for k, v in errs.items() if not v < tol}
         assert not bad, (rank, autocast, bad)
         worst = max(worst, max(errs.values()))
+        # evaluation: no capacity limit, the exchange segments are sized from the counts reduced over the ranks
+        lr.eval(); le.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            ev_r, ev_e = lr(x.to(dev))[0], le(x.to(dev))[0]
+        assert rel(ev_e, ev_r) < tol, (rank, autocast, "eval", rel(ev_e, ev_r))
+        assert torch.equal(lr.feed_forward.ffn.last_counts, le.feed_forward.ffn.last_counts)
     transport = os.environ.get("APERTIS_B200_EP", "auto")
     if transport == "peer":
         assert ep._peer_cache, "the peer-memory transport was requested but never used"
