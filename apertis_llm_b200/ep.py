@@ -286,7 +286,7 @@ class _MoEExpertsEP(torch.autograd.Function):
                  stream_ptr())
         aux = r["aux"]
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
-        lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
+        lb = (cfg["lb_coef"] * E / (S * S)) * (aux[:E] * aux[E:2 * E]).sum() if (training and cfg["lb_coef"] > 0) else zero
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
         ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, El=El, I=I, W=W, seg=seg, use_noise=use_noise, rows=rows_local, cdt=cdt, drop_p=drop_p,
                        out_p=out_p, has_res=res is not None, res_shape=res.shape if res is not None else None,

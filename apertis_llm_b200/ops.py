@@ -820,7 +820,7 @@ class _MoEExperts(torch.autograd.Function):
         # ---- aux losses (core.py:499-505, 524-526) from the kernel's deterministic sums
         aux = r["aux"]
         zero = torch.zeros((), dtype=x2.dtype, device=dev)
-        lb = (cfg["lb_coef"] * E / (S * S)) * torch.dot(aux[:E], aux[E:2 * E]) if (training and cfg["lb_coef"] > 0) else zero
+        lb = (cfg["lb_coef"] * E / (S * S)) * (aux[:E] * aux[E:2 * E]).sum() if (training and cfg["lb_coef"] > 0) else zero
         rz = (cfg["rz_coef"] / S) * aux[2 * E] if (training and cfg["rz_coef"] > 0) else zero
         ctx.cfg = dict(cfg, S=S, Dm=Dm, E=E, I=I, use_noise=use_noise, max_rows=max_rows, cdt=cdt, drop_p=drop_p, out_p=out_p,
                        has_res=res is not None, res_shape=res.shape if res is not None else None,
