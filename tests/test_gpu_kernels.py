@@ -389,6 +389,79 @@ def test_grouped_gemm_tn_source_blocks(W, El, M, N):
         assert rel_err(out[e], ref) < 2e-5, e
 
 
+def test_ep_peer_kernels_two_ranks_emulated_on_one_gpu():
+    """The peer-memory kernels of expert parallelism (ab_ep_permute_ln, ab_ep_grouped_gemm_nt / nn, ab_ep_unpermute_bwd)
+    with two ranks emulated on ONE device: each 'rank' gets its own receive buffers and the address table lists both.  A
+    rank's producers must leave exactly the rows, at exactly the places, that the local kernels plus an all-to-all would
+    (the multi-GPU NCCL / NVLink runs of the same kernels are tests/test_ep.py and bench.py's ep_parity)."""
+    import ctypes
+    from apertis_llm_b200 import _lib, ops
+    from apertis_llm_b200._lib import call, dt, ptr, stream_ptr
+    d = dev()
+    RA = _lib_row_align()
+    W, El, E, K, S, Dm, I = 2, 2, 4, 2, 600, 96, 160
+    cap = 260
+    seg = (cap + RA - 1) // RA * RA
+    rpp = El * seg                       # rows per peer
+    rows = W * rpp
+    g = torch.Generator().manual_seed(11)
+    table = lambda bufs: (ctypes.c_uint64 * W)(*[b.data_ptr() for b in bufs])
+    xn_recv = [torch.full((rows, Dm), float("nan"), dtype=torch.bfloat16, device=d) for _ in range(W)]
+    y_in = [torch.full((rows, Dm), float("nan"), dtype=torch.bfloat16, device=d) for _ in range(W)]
+    dy_recv = [torch.full((rows, Dm), float("nan"), dtype=torch.bfloat16, device=d) for _ in range(W)]
+    local = []
+    for rank in range(W):
+        x2 = torch.randn(S, Dm, generator=g).to(d)
+        idx = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(S)]).to(torch.int32).to(d)
+        w = (torch.rand(S, K, generator=g) * 0.9 + 0.05).to(d)
+        stats = torch.stack([x2.mean(-1), (x2.var(-1, unbiased=False) + 1e-12).rsqrt()], -1).contiguous()
+        ln_w, ln_b = (1 + 0.1 * torch.randn(E, Dm, generator=g)).to(d), (0.1 * torch.randn(E, Dm, generator=g)).to(d)
+        plan = ops.moe_plan(idx, w, E, cap, None, fixed_seg=seg)
+        # local kernel, then what an all-to-all would deliver: block `dst` of the local layout -> block `rank` of rank dst
+        xn = torch.empty(rows, Dm, dtype=torch.bfloat16, device=d)
+        call("ab_moe_permute_ln", ptr(x2), ptr(stats), ptr(ln_w), ptr(ln_b), ptr(plan["tok_of_row"]), ptr(plan["tile_expert"]),
+             ptr(plan["n_rows"]), ptr(xn), Dm, RA, rows, dt(x2), dt(xn), stream_ptr())
+        call("ab_ep_permute_ln", ptr(x2), ptr(stats), ptr(ln_w), ptr(ln_b), ptr(plan["tok_of_row"]), ptr(plan["tile_expert"]),
+             ptr(plan["n_rows"]), table(xn_recv), W, rank, rpp, Dm, RA, rows, dt(x2), dt(xn), stream_ptr())
+        dout = torch.randn(S, Dm, generator=g).to(d)
+        yloc = (torch.randn(rows, Dm, generator=g) * 0.5).to(torch.bfloat16).to(d)
+        dy = torch.empty(rows, Dm, dtype=torch.bfloat16, device=d)
+        dwr, dwr2 = torch.empty(rows, device=d), torch.empty(rows, device=d)
+        call("ab_moe_unpermute_bwd", ptr(dout), ptr(yloc), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
+             ptr(dy), ptr(dwr), 0.0, None, K, Dm, rows, dt(dout), dt(yloc), dt(dy), stream_ptr())
+        call("ab_ep_unpermute_bwd", ptr(dout), ptr(yloc), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
+             table(dy_recv), W, rank, rpp, ptr(dwr2), 0.0, None, K, Dm, rows, dt(dout), dt(yloc), dt(dy), stream_ptr())
+        assert torch.equal(dwr, dwr2)
+        local.append((xn, dy))
+    torch.cuda.synchronize()
+    for owner in range(W):
+        for src in range(W):
+            blk = slice(src * rpp, (src + 1) * rpp)
+            sent = slice(owner * rpp, (owner + 1) * rpp)
+            assert torch.equal(xn_recv[owner][blk], local[src][0][sent]), ("dispatch", owner, src)
+            assert torch.equal(dy_recv[owner][blk], local[src][1][sent]), ("dY dispatch", owner, src)
+    # the owners' GEMMs return their result rows into the source ranks' buffers
+    tile_expert = torch.arange(El, dtype=torch.int32, device=d).repeat_interleave(seg // RA).repeat(W)
+    n_rows = torch.full((2,), rows, dtype=torch.int32, device=d)
+    rplan = dict(tile_expert=tile_expert, n_rows=n_rows)
+    for owner in range(W):
+        A = xn_recv[owner]
+        Wt = (torch.randn(El, Dm, Dm, generator=g) * 0.1).to(torch.bfloat16).to(d)
+        bias = torch.randn(El, Dm, generator=g).to(d)
+        ref = ops.grouped_gemm("nt", A, Wt, rplan, Dm, Dm, El, bias=bias, epi=_lib.EPI_BIAS)
+        call("ab_ep_grouped_gemm_nt", ptr(A), ptr(Wt), ptr(bias), None, table(y_in), W, owner, rpp, ptr(tile_expert), ptr(n_rows), rows,
+             Dm, Dm, El, _lib.EPI_BIAS, 0, dt(torch.bfloat16), stream_ptr())
+        ref2 = ops.grouped_gemm("nn", A, Wt, rplan, Dm, Dm, El)
+        torch.cuda.synchronize()
+        for src in range(W):
+            assert torch.equal(y_in[src][owner * rpp:(owner + 1) * rpp], ref[src * rpp:(src + 1) * rpp]), ("combine", owner, src)
+        call("ab_ep_grouped_gemm_nn", ptr(A), ptr(Wt), None, None, table(y_in), W, owner, rpp, ptr(tile_expert), ptr(n_rows), rows,
+             Dm, Dm, El, _lib.EPI_NONE, 0, dt(torch.bfloat16), stream_ptr())
+        torch.cuda.synchronize()
+        for src in range(W):
+            assert torch.equal(y_in[src][owner * rpp:(owner + 1) * rpp], ref2[src * rpp:(src + 1) * rpp]), ("dXn return", owner, src)
+
+
 # ------------------------------------------------------------------------------------------------
 # block-wrapper LayerNorm
 # ------------------------------------------------------------------------------------------------
