@@ -45,6 +45,8 @@ SIGNATURES = {
     "ab_ssm_scan_bwd": (I, [P, I64, P, P, I64, P, I64, P, P, P, P, P, P, I64, P, P, I64, P, I64, P, I64, I, P, P, P, P, SZ,
                             I, I, I, I, I, P]),
     "ab_gemm_row_tile": (I, []),
+    "ab_shifted_ce_fwd": (I, [P, P, P, P, P, P, I, I, I, I64, I, P]),
+    "ab_shifted_ce_bwd": (I, [P, P, P, P, P, I, I, I, I64, I, P]),
     "ab_ep_permute_ln": (I, [P, P, P, P, P, P, P, P, I, I, I64, I, I, I64, I, I, P]),
     "ab_ep_unpermute_bwd": (I, [P, P, P, P, P, P, P, I, I, I64, P, F, P, I, I, I64, I, I, I, P]),
     "ab_ep_grouped_gemm_nt": (I, [P, P, P, P, P, I, I, I64, P, P, I64, I, I, I, I, I, I, P]),
@@ -167,7 +169,7 @@ KERNELS_PER_CALL = {
     "ab_moe_unpermute_bwd": 1, "ab_moe_permute_ln_bwd": 2, "ab_moe_segment_colsum": 2, "ab_moe_router_bwd": 3,
     "ab_layernorm_fwd": 1, "ab_layernorm_bwd": 3,
     "ab_grouped_gemm_nt": 1, "ab_grouped_gemm_nn": 1, "ab_grouped_gemm_tn": 1, "ab_cast_f32_to_bf16": 1,
-    "ab_ep_permute_ln": 1, "ab_ep_unpermute_bwd": 1, "ab_ep_grouped_gemm_nt": 1, "ab_ep_grouped_gemm_nn": 1,
+    "ab_shifted_ce_fwd": 2, "ab_shifted_ce_bwd": 1, "ab_ep_permute_ln": 1, "ab_ep_unpermute_bwd": 1, "ab_ep_grouped_gemm_nt": 1, "ab_ep_grouped_gemm_nn": 1,
     "ab_split_f32_to_bf16x3": 1, "ab_split_f32_to_bf16x3_rows": 1,
 }
 launch_count = 0          # kernels launched through this binding since import (bench.py reads deltas)

@@ -401,8 +401,45 @@ class ApertisLayerB200(nn.Module):
         return out, att_w, cache, lb, rz
 
 
-def patch_apertis_model(model: nn.Module, ep_group=None) -> nn.Module:
+def _causal_lm_forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                       pixel_values=None, labels=None, use_cache=None, output_attentions=None, output_hidden_states=None):
+    """ApertisForCausalLM.forward (core.py:1361-1473) with the language-model head and the shifted cross-entropy on the
+    B200 kernels: same arguments, same return tuple.  Installed on a model instance by
+    patch_apertis_model(fuse_lm_head=True); shapes the fused path does not cover (no labels, a vocabulary that is not a
+    multiple of 8, label / logit lengths that differ, sequences of one token) go through the reference's own forward."""
+    ref_forward = type(self).forward
+    kw = dict(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids, past_key_values=past_key_values,
+              inputs_embeds=inputs_embeds, pixel_values=pixel_values, labels=labels, use_cache=use_cache,
+              output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+    V = self.lm_head.weight.shape[0]
+    if labels is None or V % 8 or getattr(self.lm_head, "bias", None) is not None:
+        return ref_forward(self, **kw)
+    model_outputs = self.model(**{k: v for k, v in kw.items() if k != "labels"})
+    hidden = model_outputs[0]
+    text_hidden = hidden
+    if self.config.multimodal and pixel_values is not None and past_key_values is None and input_ids is not None:   # core.py:1398-1405
+        start = hidden.shape[1] - input_ids.shape[1]
+        if start >= 0:
+            text_hidden = hidden[:, start:, :]
+    if text_hidden.shape[1] != labels.shape[1] or text_hidden.shape[1] < 2 or not text_hidden.is_cuda:
+        return ref_forward(self, **kw)
+    ac = _autocast_dtype()
+    precise = text_hidden.dtype == torch.float32 and ac is None
+    logits, loss = ops.lm_head_cross_entropy(text_hidden.contiguous(), self.lm_head.weight, labels, -100, precise)
+    if ac == torch.float16:
+        logits = logits.to(torch.float16)
+    if model_outputs[4] is not None:                                # core.py:1449-1456: aux losses of the expert layers
+        loss = loss + model_outputs[4]
+    if model_outputs[5] is not None:
+        loss = loss + model_outputs[5]
+    return (loss, logits) + tuple(model_outputs[1:])
+
+
+def patch_apertis_model(model: nn.Module, ep_group=None, fuse_lm_head: bool = False) -> nn.Module:
     """Swaps the B200 modules into a reference ApertisModel / ApertisForCausalLM in place.
+
+    fuse_lm_head=True additionally routes ApertisForCausalLM's language-model head and shifted cross-entropy
+    (core.py:1412-1460) through the B200 kernels (_causal_lm_forward): the tied embedding matrix is used as it is.
 
     For every layer: ``attention.attention_mechanism_impl`` (core.py:650) is replaced by a
     SelectiveLinearAttention that adopts the SAME Parameter objects, and ``feed_forward.ffn`` (core.py:861)
@@ -429,4 +466,7 @@ def patch_apertis_model(model: nn.Module, ep_group=None) -> nn.Module:
             newf.load_state_dict(oldf.state_dict(), strict=True)
             newf.train(oldf.training)
             ff.ffn = newf
+    if fuse_lm_head and hasattr(model, "lm_head") and hasattr(model, "model"):
+        import types
+        model.forward = types.MethodType(_causal_lm_forward, model)
     return model

@@ -665,6 +665,59 @@ def ssm_core(xz, conv_w, conv_b, Wp, Wdt, dt_bias, A_log, D, precise):
 
 
 # --------------------------------------------------------------------------------------------
+# language-model head + shifted cross-entropy (core.py:1412-1460)
+# --------------------------------------------------------------------------------------------
+class _LMHeadCE(torch.autograd.Function):
+    """logits = hidden @ weight^T on the tcgen05 GEMM, loss = CrossEntropy(logits[:, :-1], labels[:, 1:]) (mean over the
+    positions whose label is not ignore_index) with one read of the logits forward and one write of d logits backward.
+    Returns (logits [B, L, V], loss); both are differentiable (a gradient arriving on the logits is added)."""
+
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, hidden, weight, labels, ignore_index, precise):
+        _lib.ensure_device(hidden.device)
+        dev = hidden.device
+        B, L, Dm = hidden.shape
+        V = weight.shape[0]
+        h2 = hidden.reshape(B * L, Dm)
+        hb = h2.float().contiguous() if precise else _as_bf16(h2)
+        wb = weight.float().contiguous() if precise else _as_bf16(weight)
+        logits = dense_nt(hb, wb, precise)                      # [B*L, V] fp32 | bf16
+        labels = labels.to(torch.int64).contiguous()
+        n = B * (L - 1)
+        f32 = dict(dtype=torch.float32, device=dev)
+        lse, row_loss, row_valid, sums = torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(2, **f32)
+        call("ab_shifted_ce_fwd", ptr(logits), ptr(labels), ptr(lse), ptr(row_loss), ptr(row_valid), ptr(sums), B, L, V, int(ignore_index),
+             dt(logits), stream_ptr(dev))
+        loss = sums[0] / sums[1]
+        ctx.save_for_backward(hb, wb, logits, labels, lse, sums)
+        ctx.meta = (B, L, V, Dm, int(ignore_index), precise, hidden.dtype, weight.dtype)
+        return logits.view(B, L, V), loss
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, dlogits_ext, dloss):
+        hb, wb, logits, labels, lse, sums = ctx.saved_tensors
+        B, L, V, Dm, ignore_index, precise, hdtype, wdtype = ctx.meta
+        dev = logits.device
+        g = dloss.float() if dloss is not None else torch.zeros((), dtype=torch.float32, device=dev)
+        scale = (g / sums[1]).reshape(1).contiguous()
+        dl = torch.empty_like(logits)
+        call("ab_shifted_ce_bwd", ptr(logits), ptr(labels), ptr(lse), ptr(scale), ptr(dl), B, L, V, ignore_index, dt(logits), stream_ptr(dev))
+        if dlogits_ext is not None:
+            dl += dlogits_ext.reshape(B * L, V).to(dl.dtype)
+        dlb = dl if precise else _as_bf16(dl)
+        dh = dense_nn(dlb, wb, precise).view(B, L, Dm).to(hdtype)
+        dw = dense_tn(dlb, hb, precise).to(wdtype)
+        return dh, dw, None, None, None
+
+
+def lm_head_cross_entropy(hidden, weight, labels, ignore_index: int = -100, precise: bool = False):
+    """(logits, loss) of the causal-LM head; see _LMHeadCE."""
+    return _LMHeadCE.apply(hidden, weight, labels, ignore_index, precise)
+
+
+# --------------------------------------------------------------------------------------------
 # MoE
 # --------------------------------------------------------------------------------------------
 def _u8(n, dev):

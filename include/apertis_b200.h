@@ -328,6 +328,20 @@ size_t ab_dense_gemm_tn_workspace_bytes(int64_t S, int M, int N);
 int ab_dense_gemm_tn(const void* A, const void* Bm, float* Cw, void* ws, size_t ws_bytes, int64_t S, int M, int N,
                      cudaStream_t stream);
 
+/* ---- language-model head: shifted cross-entropy  (core.py:1412-1460) -----------------------------
+ * loss = mean over the counted positions of CE(logits[b, l, :], labels[b, l+1]), l < L-1, labels == ignore_index not counted
+ * (nn.CrossEntropyLoss(ignore_index=-100) on logits[..., :-1, :] / labels[..., 1:]).  The logits [B, L, V] come from
+ * ab_dense_gemm_nt of the hidden states with the (tied) embedding matrix, in c_dtype; V*sizeof must be a multiple of 16.
+ *   fwd: lse[B*(L-1)] = log-sum-exp per row, row_loss / row_valid [B*(L-1)], sums[2] = {sum of row losses, counted rows}
+ *        (fixed-order reduction); the loss is sums[0] / sums[1].  One read of the logits.
+ *   bwd: dlogits[B, L, V] = (softmax - onehot) * scale[0] on the counted positions, 0 elsewhere (scale: device float =
+ *        upstream gradient / sums[1]); feeds ab_dense_gemm_nn / _tn for the hidden-state and embedding gradients.
+ * An out-of-range label traps (torch raises a device assert). */
+int ab_shifted_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* row_loss, float* row_valid, float* sums,
+                      int B, int L, int V, int64_t ignore_index, int dtype, cudaStream_t stream);
+int ab_shifted_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* scale, void* dlogits, int B,
+                      int L, int V, int64_t ignore_index, int dtype, cudaStream_t stream);
+
 /* ---- block wrappers: pre-norm LayerNorm  (core.py:694-695, 887-888) ------------
  * y = (x - mean) * rstd * w + b per row, eps inside the sqrt; stats [S,2] = (mean, rstd) saved for the backward.
  * backward: dx = LayerNorm-backward(dy) (+ dres when given: the residual branch's gradient, fused add),

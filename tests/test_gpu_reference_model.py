@@ -252,6 +252,61 @@ def test_patched_model_fp16_autocast_with_grad_scaler():
     scaler.update()
 
 
+def test_fused_lm_head_cross_entropy_matches_reference():
+    """ApertisForCausalLM's lm_head + shifted CrossEntropyLoss (core.py:1412-1460) on the B200 kernels
+    (patch_apertis_model(fuse_lm_head=True)): loss, logits and every gradient (the tied embedding matrix included) against
+    the unmodified reference, with ignored labels (-100) in the batch; text and multimodal; then bf16 autocast."""
+    import apertis_llm_b200 as ab
+    for multimodal in (False, True):
+        core, ref, mine = make_models(multimodal=multimodal, vocab=208)
+        ab.patch_apertis_model(mine, fuse_lm_head=True)
+        ref.train(); mine.train()
+        batch = text_batch(vocab=208)
+        labels = batch["labels"].clone()
+        labels[0, :7] = -100
+        labels[1, 40:55] = -100
+        batch["labels"] = labels
+        if multimodal:
+            g = torch.Generator().manual_seed(3)
+            batch["pixel_values"] = torch.rand(2, 3, 32, 32, generator=g).to(dev())
+        compare_models(ref, mine, batch, 1e-4)
+    core, ref, mine = make_models(vocab=208, router_gain=6.0)
+    ab.patch_apertis_model(mine, fuse_lm_head=True)
+    ref.train(); mine.train()
+    compare_models(ref, mine, text_batch(vocab=208), 2e-2, autocast=torch.bfloat16, grad_tol=8e-2, robust=True)
+    # a vocabulary the GEMM cannot tile (not a multiple of 8) keeps the reference's own head
+    core, ref, mine = make_models(vocab=211)
+    ab.patch_apertis_model(mine, fuse_lm_head=True)
+    ref.train(); mine.train()
+    compare_models(ref, mine, text_batch(vocab=211), 1e-4)
+
+
+def test_shifted_cross_entropy_kernel_vs_torch():
+    """ab_shifted_ce_fwd / _bwd alone at a real vocabulary size: loss and d logits against torch's cross_entropy on the
+    shifted fp32 logits, ignore_index rows, bf16 and fp32 logits."""
+    from apertis_llm_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    B, L, Dm, V = 2, 33, 64, 32000
+    hidden = torch.randn(B, L, Dm, generator=g).to(dev())
+    weight = (torch.randn(V, Dm, generator=g) * 0.2).to(dev())
+    labels = torch.randint(0, V, (B, L), generator=g).to(dev())
+    labels[0, 3:9] = -100
+    for precise in (True, False):
+        h, w = hidden.clone().requires_grad_(True), weight.clone().requires_grad_(True)
+        logits, loss = ops.lm_head_cross_entropy(h, w, labels, -100, precise)
+        loss.backward()
+        hr, wr = hidden.clone().requires_grad_(True), weight.clone().requires_grad_(True)
+        lg = F.linear(hr, wr) if precise else F.linear(hr.bfloat16(), wr.bfloat16()).float()
+        ref = F.cross_entropy(lg[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1), ignore_index=-100)
+        ref.backward()
+        tol = 1e-4 if precise else 2e-2
+        assert abs(float(loss) - float(ref)) < tol * abs(float(ref)), (float(loss), float(ref))
+        assert rel_err(logits.float(), lg.detach()) < tol
+        # d hidden contracts over the 32000-wide vocabulary: fp32 accumulation order alone moves it by ~1e-4 of its maximum
+        assert rel_err(h.grad, hr.grad) < (3e-4 if precise else tol) and rel_err(w.grad, wr.grad) < tol
+
+
 def test_patched_model_eval_and_generate_match_reference():
     """Eval forward and greedy generate() (core.py:1520-1644): prefill + cached single-token steps through the drop-in's
     recurrent path, including the reference's cached-conv quirk (core.py:369-373)."""
