@@ -78,15 +78,36 @@ __device__ __forceinline__ int block_excl_scan(int cnt, int* warp_tot /*[32]*/, 
 // back to the same algorithm over global memory.
 constexpr int TPT = 8;   // consecutive tokens per thread per compaction sweep
 
+// From a 256-bin histogram: the bin holding the `need`-th largest element counted from the top, and how many are still needed
+// inside it.  Warp 0: lane l owns bins [8l, 8l+8); suffix sums over the lanes by shuffles instead of a 256-step serial scan.
 __device__ __forceinline__ void radix_select_bin(int* hist, int& need, int& sel_bin, int* s_sel_bin, int* s_need) {
-    if (threadIdx.x == 0) {
-        int nd = need, bin = 255;
-        for (; bin > 0; --bin) {
-            if (hist[bin] >= nd) break;
-            nd -= hist[bin];
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int h[8], mine = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; mine += h[i]; }
+        // elements in the bins of higher lanes: inclusive suffix scan by shuffles, minus the lane's own count
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
         }
-        *s_sel_bin = bin;
-        *s_need = nd;
+        const int above = incl - mine;
+        const int nd0 = need;
+        const bool here = above < nd0 && above + mine >= nd0;       // the wanted element lies in this lane's bins
+        const unsigned who = __ballot_sync(0xffffffffu, here);
+        if (who == 0u) {                                            // fewer than `need` elements in total: lowest bin
+            if (lane == 0) { *s_sel_bin = 0; *s_need = nd0 - (above + mine) + h[0]; }
+        } else if (lane == __ffs(who) - 1) {
+            int nd = nd0 - above, bin = 7;
+            for (; bin > 0; --bin) {
+                if (h[bin] >= nd) break;
+                nd -= h[bin];
+            }
+            *s_sel_bin = lane * 8 + bin;
+            *s_need = nd;
+        }
     }
     __syncthreads();
     sel_bin = *s_sel_bin;
@@ -605,10 +626,27 @@ __global__ void __launch_bounds__(256) tile_colsum_kernel(const T* __restrict__ 
 #pragma unroll
     for (int v = 0; v < 8; ++v) acc[v] = 0.f;
     if (c0 < C) {
-        for (int i = warp; i < align; i += 8) {
-            const T* row = a + ((size_t)t * align + i) * C + c0;
+        // 8 columns per thread as whole 16-byte vectors, 4 rows in flight
+        constexpr int VN = 16 / (int)sizeof(T);          // elements per vector (8 bf16 / 4 fp32)
+        for (int i0 = warp; i0 < align; i0 += 32) {
+            uint4 q[4][8 / VN];
 #pragma unroll
-            for (int v = 0; v < 8; ++v) acc[v] += ab_to_float(row[v]);
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 8;
+                const uint4* row = reinterpret_cast<const uint4*>(a + ((size_t)t * align + i) * C + c0);
+#pragma unroll
+                for (int w = 0; w < 8 / VN; ++w) q[u][w] = i < align ? __ldg(row + w) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int w = 0; w < 8 / VN; ++w) {
+                    float f[VN];
+                    ab_vec16<T>::unpack(q[u][w], f);
+#pragma unroll
+                    for (int v = 0; v < VN; ++v) acc[w * VN + v] += f[v];
+                }
+            }
         }
     }
 #pragma unroll
@@ -904,7 +942,7 @@ extern "C" int ab_moe_segment_colsum(const void* a, const int32_t* tile_expert, 
     const int sub = work_rows(row_align), ratio = row_align / sub;
     const int ntiles = (int)(max_rows / sub);
     float* part = (float*)ws;
-    AB_REQUIRE(C % 8 == 0, "moe_segment_colsum: column count must be a multiple of 8");
+    AB_REQUIRE(C % 8 == 0 && ((uintptr_t)a % 16) == 0, "moe_segment_colsum: column count must be a multiple of 8 and the matrix 16-byte aligned");
     dim3 cgrid(ntiles, (unsigned)ab_ceil_div(C, 256));
     if (dtype == AB_F32) tile_colsum_kernel<float><<<cgrid, 256, 0, stream>>>((const float*)a, tile_expert, n_rows, part, C, sub, ratio);
     else tile_colsum_kernel<__nv_bfloat16><<<cgrid, 256, 0, stream>>>((const __nv_bfloat16*)a, tile_expert, n_rows, part, C, sub, ratio);

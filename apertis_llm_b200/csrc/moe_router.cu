@@ -234,7 +234,7 @@ __device__ __forceinline__ float reduce_dots_to_lane(float (&dot)[EM], int lane,
 }
 
 template <typename T, int EM, int NV>
-__global__ void __launch_bounds__(WARPS * 32) router_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
+__global__ void __launch_bounds__(WARPS * 32, (NV * ab_vec16<T>::N <= 24 && EM <= 8) ? 4 : 1) router_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ ln_w,
                                                                     const float* __restrict__ ln_b, float eps,
                                                                     const float* __restrict__ Wr, const float* __restrict__ br,
                                                                     const float* __restrict__ noise,
@@ -550,11 +550,21 @@ __global__ void __launch_bounds__(256) router_q_kernel(const T* __restrict__ x, 
     float acc[EM];
 #pragma unroll
     for (int e = 0; e < EM; ++e) acc[e] = 0.f;
-    for (int j = 0; j < ns; ++j) {
-        const float xh = (ab_to_float(x[(size_t)(s0 + j) * Dm + d]) - sst[2 * j]) * sst[2 * j + 1];
+    // 8 rows in flight per thread: the loop is a stream of independent, coalesced loads, not a dependent chain
+    for (int j0 = 0; j0 < ns; j0 += 8) {
+        float xv[8];
 #pragma unroll
-        for (int e = 0; e < EM; ++e)
-            if (e < E) acc[e] = fmaf(sdl[j * E + e], xh, acc[e]);
+        for (int u = 0; u < 8; ++u) xv[u] = j0 + u < ns ? ab_to_float(x[(size_t)(s0 + j0 + u) * Dm + d]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            if (j < ns) {
+                const float xh = (xv[u] - sst[2 * j]) * sst[2 * j + 1];
+#pragma unroll
+                for (int e = 0; e < EM; ++e)
+                    if (e < E) acc[e] = fmaf(sdl[j * E + e], xh, acc[e]);
+            }
+        }
     }
 #pragma unroll
     for (int e = 0; e < EM; ++e)
