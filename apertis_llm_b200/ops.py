@@ -724,6 +724,19 @@ def _u8(n, dev):
     return torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev)
 
 
+_side_streams = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that is off the critical path of the MoE (weight casts while the router
+    and the plan run, bias column sums beside the gradient GEMMs).  Fork / join by stream waits: capturable in CUDA graphs."""
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[device.index] = st
+    return st
+
+
 def moe_route(x2, ln_w, ln_b, eps, Wr, br, noise, noise_scale, K, quant=_lib.ROUTER_EXACT):
     """Router forward (no autograd).  Returns dict of routing tensors."""
     S, Dm = x2.shape
@@ -814,6 +827,14 @@ def grouped_gemm_tn(A, Bm, seg_off, M, N, E, nsrc=1, src_stride=0):
     return out
 
 
+def _colsum_side(side, main, a, plan, out, ws, C, E, max_rows, dev):
+    """Column sums of `a` per expert segment on the side stream, after everything queued on the main stream so far."""
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        call("ab_moe_segment_colsum", ptr(a), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(out), ptr(ws), ws.numel(), C, E,
+             ROW_ALIGN, max_rows, dt(a), stream_ptr(dev))
+
+
 class _MoEExperts(torch.autograd.Function):
     """Whole AdaptiveExpertSystem.forward as one autograd node.
 
@@ -835,6 +856,16 @@ class _MoEExperts(torch.autograd.Function):
         rn_w, rn_b, Wr, br, ln_w, ln_b, b1, b2 = map(f, (rn_w, rn_b, Wr, br, ln_w, ln_b, b1, b2))
         W1, W2 = f(W1), f(W2)
         use_noise = noise is not None and noise_scale is not None
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        w1 = w2 = None
+        if not precise:
+            # the bf16 shadows of the expert weights do not depend on the routing: cast them beside the router and the plan
+            # (those are latency-bound kernels on a few SMs); buffers come from the main stream's pool
+            w1, w2 = torch.empty(W1.shape, dtype=torch.bfloat16, device=dev), torch.empty(W2.shape, dtype=torch.bfloat16, device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                call("ab_cast_f32_to_bf16", ptr(W1), ptr(w1), W1.numel(), stream_ptr(dev))
+                call("ab_cast_f32_to_bf16", ptr(W2), ptr(w2), W2.numel(), stream_ptr(dev))
         r = moe_route(x2, rn_w, rn_b, cfg["eps"], Wr, br, f(noise) if use_noise else None,
                       f(noise_scale) if use_noise else None, K, cfg.get("quant", _lib.ROUTER_EXACT))
         plan = moe_plan(r["idx"], r["w"], E, cfg["cap"], cfg["active"])
@@ -849,7 +880,8 @@ class _MoEExperts(torch.autograd.Function):
             w1 = _split_cols(W1.view(E * I, Dm), 1)
             k1 = 3 * Dm
         else:
-            a1, w1, k1 = xn, _cast_bf16(W1), Dm
+            a1, k1 = xn, Dm
+            main.wait_stream(side)
         drop_p = float(cfg.get("drop_p", 0.0)) if training else 0.0
         drop_seed = None
         if drop_p > 0.0:      # seed from torch's CUDA generator (restored by torch.utils.checkpoint on recompute), kept on device
@@ -861,7 +893,7 @@ class _MoEExperts(torch.autograd.Function):
             w2 = _split_cols(W2.view(E * Dm, I), 1)
             k2 = 3 * I
         else:
-            a2, w2, k2 = h, _cast_bf16(W2), I
+            a2, k2 = h, I
         y = grouped_gemm("nt", a2, w2, plan, Dm, k2, E, bias=b2, epi=_lib.EPI_BIAS, out_dtype=cdt)
         # ---- combine (core.py:605) + the caller's output dropout and residual add (core.py:918-919) when it hands them in
         out_p = float(cfg.get("out_drop_p", 0.0)) if training else 0.0
@@ -907,11 +939,23 @@ class _MoEExperts(torch.autograd.Function):
         call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
              ptr(dy), ptr(dw_row), cfg["out_p"], ptr(ctx.out_seed), K, Dm, max_rows, dt(dout), dt(y), dt(cdt), stream_ptr())
         seg = plan["seg_off"]
+        # bias gradients (column sums of dY and dHpre over each expert's rows) run beside the gradient GEMMs on the side
+        # stream: small CTAs that fit next to the GEMM's one CTA per SM; joined before the node returns
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        db2 = torch.empty(E, Dm, **f32)
+        db1 = torch.empty(E, I, **f32)
+        ws_b2 = _u8(query("ab_moe_segment_colsum_workspace_bytes", Dm, ROW_ALIGN, max_rows), dev)
+        ws_b1 = _u8(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, max_rows), dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            call("ab_moe_segment_colsum", ptr(dy), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(db2), ptr(ws_b2), ws_b2.numel(), Dm, E,
+                 ROW_ALIGN, max_rows, dt(dy), stream_ptr(dev))
         if precise:
             seg3 = (seg * 3).contiguous()
             w2r = _split_rows(W2.view(E * Dm, I), 1, None, E, Dm)                 # [E, 3*Dm, I]
             dhpre = grouped_gemm("nn", _split_cols(dy, 0), w2r, plan, I, 3 * Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                  drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
+            _colsum_side(side, main, dhpre, plan, db1, ws_b1, I, E, max_rows, dev)
             dW2 = grouped_gemm_tn(_split_rows(dy, 0, seg, E), _split_rows(h, 1, seg, E), seg3, Dm, I, E)
             dW1 = grouped_gemm_tn(_split_rows(dhpre, 0, seg, E), _split_rows(xn, 1, seg, E), seg3, I, Dm, E)
             w1r = _split_rows(W1.view(E * I, Dm), 1, None, E, I)                  # [E, 3*I, Dm]
@@ -920,20 +964,11 @@ class _MoEExperts(torch.autograd.Function):
             w1b, w2b = ctx.shadows
             dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                  drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
+            _colsum_side(side, main, dhpre, plan, db1, ws_b1, I, E, max_rows, dev)
             dW2 = grouped_gemm_tn(dy, h, seg, Dm, I, E)
             dW1 = grouped_gemm_tn(dhpre, xn, seg, I, Dm, E)
             dxn = grouped_gemm("nn", dhpre, w1b, plan, Dm, I, E, out_dtype=torch.bfloat16)    # bf16 like the reference's autocast Linear backward
-        # ---- bias grads
-        db2 = torch.empty(E, Dm, **f32)
-        db1 = torch.empty(E, I, **f32)
-        nws = max(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, max_rows),
-                  query("ab_moe_segment_colsum_workspace_bytes", Dm, ROW_ALIGN, max_rows),
-                  query("ab_moe_permute_ln_bwd_workspace_bytes", Dm, ROW_ALIGN, max_rows))
-        ws = _u8(nws, dev)
-        call("ab_moe_segment_colsum", ptr(dy), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(db2), ptr(ws), ws.numel(), Dm, E,
-             ROW_ALIGN, max_rows, dt(dy), stream_ptr())
-        call("ab_moe_segment_colsum", ptr(dhpre), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(db1), ptr(ws), ws.numel(), I, E,
-             ROW_ALIGN, max_rows, dt(dhpre), stream_ptr())
+        ws = _u8(query("ab_moe_permute_ln_bwd_workspace_bytes", Dm, ROW_ALIGN, max_rows), dev)
         # ---- per-expert LayerNorm backward on the permuted rows
         dxrow = torch.empty(max_rows, Dm, **f32)
         dln_w = torch.empty(E, Dm, **f32)
@@ -958,6 +993,7 @@ class _MoEExperts(torch.autograd.Function):
              ptr(dxrow), ptr(plan["row_of"]), ptr(dx), ptr(dWr), ptr(dbr), ptr(drn_w), ptr(drn_b), ptr(dns), ptr(ws2), ws2.numel(),
              S, Dm, E, K, dt(x2), stream_ptr())
         dres = dout.reshape(cfg["res_shape"]).to(cfg["res_dtype"]) if cfg["has_res"] else None       # the residual passes the gradient on
+        main.wait_stream(side)                                       # bias gradients
         return (dx, drn_w, drn_b, dWr, dbr, None, dns, dln_w, dln_b, dW1, db1, dW2, db2, dres, None)
 
 
