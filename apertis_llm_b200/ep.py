@@ -337,13 +337,12 @@ class _MoEExpertsEP(torch.autograd.Function):
             dyr = all_to_all_equal(dy.view(W, El * seg, Dm), group).view(rows, Dm)
         lseg = rplan["seg_off"]
         stride = El * seg
-        # bias gradients (column sums over each local expert's rows) beside the gradient GEMMs, on the auxiliary stream
+        # bias gradients (column sums over each local expert's rows) on the auxiliary stream, launched after the GEMMs
         cmain, cside = torch.cuda.current_stream(dev), ops._side_stream(dev)
         db2 = torch.empty(El, Dm, **f32)
         db1 = torch.empty(El, I, **f32)
         ws_b2 = ops._u8(query("ab_moe_segment_colsum_workspace_bytes", Dm, ROW_ALIGN, rows), dev)
         ws_b1 = ops._u8(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, rows), dev)
-        ops._colsum_side(cside, cmain, dyr, rplan, db2, ws_b2, Dm, El, rows, dev)
         if precise:
             # row-stacked splits: every (source, local expert) block of `seg` rows is one group
             G = W * El
@@ -353,7 +352,6 @@ class _MoEExpertsEP(torch.autograd.Function):
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
             sr = lambda t, which: ops._split_rows(t, which, None, G, seg)
             w1r = ops._split_rows(W1.view(El * I, Dm), 1, None, El, I)
-            ops._colsum_side(cside, cmain, dhpre, rplan, db1, ws_b1, I, El, rows, dev)
             dxnr = ops.grouped_gemm("nn", ops._split_cols(dhpre, 0), w1r, rplan, Dm, 3 * I, El, out_dtype=torch.float32)
             # the gradient rows travel back to their source ranks while the weight gradients are computed
             dxn_w, dxn_wait = all_to_all_equal_start(dxnr.view(W, El * seg, Dm), group)
@@ -363,7 +361,6 @@ class _MoEExpertsEP(torch.autograd.Function):
             w1b, w2b = ctx.shadows
             dhpre = ops.grouped_gemm("nn", dyr, w2b, rplan, I, Dm, El, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                      drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
-            ops._colsum_side(cside, cmain, dhpre, rplan, db1, ws_b1, I, El, rows, dev)
             if peer is not None:
                 # the input-gradient GEMM's epilogue stores every row into its source rank's buffer; the barrier that
                 # completes the exchange waits on a side stream while the weight gradients are computed
@@ -380,6 +377,9 @@ class _MoEExpertsEP(torch.autograd.Function):
                 dxn_w, dxn_wait = all_to_all_equal_start(dxnr.view(W, El * seg, Dm), group)
             dW2 = ops.grouped_gemm_tn(dyr, h, lseg, Dm, I, El, nsrc=W, src_stride=stride)
             dW1 = ops.grouped_gemm_tn(dhpre, xr, lseg, I, Dm, El, nsrc=W, src_stride=stride)
+        # after the GEMMs (which fill every SM): the column sums run beside the latency-bound tail of the node
+        ops._colsum_side(cside, cmain, dyr, rplan, db2, ws_b2, Dm, El, rows, dev)
+        ops._colsum_side(cside, cmain, dhpre, rplan, db1, ws_b1, I, El, rows, dev)
         ws = ops._u8(query("ab_moe_permute_ln_bwd_workspace_bytes", Dm, ROW_ALIGN, rows), dev)
         # ---- gradient rows are back on their source ranks
         dxn_wait()

@@ -939,23 +939,18 @@ class _MoEExperts(torch.autograd.Function):
         call("ab_moe_unpermute_bwd", ptr(dout), ptr(y), ptr(w), ptr(plan["tok_of_row"]), ptr(plan["slot_of_row"]), ptr(plan["n_rows"]),
              ptr(dy), ptr(dw_row), cfg["out_p"], ptr(ctx.out_seed), K, Dm, max_rows, dt(dout), dt(y), dt(cdt), stream_ptr())
         seg = plan["seg_off"]
-        # bias gradients (column sums of dY and dHpre over each expert's rows) run beside the gradient GEMMs on the side
-        # stream: small CTAs that fit next to the GEMM's one CTA per SM; joined before the node returns
+        # bias gradients (column sums of dY and dHpre over each expert's rows) run on the side stream beside the
+        # latency-bound tail of this node (expert-LayerNorm backward, router backward); joined before the node returns
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         db2 = torch.empty(E, Dm, **f32)
         db1 = torch.empty(E, I, **f32)
         ws_b2 = _u8(query("ab_moe_segment_colsum_workspace_bytes", Dm, ROW_ALIGN, max_rows), dev)
         ws_b1 = _u8(query("ab_moe_segment_colsum_workspace_bytes", I, ROW_ALIGN, max_rows), dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            call("ab_moe_segment_colsum", ptr(dy), ptr(plan["tile_expert"]), ptr(plan["n_rows"]), ptr(db2), ptr(ws_b2), ws_b2.numel(), Dm, E,
-                 ROW_ALIGN, max_rows, dt(dy), stream_ptr(dev))
         if precise:
             seg3 = (seg * 3).contiguous()
             w2r = _split_rows(W2.view(E * Dm, I), 1, None, E, Dm)                 # [E, 3*Dm, I]
             dhpre = grouped_gemm("nn", _split_cols(dy, 0), w2r, plan, I, 3 * Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                  drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
-            _colsum_side(side, main, dhpre, plan, db1, ws_b1, I, E, max_rows, dev)
             dW2 = grouped_gemm_tn(_split_rows(dy, 0, seg, E), _split_rows(h, 1, seg, E), seg3, Dm, I, E)
             dW1 = grouped_gemm_tn(_split_rows(dhpre, 0, seg, E), _split_rows(xn, 1, seg, E), seg3, I, Dm, E)
             w1r = _split_rows(W1.view(E * I, Dm), 1, None, E, I)                  # [E, 3*I, Dm]
@@ -964,10 +959,12 @@ class _MoEExperts(torch.autograd.Function):
             w1b, w2b = ctx.shadows
             dhpre = grouped_gemm("nn", dy, w2b, plan, I, Dm, E, aux=hpre, epi=_lib.EPI_DACT, act=act, out_dtype=cdt,
                                  drop_p=cfg["drop_p"], drop_seed=ctx.drop_seed)
-            _colsum_side(side, main, dhpre, plan, db1, ws_b1, I, E, max_rows, dev)
             dW2 = grouped_gemm_tn(dy, h, seg, Dm, I, E)
             dW1 = grouped_gemm_tn(dhpre, xn, seg, I, Dm, E)
             dxn = grouped_gemm("nn", dhpre, w1b, plan, Dm, I, E, out_dtype=torch.bfloat16)    # bf16 like the reference's autocast Linear backward
+        # after the GEMMs (which fill every SM) come two latency-bound kernels: that is where the column sums run beside
+        _colsum_side(side, main, dy, plan, db2, ws_b2, Dm, E, max_rows, dev)
+        _colsum_side(side, main, dhpre, plan, db1, ws_b1, I, E, max_rows, dev)
         ws = _u8(query("ab_moe_permute_ln_bwd_workspace_bytes", Dm, ROW_ALIGN, max_rows), dev)
         # ---- per-expert LayerNorm backward on the permuted rows
         dxrow = torch.empty(max_rows, Dm, **f32)
