@@ -134,6 +134,21 @@ class _PeerState:
 
 
 _uniform_checked = set()
+_recv_plans = {}
+
+
+def _recv_plan(W: int, El: int, seg: int, device):
+    """The owner-side plan of the received layout (static for a given world size, local expert count and segment size):
+    built once, not by a handful of tiny kernels every step."""
+    key = (W, El, seg, device.index)
+    p = _recv_plans.get(key)
+    if p is None:
+        p = dict(tile_expert=recv_tile_expert(W, El, seg, device),
+                 n_rows=torch.full((2,), W * El * seg, dtype=torch.int32, device=device),
+                 seg_off=local_seg_off(El, seg, device))
+        if not torch.cuda.is_current_stream_capturing():
+            _recv_plans[key] = p
+    return p
 
 
 def _check_uniform(group, S: int, cap: int, training: bool, device):
@@ -229,9 +244,7 @@ class _MoEExpertsEP(torch.autograd.Function):
         cdt = torch.float32 if precise else torch.bfloat16
         peer = None if precise else _peer_state(group, rows_local, Dm, dev, cfg.get("_owner", 0))
         rank = dist.get_rank(group)
-        rplan = dict(tile_expert=recv_tile_expert(W, El, seg, dev),
-                     n_rows=torch.full((2,), rows_local, dtype=torch.int32, device=dev),
-                     seg_off=local_seg_off(El, seg, dev))
+        rplan = _recv_plan(W, El, seg, dev)
         if peer is not None:
             # ---- dispatch fused into permute + LayerNorm: every row goes straight into its owner's receive buffer
             peer.version += 1

@@ -267,8 +267,14 @@ class AdaptiveExpertSystem(nn.Module):
             keys = [f"{prefix}experts.{base + e}.{suffix}" for e in range(self.local_experts)]
             if all(k in state_dict for k in keys):
                 state_dict[prefix + name] = torch.stack([state_dict[k] for k in keys])
-        for k in [k for k in state_dict if k.startswith(prefix + "experts.")]:      # other ranks' experts under EP
-            del state_dict[k]
+        # the per-expert keys have been folded into the stacked tensors (or belong to other ranks' experts under EP): remove
+        # exactly those - a well-formed key of an expert in [0, num_experts) - and leave anything else under "experts." in
+        # place, so that malformed or out-of-range keys still surface as unexpected keys with strict=True
+        known = set(self._STACKED.values())
+        for k in [k for k in state_dict if k.startswith(prefix + "experts.")]:
+            parts = k[len(prefix) + len("experts."):].split(".", 1)
+            if len(parts) == 2 and parts[0].isdigit() and int(parts[0]) < self.num_experts and parts[1] in known:
+                del state_dict[k]
 
     # ---- hooks the parity tests use to feed both sides the same random numbers ----
     def _draw_noise(self, S: int, E: int, device) -> torch.Tensor:

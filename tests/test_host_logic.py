@@ -47,3 +47,28 @@ def test_config_derivations():
     assert cfg.ssm_d_inner == 176 and cfg.ssm_dt_rank == 44
     m = SelectiveLinearAttention(cfg)
     assert m.x_param_proj.weight.shape == (44 + 2 * 176, 176) and m.A_log.shape == (11, 16)
+
+
+def test_state_dict_rejects_malformed_expert_keys():
+    """Reference checkpoints load with strict=True; a key under 'experts.' that is not a well-formed key of an existing
+    expert is reported as unexpected instead of being dropped silently."""
+    cfg = BlockConfig(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_experts=4)
+    m = AdaptiveExpertSystem(cfg)
+    sd = m.state_dict()
+    assert "experts.3.4.bias" in sd and not any(k.startswith("expert_") for k in sd)      # reference key names only
+    AdaptiveExpertSystem(cfg).load_state_dict(sd, strict=True)
+    for bad in ("experts.7.1.weight", "experts.1.9.weight", "experts.x.1.weight"):
+        sd2 = dict(sd)
+        sd2[bad] = torch.zeros(1)
+        with pytest.raises(RuntimeError, match="Unexpected key"):
+            AdaptiveExpertSystem(cfg).load_state_dict(sd2, strict=True)
+
+
+def test_kernel_limits_are_checked_at_construction():
+    with pytest.raises(ValueError, match="num_experts <= 32"):
+        AdaptiveExpertSystem(BlockConfig(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_experts=40))
+    with pytest.raises(ValueError, match="multiples of 8"):
+        AdaptiveExpertSystem(BlockConfig(hidden_size=60, num_attention_heads=2, intermediate_size=128, num_experts=4))
+    from apertis_llm_b200 import ApertisLayerB200
+    with pytest.raises(NotImplementedError, match="use_rmsnorm"):
+        ApertisLayerB200(BlockConfig(hidden_size=64, num_attention_heads=2, intermediate_size=128, num_experts=4, use_rmsnorm=True))
