@@ -507,14 +507,26 @@ __global__ void __launch_bounds__(256, NIT <= 6 ? 3 : 2) permute_ln_bwd_fused_ke
 #pragma unroll
         for (int v = 0; v < 4; ++v) { gw[it][v] = 0.f; gb[it][v] = 0.f; }
     }
+    // The loads of a row are issued piecewise (register budget), each piece a full memory latency when it misses: the
+    // NEXT row of this warp (token id looked up two rows ahead) is therefore prefetched into L1 while this one is processed.
+    int tok_cur = tok_of_row[t * align + warp];
+    int tok_nxt = warp + wpb < align ? tok_of_row[t * align + warp + wpb] : -1;
     for (int i = warp; i < align; i += wpb) {
         const int r = t * align + i;
-        const int tok = tok_of_row[r];
+        const int tok = tok_cur;
+        tok_cur = tok_nxt;
+        tok_nxt = i + 2 * wpb < align ? tok_of_row[t * align + i + 2 * wpb] : -1;
+        if (tok_cur >= 0) {
+            const char* px = reinterpret_cast<const char*>(x + (size_t)tok_cur * Dm);
+            const char* pg = reinterpret_cast<const char*>(dxn + (size_t)(r + wpb) * Dm);
+            for (int o = lane * 128; o < Dm * (int)sizeof(TX); o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(px + o));
+            for (int o = lane * 128; o < Dm * (int)sizeof(TG); o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pg + o));
+        }
         if (tok < 0) continue;
         const float mean = stats[2 * (size_t)tok], rstd = stats[2 * (size_t)tok + 1];
         const TX* xr = x + (size_t)tok * Dm;
         const TG* gr = dxn + (size_t)r * Dm;
-        // pass 1: column partials and the two row sums (the row is read again in pass 2 from L1 / L2: keeping it in
+        // pass 1: column partials and the two row sums (the row is read again in pass 2 from L1: keeping it in
         // registers would halve the resident warps)
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll
