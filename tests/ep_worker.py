@@ -132,6 +132,21 @@ def run_gpu(rank, world, args):
         bad = {k: v for k, v in errs.items() if not v < tol}
         assert not bad, (rank, autocast, bad)
         worst = max(worst, max(errs.values()))
+        # activation checkpointing around the EP layer (the reference trainer's default, core.py:1258-1272): the
+        # recomputation rewrites the peer-mapped buffers before the backward reads them; gradients must not move beyond
+        # the run-to-run reduction-order noise of a different call sequence (measured on one GPU without EP,
+        # tools/ckpt_check.py: 8e-6 in fp32, 6e-3 under bf16 on the SSM parameters) - a stale buffer would be O(1)
+        from torch.utils.checkpoint import checkpoint
+        g_plain = {n: p.grad.clone() for n, p in le.named_parameters()}
+        for p in le.parameters():
+            p.grad = None
+        xc = x.to(dev).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out_c, lb_c, rz_c = checkpoint(lambda t: tuple(le(t)[i] for i in (0, 3, 4)), xc, use_reentrant=False)
+        O.block_loss(out_c, lb_c, rz_c).backward()
+        assert rel(xc.grad, dx_e) < tol, (rank, autocast, "checkpoint dx", rel(xc.grad, dx_e))
+        for n, p in le.named_parameters():
+            assert rel(p.grad, g_plain[n]) < tol, (rank, autocast, "checkpoint", n, rel(p.grad, g_plain[n]))
         # evaluation: no capacity limit, the exchange segments are sized from the counts reduced over the ranks
         lr.eval(); le.eval()
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
