@@ -118,7 +118,7 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, __nv_bfloat16*
 
 }  // namespace
 
-extern "C" int ab_version(void) { return 100; }
+extern "C" int ab_version(void) { return 200; }      // 2xx: round-2 ABI (256-row GEMM tile, ab_ep_*, ab_shifted_ce_*, wgrad workspace)
 
 extern "C" int ab_device_check(int device) {
     cudaDeviceProp prop;

@@ -52,3 +52,22 @@ def test_patched_model_refuses_to_run_on_cpu():
     model = ab.patch_apertis_model(_ref_model())
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         model(input_ids=torch.randint(0, 97, (1, 8)))
+
+
+def test_fuse_lm_head_installs_the_reference_shaped_forward():
+    """patch_apertis_model(fuse_lm_head=True) binds a forward with the reference's argument list on the instance; the state
+    dict (tied embeddings included) is untouched, and on a CPU model the fused path still refuses to run."""
+    import inspect
+    import apertis_llm_b200 as ab
+    from apertis_llm_b200 import modules
+    model = _ref_model()
+    keys = list(model.state_dict().keys())
+    ref_params = list(inspect.signature(type(model).forward).parameters)[1:]
+    ab.patch_apertis_model(model, fuse_lm_head=True)
+    assert model.forward.__func__ is modules._causal_lm_forward
+    assert list(inspect.signature(model.forward).parameters) == ref_params
+    assert list(model.state_dict().keys()) == keys
+    assert model.lm_head.weight is model.model.token_embeddings.weight        # still tied
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        ids = torch.randint(0, 97, (1, 8))
+        model(input_ids=ids, labels=ids)
