@@ -34,9 +34,8 @@ def _on_tensor_device(fn):
 # workspaces
 # --------------------------------------------------------------------------------------------
 _scan_ws = {}       # (device index, stream, pipelined?) -> [tensor, epoch]
-# APERTIS_B200_SCAN = auto (default) | pipelined | single | two_pass.  auto: the pipelined persistent schedule when the
-# inner width is a multiple of 64 channels and the sequence has at least 1024 tokens (one warp column per slab: its measured win, see
-# profiles/r1j_scan_*), the one-tile-per-CTA single pass otherwise.
+# APERTIS_B200_SCAN = auto (default) | rounds | pipelined | single | two_pass.  auto = the "rounds" schedule
+# (csrc/ssm_scan_rounds.cu, every shape); the other values select the older schedules of csrc/ssm_scan*.cu.
 _SCAN_ENV = os.environ.get("APERTIS_B200_SCAN", "auto")
 SCAN_MODE = {"two_pass": _lib.SCAN_TWO_PASS, "single": _lib.SCAN_SINGLE_PASS, "pipelined": _lib.SCAN_PIPELINED,
              "rounds": _lib.SCAN_ROUNDS}.get(_SCAN_ENV)
